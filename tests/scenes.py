@@ -1,0 +1,67 @@
+"""Seeded synthetic scenes shared by the oracle tests (CPU) and the CUDA parity tests (GPU)."""
+import numpy as np
+
+
+def sphere_table(radius=0.08, dx=0.01, margin=0.05):
+    """Analytic SDF / normal table of a sphere centred at the primitive origin, in the on-disk layout of
+    softmac/engine/primitive/mesh.py:235-241 (sdf[res], normal[res,3], position=(lower, upper), dx)."""
+    half = radius + margin
+    res = int(np.ceil(2 * half / dx)) + 1
+    lower = -np.ones(3) * (res - 1) * dx / 2
+    upper = lower + (res - 1) * dx
+    ax = lower[0] + np.arange(res) * dx
+    P = np.stack(np.meshgrid(ax, ax, ax, indexing="ij"), -1)
+    r = np.linalg.norm(P, axis=-1)
+    sdf = r - radius
+    normal = P / np.maximum(r, 1e-9)[..., None]
+    normal[r < 1e-9] = (0, 1, 0)
+    return dict(sdf=sdf, normal=normal, lower=lower, upper=upper, dx=dx)
+
+
+def box_table(half=(0.10, 0.04, 0.10), dx=0.01, margin=0.04):
+    """Exact box SDF with nearest-face normals (piecewise constant, like the shipped tables)."""
+    half = np.asarray(half, float)
+    res = (np.ceil(2 * (half + margin) / dx)).astype(int) + 1
+    lower = -(res - 1) * dx / 2
+    upper = lower + (res - 1) * dx
+    axs = [lower[i] + np.arange(res[i]) * dx for i in range(3)]
+    P = np.stack(np.meshgrid(*axs, indexing="ij"), -1)
+    q = np.abs(P) - half
+    outside = np.linalg.norm(np.maximum(q, 0), axis=-1)
+    inside = np.minimum(q.max(-1), 0)
+    sdf = outside + inside
+    k = q.argmax(-1)
+    normal = np.zeros_like(P)
+    idx = np.indices(k.shape)
+    normal[idx[0], idx[1], idx[2], k] = np.sign(P[idx[0], idx[1], idx[2], k]) + (P[idx[0], idx[1], idx[2], k] == 0)
+    return dict(sdf=sdf, normal=normal, lower=lower, upper=upper, dx=dx)
+
+
+def random_quat(rng, spread=0.3):
+    q = np.array([1.0, 0, 0, 0]) + spread * rng.normal(size=4)
+    return q / np.linalg.norm(q)
+
+
+def blob_state(n, rng, center=(0.5, 0.3, 0.5), width=0.12, vel=0.5, Fdev=0.02, Cdev=2.0, fp32=True):
+    """(n,24) state [x v F C]: a random cloud with non-trivial v, F, C."""
+    x = (rng.random((n, 3)) * 2 - 1) * 0.5 * width + np.asarray(center)
+    v = vel * rng.normal(size=(n, 3))
+    F = np.eye(3)[None] + Fdev * rng.normal(size=(n, 3, 3))
+    Cm = Cdev * rng.normal(size=(n, 3, 3))
+    st = np.hstack([x, v, F.reshape(n, 9), Cm.reshape(n, 9)])
+    if fp32:
+        st = st.astype(np.float32).astype(np.float64)
+    return st
+
+
+def cube_state(n, seed=0, init_pos=(0.5, 0.30, 0.5), width=0.390625):
+    """The reference generator Shapes.add_box (softmac/engine/shapes/shape_maker.py:51-60) with
+    np.random.seed(0): x uniform in the box, v = 0, F = I, C = 0."""
+    state = np.random.get_state()
+    np.random.seed(seed)
+    p = (np.random.random((n, 3)) * 2 - 1) * (0.5 * np.array([width] * 3)) + np.array(init_pos)
+    np.random.set_state(state)
+    st = np.zeros((n, 24))
+    st[:, :3] = p
+    st[:, 6] = st[:, 10] = st[:, 14] = 1.0
+    return st.astype(np.float32).astype(np.float64)
