@@ -1,0 +1,180 @@
+/*
+ * softmac_b200.h -- C ABI of libsoftmac_b200.so: a B200-native (sm_100a) implementation of SoftMAC's
+ * differentiable MLS-MPM substep loop, forward and adjoint, and of the rigid-primitive coupling
+ * interface (contact wrench out, primitive pose/twist in, and the adjoints of both).
+ *
+ * The reference (damianliumin/SoftMAC) has no FFI: its boundary is the duck-typed Python surface of
+ * `MPMSimulator` (softmac/engine/mpm_simulator.py:16-618) and `Primitive`
+ * (softmac/engine/primitive/primitive_base.py:8-335) as consumed by `TaichiEnv`
+ * (softmac/engine/taichi_env.py:93-151) and `RigidSimulator` (softmac/engine/rigid_simulator.py:85-220).
+ * Each entry point below names the reference method it replaces.  The Python mirror of that surface
+ * (softmac_b200/engine/*.py) binds exactly these symbols through ctypes; see INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative smx_status; the message of the last failure
+ *     on the calling thread is available from smx_last_error().
+ *   - pointers are HOST pointers unless the name ends in _dev.  Host arrays are borrowed for the
+ *     duration of the call.  Particle arrays are in PARTICLE-ID order (the order of the array passed
+ *     to smx_reset), float64, row-major: x,v (n,3); F,C (n,3,3); state (n,24) = [x v F C] -- the
+ *     layout of MPMSimulator.get_state (mpm_simulator.py:481-489).  Device storage is fp32, SoA,
+ *     physically sorted by grid cell; the library maps between the two.
+ *   - one smx_sim <-> one CUDA device and one stream.  Calls on one handle are not thread-safe;
+ *     different handles may be driven from different threads/processes.  Kernels are launched
+ *     asynchronously; only the smx_get_* calls, smx_synchronize and smx_timer_stop block.
+ *   - frame f of the particle state is the input of substep f, frame f+1 its output
+ *     (taichi_env.py:94-95).  Primitive frame f is what substep f collides against.
+ */
+#ifndef SOFTMAC_B200_H
+#define SOFTMAC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct smx_sim smx_sim;
+
+typedef enum {
+    SMX_OK = 0,
+    SMX_ERR_ARG = -1,      /* bad argument / null pointer */
+    SMX_ERR_RANGE = -2,    /* frame / primitive / controller index out of range */
+    SMX_ERR_CUDA = -3,     /* CUDA runtime error (message carries cudaGetErrorString) */
+    SMX_ERR_STATE = -4,    /* call sequence not valid (e.g. adjoint of a frame that was never computed) */
+    SMX_ERR_NOMEM = -5,
+    SMX_ERR_DOMAIN = -6    /* particles left the active region / the grid (see smx_get_counters) */
+} smx_status;
+
+/* MPMSimulator.__init__(cfg, primitives, env_dt, rigid_velocity_control) -- mpm_simulator.py:17-84.
+ * Field names follow cfg.SIMULATOR (softmac/config/default_config.py:14-29). */
+typedef struct {
+    int32_t n_particles;
+    int32_t n_grid;               /* int(128 * quality * 0.5); must be a multiple of 4 */
+    int32_t max_steps;            /* number of particle / primitive frames kept in HBM */
+    double dt;
+    double E, nu;                 /* Lame parameters derived as in mpm_simulator.py:41-45 */
+    double gravity[3];
+    double ground_friction;       /* >= 10 -> sticky floor (mpm_simulator.py:278) */
+    int32_t material_model;       /* 0 co-rotated, 1 neo-Hookean */
+    int32_t ptype;                /* 0 plastic, 1 elastic, 2 liquid */
+    int32_t collision_type;       /* 0 grid, 1 particle, 2 mixed (forecast) */
+    int32_t substeps;             /* int(env_dt / dt): period of `life` in grid_op_mixed3 (:425) */
+    int32_t n_control;            /* cfg.n_controllers */
+    int32_t rigid_velocity_control;
+    int32_t sort_every;           /* re-bin + re-sort particles every this many substeps (0: only at reset) */
+    int32_t device;               /* CUDA device ordinal */
+    int32_t flags;                /* SMX_FLAG_* */
+    void* stream;                 /* cudaStream_t to run on; NULL -> the library creates its own */
+} smx_config;
+
+#define SMX_FLAG_DENSE_GRID 1     /* sweep the whole grid every substep instead of the active-block list */
+#define SMX_FLAG_NO_SORT 2        /* keep particles in id order (debug / ablation) */
+
+/* lifetime ------------------------------------------------------------------------------------- */
+int smx_create(const smx_config* cfg, smx_sim** out);
+int smx_destroy(smx_sim* sim);
+const char* smx_last_error(void);
+int smx_synchronize(smx_sim* sim);
+
+/* primitives: Mesh(...) construction -- softmac/engine/primitive/mesh.py:26-43.  sdf is the
+ * (r0,r1,r2) table, normal the (r0,r1,r2,3) table, lower/upper = sdf["position"], sdf_dx = sdf["dx"][0].
+ * sdf == NULL registers a primitive without geometry (never in contact).  Returns the primitive id. */
+int smx_add_primitive(smx_sim* sim, const double* sdf, const double* normal, const int32_t res[3], const double lower[3],
+                      const double upper[3], double sdf_dx, double friction, double softness, int32_t contact_enabled);
+/* Primitive.friction / softness fields (primitive_base.py:26-27, primitives.py:43-45) */
+int smx_set_primitive_params(smx_sim* sim, int32_t id, double friction, double softness);
+/* MPMSimulator.primitives_contact[id] = flag (mpm_simulator.py:70, demo_grip.py:117) */
+int smx_set_primitive_contact(smx_sim* sim, int32_t id, int32_t enabled);
+
+/* particle state IO ---------------------------------------------------------------------------- */
+/* MPMSimulator.reset(x): ncols == 3 -> v=0, F=I, C=0; ncols == 24 -> full state (mpm_simulator.py:494-519) */
+int smx_reset(smx_sim* sim, const double* state, int32_t ncols);
+/* MPMSimulator.set_state(f, [x, v, F, C]) / setframe (mpm_simulator.py:458-466, 491-492) */
+int smx_set_frame(smx_sim* sim, int32_t f, const double* x, const double* v, const double* F, const double* C);
+/* MPMSimulator.get_state(f) -> (n,24) (mpm_simulator.py:481-489) */
+int smx_get_state(smx_sim* sim, int32_t f, double* out24);
+/* get_x / set_x / get_v / set_v (mpm_simulator.py:521-559) */
+int smx_get_x(smx_sim* sim, int32_t f, double* x);
+int smx_set_x(smx_sim* sim, int32_t f, const double* x);
+int smx_get_v(smx_sim* sim, int32_t f, double* v);
+int smx_set_v(smx_sim* sim, int32_t f, const double* v);
+/* MPMSimulator.copyframe(source, target) incl. the primitives' `substeps` frames (mpm_simulator.py:468-479) */
+int smx_copy_frame(smx_sim* sim, int32_t src, int32_t dst);
+
+/* primitive state / coupling ------------------------------------------------------------------- */
+/* Primitive.set_all_states(f, state13) for f in [f0, f1) (primitive_base.py:258-260; the rigid bridge loops
+ * `substeps` such calls, rigid_simulator.py:200-201).  state13 = [x(3) q(4, w first) v(3) w(3)]. */
+int smx_set_primitive_state(smx_sim* sim, int32_t id, int32_t f0, int32_t f1, const double* s13);
+/* Primitive.get_state(f) (first 7) + v, w */
+int smx_get_primitive_state(smx_sim* sim, int32_t id, int32_t f, double* out13);
+/* sum over f in [f0, f1) of Primitive.get_all_states_grad(f) (primitive_base.py:262-265, rigid_simulator.py:207-208) */
+int smx_get_primitive_state_grad(smx_sim* sim, int32_t id, int32_t f0, int32_t f1, double* out13);
+/* loss seed on position/rotation/v/w.grad[f] (what Taichi losses write directly, e.g. loss_grip.py:70-87) */
+int smx_add_primitive_state_grad(smx_sim* sim, int32_t id, int32_t f, const double* g13);
+/* Primitive.ext_f.to_numpy() (rigid_simulator.py:92): [force(3), torque about the primitive origin(3)] */
+int smx_get_ext_f(smx_sim* sim, int32_t id, double* out6);
+/* Primitive.clear_ext_f(): zeroes value and adjoint (primitive_base.py:183-187) */
+int smx_clear_ext_f(smx_sim* sim, int32_t id);
+/* Primitive.set_ext_f_grad(g6) (primitive_base.py:189-192) */
+int smx_set_ext_f_grad(smx_sim* sim, int32_t id, const double* g6);
+/* velocity-control mode: Primitive.set_action(s, n, a6) / get_action_grad(s, n) (primitive_base.py:285-319) */
+int smx_set_primitive_action(smx_sim* sim, int32_t id, int32_t s, int32_t n, const double* a6);
+int smx_get_primitive_action_grad(smx_sim* sim, int32_t id, int32_t s, int32_t n, double* out6);
+
+/* particle-force control ("mpm" control mode) --------------------------------------------------- */
+/* MPMSimulator.set_action(action (n_control,3)); also zeroes action.grad (mpm_simulator.py:579-592) */
+int smx_set_action(smx_sim* sim, const double* action);
+/* MPMSimulator.set_control_idx(idx (n,) int, -1 = uncontrolled) (mpm_simulator.py:594-602) */
+int smx_set_control_idx(smx_sim* sim, const int32_t* idx);
+/* action.grad.to_numpy() after substep_grad (mpm_simulator.py:378) */
+int smx_get_action_grad(smx_sim* sim, double* out);
+
+/* the hot path ---------------------------------------------------------------------------------- */
+/* MPMSimulator.substep(s) (mpm_simulator.py:320-337): frame s -> frame s+1, accumulates ext_f */
+int smx_substep(smx_sim* sim, int32_t s);
+/* MPMSimulator.substep_grad(s) (mpm_simulator.py:339-378): consumes the adjoint of frame s+1 (+ its seeds),
+ * produces the adjoint of frame s (+ its seeds), accumulates primitive-state and action adjoints */
+int smx_substep_grad(smx_sim* sim, int32_t s);
+/* `count` substeps in one call: s0, s0+1, ... (TaichiEnv.step inner loop, taichi_env.py:101-102) */
+int smx_step(smx_sim* sim, int32_t s0, int32_t count);
+/* adjoint of substeps s1-1, s1-2, ..., s1-count (TaichiEnv.step_grad inner loop, taichi_env.py:128-131) */
+int smx_step_grad(smx_sim* sim, int32_t s1, int32_t count);
+
+/* adjoint seeds and read-out -------------------------------------------------------------------- */
+/* loss -> x.grad[f] (+ v, F, C .grad[f]): g24 is (n,24) in get_state layout; g3 is (n,3) */
+int smx_add_state_grad(smx_sim* sim, int32_t f, const double* g24);
+int smx_add_x_grad(smx_sim* sim, int32_t f, const double* g3);
+/* adjoint of frame f; only the frame most recently produced by smx_substep_grad is resident
+ * (no per-frame gradient arrays are kept) */
+int smx_get_state_grad(smx_sim* sim, int32_t f, double* out24);
+/* MPMSimulator.get_grad(f) -> (x.grad[f], v.grad[f]) (mpm_simulator.py:561-574) */
+int smx_get_grad(smx_sim* sim, int32_t f, double* xg, double* vg);
+/* ti.ad.clear_all_gradients() restricted to this path (demo_grip.py:135) */
+int smx_clear_grads(smx_sim* sim);
+
+/* introspection for tests, benches and zero-copy consumers -------------------------------------- */
+/* sort key of every particle of frame f in STORAGE order, and the storage permutation (slot -> particle id).
+ * Contract: perm == numpy.argsort(key_in_previous_order, kind="stable") composed over re-sorts. */
+int smx_get_sort_keys(smx_sim* sim, int32_t f, uint32_t* keys);
+int smx_get_permutation(smx_sim* sim, int32_t f, uint32_t* perm);
+/* dense (n_grid^3, 4) fp32 copies of the grid after the last substep: g_in = (momentum xyz, mass),
+ * g_out = (velocity xyz, active flag), in (i*n_grid + j)*n_grid + k order */
+int smx_get_grid(smx_sim* sim, float* g_in, float* g_out);
+/* counters[0] = particles clamped into the grid, [1] = particles that left the active-block region,
+ * [2] = number of re-sorts, [3] = active blocks of the current ordering */
+int smx_get_counters(smx_sim* sim, int64_t out[4]);
+/* device pointer of component c (0..23, get_state column order) of frame f in storage order (fp32, n floats) */
+int smx_frame_component_dev(smx_sim* sim, int32_t f, int32_t c, void** ptr_dev);
+/* CUDA-event timer on the simulator's stream */
+int smx_timer_start(smx_sim* sim);
+int smx_timer_stop(smx_sim* sim, float* ms);
+/* number of kernels this handle has launched since creation */
+int64_t smx_launch_count(smx_sim* sim);
+/* runs smx_substep (backward == 0) or smx_substep_grad (backward != 0) of substep f with a CUDA event after every
+ * launch and returns the per-kernel-class device time: names[i] (static strings), ms[i], i < *count (<= 32) */
+int smx_profile_substep(smx_sim* sim, int32_t f, int32_t backward, const char** names, float* ms, int32_t* count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SOFTMAC_B200_H */

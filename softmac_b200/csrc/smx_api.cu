@@ -1,0 +1,905 @@
+// smx_api.cu -- host side of libsoftmac_b200.so: the C ABI declared in include/softmac_b200.h.
+//
+// Owns all device memory (per-substep particle checkpoints, grid, SDF tables, primitive time series,
+// adjoint ping-pong buffers), the particle orderings produced by the periodic cell sort, and the
+// stream-ordered launch sequences of the forward substep (mpm_simulator.py:320-337) and of its adjoint
+// (mpm_simulator.py:339-378).  No CPU compute path exists here: without a CUDA device smx_create fails.
+#include <cuda_runtime.h>
+#include <cub/cub.cuh>
+#include <cstdio>
+#include <cstdarg>
+#include <cstring>
+#include <cmath>
+#include <vector>
+#include <map>
+#include <string>
+#include <algorithm>
+
+#include "../../include/softmac_b200.h"
+#include "smx_kernels.cuh"
+
+using namespace smx;
+
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap);
+    return code;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(SMX_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+#define CKLN(sim, name) do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return fail(SMX_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); (sim)->launches++; if ((sim)->prof) { int r2_ = prof_mark((sim), (name)); if (r2_) return r2_; } } while (0)
+#define CKL(sim) CKLN(sim, "other")
+#define TRY(expr) do { int r_ = (expr); if (r_ != SMX_OK) return r_; } while (0)
+
+namespace {
+
+struct Order {                  // one physical ordering of the particles (an "epoch" of the cell sort)
+    uint32_t* perm = nullptr;   // storage slot -> particle id (nullptr: identity)
+    uint32_t* idx = nullptr;    // storage slot -> slot in the parent ordering (nullptr for roots)
+    uint32_t* flags = nullptr;  // [nb^3] active-block flags
+    uint32_t* blocks = nullptr; // active-block list
+    int* nblocks = nullptr;     // device count
+    int* ctrl_slot = nullptr;   // control_idx in storage order (lazily built)
+    int ctrl_version = -1;
+    bool live = true;
+};
+
+struct HostPrim { PrimDev d; float* sdf_dev = nullptr; float4* nrm_dev = nullptr; };
+
+}  // namespace
+
+struct smx_sim {
+    smx_config cfg;
+    Params P;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 148;
+    bool dense = true;
+    // particle frames
+    float* pool = nullptr;
+    long long frame_floats = 0;
+    std::vector<int> slot_of, order_of, trans_from;
+    int spare_slot = 0;
+    std::vector<Order> orders;
+    std::vector<Order> free_orders;     // recycled device buffers
+    std::vector<int> dead_ids;
+    // grid
+    size_t G = 0;
+    float4 *g_in = nullptr, *g_out = nullptr, *g_mix = nullptr, *gg_out = nullptr, *gg_mix = nullptr, *g_lin = nullptr;
+    // adjoint ping-pong
+    float *adj_cur = nullptr, *adj_nxt = nullptr;
+    int adj_frame = -1, adj_order = -1;
+    std::map<int, float*> seeds;        // frame -> device (n,24) fp32 AoS in particle-id order
+    // primitives
+    std::vector<HostPrim> prims;
+    PrimDev* prims_dev = nullptr;
+    float* pstate = nullptr; double* pgrad = nullptr; double* ext_f = nullptr; float* ext_f_grad = nullptr;
+    float* abuf = nullptr; double* gabuf = nullptr;     // velocity-control action buffers [np][T][6]
+    // control
+    int* ctrl_id = nullptr; int ctrl_version = 0; float* action = nullptr; double* action_grad = nullptr;
+    // staging / sort scratch
+    float* stage_dev = nullptr; float* stage_host = nullptr;
+    uint32_t *keys_a = nullptr, *keys_b = nullptr, *iota = nullptr;
+    void* cub_tmp = nullptr; size_t cub_bytes = 0;
+    unsigned long long* counters = nullptr;
+    long long n_resorts = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    long long launches = 0;
+    bool prof = false;
+    std::vector<std::pair<const char*, cudaEvent_t>> marks;
+
+    float* frame_ptr(int f) { return pool + (long long)slot_of[f] * frame_floats; }
+    PrimSet primset() const {
+        PrimSet ps; ps.prims = prims_dev; ps.pstate = pstate; ps.pgrad = pgrad; ps.ext_f = ext_f; ps.ext_f_grad = ext_f_grad; ps.T = cfg.max_steps;
+        return ps;
+    }
+    bool has_contact() const {
+        if (cfg.collision_type != 2) return false;
+        for (auto& p : prims) if (p.d.enabled) return true;
+        return false;
+    }
+};
+
+static inline int nblk(long long n, int t) { return (int)((n + t - 1) / t); }
+
+// profiling: an event after every launch of a profiled substep (smx_profile_substep)
+static int prof_mark(smx_sim* s, const char* name) {
+    cudaEvent_t e;
+    CK(cudaEventCreate(&e));
+    CK(cudaEventRecord(e, s->stream));
+    s->marks.push_back({name, e});
+    return SMX_OK;
+}
+
+static int sync_prims(smx_sim* s) {
+    if (s->prims.empty()) return SMX_OK;
+    std::vector<PrimDev> h(s->prims.size());
+    for (size_t i = 0; i < h.size(); i++) h[i] = s->prims[i].d;
+    CK(cudaMemcpyAsync(s->prims_dev, h.data(), h.size() * sizeof(PrimDev), cudaMemcpyHostToDevice, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return SMX_OK;
+}
+
+static void free_order(Order& o) {
+    cudaFree(o.perm); cudaFree(o.idx); cudaFree(o.flags); cudaFree(o.blocks); cudaFree(o.nblocks); cudaFree(o.ctrl_slot);
+    o = Order(); o.live = false;
+}
+
+// Orderings no frame refers to any more are recycled: their device buffers go to a free list and are reused by
+// the next re-sort on the same stream (no cudaMalloc / cudaFree, hence no implicit sync, in the steady state).
+static void gc_orders(smx_sim* s) {
+    std::vector<char> used(s->orders.size(), 0);
+    for (size_t f = 0; f < s->order_of.size(); f++) {
+        if (s->order_of[f] >= 0) used[s->order_of[f]] = 1;
+        if (s->trans_from[f] >= 0) used[s->trans_from[f]] = 1;
+    }
+    if (s->adj_order >= 0) used[s->adj_order] = 1;
+    for (size_t i = 0; i < s->orders.size(); i++)
+        if (!used[i] && s->orders[i].live) {
+            Order& o = s->orders[i];
+            if (o.perm || o.idx || o.flags || o.ctrl_slot) { Order keep = o; keep.ctrl_version = -1; s->free_orders.push_back(keep); }
+            o = Order(); o.live = false;
+            s->dead_ids.push_back((int)i);
+        }
+}
+static int new_order_id(smx_sim* s, const Order& o) {
+    if (!s->dead_ids.empty()) { int id = s->dead_ids.back(); s->dead_ids.pop_back(); s->orders[id] = o; return id; }
+    s->orders.push_back(o);
+    return (int)s->orders.size() - 1;
+}
+// an Order with perm / idx buffers allocated (recycled when possible)
+static int alloc_order(smx_sim* s, Order& o, bool need_idx) {
+    int n = std::max(s->P.n, 1);
+    if (!s->free_orders.empty()) { o = s->free_orders.back(); s->free_orders.pop_back(); o.live = true; o.ctrl_version = -1; }
+    if (!o.perm) CK(cudaMalloc(&o.perm, (size_t)n * sizeof(uint32_t)));
+    if (need_idx && !o.idx) CK(cudaMalloc(&o.idx, (size_t)n * sizeof(uint32_t)));
+    return SMX_OK;
+}
+
+static int build_blocks(smx_sim* s, Order& o, const float* frame) {
+    if (s->dense) return SMX_OK;
+    int nb3 = s->P.nb * s->P.nb * s->P.nb;
+    if (!o.flags) {
+        CK(cudaMalloc(&o.flags, nb3 * sizeof(uint32_t))); CK(cudaMalloc(&o.blocks, nb3 * sizeof(uint32_t))); CK(cudaMalloc(&o.nblocks, sizeof(int)));
+    }
+    CK(cudaMemsetAsync(o.flags, 0, nb3 * sizeof(uint32_t), s->stream));
+    CK(cudaMemsetAsync(o.nblocks, 0, sizeof(int), s->stream));
+    if (s->P.n > 0) { k_mark_blocks<<<nblk(s->P.n, 256), 256, 0, s->stream>>>(s->P, frame, 2, o.flags); CKL(s); }
+    k_compact_blocks<<<nblk(nb3, 256), 256, 0, s->stream>>>(nb3, o.flags, o.blocks, o.nblocks); CKL(s);
+    return SMX_OK;
+}
+
+// (re)sort frame f by cell key: new ordering, permuted copy of the frame, active-block list
+static int resort(smx_sim* s, int f, bool keep_transition) {
+    int n = s->P.n;
+    int old_id = s->order_of[f];
+    gc_orders(s);
+    Order no;
+    float* src = s->frame_ptr(f);
+    bool do_sort = !(s->cfg.flags & SMX_FLAG_NO_SORT) && n > 0;
+    if (do_sort) {
+        if (!s->dense && old_id >= 0 && s->orders[old_id].flags) { k_check_active<<<nblk(n, 256), 256, 0, s->stream>>>(s->P, src, s->orders[old_id].flags, s->counters); CKL(s); }
+        k_keys<<<nblk(n, 256), 256, 0, s->stream>>>(s->P, src, s->keys_a, s->iota, s->counters); CKL(s);
+        TRY(alloc_order(s, no, true));
+        int bits = 0; while ((1ull << bits) < s->G) bits++;
+        CK(cub::DeviceRadixSort::SortPairs(s->cub_tmp, s->cub_bytes, s->keys_a, s->keys_b, s->iota, no.idx, n, 0, bits, s->stream));
+        s->launches += 3;
+        const uint32_t* old_perm = old_id >= 0 ? s->orders[old_id].perm : nullptr;
+        k_compose_perm<<<nblk(n, 256), 256, 0, s->stream>>>(n, old_perm, no.idx, no.perm); CKL(s);
+        float* dst = s->pool + (long long)s->spare_slot * s->frame_floats;
+        k_gather_frame<<<nblk(n, 256), 256, 0, s->stream>>>(n, s->P.stride, src, dst, no.idx); CKLN(s, "resort");
+        std::swap(s->slot_of[f], s->spare_slot);
+        s->n_resorts++;
+    } else if (old_id >= 0 && s->orders[old_id].perm && n > 0) {
+        TRY(alloc_order(s, no, false));
+        CK(cudaMemcpyAsync(no.perm, s->orders[old_id].perm, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s->stream));
+    }
+    TRY(build_blocks(s, no, s->frame_ptr(f)));
+    s->order_of[f] = new_order_id(s, no);
+    // keep_transition: frame f was produced by substep f-1 in the old ordering, so the adjoint has to be carried
+    // back through idx; otherwise (user-written frame) the adjoint chain is cut here, as in the reference
+    s->trans_from[f] = (keep_transition && do_sort) ? old_id : -1;
+    return SMX_OK;
+}
+
+static int ctrl_slots(smx_sim* s, int order_id, const int** out) {
+    *out = nullptr;
+    if (s->cfg.n_control <= 0) return SMX_OK;
+    Order& o = s->orders[order_id];
+    if (!o.ctrl_slot) CK(cudaMalloc(&o.ctrl_slot, std::max(1, s->P.n) * sizeof(int)));
+    if (o.ctrl_version != s->ctrl_version) {
+        if (s->P.n > 0) { k_permute_i32<<<nblk(s->P.n, 256), 256, 0, s->stream>>>(s->P.n, s->ctrl_id, o.ctrl_slot, o.perm); CKL(s); }
+        o.ctrl_version = s->ctrl_version;
+    }
+    *out = o.ctrl_slot;
+    return SMX_OK;
+}
+
+template <typename F>
+static int dispatch_mat(int material, int ptype, F&& fn) {
+    int mat = material * 3 + ptype;
+    switch (mat) {
+        case 0: return fn(std::integral_constant<int, 0>());
+        case 1: return fn(std::integral_constant<int, 1>());
+        case 2: return fn(std::integral_constant<int, 2>());
+        case 3: return fn(std::integral_constant<int, 4>());   // neo-Hookean "plastic" falls through to elastic (mpm_simulator.py:237-241)
+        case 4: return fn(std::integral_constant<int, 4>());
+        case 5: return fn(std::integral_constant<int, 5>());
+    }
+    return fail(SMX_ERR_ARG, "bad material_model/ptype %d/%d", material, ptype);
+}
+
+static int grid_blocks_launch(smx_sim* s) { return s->sm_count * 8; }
+
+static int clear_grids(smx_sim* s, const Order& o, float4* a, float4* b, float4* c) {
+    if (s->dense) {
+        if (a) CK(cudaMemsetAsync(a, 0, s->G * sizeof(float4), s->stream));
+        if (b) CK(cudaMemsetAsync(b, 0, s->G * sizeof(float4), s->stream));
+        if (c) CK(cudaMemsetAsync(c, 0, s->G * sizeof(float4), s->stream));
+    } else {
+        k_clear_blocks<<<grid_blocks_launch(s), 256, 0, s->stream>>>(o.blocks, o.nblocks, a, b, c); CKLN(s, "clear");
+        return SMX_OK;
+    }
+    if (s->prof) TRY(prof_mark(s, "clear"));
+    return SMX_OK;
+}
+
+// P2G + grid update + forecast contact of substep f (everything before G2P); shared by forward and adjoint
+static int forward_to_grid(smx_sim* s, int f, bool write_F, bool accumulate) {
+    const Params& P = s->P;
+    Order& o = s->orders[s->order_of[f]];
+    const float* fin = s->frame_ptr(f);
+    float* fout = write_F ? s->frame_ptr(f + 1) : nullptr;
+    PrimSet ps = s->primset();
+    bool contact = s->has_contact();
+    const int* cslot = nullptr;
+    TRY(ctrl_slots(s, s->order_of[f], &cslot));
+    TRY(clear_grids(s, o, s->g_in, nullptr, nullptr));
+    if (P.n > 0) {
+        TRY(dispatch_mat(P.material, P.ptype, [&](auto mat) {
+            k_p2g<decltype(mat)::value><<<nblk(P.n, SMX_TPB), SMX_TPB, 0, s->stream>>>(P, ps, f, fin, fout, s->g_in, cslot, s->action, accumulate ? 1 : 0);
+            CKLN(s, "k_p2g"); return (int)SMX_OK;
+        }));
+    }
+    if (write_F && s->cfg.rigid_velocity_control && !s->prims.empty()) {
+        k_forward_kinematics<<<1, 32, 0, s->stream>>>(s->pstate, s->cfg.max_steps, (int)s->prims.size(), f, P.dt); CKL(s);
+    }
+    k_grid_op<<<grid_blocks_launch(s), 256, 0, s->stream>>>(P, ps, f, s->dense ? nullptr : o.blocks, o.nblocks, s->g_in, s->g_out, contact ? s->g_mix : nullptr, accumulate ? 1 : 0);
+    CKLN(s, "k_grid_op");
+    if (contact && P.n > 0) {
+        float life = 1.0f / (float)(P.substeps - f % P.substeps);      // mpm_simulator.py:425 (f32 in the reference too)
+        k_contact<<<nblk(P.n, SMX_TPB), SMX_TPB, 0, s->stream>>>(P, ps, f, life, fin, s->g_mix, s->g_out, accumulate ? 1 : 0); CKLN(s, "k_contact");
+    }
+    return SMX_OK;
+}
+
+static int check_frame(smx_sim* s, int f, const char* what) {
+    if (!s) return fail(SMX_ERR_ARG, "%s: null simulator", what);
+    if (f < 0 || f >= s->cfg.max_steps) return fail(SMX_ERR_RANGE, "%s: frame %d outside [0, %d)", what, f, s->cfg.max_steps);
+    return SMX_OK;
+}
+static int check_prim(smx_sim* s, int id, const char* what) {
+    if (!s) return fail(SMX_ERR_ARG, "%s: null simulator", what);
+    if (id < 0 || id >= (int)s->prims.size()) return fail(SMX_ERR_RANGE, "%s: primitive %d outside [0, %d)", what, id, (int)s->prims.size());
+    return SMX_OK;
+}
+
+// host (n, ncomp) f64 in id order -> frame components [c0, c0+ncomp) in storage order
+static int upload_cols(smx_sim* s, int f, const double* host, int ncomp, int c0) {
+    int n = s->P.n;
+    if (n == 0) return SMX_OK;
+    size_t cnt = (size_t)n * ncomp;
+    CK(cudaStreamSynchronize(s->stream));       // staging buffer reuse
+    for (size_t i = 0; i < cnt; i++) s->stage_host[i] = (float)host[i];
+    CK(cudaMemcpyAsync(s->stage_dev, s->stage_host, cnt * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    const uint32_t* perm = s->orders[s->order_of[f]].perm;
+    k_upload<<<nblk(n, 256), 256, 0, s->stream>>>(n, s->P.stride, s->stage_dev, ncomp, c0, s->frame_ptr(f), perm, 0); CKL(s);
+    return SMX_OK;
+}
+static int download_cols(smx_sim* s, const float* frame, const uint32_t* perm, double* host, int ncomp, int c0) {
+    int n = s->P.n;
+    if (n == 0) return SMX_OK;
+    size_t cnt = (size_t)n * ncomp;
+    k_download<<<nblk(n, 256), 256, 0, s->stream>>>(n, s->P.stride, s->stage_dev, ncomp, c0, frame, perm); CKL(s);
+    CK(cudaMemcpyAsync(s->stage_host, s->stage_dev, cnt * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    for (size_t i = 0; i < cnt; i++) host[i] = (double)s->stage_host[i];
+    return SMX_OK;
+}
+static int ensure_order(smx_sim* s, int f) {
+    if (s->order_of[f] >= 0) return SMX_OK;
+    // a frame that was never written: give it an identity ordering
+    Order o;
+    int id = new_order_id(s, o);
+    s->order_of[f] = id;
+    s->trans_from[f] = -1;
+    CK(cudaMemsetAsync(s->frame_ptr(f), 0, s->frame_floats * sizeof(float), s->stream));
+    return build_blocks(s, s->orders[id], s->frame_ptr(f));
+}
+static int apply_seed(smx_sim* s, int f, float* adj, int order_id) {
+    auto it = s->seeds.find(f);
+    if (it == s->seeds.end() || s->P.n == 0) return SMX_OK;
+    k_upload<<<nblk(s->P.n, 256), 256, 0, s->stream>>>(s->P.n, s->P.stride, it->second, 24, 0, adj, s->orders[order_id].perm, 1); CKL(s);
+    return SMX_OK;
+}
+
+// =================================================================================================
+extern "C" {
+
+const char* smx_last_error(void) { return g_err; }
+
+int smx_create(const smx_config* cfg, smx_sim** out) {
+    if (!cfg || !out) return fail(SMX_ERR_ARG, "smx_create: null argument");
+    if (cfg->n_particles < 0 || cfg->n_grid < 8 || cfg->n_grid % 4 || cfg->max_steps < 2) return fail(SMX_ERR_ARG, "smx_create: need n_particles >= 0, n_grid >= 8 and a multiple of 4, max_steps >= 2");
+    if (cfg->substeps < 1) return fail(SMX_ERR_ARG, "smx_create: substeps must be >= 1");
+    if (cfg->material_model < 0 || cfg->material_model > 1 || cfg->ptype < 0 || cfg->ptype > 2 || cfg->collision_type < 0 || cfg->collision_type > 2)
+        return fail(SMX_ERR_ARG, "smx_create: material_model in {0,1}, ptype in {0,1,2}, collision_type in {0,1,2}");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return fail(SMX_ERR_CUDA, "smx_create: no CUDA device (%s); this library has no CPU path", cudaGetErrorString(e));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(SMX_ERR_ARG, "smx_create: device %d outside [0, %d)", cfg->device, ndev);
+    CK(cudaSetDevice(cfg->device));
+    smx_sim* s = new smx_sim();
+    s->cfg = *cfg;
+    cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, cfg->device));
+    s->sm_count = prop.multiProcessorCount;
+    if (cfg->stream) s->stream = (cudaStream_t)cfg->stream; else { CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)); s->own_stream = true; }
+    Params& P = s->P;
+    int n = cfg->n_particles;
+    P.n = n; P.stride = ((long long)std::max(n, 1) + 31) / 32 * 32;
+    P.ng = cfg->n_grid; P.nb = cfg->n_grid / 4;
+    double dx = 1.0 / cfg->n_grid, p_vol = (dx * 0.5) * (dx * 0.5), p_mass = p_vol;       // mpm_simulator.py:32-35
+    double mu = cfg->E / (2 * (1 + cfg->nu)), lam = cfg->E * cfg->nu / ((1 + cfg->nu) * (1 - 2 * cfg->nu));
+    if (cfg->ptype == 1) { mu *= 0.3; lam *= 0.3; } else if (cfg->ptype == 2) mu = 0.0;     // :42-45
+    P.dt = (float)cfg->dt; P.dx = (float)dx; P.inv_dx = (float)cfg->n_grid; P.p_mass = (float)p_mass; P.mu = (float)mu; P.lam = (float)lam;
+    P.cs = (float)(-cfg->dt * p_vol * 4 * (double)cfg->n_grid * (double)cfg->n_grid);
+    P.gx = (float)cfg->gravity[0]; P.gy = (float)cfg->gravity[1]; P.gz = (float)cfg->gravity[2];
+    P.sticky = cfg->ground_friction >= 10.0;
+    P.material = cfg->material_model; P.ptype = cfg->ptype; P.ctype = cfg->collision_type; P.substeps = cfg->substeps; P.n_control = cfg->n_control; P.np = 0;
+    s->dense = (cfg->flags & SMX_FLAG_DENSE_GRID) || (cfg->flags & SMX_FLAG_NO_SORT) || cfg->sort_every <= 0;
+    s->G = (size_t)P.ng * P.ng * P.ng;
+    s->frame_floats = 24 * P.stride;
+    int T = cfg->max_steps;
+    s->slot_of.resize(T); s->order_of.assign(T, -1); s->trans_from.assign(T, -1);
+    for (int f = 0; f < T; f++) s->slot_of[f] = f;
+    s->spare_slot = T;
+    size_t pool_bytes = (size_t)(T + 1) * s->frame_floats * sizeof(float);
+    if (cudaMalloc(&s->pool, pool_bytes) != cudaSuccess) { cudaGetLastError(); delete s; return fail(SMX_ERR_NOMEM, "smx_create: cannot allocate %.1f MB of particle checkpoints", pool_bytes / 1e6); }
+    CK(cudaMalloc(&s->g_in, s->G * sizeof(float4))); CK(cudaMalloc(&s->g_out, s->G * sizeof(float4))); CK(cudaMalloc(&s->g_mix, s->G * sizeof(float4)));
+    CK(cudaMalloc(&s->gg_out, s->G * sizeof(float4))); CK(cudaMalloc(&s->gg_mix, s->G * sizeof(float4)));
+    CK(cudaMemsetAsync(s->g_in, 0, s->G * sizeof(float4), s->stream)); CK(cudaMemsetAsync(s->g_out, 0, s->G * sizeof(float4), s->stream));
+    CK(cudaMemsetAsync(s->g_mix, 0, s->G * sizeof(float4), s->stream)); CK(cudaMemsetAsync(s->gg_out, 0, s->G * sizeof(float4), s->stream));
+    CK(cudaMemsetAsync(s->gg_mix, 0, s->G * sizeof(float4), s->stream));
+    CK(cudaMalloc(&s->adj_cur, s->frame_floats * sizeof(float))); CK(cudaMalloc(&s->adj_nxt, s->frame_floats * sizeof(float)));
+    size_t stage = (size_t)std::max(n, 1) * 24;
+    CK(cudaMalloc(&s->stage_dev, stage * sizeof(float))); CK(cudaMallocHost(&s->stage_host, stage * sizeof(float)));
+    CK(cudaMalloc(&s->keys_a, std::max(n, 1) * sizeof(uint32_t))); CK(cudaMalloc(&s->keys_b, std::max(n, 1) * sizeof(uint32_t))); CK(cudaMalloc(&s->iota, std::max(n, 1) * sizeof(uint32_t)));
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, s->cub_bytes, s->keys_a, s->keys_b, s->iota, s->iota, std::max(n, 1), 0, 32, s->stream));
+    CK(cudaMalloc(&s->cub_tmp, s->cub_bytes));
+    CK(cudaMalloc(&s->counters, 4 * sizeof(unsigned long long))); CK(cudaMemsetAsync(s->counters, 0, 4 * sizeof(unsigned long long), s->stream));
+    CK(cudaMalloc(&s->prims_dev, SMX_MAXP * sizeof(PrimDev)));
+    CK(cudaMalloc(&s->pstate, (size_t)SMX_MAXP * T * 13 * sizeof(float))); CK(cudaMemsetAsync(s->pstate, 0, (size_t)SMX_MAXP * T * 13 * sizeof(float), s->stream));
+    CK(cudaMalloc(&s->pgrad, (size_t)SMX_MAXP * T * 13 * sizeof(double))); CK(cudaMemsetAsync(s->pgrad, 0, (size_t)SMX_MAXP * T * 13 * sizeof(double), s->stream));
+    CK(cudaMalloc(&s->ext_f, SMX_MAXP * 6 * sizeof(double))); CK(cudaMemsetAsync(s->ext_f, 0, SMX_MAXP * 6 * sizeof(double), s->stream));
+    CK(cudaMalloc(&s->ext_f_grad, SMX_MAXP * 6 * sizeof(float))); CK(cudaMemsetAsync(s->ext_f_grad, 0, SMX_MAXP * 6 * sizeof(float), s->stream));
+    CK(cudaMalloc(&s->abuf, (size_t)SMX_MAXP * T * 6 * sizeof(float))); CK(cudaMemsetAsync(s->abuf, 0, (size_t)SMX_MAXP * T * 6 * sizeof(float), s->stream));
+    CK(cudaMalloc(&s->gabuf, (size_t)SMX_MAXP * T * 6 * sizeof(double))); CK(cudaMemsetAsync(s->gabuf, 0, (size_t)SMX_MAXP * T * 6 * sizeof(double), s->stream));
+    int nc = std::max(cfg->n_control, 1);
+    CK(cudaMalloc(&s->ctrl_id, std::max(n, 1) * sizeof(int))); CK(cudaMemsetAsync(s->ctrl_id, 0xff, std::max(n, 1) * sizeof(int), s->stream));
+    CK(cudaMalloc(&s->action, nc * 3 * sizeof(float))); CK(cudaMemsetAsync(s->action, 0, nc * 3 * sizeof(float), s->stream));
+    CK(cudaMalloc(&s->action_grad, nc * 3 * sizeof(double))); CK(cudaMemsetAsync(s->action_grad, 0, nc * 3 * sizeof(double), s->stream));
+    CK(cudaEventCreate(&s->ev0)); CK(cudaEventCreate(&s->ev1));
+    CK(cudaStreamSynchronize(s->stream));
+    *out = s;
+    return SMX_OK;
+}
+
+int smx_destroy(smx_sim* s) {
+    if (!s) return SMX_OK;
+    cudaSetDevice(s->cfg.device);
+    cudaStreamSynchronize(s->stream);
+    for (auto& o : s->orders) if (o.live) free_order(o);
+    for (auto& o : s->free_orders) free_order(o);
+    for (auto& kv : s->seeds) cudaFree(kv.second);
+    for (auto& p : s->prims) { cudaFree(p.sdf_dev); cudaFree(p.nrm_dev); }
+    void* ptrs[] = {s->pool, s->g_in, s->g_out, s->g_mix, s->gg_out, s->gg_mix, s->g_lin, s->adj_cur, s->adj_nxt, s->stage_dev, s->keys_a, s->keys_b, s->iota, s->cub_tmp,
+                    s->counters, s->prims_dev, s->pstate, s->pgrad, s->ext_f, s->ext_f_grad, s->abuf, s->gabuf, s->ctrl_id, s->action, s->action_grad};
+    for (void* p : ptrs) cudaFree(p);
+    cudaFreeHost(s->stage_host);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->own_stream) cudaStreamDestroy(s->stream);
+    delete s;
+    return SMX_OK;
+}
+
+int smx_synchronize(smx_sim* s) {
+    if (!s) return fail(SMX_ERR_ARG, "smx_synchronize: null simulator");
+    CK(cudaStreamSynchronize(s->stream));
+    return SMX_OK;
+}
+
+int smx_add_primitive(smx_sim* s, const double* sdf, const double* normal, const int32_t res[3], const double lower[3], const double upper[3],
+                      double sdf_dx, double friction, double softness, int32_t enabled) {
+    if (!s) return fail(SMX_ERR_ARG, "smx_add_primitive: null simulator");
+    if ((int)s->prims.size() >= SMX_MAXP) return fail(SMX_ERR_RANGE, "smx_add_primitive: at most %d primitives", SMX_MAXP);
+    CK(cudaSetDevice(s->cfg.device));
+    HostPrim hp; memset(&hp.d, 0, sizeof hp.d);
+    hp.d.friction = (float)friction; hp.d.softness = (float)softness; hp.d.enabled = enabled ? 1 : 0;
+    if (sdf) {
+        if (!normal || !res || !lower || !upper || sdf_dx <= 0 || res[0] < 2 || res[1] < 2 || res[2] < 2) return fail(SMX_ERR_ARG, "smx_add_primitive: incomplete table description");
+        size_t R = (size_t)res[0] * res[1] * res[2];
+        std::vector<float> hs(R); std::vector<float4> hn(R);
+        for (size_t i = 0; i < R; i++) { hs[i] = (float)sdf[i]; hn[i] = make_float4((float)normal[3 * i], (float)normal[3 * i + 1], (float)normal[3 * i + 2], 0.f); }
+        CK(cudaMalloc(&hp.sdf_dev, R * sizeof(float))); CK(cudaMalloc(&hp.nrm_dev, R * sizeof(float4)));
+        CK(cudaMemcpy(hp.sdf_dev, hs.data(), R * sizeof(float), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(hp.nrm_dev, hn.data(), R * sizeof(float4), cudaMemcpyHostToDevice));
+        hp.d.sdf = hp.sdf_dev; hp.d.nrm = hp.nrm_dev; hp.d.has_table = 1;
+        hp.d.r0 = res[0]; hp.d.r1 = res[1]; hp.d.r2 = res[2];
+        for (int i = 0; i < 3; i++) { hp.d.lo[i] = (float)lower[i]; hp.d.hi[i] = (float)upper[i]; }
+        hp.d.inv_dx = (float)(1.0 / sdf_dx);
+    }
+    s->prims.push_back(hp);
+    s->P.np = (int)s->prims.size();
+    TRY(sync_prims(s));
+    return (int)s->prims.size() - 1;
+}
+int smx_set_primitive_params(smx_sim* s, int32_t id, double friction, double softness) {
+    TRY(check_prim(s, id, "smx_set_primitive_params"));
+    s->prims[id].d.friction = (float)friction; s->prims[id].d.softness = (float)softness;
+    return sync_prims(s);
+}
+int smx_set_primitive_contact(smx_sim* s, int32_t id, int32_t enabled) {
+    TRY(check_prim(s, id, "smx_set_primitive_contact"));
+    s->prims[id].d.enabled = enabled ? 1 : 0;
+    return sync_prims(s);
+}
+
+int smx_reset(smx_sim* s, const double* state, int32_t ncols) {
+    if (!s || !state) return fail(SMX_ERR_ARG, "smx_reset: null argument");
+    if (ncols != 3 && ncols != 24) return fail(SMX_ERR_ARG, "smx_reset: state must have 3 or 24 columns, got %d", ncols);
+    CK(cudaSetDevice(s->cfg.device));
+    CK(cudaStreamSynchronize(s->stream));
+    std::fill(s->order_of.begin(), s->order_of.end(), -1);
+    std::fill(s->trans_from.begin(), s->trans_from.end(), -1);
+    s->adj_frame = -1; s->adj_order = -1;
+    gc_orders(s);                       // every ordering is unreferenced now: recycle all of them
+    int n = s->P.n;
+    Order root; s->order_of[0] = new_order_id(s, root);
+    for (size_t p = 0; p < (size_t)n; p++) {
+        float* r = s->stage_host + 24 * p;
+        if (ncols == 24) for (int c = 0; c < 24; c++) r[c] = (float)state[24 * p + c];
+        else {
+            for (int c = 0; c < 24; c++) r[c] = 0.f;
+            r[0] = (float)state[3 * p]; r[1] = (float)state[3 * p + 1]; r[2] = (float)state[3 * p + 2];
+            r[6] = r[10] = r[14] = 1.f;
+        }
+    }
+    if (n > 0) {
+        CK(cudaMemcpyAsync(s->stage_dev, s->stage_host, (size_t)n * 24 * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+        k_upload<<<nblk(n, 256), 256, 0, s->stream>>>(n, s->P.stride, s->stage_dev, 24, 0, s->frame_ptr(0), nullptr, 0); CKL(s);
+    }
+    return resort(s, 0, false);
+}
+
+int smx_set_frame(smx_sim* s, int32_t f, const double* x, const double* v, const double* F, const double* C) {
+    TRY(check_frame(s, f, "smx_set_frame"));
+    CK(cudaSetDevice(s->cfg.device));
+    TRY(ensure_order(s, f));
+    if (x) TRY(upload_cols(s, f, x, 3, 0));
+    if (v) TRY(upload_cols(s, f, v, 3, 3));
+    if (F) TRY(upload_cols(s, f, F, 9, 6));
+    if (C) TRY(upload_cols(s, f, C, 9, 15));
+    if (x) TRY(resort(s, f, false));        // positions changed: re-bin (cuts the adjoint chain at f, as in the reference)
+    return SMX_OK;
+}
+int smx_get_state(smx_sim* s, int32_t f, double* out24) {
+    TRY(check_frame(s, f, "smx_get_state"));
+    if (!out24) return fail(SMX_ERR_ARG, "smx_get_state: null output");
+    if (s->order_of[f] < 0) return fail(SMX_ERR_STATE, "smx_get_state: frame %d has not been written", f);
+    CK(cudaSetDevice(s->cfg.device));
+    return download_cols(s, s->frame_ptr(f), s->orders[s->order_of[f]].perm, out24, 24, 0);
+}
+static int get_cols(smx_sim* s, int f, double* out, int ncomp, int c0, const char* what) {
+    TRY(check_frame(s, f, what));
+    if (!out) return fail(SMX_ERR_ARG, "%s: null output", what);
+    if (s->order_of[f] < 0) return fail(SMX_ERR_STATE, "%s: frame %d has not been written", what, f);
+    CK(cudaSetDevice(s->cfg.device));
+    return download_cols(s, s->frame_ptr(f), s->orders[s->order_of[f]].perm, out, ncomp, c0);
+}
+int smx_get_x(smx_sim* s, int32_t f, double* x) { return get_cols(s, f, x, 3, 0, "smx_get_x"); }
+int smx_get_v(smx_sim* s, int32_t f, double* v) { return get_cols(s, f, v, 3, 3, "smx_get_v"); }
+int smx_set_x(smx_sim* s, int32_t f, const double* x) { if (!x) return fail(SMX_ERR_ARG, "smx_set_x: null input"); return smx_set_frame(s, f, x, nullptr, nullptr, nullptr); }
+int smx_set_v(smx_sim* s, int32_t f, const double* v) { if (!v) return fail(SMX_ERR_ARG, "smx_set_v: null input"); return smx_set_frame(s, f, nullptr, v, nullptr, nullptr); }
+
+int smx_copy_frame(smx_sim* s, int32_t src, int32_t dst) {
+    TRY(check_frame(s, src, "smx_copy_frame")); TRY(check_frame(s, dst, "smx_copy_frame"));
+    if (s->order_of[src] < 0) return fail(SMX_ERR_STATE, "smx_copy_frame: source frame %d has not been written", src);
+    CK(cudaSetDevice(s->cfg.device));
+    if (src != dst) {
+        CK(cudaMemcpyAsync(s->frame_ptr(dst), s->frame_ptr(src), s->frame_floats * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
+        s->order_of[dst] = s->order_of[src]; s->trans_from[dst] = -1;
+        int T = s->cfg.max_steps;
+        for (size_t i = 0; i < s->prims.size(); i++)
+            for (int j = 0; j < s->cfg.substeps; j++) {
+                if (src + j >= T || dst + j >= T) break;
+                CK(cudaMemcpyAsync(s->pstate + (i * T + dst + j) * 13, s->pstate + (i * T + src + j) * 13, 13 * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
+                CK(cudaMemcpyAsync(s->abuf + (i * T + dst + j) * 6, s->abuf + (i * T + src + j) * 6, 6 * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
+            }
+    }
+    return SMX_OK;
+}
+
+// ---- primitives ---------------------------------------------------------------------------------
+int smx_set_primitive_state(smx_sim* s, int32_t id, int32_t f0, int32_t f1, const double* s13) {
+    TRY(check_prim(s, id, "smx_set_primitive_state"));
+    if (!s13) return fail(SMX_ERR_ARG, "smx_set_primitive_state: null state");
+    if (f0 < 0 || f1 > s->cfg.max_steps || f0 >= f1) return fail(SMX_ERR_RANGE, "smx_set_primitive_state: frame range [%d, %d) outside [0, %d)", f0, f1, s->cfg.max_steps);
+    CK(cudaSetDevice(s->cfg.device));
+    std::vector<float> h((size_t)(f1 - f0) * 13);
+    for (int f = 0; f < f1 - f0; f++) for (int c = 0; c < 13; c++) h[(size_t)f * 13 + c] = (float)s13[c];
+    CK(cudaMemcpyAsync(s->pstate + ((size_t)id * s->cfg.max_steps + f0) * 13, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return SMX_OK;
+}
+int smx_get_primitive_state(smx_sim* s, int32_t id, int32_t f, double* out13) {
+    TRY(check_prim(s, id, "smx_get_primitive_state")); TRY(check_frame(s, f, "smx_get_primitive_state"));
+    if (!out13) return fail(SMX_ERR_ARG, "smx_get_primitive_state: null output");
+    CK(cudaSetDevice(s->cfg.device));
+    float h[13];
+    CK(cudaMemcpyAsync(h, s->pstate + ((size_t)id * s->cfg.max_steps + f) * 13, sizeof h, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    for (int c = 0; c < 13; c++) out13[c] = h[c];
+    return SMX_OK;
+}
+int smx_get_primitive_state_grad(smx_sim* s, int32_t id, int32_t f0, int32_t f1, double* out13) {
+    TRY(check_prim(s, id, "smx_get_primitive_state_grad"));
+    if (!out13) return fail(SMX_ERR_ARG, "smx_get_primitive_state_grad: null output");
+    if (f0 < 0 || f1 > s->cfg.max_steps || f0 >= f1) return fail(SMX_ERR_RANGE, "smx_get_primitive_state_grad: frame range [%d, %d) outside [0, %d)", f0, f1, s->cfg.max_steps);
+    CK(cudaSetDevice(s->cfg.device));
+    std::vector<double> h((size_t)(f1 - f0) * 13);
+    CK(cudaMemcpyAsync(h.data(), s->pgrad + ((size_t)id * s->cfg.max_steps + f0) * 13, h.size() * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    for (int c = 0; c < 13; c++) out13[c] = 0;
+    for (int f = 0; f < f1 - f0; f++) for (int c = 0; c < 13; c++) out13[c] += h[(size_t)f * 13 + c];
+    return SMX_OK;
+}
+int smx_add_primitive_state_grad(smx_sim* s, int32_t id, int32_t f, const double* g13) {
+    TRY(check_prim(s, id, "smx_add_primitive_state_grad")); TRY(check_frame(s, f, "smx_add_primitive_state_grad"));
+    if (!g13) return fail(SMX_ERR_ARG, "smx_add_primitive_state_grad: null input");
+    CK(cudaSetDevice(s->cfg.device));
+    double h[13];
+    double* d = s->pgrad + ((size_t)id * s->cfg.max_steps + f) * 13;
+    CK(cudaMemcpyAsync(h, d, sizeof h, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    for (int c = 0; c < 13; c++) h[c] += g13[c];
+    CK(cudaMemcpyAsync(d, h, sizeof h, cudaMemcpyHostToDevice, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return SMX_OK;
+}
+int smx_get_ext_f(smx_sim* s, int32_t id, double* out6) {
+    TRY(check_prim(s, id, "smx_get_ext_f"));
+    if (!out6) return fail(SMX_ERR_ARG, "smx_get_ext_f: null output");
+    CK(cudaSetDevice(s->cfg.device));
+    CK(cudaMemcpyAsync(out6, s->ext_f + 6 * id, 6 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return SMX_OK;
+}
+int smx_clear_ext_f(smx_sim* s, int32_t id) {
+    TRY(check_prim(s, id, "smx_clear_ext_f"));
+    CK(cudaSetDevice(s->cfg.device));
+    CK(cudaMemsetAsync(s->ext_f + 6 * id, 0, 6 * sizeof(double), s->stream));
+    CK(cudaMemsetAsync(s->ext_f_grad + 6 * id, 0, 6 * sizeof(float), s->stream));
+    return SMX_OK;
+}
+int smx_set_ext_f_grad(smx_sim* s, int32_t id, const double* g6) {
+    TRY(check_prim(s, id, "smx_set_ext_f_grad"));
+    if (!g6) return fail(SMX_ERR_ARG, "smx_set_ext_f_grad: null input");
+    CK(cudaSetDevice(s->cfg.device));
+    float h[6]; for (int i = 0; i < 6; i++) h[i] = (float)g6[i];
+    CK(cudaMemcpyAsync(s->ext_f_grad + 6 * id, h, sizeof h, cudaMemcpyHostToDevice, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return SMX_OK;
+}
+int smx_set_primitive_action(smx_sim* s, int32_t id, int32_t st, int32_t n, const double* a6) {
+    TRY(check_prim(s, id, "smx_set_primitive_action"));
+    if (!a6) return fail(SMX_ERR_ARG, "smx_set_primitive_action: null input");
+    int T = s->cfg.max_steps;
+    if (st < 0 || n < 1 || (long long)(st + 1) * n > T) return fail(SMX_ERR_RANGE, "smx_set_primitive_action: frames [%d, %d) outside [0, %d)", st * n, (st + 1) * n, T);
+    CK(cudaSetDevice(s->cfg.device));
+    // action_buffer[s] = a ; v[j] = a[3:6], w[j] = a[0:3] for j in [s*n, (s+1)*n)   (primitive_base.py:285-304)
+    float a[6]; for (int i = 0; i < 6; i++) a[i] = (float)a6[i];
+    CK(cudaMemcpyAsync(s->abuf + ((size_t)id * T + st) * 6, a, sizeof a, cudaMemcpyHostToDevice, s->stream));
+    std::vector<float> h((size_t)n * 13);
+    CK(cudaMemcpyAsync(h.data(), s->pstate + ((size_t)id * T + (size_t)st * n) * 13, h.size() * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    for (int j = 0; j < n; j++) for (int k = 0; k < 3; k++) { h[(size_t)j * 13 + 7 + k] = a[3 + k]; h[(size_t)j * 13 + 10 + k] = a[k]; }
+    CK(cudaMemcpyAsync(s->pstate + ((size_t)id * T + (size_t)st * n) * 13, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return SMX_OK;
+}
+int smx_get_primitive_action_grad(smx_sim* s, int32_t id, int32_t st, int32_t n, double* out6) {
+    TRY(check_prim(s, id, "smx_get_primitive_action_grad"));
+    if (!out6) return fail(SMX_ERR_ARG, "smx_get_primitive_action_grad: null output");
+    int T = s->cfg.max_steps;
+    if (st < 0 || n < 1 || (long long)(st + 1) * n > T) return fail(SMX_ERR_RANGE, "smx_get_primitive_action_grad: frames outside [0, %d)", T);
+    CK(cudaSetDevice(s->cfg.device));
+    // set_velocity_from_action_kernel.grad accumulates into action_buffer.grad[s] (primitive_base.py:298-319)
+    std::vector<double> h((size_t)n * 13); double g[6];
+    CK(cudaMemcpyAsync(h.data(), s->pgrad + ((size_t)id * T + (size_t)st * n) * 13, h.size() * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaMemcpyAsync(g, s->gabuf + ((size_t)id * T + st) * 6, sizeof g, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    for (int j = 0; j < n; j++) for (int k = 0; k < 3; k++) { g[3 + k] += h[(size_t)j * 13 + 7 + k]; g[k] += h[(size_t)j * 13 + 10 + k]; }
+    CK(cudaMemcpyAsync(s->gabuf + ((size_t)id * T + st) * 6, g, sizeof g, cudaMemcpyHostToDevice, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    for (int i = 0; i < 6; i++) out6[i] = g[i];
+    return SMX_OK;
+}
+
+// ---- control ------------------------------------------------------------------------------------
+int smx_set_action(smx_sim* s, const double* action) {
+    if (!s || !action) return fail(SMX_ERR_ARG, "smx_set_action: null argument");
+    if (s->cfg.n_control <= 0) return fail(SMX_ERR_STATE, "smx_set_action: simulator was created with n_control == 0");
+    CK(cudaSetDevice(s->cfg.device));
+    std::vector<float> h((size_t)s->cfg.n_control * 3);
+    for (size_t i = 0; i < h.size(); i++) h[i] = (float)action[i];
+    CK(cudaMemcpyAsync(s->action, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    CK(cudaMemsetAsync(s->action_grad, 0, h.size() * sizeof(double), s->stream));    // set_action_kernel zeroes action.grad (:584-586)
+    CK(cudaStreamSynchronize(s->stream));
+    return SMX_OK;
+}
+int smx_set_control_idx(smx_sim* s, const int32_t* idx) {
+    if (!s || !idx) return fail(SMX_ERR_ARG, "smx_set_control_idx: null argument");
+    CK(cudaSetDevice(s->cfg.device));
+    if (s->P.n > 0) CK(cudaMemcpyAsync(s->ctrl_id, idx, (size_t)s->P.n * sizeof(int), cudaMemcpyHostToDevice, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    s->ctrl_version++;
+    return SMX_OK;
+}
+int smx_get_action_grad(smx_sim* s, double* out) {
+    if (!s || !out) return fail(SMX_ERR_ARG, "smx_get_action_grad: null argument");
+    if (s->cfg.n_control <= 0) return fail(SMX_ERR_STATE, "smx_get_action_grad: simulator was created with n_control == 0");
+    CK(cudaSetDevice(s->cfg.device));
+    CK(cudaMemcpyAsync(out, s->action_grad, (size_t)s->cfg.n_control * 3 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return SMX_OK;
+}
+
+// ---- the hot path -------------------------------------------------------------------------------
+int smx_substep(smx_sim* s, int32_t f) {
+    TRY(check_frame(s, f, "smx_substep"));
+    if (f + 1 >= s->cfg.max_steps) return fail(SMX_ERR_RANGE, "smx_substep: substep %d would write frame %d >= max_steps %d", f, f + 1, s->cfg.max_steps);
+    if (s->order_of[f] < 0) return fail(SMX_ERR_STATE, "smx_substep: frame %d has not been written (call smx_reset / smx_set_frame first)", f);
+    CK(cudaSetDevice(s->cfg.device));
+    s->order_of[f + 1] = s->order_of[f]; s->trans_from[f + 1] = -1;
+    TRY(forward_to_grid(s, f, true, true));
+    if (s->P.n > 0) { k_g2p<<<nblk(s->P.n, SMX_TPB), SMX_TPB, 0, s->stream>>>(s->P, s->frame_ptr(f), s->frame_ptr(f + 1), s->g_out); CKLN(s, "k_g2p"); }
+    if (s->cfg.sort_every > 0 && (f + 1) % s->cfg.sort_every == 0 && !(s->cfg.flags & SMX_FLAG_NO_SORT)) TRY(resort(s, f + 1, true));
+    return SMX_OK;
+}
+
+int smx_substep_grad(smx_sim* s, int32_t f) {
+    TRY(check_frame(s, f, "smx_substep_grad"));
+    if (f + 1 >= s->cfg.max_steps) return fail(SMX_ERR_RANGE, "smx_substep_grad: substep %d outside the stored range", f);
+    if (s->order_of[f] < 0 || s->order_of[f + 1] < 0) return fail(SMX_ERR_STATE, "smx_substep_grad: substep %d has not been run forward", f);
+    CK(cudaSetDevice(s->cfg.device));
+    const Params& P = s->P;
+    int o = s->order_of[f];
+    if (s->adj_frame != f + 1) {        // start of a backward pass: the adjoint of frame f+1 is its loss seed
+        CK(cudaMemsetAsync(s->adj_cur, 0, s->frame_floats * sizeof(float), s->stream));
+        s->adj_frame = f + 1; s->adj_order = s->order_of[f + 1];
+        TRY(apply_seed(s, f + 1, s->adj_cur, s->adj_order));
+    }
+    if (s->adj_order != o) {            // frame f+1 was re-sorted after substep f produced it: carry the adjoint back
+        if (s->adj_order != s->order_of[f + 1] || s->trans_from[f + 1] != o || !s->orders[s->adj_order].idx)
+            return fail(SMX_ERR_STATE, "smx_substep_grad: adjoint of frame %d is not connected to substep %d (frame was overwritten?)", f + 1, f);
+        if (P.n > 0) { k_scatter_frame<<<nblk(P.n, 256), 256, 0, s->stream>>>(P.n, P.stride, s->adj_cur, s->adj_nxt, s->orders[s->adj_order].idx); CKLN(s, "resort_adjoint"); }
+        std::swap(s->adj_cur, s->adj_nxt);
+        s->adj_order = o;
+    }
+    Order& ord = s->orders[o];
+    bool contact = s->has_contact();
+    PrimSet ps = s->primset();
+    TRY(forward_to_grid(s, f, false, false));
+    TRY(clear_grids(s, ord, s->gg_out, contact ? s->gg_mix : nullptr, nullptr));
+    const float* fin = s->frame_ptr(f);
+    if (P.n > 0) { k_g2p_grad<<<nblk(P.n, SMX_TPB), SMX_TPB, 0, s->stream>>>(P, fin, s->adj_cur, s->adj_nxt, s->g_out, s->gg_out); CKLN(s, "k_g2p_grad"); }
+    if (contact && P.n > 0) {
+        float life = 1.0f / (float)(P.substeps - f % P.substeps);
+        k_contact_grad<<<nblk(P.n, SMX_TPB), SMX_TPB, 0, s->stream>>>(P, ps, f, life, fin, s->adj_nxt, s->g_mix, s->gg_out, s->gg_mix); CKLN(s, "k_contact_grad");
+    }
+    k_grid_grad<<<grid_blocks_launch(s), 256, 0, s->stream>>>(P, ps, f, s->dense ? nullptr : ord.blocks, ord.nblocks, s->g_in, s->gg_out, contact ? s->gg_mix : nullptr); CKLN(s, "k_grid_grad");
+    if (s->cfg.rigid_velocity_control && !s->prims.empty()) {
+        k_forward_kinematics_grad<<<1, 32, 0, s->stream>>>(s->pstate, s->pgrad, s->cfg.max_steps, (int)s->prims.size(), f, P.dt); CKL(s);
+    }
+    const int* cslot = nullptr;
+    TRY(ctrl_slots(s, o, &cslot));
+    if (P.n > 0) {
+        TRY(dispatch_mat(P.material, P.ptype, [&](auto mat) {
+            k_p2g_grad<decltype(mat)::value><<<nblk(P.n, SMX_TPB), SMX_TPB, 0, s->stream>>>(P, ps, f, fin, s->adj_cur, s->adj_nxt, s->gg_out, cslot, s->action, s->action_grad);
+            CKLN(s, "k_p2g_grad"); return (int)SMX_OK;
+        }));
+    }
+    std::swap(s->adj_cur, s->adj_nxt);
+    s->adj_frame = f; s->adj_order = o;
+    TRY(apply_seed(s, f, s->adj_cur, o));
+    return SMX_OK;
+}
+
+int smx_step(smx_sim* s, int32_t s0, int32_t count) {
+    for (int i = 0; i < count; i++) TRY(smx_substep(s, s0 + i));
+    return SMX_OK;
+}
+int smx_step_grad(smx_sim* s, int32_t s1, int32_t count) {
+    for (int i = 1; i <= count; i++) TRY(smx_substep_grad(s, s1 - i));
+    return SMX_OK;
+}
+
+// ---- adjoint seeds / read-out ---------------------------------------------------------------------
+static int add_seed(smx_sim* s, int f, const double* g, int ncols) {
+    int n = s->P.n;
+    if (n == 0) return SMX_OK;
+    CK(cudaSetDevice(s->cfg.device));
+    CK(cudaStreamSynchronize(s->stream));
+    for (size_t p = 0; p < (size_t)n; p++) {
+        float* r = s->stage_host + 24 * p;
+        if (ncols == 24) for (int c = 0; c < 24; c++) r[c] = (float)g[24 * p + c];
+        else { for (int c = 0; c < 24; c++) r[c] = 0.f; r[0] = (float)g[3 * p]; r[1] = (float)g[3 * p + 1]; r[2] = (float)g[3 * p + 2]; }
+    }
+    CK(cudaMemcpyAsync(s->stage_dev, s->stage_host, (size_t)n * 24 * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    auto it = s->seeds.find(f);
+    if (it == s->seeds.end()) {
+        float* d = nullptr;
+        CK(cudaMalloc(&d, (size_t)n * 24 * sizeof(float)));
+        CK(cudaMemcpyAsync(d, s->stage_dev, (size_t)n * 24 * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
+        s->seeds[f] = d;
+    } else {
+        k_axpy<<<nblk((long long)n * 24, 256), 256, 0, s->stream>>>((long long)n * 24, it->second, s->stage_dev); CKL(s);
+    }
+    CK(cudaStreamSynchronize(s->stream));
+    return SMX_OK;
+}
+int smx_add_state_grad(smx_sim* s, int32_t f, const double* g24) {
+    TRY(check_frame(s, f, "smx_add_state_grad"));
+    if (!g24) return fail(SMX_ERR_ARG, "smx_add_state_grad: null input");
+    return add_seed(s, f, g24, 24);
+}
+int smx_add_x_grad(smx_sim* s, int32_t f, const double* g3) {
+    TRY(check_frame(s, f, "smx_add_x_grad"));
+    if (!g3) return fail(SMX_ERR_ARG, "smx_add_x_grad: null input");
+    return add_seed(s, f, g3, 3);
+}
+int smx_get_state_grad(smx_sim* s, int32_t f, double* out24) {
+    TRY(check_frame(s, f, "smx_get_state_grad"));
+    if (!out24) return fail(SMX_ERR_ARG, "smx_get_state_grad: null output");
+    CK(cudaSetDevice(s->cfg.device));
+    if (s->adj_frame != f) {
+        // no backward step has produced this frame's adjoint: it is just the loss seed (if any)
+        if (s->order_of[f] < 0) return fail(SMX_ERR_STATE, "smx_get_state_grad: frame %d has not been written", f);
+        CK(cudaMemsetAsync(s->adj_nxt, 0, s->frame_floats * sizeof(float), s->stream));
+        TRY(apply_seed(s, f, s->adj_nxt, s->order_of[f]));
+        return download_cols(s, s->adj_nxt, s->orders[s->order_of[f]].perm, out24, 24, 0);
+    }
+    return download_cols(s, s->adj_cur, s->orders[s->adj_order].perm, out24, 24, 0);
+}
+int smx_get_grad(smx_sim* s, int32_t f, double* xg, double* vg) {
+    TRY(check_frame(s, f, "smx_get_grad"));
+    if (!xg || !vg) return fail(SMX_ERR_ARG, "smx_get_grad: null output");
+    std::vector<double> tmp((size_t)std::max(s->P.n, 1) * 24);
+    TRY(smx_get_state_grad(s, f, tmp.data()));
+    for (size_t p = 0; p < (size_t)s->P.n; p++) for (int c = 0; c < 3; c++) { xg[3 * p + c] = tmp[24 * p + c]; vg[3 * p + c] = tmp[24 * p + 3 + c]; }
+    return SMX_OK;
+}
+int smx_clear_grads(smx_sim* s) {
+    if (!s) return fail(SMX_ERR_ARG, "smx_clear_grads: null simulator");
+    CK(cudaSetDevice(s->cfg.device));
+    CK(cudaStreamSynchronize(s->stream));
+    for (auto& kv : s->seeds) cudaFree(kv.second);
+    s->seeds.clear();
+    s->adj_frame = -1; s->adj_order = -1;
+    int T = s->cfg.max_steps;
+    CK(cudaMemsetAsync(s->pgrad, 0, (size_t)SMX_MAXP * T * 13 * sizeof(double), s->stream));
+    CK(cudaMemsetAsync(s->gabuf, 0, (size_t)SMX_MAXP * T * 6 * sizeof(double), s->stream));
+    CK(cudaMemsetAsync(s->ext_f_grad, 0, SMX_MAXP * 6 * sizeof(float), s->stream));
+    CK(cudaMemsetAsync(s->action_grad, 0, (size_t)std::max(s->cfg.n_control, 1) * 3 * sizeof(double), s->stream));
+    return SMX_OK;
+}
+
+// ---- introspection --------------------------------------------------------------------------------
+int smx_get_sort_keys(smx_sim* s, int32_t f, uint32_t* keys) {
+    TRY(check_frame(s, f, "smx_get_sort_keys"));
+    if (!keys) return fail(SMX_ERR_ARG, "smx_get_sort_keys: null output");
+    if (s->order_of[f] < 0) return fail(SMX_ERR_STATE, "smx_get_sort_keys: frame %d has not been written", f);
+    CK(cudaSetDevice(s->cfg.device));
+    int n = s->P.n;
+    if (n == 0) return SMX_OK;
+    k_keys<<<nblk(n, 256), 256, 0, s->stream>>>(s->P, s->frame_ptr(f), s->keys_a, nullptr, nullptr); CKL(s);
+    CK(cudaMemcpyAsync(keys, s->keys_a, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return SMX_OK;
+}
+int smx_get_permutation(smx_sim* s, int32_t f, uint32_t* perm) {
+    TRY(check_frame(s, f, "smx_get_permutation"));
+    if (!perm) return fail(SMX_ERR_ARG, "smx_get_permutation: null output");
+    if (s->order_of[f] < 0) return fail(SMX_ERR_STATE, "smx_get_permutation: frame %d has not been written", f);
+    CK(cudaSetDevice(s->cfg.device));
+    int n = s->P.n;
+    const uint32_t* d = s->orders[s->order_of[f]].perm;
+    if (!d) { for (int i = 0; i < n; i++) perm[i] = i; return SMX_OK; }
+    CK(cudaMemcpyAsync(perm, d, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return SMX_OK;
+}
+int smx_get_grid(smx_sim* s, float* g_in, float* g_out) {
+    if (!s) return fail(SMX_ERR_ARG, "smx_get_grid: null simulator");
+    CK(cudaSetDevice(s->cfg.device));
+    if (!s->g_lin) CK(cudaMalloc(&s->g_lin, s->G * sizeof(float4)));
+    const float4* src[2] = {s->g_in, s->g_out}; float* dst[2] = {g_in, g_out};
+    for (int a = 0; a < 2; a++) {
+        if (!dst[a]) continue;
+        k_grid_linear<<<nblk((long long)s->G, 256), 256, 0, s->stream>>>(s->P.ng, s->P.nb, src[a], s->g_lin); CKL(s);
+        CK(cudaMemcpyAsync(dst[a], s->g_lin, s->G * sizeof(float4), cudaMemcpyDeviceToHost, s->stream));
+        CK(cudaStreamSynchronize(s->stream));
+    }
+    return SMX_OK;
+}
+int smx_get_counters(smx_sim* s, int64_t out[4]) {
+    if (!s || !out) return fail(SMX_ERR_ARG, "smx_get_counters: null argument");
+    CK(cudaSetDevice(s->cfg.device));
+    unsigned long long h[4];
+    CK(cudaMemcpyAsync(h, s->counters, sizeof h, cudaMemcpyDeviceToHost, s->stream));
+    int nb = -1;
+    CK(cudaStreamSynchronize(s->stream));
+    if (!s->dense)
+        for (int f = s->cfg.max_steps - 1; f >= 0; f--)
+            if (s->order_of[f] >= 0 && s->orders[s->order_of[f]].nblocks) { CK(cudaMemcpy(&nb, s->orders[s->order_of[f]].nblocks, sizeof(int), cudaMemcpyDeviceToHost)); break; }
+    out[0] = (int64_t)h[0]; out[1] = (int64_t)h[1]; out[2] = s->n_resorts; out[3] = nb;
+    return SMX_OK;
+}
+int smx_frame_component_dev(smx_sim* s, int32_t f, int32_t c, void** ptr) {
+    TRY(check_frame(s, f, "smx_frame_component_dev"));
+    if (!ptr || c < 0 || c >= 24) return fail(SMX_ERR_ARG, "smx_frame_component_dev: bad component");
+    *ptr = s->frame_ptr(f) + (long long)c * s->P.stride;
+    return SMX_OK;
+}
+int smx_timer_start(smx_sim* s) {
+    if (!s) return fail(SMX_ERR_ARG, "smx_timer_start: null simulator");
+    CK(cudaSetDevice(s->cfg.device));
+    CK(cudaEventRecord(s->ev0, s->stream));
+    return SMX_OK;
+}
+int smx_timer_stop(smx_sim* s, float* ms) {
+    if (!s || !ms) return fail(SMX_ERR_ARG, "smx_timer_stop: null argument");
+    CK(cudaSetDevice(s->cfg.device));
+    CK(cudaEventRecord(s->ev1, s->stream));
+    CK(cudaEventSynchronize(s->ev1));
+    CK(cudaEventElapsedTime(ms, s->ev0, s->ev1));
+    return SMX_OK;
+}
+int64_t smx_launch_count(smx_sim* s) { return s ? s->launches : 0; }
+
+int smx_profile_substep(smx_sim* s, int32_t f, int32_t backward, const char** names, float* ms, int32_t* count) {
+    if (!s || !names || !ms || !count) return fail(SMX_ERR_ARG, "smx_profile_substep: null argument");
+    CK(cudaSetDevice(s->cfg.device));
+    s->marks.clear();
+    s->prof = true;
+    int r = prof_mark(s, "start");
+    if (r == SMX_OK) r = backward ? smx_substep_grad(s, f) : smx_substep(s, f);
+    s->prof = false;
+    if (r != SMX_OK) { for (auto& m : s->marks) cudaEventDestroy(m.second); s->marks.clear(); return r; }
+    CK(cudaStreamSynchronize(s->stream));
+    int n = 0;
+    for (size_t i = 1; i < s->marks.size(); i++) {
+        float t = 0.f;
+        CK(cudaEventElapsedTime(&t, s->marks[i - 1].second, s->marks[i].second));
+        int k = -1;
+        for (int j = 0; j < n; j++) if (!strcmp(names[j], s->marks[i].first)) k = j;
+        if (k < 0) { if (n >= 32) continue; k = n++; names[k] = s->marks[i].first; ms[k] = 0.f; }
+        ms[k] += t;
+    }
+    for (auto& m : s->marks) cudaEventDestroy(m.second);
+    s->marks.clear();
+    *count = n;
+    return SMX_OK;
+}
+
+}  // extern "C"

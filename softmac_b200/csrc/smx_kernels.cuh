@@ -1,0 +1,919 @@
+// smx_kernels.cuh -- hand-written sm_100a kernels of the MLS-MPM substep and of its adjoint.
+//
+// Data layout (all fp32 in HBM):
+//   particle frame  : SoA [24][stride] in get_state column order (x0..2 v3..5 F6..14 C15..23), particles
+//                     physically sorted by block-major cell key, so a warp's 32 particles share ~4 cells
+//   grid            : float4 per node, BLOCK-MAJOR: 4x4x4-node blocks are contiguous 1 KB chunks
+//                     g_in  = (momentum xyz, mass)          target of P2G        (mpm_simulator.py:261-262)
+//                     g_out = (velocity xyz, active flag)   source of G2P        (:296-297, :403-404, :443)
+//                     g_mix = (velocity xyz, active flag)   grid_v_mixed         (:403)
+//                     gg_out / gg_mix: adjoints; grid_grad overwrites gg_out with (d g_in xyz, d mass)
+//   primitives      : pstate [P][T][13] fp32, pgrad [P][T][13] f64, ext_f [P][6] f64, ext_f_grad [P][6] fp32
+//
+// Stage map (reference kernel -> kernel here):
+//   compute_F_tmp + svd + p2g (:125-133, :198-262)           -> k_p2g          (SVD and stress stay in registers)
+//   grid_op / grid_op_mixed1 (:283-297, :396-404)            -> k_grid_op
+//   grid_op_mixed2 + 3 + 4 (:406-443)                        -> k_contact      (gather, forecast contact, scatter)
+//   g2p (:299-318)                                           -> k_g2p
+//   g2p.grad                                                 -> k_g2p_grad
+//   grid_op_mixed4.grad + 3.grad + 2.grad                    -> k_contact_grad
+//   grid_op.grad / grid_op_mixed1.grad                       -> k_grid_grad
+//   p2g.grad + svd_grad + compute_F_tmp.grad (:135-157)      -> k_p2g_grad
+#pragma once
+#include "smx_contact.cuh"
+
+namespace smx {
+
+struct Params {
+    int n;                  // particles
+    long long stride;       // floats between components of a frame
+    int ng, nb;             // grid nodes per axis, blocks per axis (ng/4)
+    float dt, dx, inv_dx, p_mass, mu, lam, cs;      // cs = -dt*p_vol*4*inv_dx^2 (mpm_simulator.py:247)
+    float gx, gy, gz;       // gravity
+    int sticky;             // ground_friction >= 10
+    int material, ptype, ctype, substeps, n_control, np;
+};
+
+struct PrimSet {            // device pointers shared by all kernels that touch primitives
+    const PrimDev* prims;   // [np]
+    const float* pstate;    // [np][T][13]
+    double* pgrad;          // [np][T][13]
+    double* ext_f;          // [np][6]
+    const float* ext_f_grad;// [np][6]
+    int T;
+};
+
+#define SMX_TPB 128
+
+__device__ __forceinline__ void red_add_f4(float4* addr, float a, float b, float c, float d) {
+    // one 16-byte reduction (SASS: REDG.E.ADD.F32x4) instead of four scalar atomics
+    atomicAdd(addr, make_float4(a, b, c, d));
+}
+
+// quadratic B-spline stencil of one particle (mpm_simulator.py:215-217)
+struct Stencil {
+    int ox[3], oy[3], oz[3];    // block-major address contributions per axis offset
+    int bx, by, bz;
+    float fx, fy, fz;
+    float wx[3], wy[3], wz[3];
+};
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+__device__ __forceinline__ uint32_t node_index(int i, int j, int k, int nb) {
+    return (uint32_t)((((i >> 2) * nb + (j >> 2)) * nb + (k >> 2)) * 64 + (((i & 3) << 4) | ((j & 3) << 2) | (k & 3)));
+}
+// sort key of a particle: block-major index of its base cell (the documented variant of SURVEY.md 8a-0)
+__device__ __forceinline__ uint32_t cell_key(float x, float y, float z, float inv_dx, int ng, int nb, int* clamped) {
+    int bx = (int)(x * inv_dx - 0.5f), by = (int)(y * inv_dx - 0.5f), bz = (int)(z * inv_dx - 0.5f);
+    int cx = clampi(bx, 0, ng - 3), cy = clampi(by, 0, ng - 3), cz = clampi(bz, 0, ng - 3);
+    if (clamped) *clamped = (cx != bx) | (cy != by) | (cz != bz);
+    return node_index(cx, cy, cz, nb);
+}
+__device__ __forceinline__ void axis_weights(float f, float* w) {
+    w[0] = 0.5f * (1.5f - f) * (1.5f - f); w[1] = 0.75f - (f - 1.f) * (f - 1.f); w[2] = 0.5f * (f - 0.5f) * (f - 0.5f);
+}
+__device__ __forceinline__ void axis_dweights(float f, float* d) { d[0] = f - 1.5f; d[1] = -2.f * (f - 1.f); d[2] = f - 0.5f; }
+
+__device__ __forceinline__ Stencil make_stencil(float x, float y, float z, const Params& P) {
+    Stencil s;
+    // x*inv_dx (power-of-two scale), -0.5 and the subtraction of the integer base are exact in fp32, so base and
+    // fx equal the reference's f64 values for the same fp32 x
+    float sx = x * P.inv_dx, sy = y * P.inv_dx, sz = z * P.inv_dx;
+    s.bx = clampi((int)(sx - 0.5f), 0, P.ng - 3); s.by = clampi((int)(sy - 0.5f), 0, P.ng - 3); s.bz = clampi((int)(sz - 0.5f), 0, P.ng - 3);
+    s.fx = sx - (float)s.bx; s.fy = sy - (float)s.by; s.fz = sz - (float)s.bz;
+    axis_weights(s.fx, s.wx); axis_weights(s.fy, s.wy); axis_weights(s.fz, s.wz);
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        int i = s.bx + a, j = s.by + a, k = s.bz + a;
+        s.ox[a] = ((i >> 2) * P.nb * P.nb) * 64 + ((i & 3) << 4);
+        s.oy[a] = ((j >> 2) * P.nb) * 64 + ((j & 3) << 2);
+        s.oz[a] = (k >> 2) * 64 + (k & 3);
+    }
+    return s;
+}
+
+// warp-reduce `v` and let lane 0 add it to a double accumulator
+__device__ __forceinline__ void warp_sum_to(double* dst, float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v != 0.f) atomicAdd(dst, (double)v);
+}
+__device__ __forceinline__ void commit_wrench(double* ext_f, V3 bf, V3 r, bool active) {
+    if (!__any_sync(0xffffffffu, active)) return;
+    V3 bt = cross(r, bf);
+    if (!active) { bf = v3(0, 0, 0); bt = v3(0, 0, 0); }
+    warp_sum_to(ext_f + 0, bf.x); warp_sum_to(ext_f + 1, bf.y); warp_sum_to(ext_f + 2, bf.z);
+    warp_sum_to(ext_f + 3, bt.x); warp_sum_to(ext_f + 4, bt.y); warp_sum_to(ext_f + 5, bt.z);
+}
+__device__ __forceinline__ void commit_prim_grad(double* g13, const PrimGrad& G, bool active) {
+    if (!__any_sync(0xffffffffu, active)) return;
+    float v[13] = {G.pos.x, G.pos.y, G.pos.z, G.rot.w, G.rot.x, G.rot.y, G.rot.z, G.v.x, G.v.y, G.v.z, G.w.x, G.w.y, G.w.z};
+#pragma unroll
+    for (int i = 0; i < 13; i++) warp_sum_to(g13 + i, active ? v[i] : 0.f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// material point update (mpm_simulator.py:125-133, 219-248), deviation form.  Et = F_tmp - I.
+// ------------------------------------------------------------------------------------------------
+struct Material {
+    M3 newF;        // F[f+1]
+    M3 D;           // new_F - R (co-rotated) -- accurate small matrix
+    M3 stress;      // before the cs prefactor
+    float J, Jm1;
+    Svd svd;        // valid for co-rotated plastic / elastic
+};
+__device__ __forceinline__ M3 compute_Et(const M3& C, const M3& F, float dt) {
+    // F_tmp - I = (F - I) + dt*C + dt*C*(F - I);  F - I is exact in fp32 for F near I
+    M3 EF = F; EF.m[0] -= 1.f; EF.m[4] -= 1.f; EF.m[8] -= 1.f;
+    M3 CE = mul(C, EF), Et;
+#pragma unroll
+    for (int i = 0; i < 9; i++) Et.m[i] = fmaf(dt, C.m[i] + CE.m[i], EF.m[i]);
+    return Et;
+}
+template <int MAT>
+__device__ __forceinline__ void material_update(const M3& Et, const Params& P, Material& m) {
+    constexpr int model = MAT / 3, ptype = MAT % 3;
+    m.Jm1 = det_minus_one(Et);
+    m.J = 1.f + m.Jm1;
+    M3 Ftmp = Et; Ftmp.m[0] += 1.f; Ftmp.m[4] += 1.f; Ftmp.m[8] += 1.f;
+    if (model == 0) {
+        if (ptype == 2) {                 // liquid: mu == 0, R never contributes; skip the SVD
+            float c = cbrtf(m.J);
+            m.newF = scale(c, m3_identity());
+            m.D = m3_zero();
+        } else {
+            m.svd = svd_dev(Et);
+            M3 R = mulT(m.svd.U, m.svd.V);
+            if (ptype == 0) {             // plastic: clip sigma to [1-2e-3, 1+3e-3] (:226-229)
+                float g0 = fminf(fmaxf(m.svd.e[0], -2e-3f), 3e-3f), g1 = fminf(fmaxf(m.svd.e[1], -2e-3f), 3e-3f),
+                      g2 = fminf(fmaxf(m.svd.e[2], -2e-3f), 3e-3f);
+                m.D = udvt(m.svd.U, g0, g1, g2, m.svd.V);
+                m.newF = add(R, m.D);
+            } else {                      // elastic
+                m.D = udvt(m.svd.U, m.svd.e[0], m.svd.e[1], m.svd.e[2], m.svd.V);
+                m.newF = Ftmp;
+            }
+        }
+        m.stress = scale(2.f * P.mu, mulT(m.D, m.newF));
+        float iso = P.lam * m.J * m.Jm1;
+        m.stress.m[0] += iso; m.stress.m[4] += iso; m.stress.m[8] += iso;
+    } else {                              // neo-Hookean (:237-245)
+        if (ptype == 2) {
+            float sq = sqrtf(m.J);
+            m.newF = m3_zero(); m.newF.m[0] = sq; m.newF.m[4] = sq; m.newF.m[8] = 1.f;
+        } else m.newF = Ftmp;
+        m.stress = scale(P.mu, mulT(m.newF, m.newF));
+        float iso = P.lam * log1pf(m.Jm1) - P.mu;
+        m.stress.m[0] += iso; m.stress.m[4] += iso; m.stress.m[8] += iso;
+    }
+}
+
+__device__ __forceinline__ void load_state(const float* __restrict__ fr, long long stride, int j, V3& x, V3& v, M3& F, M3& C) {
+    x = v3(fr[j], fr[stride + j], fr[2 * stride + j]);
+    v = v3(fr[3 * stride + j], fr[4 * stride + j], fr[5 * stride + j]);
+#pragma unroll
+    for (int i = 0; i < 9; i++) { F.m[i] = fr[(6 + i) * stride + j]; C.m[i] = fr[(15 + i) * stride + j]; }
+}
+
+// particle-contact impulses (collision_type == 1, :203-206) and the control impulse (:209-213)
+__device__ __forceinline__ V3 particle_impulses(const Params& P, const PrimSet& ps, int f, int j, bool live, V3 x, V3 v,
+                                                const int* __restrict__ ctrl_slot, const float* __restrict__ action, bool accumulate) {
+    V3 imp = v3(0, 0, 0);
+    if (P.ctype == 1) {
+        for (int i = 0; i < P.np; i++) {
+            if (!ps.prims[i].enabled) continue;
+            PrimState S = load_prim_state(ps.pstate + ((size_t)i * ps.T + f) * 13);
+            bool act = false; V3 bf = v3(0, 0, 0), r = v3(0, 0, 0);
+            if (live) imp += collide_particle_fwd(ps.prims[i], S, x, v, P.dt, act, bf, r);
+            if (accumulate) commit_wrench(ps.ext_f + 6 * i, bf, r, act);
+        }
+    }
+    if (P.n_control > 0 && live) {
+        int ci = ctrl_slot[j];
+        if (ci >= 0) imp += (6e-4f * P.dt) * v3(action[3 * ci], action[3 * ci + 1], action[3 * ci + 2]);
+    }
+    return imp;
+}
+
+// ------------------------------------------------------------------------------------------------
+// P2G: F_tmp, SVD, plasticity, stress, APIC scatter.  One thread per particle slot.
+// ------------------------------------------------------------------------------------------------
+template <int MAT>
+__global__ void __launch_bounds__(SMX_TPB) k_p2g(Params P, PrimSet ps, int f, const float* __restrict__ fin, float* __restrict__ fout,
+                                                 float4* __restrict__ g_in, const int* __restrict__ ctrl_slot,
+                                                 const float* __restrict__ action, int accumulate) {
+    int j = blockIdx.x * SMX_TPB + threadIdx.x;
+    bool live = j < P.n;
+    int jj = live ? j : P.n - 1;
+    V3 x, v; M3 F, C;
+    load_state(fin, P.stride, jj, x, v, F, C);
+    V3 imp = particle_impulses(P, ps, f, jj, live, x, v, ctrl_slot, action, accumulate != 0);
+    if (!live) return;
+    Material m;
+    material_update<MAT>(compute_Et(C, F, P.dt), P, m);
+    if (fout) {
+#pragma unroll
+        for (int i = 0; i < 9; i++) fout[(6 + i) * P.stride + j] = m.newF.m[i];
+    }
+    // affine' = (cs*stress + p_mass*C) * dx ; value(node) = w * (q0 + affine' * offset), q0 = p_mass*v + imp - affine' * fx
+    M3 A;
+#pragma unroll
+    for (int i = 0; i < 9; i++) A.m[i] = (P.cs * m.stress.m[i] + P.p_mass * C.m[i]) * P.dx;
+    Stencil s = make_stencil(x.x, x.y, x.z, P);
+    V3 q0 = P.p_mass * v + imp - mulv(A, v3(s.fx, s.fy, s.fz));
+    V3 c0 = v3(A.m[0], A.m[3], A.m[6]), c1 = v3(A.m[1], A.m[4], A.m[7]), c2 = v3(A.m[2], A.m[5], A.m[8]);
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        V3 qa = q0 + (float)a * c0;
+#pragma unroll
+        for (int b = 0; b < 3; b++) {
+            V3 qb = qa + (float)b * c1;
+            float wab = s.wx[a] * s.wy[b];
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                V3 q = qb + (float)c * c2;
+                float w = wab * s.wz[c];
+                red_add_f4(g_in + (s.ox[a] + s.oy[b] + s.oz[c]), w * q.x, w * q.y, w * q.z, w * P.p_mass);
+            }
+        }
+    }
+}
+
+// boundary_condition (mpm_simulator.py:268-281); mask bit d cleared where component d was zeroed
+__device__ __forceinline__ V3 boundary_condition(int i, int j, int k, V3 v, const Params& P, int& mask) {
+    const int bound = 3;
+    mask = 7;
+    if (i < bound && v.x < 0.f) { v.x = 0.f; mask &= ~1; }
+    if (i > P.ng - bound && v.x > 0.f) { v.x = 0.f; mask &= ~1; }
+    if (j < bound && v.y < 0.f) { v.y = 0.f; mask &= ~2; }
+    if (j > P.ng - bound && v.y > 0.f) { v.y = 0.f; mask &= ~2; }
+    if (j < bound && P.sticky) { v = v3(0, 0, 0); mask = 0; }
+    if (k < bound && v.z < 0.f) { v.z = 0.f; mask &= ~4; }
+    if (k > P.ng - bound && v.z > 0.f) { v.z = 0.f; mask &= ~4; }
+    return v;
+}
+__device__ __forceinline__ void node_coords(uint32_t node, int nb, int& i, int& j, int& k) {
+    uint32_t b = node >> 6, l = node & 63;
+    int bk = b % nb, bj = (b / nb) % nb, bi = b / (nb * nb);
+    i = bi * 4 + (l >> 4); j = bj * 4 + ((l >> 2) & 3); k = bk * 4 + (l & 3);
+}
+
+// ------------------------------------------------------------------------------------------------
+// grid update: momentum -> velocity, gravity, (grid contact), boundary conditions.
+// blocks == nullptr: dense sweep; else one 64-node grid block per 64 threads from the active list.
+// Also re-zeroes nothing: inactive nodes are written as zero so g_out / g_mix never need a memset.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_grid_op(Params P, PrimSet ps, int f, const uint32_t* __restrict__ blocks, const int* __restrict__ nblocks,
+                                                 const float4* __restrict__ g_in, float4* __restrict__ g_out, float4* __restrict__ g_mix,
+                                                 int accumulate) {
+    int total = blocks ? *nblocks : P.nb * P.nb * P.nb;
+    for (int bi = blockIdx.x * 4 + (threadIdx.x >> 6); bi < total; bi += gridDim.x * 4) {
+        uint32_t node = (blocks ? blocks[bi] : (uint32_t)bi) * 64u + (threadIdx.x & 63);
+        float4 g = g_in[node];
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        bool on = g.w > 1e-10f;
+        int i, j, k;
+        node_coords(node, P.nb, i, j, k);
+        V3 v = v3(0, 0, 0);
+        if (on) {
+            float inv = 1.f / g.w;
+            v = v3(inv * g.x + P.dt * P.gx, inv * g.y + P.dt * P.gy, inv * g.z + P.dt * P.gz);
+        }
+        if (P.ctype == 0) {
+            V3 gp = v3(i * P.dx, j * P.dx, k * P.dx);
+            for (int q = 0; q < P.np; q++) {
+                if (!ps.prims[q].enabled) continue;
+                PrimState S = load_prim_state(ps.pstate + ((size_t)q * ps.T + f) * 13);
+                bool act = false; V3 r = v3(0, 0, 0), vin = v;
+                if (on) v = collide_grid_fwd(ps.prims[q], S, gp, v, act, r);
+                if (accumulate) commit_wrench(ps.ext_f + 6 * q, (g.w / P.dt) * (vin - v), r, act);
+            }
+        }
+        if (on) {
+            int mask;
+            v = boundary_condition(i, j, k, v, P, mask);
+            o = make_float4(v.x, v.y, v.z, 1.f);
+        }
+        g_out[node] = o;
+        if (g_mix) g_mix[node] = o;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// forecast contact: gather v_tmp from g_mix, chain collide_mixed over the enabled primitives,
+// scatter -2 w (v_tmp - v_tgt) into g_out where the node is active; reduce the wrench per body.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SMX_TPB) k_contact(Params P, PrimSet ps, int f, float life, const float* __restrict__ fin,
+                                                     const float4* __restrict__ g_mix, float4* __restrict__ g_out, int accumulate) {
+    int j = blockIdx.x * SMX_TPB + threadIdx.x;
+    bool live = j < P.n;
+    int jj = live ? j : P.n - 1;
+    V3 x = v3(fin[jj], fin[P.stride + jj], fin[2 * P.stride + jj]);
+    // cheap reject: is the particle within reach of any enabled primitive?
+    bool near = false;
+    for (int i = 0; i < P.np; i++) {
+        if (!ps.prims[i].enabled) continue;
+        PrimState S = load_prim_state(ps.pstate + ((size_t)i * ps.T + f) * 13);
+        near |= live && (prim_sdf(ps.prims[i], S, x) <= 5e-3f);
+    }
+    if (!__any_sync(0xffffffffu, near)) return;
+    Stencil s = make_stencil(x.x, x.y, x.z, P);
+    V3 vtmp = v3(0, 0, 0);
+    uint32_t onmask = 0;
+    if (near) {
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+            for (int b = 0; b < 3; b++)
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    float4 g = g_mix[s.ox[a] + s.oy[b] + s.oz[c]];
+                    float w = s.wx[a] * s.wy[b] * s.wz[c];
+                    vtmp.x = fmaf(w, g.x, vtmp.x); vtmp.y = fmaf(w, g.y, vtmp.y); vtmp.z = fmaf(w, g.z, vtmp.z);
+                    if (g.w > 0.f) onmask |= 1u << (a * 9 + b * 3 + c);
+                }
+    }
+    V3 vt = vtmp;
+    for (int i = 0; i < P.np; i++) {
+        if (!ps.prims[i].enabled) continue;
+        PrimState S = load_prim_state(ps.pstate + ((size_t)i * ps.T + f) * 13);
+        CmTape T; T.active = false; T.r = v3(0, 0, 0);
+        V3 vin = vt;
+        if (near) vt = collide_mixed_fwd(ps.prims[i], S, x, vin, P.dt, life, T);
+        if (accumulate) commit_wrench(ps.ext_f + 6 * i, (P.p_mass / P.dt) * (vin - vt), T.r, near && T.active);
+    }
+    if (!near) return;
+    V3 d = vtmp - vt;
+    if (d.x == 0.f && d.y == 0.f && d.z == 0.f) return;
+    d = -2.f * d;
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int b = 0; b < 3; b++)
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+                if (onmask & (1u << (a * 9 + b * 3 + c))) {
+                    float w = s.wx[a] * s.wy[b] * s.wz[c];
+                    red_add_f4(g_out + (s.ox[a] + s.oy[b] + s.oz[c]), w * d.x, w * d.y, w * d.z, 0.f);
+                }
+}
+
+// ------------------------------------------------------------------------------------------------
+// G2P: gather v, C (APIC) and advect.  Writes x, v, C of frame f+1.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SMX_TPB) k_g2p(Params P, const float* __restrict__ fin, float* __restrict__ fout, const float4* __restrict__ g_out) {
+    int j = blockIdx.x * SMX_TPB + threadIdx.x;
+    if (j >= P.n) return;
+    V3 x = v3(fin[j], fin[P.stride + j], fin[2 * P.stride + j]);
+    Stencil s = make_stencil(x.x, x.y, x.z, P);
+    V3 nv = v3(0, 0, 0);
+    M3 B = m3_zero();       // sum w g (x) offset
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int b = 0; b < 3; b++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                float4 g = g_out[s.ox[a] + s.oy[b] + s.oz[c]];
+                float w = s.wx[a] * s.wy[b] * s.wz[c];
+                V3 wg = v3(w * g.x, w * g.y, w * g.z);
+                nv += wg;
+                B.m[0] += wg.x * a; B.m[1] += wg.x * b; B.m[2] += wg.x * c;
+                B.m[3] += wg.y * a; B.m[4] += wg.y * b; B.m[5] += wg.y * c;
+                B.m[6] += wg.z * a; B.m[7] += wg.z * b; B.m[8] += wg.z * c;
+            }
+    float k4 = 4.f * P.inv_dx;
+    float f3[3] = {s.fx, s.fy, s.fz}, n3[3] = {nv.x, nv.y, nv.z};
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) fout[(15 + 3 * r + c) * P.stride + j] = k4 * (B.m[3 * r + c] - n3[r] * f3[c]);
+    fout[3 * P.stride + j] = nv.x; fout[4 * P.stride + j] = nv.y; fout[5 * P.stride + j] = nv.z;
+    fout[j] = x.x + P.dt * nv.x; fout[P.stride + j] = x.y + P.dt * nv.y; fout[2 * P.stride + j] = x.z + P.dt * nv.z;
+}
+
+// ------------------------------------------------------------------------------------------------
+// adjoint of G2P: scatter d g_out, accumulate d x through the weights.
+//   ain  = adjoint of frame f+1 (x 0..2, v 3..5, C 15..23), aout = adjoint of frame f (x written here)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SMX_TPB) k_g2p_grad(Params P, const float* __restrict__ fin, const float* __restrict__ ain,
+                                                      float* __restrict__ aout, const float4* __restrict__ g_out, float4* __restrict__ gg_out) {
+    int j = blockIdx.x * SMX_TPB + threadIdx.x;
+    if (j >= P.n) return;
+    V3 x = v3(fin[j], fin[P.stride + j], fin[2 * P.stride + j]);
+    V3 gx1 = v3(ain[j], ain[P.stride + j], ain[2 * P.stride + j]);
+    V3 gnv = v3(ain[3 * P.stride + j], ain[4 * P.stride + j], ain[5 * P.stride + j]) + P.dt * gx1;
+    M3 gC;
+#pragma unroll
+    for (int i = 0; i < 9; i++) gC.m[i] = ain[(15 + i) * P.stride + j];
+    Stencil s = make_stencil(x.x, x.y, x.z, P);
+    float dwx[3], dwy[3], dwz[3];
+    axis_dweights(s.fx, dwx); axis_dweights(s.fy, dwy); axis_dweights(s.fz, dwz);
+    float k4 = 4.f * P.inv_dx;
+    // d g_out(node) = w * (gnv + k4 * gC * (offset - fx)) = w * (q0 + k4*gC*offset)
+    M3 K = scale(k4, gC);
+    V3 q0 = gnv - mulv(K, v3(s.fx, s.fy, s.fz));
+    V3 c0 = v3(K.m[0], K.m[3], K.m[6]), c1 = v3(K.m[1], K.m[4], K.m[7]), c2 = v3(K.m[2], K.m[5], K.m[8]);
+    V3 gfx = v3(0, 0, 0), S0 = v3(0, 0, 0);     // S0 = sum w * g (for d dpos)
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        V3 qa = q0 + (float)a * c0;
+#pragma unroll
+        for (int b = 0; b < 3; b++) {
+            V3 qb = qa + (float)b * c1;
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                V3 q = qb + (float)c * c2;
+                int node = s.ox[a] + s.oy[b] + s.oz[c];
+                float4 g = g_out[node];
+                float w = s.wx[a] * s.wy[b] * s.wz[c];
+                red_add_f4(gg_out + node, w * q.x, w * q.y, w * q.z, 0.f);
+                float gw = g.x * q.x + g.y * q.y + g.z * q.z;          // d weight
+                gfx.x = fmaf(gw, dwx[a] * s.wy[b] * s.wz[c], gfx.x);
+                gfx.y = fmaf(gw, s.wx[a] * dwy[b] * s.wz[c], gfx.y);
+                gfx.z = fmaf(gw, s.wx[a] * s.wy[b] * dwz[c], gfx.z);
+                S0.x = fmaf(w, g.x, S0.x); S0.y = fmaf(w, g.y, S0.y); S0.z = fmaf(w, g.z, S0.z);
+            }
+        }
+    }
+    // d dpos = k4 * w * gC^T g  ->  d fx -= sum = K^T S0
+    gfx -= Tmulv(K, S0);
+    aout[j] = gx1.x + P.inv_dx * gfx.x; aout[P.stride + j] = gx1.y + P.inv_dx * gfx.y; aout[2 * P.stride + j] = gx1.z + P.inv_dx * gfx.z;
+}
+
+// ------------------------------------------------------------------------------------------------
+// adjoint of the forecast contact (mixed4.grad, mixed3.grad, mixed2.grad fused).
+// Particles that are not within reach of a primitive contribute exactly zero and exit early.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SMX_TPB) k_contact_grad(Params P, PrimSet ps, int f, float life, const float* __restrict__ fin,
+                                                          float* __restrict__ aout, const float4* __restrict__ g_mix,
+                                                          const float4* __restrict__ gg_out, float4* __restrict__ gg_mix) {
+    int j = blockIdx.x * SMX_TPB + threadIdx.x;
+    bool live = j < P.n;
+    int jj = live ? j : P.n - 1;
+    V3 x = v3(fin[jj], fin[P.stride + jj], fin[2 * P.stride + jj]);
+    bool near = false;
+    for (int i = 0; i < P.np; i++) {
+        if (!ps.prims[i].enabled) continue;
+        PrimState S = load_prim_state(ps.pstate + ((size_t)i * ps.T + f) * 13);
+        near |= live && (prim_sdf(ps.prims[i], S, x) <= 5e-3f);
+    }
+    if (!__any_sync(0xffffffffu, near)) return;
+    Stencil s = make_stencil(x.x, x.y, x.z, P);
+    float dwx[3], dwy[3], dwz[3];
+    axis_dweights(s.fx, dwx); axis_dweights(s.fy, dwy); axis_dweights(s.fz, dwz);
+    V3 vtmp = v3(0, 0, 0);
+    uint32_t onmask = 0;
+    if (near) {
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+            for (int b = 0; b < 3; b++)
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    float4 g = g_mix[s.ox[a] + s.oy[b] + s.oz[c]];
+                    float w = s.wx[a] * s.wy[b] * s.wz[c];
+                    vtmp.x = fmaf(w, g.x, vtmp.x); vtmp.y = fmaf(w, g.y, vtmp.y); vtmp.z = fmaf(w, g.z, vtmp.z);
+                    if (g.w > 0.f) onmask |= 1u << (a * 9 + b * 3 + c);
+                }
+    }
+    // forward chain with tape
+    V3 vin[SMX_MAXP], vout[SMX_MAXP];
+    CmTape tape[SMX_MAXP];
+    int which[SMX_MAXP], nq = 0;
+    V3 vt = vtmp;
+    for (int i = 0; i < P.np; i++) {
+        if (!ps.prims[i].enabled) continue;
+        PrimState S = load_prim_state(ps.pstate + ((size_t)i * ps.T + f) * 13);
+        vin[nq] = vt; tape[nq].active = false;
+        if (near) vt = collide_mixed_fwd(ps.prims[i], S, x, vt, P.dt, life, tape[nq]);
+        vout[nq] = vt; which[nq] = i; nq++;
+    }
+    // mixed4.grad: d(v_tmp - v_tgt) = -2 sum_on w * d g_out ; d weight = -2 d g_out . (v_tmp - v_tgt)
+    V3 d = vtmp - vt, gd = v3(0, 0, 0), gfx = v3(0, 0, 0);
+    if (near) {
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+            for (int b = 0; b < 3; b++)
+#pragma unroll
+                for (int c = 0; c < 3; c++)
+                    if (onmask & (1u << (a * 9 + b * 3 + c))) {
+                        float4 go = gg_out[s.ox[a] + s.oy[b] + s.oz[c]];
+                        float w = s.wx[a] * s.wy[b] * s.wz[c];
+                        gd.x = fmaf(-2.f * w, go.x, gd.x); gd.y = fmaf(-2.f * w, go.y, gd.y); gd.z = fmaf(-2.f * w, go.z, gd.z);
+                        float gw = -2.f * (go.x * d.x + go.y * d.y + go.z * d.z);
+                        gfx.x = fmaf(gw, dwx[a] * s.wy[b] * s.wz[c], gfx.x);
+                        gfx.y = fmaf(gw, s.wx[a] * dwy[b] * s.wz[c], gfx.y);
+                        gfx.z = fmaf(gw, s.wx[a] * s.wy[b] * dwz[c], gfx.z);
+                    }
+    }
+    // mixed3.grad: chain in reverse
+    V3 g = -gd;             // d v_tgt
+    V3 gxc = v3(0, 0, 0);   // d x from the contact model
+    for (int a = nq - 1; a >= 0; a--) {
+        int i = which[a];
+        PrimState S = load_prim_state(ps.pstate + ((size_t)i * ps.T + f) * 13);
+        PrimGrad G = prim_grad_zero();
+        V3 gin = v3(0, 0, 0);
+        bool act = near && tape[a].active;
+        if (near) collide_mixed_adj(ps.prims[i], S, x, vin[a], vout[a], P.p_mass, P.dt, life, tape[a], g, ps.ext_f_grad + 6 * i, gxc, gin, G);
+        commit_prim_grad(ps.pgrad + ((size_t)i * ps.T + f) * 13, G, act);
+        g = gin;
+    }
+    if (!near) return;
+    V3 gvtmp = gd + g;      // d v_tmp
+    // mixed2.grad: scatter w * d v_tmp into d g_mix ; d weight = g_mix . d v_tmp
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int b = 0; b < 3; b++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                int node = s.ox[a] + s.oy[b] + s.oz[c];
+                float4 gm = g_mix[node];
+                float w = s.wx[a] * s.wy[b] * s.wz[c];
+                red_add_f4(gg_mix + node, w * gvtmp.x, w * gvtmp.y, w * gvtmp.z, 0.f);
+                float gw = gm.x * gvtmp.x + gm.y * gvtmp.y + gm.z * gvtmp.z;
+                gfx.x = fmaf(gw, dwx[a] * s.wy[b] * s.wz[c], gfx.x);
+                gfx.y = fmaf(gw, s.wx[a] * dwy[b] * s.wz[c], gfx.y);
+                gfx.z = fmaf(gw, s.wx[a] * s.wy[b] * dwz[c], gfx.z);
+            }
+    aout[j] += gxc.x + P.inv_dx * gfx.x; aout[P.stride + j] += gxc.y + P.inv_dx * gfx.y; aout[2 * P.stride + j] += gxc.z + P.inv_dx * gfx.z;
+}
+
+// ------------------------------------------------------------------------------------------------
+// adjoint of the grid update (grid_op.grad / grid_op_mixed1.grad): gg_out <- (d g_in xyz, d mass) in place.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_grid_grad(Params P, PrimSet ps, int f, const uint32_t* __restrict__ blocks, const int* __restrict__ nblocks,
+                                                   const float4* __restrict__ g_in, float4* __restrict__ gg_out, const float4* __restrict__ gg_mix) {
+    int total = blocks ? *nblocks : P.nb * P.nb * P.nb;
+    for (int bi = blockIdx.x * 4 + (threadIdx.x >> 6); bi < total; bi += gridDim.x * 4) {
+        uint32_t node = (blocks ? blocks[bi] : (uint32_t)bi) * 64u + (threadIdx.x & 63);
+        float4 g = g_in[node];
+        bool on = g.w > 1e-10f;
+        int i, j, k;
+        node_coords(node, P.nb, i, j, k);
+        float4 go = gg_out[node];
+        V3 gv = v3(go.x, go.y, go.z);
+        if (gg_mix) { float4 gm = gg_mix[node]; gv += v3(gm.x, gm.y, gm.z); }
+        float inv = on ? 1.f / g.w : 0.f;
+        V3 v = v3(inv * g.x + P.dt * P.gx, inv * g.y + P.dt * P.gy, inv * g.z + P.dt * P.gz);
+        float gmass = 0.f;
+        if (P.ctype == 0) {
+            V3 gp = v3(i * P.dx, j * P.dx, k * P.dx);
+            V3 vins[SMX_MAXP]; int which[SMX_MAXP], nq = 0;
+            for (int q = 0; q < P.np; q++) {
+                if (!ps.prims[q].enabled) continue;
+                PrimState S = load_prim_state(ps.pstate + ((size_t)q * ps.T + f) * 13);
+                vins[nq] = v; which[nq++] = q;
+                bool act; V3 r;
+                if (on) v = collide_grid_fwd(ps.prims[q], S, gp, v, act, r);
+            }
+            int mask = 7;
+            if (on) boundary_condition(i, j, k, v, P, mask);
+            gv = v3((mask & 1) ? gv.x : 0.f, (mask & 2) ? gv.y : 0.f, (mask & 4) ? gv.z : 0.f);
+            for (int a = nq - 1; a >= 0; a--) {
+                int q = which[a];
+                PrimState S = load_prim_state(ps.pstate + ((size_t)q * ps.T + f) * 13);
+                PrimGrad G = prim_grad_zero();
+                V3 gin = v3(0, 0, 0);
+                if (on) collide_grid_adj(ps.prims[q], S, gp, vins[a], P.dt, g.w, gv, ps.ext_f_grad + 6 * q, gin, gmass, G);
+                commit_prim_grad(ps.pgrad + ((size_t)q * ps.T + f) * 13, G, on);
+                gv = gin;
+            }
+        } else {
+            int mask = 7;
+            if (on) boundary_condition(i, j, k, v, P, mask);
+            gv = v3((mask & 1) ? gv.x : 0.f, (mask & 2) ? gv.y : 0.f, (mask & 4) ? gv.z : 0.f);
+        }
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (on) {
+            float dotv = g.x * gv.x + g.y * gv.y + g.z * gv.z;
+            o = make_float4(inv * gv.x, inv * gv.y, inv * gv.z, gmass - dotv * inv * inv);
+        }
+        gg_out[node] = o;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// adjoint of P2G + svd_grad + compute_F_tmp.grad.  gg = (d g_in xyz, d mass) from k_grid_grad.
+//   ain  = adjoint of frame f+1 (only F, comps 6..14, is read here)
+//   aout = adjoint of frame f: x holds the partial from g2p/contact grads; v, F, C are written
+// ------------------------------------------------------------------------------------------------
+template <int MAT>
+__global__ void __launch_bounds__(SMX_TPB) k_p2g_grad(Params P, PrimSet ps, int f, const float* __restrict__ fin, const float* __restrict__ ain,
+                                                      float* __restrict__ aout, const float4* __restrict__ gg, const int* __restrict__ ctrl_slot,
+                                                      const float* __restrict__ action, double* __restrict__ action_grad) {
+    constexpr int model = MAT / 3, ptype = MAT % 3;
+    int j = blockIdx.x * SMX_TPB + threadIdx.x;
+    bool live = j < P.n;
+    int jj = live ? j : P.n - 1;
+    V3 x, v; M3 F, C;
+    load_state(fin, P.stride, jj, x, v, F, C);
+    V3 imp = particle_impulses(P, ps, f, jj, live, x, v, ctrl_slot, action, false);
+    Material m;
+    M3 Et = compute_Et(C, F, P.dt);
+    material_update<MAT>(Et, P, m);
+    M3 A;
+#pragma unroll
+    for (int i = 0; i < 9; i++) A.m[i] = (P.cs * m.stress.m[i] + P.p_mass * C.m[i]) * P.dx;
+    Stencil s = make_stencil(x.x, x.y, x.z, P);
+    float dwx[3], dwy[3], dwz[3];
+    axis_dweights(s.fx, dwx); axis_dweights(s.fy, dwy); axis_dweights(s.fz, dwz);
+    V3 q0 = P.p_mass * v + imp - mulv(A, v3(s.fx, s.fy, s.fz));
+    V3 c0 = v3(A.m[0], A.m[3], A.m[6]), c1 = v3(A.m[1], A.m[4], A.m[7]), c2 = v3(A.m[2], A.m[5], A.m[8]);
+    V3 S0 = v3(0, 0, 0), gfx = v3(0, 0, 0);
+    M3 S1 = m3_zero();      // sum w * g (x) offset
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        V3 qa = q0 + (float)a * c0;
+#pragma unroll
+        for (int b = 0; b < 3; b++) {
+            V3 qb = qa + (float)b * c1;
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                V3 q = qb + (float)c * c2;      // value scattered to this node, per unit weight
+                float4 g = gg[s.ox[a] + s.oy[b] + s.oz[c]];
+                float w = s.wx[a] * s.wy[b] * s.wz[c];
+                float gw = g.x * q.x + g.y * q.y + g.z * q.z + g.w * P.p_mass;
+                gfx.x = fmaf(gw, dwx[a] * s.wy[b] * s.wz[c], gfx.x);
+                gfx.y = fmaf(gw, s.wx[a] * dwy[b] * s.wz[c], gfx.y);
+                gfx.z = fmaf(gw, s.wx[a] * s.wy[b] * dwz[c], gfx.z);
+                V3 wg = v3(w * g.x, w * g.y, w * g.z);
+                S0 += wg;
+                S1.m[0] += wg.x * a; S1.m[1] += wg.x * b; S1.m[2] += wg.x * c;
+                S1.m[3] += wg.y * a; S1.m[4] += wg.y * b; S1.m[5] += wg.y * c;
+                S1.m[6] += wg.z * a; S1.m[7] += wg.z * b; S1.m[8] += wg.z * c;
+            }
+        }
+    }
+    // d affine = sum w g (x) dpos = dx * (S1 - S0 (x) fx);  d fx -= dx * affine^T S0 = A^T S0
+    gfx -= Tmulv(A, S0);
+    M3 gaff;
+    {
+        float f3[3] = {s.fx, s.fy, s.fz}, s3[3] = {S0.x, S0.y, S0.z};
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) gaff.m[3 * r + c] = P.dx * (S1.m[3 * r + c] - s3[r] * f3[c]);
+    }
+    V3 gx = P.inv_dx * gfx, gv = P.p_mass * S0, gimp = S0;
+    M3 gC = scale(P.p_mass, gaff);
+    M3 gstress = scale(P.cs, gaff);
+    M3 gnewF;
+#pragma unroll
+    for (int i = 0; i < 9; i++) gnewF.m[i] = ain[(6 + i) * P.stride + jj];
+    float tr = trace(gstress), gJ = 0.f;
+    M3 gFtmp = m3_zero();
+    if (model == 0) {
+        gJ = P.lam * (2.f * m.J - 1.f) * tr;
+        if (ptype == 2) {
+            gJ += (1.f / 3.f) * cbrtf(m.J) / m.J * trace(gnewF);       // d/dJ J^(1/3); mu == 0 so R carries nothing
+        } else {
+            // stress = 2 mu D newF^T, D = newF - R
+            M3 gA = scale(2.f * P.mu, mul(gstress, m.newF));
+            gnewF = add(gnewF, add(scale(2.f * P.mu, Tmul(gstress, m.D)), gA));
+            // folded svd_grad (mpm_simulator.py:140-157): see DESIGN.md "SVD adjoint in divided-difference form"
+            const M3 &U = m.svd.U, &V = m.svd.V;
+            const float* e = m.svd.e;
+            M3 M2 = scale(-1.f, mul(Tmul(U, gA), V));      // U^T (d R) V, d R = -gA
+            M3 inner = m3_zero();
+            if (ptype == 0) {
+                M3 M1 = mul(Tmul(U, gnewF), V);
+                float g3[3];
+#pragma unroll
+                for (int i = 0; i < 3; i++) g3[i] = fminf(fmaxf(e[i], -2e-3f), 3e-3f);
+#pragma unroll
+                for (int i = 0; i < 3; i++) {
+                    // min(max(sig, lo), hi): gradient reaches sig iff lo < sig and max(sig, lo) < hi
+                    inner.m[4 * i] = (e[i] > -2e-3f && e[i] < 3e-3f) ? M1.m[4 * i] : 0.f;
+#pragma unroll
+                    for (int jx = 0; jx < 3; jx++) {
+                        if (jx == i) continue;
+                        float de = e[jx] - e[i], dg = g3[jx] - g3[i];
+                        float K = 1.f / clamp_ref(de * (2.f + e[i] + e[jx]));
+                        float P1 = dg + de + (g3[jx] * e[jx] - g3[i] * e[i]);
+                        float Q1 = dg - de + (g3[jx] * e[i] - g3[i] * e[jx]);
+                        inner.m[3 * i + jx] = K * (M1.m[3 * i + jx] * P1 + M1.m[3 * jx + i] * Q1 + (M2.m[3 * i + jx] - M2.m[3 * jx + i]) * de);
+                    }
+                }
+            } else {
+                gFtmp = gnewF;      // elastic: new_F = F_tmp
+#pragma unroll
+                for (int i = 0; i < 3; i++)
+#pragma unroll
+                    for (int jx = 0; jx < 3; jx++) {
+                        if (jx == i) continue;
+                        float de = e[jx] - e[i];
+                        float K = 1.f / clamp_ref(de * (2.f + e[i] + e[jx]));
+                        inner.m[3 * i + jx] = K * (M2.m[3 * i + jx] - M2.m[3 * jx + i]) * de;
+                    }
+            }
+            gFtmp = add(gFtmp, mulT(mul(U, inner), V));
+        }
+    } else {
+        M3 sym;
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) sym.m[3 * r + c] = gstress.m[3 * r + c] + gstress.m[3 * c + r];
+        gnewF = add(gnewF, scale(P.mu, mul(sym, m.newF)));
+        gJ = P.lam / m.J * tr;
+        if (ptype == 2) gJ += (gnewF.m[0] + gnewF.m[4]) / (2.f * sqrtf(m.J));
+        else gFtmp = gnewF;
+    }
+    {
+        M3 Ftmp = Et; Ftmp.m[0] += 1.f; Ftmp.m[4] += 1.f; Ftmp.m[8] += 1.f;
+        gFtmp = add(gFtmp, scale(gJ, cofactor(Ftmp)));
+    }
+    // compute_F_tmp.grad: dC += dt * gFtmp F^T ; dF = (I + dt C)^T gFtmp
+    gC = add(gC, scale(P.dt, mulT(gFtmp, F)));
+    M3 Aq = scale(P.dt, C); Aq.m[0] += 1.f; Aq.m[4] += 1.f; Aq.m[8] += 1.f;
+    M3 gF = Tmul(Aq, gFtmp);
+    // control and particle-contact adjoints
+    if (P.n_control > 0 && live) {
+        int ci = ctrl_slot[jj];
+        if (ci >= 0) {
+            float k = 6e-4f * P.dt;
+            atomicAdd(action_grad + 3 * ci, (double)(k * gimp.x)); atomicAdd(action_grad + 3 * ci + 1, (double)(k * gimp.y));
+            atomicAdd(action_grad + 3 * ci + 2, (double)(k * gimp.z));
+        }
+    }
+    if (P.ctype == 1) {
+        for (int i = P.np - 1; i >= 0; i--) {
+            if (!ps.prims[i].enabled) continue;
+            PrimState S = load_prim_state(ps.pstate + ((size_t)i * ps.T + f) * 13);
+            PrimGrad G = prim_grad_zero();
+            if (live) collide_particle_adj(ps.prims[i], S, x, v, P.dt, gimp, ps.ext_f_grad + 6 * i, gx, gv, G);
+            commit_prim_grad(ps.pgrad + ((size_t)i * ps.T + f) * 13, G, live);
+        }
+    }
+    if (!live) return;
+    aout[j] += gx.x; aout[P.stride + j] += gx.y; aout[2 * P.stride + j] += gx.z;
+    aout[3 * P.stride + j] = gv.x; aout[4 * P.stride + j] = gv.y; aout[5 * P.stride + j] = gv.z;
+#pragma unroll
+    for (int i = 0; i < 9; i++) { aout[(6 + i) * P.stride + j] = gF.m[i]; aout[(15 + i) * P.stride + j] = gC.m[i]; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// small kernels: keys, permutation, IO, seeds, kinematics
+// ------------------------------------------------------------------------------------------------
+__global__ void k_keys(Params P, const float* __restrict__ fr, uint32_t* __restrict__ keys, uint32_t* __restrict__ iota, unsigned long long* counters) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= P.n) return;
+    int clamped;
+    keys[j] = cell_key(fr[j], fr[P.stride + j], fr[2 * P.stride + j], P.inv_dx, P.ng, P.nb, &clamped);
+    if (iota) iota[j] = j;
+    if (clamped && counters) atomicAdd(counters, 1ull);
+}
+// dst[c][j] = src[c][idx[j]] for all 24 components
+__global__ void k_gather_frame(int n, long long stride, const float* __restrict__ src, float* __restrict__ dst, const uint32_t* __restrict__ idx) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    uint32_t i = idx[j];
+#pragma unroll
+    for (int c = 0; c < 24; c++) dst[c * stride + j] = src[c * stride + i];
+}
+// dst[c][idx[j]] = src[c][j]  (inverse of the above; used to carry an adjoint back across a re-sort)
+__global__ void k_scatter_frame(int n, long long stride, const float* __restrict__ src, float* __restrict__ dst, const uint32_t* __restrict__ idx) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    uint32_t i = idx[j];
+#pragma unroll
+    for (int c = 0; c < 24; c++) dst[c * stride + i] = src[c * stride + j];
+}
+__global__ void k_compose_perm(int n, const uint32_t* __restrict__ old_perm, const uint32_t* __restrict__ idx, uint32_t* __restrict__ new_perm) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) new_perm[j] = old_perm ? old_perm[idx[j]] : idx[j];
+}
+// staging (n, ncomp) AoS in particle-id order  <->  frame SoA in storage order
+__global__ void k_upload(int n, long long stride, const float* __restrict__ aos, int ncomp, int c0, float* __restrict__ fr, const uint32_t* __restrict__ perm, int accumulate) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    uint32_t p = perm ? perm[j] : j;
+    for (int c = 0; c < ncomp; c++) {
+        float v = aos[(size_t)p * ncomp + c];
+        if (accumulate) fr[(c0 + c) * stride + j] += v; else fr[(c0 + c) * stride + j] = v;
+    }
+}
+__global__ void k_download(int n, long long stride, float* __restrict__ aos, int ncomp, int c0, const float* __restrict__ fr, const uint32_t* __restrict__ perm) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    uint32_t p = perm ? perm[j] : j;
+    for (int c = 0; c < ncomp; c++) aos[(size_t)p * ncomp + c] = fr[(c0 + c) * stride + j];
+}
+__global__ void k_permute_i32(int n, const int* __restrict__ src, int* __restrict__ dst, const uint32_t* __restrict__ perm) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) dst[j] = src[perm ? perm[j] : j];
+}
+__global__ void k_axpy(long long n, float* __restrict__ y, const float* __restrict__ x) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] += x[i];
+}
+// block-major grid -> (i,j,k) linear order, for tests
+__global__ void k_grid_linear(int ng, int nb, const float4* __restrict__ g, float4* __restrict__ out) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ng * ng * ng) return;
+    int k = t % ng, j = (t / ng) % ng, i = t / (ng * ng);
+    out[t] = g[node_index(i, j, k, nb)];
+}
+// active-block bookkeeping: flag every 4^3 block a particle's stencil (+- margin cells) can touch
+__global__ void k_mark_blocks(Params P, const float* __restrict__ fr, int margin, uint32_t* __restrict__ flags) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= P.n) return;
+    int b[3];
+    b[0] = clampi((int)(fr[j] * P.inv_dx - 0.5f), 0, P.ng - 3);
+    b[1] = clampi((int)(fr[P.stride + j] * P.inv_dx - 0.5f), 0, P.ng - 3);
+    b[2] = clampi((int)(fr[2 * P.stride + j] * P.inv_dx - 0.5f), 0, P.ng - 3);
+    int lo[3], hi[3];
+    for (int d = 0; d < 3; d++) { lo[d] = max(b[d] - margin, 0) >> 2; hi[d] = min(b[d] + 2 + margin, P.ng - 1) >> 2; }
+    for (int i = lo[0]; i <= hi[0]; i++)
+        for (int jj = lo[1]; jj <= hi[1]; jj++)
+            for (int k = lo[2]; k <= hi[2]; k++) {
+                uint32_t id = (uint32_t)((i * P.nb + jj) * P.nb + k);
+                if (!flags[id]) flags[id] = 1u;
+            }
+}
+__global__ void k_compact_blocks(int nblk, const uint32_t* __restrict__ flags, uint32_t* __restrict__ list, int* __restrict__ count) {
+    // order of the list does not matter (each entry is processed independently); one atomic per set flag
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < nblk && flags[b]) list[atomicAdd(count, 1)] = (uint32_t)b;
+}
+// zero the float4 grid arrays on the active blocks only
+__global__ void __launch_bounds__(256) k_clear_blocks(const uint32_t* __restrict__ blocks, const int* __restrict__ nblocks, float4* __restrict__ a,
+                                                      float4* __restrict__ b, float4* __restrict__ c) {
+    int total = *nblocks;
+    float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int bi = blockIdx.x * 4 + (threadIdx.x >> 6); bi < total; bi += gridDim.x * 4) {
+        uint32_t node = blocks[bi] * 64u + (threadIdx.x & 63);
+        if (a) a[node] = z;
+        if (b) b[node] = z;
+        if (c) c[node] = z;
+    }
+}
+// a particle whose stencil touches an inactive block would scatter into stale memory: count it
+__global__ void k_check_active(Params P, const float* __restrict__ fr, const uint32_t* __restrict__ flags, unsigned long long* counters) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= P.n) return;
+    int b0 = clampi((int)(fr[j] * P.inv_dx - 0.5f), 0, P.ng - 3), b1 = clampi((int)(fr[P.stride + j] * P.inv_dx - 0.5f), 0, P.ng - 3),
+        b2 = clampi((int)(fr[2 * P.stride + j] * P.inv_dx - 0.5f), 0, P.ng - 3);
+    bool ok = true;
+    for (int i = b0 >> 2; i <= (b0 + 2) >> 2; i++)
+        for (int jj = b1 >> 2; jj <= (b1 + 2) >> 2; jj++)
+            for (int k = b2 >> 2; k <= (b2 + 2) >> 2; k++) ok &= flags[(i * P.nb + jj) * P.nb + k] != 0;
+    if (!ok) atomicAdd(counters + 1, 1ull);
+}
+// Primitive.forward_kinematics and its adjoint (primitive_base.py:280-283, primitive_utils.py:20-40); one thread
+__global__ void k_forward_kinematics(float* __restrict__ pstate, int T, int np, int f, float dt) {
+    int i = threadIdx.x;
+    if (i >= np) return;
+    float* s0 = pstate + ((size_t)i * T + f) * 13;
+    float* s1 = s0 + 13;
+    for (int d = 0; d < 3; d++) s1[d] = s0[d] + s0[7 + d] * dt;
+    double aa[3] = {(double)s0[10] * dt, (double)s0[11] * dt, (double)s0[12] * dt};
+    double w = sqrt(aa[0] * aa[0] + aa[1] * aa[1] + aa[2] * aa[2] + 1e-12);
+    double sn = sin(w / 2), q[4] = {cos(w / 2), aa[0] / w * sn, aa[1] / w * sn, aa[2] / w * sn};
+    double r[4] = {s0[3], s0[4], s0[5], s0[6]}, o[4];
+    o[0] = r[0] * q[0] - r[1] * q[1] - r[2] * q[2] - r[3] * q[3];
+    o[1] = r[0] * q[1] + r[1] * q[0] - r[2] * q[3] + r[3] * q[2];
+    o[2] = r[0] * q[2] + r[1] * q[3] + r[2] * q[0] - r[3] * q[1];
+    o[3] = r[0] * q[3] - r[1] * q[2] + r[2] * q[1] + r[3] * q[0];
+    double nn = sqrt(o[0] * o[0] + o[1] * o[1] + o[2] * o[2] + o[3] * o[3]);
+    for (int d = 0; d < 4; d++) s1[3 + d] = (float)(o[d] / nn);
+}
+__global__ void k_forward_kinematics_grad(const float* __restrict__ pstate, double* __restrict__ pgrad, int T, int np, int f, float dtf) {
+    int i = threadIdx.x;
+    if (i >= np) return;
+    const float* s0 = pstate + ((size_t)i * T + f) * 13;
+    double* g0 = pgrad + ((size_t)i * T + f) * 13;
+    const double* g1 = g0 + 13;
+    double dt = dtf;
+    for (int d = 0; d < 3; d++) { g0[d] += g1[d]; g0[7 + d] += dt * g1[d]; }
+    double aa[3] = {(double)s0[10] * dt, (double)s0[11] * dt, (double)s0[12] * dt};
+    double w = sqrt(aa[0] * aa[0] + aa[1] * aa[1] + aa[2] * aa[2] + 1e-12);
+    double sn = sin(w / 2), cs = cos(w / 2), q[4] = {cs, aa[0] / w * sn, aa[1] / w * sn, aa[2] / w * sn};
+    double r[4] = {s0[3], s0[4], s0[5], s0[6]}, o[4];
+    o[0] = r[0] * q[0] - r[1] * q[1] - r[2] * q[2] - r[3] * q[3];
+    o[1] = r[0] * q[1] + r[1] * q[0] - r[2] * q[3] + r[3] * q[2];
+    o[2] = r[0] * q[2] + r[1] * q[3] + r[2] * q[0] - r[3] * q[1];
+    o[3] = r[0] * q[3] - r[1] * q[2] + r[2] * q[1] + r[3] * q[0];
+    double nn = sqrt(o[0] * o[0] + o[1] * o[1] + o[2] * o[2] + o[3] * o[3]);
+    double y[4], dd = 0, g[4];
+    for (int d = 0; d < 4; d++) { y[d] = o[d] / nn; dd += y[d] * g1[3 + d]; }
+    for (int d = 0; d < 4; d++) g[d] = (g1[3 + d] - y[d] * dd) / nn;
+    double gr[4], gq[4];
+    gr[0] = g[0] * q[0] + g[1] * q[1] + g[2] * q[2] + g[3] * q[3];
+    gr[1] = -g[0] * q[1] + g[1] * q[0] + g[2] * q[3] - g[3] * q[2];
+    gr[2] = -g[0] * q[2] - g[1] * q[3] + g[2] * q[0] + g[3] * q[1];
+    gr[3] = -g[0] * q[3] + g[1] * q[2] - g[2] * q[1] + g[3] * q[0];
+    gq[0] = g[0] * r[0] + g[1] * r[1] + g[2] * r[2] + g[3] * r[3];
+    gq[1] = -g[0] * r[1] + g[1] * r[0] - g[2] * r[3] + g[3] * r[2];
+    gq[2] = -g[0] * r[2] + g[1] * r[3] + g[2] * r[0] - g[3] * r[1];
+    gq[3] = -g[0] * r[3] - g[1] * r[2] + g[2] * r[1] + g[3] * r[0];
+    for (int d = 0; d < 4; d++) g0[3 + d] += gr[d];
+    double gw = -0.5 * sn * gq[0], gaa[3];
+    for (int d = 0; d < 3; d++) { gaa[d] = gq[d + 1] * sn / w; gw += gq[d + 1] * aa[d] * (0.5 * cs / w - sn / (w * w)); }
+    for (int d = 0; d < 3; d++) { gaa[d] += gw * aa[d] / w; g0[10 + d] += dt * gaa[d]; }
+}
+
+}  // namespace smx
