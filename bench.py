@@ -3,7 +3,9 @@
 
 Workload (SURVEY.md 8d, config 3 "cube-1M"): 1,000,000 particles from the reference generator
 (Shapes.add_box, np.random.seed(0)) in a 0.390625^3 box at (0.5, 0.30, 0.5), 128^3 grid, co-rotated plastic
-material, E = 3e3, nu = 0.2, gravity -9.8, sticky floor, dt = 2e-4, mixed (forecast) contact model.
+material, E = 3e3, nu = 0.2, gravity -9.8, sticky floor, mixed (forecast) contact model, dt = 1e-4 (SURVEY.md quotes
+2e-4 "as grip", but at dx = 1/128 the reference scheme itself is unstable there: explicit-MPM limit dt < dx/sqrt(E)
+= 1.4e-4; the f64 oracle blows up after ~20 substeps at 2e-4 -- see DESIGN.md).
 Variant A: no primitive.  Variant B (--variant B): one static rigid sphere SDF under the cube.
 One "step" = S substeps forward (smx_substep) followed by S substeps backward (smx_substep_grad) with a
 dense seed on x at the last frame; value = N_gpus * n * S / step time.
@@ -32,6 +34,7 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 
 METRIC = "particle-substeps/sec fwd+bwd (1M p, 128^3)"
 UNIT = "particle-substeps/s"
+DT = 1e-4                   # see module docstring
 ALGO_BYTES_STEP = 480.0     # 192 B forward + 288 B backward per particle-substep (fp32 storage)
 # algorithmic HBM bytes per particle of each particle kernel (DESIGN.md "Kernels"): frame components read + written
 KERNEL_BYTES = {"k_p2g": 96 + 36, "k_g2p": 12 + 60, "k_g2p_grad": 12 + 60 + 12, "k_p2g_grad": 96 + 36 + 12 + 96,
@@ -106,7 +109,7 @@ class ClockSampler:
 
 def workload_cfg(args, max_steps):
     from harness import sim_cfg
-    return sim_cfg(args.n, n_grid=args.n_grid, max_steps=max_steps, dt=2e-4, E=3e3, nu=0.2, gravity=(0., -9.8, 0.),
+    return sim_cfg(args.n, n_grid=args.n_grid, max_steps=max_steps, dt=DT, E=3e3, nu=0.2, gravity=(0., -9.8, 0.),
                    ground_friction=20., material_model=0, ptype=0, collision_type=2)
 
 
@@ -130,7 +133,7 @@ def run_reference(args, rank, world):
     import scenes
     from oracle import mpm_oracle as mo
     S = args.cpu_sample_substeps
-    sim = mo.OracleSim(args.n, n_grid=args.n_grid, max_steps=S + 1, dt=2e-4, E=3e3, nu=0.2, gravity=(0., -9.8, 0.),
+    sim = mo.OracleSim(args.n, n_grid=args.n_grid, max_steps=S + 1, dt=DT, E=3e3, nu=0.2, gravity=(0., -9.8, 0.),
                        ground_friction=20., material_model=0, ptype=0, collision_type=2, substeps=5)
     if args.variant == "B":
         t = variant_b_table()
@@ -169,7 +172,7 @@ def run_reference(args, rank, world):
 def config_dict(args, S):
     return {"workload": f"cube-{args.n} variant {args.variant}: {args.n} particles, {args.n_grid}^3 grid, corotated plastic, mixed contact, "
                         f"{S} substeps forward + {S} backward per step",
-            "n_particles": args.n, "n_grid": args.n_grid, "substeps_per_step": S, "variant": args.variant, "dt": 2e-4,
+            "n_particles": args.n, "n_grid": args.n_grid, "substeps_per_step": S, "variant": args.variant, "dt": DT,
             "sort_every": args.sort_every, "parallelism": f"{args.gpus} independent rollout(s), one per GPU, gradient all-reduce" if args.gpus > 1 else "single GPU",
             "cache": "inputs larger than L2: 96 MB per particle frame, one fresh frame per substep"}
 
@@ -178,7 +181,7 @@ def cpu_baseline(args):
     import scenes  # noqa: F401
     from oracle import mpm_oracle as mo
     S = args.cpu_sample_substeps
-    sim = mo.OracleSim(args.n, n_grid=args.n_grid, max_steps=S + 1, dt=2e-4, E=3e3, nu=0.2, gravity=(0., -9.8, 0.),
+    sim = mo.OracleSim(args.n, n_grid=args.n_grid, max_steps=S + 1, dt=DT, E=3e3, nu=0.2, gravity=(0., -9.8, 0.),
                        ground_friction=20., material_model=0, ptype=0, collision_type=2, substeps=5)
     st, seed = make_inputs(args, 0)
     g24 = np.zeros((args.n, 24)); g24[:, :3] = seed
@@ -218,7 +221,7 @@ def run_cuda(args, rank, world, local_rank):
         m.softness[None] = 666.
         prims.append(m)
     P = Primitives(primitives=prims, max_timesteps=S + 2)
-    sim = MPMSimulator(cfg, P, env_dt=1e-3, device=local_rank, sort_every=args.sort_every, flags=args.flags)
+    sim = MPMSimulator(cfg, P, env_dt=5 * DT, device=local_rank, sort_every=args.sort_every, flags=args.flags)
     for p in prims:
         p.set_all_states(0, np.array([0.5, 0.04, 0.5, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0.]), f_end=S + 2)
     st, seed = make_inputs(args, rank)

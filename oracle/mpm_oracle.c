@@ -968,6 +968,11 @@ static void svd_grad(orc_sim *s) {                                              
 static inline void stencil(const orc_sim *s, const double *x, int *base, double *fx, double w[3][3]) {
     for (int d = 0; d < 3; d++) {
         base[d] = (int)(x[d]*s->inv_dx - 0.5);
+        /* The reference has no bounds check here (out-of-domain particles are undefined behaviour, SURVEY.md
+           section 5); the restatement clamps the base cell exactly like the CUDA path does, so that a scene
+           that blows up cannot corrupt the test process. In-domain particles are unaffected. */
+        if (!(base[d] >= 0)) base[d] = 0;
+        if (base[d] > s->ng - 3) base[d] = s->ng - 3;
         fx[d] = x[d]*s->inv_dx - (double)base[d];
         w[0][d] = 0.5*(1.5 - fx[d])*(1.5 - fx[d]);
         w[1][d] = 0.75 - (fx[d] - 1.0)*(fx[d] - 1.0);

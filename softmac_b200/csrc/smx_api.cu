@@ -18,7 +18,26 @@
 #include "../../include/softmac_b200.h"
 #include "smx_kernels.cuh"
 
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
+
 using namespace smx;
+
+// SMX_BACKTRACE=1: print a native backtrace on SIGSEGV (debug aid; resolve offsets with addr2line -e <lib>)
+static void smx_segv_handler(int sig) {
+    void* frames[64];
+    int n = backtrace(frames, 64);
+    const char msg[] = "\n[libsoftmac_b200] fatal signal, native backtrace:\n";
+    ssize_t w = write(2, msg, sizeof msg - 1); (void)w;
+    backtrace_symbols_fd(frames, n, 2);
+    signal(sig, SIG_DFL);
+    raise(sig);
+}
+__attribute__((constructor)) static void smx_install_handler() {
+    const char* e = getenv("SMX_BACKTRACE");
+    if (e && e[0] == '1') { signal(SIGSEGV, smx_segv_handler); signal(SIGABRT, smx_segv_handler); }
+}
 
 static thread_local char g_err[512] = "";
 static int fail(int code, const char* fmt, ...) {

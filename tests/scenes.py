@@ -65,3 +65,22 @@ def cube_state(n, seed=0, init_pos=(0.5, 0.30, 0.5), width=0.390625):
     st[:, :3] = p
     st[:, 6] = st[:, 10] = st[:, 14] = 1.0
     return st.astype(np.float32).astype(np.float64)
+
+
+def contact_rollout_state(n, rng, sphere_center, radius=0.08, gap=5e-4, width=0.10, speed=1.0):
+    """Particles in a box resting just outside a sphere (none starts inside it), moving towards it: a scene that
+    stays physical over a multi-substep rollout (particles that start deep inside a primitive are ejected at
+    sdf/dt ~ 100 m/s by the forecast contact model and leave the domain within a few substeps)."""
+    c = np.asarray(sphere_center, float)
+    box_c = c + np.array([0.0, radius + 0.5 * width - 0.02, 0.0])
+    x = np.zeros((0, 3))
+    while len(x) < n:
+        cand = (rng.random((2 * n, 3)) * 2 - 1) * 0.5 * width + box_c
+        cand = cand[np.linalg.norm(cand - c, axis=1) > radius + gap]
+        x = np.vstack([x, cand])
+    x = x[:n]
+    v = np.tile([0.0, -speed, 0.0], (n, 1)) + 0.05 * rng.normal(size=(n, 3))
+    F = np.eye(3)[None] + 0.003 * rng.normal(size=(n, 3, 3))
+    Cm = 0.5 * rng.normal(size=(n, 3, 3))
+    st = np.hstack([x, v, F.reshape(n, 9), Cm.reshape(n, 9)])
+    return st.astype(np.float32).astype(np.float64)

@@ -142,8 +142,10 @@ def test_identity_F_first_substep():
     pair.orc.set_frame(0, st)
     pair.gpu.reset(x)
     pair.substep(0)
-    # v = g*dt everywhere, C = 0 analytically: use absolute floors for C (|C| ~ 1e-12 in f64)
-    assert_state_close(pair.gpu.get_state(1), pair.orc.get_frame(1), floors=dict(C=1e-2))
+    # v = g*dt everywhere, so C = 0 analytically (|C| ~ 1e-12 in f64): measure the C error against the natural
+    # scale of a velocity gradient, |v| / dx, instead of against ~0
+    ref = pair.orc.get_frame(1)
+    assert_state_close(pair.gpu.get_state(1), ref, floors=dict(C=np.linalg.norm(ref[:, 3:6]) * 32))
     go, gg = run_backward(pair, rng, 0)
     for k, sl in COLS.items():
         e = rel_l2(gg[:, sl], go[:, sl])
@@ -179,15 +181,21 @@ def test_rollout_with_resort_forward_and_backward():
     Seeds on x at three frames (as GripLoss does, loss_grip.py:117-140) and wrench seeds every substep."""
     rng = np.random.default_rng(240)
     n, steps = 6000, 12
-    pair, st = make_pair(rng, n=n, P=2, max_steps=steps + 2, sort_every=4, substeps=4)
+    center = np.array([0.5, 0.3, 0.5])
+    pair = Pair(n, tables=[scenes.sphere_table()], prim_params=[(0.5, 666.)], max_steps=steps + 2, sort_every=4, substeps=4)
+    s13 = np.concatenate([center, scenes.random_quat(rng), [0.0, 0.2, 0.0], 0.5 * rng.normal(size=3)])
+    pair.set_prim_state(0, 0, steps + 2, s13)
+    pair.reset(scenes.contact_rollout_state(n, rng, center))
+    pair.clear_ext_f()
     for f in range(steps):
         pair.substep(f)
         ref, got = pair.orc.get_frame(f + 1), pair.gpu.get_state(f + 1)
-        # trajectories are compared substep by substep from the *oracle's* previous frame drift: keep a loose bound here,
-        # the strict per-substep bound is enforced by the single-substep tests
-        assert rel_l2(got[:, :3], ref[:, :3]) <= 1e-4
+        # both trajectories start from the same frame 0 and drift apart by fp32 rounding only
+        assert rel_l2(got[:, :3], ref[:, :3]) <= 1e-5
+        assert rel_l2(got[:, 3:6], ref[:, 3:6]) <= 2e-3
+    fo, fg = pair.orc.get_ext_f(0), pair.prims[0].get_ext_f()
+    assert np.abs(fo[:3]).max() > 0 and rel_l2(fg, fo) <= 5e-3, (fg, fo)
     assert pair.gpu.counters()["resorts"] >= 3
-    assert rel_l2(pair.gpu.get_state(steps)[:, 3:6], pair.orc.get_frame(steps)[:, 3:6]) <= 5e-3
     pair.orc.clear_grads(); pair.gpu.clear_all_gradients()
     for f in (steps, steps - 5, 3):
         g = rng.normal(size=(n, 3)).astype(np.float32).astype(np.float64)
@@ -205,7 +213,8 @@ def test_rollout_with_resort_forward_and_backward():
     for i in range(pair.P):
         po = sum(pair.orc.get_primitive_state_grad(i, f) for f in range(steps))
         pg = pair.prims[i].get_all_states_grad(0, f_end=steps)
-        assert cosine(pg, po) >= 0.999, (pg, po)
+        assert np.abs(po).max() > 0 and cosine(pg, po) >= 0.999, (pg, po)
+    assert pair.gpu.counters()["clamped"] == 0 and pair.gpu.counters()["left_active_region"] == 0
 
 
 def test_sort_contract_bit_exact():
@@ -289,8 +298,8 @@ def test_properties_at_full_size():
     from softmac_b200.engine import MPMSimulator
     from harness import sim_cfg
     n = 1_000_000
-    cfg = sim_cfg(n, n_grid=128, max_steps=6, ground_friction=20.)
-    sim = MPMSimulator(cfg, env_dt=1e-3)
+    cfg = sim_cfg(n, n_grid=128, max_steps=6, ground_friction=20., dt=1e-4)
+    sim = MPMSimulator(cfg, env_dt=5e-4)
     st = scenes.cube_state(n)
     sim.reset(st)
     keys = sim.sort_keys(0)
@@ -301,7 +310,7 @@ def test_properties_at_full_size():
     p_mass = (1 / 128 * 0.5) ** 2
     assert abs(g_in[:, 3].astype(np.float64).sum() / (n * p_mass) - 1) < 1e-5
     s1 = sim.get_state(1)
-    assert np.allclose(s1[:, 3:6].mean(0), [0, -9.8 * 2e-4, 0], atol=1e-7)     # free fall, away from walls
+    assert np.allclose(s1[:, 3:6].mean(0), [0, -9.8 * 1e-4, 0], atol=1e-7)     # free fall, away from walls
     sim.substep(1); sim.substep(2); sim.substep(3)
     sim.clear_all_gradients()
     for f in range(3, -1, -1):
