@@ -246,14 +246,23 @@ def test_sort_contract_bit_exact():
 
 @pytest.mark.parametrize("flags", [1, 2])
 def test_dense_and_unsorted_modes_agree(flags):
-    rng = np.random.default_rng(260)
-    pair_a, st = make_pair(rng, n=5000, sort_every=2)
-    rng = np.random.default_rng(260)
-    pair_b, _ = make_pair(rng, n=5000, sort_every=2, flags=flags)
-    for f in range(4):
-        pair_a.gpu.substep(f); pair_b.gpu.substep(f)
-    a, b = pair_a.gpu.get_state(4), pair_b.gpu.get_state(4)
-    assert_state_close(a, b, tol=2e-5)      # only the fp32 summation order differs
+    """SMX_FLAG_DENSE_GRID / SMX_FLAG_NO_SORT change the traversal, not the arithmetic (up to fp32 summation order)."""
+    center = np.array([0.5, 0.3, 0.5])
+
+    def run(fl):
+        rng = np.random.default_rng(260)
+        pair = Pair(5000, tables=[scenes.sphere_table()], prim_params=[(0.5, 666.)], max_steps=8, sort_every=2, flags=fl)
+        s13 = np.concatenate([center, [1, 0, 0, 0], [0.0, 0.2, 0.0], [0, 0, 0]])
+        pair.prims[0].set_all_states(0, s13, f_end=8)
+        pair.gpu.reset(scenes.contact_rollout_state(5000, rng, center))
+        for f in range(6):
+            pair.gpu.substep(f)
+        return pair.gpu.get_state(6), pair.prims[0].get_ext_f()
+
+    (a, fa), (b, fb) = run(0), run(flags)
+    assert np.abs(fa).max() > 0
+    assert_state_close(a, b, tol=2e-5)
+    assert rel_l2(fb, fa) <= 1e-4
 
 
 def test_api_quirks_and_errors():
