@@ -51,7 +51,7 @@ def parse():
     ap.add_argument("--n", type=int, default=1_000_000)
     ap.add_argument("--n-grid", type=int, default=128)
     ap.add_argument("--variant", default="A", choices=["A", "B"])
-    ap.add_argument("--sort-every", type=int, default=8)
+    ap.add_argument("--sort-every", type=int, default=16)
     ap.add_argument("--flags", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -332,7 +332,7 @@ def kernel_roofline(sim, args, S):
     def prof(f, mode):
         _capi.check(L.smx_profile_substep(sim._h, f, mode, names, ms, C.byref(cnt)))
         for i in range(cnt.value):
-            key = names[i].decode() + ("(recompute)" if mode == 1 and names[i].decode() in ("k_p2g", "k_grid_op", "k_contact", "clear") else "")
+            key = names[i].decode() + ("(recompute)" if mode == 1 and names[i].decode() in ("k_p2g", "k_grid_op", "k_contact") else "")
             tot.setdefault(key, []).append(ms[i])
 
     sim.copyframe(S + 1, 0)

@@ -69,6 +69,8 @@ typedef struct {
 
 #define SMX_FLAG_DENSE_GRID 1     /* sweep the whole grid every substep instead of the active-block list */
 #define SMX_FLAG_NO_SORT 2        /* keep particles in id order (debug / ablation) */
+#define SMX_FLAG_NO_GRID_CKPT 8    /* adjoint re-runs P2G + grid update instead of restoring the per-substep grid checkpoint */
+#define SMX_FLAG_DIRECT_RED 4     /* one L2 reduction per particle and node instead of the warp-aggregated scatter (ablation) */
 
 /* lifetime ------------------------------------------------------------------------------------- */
 int smx_create(const smx_config* cfg, smx_sim** out);

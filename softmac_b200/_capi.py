@@ -14,6 +14,8 @@ LIB_PATH = os.path.join(_HERE, "lib", "libsoftmac_b200.so")
 
 SMX_FLAG_DENSE_GRID = 1
 SMX_FLAG_NO_SORT = 2
+SMX_FLAG_DIRECT_RED = 4
+SMX_FLAG_NO_GRID_CKPT = 8
 
 
 class SmxConfig(C.Structure):

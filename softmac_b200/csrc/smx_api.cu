@@ -60,6 +60,7 @@ struct Order {                  // one physical ordering of the particles (an "e
     int* ctrl_slot = nullptr;   // control_idx in storage order (lazily built)
     int ctrl_version = -1;
     bool live = true;
+    long long uid = 0;          // never reused (ids are)
 };
 
 struct HostPrim { PrimDev d; float* sdf_dev = nullptr; float4* nrm_dev = nullptr; };
@@ -81,9 +82,17 @@ struct smx_sim {
     std::vector<Order> orders;
     std::vector<Order> free_orders;     // recycled device buffers
     std::vector<int> dead_ids;
+    long long next_uid = 1;
     // grid
     size_t G = 0;
     float4 *g_in = nullptr, *g_out = nullptr, *g_mix = nullptr, *gg_out = nullptr, *gg_mix = nullptr, *g_lin = nullptr;
+    // grid checkpoints (g_in, g_out[, g_mix] on the active blocks of every substep) so that the adjoint does not
+    // re-run P2G and the grid update (north_star: "per-substep state buffers resident in HBM rather than recomputed")
+    float4* ckpt = nullptr;
+    size_t ckpt_rec = 0;                // float4 entries per substep record
+    int ckpt_cap = 0;                   // blocks reserved per array
+    std::vector<long long> ckpt_order;  // uid of the ordering the record of substep f was written in (-1: none)
+    std::vector<char> ckpt_contact;
     // adjoint ping-pong
     float *adj_cur = nullptr, *adj_nxt = nullptr;
     int adj_frame = -1, adj_order = -1;
@@ -161,9 +170,12 @@ static void gc_orders(smx_sim* s) {
         }
 }
 static int new_order_id(smx_sim* s, const Order& o) {
-    if (!s->dead_ids.empty()) { int id = s->dead_ids.back(); s->dead_ids.pop_back(); s->orders[id] = o; return id; }
-    s->orders.push_back(o);
-    return (int)s->orders.size() - 1;
+    int id;
+    if (!s->dead_ids.empty()) { id = s->dead_ids.back(); s->dead_ids.pop_back(); s->orders[id] = o; }
+    else { s->orders.push_back(o); id = (int)s->orders.size() - 1; }
+    s->orders[id].live = true;
+    s->orders[id].uid = s->next_uid++;
+    return id;
 }
 // an Order with perm / idx buffers allocated (recycled when possible)
 static int alloc_order(smx_sim* s, Order& o, bool need_idx) {
@@ -174,7 +186,7 @@ static int alloc_order(smx_sim* s, Order& o, bool need_idx) {
     return SMX_OK;
 }
 
-static int build_blocks(smx_sim* s, Order& o, const float* frame) {
+static int build_blocks(smx_sim* s, Order& o, const float* frame, const uint32_t* keys_sorted = nullptr) {
     if (s->dense) return SMX_OK;
     int nb3 = s->P.nb * s->P.nb * s->P.nb;
     if (!o.flags) {
@@ -182,7 +194,11 @@ static int build_blocks(smx_sim* s, Order& o, const float* frame) {
     }
     CK(cudaMemsetAsync(o.flags, 0, nb3 * sizeof(uint32_t), s->stream));
     CK(cudaMemsetAsync(o.nblocks, 0, sizeof(int), s->stream));
-    if (s->P.n > 0) { k_mark_blocks<<<nblk(s->P.n, 256), 256, 0, s->stream>>>(s->P, frame, 2, o.flags); CKL(s); }
+    if (s->P.n > 0) {
+        if (keys_sorted) k_mark_blocks_sorted<<<nblk(s->P.n, 256), 256, 0, s->stream>>>(s->P, keys_sorted, 2, o.flags);
+        else k_mark_blocks<<<nblk(s->P.n, 256), 256, 0, s->stream>>>(s->P, frame, 2, o.flags);
+        CKL(s);
+    }
     k_compact_blocks<<<nblk(nb3, 256), 256, 0, s->stream>>>(nb3, o.flags, o.blocks, o.nblocks); CKL(s);
     return SMX_OK;
 }
@@ -212,8 +228,9 @@ static int resort(smx_sim* s, int f, bool keep_transition) {
         TRY(alloc_order(s, no, false));
         CK(cudaMemcpyAsync(no.perm, s->orders[old_id].perm, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s->stream));
     }
-    TRY(build_blocks(s, no, s->frame_ptr(f)));
+    TRY(build_blocks(s, no, s->frame_ptr(f), do_sort ? s->keys_b : nullptr));
     s->order_of[f] = new_order_id(s, no);
+    s->ckpt_order[f] = -1;
     // keep_transition: frame f was produced by substep f-1 in the old ordering, so the adjoint has to be carried
     // back through idx; otherwise (user-written frame) the adjoint chain is cut here, as in the reference
     s->trans_from[f] = (keep_transition && do_sort) ? old_id : -1;
@@ -275,7 +292,8 @@ static int forward_to_grid(smx_sim* s, int f, bool write_F, bool accumulate) {
     TRY(clear_grids(s, o, s->g_in, nullptr, nullptr));
     if (P.n > 0) {
         TRY(dispatch_mat(P.material, P.ptype, [&](auto mat) {
-            k_p2g<decltype(mat)::value><<<nblk(P.n, SMX_TPB), SMX_TPB, 0, s->stream>>>(P, ps, f, fin, fout, s->g_in, cslot, s->action, accumulate ? 1 : 0);
+            if (s->cfg.flags & SMX_FLAG_DIRECT_RED) k_p2g<decltype(mat)::value, false><<<nblk(P.n, SMX_TPB_SC), SMX_TPB_SC, 0, s->stream>>>(P, ps, f, fin, fout, s->g_in, cslot, s->action, accumulate ? 1 : 0);
+            else k_p2g<decltype(mat)::value, true><<<nblk(P.n, SMX_TPB_SC), SMX_TPB_SC, 0, s->stream>>>(P, ps, f, fin, fout, s->g_in, cslot, s->action, accumulate ? 1 : 0);
             CKLN(s, "k_p2g"); return (int)SMX_OK;
         }));
     }
@@ -383,6 +401,17 @@ int smx_create(const smx_config* cfg, smx_sim** out) {
     s->spare_slot = T;
     size_t pool_bytes = (size_t)(T + 1) * s->frame_floats * sizeof(float);
     if (cudaMalloc(&s->pool, pool_bytes) != cudaSuccess) { cudaGetLastError(); delete s; return fail(SMX_ERR_NOMEM, "smx_create: cannot allocate %.1f MB of particle checkpoints", pool_bytes / 1e6); }
+    s->ckpt_order.assign(T, -1); s->ckpt_contact.assign(T, 0);
+    if (!(cfg->flags & SMX_FLAG_NO_GRID_CKPT)) {
+        // reserve one record per substep: all blocks of the grid for g_in and g_out, plus g_mix when the forecast
+        // contact model is on; skipped (adjoint recomputes instead) when that would not fit comfortably
+        int narr = cfg->collision_type == 2 ? 3 : 2;
+        s->ckpt_cap = P.nb * P.nb * P.nb;
+        s->ckpt_rec = (size_t)narr * s->ckpt_cap * 64;
+        size_t bytes = (size_t)T * s->ckpt_rec * sizeof(float4), free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        if (bytes > free_b / 3 || cudaMalloc(&s->ckpt, bytes) != cudaSuccess) { cudaGetLastError(); s->ckpt = nullptr; s->ckpt_rec = 0; }
+    }
     CK(cudaMalloc(&s->g_in, s->G * sizeof(float4))); CK(cudaMalloc(&s->g_out, s->G * sizeof(float4))); CK(cudaMalloc(&s->g_mix, s->G * sizeof(float4)));
     CK(cudaMalloc(&s->gg_out, s->G * sizeof(float4))); CK(cudaMalloc(&s->gg_mix, s->G * sizeof(float4)));
     CK(cudaMemsetAsync(s->g_in, 0, s->G * sizeof(float4), s->stream)); CK(cudaMemsetAsync(s->g_out, 0, s->G * sizeof(float4), s->stream));
@@ -420,7 +449,7 @@ int smx_destroy(smx_sim* s) {
     for (auto& o : s->free_orders) free_order(o);
     for (auto& kv : s->seeds) cudaFree(kv.second);
     for (auto& p : s->prims) { cudaFree(p.sdf_dev); cudaFree(p.nrm_dev); }
-    void* ptrs[] = {s->pool, s->g_in, s->g_out, s->g_mix, s->gg_out, s->gg_mix, s->g_lin, s->adj_cur, s->adj_nxt, s->stage_dev, s->keys_a, s->keys_b, s->iota, s->cub_tmp,
+    void* ptrs[] = {s->ckpt, s->pool, s->g_in, s->g_out, s->g_mix, s->gg_out, s->gg_mix, s->g_lin, s->adj_cur, s->adj_nxt, s->stage_dev, s->keys_a, s->keys_b, s->iota, s->cub_tmp,
                     s->counters, s->prims_dev, s->pstate, s->pgrad, s->ext_f, s->ext_f_grad, s->abuf, s->gabuf, s->ctrl_id, s->action, s->action_grad};
     for (void* p : ptrs) cudaFree(p);
     cudaFreeHost(s->stage_host);
@@ -480,6 +509,7 @@ int smx_reset(smx_sim* s, const double* state, int32_t ncols) {
     CK(cudaStreamSynchronize(s->stream));
     std::fill(s->order_of.begin(), s->order_of.end(), -1);
     std::fill(s->trans_from.begin(), s->trans_from.end(), -1);
+    std::fill(s->ckpt_order.begin(), s->ckpt_order.end(), -1);
     s->adj_frame = -1; s->adj_order = -1;
     gc_orders(s);                       // every ordering is unreferenced now: recycle all of them
     int n = s->P.n;
@@ -504,6 +534,7 @@ int smx_set_frame(smx_sim* s, int32_t f, const double* x, const double* v, const
     TRY(check_frame(s, f, "smx_set_frame"));
     CK(cudaSetDevice(s->cfg.device));
     TRY(ensure_order(s, f));
+    s->ckpt_order[f] = -1;
     if (x) TRY(upload_cols(s, f, x, 3, 0));
     if (v) TRY(upload_cols(s, f, v, 3, 3));
     if (F) TRY(upload_cols(s, f, F, 9, 6));
@@ -536,7 +567,7 @@ int smx_copy_frame(smx_sim* s, int32_t src, int32_t dst) {
     CK(cudaSetDevice(s->cfg.device));
     if (src != dst) {
         CK(cudaMemcpyAsync(s->frame_ptr(dst), s->frame_ptr(src), s->frame_floats * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
-        s->order_of[dst] = s->order_of[src]; s->trans_from[dst] = -1;
+        s->order_of[dst] = s->order_of[src]; s->trans_from[dst] = -1; s->ckpt_order[dst] = -1;
         int T = s->cfg.max_steps;
         for (size_t i = 0; i < s->prims.size(); i++)
             for (int j = 0; j < s->cfg.substeps; j++) {
@@ -690,7 +721,16 @@ int smx_substep(smx_sim* s, int32_t f) {
     if (s->order_of[f] < 0) return fail(SMX_ERR_STATE, "smx_substep: frame %d has not been written (call smx_reset / smx_set_frame first)", f);
     CK(cudaSetDevice(s->cfg.device));
     s->order_of[f + 1] = s->order_of[f]; s->trans_from[f + 1] = -1;
+    s->ckpt_order[f] = -1; s->ckpt_order[f + 1] = -1;
     TRY(forward_to_grid(s, f, true, true));
+    if (s->ckpt) {
+        Order& o = s->orders[s->order_of[f]];
+        bool contact = s->has_contact();
+        k_ckpt_copy<<<grid_blocks_launch(s), 256, 0, s->stream>>>(s->dense ? nullptr : o.blocks, o.nblocks, s->ckpt_cap, s->ckpt_cap, s->ckpt + (size_t)f * s->ckpt_rec,
+                                                                 s->g_in, s->g_out, contact ? s->g_mix : nullptr, 0);
+        CKLN(s, "ckpt_save");
+        s->ckpt_order[f] = o.uid; s->ckpt_contact[f] = contact;
+    }
     if (s->P.n > 0) { k_g2p<<<nblk(s->P.n, SMX_TPB), SMX_TPB, 0, s->stream>>>(s->P, s->frame_ptr(f), s->frame_ptr(f + 1), s->g_out); CKLN(s, "k_g2p"); }
     if (s->cfg.sort_every > 0 && (f + 1) % s->cfg.sort_every == 0 && !(s->cfg.flags & SMX_FLAG_NO_SORT)) TRY(resort(s, f + 1, true));
     return SMX_OK;
@@ -718,10 +758,20 @@ int smx_substep_grad(smx_sim* s, int32_t f) {
     Order& ord = s->orders[o];
     bool contact = s->has_contact();
     PrimSet ps = s->primset();
-    TRY(forward_to_grid(s, f, false, false));
+    if (s->ckpt && s->ckpt_order[f] == ord.uid && (bool)s->ckpt_contact[f] == contact) {
+        k_ckpt_copy<<<grid_blocks_launch(s), 256, 0, s->stream>>>(s->dense ? nullptr : ord.blocks, ord.nblocks, s->ckpt_cap, s->ckpt_cap, s->ckpt + (size_t)f * s->ckpt_rec,
+                                                                 s->g_in, s->g_out, contact ? s->g_mix : nullptr, 1);
+        CKLN(s, "ckpt_restore");
+    } else {
+        TRY(forward_to_grid(s, f, false, false));
+    }
     TRY(clear_grids(s, ord, s->gg_out, contact ? s->gg_mix : nullptr, nullptr));
     const float* fin = s->frame_ptr(f);
-    if (P.n > 0) { k_g2p_grad<<<nblk(P.n, SMX_TPB), SMX_TPB, 0, s->stream>>>(P, fin, s->adj_cur, s->adj_nxt, s->g_out, s->gg_out); CKLN(s, "k_g2p_grad"); }
+    if (P.n > 0) {
+        if (s->cfg.flags & SMX_FLAG_DIRECT_RED) k_g2p_grad<false><<<nblk(P.n, SMX_TPB_SC), SMX_TPB_SC, 0, s->stream>>>(P, fin, s->adj_cur, s->adj_nxt, s->g_out, s->gg_out);
+        else k_g2p_grad<true><<<nblk(P.n, SMX_TPB_SC), SMX_TPB_SC, 0, s->stream>>>(P, fin, s->adj_cur, s->adj_nxt, s->g_out, s->gg_out);
+        CKLN(s, "k_g2p_grad");
+    }
     if (contact && P.n > 0) {
         float life = 1.0f / (float)(P.substeps - f % P.substeps);
         k_contact_grad<<<nblk(P.n, SMX_TPB), SMX_TPB, 0, s->stream>>>(P, ps, f, life, fin, s->adj_nxt, s->g_mix, s->gg_out, s->gg_mix); CKLN(s, "k_contact_grad");

@@ -43,11 +43,55 @@ struct PrimSet {            // device pointers shared by all kernels that touch 
     int T;
 };
 
-#define SMX_TPB 128
+#define SMX_TPB 128         // gather-type particle kernels
+#define SMX_TPB_SC 64       // scatter-type particle kernels (two warps: 2 x 13.8 KB of staging)
 
 __device__ __forceinline__ void red_add_f4(float4* addr, float a, float b, float c, float d) {
     // one 16-byte reduction (SASS: REDG.E.ADD.F32x4) instead of four scalar atomics
     atomicAdd(addr, make_float4(a, b, c, d));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Warp-level aggregation of the 27-node scatter.  Particles are stored sorted by cell, so the 32
+// particles of a warp fall into a handful of runs with the same base cell.  Every lane parks its 27
+// float4 contributions in shared memory; the warp then re-partitions the work as (run, node offset)
+// tasks, each task sums one node's contributions over its run in particle order and issues ONE
+// REDG.E.ADD.F32x4.  With ~8 particles per cell this cuts the L2 reductions ~7x (27 per particle ->
+// 27 per run) and makes the within-run summation order deterministic.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t node_index(int i, int j, int k, int nb);
+struct WarpStage {
+    float4 val[32 * 27];    // [lane][offset]; row stride 27 float4 -> conflict-free 128-bit stores
+    uint32_t key[32];       // packed base cell of each run
+    uint32_t start[33];     // first lane of each run (+ sentinel)
+};
+__device__ __forceinline__ uint32_t pack_base(int bx, int by, int bz) { return (uint32_t)bx | ((uint32_t)by << 8) | ((uint32_t)bz << 16); }
+
+__device__ __forceinline__ void warp_stage_flush(WarpStage& st, uint32_t key, bool live, float4* __restrict__ grid, int nb) {
+    const unsigned lane = threadIdx.x & 31;
+    uint32_t k = live ? key : 0xffffffffu;
+    uint32_t prev = __shfl_up_sync(0xffffffffu, k, 1);
+    bool head = (lane == 0) || (k != prev);
+    unsigned heads = __ballot_sync(0xffffffffu, head);
+    int nruns = __popc(heads);
+    int rank = __popc(heads & ((1u << lane) - 1u));
+    if (head) { st.start[rank] = lane; st.key[rank] = k; }
+    if (lane == 0) st.start[nruns] = 32;
+    __syncwarp();
+    int ntasks = nruns * 27;
+    for (int t = lane; t < ntasks; t += 32) {
+        int r = t / 27, o = t - 27 * r;
+        uint32_t kk = st.key[r];
+        if (kk == 0xffffffffu) continue;
+        int p0 = st.start[r], p1 = st.start[r + 1];
+        float4 acc = st.val[p0 * 27 + o];
+        for (int p = p0 + 1; p < p1; p++) {
+            float4 v = st.val[p * 27 + o];
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        int a = o / 9, b = (o - 9 * a) / 3, c = o - 9 * a - 3 * b;
+        atomicAdd(grid + node_index((int)(kk & 0xffu) + a, (int)((kk >> 8) & 0xffu) + b, (int)(kk >> 16) + c, nb), acc);
+    }
 }
 
 // quadratic B-spline stencil of one particle (mpm_simulator.py:215-217)
@@ -142,12 +186,12 @@ __device__ __forceinline__ void material_update(const M3& Et, const Params& P, M
             m.D = m3_zero();
         } else {
             m.svd = svd_dev(Et);
-            M3 R = mulT(m.svd.U, m.svd.V);
             if (ptype == 0) {             // plastic: clip sigma to [1-2e-3, 1+3e-3] (:226-229)
                 float g0 = fminf(fmaxf(m.svd.e[0], -2e-3f), 3e-3f), g1 = fminf(fmaxf(m.svd.e[1], -2e-3f), 3e-3f),
                       g2 = fminf(fmaxf(m.svd.e[2], -2e-3f), 3e-3f);
-                m.D = udvt(m.svd.U, g0, g1, g2, m.svd.V);
-                m.newF = add(R, m.D);
+                m.D = udvt(m.svd.U, g0, g1, g2, m.svd.V);                       // new_F - R = U (Sc - I) V^T
+                // new_F = F_tmp + U (Sc - S) V^T: exactly F_tmp when nothing is clipped
+                m.newF = add(Ftmp, udvt(m.svd.U, g0 - m.svd.e[0], g1 - m.svd.e[1], g2 - m.svd.e[2], m.svd.V));
             } else {                      // elastic
                 m.D = udvt(m.svd.U, m.svd.e[0], m.svd.e[1], m.svd.e[2], m.svd.V);
                 m.newF = Ftmp;
@@ -196,46 +240,52 @@ __device__ __forceinline__ V3 particle_impulses(const Params& P, const PrimSet& 
 
 // ------------------------------------------------------------------------------------------------
 // P2G: F_tmp, SVD, plasticity, stress, APIC scatter.  One thread per particle slot.
+// STAGED: warp-aggregated scatter through shared memory (default); otherwise one REDG per node.
 // ------------------------------------------------------------------------------------------------
-template <int MAT>
-__global__ void __launch_bounds__(SMX_TPB) k_p2g(Params P, PrimSet ps, int f, const float* __restrict__ fin, float* __restrict__ fout,
-                                                 float4* __restrict__ g_in, const int* __restrict__ ctrl_slot,
-                                                 const float* __restrict__ action, int accumulate) {
-    int j = blockIdx.x * SMX_TPB + threadIdx.x;
+template <int MAT, bool STAGED>
+__global__ void __launch_bounds__(SMX_TPB_SC, 8) k_p2g(Params P, PrimSet ps, int f, const float* __restrict__ fin, float* __restrict__ fout,
+                                                    float4* __restrict__ g_in, const int* __restrict__ ctrl_slot,
+                                                    const float* __restrict__ action, int accumulate) {
+    __shared__ WarpStage stage[STAGED ? SMX_TPB_SC / 32 : 1];
+    int j = blockIdx.x * SMX_TPB_SC + threadIdx.x;
     bool live = j < P.n;
     int jj = live ? j : P.n - 1;
     V3 x, v; M3 F, C;
     load_state(fin, P.stride, jj, x, v, F, C);
     V3 imp = particle_impulses(P, ps, f, jj, live, x, v, ctrl_slot, action, accumulate != 0);
-    if (!live) return;
-    Material m;
-    material_update<MAT>(compute_Et(C, F, P.dt), P, m);
-    if (fout) {
-#pragma unroll
-        for (int i = 0; i < 9; i++) fout[(6 + i) * P.stride + j] = m.newF.m[i];
-    }
-    // affine' = (cs*stress + p_mass*C) * dx ; value(node) = w * (q0 + affine' * offset), q0 = p_mass*v + imp - affine' * fx
-    M3 A;
-#pragma unroll
-    for (int i = 0; i < 9; i++) A.m[i] = (P.cs * m.stress.m[i] + P.p_mass * C.m[i]) * P.dx;
     Stencil s = make_stencil(x.x, x.y, x.z, P);
-    V3 q0 = P.p_mass * v + imp - mulv(A, v3(s.fx, s.fy, s.fz));
-    V3 c0 = v3(A.m[0], A.m[3], A.m[6]), c1 = v3(A.m[1], A.m[4], A.m[7]), c2 = v3(A.m[2], A.m[5], A.m[8]);
+    if (live) {
+        Material m;
+        material_update<MAT>(compute_Et(C, F, P.dt), P, m);
+        if (fout) {
 #pragma unroll
-    for (int a = 0; a < 3; a++) {
-        V3 qa = q0 + (float)a * c0;
+            for (int i = 0; i < 9; i++) fout[(6 + i) * P.stride + j] = m.newF.m[i];
+        }
+        // affine' = (cs*stress + p_mass*C) * dx ; value(node) = w * (q0 + affine' * offset), q0 = p_mass*v + imp - affine' * fx
+        M3 A;
 #pragma unroll
-        for (int b = 0; b < 3; b++) {
-            V3 qb = qa + (float)b * c1;
-            float wab = s.wx[a] * s.wy[b];
+        for (int i = 0; i < 9; i++) A.m[i] = (P.cs * m.stress.m[i] + P.p_mass * C.m[i]) * P.dx;
+        V3 q0 = P.p_mass * v + imp - mulv(A, v3(s.fx, s.fy, s.fz));
+        V3 c0 = v3(A.m[0], A.m[3], A.m[6]), c1 = v3(A.m[1], A.m[4], A.m[7]), c2 = v3(A.m[2], A.m[5], A.m[8]);
+        float4* row = STAGED ? stage[threadIdx.x >> 5].val + (threadIdx.x & 31) * 27 : nullptr;
 #pragma unroll
-            for (int c = 0; c < 3; c++) {
-                V3 q = qb + (float)c * c2;
-                float w = wab * s.wz[c];
-                red_add_f4(g_in + (s.ox[a] + s.oy[b] + s.oz[c]), w * q.x, w * q.y, w * q.z, w * P.p_mass);
+        for (int a = 0; a < 3; a++) {
+            V3 qa = q0 + (float)a * c0;
+#pragma unroll
+            for (int b = 0; b < 3; b++) {
+                V3 qb = qa + (float)b * c1;
+                float wab = s.wx[a] * s.wy[b];
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    V3 q = qb + (float)c * c2;
+                    float w = wab * s.wz[c];
+                    if (STAGED) row[a * 9 + b * 3 + c] = make_float4(w * q.x, w * q.y, w * q.z, w * P.p_mass);
+                    else red_add_f4(g_in + (s.ox[a] + s.oy[b] + s.oz[c]), w * q.x, w * q.y, w * q.z, w * P.p_mass);
+                }
             }
         }
     }
+    if (STAGED) warp_stage_flush(stage[threadIdx.x >> 5], pack_base(s.bx, s.by, s.bz), live, g_in, P.nb);
 }
 
 // boundary_condition (mpm_simulator.py:268-281); mask bit d cleared where component d was zeroed
@@ -370,17 +420,20 @@ __global__ void __launch_bounds__(SMX_TPB) k_g2p(Params P, const float* __restri
 #pragma unroll
     for (int a = 0; a < 3; a++)
 #pragma unroll
-        for (int b = 0; b < 3; b++)
-#pragma unroll
-            for (int c = 0; c < 3; c++) {
-                float4 g = g_out[s.ox[a] + s.oy[b] + s.oz[c]];
-                float w = s.wx[a] * s.wy[b] * s.wz[c];
-                V3 wg = v3(w * g.x, w * g.y, w * g.z);
-                nv += wg;
-                B.m[0] += wg.x * a; B.m[1] += wg.x * b; B.m[2] += wg.x * c;
-                B.m[3] += wg.y * a; B.m[4] += wg.y * b; B.m[5] += wg.y * c;
-                B.m[6] += wg.z * a; B.m[7] += wg.z * b; B.m[8] += wg.z * c;
-            }
+        for (int b = 0; b < 3; b++) {
+            // row sums over c first: R0 = sum wz g, Rz = sum c wz g
+            const float4* gp = g_out + (s.ox[a] + s.oy[b]);
+            float4 g0 = gp[s.oz[0]], g1 = gp[s.oz[1]], g2 = gp[s.oz[2]];
+            float w1 = s.wz[1], w2 = s.wz[2], w0 = s.wz[0];
+            V3 R0 = v3(fmaf(w2, g2.x, fmaf(w1, g1.x, w0 * g0.x)), fmaf(w2, g2.y, fmaf(w1, g1.y, w0 * g0.y)), fmaf(w2, g2.z, fmaf(w1, g1.z, w0 * g0.z)));
+            V3 Rz = v3(fmaf(2.f * w2, g2.x, w1 * g1.x), fmaf(2.f * w2, g2.y, w1 * g1.y), fmaf(2.f * w2, g2.z, w1 * g1.z));
+            float wab = s.wx[a] * s.wy[b];
+            V3 r0 = wab * R0;
+            nv += r0;
+            if (a) { B.m[0] += a * r0.x; B.m[3] += a * r0.y; B.m[6] += a * r0.z; }
+            if (b) { B.m[1] += b * r0.x; B.m[4] += b * r0.y; B.m[7] += b * r0.z; }
+            B.m[2] = fmaf(wab, Rz.x, B.m[2]); B.m[5] = fmaf(wab, Rz.y, B.m[5]); B.m[8] = fmaf(wab, Rz.z, B.m[8]);
+        }
     float k4 = 4.f * P.inv_dx;
     float f3[3] = {s.fx, s.fy, s.fz}, n3[3] = {nv.x, nv.y, nv.z};
 #pragma unroll
@@ -395,49 +448,62 @@ __global__ void __launch_bounds__(SMX_TPB) k_g2p(Params P, const float* __restri
 // adjoint of G2P: scatter d g_out, accumulate d x through the weights.
 //   ain  = adjoint of frame f+1 (x 0..2, v 3..5, C 15..23), aout = adjoint of frame f (x written here)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SMX_TPB) k_g2p_grad(Params P, const float* __restrict__ fin, const float* __restrict__ ain,
-                                                      float* __restrict__ aout, const float4* __restrict__ g_out, float4* __restrict__ gg_out) {
-    int j = blockIdx.x * SMX_TPB + threadIdx.x;
-    if (j >= P.n) return;
-    V3 x = v3(fin[j], fin[P.stride + j], fin[2 * P.stride + j]);
-    V3 gx1 = v3(ain[j], ain[P.stride + j], ain[2 * P.stride + j]);
-    V3 gnv = v3(ain[3 * P.stride + j], ain[4 * P.stride + j], ain[5 * P.stride + j]) + P.dt * gx1;
-    M3 gC;
-#pragma unroll
-    for (int i = 0; i < 9; i++) gC.m[i] = ain[(15 + i) * P.stride + j];
+template <bool STAGED>
+__global__ void __launch_bounds__(SMX_TPB_SC, 8) k_g2p_grad(Params P, const float* __restrict__ fin, const float* __restrict__ ain,
+                                                         float* __restrict__ aout, const float4* __restrict__ g_out, float4* __restrict__ gg_out) {
+    __shared__ WarpStage stage[STAGED ? SMX_TPB_SC / 32 : 1];
+    int j = blockIdx.x * SMX_TPB_SC + threadIdx.x;
+    bool live = j < P.n;
+    int jj = live ? j : P.n - 1;
+    V3 x = v3(fin[jj], fin[P.stride + jj], fin[2 * P.stride + jj]);
     Stencil s = make_stencil(x.x, x.y, x.z, P);
-    float dwx[3], dwy[3], dwz[3];
-    axis_dweights(s.fx, dwx); axis_dweights(s.fy, dwy); axis_dweights(s.fz, dwz);
-    float k4 = 4.f * P.inv_dx;
-    // d g_out(node) = w * (gnv + k4 * gC * (offset - fx)) = w * (q0 + k4*gC*offset)
-    M3 K = scale(k4, gC);
-    V3 q0 = gnv - mulv(K, v3(s.fx, s.fy, s.fz));
-    V3 c0 = v3(K.m[0], K.m[3], K.m[6]), c1 = v3(K.m[1], K.m[4], K.m[7]), c2 = v3(K.m[2], K.m[5], K.m[8]);
-    V3 gfx = v3(0, 0, 0), S0 = v3(0, 0, 0);     // S0 = sum w * g (for d dpos)
+    if (live) {
+        V3 gx1 = v3(ain[j], ain[P.stride + j], ain[2 * P.stride + j]);
+        V3 gnv = v3(ain[3 * P.stride + j], ain[4 * P.stride + j], ain[5 * P.stride + j]) + P.dt * gx1;
+        M3 gC;
 #pragma unroll
-    for (int a = 0; a < 3; a++) {
-        V3 qa = q0 + (float)a * c0;
+        for (int i = 0; i < 9; i++) gC.m[i] = ain[(15 + i) * P.stride + j];
+        float dwx[3], dwy[3], dwz[3];
+        axis_dweights(s.fx, dwx); axis_dweights(s.fy, dwy); axis_dweights(s.fz, dwz);
+        float k4 = 4.f * P.inv_dx;
+        // d g_out(node) = w * (gnv + k4 * gC * (offset - fx)) = w * (q0 + k4*gC*offset)
+        M3 K = scale(k4, gC);
+        V3 q0 = gnv - mulv(K, v3(s.fx, s.fy, s.fz));
+        V3 c0 = v3(K.m[0], K.m[3], K.m[6]), c1 = v3(K.m[1], K.m[4], K.m[7]), c2 = v3(K.m[2], K.m[5], K.m[8]);
+        V3 gfx = v3(0, 0, 0), S0 = v3(0, 0, 0);     // S0 = sum w * g (for d dpos)
+        float4* row = STAGED ? stage[threadIdx.x >> 5].val + (threadIdx.x & 31) * 27 : nullptr;
 #pragma unroll
-        for (int b = 0; b < 3; b++) {
-            V3 qb = qa + (float)b * c1;
+        for (int a = 0; a < 3; a++) {
+            V3 qa = q0 + (float)a * c0;
 #pragma unroll
-            for (int c = 0; c < 3; c++) {
-                V3 q = qb + (float)c * c2;
-                int node = s.ox[a] + s.oy[b] + s.oz[c];
-                float4 g = g_out[node];
-                float w = s.wx[a] * s.wy[b] * s.wz[c];
-                red_add_f4(gg_out + node, w * q.x, w * q.y, w * q.z, 0.f);
-                float gw = g.x * q.x + g.y * q.y + g.z * q.z;          // d weight
-                gfx.x = fmaf(gw, dwx[a] * s.wy[b] * s.wz[c], gfx.x);
-                gfx.y = fmaf(gw, s.wx[a] * dwy[b] * s.wz[c], gfx.y);
-                gfx.z = fmaf(gw, s.wx[a] * s.wy[b] * dwz[c], gfx.z);
-                S0.x = fmaf(w, g.x, S0.x); S0.y = fmaf(w, g.y, S0.y); S0.z = fmaf(w, g.z, S0.z);
+            for (int b = 0; b < 3; b++) {
+                V3 qb = qa + (float)b * c1;
+                float wab = s.wx[a] * s.wy[b];
+                float G0 = 0.f, G1 = 0.f;       // sum_c gw wz[c], sum_c gw dwz[c]
+                V3 R0 = v3(0, 0, 0);            // sum_c wz[c] g
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    V3 q = qb + (float)c * c2;
+                    int node = s.ox[a] + s.oy[b] + s.oz[c];
+                    float4 g = g_out[node];
+                    float w = wab * s.wz[c];
+                    if (STAGED) row[a * 9 + b * 3 + c] = make_float4(w * q.x, w * q.y, w * q.z, 0.f);
+                    else red_add_f4(gg_out + node, w * q.x, w * q.y, w * q.z, 0.f);
+                    float gw = fmaf(g.x, q.x, fmaf(g.y, q.y, g.z * q.z));       // d weight
+                    G0 = fmaf(gw, s.wz[c], G0); G1 = fmaf(gw, dwz[c], G1);
+                    R0.x = fmaf(s.wz[c], g.x, R0.x); R0.y = fmaf(s.wz[c], g.y, R0.y); R0.z = fmaf(s.wz[c], g.z, R0.z);
+                }
+                gfx.x = fmaf(dwx[a] * s.wy[b], G0, gfx.x);
+                gfx.y = fmaf(s.wx[a] * dwy[b], G0, gfx.y);
+                gfx.z = fmaf(wab, G1, gfx.z);
+                S0 += wab * R0;
             }
         }
+        // d dpos = k4 * w * gC^T g  ->  d fx -= sum = K^T S0
+        gfx -= Tmulv(K, S0);
+        aout[j] = gx1.x + P.inv_dx * gfx.x; aout[P.stride + j] = gx1.y + P.inv_dx * gfx.y; aout[2 * P.stride + j] = gx1.z + P.inv_dx * gfx.z;
     }
-    // d dpos = k4 * w * gC^T g  ->  d fx -= sum = K^T S0
-    gfx -= Tmulv(K, S0);
-    aout[j] = gx1.x + P.inv_dx * gfx.x; aout[P.stride + j] = gx1.y + P.inv_dx * gfx.y; aout[2 * P.stride + j] = gx1.z + P.inv_dx * gfx.z;
+    if (STAGED) warp_stage_flush(stage[threadIdx.x >> 5], pack_base(s.bx, s.by, s.bz), live, gg_out, P.nb);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -601,7 +667,7 @@ __global__ void __launch_bounds__(256) k_grid_grad(Params P, PrimSet ps, int f, 
 //   aout = adjoint of frame f: x holds the partial from g2p/contact grads; v, F, C are written
 // ------------------------------------------------------------------------------------------------
 template <int MAT>
-__global__ void __launch_bounds__(SMX_TPB) k_p2g_grad(Params P, PrimSet ps, int f, const float* __restrict__ fin, const float* __restrict__ ain,
+__global__ void __launch_bounds__(SMX_TPB, 4) k_p2g_grad(Params P, PrimSet ps, int f, const float* __restrict__ fin, const float* __restrict__ ain,
                                                       float* __restrict__ aout, const float4* __restrict__ gg, const int* __restrict__ ctrl_slot,
                                                       const float* __restrict__ action, double* __restrict__ action_grad) {
     constexpr int model = MAT / 3, ptype = MAT % 3;
@@ -630,21 +696,28 @@ __global__ void __launch_bounds__(SMX_TPB) k_p2g_grad(Params P, PrimSet ps, int 
 #pragma unroll
         for (int b = 0; b < 3; b++) {
             V3 qb = qa + (float)b * c1;
+            float wab = s.wx[a] * s.wy[b];
+            const float4* gp = gg + (s.ox[a] + s.oy[b]);
+            float G0 = 0.f, G1 = 0.f;       // sum_c gw wz[c], sum_c gw dwz[c]
+            V3 R0 = v3(0, 0, 0), Rz = v3(0, 0, 0);
 #pragma unroll
             for (int c = 0; c < 3; c++) {
                 V3 q = qb + (float)c * c2;      // value scattered to this node, per unit weight
-                float4 g = gg[s.ox[a] + s.oy[b] + s.oz[c]];
-                float w = s.wx[a] * s.wy[b] * s.wz[c];
-                float gw = g.x * q.x + g.y * q.y + g.z * q.z + g.w * P.p_mass;
-                gfx.x = fmaf(gw, dwx[a] * s.wy[b] * s.wz[c], gfx.x);
-                gfx.y = fmaf(gw, s.wx[a] * dwy[b] * s.wz[c], gfx.y);
-                gfx.z = fmaf(gw, s.wx[a] * s.wy[b] * dwz[c], gfx.z);
-                V3 wg = v3(w * g.x, w * g.y, w * g.z);
-                S0 += wg;
-                S1.m[0] += wg.x * a; S1.m[1] += wg.x * b; S1.m[2] += wg.x * c;
-                S1.m[3] += wg.y * a; S1.m[4] += wg.y * b; S1.m[5] += wg.y * c;
-                S1.m[6] += wg.z * a; S1.m[7] += wg.z * b; S1.m[8] += wg.z * c;
+                float4 g = gp[s.oz[c]];
+                float gw = fmaf(g.x, q.x, fmaf(g.y, q.y, fmaf(g.z, q.z, g.w * P.p_mass)));
+                G0 = fmaf(gw, s.wz[c], G0); G1 = fmaf(gw, dwz[c], G1);
+                float wz = s.wz[c];
+                R0.x = fmaf(wz, g.x, R0.x); R0.y = fmaf(wz, g.y, R0.y); R0.z = fmaf(wz, g.z, R0.z);
+                if (c) { float cw = (float)c * wz; Rz.x = fmaf(cw, g.x, Rz.x); Rz.y = fmaf(cw, g.y, Rz.y); Rz.z = fmaf(cw, g.z, Rz.z); }
             }
+            gfx.x = fmaf(dwx[a] * s.wy[b], G0, gfx.x);
+            gfx.y = fmaf(s.wx[a] * dwy[b], G0, gfx.y);
+            gfx.z = fmaf(wab, G1, gfx.z);
+            V3 r0 = wab * R0;
+            S0 += r0;
+            if (a) { S1.m[0] += a * r0.x; S1.m[3] += a * r0.y; S1.m[6] += a * r0.z; }
+            if (b) { S1.m[1] += b * r0.x; S1.m[4] += b * r0.y; S1.m[7] += b * r0.z; }
+            S1.m[2] = fmaf(wab, Rz.x, S1.m[2]); S1.m[5] = fmaf(wab, Rz.y, S1.m[5]); S1.m[8] = fmaf(wab, Rz.z, S1.m[8]);
         }
     }
     // d affine = sum w g (x) dpos = dx * (S1 - S0 (x) fx);  d fx -= dx * affine^T S0 = A^T S0
@@ -691,7 +764,7 @@ __global__ void __launch_bounds__(SMX_TPB) k_p2g_grad(Params P, PrimSet ps, int 
                     for (int jx = 0; jx < 3; jx++) {
                         if (jx == i) continue;
                         float de = e[jx] - e[i], dg = g3[jx] - g3[i];
-                        float K = 1.f / clamp_ref(de * (2.f + e[i] + e[jx]));
+                        float K = __fdividef(1.f, clamp_ref(de * (2.f + e[i] + e[jx])));
                         float P1 = dg + de + (g3[jx] * e[jx] - g3[i] * e[i]);
                         float Q1 = dg - de + (g3[jx] * e[i] - g3[i] * e[jx]);
                         inner.m[3 * i + jx] = K * (M1.m[3 * i + jx] * P1 + M1.m[3 * jx + i] * Q1 + (M2.m[3 * i + jx] - M2.m[3 * jx + i]) * de);
@@ -705,7 +778,7 @@ __global__ void __launch_bounds__(SMX_TPB) k_p2g_grad(Params P, PrimSet ps, int 
                     for (int jx = 0; jx < 3; jx++) {
                         if (jx == i) continue;
                         float de = e[jx] - e[i];
-                        float K = 1.f / clamp_ref(de * (2.f + e[i] + e[jx]));
+                        float K = __fdividef(1.f, clamp_ref(de * (2.f + e[i] + e[jx])));
                         inner.m[3 * i + jx] = K * (M2.m[3 * i + jx] - M2.m[3 * jx + i]) * de;
                     }
             }
@@ -833,6 +906,43 @@ __global__ void k_mark_blocks(Params P, const float* __restrict__ fr, int margin
                 uint32_t id = (uint32_t)((i * P.nb + jj) * P.nb + k);
                 if (!flags[id]) flags[id] = 1u;
             }
+}
+// same, driven by the SORTED key array: only the first particle of every distinct cell does the marking
+__global__ void k_mark_blocks_sorted(Params P, const uint32_t* __restrict__ keys_sorted, int margin, uint32_t* __restrict__ flags) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= P.n) return;
+    uint32_t key = keys_sorted[j];
+    if (j > 0 && keys_sorted[j - 1] == key) return;
+    int b[3];
+    {   // invert node_index: key = block * 64 + local
+        uint32_t blk = key >> 6, l = key & 63;
+        int bk = blk % P.nb, bj = (blk / P.nb) % P.nb, bi = blk / (P.nb * P.nb);
+        b[0] = bi * 4 + (l >> 4); b[1] = bj * 4 + ((l >> 2) & 3); b[2] = bk * 4 + (l & 3);
+    }
+    int lo[3], hi[3];
+    for (int d = 0; d < 3; d++) { lo[d] = max(b[d] - margin, 0) >> 2; hi[d] = min(b[d] + 2 + margin, P.ng - 1) >> 2; }
+    for (int i = lo[0]; i <= hi[0]; i++)
+        for (int jj = lo[1]; jj <= hi[1]; jj++)
+            for (int k = lo[2]; k <= hi[2]; k++) flags[(i * P.nb + jj) * P.nb + k] = 1u;
+}
+// grid checkpoints: the active blocks of up to three float4 grids <-> a compact per-substep record
+// record layout: [array][active-block slot][64 nodes]; `cap` = blocks reserved per array
+__global__ void __launch_bounds__(256) k_ckpt_copy(const uint32_t* __restrict__ blocks, const int* __restrict__ nblocks, int nb3, int cap,
+                                                    float4* __restrict__ rec, float4* __restrict__ a, float4* __restrict__ b, float4* __restrict__ c, int restore) {
+    int total = blocks ? *nblocks : nb3;
+    for (int bi = blockIdx.x * 4 + (threadIdx.x >> 6); bi < total; bi += gridDim.x * 4) {
+        uint32_t node = (blocks ? blocks[bi] : (uint32_t)bi) * 64u + (threadIdx.x & 63);
+        size_t slot = (size_t)bi * 64 + (threadIdx.x & 63);
+        if (restore) {
+            if (a) a[node] = rec[slot];
+            if (b) b[node] = rec[(size_t)cap * 64 + slot];
+            if (c) c[node] = rec[(size_t)2 * cap * 64 + slot];
+        } else {
+            if (a) rec[slot] = a[node];
+            if (b) rec[(size_t)cap * 64 + slot] = b[node];
+            if (c) rec[(size_t)2 * cap * 64 + slot] = c[node];
+        }
+    }
 }
 __global__ void k_compact_blocks(int nblk, const uint32_t* __restrict__ flags, uint32_t* __restrict__ list, int* __restrict__ count) {
     // order of the list does not matter (each entry is processed independently); one atomic per set flag

@@ -113,18 +113,29 @@ struct Svd { M3 U, V; float e[3]; };
 
 __device__ __forceinline__ void jacobi_rot(float& app, float& aqq, float& apq, float& arp, float& arq,
                                            float& v0p, float& v0q, float& v1p, float& v1q, float& v2p, float& v2q) {
-    // annihilate apq; r is the third index.  A <- J^T A J, V <- V J with J = [[c, s], [-s, c]] on (p, q)
-    if (fabsf(apq) < 1e-30f) return;
-    float theta = (aqq - app) / (2.f * apq);
-    float t = copysignf(1.f, theta) / (fabsf(theta) + sqrtf(fmaf(theta, theta, 1.f)));
-    float c = rsqrtf(fmaf(t, t, 1.f)), s = t * c;
-    app = app - t * apq; aqq = aqq + t * apq; apq = 0.f;
+    // annihilate apq; r is the third index.  A <- J^T A J, V <- V J with J = [[c, s], [-s, c]] on (p, q).
+    // t = tan(phi) = h / (d + sign(d) sqrt(d^2 + h^2)), d = aqq - app, h = 2 apq: branch-free, two MUFU.RSQ and
+    // one MUFU.RCP; c gets one Newton step so that V stays orthonormal to fp32 rounding.
+    float d = aqq - app, h = 2.f * apq;
+    float x = fmaf(d, d, h * h);
+    float r = x * rsqrtf(fmaxf(x, 1e-37f));
+    float den = d + copysignf(r, d);
+    float t = (x > 1e-37f) ? __fdividef(h, den) : 0.f;
+    float y = fmaf(t, t, 1.f);
+    float c = rsqrtf(y);
+    c = c * fmaf(-0.5f * y, c * c, 1.5f);
+    float s = t * c;
+    app = fmaf(-t, apq, app); aqq = fmaf(t, apq, aqq); apq = 0.f;
     float nrp = c * arp - s * arq, nrq = s * arp + c * arq; arp = nrp; arq = nrq;
     float a;
     a = c * v0p - s * v0q; v0q = s * v0p + c * v0q; v0p = a;
     a = c * v1p - s * v1q; v1q = s * v1p + c * v1q; v1p = a;
     a = c * v2p - s * v2q; v2q = s * v2p + c * v2q; v2p = a;
 }
+
+#ifndef SMX_JACOBI_SWEEPS
+#define SMX_JACOBI_SWEEPS 4
+#endif
 
 __device__ __forceinline__ Svd svd_dev(const M3& E) {
     // S = E + E^T + E^T E
@@ -136,7 +147,7 @@ __device__ __forceinline__ Svd svd_dev(const M3& E) {
     float s12 = E.m[5] + E.m[7] + (E.m[1] * E.m[2] + E.m[4] * E.m[5] + E.m[7] * E.m[8]);
     float v00 = 1.f, v01 = 0.f, v02 = 0.f, v10 = 0.f, v11 = 1.f, v12 = 0.f, v20 = 0.f, v21 = 0.f, v22 = 1.f;
 #pragma unroll 1
-    for (int sweep = 0; sweep < 5; sweep++) {
+    for (int sweep = 0; sweep < SMX_JACOBI_SWEEPS; sweep++) {
         jacobi_rot(s00, s11, s01, s02, s12, v00, v01, v10, v11, v20, v21);   // (0,1), r = 2
         jacobi_rot(s00, s22, s02, s01, s12, v00, v02, v10, v12, v20, v22);   // (0,2), r = 1
         jacobi_rot(s11, s22, s12, s01, s02, v01, v02, v11, v12, v21, v22);   // (1,2), r = 0

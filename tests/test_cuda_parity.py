@@ -244,9 +244,10 @@ def test_sort_contract_bit_exact():
     assert np.all(np.diff(k2.astype(np.int64)) >= 0)
 
 
-@pytest.mark.parametrize("flags", [1, 2])
+@pytest.mark.parametrize("flags", [1, 2, 4])
 def test_dense_and_unsorted_modes_agree(flags):
-    """SMX_FLAG_DENSE_GRID / SMX_FLAG_NO_SORT change the traversal, not the arithmetic (up to fp32 summation order)."""
+    """SMX_FLAG_DENSE_GRID / SMX_FLAG_NO_SORT / SMX_FLAG_DIRECT_RED change the traversal, not the arithmetic
+    (up to fp32 summation order)."""
     center = np.array([0.5, 0.3, 0.5])
 
     def run(fl):
@@ -263,6 +264,32 @@ def test_dense_and_unsorted_modes_agree(flags):
     assert np.abs(fa).max() > 0
     assert_state_close(a, b, tol=2e-5)
     assert rel_l2(fb, fa) <= 1e-4
+
+
+def test_grid_checkpoint_and_recompute_adjoints_agree():
+    """The adjoint either restores the per-substep grid checkpoint (default) or re-runs P2G + grid update
+    (SMX_FLAG_NO_GRID_CKPT, the reference's strategy, mpm_simulator.py:351-359): same gradients."""
+    center = np.array([0.5, 0.3, 0.5])
+
+    def run(fl):
+        rng = np.random.default_rng(265)
+        n, steps = 5000, 6
+        pair = Pair(n, tables=[scenes.sphere_table()], prim_params=[(0.5, 666.)], max_steps=8, sort_every=3, flags=fl)
+        s13 = np.concatenate([center, [1, 0, 0, 0], [0.0, 0.2, 0.0], [0, 0, 0.3]])
+        pair.prims[0].set_all_states(0, s13, f_end=8)
+        pair.gpu.reset(scenes.contact_rollout_state(n, rng, center))
+        for f in range(steps):
+            pair.gpu.substep(f)
+        pair.gpu.clear_all_gradients()
+        pair.gpu.add_x_grad(steps, rng.normal(size=(n, 3)))
+        ext = [rng.normal(size=6) * 1e-3]
+        for f in range(steps - 1, -1, -1):
+            pair.gpu.substep_grad(f, ext_f_grad=ext)
+        return pair.gpu.get_state_grad(0), pair.prims[0].get_all_states_grad(0, f_end=steps)
+
+    (ga, pa), (gb, pb) = run(0), run(8)
+    assert np.abs(ga).max() > 0 and np.abs(pa).max() > 0
+    assert rel_l2(ga, gb) <= 1e-5 and rel_l2(pa, pb) <= 1e-4
 
 
 def test_api_quirks_and_errors():
