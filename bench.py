@@ -76,7 +76,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.gpu)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -289,7 +289,7 @@ def run_cuda(args, rank, world, local_rank):
         t = torch.tensor([float(np.median(times))], device="cuda", dtype=torch.float64)
         if dist:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * args.n * S / float(t.item()), "unit": UNIT, "h2d_bytes_per_step": 2 * args.n * 24 * 4,
+        e2e = {"value": world * args.n * S / float(t.item()), "unit": UNIT, "h2d_bytes_per_step": args.n * 24 * 4 + args.n * 3 * 4,
                "d2h_bytes_per_step": args.n * 24 * 4, "checksum": float(np.abs(g0).sum())}
 
     if rank == 0:

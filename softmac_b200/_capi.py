@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libsoftmac_b200.so")
+LIB_PATH = os.environ.get("SMX_LIB") or os.path.join(_HERE, "lib", "libsoftmac_b200.so")
 
 SMX_FLAG_DENSE_GRID = 1
 SMX_FLAG_NO_SORT = 2

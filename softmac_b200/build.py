@@ -10,7 +10,7 @@ SOURCES = [os.path.join(CSRC, "smx_api.cu")]
 HEADERS = [os.path.join(CSRC, h) for h in ("smx_math.cuh", "smx_contact.cuh", "smx_kernels.cuh")] + \
           [os.path.join(os.path.dirname(HERE), "include", "softmac_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--use_fast_math=false",
-              "-Xcompiler", "-fPIC", "-Xcompiler", "-g", "-shared", "--extended-lambda", "-Xptxas", "-v"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-g", "-Xcompiler", "-fopenmp", "-shared", "--extended-lambda", "-Xptxas", "-v"]
 
 
 def nvcc():

@@ -96,7 +96,8 @@ struct smx_sim {
     // adjoint ping-pong
     float *adj_cur = nullptr, *adj_nxt = nullptr;
     int adj_frame = -1, adj_order = -1;
-    std::map<int, float*> seeds;        // frame -> device (n,24) fp32 AoS in particle-id order
+    struct Seed { float* dev = nullptr; int ncols = 24; };
+    std::map<int, Seed> seeds;          // frame -> device (n, 3 | 24) fp32 AoS in particle-id order
     // primitives
     std::vector<HostPrim> prims;
     PrimDev* prims_dev = nullptr;
@@ -326,7 +327,11 @@ static int upload_cols(smx_sim* s, int f, const double* host, int ncomp, int c0)
     if (n == 0) return SMX_OK;
     size_t cnt = (size_t)n * ncomp;
     CK(cudaStreamSynchronize(s->stream));       // staging buffer reuse
-    for (size_t i = 0; i < cnt; i++) s->stage_host[i] = (float)host[i];
+    {
+        float* dst = s->stage_host;
+        #pragma omp parallel for schedule(static)
+        for (long long i = 0; i < (long long)cnt; i++) dst[i] = (float)host[i];
+    }
     CK(cudaMemcpyAsync(s->stage_dev, s->stage_host, cnt * sizeof(float), cudaMemcpyHostToDevice, s->stream));
     const uint32_t* perm = s->orders[s->order_of[f]].perm;
     k_upload<<<nblk(n, 256), 256, 0, s->stream>>>(n, s->P.stride, s->stage_dev, ncomp, c0, s->frame_ptr(f), perm, 0); CKL(s);
@@ -339,7 +344,11 @@ static int download_cols(smx_sim* s, const float* frame, const uint32_t* perm, d
     k_download<<<nblk(n, 256), 256, 0, s->stream>>>(n, s->P.stride, s->stage_dev, ncomp, c0, frame, perm); CKL(s);
     CK(cudaMemcpyAsync(s->stage_host, s->stage_dev, cnt * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
-    for (size_t i = 0; i < cnt; i++) host[i] = (double)s->stage_host[i];
+    {
+        const float* src = s->stage_host;
+        #pragma omp parallel for schedule(static)
+        for (long long i = 0; i < (long long)cnt; i++) host[i] = (double)src[i];
+    }
     return SMX_OK;
 }
 static int ensure_order(smx_sim* s, int f) {
@@ -355,7 +364,7 @@ static int ensure_order(smx_sim* s, int f) {
 static int apply_seed(smx_sim* s, int f, float* adj, int order_id) {
     auto it = s->seeds.find(f);
     if (it == s->seeds.end() || s->P.n == 0) return SMX_OK;
-    k_upload<<<nblk(s->P.n, 256), 256, 0, s->stream>>>(s->P.n, s->P.stride, it->second, 24, 0, adj, s->orders[order_id].perm, 1); CKL(s);
+    k_upload<<<nblk(s->P.n, 256), 256, 0, s->stream>>>(s->P.n, s->P.stride, it->second.dev, it->second.ncols, 0, adj, s->orders[order_id].perm, 1); CKL(s);
     return SMX_OK;
 }
 
@@ -447,7 +456,7 @@ int smx_destroy(smx_sim* s) {
     cudaStreamSynchronize(s->stream);
     for (auto& o : s->orders) if (o.live) free_order(o);
     for (auto& o : s->free_orders) free_order(o);
-    for (auto& kv : s->seeds) cudaFree(kv.second);
+    for (auto& kv : s->seeds) cudaFree(kv.second.dev);
     for (auto& p : s->prims) { cudaFree(p.sdf_dev); cudaFree(p.nrm_dev); }
     void* ptrs[] = {s->ckpt, s->pool, s->g_in, s->g_out, s->g_mix, s->gg_out, s->gg_mix, s->g_lin, s->adj_cur, s->adj_nxt, s->stage_dev, s->keys_a, s->keys_b, s->iota, s->cub_tmp,
                     s->counters, s->prims_dev, s->pstate, s->pgrad, s->ext_f, s->ext_f_grad, s->abuf, s->gabuf, s->ctrl_id, s->action, s->action_grad};
@@ -514,13 +523,17 @@ int smx_reset(smx_sim* s, const double* state, int32_t ncols) {
     gc_orders(s);                       // every ordering is unreferenced now: recycle all of them
     int n = s->P.n;
     Order root; s->order_of[0] = new_order_id(s, root);
-    for (size_t p = 0; p < (size_t)n; p++) {
-        float* r = s->stage_host + 24 * p;
-        if (ncols == 24) for (int c = 0; c < 24; c++) r[c] = (float)state[24 * p + c];
-        else {
-            for (int c = 0; c < 24; c++) r[c] = 0.f;
-            r[0] = (float)state[3 * p]; r[1] = (float)state[3 * p + 1]; r[2] = (float)state[3 * p + 2];
-            r[6] = r[10] = r[14] = 1.f;
+    {
+        float* stage = s->stage_host;
+        #pragma omp parallel for schedule(static)
+        for (long long p = 0; p < (long long)n; p++) {
+            float* r = stage + 24 * p;
+            if (ncols == 24) for (int c = 0; c < 24; c++) r[c] = (float)state[24 * p + c];
+            else {
+                for (int c = 0; c < 24; c++) r[c] = 0.f;
+                r[0] = (float)state[3 * p]; r[1] = (float)state[3 * p + 1]; r[2] = (float)state[3 * p + 2];
+                r[6] = r[10] = r[14] = 1.f;
+            }
         }
     }
     if (n > 0) {
@@ -809,20 +822,33 @@ static int add_seed(smx_sim* s, int f, const double* g, int ncols) {
     if (n == 0) return SMX_OK;
     CK(cudaSetDevice(s->cfg.device));
     CK(cudaStreamSynchronize(s->stream));
-    for (size_t p = 0; p < (size_t)n; p++) {
-        float* r = s->stage_host + 24 * p;
-        if (ncols == 24) for (int c = 0; c < 24; c++) r[c] = (float)g[24 * p + c];
-        else { for (int c = 0; c < 24; c++) r[c] = 0.f; r[0] = (float)g[3 * p]; r[1] = (float)g[3 * p + 1]; r[2] = (float)g[3 * p + 2]; }
+    size_t cnt = (size_t)n * ncols;
+    {
+        float* dst = s->stage_host;
+        #pragma omp parallel for schedule(static)
+        for (long long i = 0; i < (long long)cnt; i++) dst[i] = (float)g[i];
     }
-    CK(cudaMemcpyAsync(s->stage_dev, s->stage_host, (size_t)n * 24 * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    CK(cudaMemcpyAsync(s->stage_dev, s->stage_host, cnt * sizeof(float), cudaMemcpyHostToDevice, s->stream));
     auto it = s->seeds.find(f);
-    if (it == s->seeds.end()) {
+    if (it != s->seeds.end() && it->second.ncols < ncols) {
+        // widen an x-only seed to the full 24 columns
         float* d = nullptr;
         CK(cudaMalloc(&d, (size_t)n * 24 * sizeof(float)));
-        CK(cudaMemcpyAsync(d, s->stage_dev, (size_t)n * 24 * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
-        s->seeds[f] = d;
-    } else {
-        k_axpy<<<nblk((long long)n * 24, 256), 256, 0, s->stream>>>((long long)n * 24, it->second, s->stage_dev); CKL(s);
+        CK(cudaMemsetAsync(d, 0, (size_t)n * 24 * sizeof(float), s->stream));
+        CK(cudaMemcpy2DAsync(d, 24 * sizeof(float), it->second.dev, 3 * sizeof(float), 3 * sizeof(float), n, cudaMemcpyDeviceToDevice, s->stream));
+        CK(cudaStreamSynchronize(s->stream));
+        cudaFree(it->second.dev);
+        it->second.dev = d; it->second.ncols = 24;
+    }
+    if (it == s->seeds.end()) {
+        smx_sim::Seed sd; sd.ncols = ncols;
+        CK(cudaMalloc(&sd.dev, cnt * sizeof(float)));
+        CK(cudaMemcpyAsync(sd.dev, s->stage_dev, cnt * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
+        s->seeds[f] = sd;
+    } else if (it->second.ncols == ncols) {
+        k_axpy<<<nblk((long long)cnt, 256), 256, 0, s->stream>>>((long long)cnt, it->second.dev, s->stage_dev); CKL(s);
+    } else {    // stored 24 columns, adding 3
+        k_add_cols<<<nblk(n, 256), 256, 0, s->stream>>>(n, it->second.dev, 24, s->stage_dev, 3); CKL(s);
     }
     CK(cudaStreamSynchronize(s->stream));
     return SMX_OK;
@@ -862,7 +888,7 @@ int smx_clear_grads(smx_sim* s) {
     if (!s) return fail(SMX_ERR_ARG, "smx_clear_grads: null simulator");
     CK(cudaSetDevice(s->cfg.device));
     CK(cudaStreamSynchronize(s->stream));
-    for (auto& kv : s->seeds) cudaFree(kv.second);
+    for (auto& kv : s->seeds) cudaFree(kv.second.dev);
     s->seeds.clear();
     s->adj_frame = -1; s->adj_order = -1;
     int T = s->cfg.max_steps;

@@ -666,8 +666,11 @@ __global__ void __launch_bounds__(256) k_grid_grad(Params P, PrimSet ps, int f, 
 //   ain  = adjoint of frame f+1 (only F, comps 6..14, is read here)
 //   aout = adjoint of frame f: x holds the partial from g2p/contact grads; v, F, C are written
 // ------------------------------------------------------------------------------------------------
+#ifndef SMX_P2GG_MINB
+#define SMX_P2GG_MINB 3   // measured on B200: 3 (168 regs, no spills) 150 us < 4 (128 regs) 153 us < 5 (96 regs) 166 us < 6 (80 regs) 193 us
+#endif
 template <int MAT>
-__global__ void __launch_bounds__(SMX_TPB, 4) k_p2g_grad(Params P, PrimSet ps, int f, const float* __restrict__ fin, const float* __restrict__ ain,
+__global__ void __launch_bounds__(SMX_TPB, SMX_P2GG_MINB) k_p2g_grad(Params P, PrimSet ps, int f, const float* __restrict__ fin, const float* __restrict__ ain,
                                                       float* __restrict__ aout, const float4* __restrict__ gg, const int* __restrict__ ctrl_slot,
                                                       const float* __restrict__ action, double* __restrict__ action_grad) {
     constexpr int model = MAT / 3, ptype = MAT % 3;
@@ -882,6 +885,12 @@ __global__ void k_permute_i32(int n, const int* __restrict__ src, int* __restric
 __global__ void k_axpy(long long n, float* __restrict__ y, const float* __restrict__ x) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) y[i] += x[i];
+}
+// dst (n, nd) += src (n, ns) on the first ns columns
+__global__ void k_add_cols(int n, float* __restrict__ dst, int nd, const float* __restrict__ src, int ns) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    for (int c = 0; c < ns; c++) dst[(size_t)j * nd + c] += src[(size_t)j * ns + c];
 }
 // block-major grid -> (i,j,k) linear order, for tests
 __global__ void k_grid_linear(int ng, int nb, const float4* __restrict__ g, float4* __restrict__ out) {
