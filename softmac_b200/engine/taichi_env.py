@@ -1,0 +1,96 @@
+"""``TaichiEnv`` -- the orchestration loop of ``softmac/engine/taichi_env.py`` (step / step_grad / backward / reset /
+compute_loss / set_copy) around injected components.
+
+The reference builds everything from a yacs cfg (URDF + trimesh primitives, Jade, pyrender); those builders are out
+of scope, so the components are passed in: any simulator with the ``MPMSimulator``
+surface, a ``Primitives`` container, a rigid simulator with the ``RigidSimulator`` surface and an optional loss with
+``compute_loss(f)`` / ``seed(f)``.  The control flow -- which is what couples the MPM hot path to the rigid
+simulator -- is the reference's, line for line (taichi_env.py:93-151).
+"""
+import numpy as np
+
+
+class TaichiEnv:
+    def __init__(self, simulator, primitives, rigid_simulator, init_particles, loss=None, control_mode="rigid",
+                 rigid_velocity_control=False):
+        assert control_mode in ("mpm", "rigid")
+        self.control_mode = control_mode
+        self.rigid_velocity_control = rigid_velocity_control
+        self.simulator, self.primitives, self.rigid_simulator, self.loss = simulator, primitives, rigid_simulator, loss
+        self.init_particles = np.asarray(init_particles, dtype=np.float64)
+        self.n_particles = len(self.init_particles)
+        self.substeps = simulator.substeps
+        self.use_loss = loss is not None
+        self._is_copy = False
+        self.action_list = []
+        self.initialize()
+
+    def set_copy(self, is_copy: bool):
+        self._is_copy = is_copy
+
+    def initialize(self):
+        self.primitives.initialize()
+        self.simulator.initialize()
+        self.rigid_simulator.initialize()
+        if self.loss:
+            self.loss.initialize()
+        self.reset()
+
+    def reset(self):
+        self.primitives.reset()
+        self.simulator.reset(self.init_particles)
+        self.rigid_simulator.reset()
+        if self.loss:
+            self.loss.reset()
+        self.action_list = []
+
+    def step(self, action=None):                                         # taichi_env.py:93-115
+        start = 0 if self._is_copy else self.simulator.cur
+        self.simulator.cur = start + self.substeps
+        mpm_action = action if self.control_mode == "mpm" else None
+        rigid_action = action if self.control_mode == "rigid" else None
+        self.action_list.append(action)
+        for s in range(start, self.simulator.cur):
+            self.simulator.substep(s, mpm_action)
+        self.rigid_simulator.step(start // self.substeps, rigid_action)
+        if self._is_copy:
+            self.simulator.copyframe(self.simulator.cur, 0)
+            self.simulator.cur = 0
+            if self.rigid_simulator.n_primitive > 0 and not self.rigid_velocity_control:
+                self.rigid_simulator.states = [self.rigid_simulator.states[-1], ]
+                self.rigid_simulator.jacob_ds_df = []
+                self.rigid_simulator.jacob_ds_ds = []
+                self.rigid_simulator.jacob_ds_da = []
+                self.rigid_simulator.jacob_external = []
+
+    def step_grad(self, action=None):                                    # taichi_env.py:117-137
+        start = self.simulator.cur
+        self.simulator.cur = start - self.substeps
+        mpm_action = action if self.control_mode == "mpm" else None
+        rigid_action = action if self.control_mode == "rigid" else None
+        rigid_action_grad, ext_f_grad_list = self.rigid_simulator.step_grad(self.simulator.cur // self.substeps, rigid_action)
+        mpm_action_grad = np.zeros(np.shape(action)) if action is not None else None
+        for s in range(start - 1, self.simulator.cur - 1, -1):
+            tmp = self.simulator.substep_grad(s, action=mpm_action, ext_f_grad=ext_f_grad_list if ext_f_grad_list else None)
+            if tmp is not None:
+                mpm_action_grad += tmp
+        if action is None:
+            return None
+        return mpm_action_grad if self.control_mode == "mpm" else rigid_action_grad
+
+    def backward(self):                                                  # taichi_env.py:139-151
+        if not self.rigid_velocity_control:
+            self.rigid_simulator.state_grad = np.zeros(self.rigid_simulator.state_dim)
+        total_steps = self.simulator.cur // self.substeps
+        action_grad = []
+        for s in range(total_steps - 1, -1, -1):
+            action_grad = [self.step_grad(self.action_list[s])] + action_grad
+        if not self.rigid_velocity_control:
+            self.rigid_simulator.state_grad = self.rigid_simulator.state_grad + self.rigid_simulator.get_ext_state_grad(0)
+        return np.vstack(action_grad)
+
+    def compute_loss(self, f=None, **kwargs):
+        assert self.loss is not None
+        if f is None:
+            f = 0 if self._is_copy else self.simulator.cur
+        return self.loss.compute_loss(f, **kwargs)

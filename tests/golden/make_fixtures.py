@@ -1,0 +1,79 @@
+"""Generates tests/golden/*.npz.  Run HERE (needs /root/reference, which does not exist on the GPU box):
+
+    python tests/golden/make_fixtures.py
+
+Inputs come from the reference's own data fixtures:
+  softmac/envs/grip/grip_mpm_init_state.npy            (10000, 24) f64  -- initial plasticine state of demo_grip
+  softmac/assets/gripper/68956732...                   cached SDF pickle of the gripper palm (mesh.py:148-163)
+Outputs ("golden vectors") come from the f64 oracle, because the reference itself (Taichi 1.4.1) cannot be imported
+in this image -- they are REGRESSION pins of the restatement, not outputs of the reference (parity unpinned).
+
+grip_palm_contact.npz : 2500 grip particles (fp32-rounded), the palm SDF (fp32) pressed into the top of the blob,
+                        5 substeps (substeps = 5 => life = 1/5 .. 1), demo_grip material (plastic, corotated, E 3e3,
+                        nu 0.2, gravity -9.8, sticky floor, mixed contact, softness 666, friction 0.001), then the adjoint
+                        of a dense seed x_bar[5] = x[5] - mean and a wrench seed.
+"""
+import os
+import pickle
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+REF = "/root/reference/softmac"
+
+
+def main():
+    from oracle import mpm_oracle as mo
+    st = np.load(os.path.join(REF, "envs/grip/grip_mpm_init_state.npy"))
+    rng = np.random.default_rng(0)
+    sel = np.sort(rng.choice(len(st), 2500, replace=False))
+    st = st[sel].astype(np.float32).astype(np.float64)
+    with open(os.path.join(REF, "assets/gripper/68956732a79bf09d8703ab990a2e2319bf5492c792294e9a86632db03b5ac4d5"), "rb") as f:
+        blob = pickle.load(f)["sdf"]
+    sdf = blob["sdf"].astype(np.float32)
+    nrm = blob["normal"].astype(np.float32)
+    lower, upper = [np.asarray(p, dtype=np.float32) for p in blob["position"]]
+    dx = float(blob["dx"][0])
+    # palm box is 0.6 x 0.3 x 0.16 (half extents 0.3, 0.15, 0.08); rotate it so that its thin axis (z) points up (+y) and press
+    # its bottom face 4 mm into the top of the plasticine blob, moving down at 0.3 m/s with a small spin
+    ymax = st[:, 1].max()
+    c, s_ = np.cos(-np.pi / 4), np.sin(-np.pi / 4)          # rotation by -90 deg about x: (w, x, y, z)
+    quat = np.array([c, s_, 0.0, 0.0])
+    pos = np.array([0.5, ymax + 0.08 - 0.004, 0.5])
+    s13 = np.concatenate([pos, quat, [0.0, -0.3, 0.0], [0.0, 0.0, 0.5]]).astype(np.float32).astype(np.float64)
+    steps = 5
+    sim = mo.OracleSim(len(st), n_grid=64, max_steps=steps + 1, dt=2e-4, E=3e3, nu=0.2, gravity=(0., -9.8, 0.), ground_friction=20.,
+                       material_model=0, ptype=0, collision_type=2, substeps=5)
+    sim.add_primitive(sdf.astype(np.float64), nrm.astype(np.float64), lower.astype(np.float64), upper.astype(np.float64), dx,
+                      friction=0.001, softness=666.)
+    for f in range(steps + 1):
+        sim.set_primitive_state(0, f, s13)
+    sim.set_frame(0, st)
+    frames = [st]
+    for f in range(steps):
+        sim.substep(f)
+        frames.append(sim.get_frame(f + 1))
+    ext_f = sim.get_ext_f(0)
+    assert np.abs(ext_f).max() > 0, "fixture must exercise contact"
+    seed = frames[-1][:, :3] - frames[-1][:, :3].mean(0)
+    g24 = np.zeros_like(st); g24[:, :3] = seed
+    ext_seed = np.array([1e-3, -2e-3, 5e-4, 1e-4, 2e-4, -1e-4])
+    sim.clear_grads()
+    sim.add_frame_grad(steps, g24)
+    for f in range(steps - 1, -1, -1):
+        sim.set_ext_f_grad(0, ext_seed)
+        sim.substep_grad(f)
+    adj0 = sim.get_frame_grad(0)
+    pgrad = np.stack([sim.get_primitive_state_grad(0, f) for f in range(steps)])
+    out = os.path.join(HERE, "grip_palm_contact.npz")
+    np.savez_compressed(out, state0=st.astype(np.float32), sdf=sdf, normal=nrm, lower=lower, upper=upper, sdf_dx=np.float64(dx),
+                        prim_state=s13, steps=np.int32(steps), state_final=frames[-1], state_1=frames[1], ext_f=ext_f,
+                        seed_x=seed, ext_seed=ext_seed, adj0=adj0, prim_grad=pgrad, particle_index=sel.astype(np.int32))
+    print("wrote", out, os.path.getsize(out) / 1e6, "MB; ext_f", ext_f, "| |adj0|", np.linalg.norm(adj0), "| prim grad", np.abs(pgrad).max())
+
+
+if __name__ == "__main__":
+    main()
