@@ -67,6 +67,13 @@ struct WarpStage {
 };
 __device__ __forceinline__ uint32_t pack_base(int bx, int by, int bz) { return (uint32_t)bx | ((uint32_t)by << 8) | ((uint32_t)bz << 16); }
 
+// packed fp32x2 add (sm_100a: one FADD2 instead of two FADD)
+__device__ __forceinline__ void add_f4(float4& a, const float4& b) {
+    float2 lo = __fadd2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y));
+    float2 hi = __fadd2_rn(make_float2(a.z, a.w), make_float2(b.z, b.w));
+    a = make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+
 __device__ __forceinline__ void warp_stage_flush(WarpStage& st, uint32_t key, bool live, float4* __restrict__ grid, int nb) {
     const unsigned lane = threadIdx.x & 31;
     uint32_t k = live ? key : 0xffffffffu;
@@ -84,11 +91,19 @@ __device__ __forceinline__ void warp_stage_flush(WarpStage& st, uint32_t key, bo
         uint32_t kk = st.key[r];
         if (kk == 0xffffffffu) continue;
         int p0 = st.start[r], p1 = st.start[r + 1];
-        float4 acc = st.val[p0 * 27 + o];
-        for (int p = p0 + 1; p < p1; p++) {
-            float4 v = st.val[p * 27 + o];
-            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        const float4* src = st.val + p0 * 27 + o;
+        float4 acc = src[0];
+        int cnt = p1 - p0 - 1;
+        src += 27;
+        // two independent accumulators, four particles per trip
+        float4 acc2 = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (; cnt >= 4; cnt -= 4, src += 4 * 27) {
+            float4 v0 = src[0], v1 = src[27], v2 = src[54], v3 = src[81];
+            add_f4(acc, v0); add_f4(acc2, v1); add_f4(acc, v2); add_f4(acc2, v3);
         }
+        if (cnt >= 2) { float4 v0 = src[0], v1 = src[27]; add_f4(acc, v0); add_f4(acc2, v1); src += 2 * 27; cnt -= 2; }
+        if (cnt >= 1) { float4 v0 = src[0]; add_f4(acc, v0); }
+        add_f4(acc, acc2);
         int a = o / 9, b = (o - 9 * a) / 3, c = o - 9 * a - 3 * b;
         atomicAdd(grid + node_index((int)(kk & 0xffu) + a, (int)((kk >> 8) & 0xffu) + b, (int)(kk >> 16) + c, nb), acc);
     }
@@ -686,6 +701,7 @@ __global__ void __launch_bounds__(SMX_TPB, SMX_P2GG_MINB) k_p2g_grad(Params P, P
     M3 A;
 #pragma unroll
     for (int i = 0; i < 9; i++) A.m[i] = (P.cs * m.stress.m[i] + P.p_mass * C.m[i]) * P.dx;
+    // (an L1 prefetch of the 27 gather nodes before the SVD was measured on B200: 148 -> 158 us, so it is not used)
     Stencil s = make_stencil(x.x, x.y, x.z, P);
     float dwx[3], dwy[3], dwz[3];
     axis_dweights(s.fx, dwx); axis_dweights(s.fy, dwy); axis_dweights(s.fz, dwz);
