@@ -164,8 +164,11 @@ __device__ __forceinline__ Svd svd_dev(const M3& E) {
     if (flip) { v02 = -v02; v12 = -v12; v22 = -v22; }
     Svd r;
     r.V.m[0] = v00; r.V.m[1] = v01; r.V.m[2] = v02; r.V.m[3] = v10; r.V.m[4] = v11; r.V.m[5] = v12; r.V.m[6] = v20; r.V.m[7] = v21; r.V.m[8] = v22;
-    float sg0 = sqrtf(fmaxf(1.f + l0, 0.f)), sg1 = sqrtf(fmaxf(1.f + l1, 0.f)), sg2 = sqrtf(fmaxf(1.f + l2, 0.f));
-    r.e[0] = l0 / (1.f + sg0); r.e[1] = l1 / (1.f + sg1); r.e[2] = l2 / (1.f + sg2);
+    // sigma = sqrt(1 + lambda) as x * rsqrt(x) (2 ulp) and sigma - 1 = lambda / (1 + sigma) with a fast reciprocal:
+    // both errors are relative, i.e. ~1e-7 of the *deviation*
+    float y0 = fmaxf(1.f + l0, 0.f), y1 = fmaxf(1.f + l1, 0.f), y2 = fmaxf(1.f + l2, 0.f);
+    float sg0 = y0 * rsqrtf(fmaxf(y0, 1e-37f)), sg1 = y1 * rsqrtf(fmaxf(y1, 1e-37f)), sg2 = y2 * rsqrtf(fmaxf(y2, 1e-37f));
+    r.e[0] = __fdividef(l0, 1.f + sg0); r.e[1] = __fdividef(l1, 1.f + sg1); r.e[2] = __fdividef(l2, 1.f + sg2);
     // B = F V = V + E V ; U from Gram-Schmidt on its columns (they are orthogonal up to rounding)
     M3 B = add(r.V, mul(E, r.V));
     V3 b0 = v3(B.m[0], B.m[3], B.m[6]), b1 = v3(B.m[1], B.m[4], B.m[7]), b2 = v3(B.m[2], B.m[5], B.m[8]);
