@@ -65,6 +65,9 @@ typedef struct {
     int32_t device;               /* CUDA device ordinal */
     int32_t flags;                /* SMX_FLAG_* */
     void* stream;                 /* cudaStream_t to run on; NULL -> the library creates its own */
+    int32_t n_batch;              /* independent rollouts batched in this handle (0/1: one).  n_particles, primitives' states,
+                                     wrenches and actions are PER BATCH; particle arrays at the API have n_batch * n_particles
+                                     rows, batch-major (BASELINE config 4: several rollouts per GPU in one handle) */
 } smx_config;
 
 #define SMX_FLAG_DENSE_GRID 1     /* sweep the whole grid every substep instead of the active-block list */
@@ -119,12 +122,22 @@ int smx_get_ext_f(smx_sim* sim, int32_t id, double* out6);
 int smx_clear_ext_f(smx_sim* sim, int32_t id);
 /* Primitive.set_ext_f_grad(g6) (primitive_base.py:189-192) */
 int smx_set_ext_f_grad(smx_sim* sim, int32_t id, const double* g6);
+/* batch-addressed variants of the six calls above (n_batch > 1: every rollout has its own rigid bodies).  The
+ * un-suffixed setters / clears act on every batch, the un-suffixed getters on batch 0. */
+int smx_set_primitive_state_b(smx_sim* sim, int32_t batch, int32_t id, int32_t f0, int32_t f1, const double* s13);
+int smx_get_primitive_state_b(smx_sim* sim, int32_t batch, int32_t id, int32_t f, double* out13);
+int smx_get_primitive_state_grad_b(smx_sim* sim, int32_t batch, int32_t id, int32_t f0, int32_t f1, double* out13);
+int smx_add_primitive_state_grad_b(smx_sim* sim, int32_t batch, int32_t id, int32_t f, const double* g13);
+int smx_get_ext_f_b(smx_sim* sim, int32_t batch, int32_t id, double* out6);
+int smx_clear_ext_f_b(smx_sim* sim, int32_t batch, int32_t id);
+int smx_set_ext_f_grad_b(smx_sim* sim, int32_t batch, int32_t id, const double* g6);
 /* velocity-control mode: Primitive.set_action(s, n, a6) / get_action_grad(s, n) (primitive_base.py:285-319) */
 int smx_set_primitive_action(smx_sim* sim, int32_t id, int32_t s, int32_t n, const double* a6);
 int smx_get_primitive_action_grad(smx_sim* sim, int32_t id, int32_t s, int32_t n, double* out6);
 
 /* particle-force control ("mpm" control mode) --------------------------------------------------- */
-/* MPMSimulator.set_action(action (n_control,3)); also zeroes action.grad (mpm_simulator.py:579-592) */
+/* MPMSimulator.set_action(action (n_control,3)); also zeroes action.grad (mpm_simulator.py:579-592).
+ * With n_batch > 1 the array is (n_batch * n_control, 3), batch-major (likewise smx_get_action_grad). */
 int smx_set_action(smx_sim* sim, const double* action);
 /* MPMSimulator.set_control_idx(idx (n,) int, -1 = uncontrolled) (mpm_simulator.py:594-602) */
 int smx_set_control_idx(smx_sim* sim, const int32_t* idx);

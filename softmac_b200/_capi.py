@@ -25,7 +25,7 @@ class SmxConfig(C.Structure):
         ("ground_friction", C.c_double),
         ("material_model", C.c_int32), ("ptype", C.c_int32), ("collision_type", C.c_int32), ("substeps", C.c_int32),
         ("n_control", C.c_int32), ("rigid_velocity_control", C.c_int32), ("sort_every", C.c_int32),
-        ("device", C.c_int32), ("flags", C.c_int32), ("stream", C.c_void_p),
+        ("device", C.c_int32), ("flags", C.c_int32), ("stream", C.c_void_p), ("n_batch", C.c_int32),
     ]
 
 
@@ -65,6 +65,13 @@ _SIGS = {
     "smx_get_ext_f": [vp, C.c_int32, dp],
     "smx_clear_ext_f": [vp, C.c_int32],
     "smx_set_ext_f_grad": [vp, C.c_int32, dp],
+    "smx_set_primitive_state_b": [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, dp],
+    "smx_get_primitive_state_b": [vp, C.c_int32, C.c_int32, C.c_int32, dp],
+    "smx_get_primitive_state_grad_b": [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, dp],
+    "smx_add_primitive_state_grad_b": [vp, C.c_int32, C.c_int32, C.c_int32, dp],
+    "smx_get_ext_f_b": [vp, C.c_int32, C.c_int32, dp],
+    "smx_clear_ext_f_b": [vp, C.c_int32, C.c_int32],
+    "smx_set_ext_f_grad_b": [vp, C.c_int32, C.c_int32, dp],
     "smx_set_primitive_action": [vp, C.c_int32, C.c_int32, C.c_int32, dp],
     "smx_get_primitive_action_grad": [vp, C.c_int32, C.c_int32, C.c_int32, dp],
     "smx_set_action": [vp, dp],

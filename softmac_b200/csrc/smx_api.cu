@@ -73,6 +73,7 @@ struct smx_sim {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     int sm_count = 148;
+    int B = 1;                          // batched independent rollouts
     bool dense = true;
     // particle frames
     float* pool = nullptr;
@@ -129,6 +130,7 @@ struct smx_sim {
 };
 
 static inline int nblk(long long n, int t) { return (int)((n + t - 1) / t); }
+static inline size_t prim_slot_of(int b, int id) { return (size_t)b * SMX_MAXP + id; }
 
 // profiling: an event after every launch of a profiled substep (smx_profile_substep)
 static int prof_mark(smx_sim* s, const char* name) {
@@ -189,7 +191,7 @@ static int alloc_order(smx_sim* s, Order& o, bool need_idx) {
 
 static int build_blocks(smx_sim* s, Order& o, const float* frame, const uint32_t* keys_sorted = nullptr) {
     if (s->dense) return SMX_OK;
-    int nb3 = s->P.nb * s->P.nb * s->P.nb;
+    int nb3 = s->B * s->P.nb3;
     if (!o.flags) {
         CK(cudaMalloc(&o.flags, nb3 * sizeof(uint32_t))); CK(cudaMalloc(&o.blocks, nb3 * sizeof(uint32_t))); CK(cudaMalloc(&o.nblocks, sizeof(int)));
     }
@@ -299,7 +301,7 @@ static int forward_to_grid(smx_sim* s, int f, bool write_F, bool accumulate) {
         }));
     }
     if (write_F && s->cfg.rigid_velocity_control && !s->prims.empty()) {
-        k_forward_kinematics<<<1, 32, 0, s->stream>>>(s->pstate, s->cfg.max_steps, (int)s->prims.size(), f, P.dt); CKL(s);
+        k_forward_kinematics<<<nblk((long long)s->prims.size() * s->B, 64), 64, 0, s->stream>>>(s->pstate, s->cfg.max_steps, (int)s->prims.size(), s->B, f, P.dt); CKL(s);
     }
     k_grid_op<<<grid_blocks_launch(s), 256, 0, s->stream>>>(P, ps, f, s->dense ? nullptr : o.blocks, o.nblocks, s->g_in, s->g_out, contact ? s->g_mix : nullptr, accumulate ? 1 : 0);
     CKLN(s, "k_grid_op");
@@ -391,6 +393,12 @@ int smx_create(const smx_config* cfg, smx_sim** out) {
     if (cfg->stream) s->stream = (cudaStream_t)cfg->stream; else { CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)); s->own_stream = true; }
     Params& P = s->P;
     int n = cfg->n_particles;
+    const int B = std::max(cfg->n_batch, 1);
+    if (B > 255) { delete s; return fail(SMX_ERR_ARG, "smx_create: at most 255 batched rollouts per handle"); }
+    if (cfg->n_grid > 256) { delete s; return fail(SMX_ERR_ARG, "smx_create: n_grid <= 256 (8-bit base-cell packing of the staged scatter)"); }
+    if ((long long)B * cfg->n_particles > 2000000000LL) { delete s; return fail(SMX_ERR_ARG, "smx_create: n_batch * n_particles too large"); }
+    P.nbatch = B; P.npb = cfg->n_particles;
+    n = B * cfg->n_particles;           // total particle slots of the handle
     P.n = n; P.stride = ((long long)std::max(n, 1) + 31) / 32 * 32;
     P.ng = cfg->n_grid; P.nb = cfg->n_grid / 4;
     double dx = 1.0 / cfg->n_grid, p_vol = (dx * 0.5) * (dx * 0.5), p_mass = p_vol;       // mpm_simulator.py:32-35
@@ -402,7 +410,9 @@ int smx_create(const smx_config* cfg, smx_sim** out) {
     P.sticky = cfg->ground_friction >= 10.0;
     P.material = cfg->material_model; P.ptype = cfg->ptype; P.ctype = cfg->collision_type; P.substeps = cfg->substeps; P.n_control = cfg->n_control; P.np = 0;
     s->dense = (cfg->flags & SMX_FLAG_DENSE_GRID) || (cfg->flags & SMX_FLAG_NO_SORT) || cfg->sort_every <= 0;
-    s->G = (size_t)P.ng * P.ng * P.ng;
+    P.Gb = P.ng * P.ng * P.ng; P.nb3 = P.nb * P.nb * P.nb;
+    s->G = (size_t)B * P.Gb;
+    s->B = B;
     s->frame_floats = 24 * P.stride;
     int T = cfg->max_steps;
     s->slot_of.resize(T); s->order_of.assign(T, -1); s->trans_from.assign(T, -1);
@@ -415,7 +425,7 @@ int smx_create(const smx_config* cfg, smx_sim** out) {
         // reserve one record per substep: all blocks of the grid for g_in and g_out, plus g_mix when the forecast
         // contact model is on; skipped (adjoint recomputes instead) when that would not fit comfortably
         int narr = cfg->collision_type == 2 ? 3 : 2;
-        s->ckpt_cap = P.nb * P.nb * P.nb;
+        s->ckpt_cap = B * P.nb3;
         s->ckpt_rec = (size_t)narr * s->ckpt_cap * 64;
         size_t bytes = (size_t)T * s->ckpt_rec * sizeof(float4), free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);
@@ -434,13 +444,13 @@ int smx_create(const smx_config* cfg, smx_sim** out) {
     CK(cudaMalloc(&s->cub_tmp, s->cub_bytes));
     CK(cudaMalloc(&s->counters, 4 * sizeof(unsigned long long))); CK(cudaMemsetAsync(s->counters, 0, 4 * sizeof(unsigned long long), s->stream));
     CK(cudaMalloc(&s->prims_dev, SMX_MAXP * sizeof(PrimDev)));
-    CK(cudaMalloc(&s->pstate, (size_t)SMX_MAXP * T * 13 * sizeof(float))); CK(cudaMemsetAsync(s->pstate, 0, (size_t)SMX_MAXP * T * 13 * sizeof(float), s->stream));
-    CK(cudaMalloc(&s->pgrad, (size_t)SMX_MAXP * T * 13 * sizeof(double))); CK(cudaMemsetAsync(s->pgrad, 0, (size_t)SMX_MAXP * T * 13 * sizeof(double), s->stream));
-    CK(cudaMalloc(&s->ext_f, SMX_MAXP * 6 * sizeof(double))); CK(cudaMemsetAsync(s->ext_f, 0, SMX_MAXP * 6 * sizeof(double), s->stream));
-    CK(cudaMalloc(&s->ext_f_grad, SMX_MAXP * 6 * sizeof(float))); CK(cudaMemsetAsync(s->ext_f_grad, 0, SMX_MAXP * 6 * sizeof(float), s->stream));
-    CK(cudaMalloc(&s->abuf, (size_t)SMX_MAXP * T * 6 * sizeof(float))); CK(cudaMemsetAsync(s->abuf, 0, (size_t)SMX_MAXP * T * 6 * sizeof(float), s->stream));
-    CK(cudaMalloc(&s->gabuf, (size_t)SMX_MAXP * T * 6 * sizeof(double))); CK(cudaMemsetAsync(s->gabuf, 0, (size_t)SMX_MAXP * T * 6 * sizeof(double), s->stream));
-    int nc = std::max(cfg->n_control, 1);
+    CK(cudaMalloc(&s->pstate, (size_t)B * SMX_MAXP * T * 13 * sizeof(float))); CK(cudaMemsetAsync(s->pstate, 0, (size_t)B * SMX_MAXP * T * 13 * sizeof(float), s->stream));
+    CK(cudaMalloc(&s->pgrad, (size_t)B * SMX_MAXP * T * 13 * sizeof(double))); CK(cudaMemsetAsync(s->pgrad, 0, (size_t)B * SMX_MAXP * T * 13 * sizeof(double), s->stream));
+    CK(cudaMalloc(&s->ext_f, (size_t)B * SMX_MAXP * 6 * sizeof(double))); CK(cudaMemsetAsync(s->ext_f, 0, (size_t)B * SMX_MAXP * 6 * sizeof(double), s->stream));
+    CK(cudaMalloc(&s->ext_f_grad, (size_t)B * SMX_MAXP * 6 * sizeof(float))); CK(cudaMemsetAsync(s->ext_f_grad, 0, (size_t)B * SMX_MAXP * 6 * sizeof(float), s->stream));
+    CK(cudaMalloc(&s->abuf, (size_t)B * SMX_MAXP * T * 6 * sizeof(float))); CK(cudaMemsetAsync(s->abuf, 0, (size_t)B * SMX_MAXP * T * 6 * sizeof(float), s->stream));
+    CK(cudaMalloc(&s->gabuf, (size_t)B * SMX_MAXP * T * 6 * sizeof(double))); CK(cudaMemsetAsync(s->gabuf, 0, (size_t)B * SMX_MAXP * T * 6 * sizeof(double), s->stream));
+    int nc = std::max(cfg->n_control, 1) * B;
     CK(cudaMalloc(&s->ctrl_id, std::max(n, 1) * sizeof(int))); CK(cudaMemsetAsync(s->ctrl_id, 0xff, std::max(n, 1) * sizeof(int), s->stream));
     CK(cudaMalloc(&s->action, nc * 3 * sizeof(float))); CK(cudaMemsetAsync(s->action, 0, nc * 3 * sizeof(float), s->stream));
     CK(cudaMalloc(&s->action_grad, nc * 3 * sizeof(double))); CK(cudaMemsetAsync(s->action_grad, 0, nc * 3 * sizeof(double), s->stream));
@@ -582,56 +592,77 @@ int smx_copy_frame(smx_sim* s, int32_t src, int32_t dst) {
         CK(cudaMemcpyAsync(s->frame_ptr(dst), s->frame_ptr(src), s->frame_floats * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
         s->order_of[dst] = s->order_of[src]; s->trans_from[dst] = -1; s->ckpt_order[dst] = -1;
         int T = s->cfg.max_steps;
-        for (size_t i = 0; i < s->prims.size(); i++)
-            for (int j = 0; j < s->cfg.substeps; j++) {
-                if (src + j >= T || dst + j >= T) break;
-                CK(cudaMemcpyAsync(s->pstate + (i * T + dst + j) * 13, s->pstate + (i * T + src + j) * 13, 13 * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
-                CK(cudaMemcpyAsync(s->abuf + (i * T + dst + j) * 6, s->abuf + (i * T + src + j) * 6, 6 * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
+        for (int b = 0; b < s->B; b++)
+            for (size_t ii = 0; ii < s->prims.size(); ii++) {
+                size_t i = prim_slot_of(b, (int)ii);
+                for (int j = 0; j < s->cfg.substeps; j++) {
+                    if (src + j >= T || dst + j >= T) break;
+                    CK(cudaMemcpyAsync(s->pstate + (i * T + dst + j) * 13, s->pstate + (i * T + src + j) * 13, 13 * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
+                    CK(cudaMemcpyAsync(s->abuf + (i * T + dst + j) * 6, s->abuf + (i * T + src + j) * 6, 6 * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
+                }
             }
     }
     return SMX_OK;
 }
 
 // ---- primitives ---------------------------------------------------------------------------------
-int smx_set_primitive_state(smx_sim* s, int32_t id, int32_t f0, int32_t f1, const double* s13) {
-    TRY(check_prim(s, id, "smx_set_primitive_state"));
+// Batch-addressed implementations; the un-suffixed entry points act on every batch (setters / clears) or on batch 0
+// (getters), which is the whole handle when n_batch == 1.
+static int check_batch(smx_sim* s, int b, const char* what) {
+    if (b < 0 || b >= s->B) return fail(SMX_ERR_RANGE, "%s: batch %d outside [0, %d)", what, b, s->B);
+    return SMX_OK;
+}
+static inline size_t prim_slot(smx_sim* s, int b, int id) { return (size_t)b * SMX_MAXP + id; }
+
+static int set_prim_state(smx_sim* s, int b0, int b1, int id, int f0, int f1, const double* s13) {
     if (!s13) return fail(SMX_ERR_ARG, "smx_set_primitive_state: null state");
     if (f0 < 0 || f1 > s->cfg.max_steps || f0 >= f1) return fail(SMX_ERR_RANGE, "smx_set_primitive_state: frame range [%d, %d) outside [0, %d)", f0, f1, s->cfg.max_steps);
     CK(cudaSetDevice(s->cfg.device));
     std::vector<float> h((size_t)(f1 - f0) * 13);
     for (int f = 0; f < f1 - f0; f++) for (int c = 0; c < 13; c++) h[(size_t)f * 13 + c] = (float)s13[c];
-    CK(cudaMemcpyAsync(s->pstate + ((size_t)id * s->cfg.max_steps + f0) * 13, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    for (int b = b0; b < b1; b++)
+        CK(cudaMemcpyAsync(s->pstate + (prim_slot(s, b, id) * s->cfg.max_steps + f0) * 13, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, s->stream));
     CK(cudaStreamSynchronize(s->stream));
     return SMX_OK;
 }
-int smx_get_primitive_state(smx_sim* s, int32_t id, int32_t f, double* out13) {
-    TRY(check_prim(s, id, "smx_get_primitive_state")); TRY(check_frame(s, f, "smx_get_primitive_state"));
+int smx_set_primitive_state(smx_sim* s, int32_t id, int32_t f0, int32_t f1, const double* s13) {
+    TRY(check_prim(s, id, "smx_set_primitive_state"));
+    return set_prim_state(s, 0, s->B, id, f0, f1, s13);
+}
+int smx_set_primitive_state_b(smx_sim* s, int32_t batch, int32_t id, int32_t f0, int32_t f1, const double* s13) {
+    TRY(check_prim(s, id, "smx_set_primitive_state_b")); TRY(check_batch(s, batch, "smx_set_primitive_state_b"));
+    return set_prim_state(s, batch, batch + 1, id, f0, f1, s13);
+}
+int smx_get_primitive_state_b(smx_sim* s, int32_t batch, int32_t id, int32_t f, double* out13) {
+    TRY(check_prim(s, id, "smx_get_primitive_state")); TRY(check_frame(s, f, "smx_get_primitive_state")); TRY(check_batch(s, batch, "smx_get_primitive_state"));
     if (!out13) return fail(SMX_ERR_ARG, "smx_get_primitive_state: null output");
     CK(cudaSetDevice(s->cfg.device));
     float h[13];
-    CK(cudaMemcpyAsync(h, s->pstate + ((size_t)id * s->cfg.max_steps + f) * 13, sizeof h, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaMemcpyAsync(h, s->pstate + (prim_slot(s, batch, id) * s->cfg.max_steps + f) * 13, sizeof h, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
     for (int c = 0; c < 13; c++) out13[c] = h[c];
     return SMX_OK;
 }
-int smx_get_primitive_state_grad(smx_sim* s, int32_t id, int32_t f0, int32_t f1, double* out13) {
-    TRY(check_prim(s, id, "smx_get_primitive_state_grad"));
+int smx_get_primitive_state(smx_sim* s, int32_t id, int32_t f, double* out13) { return smx_get_primitive_state_b(s, 0, id, f, out13); }
+int smx_get_primitive_state_grad_b(smx_sim* s, int32_t batch, int32_t id, int32_t f0, int32_t f1, double* out13) {
+    TRY(check_prim(s, id, "smx_get_primitive_state_grad")); TRY(check_batch(s, batch, "smx_get_primitive_state_grad"));
     if (!out13) return fail(SMX_ERR_ARG, "smx_get_primitive_state_grad: null output");
     if (f0 < 0 || f1 > s->cfg.max_steps || f0 >= f1) return fail(SMX_ERR_RANGE, "smx_get_primitive_state_grad: frame range [%d, %d) outside [0, %d)", f0, f1, s->cfg.max_steps);
     CK(cudaSetDevice(s->cfg.device));
     std::vector<double> h((size_t)(f1 - f0) * 13);
-    CK(cudaMemcpyAsync(h.data(), s->pgrad + ((size_t)id * s->cfg.max_steps + f0) * 13, h.size() * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaMemcpyAsync(h.data(), s->pgrad + (prim_slot(s, batch, id) * s->cfg.max_steps + f0) * 13, h.size() * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
     for (int c = 0; c < 13; c++) out13[c] = 0;
     for (int f = 0; f < f1 - f0; f++) for (int c = 0; c < 13; c++) out13[c] += h[(size_t)f * 13 + c];
     return SMX_OK;
 }
-int smx_add_primitive_state_grad(smx_sim* s, int32_t id, int32_t f, const double* g13) {
-    TRY(check_prim(s, id, "smx_add_primitive_state_grad")); TRY(check_frame(s, f, "smx_add_primitive_state_grad"));
+int smx_get_primitive_state_grad(smx_sim* s, int32_t id, int32_t f0, int32_t f1, double* out13) { return smx_get_primitive_state_grad_b(s, 0, id, f0, f1, out13); }
+int smx_add_primitive_state_grad_b(smx_sim* s, int32_t batch, int32_t id, int32_t f, const double* g13) {
+    TRY(check_prim(s, id, "smx_add_primitive_state_grad")); TRY(check_frame(s, f, "smx_add_primitive_state_grad")); TRY(check_batch(s, batch, "smx_add_primitive_state_grad"));
     if (!g13) return fail(SMX_ERR_ARG, "smx_add_primitive_state_grad: null input");
     CK(cudaSetDevice(s->cfg.device));
     double h[13];
-    double* d = s->pgrad + ((size_t)id * s->cfg.max_steps + f) * 13;
+    double* d = s->pgrad + (prim_slot(s, batch, id) * s->cfg.max_steps + f) * 13;
     CK(cudaMemcpyAsync(h, d, sizeof h, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
     for (int c = 0; c < 13; c++) h[c] += g13[c];
@@ -639,29 +670,41 @@ int smx_add_primitive_state_grad(smx_sim* s, int32_t id, int32_t f, const double
     CK(cudaStreamSynchronize(s->stream));
     return SMX_OK;
 }
-int smx_get_ext_f(smx_sim* s, int32_t id, double* out6) {
-    TRY(check_prim(s, id, "smx_get_ext_f"));
+int smx_add_primitive_state_grad(smx_sim* s, int32_t id, int32_t f, const double* g13) { return smx_add_primitive_state_grad_b(s, 0, id, f, g13); }
+int smx_get_ext_f_b(smx_sim* s, int32_t batch, int32_t id, double* out6) {
+    TRY(check_prim(s, id, "smx_get_ext_f")); TRY(check_batch(s, batch, "smx_get_ext_f"));
     if (!out6) return fail(SMX_ERR_ARG, "smx_get_ext_f: null output");
     CK(cudaSetDevice(s->cfg.device));
-    CK(cudaMemcpyAsync(out6, s->ext_f + 6 * id, 6 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaMemcpyAsync(out6, s->ext_f + 6 * prim_slot(s, batch, id), 6 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
     return SMX_OK;
 }
-int smx_clear_ext_f(smx_sim* s, int32_t id) {
-    TRY(check_prim(s, id, "smx_clear_ext_f"));
+int smx_get_ext_f(smx_sim* s, int32_t id, double* out6) { return smx_get_ext_f_b(s, 0, id, out6); }
+static int clear_ext_f(smx_sim* s, int b0, int b1, int id) {
     CK(cudaSetDevice(s->cfg.device));
-    CK(cudaMemsetAsync(s->ext_f + 6 * id, 0, 6 * sizeof(double), s->stream));
-    CK(cudaMemsetAsync(s->ext_f_grad + 6 * id, 0, 6 * sizeof(float), s->stream));
+    for (int b = b0; b < b1; b++) {
+        CK(cudaMemsetAsync(s->ext_f + 6 * prim_slot(s, b, id), 0, 6 * sizeof(double), s->stream));
+        CK(cudaMemsetAsync(s->ext_f_grad + 6 * prim_slot(s, b, id), 0, 6 * sizeof(float), s->stream));
+    }
     return SMX_OK;
 }
-int smx_set_ext_f_grad(smx_sim* s, int32_t id, const double* g6) {
-    TRY(check_prim(s, id, "smx_set_ext_f_grad"));
+int smx_clear_ext_f(smx_sim* s, int32_t id) { TRY(check_prim(s, id, "smx_clear_ext_f")); return clear_ext_f(s, 0, s->B, id); }
+int smx_clear_ext_f_b(smx_sim* s, int32_t batch, int32_t id) {
+    TRY(check_prim(s, id, "smx_clear_ext_f_b")); TRY(check_batch(s, batch, "smx_clear_ext_f_b"));
+    return clear_ext_f(s, batch, batch + 1, id);
+}
+static int set_ext_f_grad(smx_sim* s, int b0, int b1, int id, const double* g6) {
     if (!g6) return fail(SMX_ERR_ARG, "smx_set_ext_f_grad: null input");
     CK(cudaSetDevice(s->cfg.device));
     float h[6]; for (int i = 0; i < 6; i++) h[i] = (float)g6[i];
-    CK(cudaMemcpyAsync(s->ext_f_grad + 6 * id, h, sizeof h, cudaMemcpyHostToDevice, s->stream));
+    for (int b = b0; b < b1; b++) CK(cudaMemcpyAsync(s->ext_f_grad + 6 * prim_slot(s, b, id), h, sizeof h, cudaMemcpyHostToDevice, s->stream));
     CK(cudaStreamSynchronize(s->stream));
     return SMX_OK;
+}
+int smx_set_ext_f_grad(smx_sim* s, int32_t id, const double* g6) { TRY(check_prim(s, id, "smx_set_ext_f_grad")); return set_ext_f_grad(s, 0, s->B, id, g6); }
+int smx_set_ext_f_grad_b(smx_sim* s, int32_t batch, int32_t id, const double* g6) {
+    TRY(check_prim(s, id, "smx_set_ext_f_grad_b")); TRY(check_batch(s, batch, "smx_set_ext_f_grad_b"));
+    return set_ext_f_grad(s, batch, batch + 1, id, g6);
 }
 int smx_set_primitive_action(smx_sim* s, int32_t id, int32_t st, int32_t n, const double* a6) {
     TRY(check_prim(s, id, "smx_set_primitive_action"));
@@ -671,13 +714,16 @@ int smx_set_primitive_action(smx_sim* s, int32_t id, int32_t st, int32_t n, cons
     CK(cudaSetDevice(s->cfg.device));
     // action_buffer[s] = a ; v[j] = a[3:6], w[j] = a[0:3] for j in [s*n, (s+1)*n)   (primitive_base.py:285-304)
     float a[6]; for (int i = 0; i < 6; i++) a[i] = (float)a6[i];
-    CK(cudaMemcpyAsync(s->abuf + ((size_t)id * T + st) * 6, a, sizeof a, cudaMemcpyHostToDevice, s->stream));
-    std::vector<float> h((size_t)n * 13);
-    CK(cudaMemcpyAsync(h.data(), s->pstate + ((size_t)id * T + (size_t)st * n) * 13, h.size() * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
-    CK(cudaStreamSynchronize(s->stream));
-    for (int j = 0; j < n; j++) for (int k = 0; k < 3; k++) { h[(size_t)j * 13 + 7 + k] = a[3 + k]; h[(size_t)j * 13 + 10 + k] = a[k]; }
-    CK(cudaMemcpyAsync(s->pstate + ((size_t)id * T + (size_t)st * n) * 13, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, s->stream));
-    CK(cudaStreamSynchronize(s->stream));
+    for (int b = 0; b < s->B; b++) {        // velocity-control actions are shared by all batches
+        size_t ps = prim_slot(s, b, id);
+        CK(cudaMemcpyAsync(s->abuf + (ps * T + st) * 6, a, sizeof a, cudaMemcpyHostToDevice, s->stream));
+        std::vector<float> h((size_t)n * 13);
+        CK(cudaMemcpyAsync(h.data(), s->pstate + (ps * T + (size_t)st * n) * 13, h.size() * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+        CK(cudaStreamSynchronize(s->stream));
+        for (int j = 0; j < n; j++) for (int k = 0; k < 3; k++) { h[(size_t)j * 13 + 7 + k] = a[3 + k]; h[(size_t)j * 13 + 10 + k] = a[k]; }
+        CK(cudaMemcpyAsync(s->pstate + (ps * T + (size_t)st * n) * 13, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+        CK(cudaStreamSynchronize(s->stream));
+    }
     return SMX_OK;
 }
 int smx_get_primitive_action_grad(smx_sim* s, int32_t id, int32_t st, int32_t n, double* out6) {
@@ -703,7 +749,7 @@ int smx_set_action(smx_sim* s, const double* action) {
     if (!s || !action) return fail(SMX_ERR_ARG, "smx_set_action: null argument");
     if (s->cfg.n_control <= 0) return fail(SMX_ERR_STATE, "smx_set_action: simulator was created with n_control == 0");
     CK(cudaSetDevice(s->cfg.device));
-    std::vector<float> h((size_t)s->cfg.n_control * 3);
+    std::vector<float> h((size_t)s->B * s->cfg.n_control * 3);       // (n_batch * n_control, 3)
     for (size_t i = 0; i < h.size(); i++) h[i] = (float)action[i];
     CK(cudaMemcpyAsync(s->action, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, s->stream));
     CK(cudaMemsetAsync(s->action_grad, 0, h.size() * sizeof(double), s->stream));    // set_action_kernel zeroes action.grad (:584-586)
@@ -722,7 +768,7 @@ int smx_get_action_grad(smx_sim* s, double* out) {
     if (!s || !out) return fail(SMX_ERR_ARG, "smx_get_action_grad: null argument");
     if (s->cfg.n_control <= 0) return fail(SMX_ERR_STATE, "smx_get_action_grad: simulator was created with n_control == 0");
     CK(cudaSetDevice(s->cfg.device));
-    CK(cudaMemcpyAsync(out, s->action_grad, (size_t)s->cfg.n_control * 3 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaMemcpyAsync(out, s->action_grad, (size_t)s->B * s->cfg.n_control * 3 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
     return SMX_OK;
 }
@@ -791,7 +837,7 @@ int smx_substep_grad(smx_sim* s, int32_t f) {
     }
     k_grid_grad<<<grid_blocks_launch(s), 256, 0, s->stream>>>(P, ps, f, s->dense ? nullptr : ord.blocks, ord.nblocks, s->g_in, s->gg_out, contact ? s->gg_mix : nullptr); CKLN(s, "k_grid_grad");
     if (s->cfg.rigid_velocity_control && !s->prims.empty()) {
-        k_forward_kinematics_grad<<<1, 32, 0, s->stream>>>(s->pstate, s->pgrad, s->cfg.max_steps, (int)s->prims.size(), f, P.dt); CKL(s);
+        k_forward_kinematics_grad<<<nblk((long long)s->prims.size() * s->B, 64), 64, 0, s->stream>>>(s->pstate, s->pgrad, s->cfg.max_steps, (int)s->prims.size(), s->B, f, P.dt); CKL(s);
     }
     const int* cslot = nullptr;
     TRY(ctrl_slots(s, o, &cslot));
@@ -892,10 +938,11 @@ int smx_clear_grads(smx_sim* s) {
     s->seeds.clear();
     s->adj_frame = -1; s->adj_order = -1;
     int T = s->cfg.max_steps;
-    CK(cudaMemsetAsync(s->pgrad, 0, (size_t)SMX_MAXP * T * 13 * sizeof(double), s->stream));
-    CK(cudaMemsetAsync(s->gabuf, 0, (size_t)SMX_MAXP * T * 6 * sizeof(double), s->stream));
-    CK(cudaMemsetAsync(s->ext_f_grad, 0, SMX_MAXP * 6 * sizeof(float), s->stream));
-    CK(cudaMemsetAsync(s->action_grad, 0, (size_t)std::max(s->cfg.n_control, 1) * 3 * sizeof(double), s->stream));
+    const int B = s->B;
+    CK(cudaMemsetAsync(s->pgrad, 0, (size_t)B * SMX_MAXP * T * 13 * sizeof(double), s->stream));
+    CK(cudaMemsetAsync(s->gabuf, 0, (size_t)B * SMX_MAXP * T * 6 * sizeof(double), s->stream));
+    CK(cudaMemsetAsync(s->ext_f_grad, 0, (size_t)B * SMX_MAXP * 6 * sizeof(float), s->stream));
+    CK(cudaMemsetAsync(s->action_grad, 0, (size_t)B * std::max(s->cfg.n_control, 1) * 3 * sizeof(double), s->stream));
     return SMX_OK;
 }
 
@@ -927,12 +974,13 @@ int smx_get_permutation(smx_sim* s, int32_t f, uint32_t* perm) {
 int smx_get_grid(smx_sim* s, float* g_in, float* g_out) {
     if (!s) return fail(SMX_ERR_ARG, "smx_get_grid: null simulator");
     CK(cudaSetDevice(s->cfg.device));
-    if (!s->g_lin) CK(cudaMalloc(&s->g_lin, s->G * sizeof(float4)));
+    size_t Gb = (size_t)s->P.Gb;      // batch 0 only
+    if (!s->g_lin) CK(cudaMalloc(&s->g_lin, Gb * sizeof(float4)));
     const float4* src[2] = {s->g_in, s->g_out}; float* dst[2] = {g_in, g_out};
     for (int a = 0; a < 2; a++) {
         if (!dst[a]) continue;
-        k_grid_linear<<<nblk((long long)s->G, 256), 256, 0, s->stream>>>(s->P.ng, s->P.nb, src[a], s->g_lin); CKL(s);
-        CK(cudaMemcpyAsync(dst[a], s->g_lin, s->G * sizeof(float4), cudaMemcpyDeviceToHost, s->stream));
+        k_grid_linear<<<nblk((long long)Gb, 256), 256, 0, s->stream>>>(s->P.ng, s->P.nb, src[a], s->g_lin); CKL(s);
+        CK(cudaMemcpyAsync(dst[a], s->g_lin, Gb * sizeof(float4), cudaMemcpyDeviceToHost, s->stream));
         CK(cudaStreamSynchronize(s->stream));
     }
     return SMX_OK;

@@ -8,7 +8,9 @@
 //                     g_out = (velocity xyz, active flag)   source of G2P        (:296-297, :403-404, :443)
 //                     g_mix = (velocity xyz, active flag)   grid_v_mixed         (:403)
 //                     gg_out / gg_mix: adjoints; grid_grad overwrites gg_out with (d g_in xyz, d mass)
-//   primitives      : pstate [P][T][13] fp32, pgrad [P][T][13] f64, ext_f [P][6] f64, ext_f_grad [P][6] fp32
+//   primitives      : pstate [B][P][T][13] fp32, pgrad [B][P][T][13] f64, ext_f [B][P][6] f64, ext_f_grad [B][P][6] fp32
+//   batching        : B independent rollouts share one handle: particle slot j belongs to batch j / npb (the sort key
+//                     carries the batch in its high bits), node indices are offset by batch * ng^3
 //
 // Stage map (reference kernel -> kernel here):
 //   compute_F_tmp + svd + p2g (:125-133, :198-262)           -> k_p2g          (SVD and stress stay in registers)
@@ -32,6 +34,7 @@ struct Params {
     float gx, gy, gz;       // gravity
     int sticky;             // ground_friction >= 10
     int material, ptype, ctype, substeps, n_control, np;
+    int nbatch, npb, Gb, nb3;   // independent rollouts batched in one handle: count, particles per batch, nodes and blocks per batch
 };
 
 struct PrimSet {            // device pointers shared by all kernels that touch primitives
@@ -42,6 +45,12 @@ struct PrimSet {            // device pointers shared by all kernels that touch 
     const float* ext_f_grad;// [np][6]
     int T;
 };
+// batch-major primitive arrays: [batch][SMX_MAXP][...]
+__device__ __forceinline__ const float* pstate_at(const PrimSet& ps, int b, int i, int f) { return ps.pstate + (((size_t)b * SMX_MAXP + i) * ps.T + f) * 13; }
+__device__ __forceinline__ double* pgrad_at(const PrimSet& ps, int b, int i, int f) { return ps.pgrad + (((size_t)b * SMX_MAXP + i) * ps.T + f) * 13; }
+__device__ __forceinline__ double* ext_f_at(const PrimSet& ps, int b, int i) { return ps.ext_f + ((size_t)b * SMX_MAXP + i) * 6; }
+__device__ __forceinline__ const float* ext_f_grad_at(const PrimSet& ps, int b, int i) { return ps.ext_f_grad + ((size_t)b * SMX_MAXP + i) * 6; }
+__device__ __forceinline__ int batch_of(const Params& P, int j) { return P.nbatch > 1 ? j / P.npb : 0; }
 
 #define SMX_TPB 128         // gather-type particle kernels
 #define SMX_TPB_SC 64       // scatter-type particle kernels (two warps: 2 x 13.8 KB of staging)
@@ -65,7 +74,7 @@ struct WarpStage {
     uint32_t key[32];       // packed base cell of each run
     uint32_t start[33];     // first lane of each run (+ sentinel)
 };
-__device__ __forceinline__ uint32_t pack_base(int bx, int by, int bz) { return (uint32_t)bx | ((uint32_t)by << 8) | ((uint32_t)bz << 16); }
+__device__ __forceinline__ uint32_t pack_base(int bx, int by, int bz, int bt = 0) { return (uint32_t)bx | ((uint32_t)by << 8) | ((uint32_t)bz << 16) | ((uint32_t)bt << 24); }
 
 // packed fp32x2 add (sm_100a: one FADD2 instead of two FADD)
 __device__ __forceinline__ void add_f4(float4& a, const float4& b) {
@@ -74,7 +83,7 @@ __device__ __forceinline__ void add_f4(float4& a, const float4& b) {
     a = make_float4(lo.x, lo.y, hi.x, hi.y);
 }
 
-__device__ __forceinline__ void warp_stage_flush(WarpStage& st, uint32_t key, bool live, float4* __restrict__ grid, int nb) {
+__device__ __forceinline__ void warp_stage_flush(WarpStage& st, uint32_t key, bool live, float4* __restrict__ grid, int nb, int Gb) {
     const unsigned lane = threadIdx.x & 31;
     uint32_t k = live ? key : 0xffffffffu;
     uint32_t prev = __shfl_up_sync(0xffffffffu, k, 1);
@@ -105,7 +114,7 @@ __device__ __forceinline__ void warp_stage_flush(WarpStage& st, uint32_t key, bo
         if (cnt >= 1) { float4 v0 = src[0]; add_f4(acc, v0); }
         add_f4(acc, acc2);
         int a = o / 9, b = (o - 9 * a) / 3, c = o - 9 * a - 3 * b;
-        atomicAdd(grid + node_index((int)(kk & 0xffu) + a, (int)((kk >> 8) & 0xffu) + b, (int)(kk >> 16) + c, nb), acc);
+        atomicAdd(grid + ((kk >> 24) * (uint32_t)Gb + node_index((int)(kk & 0xffu) + a, (int)((kk >> 8) & 0xffu) + b, (int)((kk >> 16) & 0xffu) + c, nb)), acc);
     }
 }
 
@@ -132,7 +141,7 @@ __device__ __forceinline__ void axis_weights(float f, float* w) {
 }
 __device__ __forceinline__ void axis_dweights(float f, float* d) { d[0] = f - 1.5f; d[1] = -2.f * (f - 1.f); d[2] = f - 0.5f; }
 
-__device__ __forceinline__ Stencil make_stencil(float x, float y, float z, const Params& P) {
+__device__ __forceinline__ Stencil make_stencil(float x, float y, float z, const Params& P, int bt = 0) {
     Stencil s;
     // x*inv_dx (power-of-two scale), -0.5 and the subtraction of the integer base are exact in fp32, so base and
     // fx equal the reference's f64 values for the same fp32 x
@@ -143,7 +152,7 @@ __device__ __forceinline__ Stencil make_stencil(float x, float y, float z, const
 #pragma unroll
     for (int a = 0; a < 3; a++) {
         int i = s.bx + a, j = s.by + a, k = s.bz + a;
-        s.ox[a] = ((i >> 2) * P.nb * P.nb) * 64 + ((i & 3) << 4);
+        s.ox[a] = bt * P.Gb + ((i >> 2) * P.nb * P.nb) * 64 + ((i & 3) << 4);
         s.oy[a] = ((j >> 2) * P.nb) * 64 + ((j & 3) << 2);
         s.oz[a] = (k >> 2) * 64 + (k & 3);
     }
@@ -156,18 +165,30 @@ __device__ __forceinline__ void warp_sum_to(double* dst, float v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if ((threadIdx.x & 31) == 0 && v != 0.f) atomicAdd(dst, (double)v);
 }
-__device__ __forceinline__ void commit_wrench(double* ext_f, V3 bf, V3 r, bool active) {
+// lanes of a warp normally belong to one batch; a warp straddling two batches falls back to per-lane atomics
+__device__ __forceinline__ bool warp_one_batch(int bt) { return __all_sync(0xffffffffu, bt == __shfl_sync(0xffffffffu, bt, 0)); }
+__device__ __forceinline__ void commit_wrench(double* ext_f, V3 bf, V3 r, bool active, int bt) {
     if (!__any_sync(0xffffffffu, active)) return;
-    V3 bt = cross(r, bf);
-    if (!active) { bf = v3(0, 0, 0); bt = v3(0, 0, 0); }
-    warp_sum_to(ext_f + 0, bf.x); warp_sum_to(ext_f + 1, bf.y); warp_sum_to(ext_f + 2, bf.z);
-    warp_sum_to(ext_f + 3, bt.x); warp_sum_to(ext_f + 4, bt.y); warp_sum_to(ext_f + 5, bt.z);
+    V3 bt3 = cross(r, bf);
+    if (!active) { bf = v3(0, 0, 0); bt3 = v3(0, 0, 0); }
+    if (warp_one_batch(bt)) {
+        warp_sum_to(ext_f + 0, bf.x); warp_sum_to(ext_f + 1, bf.y); warp_sum_to(ext_f + 2, bf.z);
+        warp_sum_to(ext_f + 3, bt3.x); warp_sum_to(ext_f + 4, bt3.y); warp_sum_to(ext_f + 5, bt3.z);
+    } else if (active) {
+        atomicAdd(ext_f + 0, (double)bf.x); atomicAdd(ext_f + 1, (double)bf.y); atomicAdd(ext_f + 2, (double)bf.z);
+        atomicAdd(ext_f + 3, (double)bt3.x); atomicAdd(ext_f + 4, (double)bt3.y); atomicAdd(ext_f + 5, (double)bt3.z);
+    }
 }
-__device__ __forceinline__ void commit_prim_grad(double* g13, const PrimGrad& G, bool active) {
+__device__ __forceinline__ void commit_prim_grad(double* g13, const PrimGrad& G, bool active, int bt) {
     if (!__any_sync(0xffffffffu, active)) return;
     float v[13] = {G.pos.x, G.pos.y, G.pos.z, G.rot.w, G.rot.x, G.rot.y, G.rot.z, G.v.x, G.v.y, G.v.z, G.w.x, G.w.y, G.w.z};
+    if (warp_one_batch(bt)) {
 #pragma unroll
-    for (int i = 0; i < 13; i++) warp_sum_to(g13 + i, active ? v[i] : 0.f);
+        for (int i = 0; i < 13; i++) warp_sum_to(g13 + i, active ? v[i] : 0.f);
+    } else if (active) {
+#pragma unroll
+        for (int i = 0; i < 13; i++) if (v[i] != 0.f) atomicAdd(g13 + i, (double)v[i]);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -234,21 +255,21 @@ __device__ __forceinline__ void load_state(const float* __restrict__ fr, long lo
 }
 
 // particle-contact impulses (collision_type == 1, :203-206) and the control impulse (:209-213)
-__device__ __forceinline__ V3 particle_impulses(const Params& P, const PrimSet& ps, int f, int j, bool live, V3 x, V3 v,
+__device__ __forceinline__ V3 particle_impulses(const Params& P, const PrimSet& ps, int f, int j, int bt, bool live, V3 x, V3 v,
                                                 const int* __restrict__ ctrl_slot, const float* __restrict__ action, bool accumulate) {
     V3 imp = v3(0, 0, 0);
     if (P.ctype == 1) {
         for (int i = 0; i < P.np; i++) {
             if (!ps.prims[i].enabled) continue;
-            PrimState S = load_prim_state(ps.pstate + ((size_t)i * ps.T + f) * 13);
+            PrimState S = load_prim_state(pstate_at(ps, bt, i, f));
             bool act = false; V3 bf = v3(0, 0, 0), r = v3(0, 0, 0);
             if (live) imp += collide_particle_fwd(ps.prims[i], S, x, v, P.dt, act, bf, r);
-            if (accumulate) commit_wrench(ps.ext_f + 6 * i, bf, r, act);
+            if (accumulate) commit_wrench(ext_f_at(ps, bt, i), bf, r, act, bt);
         }
     }
     if (P.n_control > 0 && live) {
         int ci = ctrl_slot[j];
-        if (ci >= 0) imp += (6e-4f * P.dt) * v3(action[3 * ci], action[3 * ci + 1], action[3 * ci + 2]);
+        if (ci >= 0) { ci += bt * P.n_control; imp += (6e-4f * P.dt) * v3(action[3 * ci], action[3 * ci + 1], action[3 * ci + 2]); }
     }
     return imp;
 }
@@ -267,8 +288,9 @@ __global__ void __launch_bounds__(SMX_TPB_SC, 8) k_p2g(Params P, PrimSet ps, int
     int jj = live ? j : P.n - 1;
     V3 x, v; M3 F, C;
     load_state(fin, P.stride, jj, x, v, F, C);
-    V3 imp = particle_impulses(P, ps, f, jj, live, x, v, ctrl_slot, action, accumulate != 0);
-    Stencil s = make_stencil(x.x, x.y, x.z, P);
+    int bt = batch_of(P, jj);
+    V3 imp = particle_impulses(P, ps, f, jj, bt, live, x, v, ctrl_slot, action, accumulate != 0);
+    Stencil s = make_stencil(x.x, x.y, x.z, P, bt);
     if (live) {
         Material m;
         material_update<MAT>(compute_Et(C, F, P.dt), P, m);
@@ -300,7 +322,7 @@ __global__ void __launch_bounds__(SMX_TPB_SC, 8) k_p2g(Params P, PrimSet ps, int
             }
         }
     }
-    if (STAGED) warp_stage_flush(stage[threadIdx.x >> 5], pack_base(s.bx, s.by, s.bz), live, g_in, P.nb);
+    if (STAGED) warp_stage_flush(stage[threadIdx.x >> 5], pack_base(s.bx, s.by, s.bz, bt), live, g_in, P.nb, P.Gb);
 }
 
 // boundary_condition (mpm_simulator.py:268-281); mask bit d cleared where component d was zeroed
@@ -330,14 +352,15 @@ __device__ __forceinline__ void node_coords(uint32_t node, int nb, int& i, int& 
 __global__ void __launch_bounds__(256) k_grid_op(Params P, PrimSet ps, int f, const uint32_t* __restrict__ blocks, const int* __restrict__ nblocks,
                                                  const float4* __restrict__ g_in, float4* __restrict__ g_out, float4* __restrict__ g_mix,
                                                  int accumulate) {
-    int total = blocks ? *nblocks : P.nb * P.nb * P.nb;
+    int total = blocks ? *nblocks : P.nbatch * P.nb3;
     for (int bi = blockIdx.x * 4 + (threadIdx.x >> 6); bi < total; bi += gridDim.x * 4) {
         uint32_t node = (blocks ? blocks[bi] : (uint32_t)bi) * 64u + (threadIdx.x & 63);
         float4 g = g_in[node];
         float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
         bool on = g.w > 1e-10f;
         int i, j, k;
-        node_coords(node, P.nb, i, j, k);
+        int bt = P.nbatch > 1 ? (int)(node / (uint32_t)P.Gb) : 0;
+        node_coords(node - (uint32_t)(bt * P.Gb), P.nb, i, j, k);
         V3 v = v3(0, 0, 0);
         if (on) {
             float inv = 1.f / g.w;
@@ -347,10 +370,10 @@ __global__ void __launch_bounds__(256) k_grid_op(Params P, PrimSet ps, int f, co
             V3 gp = v3(i * P.dx, j * P.dx, k * P.dx);
             for (int q = 0; q < P.np; q++) {
                 if (!ps.prims[q].enabled) continue;
-                PrimState S = load_prim_state(ps.pstate + ((size_t)q * ps.T + f) * 13);
+                PrimState S = load_prim_state(pstate_at(ps, bt, q, f));
                 bool act = false; V3 r = v3(0, 0, 0), vin = v;
                 if (on) v = collide_grid_fwd(ps.prims[q], S, gp, v, act, r);
-                if (accumulate) commit_wrench(ps.ext_f + 6 * q, (g.w / P.dt) * (vin - v), r, act);
+                if (accumulate) commit_wrench(ext_f_at(ps, bt, q), (g.w / P.dt) * (vin - v), r, act, bt);
             }
         }
         if (on) {
@@ -373,15 +396,16 @@ __global__ void __launch_bounds__(SMX_TPB) k_contact(Params P, PrimSet ps, int f
     bool live = j < P.n;
     int jj = live ? j : P.n - 1;
     V3 x = v3(fin[jj], fin[P.stride + jj], fin[2 * P.stride + jj]);
+    int bt = batch_of(P, jj);
     // cheap reject: is the particle within reach of any enabled primitive?
     bool near = false;
     for (int i = 0; i < P.np; i++) {
         if (!ps.prims[i].enabled) continue;
-        PrimState S = load_prim_state(ps.pstate + ((size_t)i * ps.T + f) * 13);
+        PrimState S = load_prim_state(pstate_at(ps, bt, i, f));
         near |= live && (prim_sdf(ps.prims[i], S, x) <= 5e-3f);
     }
     if (!__any_sync(0xffffffffu, near)) return;
-    Stencil s = make_stencil(x.x, x.y, x.z, P);
+    Stencil s = make_stencil(x.x, x.y, x.z, P, bt);
     V3 vtmp = v3(0, 0, 0);
     uint32_t onmask = 0;
     if (near) {
@@ -400,11 +424,11 @@ __global__ void __launch_bounds__(SMX_TPB) k_contact(Params P, PrimSet ps, int f
     V3 vt = vtmp;
     for (int i = 0; i < P.np; i++) {
         if (!ps.prims[i].enabled) continue;
-        PrimState S = load_prim_state(ps.pstate + ((size_t)i * ps.T + f) * 13);
+        PrimState S = load_prim_state(pstate_at(ps, bt, i, f));
         CmTape T; T.active = false; T.r = v3(0, 0, 0);
         V3 vin = vt;
         if (near) vt = collide_mixed_fwd(ps.prims[i], S, x, vin, P.dt, life, T);
-        if (accumulate) commit_wrench(ps.ext_f + 6 * i, (P.p_mass / P.dt) * (vin - vt), T.r, near && T.active);
+        if (accumulate) commit_wrench(ext_f_at(ps, bt, i), (P.p_mass / P.dt) * (vin - vt), T.r, near && T.active, bt);
     }
     if (!near) return;
     V3 d = vtmp - vt;
@@ -429,7 +453,7 @@ __global__ void __launch_bounds__(SMX_TPB) k_g2p(Params P, const float* __restri
     int j = blockIdx.x * SMX_TPB + threadIdx.x;
     if (j >= P.n) return;
     V3 x = v3(fin[j], fin[P.stride + j], fin[2 * P.stride + j]);
-    Stencil s = make_stencil(x.x, x.y, x.z, P);
+    Stencil s = make_stencil(x.x, x.y, x.z, P, batch_of(P, j));
     V3 nv = v3(0, 0, 0);
     M3 B = m3_zero();       // sum w g (x) offset
 #pragma unroll
@@ -471,7 +495,8 @@ __global__ void __launch_bounds__(SMX_TPB_SC, 8) k_g2p_grad(Params P, const floa
     bool live = j < P.n;
     int jj = live ? j : P.n - 1;
     V3 x = v3(fin[jj], fin[P.stride + jj], fin[2 * P.stride + jj]);
-    Stencil s = make_stencil(x.x, x.y, x.z, P);
+    int bt = batch_of(P, jj);
+    Stencil s = make_stencil(x.x, x.y, x.z, P, bt);
     if (live) {
         V3 gx1 = v3(ain[j], ain[P.stride + j], ain[2 * P.stride + j]);
         V3 gnv = v3(ain[3 * P.stride + j], ain[4 * P.stride + j], ain[5 * P.stride + j]) + P.dt * gx1;
@@ -518,7 +543,7 @@ __global__ void __launch_bounds__(SMX_TPB_SC, 8) k_g2p_grad(Params P, const floa
         gfx -= Tmulv(K, S0);
         aout[j] = gx1.x + P.inv_dx * gfx.x; aout[P.stride + j] = gx1.y + P.inv_dx * gfx.y; aout[2 * P.stride + j] = gx1.z + P.inv_dx * gfx.z;
     }
-    if (STAGED) warp_stage_flush(stage[threadIdx.x >> 5], pack_base(s.bx, s.by, s.bz), live, gg_out, P.nb);
+    if (STAGED) warp_stage_flush(stage[threadIdx.x >> 5], pack_base(s.bx, s.by, s.bz, bt), live, gg_out, P.nb, P.Gb);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -532,14 +557,15 @@ __global__ void __launch_bounds__(SMX_TPB) k_contact_grad(Params P, PrimSet ps, 
     bool live = j < P.n;
     int jj = live ? j : P.n - 1;
     V3 x = v3(fin[jj], fin[P.stride + jj], fin[2 * P.stride + jj]);
+    int bt = batch_of(P, jj);
     bool near = false;
     for (int i = 0; i < P.np; i++) {
         if (!ps.prims[i].enabled) continue;
-        PrimState S = load_prim_state(ps.pstate + ((size_t)i * ps.T + f) * 13);
+        PrimState S = load_prim_state(pstate_at(ps, bt, i, f));
         near |= live && (prim_sdf(ps.prims[i], S, x) <= 5e-3f);
     }
     if (!__any_sync(0xffffffffu, near)) return;
-    Stencil s = make_stencil(x.x, x.y, x.z, P);
+    Stencil s = make_stencil(x.x, x.y, x.z, P, bt);
     float dwx[3], dwy[3], dwz[3];
     axis_dweights(s.fx, dwx); axis_dweights(s.fy, dwy); axis_dweights(s.fz, dwz);
     V3 vtmp = v3(0, 0, 0);
@@ -564,7 +590,7 @@ __global__ void __launch_bounds__(SMX_TPB) k_contact_grad(Params P, PrimSet ps, 
     V3 vt = vtmp;
     for (int i = 0; i < P.np; i++) {
         if (!ps.prims[i].enabled) continue;
-        PrimState S = load_prim_state(ps.pstate + ((size_t)i * ps.T + f) * 13);
+        PrimState S = load_prim_state(pstate_at(ps, bt, i, f));
         vin[nq] = vt; tape[nq].active = false;
         if (near) vt = collide_mixed_fwd(ps.prims[i], S, x, vt, P.dt, life, tape[nq]);
         vout[nq] = vt; which[nq] = i; nq++;
@@ -593,12 +619,12 @@ __global__ void __launch_bounds__(SMX_TPB) k_contact_grad(Params P, PrimSet ps, 
     V3 gxc = v3(0, 0, 0);   // d x from the contact model
     for (int a = nq - 1; a >= 0; a--) {
         int i = which[a];
-        PrimState S = load_prim_state(ps.pstate + ((size_t)i * ps.T + f) * 13);
+        PrimState S = load_prim_state(pstate_at(ps, bt, i, f));
         PrimGrad G = prim_grad_zero();
         V3 gin = v3(0, 0, 0);
         bool act = near && tape[a].active;
-        if (near) collide_mixed_adj(ps.prims[i], S, x, vin[a], vout[a], P.p_mass, P.dt, life, tape[a], g, ps.ext_f_grad + 6 * i, gxc, gin, G);
-        commit_prim_grad(ps.pgrad + ((size_t)i * ps.T + f) * 13, G, act);
+        if (near) collide_mixed_adj(ps.prims[i], S, x, vin[a], vout[a], P.p_mass, P.dt, life, tape[a], g, ext_f_grad_at(ps, bt, i), gxc, gin, G);
+        commit_prim_grad(pgrad_at(ps, bt, i, f), G, act, bt);
         g = gin;
     }
     if (!near) return;
@@ -627,13 +653,14 @@ __global__ void __launch_bounds__(SMX_TPB) k_contact_grad(Params P, PrimSet ps, 
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_grid_grad(Params P, PrimSet ps, int f, const uint32_t* __restrict__ blocks, const int* __restrict__ nblocks,
                                                    const float4* __restrict__ g_in, float4* __restrict__ gg_out, const float4* __restrict__ gg_mix) {
-    int total = blocks ? *nblocks : P.nb * P.nb * P.nb;
+    int total = blocks ? *nblocks : P.nbatch * P.nb3;
     for (int bi = blockIdx.x * 4 + (threadIdx.x >> 6); bi < total; bi += gridDim.x * 4) {
         uint32_t node = (blocks ? blocks[bi] : (uint32_t)bi) * 64u + (threadIdx.x & 63);
         float4 g = g_in[node];
         bool on = g.w > 1e-10f;
         int i, j, k;
-        node_coords(node, P.nb, i, j, k);
+        int bt = P.nbatch > 1 ? (int)(node / (uint32_t)P.Gb) : 0;
+        node_coords(node - (uint32_t)(bt * P.Gb), P.nb, i, j, k);
         float4 go = gg_out[node];
         V3 gv = v3(go.x, go.y, go.z);
         if (gg_mix) { float4 gm = gg_mix[node]; gv += v3(gm.x, gm.y, gm.z); }
@@ -645,7 +672,7 @@ __global__ void __launch_bounds__(256) k_grid_grad(Params P, PrimSet ps, int f, 
             V3 vins[SMX_MAXP]; int which[SMX_MAXP], nq = 0;
             for (int q = 0; q < P.np; q++) {
                 if (!ps.prims[q].enabled) continue;
-                PrimState S = load_prim_state(ps.pstate + ((size_t)q * ps.T + f) * 13);
+                PrimState S = load_prim_state(pstate_at(ps, bt, q, f));
                 vins[nq] = v; which[nq++] = q;
                 bool act; V3 r;
                 if (on) v = collide_grid_fwd(ps.prims[q], S, gp, v, act, r);
@@ -655,11 +682,11 @@ __global__ void __launch_bounds__(256) k_grid_grad(Params P, PrimSet ps, int f, 
             gv = v3((mask & 1) ? gv.x : 0.f, (mask & 2) ? gv.y : 0.f, (mask & 4) ? gv.z : 0.f);
             for (int a = nq - 1; a >= 0; a--) {
                 int q = which[a];
-                PrimState S = load_prim_state(ps.pstate + ((size_t)q * ps.T + f) * 13);
+                PrimState S = load_prim_state(pstate_at(ps, bt, q, f));
                 PrimGrad G = prim_grad_zero();
                 V3 gin = v3(0, 0, 0);
-                if (on) collide_grid_adj(ps.prims[q], S, gp, vins[a], P.dt, g.w, gv, ps.ext_f_grad + 6 * q, gin, gmass, G);
-                commit_prim_grad(ps.pgrad + ((size_t)q * ps.T + f) * 13, G, on);
+                if (on) collide_grid_adj(ps.prims[q], S, gp, vins[a], P.dt, g.w, gv, ext_f_grad_at(ps, bt, q), gin, gmass, G);
+                commit_prim_grad(pgrad_at(ps, bt, q, f), G, on, bt);
                 gv = gin;
             }
         } else {
@@ -694,7 +721,8 @@ __global__ void __launch_bounds__(SMX_TPB, SMX_P2GG_MINB) k_p2g_grad(Params P, P
     int jj = live ? j : P.n - 1;
     V3 x, v; M3 F, C;
     load_state(fin, P.stride, jj, x, v, F, C);
-    V3 imp = particle_impulses(P, ps, f, jj, live, x, v, ctrl_slot, action, false);
+    int bt = batch_of(P, jj);
+    V3 imp = particle_impulses(P, ps, f, jj, bt, live, x, v, ctrl_slot, action, false);
     Material m;
     M3 Et = compute_Et(C, F, P.dt);
     material_update<MAT>(Et, P, m);
@@ -702,7 +730,7 @@ __global__ void __launch_bounds__(SMX_TPB, SMX_P2GG_MINB) k_p2g_grad(Params P, P
 #pragma unroll
     for (int i = 0; i < 9; i++) A.m[i] = (P.cs * m.stress.m[i] + P.p_mass * C.m[i]) * P.dx;
     // (an L1 prefetch of the 27 gather nodes before the SVD was measured on B200: 148 -> 158 us, so it is not used)
-    Stencil s = make_stencil(x.x, x.y, x.z, P);
+    Stencil s = make_stencil(x.x, x.y, x.z, P, bt);
     float dwx[3], dwy[3], dwz[3];
     axis_dweights(s.fx, dwx); axis_dweights(s.fy, dwy); axis_dweights(s.fz, dwz);
     V3 q0 = P.p_mass * v + imp - mulv(A, v3(s.fx, s.fy, s.fz));
@@ -826,6 +854,7 @@ __global__ void __launch_bounds__(SMX_TPB, SMX_P2GG_MINB) k_p2g_grad(Params P, P
     if (P.n_control > 0 && live) {
         int ci = ctrl_slot[jj];
         if (ci >= 0) {
+            ci += bt * P.n_control;
             float k = 6e-4f * P.dt;
             atomicAdd(action_grad + 3 * ci, (double)(k * gimp.x)); atomicAdd(action_grad + 3 * ci + 1, (double)(k * gimp.y));
             atomicAdd(action_grad + 3 * ci + 2, (double)(k * gimp.z));
@@ -834,10 +863,10 @@ __global__ void __launch_bounds__(SMX_TPB, SMX_P2GG_MINB) k_p2g_grad(Params P, P
     if (P.ctype == 1) {
         for (int i = P.np - 1; i >= 0; i--) {
             if (!ps.prims[i].enabled) continue;
-            PrimState S = load_prim_state(ps.pstate + ((size_t)i * ps.T + f) * 13);
+            PrimState S = load_prim_state(pstate_at(ps, bt, i, f));
             PrimGrad G = prim_grad_zero();
-            if (live) collide_particle_adj(ps.prims[i], S, x, v, P.dt, gimp, ps.ext_f_grad + 6 * i, gx, gv, G);
-            commit_prim_grad(ps.pgrad + ((size_t)i * ps.T + f) * 13, G, live);
+            if (live) collide_particle_adj(ps.prims[i], S, x, v, P.dt, gimp, ext_f_grad_at(ps, bt, i), gx, gv, G);
+            commit_prim_grad(pgrad_at(ps, bt, i, f), G, live, bt);
         }
     }
     if (!live) return;
@@ -854,7 +883,7 @@ __global__ void k_keys(Params P, const float* __restrict__ fr, uint32_t* __restr
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= P.n) return;
     int clamped;
-    keys[j] = cell_key(fr[j], fr[P.stride + j], fr[2 * P.stride + j], P.inv_dx, P.ng, P.nb, &clamped);
+    keys[j] = (uint32_t)(batch_of(P, j) * P.Gb) + cell_key(fr[j], fr[P.stride + j], fr[2 * P.stride + j], P.inv_dx, P.ng, P.nb, &clamped);
     if (iota) iota[j] = j;
     if (clamped && counters) atomicAdd(counters, 1ull);
 }
@@ -928,7 +957,7 @@ __global__ void k_mark_blocks(Params P, const float* __restrict__ fr, int margin
     for (int i = lo[0]; i <= hi[0]; i++)
         for (int jj = lo[1]; jj <= hi[1]; jj++)
             for (int k = lo[2]; k <= hi[2]; k++) {
-                uint32_t id = (uint32_t)((i * P.nb + jj) * P.nb + k);
+                uint32_t id = (uint32_t)(batch_of(P, j) * P.nb3 + (i * P.nb + jj) * P.nb + k);
                 if (!flags[id]) flags[id] = 1u;
             }
 }
@@ -940,7 +969,7 @@ __global__ void k_mark_blocks_sorted(Params P, const uint32_t* __restrict__ keys
     if (j > 0 && keys_sorted[j - 1] == key) return;
     int b[3];
     {   // invert node_index: key = block * 64 + local
-        uint32_t blk = key >> 6, l = key & 63;
+        uint32_t blk = (key >> 6) % (uint32_t)P.nb3, l = key & 63;
         int bk = blk % P.nb, bj = (blk / P.nb) % P.nb, bi = blk / (P.nb * P.nb);
         b[0] = bi * 4 + (l >> 4); b[1] = bj * 4 + ((l >> 2) & 3); b[2] = bk * 4 + (l & 3);
     }
@@ -948,7 +977,7 @@ __global__ void k_mark_blocks_sorted(Params P, const uint32_t* __restrict__ keys
     for (int d = 0; d < 3; d++) { lo[d] = max(b[d] - margin, 0) >> 2; hi[d] = min(b[d] + 2 + margin, P.ng - 1) >> 2; }
     for (int i = lo[0]; i <= hi[0]; i++)
         for (int jj = lo[1]; jj <= hi[1]; jj++)
-            for (int k = lo[2]; k <= hi[2]; k++) flags[(i * P.nb + jj) * P.nb + k] = 1u;
+            for (int k = lo[2]; k <= hi[2]; k++) flags[(key >> 6) / (uint32_t)P.nb3 * P.nb3 + (i * P.nb + jj) * P.nb + k] = 1u;
 }
 // grid checkpoints: the active blocks of up to three float4 grids <-> a compact per-substep record
 // record layout: [array][active-block slot][64 nodes]; `cap` = blocks reserved per array
@@ -995,13 +1024,14 @@ __global__ void k_check_active(Params P, const float* __restrict__ fr, const uin
     bool ok = true;
     for (int i = b0 >> 2; i <= (b0 + 2) >> 2; i++)
         for (int jj = b1 >> 2; jj <= (b1 + 2) >> 2; jj++)
-            for (int k = b2 >> 2; k <= (b2 + 2) >> 2; k++) ok &= flags[(i * P.nb + jj) * P.nb + k] != 0;
+            for (int k = b2 >> 2; k <= (b2 + 2) >> 2; k++) ok &= flags[batch_of(P, j) * P.nb3 + (i * P.nb + jj) * P.nb + k] != 0;
     if (!ok) atomicAdd(counters + 1, 1ull);
 }
 // Primitive.forward_kinematics and its adjoint (primitive_base.py:280-283, primitive_utils.py:20-40); one thread
-__global__ void k_forward_kinematics(float* __restrict__ pstate, int T, int np, int f, float dt) {
-    int i = threadIdx.x;
-    if (i >= np) return;
+__global__ void k_forward_kinematics(float* __restrict__ pstate, int T, int np, int nbatch, int f, float dt) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= np * nbatch) return;
+    int i = (t / np) * SMX_MAXP + (t % np);
     float* s0 = pstate + ((size_t)i * T + f) * 13;
     float* s1 = s0 + 13;
     for (int d = 0; d < 3; d++) s1[d] = s0[d] + s0[7 + d] * dt;
@@ -1016,9 +1046,10 @@ __global__ void k_forward_kinematics(float* __restrict__ pstate, int T, int np, 
     double nn = sqrt(o[0] * o[0] + o[1] * o[1] + o[2] * o[2] + o[3] * o[3]);
     for (int d = 0; d < 4; d++) s1[3 + d] = (float)(o[d] / nn);
 }
-__global__ void k_forward_kinematics_grad(const float* __restrict__ pstate, double* __restrict__ pgrad, int T, int np, int f, float dtf) {
-    int i = threadIdx.x;
-    if (i >= np) return;
+__global__ void k_forward_kinematics_grad(const float* __restrict__ pstate, double* __restrict__ pgrad, int T, int np, int nbatch, int f, float dtf) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= np * nbatch) return;
+    int i = (t / np) * SMX_MAXP + (t % np);
     const float* s0 = pstate + ((size_t)i * T + f) * 13;
     double* g0 = pgrad + ((size_t)i * T + f) * 13;
     const double* g1 = g0 + 13;

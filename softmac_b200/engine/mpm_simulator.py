@@ -31,7 +31,7 @@ class _ContactFlags(list):
 
 class MPMSimulator:
     def __init__(self, cfg, primitives=(), env_dt=2e-3, rigid_velocity_control=False, device=0, sort_every=None,
-                 flags=0, stream=None):
+                 flags=0, stream=None, n_batch=1):
         dim = self.dim = cfg.dim
         assert dim == 3, "the B200 path implements the 3-D simulator used by every reference config"
         assert cfg.dtype == "float64"      # mpm_simulator.py:19 -- boundary dtype; device storage is fp32
@@ -41,7 +41,9 @@ class MPMSimulator:
         self.default_gravity = cfg.gravity
         self.n_primitive = len(primitives)
         quality = cfg.quality * 0.5
-        self.n_particles = cfg.n_particles
+        self.n_particles = cfg.n_particles          # per rollout
+        self.n_batch = max(int(n_batch), 1)         # independent rollouts batched in this handle (new; reference: 1)
+        self.n_total = self.n_particles * self.n_batch
         self.n_grid = int(128 * quality)
         self.dx, self.inv_dx = 1 / self.n_grid, float(self.n_grid)
         self.dt = cfg.dt
@@ -74,6 +76,7 @@ class MPMSimulator:
         c.sort_every = max(self.substeps, 4) if sort_every is None else sort_every
         c.device, c.flags = device, flags
         c.stream = stream
+        c.n_batch = self.n_batch
         h = vp()
         check(lib().smx_create(C.byref(c), C.byref(h)))
         self._h = h
@@ -126,9 +129,9 @@ class MPMSimulator:
         check(lib().smx_substep_grad(self._h, int(s)))
         if action is None:
             return None
-        g = np.zeros((self.n_control, self.dim))
+        g = np.zeros((self.n_batch * self.n_control, self.dim))
         check(lib().smx_get_action_grad(self._h, d_ptr(g)))
-        return g.reshape(np.shape(action))
+        return g.reshape(np.shape(action)) if np.size(action) == g.size else g
 
     def step(self, s0, count):
         """`count` substeps in one native call (the inner loop of TaichiEnv.step, taichi_env.py:101-102)."""
@@ -139,59 +142,62 @@ class MPMSimulator:
 
     # -- IO (mpm_simulator.py:448-574) ----------------------------------------------------------------------
     def get_state(self, f):
-        out = np.zeros((self.n_particles, 24))
+        out = np.zeros((self.n_total, 24))
         check(lib().smx_get_state(self._h, int(f), d_ptr(out)))
         return out
 
     def set_state(self, f, state):
         x, v, F, Cm = [as_d(a) for a in state[:4]]
-        n = self.n_particles
+        n = self.n_total
         assert x.size == 3 * n and v.size == 3 * n and F.size == 9 * n and Cm.size == 9 * n
         check(lib().smx_set_frame(self._h, int(f), d_ptr(x), d_ptr(v), d_ptr(F), d_ptr(Cm)))
 
     def reset(self, x):
         x = as_d(x)
-        assert x.ndim == 2 and x.shape[0] == self.n_particles and x.shape[1] in (self.dim, 24)
+        assert x.ndim == 2 and x.shape[1] in (self.dim, 24)
+        if x.shape[0] == self.n_particles and self.n_batch > 1:
+            x = np.ascontiguousarray(np.tile(x, (self.n_batch, 1)))     # same initial state for every rollout
+        assert x.shape[0] == self.n_total
         check(lib().smx_reset(self._h, d_ptr(x), int(x.shape[1])))
         self.cur = 0
 
     def get_x(self, f):
-        out = np.zeros((self.n_particles, self.dim))
+        out = np.zeros((self.n_total, self.dim))
         check(lib().smx_get_x(self._h, int(f), d_ptr(out)))
         return out
 
     def set_x(self, f, x):
-        x = as_d(x, (self.n_particles, self.dim))
+        x = as_d(x, (self.n_total, self.dim))
         check(lib().smx_set_x(self._h, int(f), d_ptr(x)))
 
     def get_v(self, f):
-        out = np.zeros((self.n_particles, self.dim))
+        out = np.zeros((self.n_total, self.dim))
         check(lib().smx_get_v(self._h, int(f), d_ptr(out)))
         return out
 
     def set_v(self, f, v):
-        v = as_d(v, (self.n_particles, self.dim))
+        v = as_d(v, (self.n_total, self.dim))
         check(lib().smx_set_v(self._h, int(f), d_ptr(v)))
 
     def copyframe(self, source, target):
         check(lib().smx_copy_frame(self._h, int(source), int(target)))
 
     def get_grad(self, f):
-        xg, vg = np.zeros((self.n_particles, self.dim)), np.zeros((self.n_particles, self.dim))
+        xg, vg = np.zeros((self.n_total, self.dim)), np.zeros((self.n_total, self.dim))
         check(lib().smx_get_grad(self._h, int(f), d_ptr(xg), d_ptr(vg)))
         return xg, vg
 
     # -- adjoint seeds (what Taichi losses do by writing x.grad[f] directly) --------------------------------
     def add_x_grad(self, f, g):
-        g = as_d(g, (self.n_particles, self.dim))
+        g = as_d(g, (self.n_total, self.dim))
         check(lib().smx_add_x_grad(self._h, int(f), d_ptr(g)))
 
     def add_state_grad(self, f, g24):
-        g = as_d(g24, (self.n_particles, 24))
+        g = as_d(g24, (self.n_total, 24))
         check(lib().smx_add_state_grad(self._h, int(f), d_ptr(g)))
 
     def get_state_grad(self, f):
-        out = np.zeros((self.n_particles, 24))
+        out = np.zeros((self.n_total, 24))
         check(lib().smx_get_state_grad(self._h, int(f), d_ptr(out)))
         return out
 
@@ -201,11 +207,16 @@ class MPMSimulator:
 
     # -- control (mpm_simulator.py:579-602) ---------------------------------------------------------------------
     def set_action(self, action):
-        a = as_d(np.asarray(action, dtype=np.float64)).reshape(self.n_control, self.dim)
+        a = as_d(np.asarray(action, dtype=np.float64)).reshape(-1, self.dim)
+        if a.shape[0] == self.n_control and self.n_batch > 1:
+            a = np.ascontiguousarray(np.tile(a, (self.n_batch, 1)))
+        assert a.shape[0] == self.n_batch * self.n_control
         check(lib().smx_set_action(self._h, d_ptr(a)))
 
     def set_control_idx(self, idx=None):
         idx = np.asarray(idx)
+        if idx.shape[0] == self.n_particles and self.n_batch > 1:
+            idx = np.tile(idx, self.n_batch)
         if self.n_control == 0:
             idx = idx * 0
         i = np.ascontiguousarray(idx, dtype=np.int32)
@@ -216,12 +227,12 @@ class MPMSimulator:
         check(lib().smx_synchronize(self._h))
 
     def sort_keys(self, f):
-        k = np.zeros(self.n_particles, dtype=np.uint32)
+        k = np.zeros(self.n_total, dtype=np.uint32)
         check(lib().smx_get_sort_keys(self._h, int(f), k.ctypes.data_as(C.POINTER(C.c_uint32))))
         return k
 
     def permutation(self, f):
-        p = np.zeros(self.n_particles, dtype=np.uint32)
+        p = np.zeros(self.n_total, dtype=np.uint32)
         check(lib().smx_get_permutation(self._h, int(f), p.ctypes.data_as(C.POINTER(C.c_uint32))))
         return p
 

@@ -40,8 +40,60 @@ class _ExtF:
         return a if dtype is None else a.astype(dtype)
 
 
+class PrimitiveBatchView:
+    """The coupling surface of a primitive for ONE rollout of a batched handle (MPMSimulator(n_batch > 1)): same
+    methods as ``Primitive`` (set_all_states / get_all_states_grad / ext_f / clear_ext_f / set_ext_f_grad), addressed to
+    batch ``b`` through the ``smx_*_b`` entry points.  A rigid simulator per rollout is handed these views."""
+
+    def __init__(self, prim, batch):
+        self._p, self._b = prim, int(batch)
+        self.ext_f = _ExtF(self)
+        self.enable_external_force = prim.enable_external_force
+        self.friction, self.softness = prim.friction, prim.softness
+
+    def get_ext_f(self):
+        o = np.zeros(6)
+        check(lib().smx_get_ext_f_b(self._p._sim, self._b, self._p._id, d_ptr(o)))
+        return o
+
+    def clear_ext_f(self):
+        check(lib().smx_clear_ext_f_b(self._p._sim, self._b, self._p._id))
+
+    def set_ext_f_grad(self, g):
+        g = as_d(np.asarray(g, dtype=np.float64), (6,))
+        check(lib().smx_set_ext_f_grad_b(self._p._sim, self._b, self._p._id, d_ptr(g)))
+
+    def set_all_states(self, f, state, f_end=None):
+        s = as_d(np.asarray(state, dtype=np.float64), (13,))
+        check(lib().smx_set_primitive_state_b(self._p._sim, self._b, self._p._id, f, (f + 1) if f_end is None else f_end, d_ptr(s)))
+
+    def get_all_states(self, f):
+        o = np.zeros(13)
+        check(lib().smx_get_primitive_state_b(self._p._sim, self._b, self._p._id, f, d_ptr(o)))
+        return o
+
+    def get_state(self, f):
+        return self.get_all_states(f)[:7]
+
+    def get_all_states_grad(self, f, f_end=None):
+        o = np.zeros(13)
+        check(lib().smx_get_primitive_state_grad_b(self._p._sim, self._b, self._p._id, f, (f + 1) if f_end is None else f_end, d_ptr(o)))
+        return o
+
+    def add_all_states_grad(self, f, g13):
+        g = as_d(np.asarray(g13, dtype=np.float64), (13,))
+        check(lib().smx_add_primitive_state_grad_b(self._p._sim, self._b, self._p._id, f, d_ptr(g)))
+
+    def reset(self):
+        self.clear_ext_f()
+
+
 class Primitive:
     state_dim = 7
+
+    def view(self, batch):
+        self._need()
+        return PrimitiveBatchView(self, batch)
 
     def __init__(self, cfg=None, dim=3, max_timesteps=2048, dtype="float64", rigid_velocity_control=False, **kwargs):
         defaults = self.default_config()

@@ -27,9 +27,22 @@ class Primitives:
     def __iter__(self):
         return iter(self.primitives)
 
+    def view(self, batch):
+        """Per-rollout container for a batched handle: the same primitives addressed to batch `batch`."""
+        return _PrimitivesView([p.view(batch) for p in self.primitives])
+
     def initialize(self):
         self.set_softness(666.)
 
     def reset(self):
         for i in self.primitives:
             i.reset()
+
+
+class _PrimitivesView(list):
+    def initialize(self):
+        pass
+
+    def reset(self):
+        for p in self:
+            p.reset()
