@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--n", type=int, default=1_000_000)
     ap.add_argument("--n-grid", type=int, default=128)
     ap.add_argument("--variant", default="A", choices=["A", "B"])
+    ap.add_argument("--batch", type=int, default=1, help="independent rollouts batched in one handle (per GPU)")
     ap.add_argument("--sort-every", type=int, default=16)
     ap.add_argument("--flags", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -172,7 +173,7 @@ def run_reference(args, rank, world):
 def config_dict(args, S):
     return {"workload": f"cube-{args.n} variant {args.variant}: {args.n} particles, {args.n_grid}^3 grid, corotated plastic, mixed contact, "
                         f"{S} substeps forward + {S} backward per step",
-            "n_particles": args.n, "n_grid": args.n_grid, "substeps_per_step": S, "variant": args.variant, "dt": DT,
+            "n_particles": args.n, "rollouts_per_gpu": args.batch, "n_grid": args.n_grid, "substeps_per_step": S, "variant": args.variant, "dt": DT,
             "sort_every": args.sort_every, "parallelism": f"{args.gpus} independent rollout(s), one per GPU, gradient all-reduce" if args.gpus > 1 else "single GPU",
             "cache": "inputs larger than L2: 96 MB per particle frame, one fresh frame per substep"}
 
@@ -221,10 +222,12 @@ def run_cuda(args, rank, world, local_rank):
         m.softness[None] = 666.
         prims.append(m)
     P = Primitives(primitives=prims, max_timesteps=S + 2)
-    sim = MPMSimulator(cfg, P, env_dt=5 * DT, device=local_rank, sort_every=args.sort_every, flags=args.flags)
+    sim = MPMSimulator(cfg, P, env_dt=5 * DT, device=local_rank, sort_every=args.sort_every, flags=args.flags, n_batch=args.batch)
     for p in prims:
         p.set_all_states(0, np.array([0.5, 0.04, 0.5, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0.]), f_end=S + 2)
     st, seed = make_inputs(args, rank)
+    if args.batch > 1:
+        st, seed = np.tile(st, (args.batch, 1)), np.tile(seed, (args.batch, 1))
     gsum = torch.zeros(16, device="cuda")
 
     def barrier():
@@ -261,7 +264,7 @@ def run_cuda(args, rank, world, local_rank):
     if dist:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
     ms_step = float(t_dev.item())
-    value = world * args.n * S / (ms_step * 1e-3)
+    value = world * args.batch * args.n * S / (ms_step * 1e-3)
     counters = sim.counters()
 
     # ---- per-kernel durations (CUDA events on the simulator's stream), one extra step --------------------------
@@ -289,8 +292,8 @@ def run_cuda(args, rank, world, local_rank):
         t = torch.tensor([float(np.median(times))], device="cuda", dtype=torch.float64)
         if dist:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * args.n * S / float(t.item()), "unit": UNIT, "h2d_bytes_per_step": args.n * 24 * 4 + args.n * 3 * 4,
-               "d2h_bytes_per_step": args.n * 24 * 4, "checksum": float(np.abs(g0).sum())}
+        e2e = {"value": world * args.batch * args.n * S / float(t.item()), "unit": UNIT, "h2d_bytes_per_step": args.batch * (args.n * 24 * 4 + args.n * 3 * 4),
+               "d2h_bytes_per_step": args.batch * args.n * 24 * 4, "checksum": float(np.abs(g0).sum())}
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -349,9 +352,9 @@ def kernel_roofline(sim, args, S):
     avg = {k: float(np.mean(v)) for k, v in tot.items()}
     total = sum(avg.values())
     top = max((k for k in avg if k in KERNEL_BYTES), key=lambda k: avg[k])
-    achieved = KERNEL_BYTES[top] * args.n / (avg[top] * 1e-3) / 1e9
+    achieved = KERNEL_BYTES[top] * args.n * args.batch / (avg[top] * 1e-3) / 1e9
     return {"bound": "hbm", "kernel": top, "achieved": achieved, "unit": "GB/s", "traffic": None,
-            "algorithmic_bytes_per_launch": KERNEL_BYTES[top] * args.n, "avg_launch_ms": avg[top],
+            "algorithmic_bytes_per_launch": KERNEL_BYTES[top] * args.n * args.batch, "avg_launch_ms": avg[top],
             "share_of_substep_pair": avg[top] / total if total > 0 else None,
             "kernel_ms": avg, "how": "CUDA events around each launch on the simulator stream, 8 forward + 8 backward substeps after the timed region"}
 

@@ -92,6 +92,11 @@ struct smx_sim {
     float4* ckpt = nullptr;
     size_t ckpt_rec = 0;                // float4 entries per substep record
     int ckpt_cap = 0;                   // blocks reserved per array
+    int ckpt_narr = 0;
+    bool ckpt_enabled = true, ckpt_dirty = true;
+    unsigned long long ckpt_overflow_seen = 0;
+    int ckpt_cap_hint = 1;
+    size_t ckpt_bytes = 0;
     std::vector<long long> ckpt_order;  // uid of the ordering the record of substep f was written in (-1: none)
     std::vector<char> ckpt_contact;
     // adjoint ping-pong
@@ -111,7 +116,7 @@ struct smx_sim {
     uint32_t *keys_a = nullptr, *keys_b = nullptr, *iota = nullptr;
     void* cub_tmp = nullptr; size_t cub_bytes = 0;
     unsigned long long* counters = nullptr;
-    long long n_resorts = 0;
+    long long n_resorts = 0, last_ckpt_overflow = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     long long launches = 0;
     bool prof = false;
@@ -282,6 +287,32 @@ static int clear_grids(smx_sim* s, const Order& o, float4* a, float4* b, float4*
     return SMX_OK;
 }
 
+// Size the grid-checkpoint arena from the ordering of frame f: one record per substep holding g_in, g_out (+ g_mix
+// with contact) of up to `cap` active blocks, cap = 1.5 x the current active-block count (the count only grows slowly as
+// the material spreads; a record that does not fit is flagged on the device and the adjoint recomputes instead).
+// One host sync, done once after reset / set_frame.
+static int ensure_ckpt(smx_sim* s, int f) {
+    s->ckpt_dirty = false;
+    if (!s->ckpt_enabled) return SMX_OK;
+    int total = s->B * s->P.nb3, nbk = total;
+    Order& o = s->orders[s->order_of[f]];
+    if (!s->dense && o.nblocks) {
+        CK(cudaStreamSynchronize(s->stream));
+        CK(cudaMemcpy(&nbk, o.nblocks, sizeof(int), cudaMemcpyDeviceToHost));
+    }
+    int cap = (int)std::min<long long>(total, (long long)s->ckpt_cap_hint * (nbk + nbk / 2) + 64);
+    int narr = s->has_contact() ? 3 : 2;
+    if (s->ckpt && cap <= s->ckpt_cap && narr <= s->ckpt_narr) return SMX_OK;
+    if (s->ckpt) { CK(cudaStreamSynchronize(s->stream)); cudaFree(s->ckpt); s->ckpt = nullptr; }
+    std::fill(s->ckpt_order.begin(), s->ckpt_order.end(), -1);
+    size_t rec = (size_t)narr * cap * 64;
+    size_t bytes = (size_t)s->cfg.max_steps * rec * sizeof(float4), free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    if (bytes > free_b / 2 || cudaMalloc(&s->ckpt, bytes) != cudaSuccess) { cudaGetLastError(); s->ckpt = nullptr; s->ckpt_rec = 0; s->ckpt_cap = 0; return SMX_OK; }
+    s->ckpt_rec = rec; s->ckpt_cap = cap; s->ckpt_narr = narr; s->ckpt_bytes = bytes;
+    return SMX_OK;
+}
+
 // P2G + grid update + forecast contact of substep f (everything before G2P); shared by forward and adjoint
 static int forward_to_grid(smx_sim* s, int f, bool write_F, bool accumulate) {
     const Params& P = s->P;
@@ -421,16 +452,7 @@ int smx_create(const smx_config* cfg, smx_sim** out) {
     size_t pool_bytes = (size_t)(T + 1) * s->frame_floats * sizeof(float);
     if (cudaMalloc(&s->pool, pool_bytes) != cudaSuccess) { cudaGetLastError(); delete s; return fail(SMX_ERR_NOMEM, "smx_create: cannot allocate %.1f MB of particle checkpoints", pool_bytes / 1e6); }
     s->ckpt_order.assign(T, -1); s->ckpt_contact.assign(T, 0);
-    if (!(cfg->flags & SMX_FLAG_NO_GRID_CKPT)) {
-        // reserve one record per substep: all blocks of the grid for g_in and g_out, plus g_mix when the forecast
-        // contact model is on; skipped (adjoint recomputes instead) when that would not fit comfortably
-        int narr = cfg->collision_type == 2 ? 3 : 2;
-        s->ckpt_cap = B * P.nb3;
-        s->ckpt_rec = (size_t)narr * s->ckpt_cap * 64;
-        size_t bytes = (size_t)T * s->ckpt_rec * sizeof(float4), free_b = 0, total_b = 0;
-        cudaMemGetInfo(&free_b, &total_b);
-        if (bytes > free_b / 3 || cudaMalloc(&s->ckpt, bytes) != cudaSuccess) { cudaGetLastError(); s->ckpt = nullptr; s->ckpt_rec = 0; }
-    }
+    s->ckpt_enabled = !(cfg->flags & SMX_FLAG_NO_GRID_CKPT);
     CK(cudaMalloc(&s->g_in, s->G * sizeof(float4))); CK(cudaMalloc(&s->g_out, s->G * sizeof(float4))); CK(cudaMalloc(&s->g_mix, s->G * sizeof(float4)));
     CK(cudaMalloc(&s->gg_out, s->G * sizeof(float4))); CK(cudaMalloc(&s->gg_mix, s->G * sizeof(float4)));
     CK(cudaMemsetAsync(s->g_in, 0, s->G * sizeof(float4), s->stream)); CK(cudaMemsetAsync(s->g_out, 0, s->G * sizeof(float4), s->stream));
@@ -506,6 +528,7 @@ int smx_add_primitive(smx_sim* s, const double* sdf, const double* normal, const
         hp.d.inv_dx = (float)(1.0 / sdf_dx);
     }
     s->prims.push_back(hp);
+    s->ckpt_dirty = true;
     s->P.np = (int)s->prims.size();
     TRY(sync_prims(s));
     return (int)s->prims.size() - 1;
@@ -518,6 +541,7 @@ int smx_set_primitive_params(smx_sim* s, int32_t id, double friction, double sof
 int smx_set_primitive_contact(smx_sim* s, int32_t id, int32_t enabled) {
     TRY(check_prim(s, id, "smx_set_primitive_contact"));
     s->prims[id].d.enabled = enabled ? 1 : 0;
+    s->ckpt_dirty = true;
     return sync_prims(s);
 }
 
@@ -530,6 +554,7 @@ int smx_reset(smx_sim* s, const double* state, int32_t ncols) {
     std::fill(s->trans_from.begin(), s->trans_from.end(), -1);
     std::fill(s->ckpt_order.begin(), s->ckpt_order.end(), -1);
     s->adj_frame = -1; s->adj_order = -1;
+    s->ckpt_dirty = true;
     gc_orders(s);                       // every ordering is unreferenced now: recycle all of them
     int n = s->P.n;
     Order root; s->order_of[0] = new_order_id(s, root);
@@ -562,7 +587,7 @@ int smx_set_frame(smx_sim* s, int32_t f, const double* x, const double* v, const
     if (v) TRY(upload_cols(s, f, v, 3, 3));
     if (F) TRY(upload_cols(s, f, F, 9, 6));
     if (C) TRY(upload_cols(s, f, C, 9, 15));
-    if (x) TRY(resort(s, f, false));        // positions changed: re-bin (cuts the adjoint chain at f, as in the reference)
+    if (x) { TRY(resort(s, f, false)); s->ckpt_dirty = true; }      // positions changed: re-bin (cuts the adjoint chain at f, as in the reference)
     return SMX_OK;
 }
 int smx_get_state(smx_sim* s, int32_t f, double* out24) {
@@ -781,12 +806,13 @@ int smx_substep(smx_sim* s, int32_t f) {
     CK(cudaSetDevice(s->cfg.device));
     s->order_of[f + 1] = s->order_of[f]; s->trans_from[f + 1] = -1;
     s->ckpt_order[f] = -1; s->ckpt_order[f + 1] = -1;
+    if (s->ckpt_dirty) TRY(ensure_ckpt(s, f));
     TRY(forward_to_grid(s, f, true, true));
-    if (s->ckpt) {
+    if (s->ckpt && (!s->has_contact() || s->ckpt_narr == 3)) {
         Order& o = s->orders[s->order_of[f]];
         bool contact = s->has_contact();
-        k_ckpt_copy<<<grid_blocks_launch(s), 256, 0, s->stream>>>(s->dense ? nullptr : o.blocks, o.nblocks, s->ckpt_cap, s->ckpt_cap, s->ckpt + (size_t)f * s->ckpt_rec,
-                                                                 s->g_in, s->g_out, contact ? s->g_mix : nullptr, 0);
+        k_ckpt_copy<<<grid_blocks_launch(s), 256, 0, s->stream>>>(s->dense ? nullptr : o.blocks, o.nblocks, s->B * s->P.nb3, s->ckpt_cap, s->ckpt + (size_t)f * s->ckpt_rec,
+                                                                 s->g_in, s->g_out, contact ? s->g_mix : nullptr, 0, s->counters);
         CKLN(s, "ckpt_save");
         s->ckpt_order[f] = o.uid; s->ckpt_contact[f] = contact;
     }
@@ -802,6 +828,16 @@ int smx_substep_grad(smx_sim* s, int32_t f) {
     CK(cudaSetDevice(s->cfg.device));
     const Params& P = s->P;
     int o = s->order_of[f];
+    if (s->adj_frame != f + 1 && s->ckpt) {     // start of a backward pass: did every grid record fit? (one sync)
+        unsigned long long ov = 0;
+        CK(cudaStreamSynchronize(s->stream));
+        CK(cudaMemcpy(&ov, s->counters + 2, sizeof ov, cudaMemcpyDeviceToHost));
+        if (ov != s->ckpt_overflow_seen) {
+            s->ckpt_overflow_seen = ov;
+            std::fill(s->ckpt_order.begin(), s->ckpt_order.end(), -1);      // recompute instead; grow the arena at the next reset
+            s->ckpt_cap_hint = 2;
+        }
+    }
     if (s->adj_frame != f + 1) {        // start of a backward pass: the adjoint of frame f+1 is its loss seed
         CK(cudaMemsetAsync(s->adj_cur, 0, s->frame_floats * sizeof(float), s->stream));
         s->adj_frame = f + 1; s->adj_order = s->order_of[f + 1];
@@ -818,8 +854,8 @@ int smx_substep_grad(smx_sim* s, int32_t f) {
     bool contact = s->has_contact();
     PrimSet ps = s->primset();
     if (s->ckpt && s->ckpt_order[f] == ord.uid && (bool)s->ckpt_contact[f] == contact) {
-        k_ckpt_copy<<<grid_blocks_launch(s), 256, 0, s->stream>>>(s->dense ? nullptr : ord.blocks, ord.nblocks, s->ckpt_cap, s->ckpt_cap, s->ckpt + (size_t)f * s->ckpt_rec,
-                                                                 s->g_in, s->g_out, contact ? s->g_mix : nullptr, 1);
+        k_ckpt_copy<<<grid_blocks_launch(s), 256, 0, s->stream>>>(s->dense ? nullptr : ord.blocks, ord.nblocks, s->B * s->P.nb3, s->ckpt_cap, s->ckpt + (size_t)f * s->ckpt_rec,
+                                                                 s->g_in, s->g_out, contact ? s->g_mix : nullptr, 1, s->counters);
         CKLN(s, "ckpt_restore");
     } else {
         TRY(forward_to_grid(s, f, false, false));
@@ -996,6 +1032,7 @@ int smx_get_counters(smx_sim* s, int64_t out[4]) {
         for (int f = s->cfg.max_steps - 1; f >= 0; f--)
             if (s->order_of[f] >= 0 && s->orders[s->order_of[f]].nblocks) { CK(cudaMemcpy(&nb, s->orders[s->order_of[f]].nblocks, sizeof(int), cudaMemcpyDeviceToHost)); break; }
     out[0] = (int64_t)h[0]; out[1] = (int64_t)h[1]; out[2] = s->n_resorts; out[3] = nb;
+    s->last_ckpt_overflow = (long long)h[2];
     return SMX_OK;
 }
 int smx_frame_component_dev(smx_sim* s, int32_t f, int32_t c, void** ptr) {

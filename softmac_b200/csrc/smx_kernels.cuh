@@ -982,8 +982,13 @@ __global__ void k_mark_blocks_sorted(Params P, const uint32_t* __restrict__ keys
 // grid checkpoints: the active blocks of up to three float4 grids <-> a compact per-substep record
 // record layout: [array][active-block slot][64 nodes]; `cap` = blocks reserved per array
 __global__ void __launch_bounds__(256) k_ckpt_copy(const uint32_t* __restrict__ blocks, const int* __restrict__ nblocks, int nb3, int cap,
-                                                    float4* __restrict__ rec, float4* __restrict__ a, float4* __restrict__ b, float4* __restrict__ c, int restore) {
+                                                    float4* __restrict__ rec, float4* __restrict__ a, float4* __restrict__ b, float4* __restrict__ c, int restore,
+                                                    unsigned long long* __restrict__ counters) {
     int total = blocks ? *nblocks : nb3;
+    if (total > cap) {      // record does not fit: flagged, the host falls back to recomputation (counters[2])
+        if (blockIdx.x == 0 && threadIdx.x == 0 && !restore) atomicAdd(counters + 2, 1ull);
+        total = cap;
+    }
     for (int bi = blockIdx.x * 4 + (threadIdx.x >> 6); bi < total; bi += gridDim.x * 4) {
         uint32_t node = (blocks ? blocks[bi] : (uint32_t)bi) * 64u + (threadIdx.x & 63);
         size_t slot = (size_t)bi * 64 + (threadIdx.x & 63);
