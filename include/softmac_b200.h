@@ -131,6 +131,13 @@ int smx_add_primitive_state_grad_b(smx_sim* sim, int32_t batch, int32_t id, int3
 int smx_get_ext_f_b(smx_sim* sim, int32_t batch, int32_t id, double* out6);
 int smx_clear_ext_f_b(smx_sim* sim, int32_t batch, int32_t id);
 int smx_set_ext_f_grad_b(smx_sim* sim, int32_t batch, int32_t id, const double* g6);
+/* bulk coupling for batched handles: ONE transfer for all rollouts and primitives per env step.  Arrays are
+ * [n_batch][n_primitives][6 | 13], batch-major.  Same semantics as looping the calls above over (batch, id). */
+int smx_get_ext_f_all(smx_sim* sim, double* out6);
+int smx_clear_ext_f_all(smx_sim* sim);
+int smx_set_ext_f_grads_all(smx_sim* sim, const double* g6);
+int smx_set_primitive_states_all(smx_sim* sim, int32_t f0, int32_t f1, const double* s13);
+int smx_get_primitive_state_grads_all(smx_sim* sim, int32_t f0, int32_t f1, double* out13);
 /* velocity-control mode: Primitive.set_action(s, n, a6) / get_action_grad(s, n) (primitive_base.py:285-319) */
 int smx_set_primitive_action(smx_sim* sim, int32_t id, int32_t s, int32_t n, const double* a6);
 int smx_get_primitive_action_grad(smx_sim* sim, int32_t id, int32_t s, int32_t n, double* out6);

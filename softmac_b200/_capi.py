@@ -72,6 +72,11 @@ _SIGS = {
     "smx_get_ext_f_b": [vp, C.c_int32, C.c_int32, dp],
     "smx_clear_ext_f_b": [vp, C.c_int32, C.c_int32],
     "smx_set_ext_f_grad_b": [vp, C.c_int32, C.c_int32, dp],
+    "smx_get_ext_f_all": [vp, dp],
+    "smx_clear_ext_f_all": [vp],
+    "smx_set_ext_f_grads_all": [vp, dp],
+    "smx_set_primitive_states_all": [vp, C.c_int32, C.c_int32, dp],
+    "smx_get_primitive_state_grads_all": [vp, C.c_int32, C.c_int32, dp],
     "smx_set_primitive_action": [vp, C.c_int32, C.c_int32, C.c_int32, dp],
     "smx_get_primitive_action_grad": [vp, C.c_int32, C.c_int32, C.c_int32, dp],
     "smx_set_action": [vp, dp],

@@ -731,6 +731,64 @@ int smx_set_ext_f_grad_b(smx_sim* s, int32_t batch, int32_t id, const double* g6
     TRY(check_prim(s, id, "smx_set_ext_f_grad_b")); TRY(check_batch(s, batch, "smx_set_ext_f_grad_b"));
     return set_ext_f_grad(s, batch, batch + 1, id, g6);
 }
+// ---- bulk coupling (batched handles): one transfer for all rollouts and primitives ---------------------------------
+int smx_get_ext_f_all(smx_sim* s, double* out) {
+    if (!s || !out) return fail(SMX_ERR_ARG, "smx_get_ext_f_all: null argument");
+    CK(cudaSetDevice(s->cfg.device));
+    int np = (int)s->prims.size();
+    std::vector<double> h((size_t)s->B * SMX_MAXP * 6);
+    CK(cudaMemcpyAsync(h.data(), s->ext_f, h.size() * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    for (int b = 0; b < s->B; b++) for (int i = 0; i < np; i++) for (int c = 0; c < 6; c++) out[((size_t)b * np + i) * 6 + c] = h[((size_t)b * SMX_MAXP + i) * 6 + c];
+    return SMX_OK;
+}
+int smx_clear_ext_f_all(smx_sim* s) {
+    if (!s) return fail(SMX_ERR_ARG, "smx_clear_ext_f_all: null simulator");
+    CK(cudaSetDevice(s->cfg.device));
+    CK(cudaMemsetAsync(s->ext_f, 0, (size_t)s->B * SMX_MAXP * 6 * sizeof(double), s->stream));
+    CK(cudaMemsetAsync(s->ext_f_grad, 0, (size_t)s->B * SMX_MAXP * 6 * sizeof(float), s->stream));
+    return SMX_OK;
+}
+int smx_set_ext_f_grads_all(smx_sim* s, const double* g) {
+    if (!s || !g) return fail(SMX_ERR_ARG, "smx_set_ext_f_grads_all: null argument");
+    CK(cudaSetDevice(s->cfg.device));
+    int np = (int)s->prims.size();
+    std::vector<float> h((size_t)s->B * SMX_MAXP * 6, 0.f);
+    for (int b = 0; b < s->B; b++) for (int i = 0; i < np; i++) for (int c = 0; c < 6; c++) h[((size_t)b * SMX_MAXP + i) * 6 + c] = (float)g[((size_t)b * np + i) * 6 + c];
+    CK(cudaMemcpyAsync(s->ext_f_grad, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return SMX_OK;
+}
+int smx_set_primitive_states_all(smx_sim* s, int32_t f0, int32_t f1, const double* st) {
+    if (!s || !st) return fail(SMX_ERR_ARG, "smx_set_primitive_states_all: null argument");
+    if (f0 < 0 || f1 > s->cfg.max_steps || f0 >= f1) return fail(SMX_ERR_RANGE, "smx_set_primitive_states_all: frame range [%d, %d) outside [0, %d)", f0, f1, s->cfg.max_steps);
+    CK(cudaSetDevice(s->cfg.device));
+    int np = (int)s->prims.size();
+    if (np == 0) return SMX_OK;
+    size_t cnt = (size_t)s->B * np * 13;
+    if (cnt > (size_t)std::max(s->P.n, 1) * 24) return fail(SMX_ERR_ARG, "smx_set_primitive_states_all: staging buffer too small");
+    CK(cudaStreamSynchronize(s->stream));
+    for (size_t i = 0; i < cnt; i++) s->stage_host[i] = (float)st[i];
+    CK(cudaMemcpyAsync(s->stage_dev, s->stage_host, cnt * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    long long nt = (long long)s->B * np * (f1 - f0);
+    k_fill_prim_states<<<nblk(nt, 128), 128, 0, s->stream>>>(s->pstate, s->stage_dev, s->cfg.max_steps, np, s->B, f0, f1); CKL(s);
+    return SMX_OK;
+}
+int smx_get_primitive_state_grads_all(smx_sim* s, int32_t f0, int32_t f1, double* out) {
+    if (!s || !out) return fail(SMX_ERR_ARG, "smx_get_primitive_state_grads_all: null argument");
+    if (f0 < 0 || f1 > s->cfg.max_steps || f0 >= f1) return fail(SMX_ERR_RANGE, "smx_get_primitive_state_grads_all: frame range [%d, %d) outside [0, %d)", f0, f1, s->cfg.max_steps);
+    CK(cudaSetDevice(s->cfg.device));
+    int np = (int)s->prims.size();
+    if (np == 0) return SMX_OK;
+    size_t cnt = (size_t)s->B * np * 13;
+    if (cnt * 2 > (size_t)std::max(s->P.n, 1) * 24) return fail(SMX_ERR_ARG, "smx_get_primitive_state_grads_all: staging buffer too small");
+    double* dev = reinterpret_cast<double*>(s->stage_dev);
+    k_sum_prim_grads<<<nblk((long long)cnt, 128), 128, 0, s->stream>>>(s->pgrad, dev, s->cfg.max_steps, np, s->B, f0, f1); CKL(s);
+    CK(cudaMemcpyAsync(out, dev, cnt * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return SMX_OK;
+}
+
 int smx_set_primitive_action(smx_sim* s, int32_t id, int32_t st, int32_t n, const double* a6) {
     TRY(check_prim(s, id, "smx_set_primitive_action"));
     if (!a6) return fail(SMX_ERR_ARG, "smx_set_primitive_action: null input");

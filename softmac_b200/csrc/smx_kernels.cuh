@@ -1032,6 +1032,26 @@ __global__ void k_check_active(Params P, const float* __restrict__ fr, const uin
             for (int k = b2 >> 2; k <= (b2 + 2) >> 2; k++) ok &= flags[batch_of(P, j) * P.nb3 + (i * P.nb + jj) * P.nb + k] != 0;
     if (!ok) atomicAdd(counters + 1, 1ull);
 }
+// bulk coupling for batched handles: one launch writes / reads the state series of every (batch, primitive)
+__global__ void k_fill_prim_states(float* __restrict__ pstate, const float* __restrict__ staged, int T, int np, int nbatch, int f0, int f1) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;      // one thread per (batch, primitive, frame)
+    int nf = f1 - f0;
+    if (t >= nbatch * np * nf) return;
+    int f = f0 + t % nf, bi = t / nf, i = bi % np, b = bi / np;
+    const float* src = staged + (size_t)(b * np + i) * 13;
+    float* dst = pstate + (((size_t)b * SMX_MAXP + i) * T + f) * 13;
+#pragma unroll
+    for (int c = 0; c < 13; c++) dst[c] = src[c];
+}
+__global__ void k_sum_prim_grads(const double* __restrict__ pgrad, double* __restrict__ out, int T, int np, int nbatch, int f0, int f1) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;      // one thread per (batch, primitive, component)
+    if (t >= nbatch * np * 13) return;
+    int c = t % 13, bi = t / 13, i = bi % np, b = bi / np;
+    const double* src = pgrad + (((size_t)b * SMX_MAXP + i) * T) * 13 + c;
+    double acc = 0;
+    for (int f = f0; f < f1; f++) acc += src[(size_t)f * 13];
+    out[t] = acc;
+}
 // Primitive.forward_kinematics and its adjoint (primitive_base.py:280-283, primitive_utils.py:20-40); one thread
 __global__ void k_forward_kinematics(float* __restrict__ pstate, int T, int np, int nbatch, int f, float dt) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;

@@ -1,0 +1,171 @@
+"""Lock-step environment for B independent rollouts batched in ONE simulator handle (BASELINE config 4:
+"64 independent demo_grip rollouts ... several rollouts per GPU batched in one handle").
+
+The control flow per rollout is exactly ``TaichiEnv.step / step_grad / backward`` (softmac/engine/taichi_env.py:93-151);
+what changes is the plumbing: the MPM substeps of all rollouts run in the same kernel launches, and the per-env-step
+coupling traffic (wrench out, primitive states in, state adjoints out, wrench adjoints in) is ONE transfer for all
+rollouts and primitives (``smx_*_all``) instead of B x P small ones.  Every rollout keeps its own rigid simulator
+(the Jade bridge or the stand-in), which talks to ``BufferedPrimitiveView`` objects backed by host mirrors.
+"""
+import numpy as np
+
+from .._capi import lib, check, d_ptr
+
+
+class _ExtF:
+    def __init__(self, v):
+        self._v = v
+
+    def to_numpy(self):
+        return self._v.buf.ext_f[self._v.b, self._v.i].copy()
+
+
+class BufferedPrimitiveView:
+    """Primitive coupling surface of rollout `b`, primitive `i`, backed by a CouplingBuffer."""
+
+    def __init__(self, buf, b, i, prim):
+        self.buf, self.b, self.i = buf, b, i
+        self.enable_external_force = prim.enable_external_force
+        self.friction, self.softness = prim.friction, prim.softness
+        self.ext_f = _ExtF(self)
+
+    def clear_ext_f(self):                      # the device-side wrench was cleared for all rollouts right after the pull
+        self.buf.ext_f[self.b, self.i] = 0.0
+
+    def set_ext_f_grad(self, g):
+        self.buf.ext_f_grad[self.b, self.i] = np.asarray(g, dtype=np.float64)
+
+    def set_all_states(self, f, state, f_end=None):
+        self.buf.note_state(self.b, self.i, f, (f + 1) if f_end is None else f_end, np.asarray(state, dtype=np.float64))
+
+    def get_all_states_grad(self, f, f_end=None):
+        return self.buf.state_grad_of(self.b, self.i, f, (f + 1) if f_end is None else f_end)
+
+    def reset(self):
+        self.clear_ext_f()
+
+
+class _Views(list):
+    def initialize(self):
+        pass
+
+    def reset(self):
+        for p in self:
+            p.reset()
+
+
+class CouplingBuffer:
+    def __init__(self, sim, primitives):
+        self.sim, self.h = sim, sim._h
+        self.B, self.P = sim.n_batch, len(primitives)
+        self.ext_f = np.zeros((self.B, self.P, 6))
+        self.ext_f_grad = np.zeros((self.B, self.P, 6))
+        self.states = np.zeros((self.B, self.P, 13))
+        self.state_range = None
+        self.grads = np.zeros((self.B, self.P, 13))
+        self.grad_range = None
+        self.views = [_Views(BufferedPrimitiveView(self, b, i, primitives[i]) for i in range(self.P)) for b in range(self.B)]
+
+    # wrench ------------------------------------------------------------------------------------------------------
+    def pull_ext_f(self):
+        check(lib().smx_get_ext_f_all(self.h, d_ptr(self.ext_f)))
+        check(lib().smx_clear_ext_f_all(self.h))
+
+    def push_ext_f_grads(self):
+        check(lib().smx_set_ext_f_grads_all(self.h, d_ptr(self.ext_f_grad)))
+
+    # primitive states ----------------------------------------------------------------------------------------------
+    def note_state(self, b, i, f0, f1, s13):
+        self.states[b, i] = s13
+        if self.state_range is None:
+            self.state_range = [f0, f1]
+        else:
+            self.state_range = [min(self.state_range[0], f0), max(self.state_range[1], f1)]
+
+    def push_states(self):
+        if self.state_range is not None:
+            f0, f1 = self.state_range
+            f1 = min(f1, self.sim.max_steps)
+            if f0 < f1:
+                check(lib().smx_set_primitive_states_all(self.h, int(f0), int(f1), d_ptr(self.states)))
+            self.state_range = None
+
+    # primitive state adjoints ----------------------------------------------------------------------------------------
+    def pull_state_grads(self, f0, f1):
+        f1 = min(f1, self.sim.max_steps)
+        self.grads[:] = 0
+        if f0 < f1:
+            check(lib().smx_get_primitive_state_grads_all(self.h, int(f0), int(f1), d_ptr(self.grads)))
+        self.grad_range = (f0, f1)
+
+    def state_grad_of(self, b, i, f0, f1):
+        """The rigid bridge sums get_all_states_grad(j) over the frames of an env step (rigid_simulator.py:207-208); the sum
+        over the pulled range is returned for its first frame and zero for the others."""
+        r0, r1 = self.grad_range
+        if f0 <= r0 < f1:
+            return self.grads[b, i].copy()
+        return np.zeros(13)
+
+
+class BatchedTaichiEnv:
+    def __init__(self, simulator, primitives, make_rigid, init_particles, loss=None):
+        """make_rigid(b, views) -> a rigid simulator (RigidSimulator surface) for rollout b talking to `views`."""
+        self.simulator, self.primitives, self.loss = simulator, primitives, loss
+        self.B, self.substeps = simulator.n_batch, simulator.substeps
+        self.buf = CouplingBuffer(simulator, primitives)
+        self.rigid = [make_rigid(b, self.buf.views[b]) for b in range(self.B)]
+        self.init_particles = np.asarray(init_particles, dtype=np.float64)
+        self.action_list = []
+        primitives.initialize()
+        simulator.initialize()
+        self.reset()
+
+    def reset(self):
+        self.primitives.reset()
+        self.simulator.reset(self.init_particles)
+        for r in self.rigid:
+            r.reset()                      # writes the initial pose of frames [0, substeps) into the buffer
+        self.buf.push_states()
+        check(lib().smx_clear_ext_f_all(self.simulator._h))
+        self.action_list = []
+
+    def step(self, actions):
+        """actions: (B, action_dim)."""
+        sim = self.simulator
+        start = sim.cur
+        sim.cur = start + self.substeps
+        self.action_list.append(np.asarray(actions, dtype=np.float64))
+        sim.step(start, self.substeps)
+        self.buf.pull_ext_f()
+        for b, r in enumerate(self.rigid):
+            r.step(start // self.substeps, actions[b])
+        self.buf.push_states()
+
+    def step_grad(self, actions):
+        sim = self.simulator
+        start = sim.cur
+        sim.cur = start - self.substeps
+        k = sim.cur // self.substeps
+        # rigid.step_grad(k) pulls the primitive-state adjoints of env step k+1 (frames [(k+1) sub, (k+2) sub))
+        self.buf.pull_state_grads((k + 1) * self.substeps, (k + 2) * self.substeps)
+        grads = []
+        for b, r in enumerate(self.rigid):
+            ag, ext_list = r.step_grad(k, actions[b])
+            grads.append(ag)
+            for i, g in enumerate(ext_list):
+                self.buf.ext_f_grad[b, i] = g
+        self.buf.push_ext_f_grads()
+        sim.step_grad(start, self.substeps)
+        return np.stack(grads)
+
+    def backward(self):
+        for r in self.rigid:
+            r.state_grad = np.zeros(r.state_dim)
+        total = self.simulator.cur // self.substeps
+        out = []
+        for s in range(total - 1, -1, -1):
+            out = [self.step_grad(self.action_list[s])] + out
+        self.buf.pull_state_grads(0, self.substeps)
+        for r in self.rigid:
+            r.state_grad = r.state_grad + r.get_ext_state_grad(0)
+        return np.stack(out, axis=1)            # (B, steps, action_dim)

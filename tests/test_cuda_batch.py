@@ -86,3 +86,57 @@ def test_batch_broadcast_reset_and_permutation():
         assert perm[b].min() >= b * n and perm[b].max() < (b + 1) * n
     keys = sim.sort_keys(0)
     assert np.all(np.diff(keys.astype(np.int64)) >= 0)
+
+
+def test_batched_env_matches_single_rollout_envs():
+    """Two rollouts with different actions in one handle + bulk coupling == two separate TaichiEnv episodes."""
+    from softmac_b200.engine import MPMSimulator, Primitives, Mesh
+    from softmac_b200.engine.taichi_env import TaichiEnv
+    from softmac_b200.engine.batched_env import BatchedTaichiEnv
+    from softmac_b200.engine.rigid_simulator import RigidSimulator
+    from softmac_b200.engine.losses import PointwiseLoss
+    from softmac_b200.config import CfgNode
+    n, B, env_steps, substeps = 2000, 2, 4, 5
+    n_grid, dt = 32, 2e-4
+    max_steps = env_steps * substeps + substeps + 2
+    rng = np.random.default_rng(5)
+    x = ((rng.random((n, 3)) * 2 - 1) * 0.05 + np.array([0.5, 0.3, 0.5])).astype(np.float32).astype(np.float64)
+    tab = scenes.sphere_table(radius=0.06, dx=0.01, margin=0.04)
+    bodies = [dict(joint="prismatic", axis=(1, 0, 0), origin=(0.5 - 0.108, 0.3, 0.5), mass=1.0, gravity=False),
+              dict(joint="prismatic", axis=(1, 0, 0), origin=(0.5 + 0.108, 0.3, 0.5), mass=1.0, gravity=False)]
+    rcfg = CfgNode(gravity=(0., 0., 0.), init_state=(0., 0., 0.4, -0.4), bodies=bodies)
+    target = x + np.array([0.0, 0.01, 0.0])
+    actions = np.stack([np.tile([40.0, -40.0], (env_steps, 1)), np.tile([10.0, -70.0], (env_steps, 1))])     # (B, steps, 2)
+
+    def build(nb):
+        ms = [Mesh(sdf=dict(sdf=tab["sdf"], normal=tab["normal"], position=(tab["lower"], tab["upper"]), dx=tab["dx"]), cfg=dict(friction=0.3),
+                   max_timesteps=max_steps) for _ in range(2)]
+        prims = Primitives(primitives=ms, max_timesteps=max_steps)
+        sim = MPMSimulator(sim_cfg(n, n_grid=n_grid, max_steps=max_steps, dt=dt), prims, env_dt=dt * substeps, n_batch=nb)
+        return sim, prims
+
+    # batched
+    sim, prims = build(B)
+    env = BatchedTaichiEnv(sim, prims, lambda b, views: RigidSimulator(rcfg, views, substeps=substeps, env_dt=dt * substeps), x)
+    sim.clear_all_gradients()
+    for k in range(env_steps):
+        env.step(actions[:, k])
+    f_end = env_steps * substeps
+    xs = sim.get_x(f_end).reshape(B, n, 3)
+    sim.add_x_grad(f_end, (xs - target).reshape(B * n, 3))
+    gb = env.backward()                                                     # (B, steps, 2)
+    rb = [r.states[-1].copy() for r in env.rigid]
+
+    # one env per rollout
+    for b in range(B):
+        s1, p1 = build(1)
+        rigid = RigidSimulator(rcfg, p1, substeps=substeps, env_dt=dt * substeps)
+        e1 = TaichiEnv(s1, p1, rigid, x, loss=PointwiseLoss(s1, target))
+        s1.clear_all_gradients()
+        for k in range(env_steps):
+            e1.step(actions[b, k])
+        e1.compute_loss(f_end)
+        g1 = e1.backward()
+        assert rel_l2(xs[b], s1.get_x(f_end)) <= 1e-6
+        assert rel_l2(rb[b], rigid.states[-1]) <= 1e-6
+        assert np.abs(g1).max() > 0 and rel_l2(gb[b], g1) <= 1e-3, (gb[b], g1)
