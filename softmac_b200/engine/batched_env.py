@@ -107,13 +107,77 @@ class CouplingBuffer:
         return np.zeros(13)
 
 
+class LinearBatchedRigid:
+    """All B rigid stand-ins advanced at once with numpy matmuls.  Valid when every joint is fixed or prismatic: then
+    ``RigidSimulator._advance`` and ``_pose`` are affine in (state, action, wrench), so their exact Jacobians are constant
+    matrices, taken once from a prototype by finite differences.  Same coupling semantics as B separate bridges
+    (wrench averaged over the env step and truncated to fp32, pose handed over in fp32, rigid_simulator.py:92-93,185)."""
+
+    def __init__(self, proto, B):
+        assert all(b.joint in ("fixed", "prismatic") for b in proto.bodies), "LinearBatchedRigid needs fixed / prismatic joints"
+        self.p, self.B, self.P = proto, B, proto.n_primitive
+        self.substeps, self.sd, self.ad = proto.substeps, proto.state_dim, proto.action_dim
+        s0, a0, w0 = np.zeros(self.sd), np.zeros(self.ad), np.zeros(6 * self.P)
+        self.c = proto._advance(s0, a0, w0)
+        self.As = proto._jac(lambda x: proto._advance(x, a0, w0), s0).T            # s' = s As + a Aa + w Aw + c
+        self.Aa = proto._jac(lambda x: proto._advance(s0, x, w0), a0).T if self.ad else np.zeros((0, self.sd))
+        self.Aw = proto._jac(lambda x: proto._advance(s0, a0, x), w0).T
+        self.pose0 = np.stack([proto._pose(s0, i) for i in range(self.P)])            # (P, 13)
+        self.M = np.stack([proto._jac(lambda x, i=i: proto._pose(x, i), s0).T for i in range(self.P)])   # (P, sd, 13)
+        self.enable = np.array([proto.primitives[i].enable_external_force for i in range(self.P)], dtype=bool)
+        self.fp32 = proto.fp32_bridge
+        self.reset()
+
+    def reset(self):
+        self.states = [np.tile(self.p.init_state, (self.B, 1))]
+        self.masks = []
+        self.state_grad = np.zeros((self.B, self.sd))
+
+    def poses(self):
+        s = self.states[-1]
+        out = np.einsum("bs,psk->bpk", s, self.M) + self.pose0[None]
+        return out.astype(np.float32).astype(np.float64) if self.fp32 else out
+
+    def step(self, actions, ext_f):
+        """actions (B, ad); ext_f (B, P, 6) accumulated over the env step.  Returns the (B, P, 13) poses of the next step."""
+        w = np.asarray(ext_f, dtype=np.float64)
+        if self.fp32:
+            w = w.astype(np.float32).astype(np.float64)
+        w = w / self.substeps
+        mask = ((np.abs(w) > 1e-10).any(axis=2) & self.enable[None]).astype(np.float64)          # rigid_simulator.py:96
+        w = w * mask[:, :, None]
+        self.masks.append(mask)
+        a = np.zeros((self.B, self.ad)) if actions is None else np.asarray(actions, dtype=np.float64).reshape(self.B, self.ad)
+        self.states.append(self.states[-1] @ self.As + a @ self.Aa + w.reshape(self.B, -1) @ self.Aw + self.c[None])
+        return self.poses()
+
+    def step_grad(self, k, pose_grads):
+        """pose_grads (B, P, 13): primitive-state adjoints summed over the frames of env step k+1.
+        Returns (action grads (B, ad), wrench adjoints (B, P, 6))."""
+        self.state_grad = self.state_grad + np.einsum("bpk,psk->bs", pose_grads, self.M) * self.p.ext_grad_scale
+        ag = self.state_grad @ self.Aa.T
+        gw = (self.state_grad @ self.Aw.T).reshape(self.B, self.P, 6) * self.masks[k][:, :, None] / self.substeps
+        self.state_grad = self.state_grad @ self.As.T
+        return ag, gw
+
+    def finish(self, pose_grads0):
+        self.state_grad = self.state_grad + np.einsum("bpk,psk->bs", pose_grads0, self.M)
+
+
 class BatchedTaichiEnv:
-    def __init__(self, simulator, primitives, make_rigid, init_particles, loss=None):
-        """make_rigid(b, views) -> a rigid simulator (RigidSimulator surface) for rollout b talking to `views`."""
+    def __init__(self, simulator, primitives, make_rigid, init_particles, loss=None, vectorize=True):
+        """make_rigid(b, views) -> a rigid simulator (RigidSimulator surface) for rollout b talking to `views`.
+        vectorize: when every joint of the stand-in is fixed / prismatic, advance all rollouts with LinearBatchedRigid
+        (numpy matmuls) instead of B Python bridges."""
         self.simulator, self.primitives, self.loss = simulator, primitives, loss
         self.B, self.substeps = simulator.n_batch, simulator.substeps
         self.buf = CouplingBuffer(simulator, primitives)
-        self.rigid = [make_rigid(b, self.buf.views[b]) for b in range(self.B)]
+        self.rigid = [make_rigid(0, self.buf.views[0])]
+        self.vec = None
+        if vectorize and hasattr(self.rigid[0], "bodies") and all(b.joint in ("fixed", "prismatic") for b in self.rigid[0].bodies):
+            self.vec = LinearBatchedRigid(self.rigid[0], self.B)
+        else:
+            self.rigid += [make_rigid(b, self.buf.views[b]) for b in range(1, self.B)]
         self.init_particles = np.asarray(init_particles, dtype=np.float64)
         self.action_list = []
         primitives.initialize()
@@ -123,9 +187,13 @@ class BatchedTaichiEnv:
     def reset(self):
         self.primitives.reset()
         self.simulator.reset(self.init_particles)
-        for r in self.rigid:
-            r.reset()                      # writes the initial pose of frames [0, substeps) into the buffer
-        self.buf.push_states()
+        if self.vec:
+            self.vec.reset()
+            self._push_poses(self.vec.poses(), 0, self.substeps)
+        else:
+            for r in self.rigid:
+                r.reset()                  # writes the initial pose of frames [0, substeps) into the buffer
+            self.buf.push_states()
         check(lib().smx_clear_ext_f_all(self.simulator._h))
         self.action_list = []
 
@@ -137,9 +205,19 @@ class BatchedTaichiEnv:
         self.action_list.append(np.asarray(actions, dtype=np.float64))
         sim.step(start, self.substeps)
         self.buf.pull_ext_f()
+        k = start // self.substeps
+        if self.vec:
+            self._push_poses(self.vec.step(actions, self.buf.ext_f), (k + 1) * self.substeps, (k + 2) * self.substeps)
+            return
         for b, r in enumerate(self.rigid):
-            r.step(start // self.substeps, actions[b])
+            r.step(k, actions[b])
         self.buf.push_states()
+
+    def _push_poses(self, poses, f0, f1):
+        f1 = min(f1, self.simulator.max_steps)
+        if f0 < f1:
+            self.buf.states[:] = poses
+            check(lib().smx_set_primitive_states_all(self.simulator._h, int(f0), int(f1), d_ptr(self.buf.states)))
 
     def step_grad(self, actions):
         sim = self.simulator
@@ -148,6 +226,12 @@ class BatchedTaichiEnv:
         k = sim.cur // self.substeps
         # rigid.step_grad(k) pulls the primitive-state adjoints of env step k+1 (frames [(k+1) sub, (k+2) sub))
         self.buf.pull_state_grads((k + 1) * self.substeps, (k + 2) * self.substeps)
+        if self.vec:
+            ag, gw = self.vec.step_grad(k, self.buf.grads)
+            self.buf.ext_f_grad[:] = gw
+            self.buf.push_ext_f_grads()
+            sim.step_grad(start, self.substeps)
+            return ag
         grads = []
         for b, r in enumerate(self.rigid):
             ag, ext_list = r.step_grad(k, actions[b])
@@ -159,6 +243,8 @@ class BatchedTaichiEnv:
         return np.stack(grads)
 
     def backward(self):
+        if self.vec:
+            self.vec.state_grad = np.zeros((self.B, self.vec.sd))
         for r in self.rigid:
             r.state_grad = np.zeros(r.state_dim)
         total = self.simulator.cur // self.substeps
@@ -166,6 +252,13 @@ class BatchedTaichiEnv:
         for s in range(total - 1, -1, -1):
             out = [self.step_grad(self.action_list[s])] + out
         self.buf.pull_state_grads(0, self.substeps)
-        for r in self.rigid:
-            r.state_grad = r.state_grad + r.get_ext_state_grad(0)
+        if self.vec:
+            self.vec.finish(self.buf.grads)
+        else:
+            for r in self.rigid:
+                r.state_grad = r.state_grad + r.get_ext_state_grad(0)
         return np.stack(out, axis=1)            # (B, steps, action_dim)
+
+    def rigid_states(self):
+        """(B, state_dim) current rigid states."""
+        return self.vec.states[-1].copy() if self.vec else np.stack([r.states[-1] for r in self.rigid])

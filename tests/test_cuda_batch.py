@@ -125,7 +125,8 @@ def test_batched_env_matches_single_rollout_envs():
     xs = sim.get_x(f_end).reshape(B, n, 3)
     sim.add_x_grad(f_end, (xs - target).reshape(B * n, 3))
     gb = env.backward()                                                     # (B, steps, 2)
-    rb = [r.states[-1].copy() for r in env.rigid]
+    rb = env.rigid_states()
+    assert env.vec is not None                                              # prismatic joints: vectorised stand-in
 
     # one env per rollout
     for b in range(B):
