@@ -133,6 +133,7 @@ def run_reference(args, rank, world):
         return
     import scenes
     from oracle import mpm_oracle as mo
+    mo.set_num_threads(os.cpu_count())          # all host threads (torchrun exports OMP_NUM_THREADS=1)
     S = args.cpu_sample_substeps
     sim = mo.OracleSim(args.n, n_grid=args.n_grid, max_steps=S + 1, dt=DT, E=3e3, nu=0.2, gravity=(0., -9.8, 0.),
                        ground_friction=20., material_model=0, ptype=0, collision_type=2, substeps=5)
@@ -181,6 +182,7 @@ def config_dict(args, S):
 def cpu_baseline(args):
     import scenes  # noqa: F401
     from oracle import mpm_oracle as mo
+    mo.set_num_threads(os.cpu_count())
     S = args.cpu_sample_substeps
     sim = mo.OracleSim(args.n, n_grid=args.n_grid, max_steps=S + 1, dt=DT, E=3e3, nu=0.2, gravity=(0., -9.8, 0.),
                        ground_friction=20., material_model=0, ptype=0, collision_type=2, substeps=5)

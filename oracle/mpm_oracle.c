@@ -1508,6 +1508,14 @@ void orc_get_grid(const orc_sim *s, double *gvin, double *gm, double *gvout) {
     if (gm) memcpy(gm, s->gm, G*8);
     if (gvout) memcpy(gvout, s->gvout, G*24);
 }
+/* torchrun exports OMP_NUM_THREADS=1; the timed CPU baseline asks for its thread count explicitly */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
 int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

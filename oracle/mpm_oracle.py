@@ -66,6 +66,7 @@ def lib():
         L.orc_prim_normal.argtypes = [vp, C.c_int, C.c_int, dp, dp]
         L.orc_get_grid.argtypes = [vp, dp, dp, dp]
         L.orc_num_threads.restype = C.c_int
+        L.orc_set_num_threads.argtypes = [C.c_int]
     return _lib
 
 
@@ -202,3 +203,7 @@ def backward_svd(gu, gs, gv, u, s, v):
 
 def num_threads():
     return lib().orc_num_threads()
+
+
+def set_num_threads(n):
+    lib().orc_set_num_threads(int(n))

@@ -22,7 +22,24 @@
 #include <signal.h>
 #include <unistd.h>
 
+#include <thread>
+#include <omp.h>
+
 using namespace smx;
+
+// Threads for the host-side f64 <-> f32 conversion loops.  Not taken from OMP_NUM_THREADS (torchrun exports
+// OMP_NUM_THREADS=1 to every rank): SMX_HOST_THREADS, else hardware threads / LOCAL_WORLD_SIZE, capped at 16.
+__attribute__((used)) static int smx_host_threads() {
+    static int n = 0;
+    if (n) return n;
+    const char* e = getenv("SMX_HOST_THREADS");
+    if (e && atoi(e) > 0) return n = atoi(e);
+    int hw = (int)std::thread::hardware_concurrency();
+    const char* lw = getenv("LOCAL_WORLD_SIZE");
+    int ranks = (lw && atoi(lw) > 0) ? atoi(lw) : 1;
+    n = std::max(1, std::min(16, hw / ranks));
+    return n;
+}
 
 // SMX_BACKTRACE=1: print a native backtrace on SIGSEGV (debug aid; resolve offsets with addr2line -e <lib>)
 static void smx_segv_handler(int sig) {
@@ -362,7 +379,7 @@ static int upload_cols(smx_sim* s, int f, const double* host, int ncomp, int c0)
     CK(cudaStreamSynchronize(s->stream));       // staging buffer reuse
     {
         float* dst = s->stage_host;
-        #pragma omp parallel for schedule(static)
+        #pragma omp parallel for schedule(static) num_threads(smx_host_threads())
         for (long long i = 0; i < (long long)cnt; i++) dst[i] = (float)host[i];
     }
     CK(cudaMemcpyAsync(s->stage_dev, s->stage_host, cnt * sizeof(float), cudaMemcpyHostToDevice, s->stream));
@@ -379,7 +396,7 @@ static int download_cols(smx_sim* s, const float* frame, const uint32_t* perm, d
     CK(cudaStreamSynchronize(s->stream));
     {
         const float* src = s->stage_host;
-        #pragma omp parallel for schedule(static)
+        #pragma omp parallel for schedule(static) num_threads(smx_host_threads())
         for (long long i = 0; i < (long long)cnt; i++) host[i] = (double)src[i];
     }
     return SMX_OK;
@@ -560,7 +577,7 @@ int smx_reset(smx_sim* s, const double* state, int32_t ncols) {
     Order root; s->order_of[0] = new_order_id(s, root);
     {
         float* stage = s->stage_host;
-        #pragma omp parallel for schedule(static)
+        #pragma omp parallel for schedule(static) num_threads(smx_host_threads())
         for (long long p = 0; p < (long long)n; p++) {
             float* r = stage + 24 * p;
             if (ncols == 24) for (int c = 0; c < 24; c++) r[c] = (float)state[24 * p + c];
@@ -965,7 +982,7 @@ static int add_seed(smx_sim* s, int f, const double* g, int ncols) {
     size_t cnt = (size_t)n * ncols;
     {
         float* dst = s->stage_host;
-        #pragma omp parallel for schedule(static)
+        #pragma omp parallel for schedule(static) num_threads(smx_host_threads())
         for (long long i = 0; i < (long long)cnt; i++) dst[i] = (float)g[i];
     }
     CK(cudaMemcpyAsync(s->stage_dev, s->stage_host, cnt * sizeof(float), cudaMemcpyHostToDevice, s->stream));
