@@ -157,6 +157,23 @@ int smx_substep(smx_sim* sim, int32_t s);
 /* MPMSimulator.substep_grad(s) (mpm_simulator.py:339-378): consumes the adjoint of frame s+1 (+ its seeds),
  * produces the adjoint of frame s (+ its seeds), accumulates primitive-state and action adjoints */
 int smx_substep_grad(smx_sim* sim, int32_t s);
+/* The two halves of a substep, for callers that exchange grid halos between them (spatial slab decomposition):
+ * begin = clear + P2G;  end = grid update, contact, G2P.  smx_substep == begin followed by end.  Likewise for the
+ * adjoint: begin = adjoint set-up, grid restore, G2P adjoint (scatter into gg_out);  end = grid adjoint + P2G adjoint. */
+int smx_substep_begin(smx_sim* sim, int32_t s);
+int smx_substep_end(smx_sim* sim, int32_t s);
+int smx_substep_grad_begin(smx_sim* sim, int32_t s);
+int smx_substep_grad_end(smx_sim* sim, int32_t s);
+/* Declares this handle one rank of an x-slab decomposition: it owns the x-block columns [xb_lo, xb_hi) (4 nodes per
+ * column) and has neighbours on the flagged sides.  The halo columns {xb_lo-1, xb_lo} / {xb_hi-1, xb_hi} are kept active
+ * every substep; the caller sums them with the neighbour's copies between begin and end (g_in forward, gg_out backward).
+ * Call before smx_reset.  Particle migration between ranks is not implemented: particles whose stencil leaves the own
+ * slab + halo are counted in counters[1]. */
+int smx_set_slab(smx_sim* sim, int32_t xb_lo, int32_t xb_hi, int32_t has_lo_neighbour, int32_t has_hi_neighbour);
+/* device pointer / element count of a grid array: 0 g_in, 1 g_out, 2 g_mix, 3 gg_out, 4 gg_mix (float4 per node,
+ * block-major; x-block column c is the contiguous range [c*nb^2*64, (c+1)*nb^2*64), nb = n_grid/4) */
+int smx_grid_dev(smx_sim* sim, int32_t which, void** ptr_dev, int64_t* n_float4);
+int smx_stream(smx_sim* sim, void** stream);
 /* `count` substeps in one call: s0, s0+1, ... (TaichiEnv.step inner loop, taichi_env.py:101-102) */
 int smx_step(smx_sim* sim, int32_t s0, int32_t count);
 /* adjoint of substeps s1-1, s1-2, ..., s1-count (TaichiEnv.step_grad inner loop, taichi_env.py:128-131) */

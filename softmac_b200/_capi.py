@@ -84,6 +84,13 @@ _SIGS = {
     "smx_get_action_grad": [vp, dp],
     "smx_substep": [vp, C.c_int32],
     "smx_substep_grad": [vp, C.c_int32],
+    "smx_substep_begin": [vp, C.c_int32],
+    "smx_substep_end": [vp, C.c_int32],
+    "smx_substep_grad_begin": [vp, C.c_int32],
+    "smx_substep_grad_end": [vp, C.c_int32],
+    "smx_set_slab": [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32],
+    "smx_grid_dev": [vp, C.c_int32, C.POINTER(vp), C.POINTER(C.c_int64)],
+    "smx_stream": [vp, C.POINTER(vp)],
     "smx_step": [vp, C.c_int32, C.c_int32],
     "smx_step_grad": [vp, C.c_int32, C.c_int32],
     "smx_add_state_grad": [vp, C.c_int32, dp],

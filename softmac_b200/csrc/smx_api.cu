@@ -91,6 +91,9 @@ struct smx_sim {
     bool own_stream = false;
     int sm_count = 148;
     int B = 1;                          // batched independent rollouts
+    // spatial slab decomposition (one rank of several): owned x-block columns [slab_lo, slab_hi), neighbours present?
+    bool slab = false, halo_lo = false, halo_hi = false;
+    int slab_lo = 0, slab_hi = 0;
     bool dense = true;
     // particle frames
     float* pool = nullptr;
@@ -119,6 +122,7 @@ struct smx_sim {
     // adjoint ping-pong
     float *adj_cur = nullptr, *adj_nxt = nullptr;
     int adj_frame = -1, adj_order = -1;
+    int grad_pending = -1;
     struct Seed { float* dev = nullptr; int ncols = 24; };
     std::map<int, Seed> seeds;          // frame -> device (n, 3 | 24) fp32 AoS in particle-id order
     // primitives
@@ -223,6 +227,11 @@ static int build_blocks(smx_sim* s, Order& o, const float* frame, const uint32_t
         if (keys_sorted) k_mark_blocks_sorted<<<nblk(s->P.n, 256), 256, 0, s->stream>>>(s->P, keys_sorted, 2, o.flags);
         else k_mark_blocks<<<nblk(s->P.n, 256), 256, 0, s->stream>>>(s->P, frame, 2, o.flags);
         CKL(s);
+    }
+    if (s->slab) {
+        int nb = s->P.nb;
+        if (s->halo_lo) for (int c = s->slab_lo - 1; c <= s->slab_lo; c++) { k_mark_column<<<nblk(nb * nb, 256), 256, 0, s->stream>>>(o.flags, nb, c); CKL(s); }
+        if (s->halo_hi) for (int c = s->slab_hi - 1; c <= s->slab_hi; c++) { k_mark_column<<<nblk(nb * nb, 256), 256, 0, s->stream>>>(o.flags, nb, c); CKL(s); }
     }
     k_compact_blocks<<<nblk(nb3, 256), 256, 0, s->stream>>>(nb3, o.flags, o.blocks, o.nblocks); CKL(s);
     return SMX_OK;
@@ -331,16 +340,18 @@ static int ensure_ckpt(smx_sim* s, int f) {
 }
 
 // P2G + grid update + forecast contact of substep f (everything before G2P); shared by forward and adjoint
-static int forward_to_grid(smx_sim* s, int f, bool write_F, bool accumulate) {
+static int forward_p2g(smx_sim* s, int f, bool write_F, bool accumulate) {
     const Params& P = s->P;
     Order& o = s->orders[s->order_of[f]];
     const float* fin = s->frame_ptr(f);
     float* fout = write_F ? s->frame_ptr(f + 1) : nullptr;
     PrimSet ps = s->primset();
-    bool contact = s->has_contact();
     const int* cslot = nullptr;
     TRY(ctrl_slots(s, s->order_of[f], &cslot));
     TRY(clear_grids(s, o, s->g_in, nullptr, nullptr));
+    if (s->slab && P.n > 0) {
+        k_check_slab<<<nblk(P.n, 256), 256, 0, s->stream>>>(P, fin, s->halo_lo ? s->slab_lo - 1 : 0, s->halo_hi ? s->slab_hi : P.nb - 1, s->counters); CKL(s);
+    }
     if (P.n > 0) {
         TRY(dispatch_mat(P.material, P.ptype, [&](auto mat) {
             if (s->cfg.flags & SMX_FLAG_DIRECT_RED) k_p2g<decltype(mat)::value, false><<<nblk(P.n, SMX_TPB_SC), SMX_TPB_SC, 0, s->stream>>>(P, ps, f, fin, fout, s->g_in, cslot, s->action, accumulate ? 1 : 0);
@@ -351,13 +362,25 @@ static int forward_to_grid(smx_sim* s, int f, bool write_F, bool accumulate) {
     if (write_F && s->cfg.rigid_velocity_control && !s->prims.empty()) {
         k_forward_kinematics<<<nblk((long long)s->prims.size() * s->B, 64), 64, 0, s->stream>>>(s->pstate, s->cfg.max_steps, (int)s->prims.size(), s->B, f, P.dt); CKL(s);
     }
+    return SMX_OK;
+}
+static int forward_grid(smx_sim* s, int f, bool accumulate) {
+    const Params& P = s->P;
+    Order& o = s->orders[s->order_of[f]];
+    PrimSet ps = s->primset();
+    bool contact = s->has_contact();
     k_grid_op<<<grid_blocks_launch(s), 256, 0, s->stream>>>(P, ps, f, s->dense ? nullptr : o.blocks, o.nblocks, s->g_in, s->g_out, contact ? s->g_mix : nullptr, accumulate ? 1 : 0);
     CKLN(s, "k_grid_op");
     if (contact && P.n > 0) {
         float life = 1.0f / (float)(P.substeps - f % P.substeps);      // mpm_simulator.py:425 (f32 in the reference too)
-        k_contact<<<nblk(P.n, SMX_TPB), SMX_TPB, 0, s->stream>>>(P, ps, f, life, fin, s->g_mix, s->g_out, accumulate ? 1 : 0); CKLN(s, "k_contact");
+        k_contact<<<nblk(P.n, SMX_TPB), SMX_TPB, 0, s->stream>>>(P, ps, f, life, s->frame_ptr(f), s->g_mix, s->g_out, accumulate ? 1 : 0); CKLN(s, "k_contact");
     }
     return SMX_OK;
+}
+// P2G + grid update + forecast contact of substep f (everything before G2P); shared by forward and adjoint
+static int forward_to_grid(smx_sim* s, int f, bool write_F, bool accumulate) {
+    TRY(forward_p2g(s, f, write_F, accumulate));
+    return forward_grid(s, f, accumulate);
 }
 
 static int check_frame(smx_sim* s, int f, const char* what) {
@@ -874,15 +897,23 @@ int smx_get_action_grad(smx_sim* s, double* out) {
 }
 
 // ---- the hot path -------------------------------------------------------------------------------
-int smx_substep(smx_sim* s, int32_t f) {
+// substep = begin (clear + P2G) ; [slab mode: halo exchange of g_in by the caller] ; end (grid update, contact, G2P)
+int smx_substep_begin(smx_sim* s, int32_t f) {
     TRY(check_frame(s, f, "smx_substep"));
     if (f + 1 >= s->cfg.max_steps) return fail(SMX_ERR_RANGE, "smx_substep: substep %d would write frame %d >= max_steps %d", f, f + 1, s->cfg.max_steps);
     if (s->order_of[f] < 0) return fail(SMX_ERR_STATE, "smx_substep: frame %d has not been written (call smx_reset / smx_set_frame first)", f);
+    if (s->slab && s->has_contact()) return fail(SMX_ERR_STATE, "smx_substep: slab decomposition does not yet exchange the forecast-contact scatter (disable contact or use one GPU)");
     CK(cudaSetDevice(s->cfg.device));
     s->order_of[f + 1] = s->order_of[f]; s->trans_from[f + 1] = -1;
     s->ckpt_order[f] = -1; s->ckpt_order[f + 1] = -1;
     if (s->ckpt_dirty) TRY(ensure_ckpt(s, f));
-    TRY(forward_to_grid(s, f, true, true));
+    return forward_p2g(s, f, true, true);
+}
+int smx_substep_end(smx_sim* s, int32_t f) {
+    TRY(check_frame(s, f, "smx_substep"));
+    if (f + 1 >= s->cfg.max_steps || s->order_of[f] < 0 || s->order_of[f + 1] != s->order_of[f]) return fail(SMX_ERR_STATE, "smx_substep_end: smx_substep_begin(%d) has not been called", f);
+    CK(cudaSetDevice(s->cfg.device));
+    TRY(forward_grid(s, f, true));
     if (s->ckpt && (!s->has_contact() || s->ckpt_narr == 3)) {
         Order& o = s->orders[s->order_of[f]];
         bool contact = s->has_contact();
@@ -895,8 +926,14 @@ int smx_substep(smx_sim* s, int32_t f) {
     if (s->cfg.sort_every > 0 && (f + 1) % s->cfg.sort_every == 0 && !(s->cfg.flags & SMX_FLAG_NO_SORT)) TRY(resort(s, f + 1, true));
     return SMX_OK;
 }
+int smx_substep(smx_sim* s, int32_t f) {
+    TRY(smx_substep_begin(s, f));
+    return smx_substep_end(s, f);
+}
 
-int smx_substep_grad(smx_sim* s, int32_t f) {
+// adjoint substep = begin (adjoint set-up, grid restore, G2P adjoint, contact adjoint) ; [slab mode: halo exchange of
+// gg_out by the caller] ; end (grid adjoint, P2G adjoint)
+int smx_substep_grad_begin(smx_sim* s, int32_t f) {
     TRY(check_frame(s, f, "smx_substep_grad"));
     if (f + 1 >= s->cfg.max_steps) return fail(SMX_ERR_RANGE, "smx_substep_grad: substep %d outside the stored range", f);
     if (s->order_of[f] < 0 || s->order_of[f + 1] < 0) return fail(SMX_ERR_STATE, "smx_substep_grad: substep %d has not been run forward", f);
@@ -933,6 +970,7 @@ int smx_substep_grad(smx_sim* s, int32_t f) {
                                                                  s->g_in, s->g_out, contact ? s->g_mix : nullptr, 1, s->counters);
         CKLN(s, "ckpt_restore");
     } else {
+        if (s->slab) return fail(SMX_ERR_STATE, "smx_substep_grad: slab decomposition needs the grid checkpoint of substep %d (run it forward in this handle; do not set SMX_FLAG_NO_GRID_CKPT)", f);
         TRY(forward_to_grid(s, f, false, false));
     }
     TRY(clear_grids(s, ord, s->gg_out, contact ? s->gg_mix : nullptr, nullptr));
@@ -946,6 +984,20 @@ int smx_substep_grad(smx_sim* s, int32_t f) {
         float life = 1.0f / (float)(P.substeps - f % P.substeps);
         k_contact_grad<<<nblk(P.n, SMX_TPB), SMX_TPB, 0, s->stream>>>(P, ps, f, life, fin, s->adj_nxt, s->g_mix, s->gg_out, s->gg_mix); CKLN(s, "k_contact_grad");
     }
+    s->grad_pending = f;
+    return SMX_OK;
+}
+int smx_substep_grad_end(smx_sim* s, int32_t f) {
+    TRY(check_frame(s, f, "smx_substep_grad"));
+    if (s->grad_pending != f) return fail(SMX_ERR_STATE, "smx_substep_grad_end: smx_substep_grad_begin(%d) has not been called", f);
+    s->grad_pending = -1;
+    CK(cudaSetDevice(s->cfg.device));
+    const Params& P = s->P;
+    int o = s->order_of[f];
+    Order& ord = s->orders[o];
+    bool contact = s->has_contact();
+    PrimSet ps = s->primset();
+    const float* fin = s->frame_ptr(f);
     k_grid_grad<<<grid_blocks_launch(s), 256, 0, s->stream>>>(P, ps, f, s->dense ? nullptr : ord.blocks, ord.nblocks, s->g_in, s->gg_out, contact ? s->gg_mix : nullptr); CKLN(s, "k_grid_grad");
     if (s->cfg.rigid_velocity_control && !s->prims.empty()) {
         k_forward_kinematics_grad<<<nblk((long long)s->prims.size() * s->B, 64), 64, 0, s->stream>>>(s->pstate, s->pgrad, s->cfg.max_steps, (int)s->prims.size(), s->B, f, P.dt); CKL(s);
@@ -961,6 +1013,36 @@ int smx_substep_grad(smx_sim* s, int32_t f) {
     std::swap(s->adj_cur, s->adj_nxt);
     s->adj_frame = f; s->adj_order = o;
     TRY(apply_seed(s, f, s->adj_cur, o));
+    return SMX_OK;
+}
+int smx_substep_grad(smx_sim* s, int32_t f) {
+    TRY(smx_substep_grad_begin(s, f));
+    return smx_substep_grad_end(s, f);
+}
+
+// ---- spatial slab decomposition ----------------------------------------------------------------------------------------
+int smx_set_slab(smx_sim* s, int32_t xb_lo, int32_t xb_hi, int32_t has_lo_neighbour, int32_t has_hi_neighbour) {
+    if (!s) return fail(SMX_ERR_ARG, "smx_set_slab: null simulator");
+    int nb = s->P.nb;
+    if (xb_lo < 0 || xb_hi > nb || xb_lo >= xb_hi) return fail(SMX_ERR_RANGE, "smx_set_slab: block columns [%d, %d) outside [0, %d)", xb_lo, xb_hi, nb);
+    if ((has_lo_neighbour && xb_lo < 1) || (has_hi_neighbour && xb_hi > nb - 1)) return fail(SMX_ERR_RANGE, "smx_set_slab: no room for a halo column");
+    if (s->B != 1) return fail(SMX_ERR_STATE, "smx_set_slab: not available for batched handles");
+    if (s->dense) return fail(SMX_ERR_STATE, "smx_set_slab: needs active-block lists (sort_every > 0, no SMX_FLAG_DENSE_GRID / SMX_FLAG_NO_SORT)");
+    s->slab = true; s->slab_lo = xb_lo; s->slab_hi = xb_hi; s->halo_lo = has_lo_neighbour != 0; s->halo_hi = has_hi_neighbour != 0;
+    return SMX_OK;
+}
+// device pointer and size of a grid array: 0 g_in, 1 g_out, 2 g_mix, 3 gg_out, 4 gg_mix (float4 per node, block-major:
+// x-block column c is the contiguous element range [c * nb^2 * 64, (c+1) * nb^2 * 64))
+int smx_grid_dev(smx_sim* s, int32_t which, void** ptr, int64_t* n_float4) {
+    if (!s || !ptr || !n_float4) return fail(SMX_ERR_ARG, "smx_grid_dev: null argument");
+    float4* t[5] = {s->g_in, s->g_out, s->g_mix, s->gg_out, s->gg_mix};
+    if (which < 0 || which > 4) return fail(SMX_ERR_RANGE, "smx_grid_dev: which in [0, 5)");
+    *ptr = t[which]; *n_float4 = (int64_t)s->G;
+    return SMX_OK;
+}
+int smx_stream(smx_sim* s, void** stream) {
+    if (!s || !stream) return fail(SMX_ERR_ARG, "smx_stream: null argument");
+    *stream = (void*)s->stream;
     return SMX_OK;
 }
 

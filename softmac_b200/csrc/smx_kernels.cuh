@@ -1003,6 +1003,20 @@ __global__ void __launch_bounds__(256) k_ckpt_copy(const uint32_t* __restrict__ 
         }
     }
 }
+// slab decomposition: force every block of x-block column `col` active (the halo columns exchanged with a neighbour
+// must be cleared / updated every substep even where no local particle reaches them)
+__global__ void k_mark_column(uint32_t* __restrict__ flags, int nb, int col) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nb * nb) flags[(size_t)col * nb * nb + t] = 1u;
+}
+// slab decomposition: a local particle whose stencil leaves [lo_col, hi_col] (own slab + one halo column per side) would
+// scatter into nodes that are not exchanged: counted in counters[1]
+__global__ void k_check_slab(Params P, const float* __restrict__ fr, int lo_col, int hi_col, unsigned long long* counters) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= P.n) return;
+    int b0 = clampi((int)(fr[j] * P.inv_dx - 0.5f), 0, P.ng - 3);
+    if ((b0 >> 2) < lo_col || ((b0 + 2) >> 2) > hi_col) atomicAdd(counters + 1, 1ull);
+}
 __global__ void k_compact_blocks(int nblk, const uint32_t* __restrict__ flags, uint32_t* __restrict__ list, int* __restrict__ count) {
     // order of the list does not matter (each entry is processed independently); one atomic per set flag
     int b = blockIdx.x * blockDim.x + threadIdx.x;

@@ -1,0 +1,212 @@
+"""Spatial slab decomposition of one large scene across the GPUs of a box (BASELINE config 5).
+
+The grid is cut along x into slabs of whole 4-node block columns; every rank owns the particles whose base cell lies in
+its slab and runs the ordinary substep kernels on them, on a grid array with the GLOBAL index space (only the active
+blocks of the slab are ever touched).  The block-major grid layout makes an x-block column one contiguous range of
+nb^2 KB, so the halo of a boundary -- the last column of the left rank and the first column of the right rank -- is a
+single contiguous 2-column range that is exchanged with one send/recv pair and summed on both sides:
+
+    forward  : begin (clear + P2G)       -> sum g_in halo    -> end (grid update, G2P)
+    adjoint  : begin (restore, G2P adj)  -> sum gg_out halo  -> end (grid adjoint, P2G adj)
+
+Both ranks then hold identical, complete values on the shared columns (a + b == b + a) and update them redundantly, so
+no second (broadcast) exchange is needed.  Transport: ``torch.distributed`` P2P (NCCL over NVLink) with one process per
+GPU, or plain tensor adds for several ranks emulated in one process (tests on a single GPU).
+
+Not implemented in round 1: particle migration between ranks (ownership is fixed at reset; a particle may drift up
+to two cells out of its slab before the counters flag it), and the exchange of the forecast-contact scatter (slab mode
+refuses contact-enabled primitives with collision_type 2).
+"""
+import ctypes as C
+
+import numpy as np
+
+from ._capi import lib, check, vp
+
+
+class _DevArray:
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f4", "data": (int(ptr), False), "version": 3, "strides": None}
+
+
+def choose_bounds(x, n_ranks, n_grid):
+    """Block-column boundaries [b_0 = 0, ..., b_R = nb] with ~equal particle counts and >= 2 columns per slab."""
+    nb = n_grid // 4
+    base = np.clip((np.asarray(x, dtype=np.float32) * np.float32(n_grid) - np.float32(0.5)).astype(np.int32), 0, n_grid - 3)
+    hist = np.bincount(base >> 2, minlength=nb)
+    cum = np.concatenate([[0], np.cumsum(hist)])
+    bounds = [0]
+    for r in range(1, n_ranks):
+        b = int(np.searchsorted(cum, cum[-1] * r / n_ranks))
+        b = max(b, bounds[-1] + 2)
+        bounds.append(b)
+    bounds.append(nb)
+    for r in range(n_ranks - 1, 0, -1):         # keep >= 2 columns at the high end too
+        bounds[r] = min(bounds[r], bounds[r + 1] - 2)
+    assert all(bounds[r + 1] - bounds[r] >= 2 for r in range(n_ranks)), "grid too small for this many slabs"
+    return bounds
+
+
+class SlabRank:
+    """One rank: a simulator over the particles of its slab."""
+
+    def __init__(self, cfg, rank, bounds, state, device=0, use_torch_stream=True, **sim_kw):
+        import copy
+        import torch
+        from .engine.mpm_simulator import MPMSimulator
+        self.rank, self.n_ranks, self.bounds = rank, len(bounds) - 1, list(bounds)
+        self.lo, self.hi = bounds[rank], bounds[rank + 1]
+        n_grid = int(128 * cfg.quality * 0.5)
+        self.nb = n_grid // 4
+        st = np.asarray(state, dtype=np.float64)
+        base = np.clip((st[:, 0].astype(np.float32) * np.float32(n_grid) - np.float32(0.5)).astype(np.int32), 0, n_grid - 3) >> 2
+        self.ids = np.nonzero((base >= self.lo) & (base < self.hi))[0]
+        c = copy.deepcopy(cfg)
+        c.n_particles = len(self.ids)
+        self.device = device
+        stream = torch.cuda.current_stream(device).cuda_stream if use_torch_stream else None
+        self.sim = MPMSimulator(c, (), device=device, stream=stream, **sim_kw)
+        check(lib().smx_set_slab(self.sim._h, self.lo, self.hi, int(rank > 0), int(rank < self.n_ranks - 1)))
+        self.sim.reset(st[self.ids] if st.shape[1] == 24 else st[self.ids, :3])
+        self._views = {}
+
+    def halo(self, which, side):
+        """float32 torch view of the 2-column halo range of grid array `which` at the 'lo' or 'hi' boundary."""
+        import torch
+        key = (which, side)
+        if key not in self._views:
+            p, n = vp(), C.c_int64()
+            check(lib().smx_grid_dev(self.sim._h, which, C.byref(p), C.byref(n)))
+            full = torch.as_tensor(_DevArray(p.value, n.value * 4), device=f"cuda:{self.device}")
+            col = self.nb * self.nb * 64 * 4
+            b = self.lo if side == "lo" else self.hi
+            self._views[key] = full[(b - 1) * col:(b + 1) * col]
+        return self._views[key]
+
+    # phases ------------------------------------------------------------------------------------------------------
+    def begin(self, f):
+        check(lib().smx_substep_begin(self.sim._h, int(f)))
+
+    def end(self, f):
+        check(lib().smx_substep_end(self.sim._h, int(f)))
+
+    def grad_begin(self, f):
+        check(lib().smx_substep_grad_begin(self.sim._h, int(f)))
+
+    def grad_end(self, f):
+        check(lib().smx_substep_grad_end(self.sim._h, int(f)))
+
+    def scatter_to_global(self, local, n_global):
+        out = np.zeros((n_global,) + local.shape[1:])
+        out[self.ids] = local
+        return out
+
+
+class SlabCluster:
+    """All ranks emulated in ONE process on one device (tests / single-GPU use): same phases, halos summed directly."""
+
+    def __init__(self, cfg, n_ranks, state, device=0, **sim_kw):
+        n_grid = int(128 * cfg.quality * 0.5)
+        self.n = len(state)
+        self.bounds = choose_bounds(np.asarray(state)[:, 0], n_ranks, n_grid)
+        self.ranks = [SlabRank(cfg, r, self.bounds, state, device=device, **sim_kw) for r in range(n_ranks)]
+
+    def _exchange(self, which):
+        for r in range(len(self.ranks) - 1):
+            a, b = self.ranks[r].halo(which, "hi"), self.ranks[r + 1].halo(which, "lo")
+            t = a + b
+            a.copy_(t); b.copy_(t)
+
+    def substep(self, f):
+        for r in self.ranks:
+            r.begin(f)
+        self._exchange(0)
+        for r in self.ranks:
+            r.end(f)
+
+    def substep_grad(self, f):
+        for r in self.ranks:
+            r.grad_begin(f)
+        self._exchange(3)
+        for r in self.ranks:
+            r.grad_end(f)
+
+    def get_state(self, f):
+        out = np.zeros((self.n, 24))
+        for r in self.ranks:
+            out[r.ids] = r.sim.get_state(f)
+        return out
+
+    def add_x_grad(self, f, g):
+        for r in self.ranks:
+            r.sim.add_x_grad(f, np.asarray(g)[r.ids])
+
+    def get_state_grad(self, f):
+        out = np.zeros((self.n, 24))
+        for r in self.ranks:
+            out[r.ids] = r.sim.get_state_grad(f)
+        return out
+
+    def counters(self):
+        return [r.sim.counters() for r in self.ranks]
+
+
+class DistSlab:
+    """One rank per process (torchrun, NCCL): this process's slab + P2P halo exchange with its x-neighbours."""
+
+    def __init__(self, cfg, state, device=None, **sim_kw):
+        import torch
+        import torch.distributed as dist
+        self.dist = dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.device = torch.cuda.current_device() if device is None else device
+        n_grid = int(128 * cfg.quality * 0.5)
+        self.n = len(state)
+        self.bounds = choose_bounds(np.asarray(state)[:, 0], self.world, n_grid)     # deterministic: same on every rank
+        self.r = SlabRank(cfg, self.rank, self.bounds, state, device=self.device, **sim_kw)
+        self.sim = self.r.sim
+        self._tmp = {}
+
+    def _exchange(self, which):
+        import torch
+        dist, ops, pend = self.dist, [], []
+        for side, peer in (("lo", self.rank - 1), ("hi", self.rank + 1)):
+            if 0 <= peer < self.world:
+                v = self.r.halo(which, side)
+                t = self._tmp.setdefault((which, side), torch.empty_like(v))
+                ops += [dist.P2POp(dist.isend, v, peer), dist.P2POp(dist.irecv, t, peer)]
+                pend.append((v, t))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+            for v, t in pend:
+                v.add_(t)
+
+    def substep(self, f):
+        self.r.begin(f)
+        self._exchange(0)
+        self.r.end(f)
+
+    def substep_grad(self, f):
+        self.r.grad_begin(f)
+        self._exchange(3)
+        self.r.grad_end(f)
+
+    def step(self, s0, count):
+        for f in range(s0, s0 + count):
+            self.substep(f)
+
+    def step_grad(self, s1, count):
+        for f in range(s1 - 1, s1 - 1 - count, -1):
+            self.substep_grad(f)
+
+    def add_x_grad(self, f, g_global):
+        self.sim.add_x_grad(f, np.asarray(g_global)[self.r.ids])
+
+    def gather_state(self, f):
+        """Global (n, 24) state on every rank (all-reduce of the scattered local rows; for tests and read-out)."""
+        import torch
+        out = torch.zeros((self.n, 24), dtype=torch.float64, device=f"cuda:{self.device}")
+        out[torch.as_tensor(self.r.ids, device=out.device)] = torch.as_tensor(self.sim.get_state(f), device=out.device)
+        self.dist.all_reduce(out)
+        return out.cpu().numpy()
