@@ -461,7 +461,8 @@ int smx_create(const smx_config* cfg, smx_sim** out) {
     s->cfg = *cfg;
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, cfg->device));
     s->sm_count = prop.multiProcessorCount;
-    if (cfg->stream) s->stream = (cudaStream_t)cfg->stream; else { CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)); s->own_stream = true; }
+    if (cfg->stream || (cfg->flags & SMX_FLAG_EXTERNAL_STREAM)) s->stream = (cudaStream_t)cfg->stream;   // NULL + flag: the legacy default stream
+    else { CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)); s->own_stream = true; }
     Params& P = s->P;
     int n = cfg->n_particles;
     const int B = std::max(cfg->n_batch, 1);

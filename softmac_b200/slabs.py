@@ -21,7 +21,7 @@ import ctypes as C
 
 import numpy as np
 
-from ._capi import lib, check, vp
+from ._capi import lib, check, vp, SMX_FLAG_EXTERNAL_STREAM
 
 
 class _DevArray:
@@ -64,8 +64,10 @@ class SlabRank:
         c = copy.deepcopy(cfg)
         c.n_particles = len(self.ids)
         self.device = device
+        # run on torch's current stream so that the halo sums / NCCL P2P (torch ops) are ordered with the kernels
         stream = torch.cuda.current_stream(device).cuda_stream if use_torch_stream else None
-        self.sim = MPMSimulator(c, (), device=device, stream=stream, **sim_kw)
+        flags = sim_kw.pop("flags", 0) | (SMX_FLAG_EXTERNAL_STREAM if use_torch_stream else 0)
+        self.sim = MPMSimulator(c, (), device=device, stream=stream or None, flags=flags, **sim_kw)
         check(lib().smx_set_slab(self.sim._h, self.lo, self.hi, int(rank > 0), int(rank < self.n_ranks - 1)))
         self.sim.reset(st[self.ids] if st.shape[1] == 24 else st[self.ids, :3])
         self._views = {}

@@ -2,7 +2,7 @@
 """BASELINE config 4: N independent grip-like rollouts sharded over the GPUs of one box, several rollouts per GPU
 batched in one handle, action-gradient all-reduce (mean) at the end of the episode.
 
-  python tools/bench_rollouts.py [--rollouts 64] [--n 10000] [--env-steps 40] [--substeps 5] [--reps 3]
+  python tools/bench_rollouts.py [--rollouts 64] [--particles 10000] [--env-steps 40] [--substeps 5] [--reps 3]
   torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/bench_rollouts.py ...
 
 Scene (the structure of demo_grip, softmac/config/demo_grip_config.py + demo_grip.py:117-124, with analytic sphere SDFs
@@ -27,7 +27,7 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--rollouts", type=int, default=64)
-    ap.add_argument("--n", type=int, default=10000)
+    ap.add_argument("--particles", dest="n", type=int, default=10000)
     ap.add_argument("--env-steps", type=int, default=40)
     ap.add_argument("--substeps", type=int, default=5)
     ap.add_argument("--reps", type=int, default=3)

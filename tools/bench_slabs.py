@@ -1,0 +1,111 @@
+#!/usr/bin/env python
+"""BASELINE config 5: one large scene split into x-slabs across the GPUs of a box, halo exchange over NCCL P2P.
+
+  torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/bench_slabs.py [--particles 8000000] [--grid 256] [--substeps 32]
+  python tools/bench_slabs.py --check           # (under torchrun) small scene, compares against a single-handle run on rank 0
+
+Strong scaling: the scene is fixed, every rank owns the particles of its slab.  Prints one JSON line on rank 0:
+particle-substeps/s forward+backward, max over ranks of the device time.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--particles", dest="n", type=int, default=8_000_000)
+    ap.add_argument("--grid", dest="n_grid", type=int, default=256)
+    ap.add_argument("--substeps", type=int, default=32)
+    ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--sort-every", type=int, default=16)
+    ap.add_argument("--check", action="store_true")
+    args = ap.parse_args()
+    import torch
+    import torch.distributed as dist
+    import scenes
+    from harness import sim_cfg, rel_l2
+    from softmac_b200 import rollouts
+    from softmac_b200.slabs import DistSlab
+    rank, ws, local = rollouts.init()
+    torch.cuda.set_device(local)
+    if args.check:
+        args.n, args.n_grid, args.substeps = 200_000, 64, 8
+    S = args.substeps
+    dt = 2e-4 * 64 / args.n_grid * 0.5 if args.n_grid > 64 else 2e-4          # 1e-4 at 128^3, 5e-5 at 256^3 (stability: DESIGN.md section 5)
+    cfg = sim_cfg(args.n, n_grid=args.n_grid, max_steps=S + 2, dt=dt)
+    st = scenes.cube_state(args.n)                                              # same on every rank (np.random.seed(0))
+    if args.check:
+        st[:, 3:6] = 0.5 * np.random.default_rng(1).normal(size=(args.n, 3)).astype(np.float32)
+    seed = st[:, :3] - st[:, :3].mean(0)
+    if ws > 1:
+        sl = DistSlab(cfg, st, env_dt=5 * dt, sort_every=args.sort_every)
+    else:
+        from softmac_b200.slabs import SlabCluster
+        sl = None
+    from softmac_b200.engine import MPMSimulator
+    if ws == 1:
+        sim = MPMSimulator(cfg, (), env_dt=5 * dt, sort_every=args.sort_every)
+        sim.reset(st)
+
+        class _One:
+            def step(self, s0, c): sim.step(s0, c)
+            def step_grad(self, s1, c): sim.step_grad(s1, c)
+            def add_x_grad(self, f, g): sim.add_x_grad(f, g)
+        sl, the_sim = _One(), sim
+        sl.sim = sim
+    sim = sl.sim
+    sim.copyframe(0, S + 1)
+    sl.add_x_grad(S, seed)
+
+    def step():
+        sim.copyframe(S + 1, 0)
+        sl.step(0, S)
+        sl.step_grad(S, S)
+
+    times = []
+    for r in range(args.reps + 2):
+        if ws > 1:
+            dist.barrier()
+        torch.cuda.synchronize(); sim.synchronize()
+        t0 = time.perf_counter()
+        step()
+        torch.cuda.synchronize(); sim.synchronize()
+        if ws > 1:
+            dist.barrier()
+        if r >= 2:
+            times.append(time.perf_counter() - t0)
+    t = torch.tensor([float(np.median(times))], dtype=torch.float64, device="cuda")
+    if ws > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    T = float(t.item())
+    out = {"workload": f"slab decomposition (config 5): {args.n} particles, {args.n_grid}^3, {S} substeps fwd + {S} bwd", "n_gpus": ws,
+           "ms_per_step": T * 1e3, "particle_substeps_per_s_fwd_bwd": args.n * S / T, "scaling": "strong", "local_particles": int(sim.n_particles),
+           "counters": sim.counters()}
+    if args.check and ws > 1:
+        got = sl.gather_state(S)
+        if rank == 0:
+            ref = MPMSimulator(cfg, (), env_dt=5 * dt, sort_every=args.sort_every, device=local)
+            ref.reset(st)
+            ref.step(0, S)
+            r = ref.get_state(S)
+            out["check_rel_l2_x"] = rel_l2(got[:, :3], r[:, :3]); out["check_rel_l2_v"] = rel_l2(got[:, 3:6], r[:, 3:6])
+            out["check_rel_l2_F"] = rel_l2(got[:, 6:15], r[:, 6:15])
+            assert out["check_rel_l2_x"] <= 1e-6 and out["check_rel_l2_v"] <= 5e-5 and out["check_rel_l2_F"] <= 5e-5, out
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if ws > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
