@@ -123,6 +123,8 @@ struct smx_sim {
     float *adj_cur = nullptr, *adj_nxt = nullptr;
     int adj_frame = -1, adj_order = -1;
     int grad_pending = -1;
+    int last_fwd = -1;
+    long long g_in_clean_uid = -1;      // ordering whose active blocks of g_in are known to be zero (k_grid_op re-zeroes them)
     struct Seed { float* dev = nullptr; int ncols = 24; };
     std::map<int, Seed> seeds;          // frame -> device (n, 3 | 24) fp32 AoS in particle-id order
     // primitives
@@ -339,7 +341,6 @@ static int ensure_ckpt(smx_sim* s, int f) {
     return SMX_OK;
 }
 
-// P2G + grid update + forecast contact of substep f (everything before G2P); shared by forward and adjoint
 static int forward_p2g(smx_sim* s, int f, bool write_F, bool accumulate) {
     const Params& P = s->P;
     Order& o = s->orders[s->order_of[f]];
@@ -348,7 +349,8 @@ static int forward_p2g(smx_sim* s, int f, bool write_F, bool accumulate) {
     PrimSet ps = s->primset();
     const int* cslot = nullptr;
     TRY(ctrl_slots(s, s->order_of[f], &cslot));
-    TRY(clear_grids(s, o, s->g_in, nullptr, nullptr));
+    if (s->g_in_clean_uid != o.uid) TRY(clear_grids(s, o, s->g_in, nullptr, nullptr));
+    s->g_in_clean_uid = -1;             // P2G is about to write it
     if (s->slab && P.n > 0) {
         k_check_slab<<<nblk(P.n, 256), 256, 0, s->stream>>>(P, fin, s->halo_lo ? s->slab_lo - 1 : 0, s->halo_hi ? s->slab_hi : P.nb - 1, s->counters); CKL(s);
     }
@@ -364,23 +366,36 @@ static int forward_p2g(smx_sim* s, int f, bool write_F, bool accumulate) {
     }
     return SMX_OK;
 }
-static int forward_grid(smx_sim* s, int f, bool accumulate) {
+static int forward_grid(smx_sim* s, int f, bool accumulate, bool checkpoint) {
     const Params& P = s->P;
     Order& o = s->orders[s->order_of[f]];
     PrimSet ps = s->primset();
     bool contact = s->has_contact();
-    k_grid_op<<<grid_blocks_launch(s), 256, 0, s->stream>>>(P, ps, f, s->dense ? nullptr : o.blocks, o.nblocks, s->g_in, s->g_out, contact ? s->g_mix : nullptr, accumulate ? 1 : 0);
+    bool save = checkpoint && s->ckpt && (!contact || s->ckpt_narr == 3);
+    float4* rec = save ? s->ckpt + (size_t)f * s->ckpt_rec : nullptr;
+    // checkpoint == forward pass proper: also save the grid record and re-zero g_in for the next substep's P2G
+    k_grid_op<<<grid_blocks_launch(s), 256, 0, s->stream>>>(P, ps, f, s->dense ? nullptr : o.blocks, o.nblocks, s->g_in, s->g_out, contact ? s->g_mix : nullptr,
+                                                           accumulate ? 1 : 0, rec, s->ckpt_cap, contact ? 0 : 1, checkpoint ? 1 : 0, s->counters);
     CKLN(s, "k_grid_op");
+    if (checkpoint) s->g_in_clean_uid = o.uid;
     if (contact && P.n > 0) {
         float life = 1.0f / (float)(P.substeps - f % P.substeps);      // mpm_simulator.py:425 (f32 in the reference too)
         k_contact<<<nblk(P.n, SMX_TPB), SMX_TPB, 0, s->stream>>>(P, ps, f, life, s->frame_ptr(f), s->g_mix, s->g_out, accumulate ? 1 : 0); CKLN(s, "k_contact");
+    }
+    if (save) {
+        if (contact) {      // g_out is final only after the contact scatter
+            k_ckpt_copy<<<grid_blocks_launch(s), 256, 0, s->stream>>>(s->dense ? nullptr : o.blocks, o.nblocks, s->B * s->P.nb3, s->ckpt_cap, rec,
+                                                                     nullptr, s->g_out, s->g_mix, 0, s->counters);
+            CKLN(s, "ckpt_save");
+        }
+        s->ckpt_order[f] = o.uid; s->ckpt_contact[f] = contact;
     }
     return SMX_OK;
 }
 // P2G + grid update + forecast contact of substep f (everything before G2P); shared by forward and adjoint
 static int forward_to_grid(smx_sim* s, int f, bool write_F, bool accumulate) {
     TRY(forward_p2g(s, f, write_F, accumulate));
-    return forward_grid(s, f, accumulate);
+    return forward_grid(s, f, accumulate, false);
 }
 
 static int check_frame(smx_sim* s, int f, const char* what) {
@@ -914,15 +929,8 @@ int smx_substep_end(smx_sim* s, int32_t f) {
     TRY(check_frame(s, f, "smx_substep"));
     if (f + 1 >= s->cfg.max_steps || s->order_of[f] < 0 || s->order_of[f + 1] != s->order_of[f]) return fail(SMX_ERR_STATE, "smx_substep_end: smx_substep_begin(%d) has not been called", f);
     CK(cudaSetDevice(s->cfg.device));
-    TRY(forward_grid(s, f, true));
-    if (s->ckpt && (!s->has_contact() || s->ckpt_narr == 3)) {
-        Order& o = s->orders[s->order_of[f]];
-        bool contact = s->has_contact();
-        k_ckpt_copy<<<grid_blocks_launch(s), 256, 0, s->stream>>>(s->dense ? nullptr : o.blocks, o.nblocks, s->B * s->P.nb3, s->ckpt_cap, s->ckpt + (size_t)f * s->ckpt_rec,
-                                                                 s->g_in, s->g_out, contact ? s->g_mix : nullptr, 0, s->counters);
-        CKLN(s, "ckpt_save");
-        s->ckpt_order[f] = o.uid; s->ckpt_contact[f] = contact;
-    }
+    TRY(forward_grid(s, f, true, true));
+    s->last_fwd = f;
     if (s->P.n > 0) { k_g2p<<<nblk(s->P.n, SMX_TPB), SMX_TPB, 0, s->stream>>>(s->P, s->frame_ptr(f), s->frame_ptr(f + 1), s->g_out); CKLN(s, "k_g2p"); }
     if (s->cfg.sort_every > 0 && (f + 1) % s->cfg.sort_every == 0 && !(s->cfg.flags & SMX_FLAG_NO_SORT)) TRY(resort(s, f + 1, true));
     return SMX_OK;
@@ -967,14 +975,16 @@ int smx_substep_grad_begin(smx_sim* s, int32_t f) {
     bool contact = s->has_contact();
     PrimSet ps = s->primset();
     if (s->ckpt && s->ckpt_order[f] == ord.uid && (bool)s->ckpt_contact[f] == contact) {
+        // restore g_in / g_out (/ g_mix) and zero the adjoint grids of the same blocks in one launch
         k_ckpt_copy<<<grid_blocks_launch(s), 256, 0, s->stream>>>(s->dense ? nullptr : ord.blocks, ord.nblocks, s->B * s->P.nb3, s->ckpt_cap, s->ckpt + (size_t)f * s->ckpt_rec,
-                                                                 s->g_in, s->g_out, contact ? s->g_mix : nullptr, 1, s->counters);
+                                                                 s->g_in, s->g_out, contact ? s->g_mix : nullptr, 1, s->counters, s->gg_out, contact ? s->gg_mix : nullptr);
         CKLN(s, "ckpt_restore");
     } else {
         if (s->slab) return fail(SMX_ERR_STATE, "smx_substep_grad: slab decomposition needs the grid checkpoint of substep %d (run it forward in this handle; do not set SMX_FLAG_NO_GRID_CKPT)", f);
         TRY(forward_to_grid(s, f, false, false));
+        TRY(clear_grids(s, ord, s->gg_out, contact ? s->gg_mix : nullptr, nullptr));
     }
-    TRY(clear_grids(s, ord, s->gg_out, contact ? s->gg_mix : nullptr, nullptr));
+    s->g_in_clean_uid = -1;             // g_in now holds substep f's values
     const float* fin = s->frame_ptr(f);
     if (P.n > 0) {
         if (s->cfg.flags & SMX_FLAG_DIRECT_RED) k_g2p_grad<false><<<nblk(P.n, SMX_TPB_SC), SMX_TPB_SC, 0, s->stream>>>(P, fin, s->adj_cur, s->adj_nxt, s->g_out, s->gg_out);
@@ -1168,6 +1178,17 @@ int smx_get_permutation(smx_sim* s, int32_t f, uint32_t* perm) {
 int smx_get_grid(smx_sim* s, float* g_in, float* g_out) {
     if (!s) return fail(SMX_ERR_ARG, "smx_get_grid: null simulator");
     CK(cudaSetDevice(s->cfg.device));
+    if (g_in && s->last_fwd >= 0) {
+        // k_grid_op re-zeroes g_in for the next substep; the values of the last substep live in its checkpoint record
+        int f = s->last_fwd;
+        if (!s->ckpt || s->order_of[f] < 0 || s->ckpt_order[f] != s->orders[s->order_of[f]].uid)
+            return fail(SMX_ERR_STATE, "smx_get_grid: g_in of substep %d was not retained (grid checkpoints disabled)", f);
+        Order& o = s->orders[s->order_of[f]];
+        k_ckpt_copy<<<grid_blocks_launch(s), 256, 0, s->stream>>>(s->dense ? nullptr : o.blocks, o.nblocks, s->B * s->P.nb3, s->ckpt_cap, s->ckpt + (size_t)f * s->ckpt_rec,
+                                                                 s->g_in, nullptr, nullptr, 1, s->counters);
+        CKL(s);
+        s->g_in_clean_uid = -1;
+    }
     size_t Gb = (size_t)s->P.Gb;      // batch 0 only
     if (!s->g_lin) CK(cudaMalloc(&s->g_lin, Gb * sizeof(float4)));
     const float4* src[2] = {s->g_in, s->g_out}; float* dst[2] = {g_in, g_out};

@@ -349,10 +349,14 @@ __device__ __forceinline__ void node_coords(uint32_t node, int nb, int& i, int& 
 // blocks == nullptr: dense sweep; else one 64-node grid block per 64 threads from the active list.
 // Also re-zeroes nothing: inactive nodes are written as zero so g_out / g_mix never need a memset.
 // ------------------------------------------------------------------------------------------------
+// Fused with it (to keep the launch count down): the grid checkpoint of this substep (rec: g_in always, g_out when
+// no contact kernel follows) and the zeroing of g_in for the next substep's P2G.
 __global__ void __launch_bounds__(256) k_grid_op(Params P, PrimSet ps, int f, const uint32_t* __restrict__ blocks, const int* __restrict__ nblocks,
-                                                 const float4* __restrict__ g_in, float4* __restrict__ g_out, float4* __restrict__ g_mix,
-                                                 int accumulate) {
+                                                 float4* __restrict__ g_in, float4* __restrict__ g_out, float4* __restrict__ g_mix,
+                                                 int accumulate, float4* __restrict__ rec, int cap, int save_out, int zero_in,
+                                                 unsigned long long* __restrict__ counters) {
     int total = blocks ? *nblocks : P.nbatch * P.nb3;
+    if (rec && total > cap && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(counters + 2, 1ull);   // record does not fit
     for (int bi = blockIdx.x * 4 + (threadIdx.x >> 6); bi < total; bi += gridDim.x * 4) {
         uint32_t node = (blocks ? blocks[bi] : (uint32_t)bi) * 64u + (threadIdx.x & 63);
         float4 g = g_in[node];
@@ -383,6 +387,12 @@ __global__ void __launch_bounds__(256) k_grid_op(Params P, PrimSet ps, int f, co
         }
         g_out[node] = o;
         if (g_mix) g_mix[node] = o;
+        if (rec && bi < cap) {
+            size_t slot = (size_t)bi * 64 + (threadIdx.x & 63);
+            rec[slot] = g;
+            if (save_out) rec[(size_t)cap * 64 + slot] = o;
+        }
+        if (zero_in) g_in[node] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
 
@@ -983,7 +993,7 @@ __global__ void k_mark_blocks_sorted(Params P, const uint32_t* __restrict__ keys
 // record layout: [array][active-block slot][64 nodes]; `cap` = blocks reserved per array
 __global__ void __launch_bounds__(256) k_ckpt_copy(const uint32_t* __restrict__ blocks, const int* __restrict__ nblocks, int nb3, int cap,
                                                     float4* __restrict__ rec, float4* __restrict__ a, float4* __restrict__ b, float4* __restrict__ c, int restore,
-                                                    unsigned long long* __restrict__ counters) {
+                                                    unsigned long long* __restrict__ counters, float4* __restrict__ zero_a = nullptr, float4* __restrict__ zero_b = nullptr) {
     int total = blocks ? *nblocks : nb3;
     if (total > cap) {      // record does not fit: flagged, the host falls back to recomputation (counters[2])
         if (blockIdx.x == 0 && threadIdx.x == 0 && !restore) atomicAdd(counters + 2, 1ull);
@@ -992,6 +1002,8 @@ __global__ void __launch_bounds__(256) k_ckpt_copy(const uint32_t* __restrict__ 
     for (int bi = blockIdx.x * 4 + (threadIdx.x >> 6); bi < total; bi += gridDim.x * 4) {
         uint32_t node = (blocks ? blocks[bi] : (uint32_t)bi) * 64u + (threadIdx.x & 63);
         size_t slot = (size_t)bi * 64 + (threadIdx.x & 63);
+        if (zero_a) zero_a[node] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (zero_b) zero_b[node] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (restore) {
             if (a) a[node] = rec[slot];
             if (b) b[node] = rec[(size_t)cap * 64 + slot];
