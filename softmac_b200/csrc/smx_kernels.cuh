@@ -226,8 +226,11 @@ __device__ __forceinline__ void material_update(const M3& Et, const Params& P, M
                 float g0 = fminf(fmaxf(m.svd.e[0], -2e-3f), 3e-3f), g1 = fminf(fmaxf(m.svd.e[1], -2e-3f), 3e-3f),
                       g2 = fminf(fmaxf(m.svd.e[2], -2e-3f), 3e-3f);
                 m.D = udvt(m.svd.U, g0, g1, g2, m.svd.V);                       // new_F - R = U (Sc - I) V^T
-                // new_F = F_tmp + U (Sc - S) V^T: exactly F_tmp when nothing is clipped
-                m.newF = add(Ftmp, udvt(m.svd.U, g0 - m.svd.e[0], g1 - m.svd.e[1], g2 - m.svd.e[2], m.svd.V));
+                // new_F = F_tmp + U (Sc - S) V^T: exactly F_tmp when nothing is clipped (skipped warp-wide in that case)
+                bool clipped = (g0 != m.svd.e[0]) | (g1 != m.svd.e[1]) | (g2 != m.svd.e[2]);
+                m.newF = Ftmp;
+                if (__any_sync(__activemask(), clipped))
+                    m.newF = add(Ftmp, udvt(m.svd.U, g0 - m.svd.e[0], g1 - m.svd.e[1], g2 - m.svd.e[2], m.svd.V));
             } else {                      // elastic
                 m.D = udvt(m.svd.U, m.svd.e[0], m.svd.e[1], m.svd.e[2], m.svd.V);
                 m.newF = Ftmp;

@@ -148,6 +148,10 @@ __device__ __forceinline__ Svd svd_dev(const M3& E) {
     float v00 = 1.f, v01 = 0.f, v02 = 0.f, v10 = 0.f, v11 = 1.f, v12 = 0.f, v20 = 0.f, v21 = 0.f, v22 = 1.f;
 #pragma unroll 1
     for (int sweep = 0; sweep < SMX_JACOBI_SWEEPS; sweep++) {
+        // warp-uniform convergence test: off-diagonal mass below fp32 resolution of the diagonal, or below 1e-9 absolute
+        // (an eigenvalue error of 1e-9 is 5e-7 of the plastic clip range; quantities this small do not move x/v/F/C)
+        float off2 = s01 * s01 + s02 * s02 + s12 * s12, dg2 = s00 * s00 + s11 * s11 + s22 * s22;
+        if (__all_sync(__activemask(), off2 <= fmaxf(1e-15f * dg2, 1e-18f))) break;
         jacobi_rot(s00, s11, s01, s02, s12, v00, v01, v10, v11, v20, v21);   // (0,1), r = 2
         jacobi_rot(s00, s22, s02, s01, s12, v00, v02, v10, v12, v20, v22);   // (0,2), r = 1
         jacobi_rot(s11, s22, s12, s01, s02, v01, v02, v11, v12, v21, v22);   // (1,2), r = 0
