@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--n", type=int, default=1_000_000)
     ap.add_argument("--n-grid", type=int, default=128)
     ap.add_argument("--variant", default="A", choices=["A", "B"])
+    ap.add_argument("--init", default="rest", choices=["rest", "stressed"], help="rest: the reference generator (v=0, F=I, C=0); stressed: same x with F = I + 0.01 N(0,1), v = 0.3 N(0,1), C = N(0,1) (every particle needs full SVD sweeps and clips plastically)")
     ap.add_argument("--batch", type=int, default=1, help="independent rollouts batched in one handle (per GPU)")
     ap.add_argument("--sort-every", type=int, default=16)
     ap.add_argument("--flags", type=int, default=0)
@@ -122,6 +123,12 @@ def variant_b_table():
 def make_inputs(args, rank):
     import scenes
     st = scenes.cube_state(args.n, seed=rank)           # rank r: np.random.seed(r) (rank 0 = the reference generator's seed)
+    if getattr(args, "init", "rest") == "stressed":
+        rng = np.random.default_rng(1000 + rank)
+        st[:, 3:6] = 0.3 * rng.normal(size=(args.n, 3))
+        st[:, 6:15] += 0.01 * rng.normal(size=(args.n, 9))
+        st[:, 15:24] = rng.normal(size=(args.n, 9))
+        st = st.astype(np.float32).astype(np.float64)
     seed = st[:, :3] - st[:, :3].mean(0)                # x_bar[S] = x[S] - mean (any fixed dense seed)
     return st, np.ascontiguousarray(seed)
 
@@ -174,7 +181,7 @@ def run_reference(args, rank, world):
 def config_dict(args, S):
     return {"workload": f"cube-{args.n} variant {args.variant}: {args.n} particles, {args.n_grid}^3 grid, corotated plastic, mixed contact, "
                         f"{S} substeps forward + {S} backward per step",
-            "n_particles": args.n, "rollouts_per_gpu": args.batch, "n_grid": args.n_grid, "substeps_per_step": S, "variant": args.variant, "dt": DT,
+            "n_particles": args.n, "rollouts_per_gpu": args.batch, "n_grid": args.n_grid, "substeps_per_step": S, "variant": args.variant, "init": args.init, "dt": DT,
             "sort_every": args.sort_every, "parallelism": f"{args.gpus} independent rollout(s), one per GPU, gradient all-reduce" if args.gpus > 1 else "single GPU",
             "cache": "inputs larger than L2: 96 MB per particle frame, one fresh frame per substep"}
 

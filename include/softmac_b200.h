@@ -211,6 +211,11 @@ int smx_timer_start(smx_sim* sim);
 int smx_timer_stop(smx_sim* sim, float* ms);
 /* number of kernels this handle has launched since creation */
 int64_t smx_launch_count(smx_sim* sim);
+/* Mesh.task / Mesh.trimesh2sdf (softmac/engine/primitive/mesh.py:167-241) on the GPU: signed distance (negative inside)
+ * and nearest-face unit normal / (1 + 1e-8) at lower + (i,j,k)*dx for a triangle mesh (vertices (nv,3) f64, faces (nf,3)
+ * int32).  Stand-alone: no simulator handle.  Outputs: sdf[r0*r1*r2], normal[r0*r1*r2*3] (host). */
+int smx_build_sdf_table(const double* vertices, int32_t nv, const int32_t* faces, int32_t nf, const int32_t res[3], const double lower[3],
+                        double dx, double* sdf_out, double* normal_out, int32_t device);
 /* runs smx_substep (backward == 0) or smx_substep_grad (backward != 0) of substep f with a CUDA event after every
  * launch and returns the per-kernel-class device time: names[i] (static strings), ms[i], i < *count (<= 32) */
 int smx_profile_substep(smx_sim* sim, int32_t f, int32_t backward, const char** names, float* ms, int32_t* count);

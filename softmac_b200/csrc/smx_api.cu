@@ -17,6 +17,7 @@
 
 #include "../../include/softmac_b200.h"
 #include "smx_kernels.cuh"
+#include "smx_sdf.cuh"
 
 #include <execinfo.h>
 #include <signal.h>
@@ -1235,6 +1236,31 @@ int smx_timer_stop(smx_sim* s, float* ms) {
     return SMX_OK;
 }
 int64_t smx_launch_count(smx_sim* s) { return s ? s->launches : 0; }
+
+// Mesh.trimesh2sdf (mesh.py:178-241) on the GPU; stand-alone (no simulator handle).  Outputs are host arrays
+// sdf[r0*r1*r2], normal[r0*r1*r2*3] sampled at lower + (i,j,k)*dx.
+int smx_build_sdf_table(const double* vertices, int32_t nv, const int32_t* faces, int32_t nf, const int32_t res[3], const double lower[3], double dx,
+                        double* sdf_out, double* normal_out, int32_t device) {
+    if (!vertices || !faces || !res || !lower || !sdf_out || !normal_out || nv < 3 || nf < 1 || dx <= 0) return fail(SMX_ERR_ARG, "smx_build_sdf_table: bad argument");
+    for (int i = 0; i < 3 * nf; i++) if (faces[i] < 0 || faces[i] >= nv) return fail(SMX_ERR_RANGE, "smx_build_sdf_table: face index %d outside [0, %d)", faces[i], nv);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(SMX_ERR_CUDA, "smx_build_sdf_table: no CUDA device; this library has no CPU path"); }
+    CK(cudaSetDevice(device));
+    long long total = (long long)res[0] * res[1] * res[2];
+    double *dv = nullptr, *ds = nullptr, *dn = nullptr; int* df = nullptr;
+    CK(cudaMalloc(&dv, (size_t)nv * 3 * sizeof(double))); CK(cudaMalloc(&df, (size_t)nf * 3 * sizeof(int)));
+    CK(cudaMalloc(&ds, (size_t)total * sizeof(double))); CK(cudaMalloc(&dn, (size_t)total * 3 * sizeof(double)));
+    CK(cudaMemcpy(dv, vertices, (size_t)nv * 3 * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(df, faces, (size_t)nf * 3 * sizeof(int), cudaMemcpyHostToDevice));
+    k_build_sdf<<<(unsigned)((total + 127) / 128), 128>>>(dv, df, nf, res[0], res[1], res[2], lower[0], lower[1], lower[2], dx, ds, dn);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(sdf_out, ds, (size_t)total * sizeof(double), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(normal_out, dn, (size_t)total * 3 * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaFree(dv); cudaFree(df); cudaFree(ds); cudaFree(dn);
+    if (e != cudaSuccess) return fail(SMX_ERR_CUDA, "smx_build_sdf_table: %s", cudaGetErrorString(e));
+    return SMX_OK;
+}
 
 int smx_profile_substep(smx_sim* s, int32_t f, int32_t backward, const char** names, float* ms, int32_t* count) {
     if (!s || !names || !ms || !count) return fail(SMX_ERR_ARG, "smx_profile_substep: null argument");

@@ -14,13 +14,18 @@ from .primitive_base import Primitive
 
 
 class Mesh(Primitive):
-    def __init__(self, mesh_path=None, color=None, sdf=None, **kwargs):
+    def __init__(self, mesh_path=None, color=None, sdf=None, cache_dir=None, device=0, **kwargs):
         super().__init__(**kwargs)
         self.mesh_path, self.color = mesh_path, color
         self.urdf_path = self.cfg.get("urdf_path", "")
         self.mesh_rest = None
         if sdf is not None:
             self.load_sdf(sdf)
+        elif mesh_path is not None:
+            # Mesh.preprocess_sdf (mesh.py:136-165): tables built on the GPU from the OBJ (or loaded from the cache)
+            from .sdf_builder import cached_sdf
+            tables, self.mesh_rest = cached_sdf(str(mesh_path), cache_dir=cache_dir, device=device)
+            self.load_sdf(tables)
 
     def load_sdf(self, sdf):
         """sdf: dict with keys sdf, normal, position=(lower, upper), dx (the "sdf" entry of the pickle)."""

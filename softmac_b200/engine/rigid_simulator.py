@@ -40,6 +40,43 @@ class Body:
         self.ndof = {"fixed": 0, "prismatic": 1, "free": 6}[joint]
 
 
+def bodies_from_urdf(urdf_path):
+    """One Body per link with a collision mesh, in document order (the order ``Primitives`` creates the primitives in,
+    primitives.py:25-41): joint type (fixed / prismatic / floating -> free), axis, origin accumulated along the parent
+    chain (translations only; the reference assets use rpy = 0), mass of the child link."""
+    import xml.etree.ElementTree as ET
+    root = ET.parse(urdf_path).getroot()
+    joints = {j.find("child").attrib["link"]: j for j in root.findall("joint")}
+
+    def origin_of(link):
+        o = np.zeros(3)
+        while link in joints:
+            j = joints[link]
+            org = j.find("origin")
+            if org is not None:
+                o += np.array([float(v) for v in org.attrib.get("xyz", "0 0 0").split()])
+            link = j.find("parent").attrib["link"]
+        return o
+
+    out = []
+    for link in root.findall("link"):
+        if link.find("collision/geometry/mesh") is None:
+            continue
+        name = link.attrib["name"]
+        j = joints.get(name)
+        jt = j.attrib.get("type", "fixed") if j is not None else "floating"
+        joint = {"fixed": "fixed", "prismatic": "prismatic", "floating": "free"}.get(jt)
+        if joint is None:
+            raise NotImplementedError(f"stand-in rigid simulator: joint type {jt!r} of link {name!r}")
+        axis = (1, 0, 0)
+        if j is not None and j.find("axis") is not None:
+            axis = tuple(float(v) for v in j.find("axis").attrib["xyz"].split())
+        mass = link.find("inertial/mass")
+        out.append(dict(joint=joint, axis=axis, origin=tuple(origin_of(name)), mass=float(mass.attrib["value"]) if mass is not None else 1.0,
+                        gravity=False))
+    return out
+
+
 class RigidSimulator:
     def __init__(self, cfg, primitives, substeps=20, env_dt=2e-3, bodies=None, fp32_bridge=True):
         self.cfg, self.primitives = cfg, primitives

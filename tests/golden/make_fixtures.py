@@ -77,3 +77,26 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def reference_sdf_tables():
+    """tests/golden/mesh_sdf_reference_tables.npz: the two SDF caches the REFERENCE ships (output of its own
+    Mesh.trimesh2sdf with trimesh 3.21.5): gripper palm and door -- mesh (vertices, faces) + tables.  sdf stored as fp32,
+    normals as int8 (both meshes are axis-aligned boxes: every stored normal is +-e_k / (1 + 1e-8))."""
+    out = {}
+    for name, rel in (("palm", "assets/gripper/68956732a79bf09d8703ab990a2e2319bf5492c792294e9a86632db03b5ac4d5"),
+                      ("door", "assets/door/e7ab3378b317f8d1d4de18fa5bfa4d98e79629e714104b720ebcf0470dfc561a")):
+        with open(os.path.join(REF, rel), "rb") as f:
+            b = pickle.load(f)
+        V, Fc = [np.array(a) for a in b["meshes"][0]]
+        s = b["sdf"]
+        assert np.allclose(np.abs(np.round(s["normal"])), np.abs(s["normal"]) * (1 + 1e-8))
+        out[name + "_V"], out[name + "_F"] = V, Fc.astype(np.int32)
+        out[name + "_sdf"], out[name + "_normal"] = s["sdf"].astype(np.float32), np.round(s["normal"]).astype(np.int8)
+        out[name + "_lower"], out[name + "_upper"] = s["position"]
+        out[name + "_dx"], out[name + "_res"] = s["dx"][0], np.array(s["res"])
+    np.savez_compressed(os.path.join(HERE, "mesh_sdf_reference_tables.npz"), **out)
+
+
+if __name__ == "__main__" and "--sdf" in sys.argv:
+    reference_sdf_tables()
