@@ -353,3 +353,65 @@ def test_properties_at_full_size():
         sim.substep_grad(f)
     assert np.all(sim.get_state_grad(0) == 0)
     assert sim.counters()["clamped"] == 0 and sim.counters()["left_active_region"] == 0
+
+
+def test_velocity_control_forward_kinematics_and_action_grad():
+    """rigid_velocity_control: Primitive.set_action writes v, w of `substeps` frames, forward_kinematics integrates the pose
+    inside every substep (mpm_simulator.py:329-331, primitive_base.py:280-304) and get_action_grad collects the adjoint."""
+    rng = np.random.default_rng(280)
+    n, substeps = 3000, 4
+    center = np.array([0.5, 0.3, 0.5])
+    pair = Pair(n, tables=[scenes.sphere_table()], prim_params=[(0.5, 666.)], max_steps=2 * substeps + 2, sort_every=3, substeps=substeps, vctrl=True)
+    s13 = np.concatenate([center, scenes.random_quat(rng), np.zeros(6)])
+    pair.set_prim_state(0, 0, 1, s13)
+    a6 = np.array([0.4, -0.3, 0.2, 0.0, 0.15, 0.0]).astype(np.float32).astype(np.float64)       # [w(3), v(3)]
+    pair.orc.set_primitive_action(0, 0, substeps, a6)
+    pair.prims[0].set_action(0, substeps, a6)
+    pair.reset(scenes.contact_rollout_state(n, rng, center))
+    pair.clear_ext_f()
+    for f in range(substeps):
+        pair.substep(f)
+    po, pg = pair.orc.get_primitive_state(0, substeps), pair.prims[0].get_all_states(substeps)
+    assert rel_l2(pg[:7], po[:7]) <= 1e-6                                                   # integrated pose
+    assert_state_close(pair.gpu.get_state(substeps), pair.orc.get_frame(substeps), tol=2e-4)
+    pair.orc.clear_grads(); pair.gpu.clear_all_gradients()
+    g = rng.normal(size=(n, 3)).astype(np.float32).astype(np.float64)
+    g24 = np.zeros((n, 24)); g24[:, :3] = g
+    pair.orc.add_frame_grad(substeps, g24); pair.gpu.add_x_grad(substeps, g)
+    for f in range(substeps - 1, -1, -1):
+        pair.orc.substep_grad(f); pair.gpu.substep_grad(f)
+    ao, ag = pair.orc.get_primitive_action_grad(0, 0, substeps), pair.prims[0].get_action_grad(0, substeps)
+    assert np.abs(ao).max() > 0 and cosine(ag, ao) >= 0.999 and rel_l2(ag, ao) <= 2e-2, (ag, ao)
+
+
+def test_copy_mode_and_mid_run_set_state():
+    """TaichiEnv._is_copy (taichi_env.py:106-115): run `substeps` substeps, copy the last frame to frame 0, repeat; and a
+    set_state in the middle of a run re-bins the particles without disturbing the result."""
+    rng = np.random.default_rng(290)
+    n, substeps = 4000, 3
+    pair = Pair(n, max_steps=substeps + 2, sort_every=2, substeps=substeps)
+    st = scenes.blob_state(n, rng, Fdev=0.003, vel=0.3, Cdev=0.5)
+    pair.reset(st)
+    ref = mo_rollout(pair.orc, st, 3 * substeps)
+    for rep in range(3):
+        for f in range(substeps):
+            pair.gpu.substep(f)
+        pair.gpu.copyframe(substeps, 0)
+    got = pair.gpu.get_state(0)
+    assert rel_l2(got[:, :3], ref[:, :3]) <= 1e-6 and rel_l2(got[:, 3:6], ref[:, 3:6]) <= 1e-4
+    # set_state of the same values at frame 0, then continue: identical to continuing directly
+    a = pair.gpu.get_state(0)
+    pair.gpu.substep(0)
+    cont = pair.gpu.get_state(1)
+    pair.gpu.set_state(0, [a[:, :3], a[:, 3:6], a[:, 6:15].reshape(n, 3, 3), a[:, 15:].reshape(n, 3, 3)])
+    pair.gpu.substep(0)
+    assert rel_l2(pair.gpu.get_state(1), cont) <= 1e-6
+
+
+def mo_rollout(orc, st, steps):
+    """oracle rollout that recycles two frames (the oracle keeps only max_steps frames)."""
+    orc.set_frame(0, st)
+    for f in range(steps):
+        orc.substep(0)
+        orc.set_frame(0, orc.get_frame(1))
+    return orc.get_frame(0)
