@@ -185,6 +185,11 @@ int smx_step_grad(smx_sim* sim, int32_t s1, int32_t count);
 /* loss -> x.grad[f] (+ v, F, C .grad[f]): g24 is (n,24) in get_state layout; g3 is (n,3) */
 int smx_add_state_grad(smx_sim* sim, int32_t f, const double* g24);
 int smx_add_x_grad(smx_sim* sim, int32_t f, const double* g3);
+/* GripLoss with weight (1,0,0) on the device (softmac/engine/losses/loss_grip.py:45-68, 117-140): Chamfer distance between
+ * the particles of frame f (of every batched rollout) and a target cloud (m,3); the value is returned and its gradient is
+ * accumulated into the loss seed of frame f (nearest neighbours by brute force, reference tie rule, fixed in the gradient). */
+int smx_set_chamfer_target(smx_sim* sim, const double* target, int32_t m);
+int smx_chamfer_loss(smx_sim* sim, int32_t f, double weight, double* loss_out);
 /* adjoint of frame f; only the frame most recently produced by smx_substep_grad is resident
  * (no per-frame gradient arrays are kept) */
 int smx_get_state_grad(smx_sim* sim, int32_t f, double* out24);

@@ -96,6 +96,8 @@ _SIGS = {
     "smx_step_grad": [vp, C.c_int32, C.c_int32],
     "smx_add_state_grad": [vp, C.c_int32, dp],
     "smx_add_x_grad": [vp, C.c_int32, dp],
+    "smx_set_chamfer_target": [vp, dp, C.c_int32],
+    "smx_chamfer_loss": [vp, C.c_int32, C.c_double, dp],
     "smx_get_state_grad": [vp, C.c_int32, dp],
     "smx_get_grad": [vp, C.c_int32, dp, dp],
     "smx_clear_grads": [vp],

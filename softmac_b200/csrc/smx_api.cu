@@ -124,6 +124,7 @@ struct smx_sim {
     float *adj_cur = nullptr, *adj_nxt = nullptr;
     int adj_frame = -1, adj_order = -1;
     int grad_pending = -1;
+    float* ch_target = nullptr; int ch_m = 0; double* ch_loss = nullptr;   // Chamfer target cloud (m,3) and loss accumulator
     int last_fwd = -1;
     long long g_in_clean_uid = -1;      // ordering whose active blocks of g_in are known to be zero (k_grid_op re-zeroes them)
     struct Seed { float* dev = nullptr; int ncols = 24; };
@@ -485,6 +486,7 @@ int smx_create(const smx_config* cfg, smx_sim** out) {
     if (B > 255) { delete s; return fail(SMX_ERR_ARG, "smx_create: at most 255 batched rollouts per handle"); }
     if (cfg->n_grid > 256) { delete s; return fail(SMX_ERR_ARG, "smx_create: n_grid <= 256 (8-bit base-cell packing of the staged scatter)"); }
     if ((long long)B * cfg->n_particles > 2000000000LL) { delete s; return fail(SMX_ERR_ARG, "smx_create: n_batch * n_particles too large"); }
+    if ((long long)B * cfg->n_grid * cfg->n_grid * cfg->n_grid >= (1LL << 31)) { delete s; return fail(SMX_ERR_ARG, "smx_create: n_batch * n_grid^3 must stay below 2^31 (32-bit node indices)"); }
     P.nbatch = B; P.npb = cfg->n_particles;
     n = B * cfg->n_particles;           // total particle slots of the handle
     P.n = n; P.stride = ((long long)std::max(n, 1) + 31) / 32 * 32;
@@ -547,7 +549,7 @@ int smx_destroy(smx_sim* s) {
     for (auto& o : s->free_orders) free_order(o);
     for (auto& kv : s->seeds) cudaFree(kv.second.dev);
     for (auto& p : s->prims) { cudaFree(p.sdf_dev); cudaFree(p.nrm_dev); }
-    void* ptrs[] = {s->ckpt, s->pool, s->g_in, s->g_out, s->g_mix, s->gg_out, s->gg_mix, s->g_lin, s->adj_cur, s->adj_nxt, s->stage_dev, s->keys_a, s->keys_b, s->iota, s->cub_tmp,
+    void* ptrs[] = {s->ch_target, s->ch_loss, s->ckpt, s->pool, s->g_in, s->g_out, s->g_mix, s->gg_out, s->gg_mix, s->g_lin, s->adj_cur, s->adj_nxt, s->stage_dev, s->keys_a, s->keys_b, s->iota, s->cub_tmp,
                     s->counters, s->prims_dev, s->pstate, s->pgrad, s->ext_f, s->ext_f_grad, s->abuf, s->gabuf, s->ctrl_id, s->action, s->action_grad};
     for (void* p : ptrs) cudaFree(p);
     cudaFreeHost(s->stage_host);
@@ -1114,6 +1116,46 @@ int smx_add_x_grad(smx_sim* s, int32_t f, const double* g3) {
     if (!g3) return fail(SMX_ERR_ARG, "smx_add_x_grad: null input");
     return add_seed(s, f, g3, 3);
 }
+// Chamfer loss between the particles of frame f and a target cloud, and its seed on x.grad[f] (loss_grip.py:45-68,117-140)
+int smx_set_chamfer_target(smx_sim* s, const double* target, int32_t m) {
+    if (!s || !target || m < 1) return fail(SMX_ERR_ARG, "smx_set_chamfer_target: bad argument");
+    CK(cudaSetDevice(s->cfg.device));
+    std::vector<float> h((size_t)m * 3);
+    for (size_t i = 0; i < h.size(); i++) h[i] = (float)target[i];
+    CK(cudaStreamSynchronize(s->stream));
+    cudaFree(s->ch_target); s->ch_target = nullptr;
+    CK(cudaMalloc(&s->ch_target, h.size() * sizeof(float)));
+    CK(cudaMemcpy(s->ch_target, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+    s->ch_m = m;
+    if (!s->ch_loss) CK(cudaMalloc(&s->ch_loss, sizeof(double)));
+    return SMX_OK;
+}
+int smx_chamfer_loss(smx_sim* s, int32_t f, double weight, double* loss_out) {
+    TRY(check_frame(s, f, "smx_chamfer_loss"));
+    if (!loss_out) return fail(SMX_ERR_ARG, "smx_chamfer_loss: null output");
+    if (!s->ch_target) return fail(SMX_ERR_STATE, "smx_chamfer_loss: call smx_set_chamfer_target first");
+    if (s->order_of[f] < 0) return fail(SMX_ERR_STATE, "smx_chamfer_loss: frame %d has not been written", f);
+    CK(cudaSetDevice(s->cfg.device));
+    int n = s->P.n;
+    *loss_out = 0.0;
+    if (n == 0) return SMX_OK;
+    auto it = s->seeds.find(f);
+    if (it == s->seeds.end()) {         // create an x-only seed buffer for this frame
+        smx_sim::Seed sd; sd.ncols = 3;
+        CK(cudaMalloc(&sd.dev, (size_t)n * 3 * sizeof(float)));
+        CK(cudaMemsetAsync(sd.dev, 0, (size_t)n * 3 * sizeof(float), s->stream));
+        s->seeds[f] = sd;
+        it = s->seeds.find(f);
+    }
+    CK(cudaMemsetAsync(s->ch_loss, 0, sizeof(double), s->stream));
+    const uint32_t* perm = s->orders[s->order_of[f]].perm;
+    k_chamfer<<<nblk(n, 128), 128, 0, s->stream>>>(s->P, s->frame_ptr(f), perm, s->ch_target, s->ch_m, (float)weight, it->second.dev, it->second.ncols, s->ch_loss, 0); CKL(s);
+    k_chamfer<<<nblk((long long)s->B * s->ch_m, 128), 128, 0, s->stream>>>(s->P, s->frame_ptr(f), perm, s->ch_target, s->ch_m, (float)weight, it->second.dev, it->second.ncols, s->ch_loss, 1); CKL(s);
+    CK(cudaMemcpyAsync(loss_out, s->ch_loss, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return SMX_OK;
+}
+
 int smx_get_state_grad(smx_sim* s, int32_t f, double* out24) {
     TRY(check_frame(s, f, "smx_get_state_grad"));
     if (!out24) return fail(SMX_ERR_ARG, "smx_get_state_grad: null output");

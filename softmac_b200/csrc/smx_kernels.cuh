@@ -1081,6 +1081,73 @@ __global__ void k_sum_prim_grads(const double* __restrict__ pgrad, double* __res
     for (int f = f0; f < f1; f++) acc += src[(size_t)f * 13];
     out[t] = acc;
 }
+// ------------------------------------------------------------------------------------------------
+// Chamfer loss seeds on the device (softmac/engine/losses/loss_grip.py:45-68, GripLoss with weight (1,0,0)):
+//   loss = sum_i |x_i - t_nn(i)|^2 + sum_j |x_nn(j) - t_j|^2, nearest neighbours found by brute force with the reference's
+//   tie rule (strict <, scanning in index order => smallest index wins), held fixed in the gradient.
+// pass 0: one thread per particle slot, targets tiled through shared memory; pass 1: one thread per (batch, target).
+// seed: (n, ncols) AoS in particle-id order (the library's loss-seed buffer of the frame), accumulated with atomics.
+// ------------------------------------------------------------------------------------------------
+#define SMX_CH_TILE 512
+__global__ void __launch_bounds__(128) k_chamfer(Params P, const float* __restrict__ fr, const uint32_t* __restrict__ perm, const float* __restrict__ tgt, int m,
+                                                 float weight, float* __restrict__ seed, int ncols, double* __restrict__ loss, int pass) {
+    __shared__ float4 tile[SMX_CH_TILE];
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pass == 0) {
+        bool live = t < P.n;
+        int j = live ? t : P.n - 1;
+        float x = fr[j], y = fr[P.stride + j], z = fr[2 * P.stride + j];
+        float best = 3.0e38f; int bi = 0;
+        for (int base = 0; base < m; base += SMX_CH_TILE) {
+            int cnt = min(SMX_CH_TILE, m - base);
+            __syncthreads();
+            for (int e = threadIdx.x; e < cnt; e += blockDim.x) tile[e] = make_float4(tgt[3 * (base + e)], tgt[3 * (base + e) + 1], tgt[3 * (base + e) + 2], 0.f);
+            __syncthreads();
+            for (int e = 0; e < cnt; e++) {
+                float dx = x - tile[e].x, dy = y - tile[e].y, dz = z - tile[e].z;
+                float d = dx * dx + dy * dy + dz * dz;
+                if (d < best) { best = d; bi = base + e; }
+            }
+        }
+        float part = 0.f;
+        if (live) {
+            uint32_t id = perm ? perm[j] : (uint32_t)j;
+            float dx = x - tgt[3 * bi], dy = y - tgt[3 * bi + 1], dz = z - tgt[3 * bi + 2];
+            atomicAdd(seed + (size_t)id * ncols, 2.f * weight * dx); atomicAdd(seed + (size_t)id * ncols + 1, 2.f * weight * dy);
+            atomicAdd(seed + (size_t)id * ncols + 2, 2.f * weight * dz);
+            part = dx * dx + dy * dy + dz * dz;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if ((threadIdx.x & 31) == 0) atomicAdd(loss, (double)(weight * part));
+    } else {
+        // one thread per (batch, target): nearest particle of that batch; ties go to the smallest particle id
+        bool live = t < P.nbatch * m;
+        int tt = live ? t : 0;
+        int b = tt / m, i = tt - b * m;
+        float tx = tgt[3 * i], ty = tgt[3 * i + 1], tz = tgt[3 * i + 2];
+        float best = 3.0e38f; uint32_t bid = 0xffffffffu; int bj = 0;
+        int j0 = b * P.npb, j1 = j0 + P.npb;
+        {
+            for (int j = j0; j < j1; j++) {     // particle coordinates are read straight from the frame (L1/L2 resident, warp-uniform address)
+                float dx = fr[j] - tx, dy = fr[P.stride + j] - ty, dz = fr[2 * P.stride + j] - tz;
+                float d = dx * dx + dy * dy + dz * dz;
+                uint32_t id = perm ? perm[j] : (uint32_t)j;
+                if (d < best || (d == best && id < bid)) { best = d; bid = id; bj = j; }
+            }
+        }
+        float part = 0.f;
+        if (live && P.npb > 0) {
+            float dx = fr[bj] - tx, dy = fr[P.stride + bj] - ty, dz = fr[2 * P.stride + bj] - tz;
+            atomicAdd(seed + (size_t)bid * ncols, 2.f * weight * dx); atomicAdd(seed + (size_t)bid * ncols + 1, 2.f * weight * dy);
+            atomicAdd(seed + (size_t)bid * ncols + 2, 2.f * weight * dz);
+            part = dx * dx + dy * dy + dz * dz;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if ((threadIdx.x & 31) == 0) atomicAdd(loss, (double)(weight * part));
+    }
+}
 // Primitive.forward_kinematics and its adjoint (primitive_base.py:280-283, primitive_utils.py:20-40); one thread
 __global__ void k_forward_kinematics(float* __restrict__ pstate, int T, int np, int nbatch, int f, float dt) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;

@@ -52,3 +52,27 @@ class ChamferLoss:
         np.add.at(g, i_tar, 2 * d2)
         self.sim.add_x_grad(f, self.weight * g)
         return {"loss": self.weight * loss, "chamfer_loss": self.weight * loss}
+
+
+class DeviceChamferLoss:
+    """ChamferLoss evaluated on the GPU (smx_chamfer_loss): no device->host copy of x, no O(N^2) numpy; the seed goes straight
+    into the simulator's loss-seed buffer of frame f.  With a batched handle the loss is summed over the rollouts."""
+
+    def __init__(self, simulator, target, weight=1.0):
+        import ctypes as C
+        from .._capi import lib, check, as_d, d_ptr
+        self.sim, self.weight = simulator, float(weight)
+        t = as_d(np.asarray(target, dtype=np.float64)).reshape(-1, 3)
+        check(lib().smx_set_chamfer_target(simulator._h, d_ptr(t), len(t)))
+        self._C, self._lib, self._check = C, lib, check
+
+    def initialize(self):
+        pass
+
+    def reset(self):
+        pass
+
+    def compute_loss(self, f):
+        out = self._C.c_double()
+        self._check(self._lib().smx_chamfer_loss(self.sim._h, int(f), self.weight, self._C.byref(out)))
+        return {"loss": out.value, "chamfer_loss": out.value}
