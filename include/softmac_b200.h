@@ -166,10 +166,17 @@ int smx_substep_begin(smx_sim* sim, int32_t s);
 int smx_substep_end(smx_sim* sim, int32_t s);
 int smx_substep_grad_begin(smx_sim* sim, int32_t s);
 int smx_substep_grad_end(smx_sim* sim, int32_t s);
+/* With the forecast contact model a slab caller needs one more cut per direction: forward mid = grid update + contact
+ * scatter into g_out (then exchange g_out - g_mix on the halo, add the neighbour's part, call end); adjoint mid = contact
+ * adjoint (gathers the halo-complete gg_out, scatters gg_mix; then sum the gg_mix halo, call end).  Optional: end runs mid
+ * itself when the caller did not. */
+int smx_substep_mid(smx_sim* sim, int32_t s);
+int smx_substep_grad_mid(smx_sim* sim, int32_t s);
 /* Declares this handle one rank of an x-slab decomposition: it owns the x-block columns [xb_lo, xb_hi) (4 nodes per
  * column) and has neighbours on the flagged sides.  The halo columns {xb_lo-1, xb_lo} / {xb_hi-1, xb_hi} are kept active
  * every substep; the caller sums them with the neighbour's copies between begin and end (g_in forward, gg_out backward).
- * Call before smx_reset.  Particle migration between ranks is not implemented: particles whose stencil leaves the own
+ * Call before smx_reset.  Wrenches, primitive-state adjoints and action adjoints are per-rank partial sums (the caller
+ * all-reduces them).  Particle migration between ranks is not implemented: particles whose stencil leaves the own
  * slab + halo are counted in counters[1]. */
 int smx_set_slab(smx_sim* sim, int32_t xb_lo, int32_t xb_hi, int32_t has_lo_neighbour, int32_t has_hi_neighbour);
 /* device pointer / element count of a grid array: 0 g_in, 1 g_out, 2 g_mix, 3 gg_out, 4 gg_mix (float4 per node,

@@ -87,6 +87,8 @@ _SIGS = {
     "smx_substep_grad": [vp, C.c_int32],
     "smx_substep_begin": [vp, C.c_int32],
     "smx_substep_end": [vp, C.c_int32],
+    "smx_substep_mid": [vp, C.c_int32],
+    "smx_substep_grad_mid": [vp, C.c_int32],
     "smx_substep_grad_begin": [vp, C.c_int32],
     "smx_substep_grad_end": [vp, C.c_int32],
     "smx_set_slab": [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32],

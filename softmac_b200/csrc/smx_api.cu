@@ -123,7 +123,7 @@ struct smx_sim {
     // adjoint ping-pong
     float *adj_cur = nullptr, *adj_nxt = nullptr;
     int adj_frame = -1, adj_order = -1;
-    int grad_pending = -1;
+    int grad_pending = -1, mid_done = -1, grad_mid_done = -1;
     float* ch_target = nullptr; int ch_m = 0; double* ch_loss = nullptr;   // Chamfer target cloud (m,3) and loss accumulator
     int last_fwd = -1;
     long long g_in_clean_uid = -1;      // ordering whose active blocks of g_in are known to be zero (k_grid_op re-zeroes them)
@@ -384,14 +384,17 @@ static int forward_grid(smx_sim* s, int f, bool accumulate, bool checkpoint) {
         float life = 1.0f / (float)(P.substeps - f % P.substeps);      // mpm_simulator.py:425 (f32 in the reference too)
         k_contact<<<nblk(P.n, SMX_TPB), SMX_TPB, 0, s->stream>>>(P, ps, f, life, s->frame_ptr(f), s->g_mix, s->g_out, accumulate ? 1 : 0); CKLN(s, "k_contact");
     }
-    if (save) {
-        if (contact) {      // g_out is final only after the contact scatter
-            k_ckpt_copy<<<grid_blocks_launch(s), 256, 0, s->stream>>>(s->dense ? nullptr : o.blocks, o.nblocks, s->B * s->P.nb3, s->ckpt_cap, rec,
-                                                                     nullptr, s->g_out, s->g_mix, 0, s->counters);
-            CKLN(s, "ckpt_save");
-        }
-        s->ckpt_order[f] = o.uid; s->ckpt_contact[f] = contact;
-    }
+    if (save && !contact) { s->ckpt_order[f] = o.uid; s->ckpt_contact[f] = 0; }
+    return SMX_OK;
+}
+// with contact, g_out is final only after the contact scatter (and, in slab mode, after the halo exchange of that scatter)
+static int forward_grid_save_contact(smx_sim* s, int f) {
+    Order& o = s->orders[s->order_of[f]];
+    if (!(s->has_contact() && s->ckpt && s->ckpt_narr == 3)) return SMX_OK;
+    k_ckpt_copy<<<grid_blocks_launch(s), 256, 0, s->stream>>>(s->dense ? nullptr : o.blocks, o.nblocks, s->B * s->P.nb3, s->ckpt_cap, s->ckpt + (size_t)f * s->ckpt_rec,
+                                                             nullptr, s->g_out, s->g_mix, 0, s->counters);
+    CKLN(s, "ckpt_save");
+    s->ckpt_order[f] = o.uid; s->ckpt_contact[f] = 1;
     return SMX_OK;
 }
 // P2G + grid update + forecast contact of substep f (everything before G2P); shared by forward and adjoint
@@ -921,18 +924,28 @@ int smx_substep_begin(smx_sim* s, int32_t f) {
     TRY(check_frame(s, f, "smx_substep"));
     if (f + 1 >= s->cfg.max_steps) return fail(SMX_ERR_RANGE, "smx_substep: substep %d would write frame %d >= max_steps %d", f, f + 1, s->cfg.max_steps);
     if (s->order_of[f] < 0) return fail(SMX_ERR_STATE, "smx_substep: frame %d has not been written (call smx_reset / smx_set_frame first)", f);
-    if (s->slab && s->has_contact()) return fail(SMX_ERR_STATE, "smx_substep: slab decomposition does not yet exchange the forecast-contact scatter (disable contact or use one GPU)");
     CK(cudaSetDevice(s->cfg.device));
     s->order_of[f + 1] = s->order_of[f]; s->trans_from[f + 1] = -1;
     s->ckpt_order[f] = -1; s->ckpt_order[f + 1] = -1;
     if (s->ckpt_dirty) TRY(ensure_ckpt(s, f));
     return forward_p2g(s, f, true, true);
 }
+// grid update + contact scatter; separate from `end` so that a slab caller can exchange the contact scatter in between
+int smx_substep_mid(smx_sim* s, int32_t f) {
+    TRY(check_frame(s, f, "smx_substep"));
+    if (f + 1 >= s->cfg.max_steps || s->order_of[f] < 0 || s->order_of[f + 1] != s->order_of[f]) return fail(SMX_ERR_STATE, "smx_substep_mid: smx_substep_begin(%d) has not been called", f);
+    CK(cudaSetDevice(s->cfg.device));
+    TRY(forward_grid(s, f, true, true));
+    s->mid_done = f;
+    return SMX_OK;
+}
 int smx_substep_end(smx_sim* s, int32_t f) {
     TRY(check_frame(s, f, "smx_substep"));
     if (f + 1 >= s->cfg.max_steps || s->order_of[f] < 0 || s->order_of[f + 1] != s->order_of[f]) return fail(SMX_ERR_STATE, "smx_substep_end: smx_substep_begin(%d) has not been called", f);
     CK(cudaSetDevice(s->cfg.device));
-    TRY(forward_grid(s, f, true, true));
+    if (s->mid_done != f) TRY(smx_substep_mid(s, f));
+    s->mid_done = -1;
+    TRY(forward_grid_save_contact(s, f));
     s->last_fwd = f;
     if (s->P.n > 0) { k_g2p<<<nblk(s->P.n, SMX_TPB), SMX_TPB, 0, s->stream>>>(s->P, s->frame_ptr(f), s->frame_ptr(f + 1), s->g_out); CKLN(s, "k_g2p"); }
     if (s->cfg.sort_every > 0 && (f + 1) % s->cfg.sort_every == 0 && !(s->cfg.flags & SMX_FLAG_NO_SORT)) TRY(resort(s, f + 1, true));
@@ -994,17 +1007,29 @@ int smx_substep_grad_begin(smx_sim* s, int32_t f) {
         else k_g2p_grad<true><<<nblk(P.n, SMX_TPB_SC), SMX_TPB_SC, 0, s->stream>>>(P, fin, s->adj_cur, s->adj_nxt, s->g_out, s->gg_out);
         CKLN(s, "k_g2p_grad");
     }
-    if (contact && P.n > 0) {
-        float life = 1.0f / (float)(P.substeps - f % P.substeps);
-        k_contact_grad<<<nblk(P.n, SMX_TPB), SMX_TPB, 0, s->stream>>>(P, ps, f, life, fin, s->adj_nxt, s->g_mix, s->gg_out, s->gg_mix); CKLN(s, "k_contact_grad");
-    }
     s->grad_pending = f;
+    (void)ps;
+    return SMX_OK;
+}
+// adjoint of the forecast contact: gathers gg_out (complete after the slab caller's halo sum), scatters into gg_mix
+int smx_substep_grad_mid(smx_sim* s, int32_t f) {
+    TRY(check_frame(s, f, "smx_substep_grad"));
+    if (s->grad_pending != f) return fail(SMX_ERR_STATE, "smx_substep_grad_mid: smx_substep_grad_begin(%d) has not been called", f);
+    CK(cudaSetDevice(s->cfg.device));
+    const Params& P = s->P;
+    if (s->has_contact() && P.n > 0) {
+        PrimSet ps = s->primset();
+        float life = 1.0f / (float)(P.substeps - f % P.substeps);
+        k_contact_grad<<<nblk(P.n, SMX_TPB), SMX_TPB, 0, s->stream>>>(P, ps, f, life, s->frame_ptr(f), s->adj_nxt, s->g_mix, s->gg_out, s->gg_mix); CKLN(s, "k_contact_grad");
+    }
+    s->grad_mid_done = f;
     return SMX_OK;
 }
 int smx_substep_grad_end(smx_sim* s, int32_t f) {
     TRY(check_frame(s, f, "smx_substep_grad"));
     if (s->grad_pending != f) return fail(SMX_ERR_STATE, "smx_substep_grad_end: smx_substep_grad_begin(%d) has not been called", f);
-    s->grad_pending = -1;
+    if (s->grad_mid_done != f) TRY(smx_substep_grad_mid(s, f));
+    s->grad_pending = -1; s->grad_mid_done = -1;
     CK(cudaSetDevice(s->cfg.device));
     const Params& P = s->P;
     int o = s->order_of[f];

@@ -13,9 +13,13 @@ Both ranks then hold identical, complete values on the shared columns (a + b == 
 no second (broadcast) exchange is needed.  Transport: ``torch.distributed`` P2P (NCCL over NVLink) with one process per
 GPU, or plain tensor adds for several ranks emulated in one process (tests on a single GPU).
 
+With the forecast contact model two more halo operations are needed: the contact kernel scatters velocity corrections
+into g_out, so after it every rank adds the neighbour's part of (g_out - g_mix) on the halo; in the adjoint the contact
+kernel gathers gg_out (complete after the first halo sum) and scatters into gg_mix, whose halo is then summed too.
+Wrenches and primitive-state adjoints are per-rank partial sums and are reduced when read.
+
 Not implemented in round 1: particle migration between ranks (ownership is fixed at reset; a particle may drift up
-to two cells out of its slab before the counters flag it), and the exchange of the forecast-contact scatter (slab mode
-refuses contact-enabled primitives with collision_type 2).
+to two cells out of its slab before the counters flag it).
 """
 import ctypes as C
 
@@ -50,7 +54,7 @@ def choose_bounds(x, n_ranks, n_grid):
 class SlabRank:
     """One rank: a simulator over the particles of its slab."""
 
-    def __init__(self, cfg, rank, bounds, state, device=0, use_torch_stream=True, **sim_kw):
+    def __init__(self, cfg, rank, bounds, state, device=0, use_torch_stream=True, primitives=(), **sim_kw):
         import copy
         import torch
         from .engine.mpm_simulator import MPMSimulator
@@ -67,7 +71,8 @@ class SlabRank:
         # run on torch's current stream so that the halo sums / NCCL P2P (torch ops) are ordered with the kernels
         stream = torch.cuda.current_stream(device).cuda_stream if use_torch_stream else None
         flags = sim_kw.pop("flags", 0) | (SMX_FLAG_EXTERNAL_STREAM if use_torch_stream else 0)
-        self.sim = MPMSimulator(c, (), device=device, stream=stream or None, flags=flags, **sim_kw)
+        self.primitives = primitives
+        self.sim = MPMSimulator(c, primitives, device=device, stream=stream or None, flags=flags, **sim_kw)
         check(lib().smx_set_slab(self.sim._h, self.lo, self.hi, int(rank > 0), int(rank < self.n_ranks - 1)))
         self.sim.reset(st[self.ids] if st.shape[1] == 24 else st[self.ids, :3])
         self._views = {}
@@ -98,6 +103,15 @@ class SlabRank:
     def grad_end(self, f):
         check(lib().smx_substep_grad_end(self.sim._h, int(f)))
 
+    def mid(self, f):
+        check(lib().smx_substep_mid(self.sim._h, int(f)))
+
+    def grad_mid(self, f):
+        check(lib().smx_substep_grad_mid(self.sim._h, int(f)))
+
+    def has_contact(self):
+        return self.sim.collision_type == 2 and any(self.sim.primitives_contact)
+
     def scatter_to_global(self, local, n_global):
         out = np.zeros((n_global,) + local.shape[1:])
         out[self.ids] = local
@@ -107,11 +121,13 @@ class SlabRank:
 class SlabCluster:
     """All ranks emulated in ONE process on one device (tests / single-GPU use): same phases, halos summed directly."""
 
-    def __init__(self, cfg, n_ranks, state, device=0, **sim_kw):
+    def __init__(self, cfg, n_ranks, state, device=0, make_primitives=None, **sim_kw):
+        """make_primitives() -> a fresh Primitives container (every rank needs its own, bound to its handle)."""
         n_grid = int(128 * cfg.quality * 0.5)
         self.n = len(state)
         self.bounds = choose_bounds(np.asarray(state)[:, 0], n_ranks, n_grid)
-        self.ranks = [SlabRank(cfg, r, self.bounds, state, device=device, **sim_kw) for r in range(n_ranks)]
+        self.ranks = [SlabRank(cfg, r, self.bounds, state, device=device, primitives=make_primitives() if make_primitives else (), **sim_kw)
+                      for r in range(n_ranks)]
 
     def _exchange(self, which):
         for r in range(len(self.ranks) - 1):
@@ -119,19 +135,56 @@ class SlabCluster:
             t = a + b
             a.copy_(t); b.copy_(t)
 
+    def _exchange_contact(self):
+        for r in range(len(self.ranks) - 1):
+            L, R = self.ranks[r], self.ranks[r + 1]
+            da = L.halo(1, "hi") - L.halo(2, "hi")          # own contact scatter = g_out - g_mix
+            db = R.halo(1, "lo") - R.halo(2, "lo")
+            L.halo(1, "hi").add_(db); R.halo(1, "lo").add_(da)
+
     def substep(self, f):
+        contact = self.ranks[0].has_contact()
         for r in self.ranks:
             r.begin(f)
         self._exchange(0)
+        if contact:
+            for r in self.ranks:
+                r.mid(f)
+            self._exchange_contact()
         for r in self.ranks:
             r.end(f)
 
     def substep_grad(self, f):
+        contact = self.ranks[0].has_contact()
         for r in self.ranks:
             r.grad_begin(f)
         self._exchange(3)
+        if contact:
+            for r in self.ranks:
+                r.grad_mid(f)
+            self._exchange(4)
         for r in self.ranks:
             r.grad_end(f)
+
+    # reductions over ranks of the per-rank partial sums
+    def set_primitive_state(self, i, f0, f1, s13):
+        for r in self.ranks:
+            r.primitives[i].set_all_states(f0, s13, f_end=f1)
+
+    def clear_ext_f(self):
+        for r in self.ranks:
+            for p in r.primitives:
+                p.clear_ext_f()
+
+    def ext_f(self, i):
+        return sum(r.primitives[i].get_ext_f() for r in self.ranks)
+
+    def set_ext_f_grad(self, i, g):
+        for r in self.ranks:
+            r.primitives[i].set_ext_f_grad(g)
+
+    def primitive_state_grad(self, i, f0, f1):
+        return sum(r.primitives[i].get_all_states_grad(f0, f_end=f1) for r in self.ranks)
 
     def get_state(self, f):
         out = np.zeros((self.n, 24))
@@ -156,7 +209,7 @@ class SlabCluster:
 class DistSlab:
     """One rank per process (torchrun, NCCL): this process's slab + P2P halo exchange with its x-neighbours."""
 
-    def __init__(self, cfg, state, device=None, **sim_kw):
+    def __init__(self, cfg, state, device=None, make_primitives=None, **sim_kw):
         import torch
         import torch.distributed as dist
         self.dist = dist
@@ -165,7 +218,8 @@ class DistSlab:
         n_grid = int(128 * cfg.quality * 0.5)
         self.n = len(state)
         self.bounds = choose_bounds(np.asarray(state)[:, 0], self.world, n_grid)     # deterministic: same on every rank
-        self.r = SlabRank(cfg, self.rank, self.bounds, state, device=self.device, **sim_kw)
+        self.r = SlabRank(cfg, self.rank, self.bounds, state, device=self.device, primitives=make_primitives() if make_primitives else (), **sim_kw)
+        self.primitives = self.r.primitives
         self.sim = self.r.sim
         self._tmp = {}
 
@@ -184,15 +238,49 @@ class DistSlab:
             for v, t in pend:
                 v.add_(t)
 
+    def _exchange_contact(self):
+        import torch
+        dist, ops, pend = self.dist, [], []
+        for side, peer in (("lo", self.rank - 1), ("hi", self.rank + 1)):
+            if 0 <= peer < self.world:
+                own = self.r.halo(1, side) - self.r.halo(2, side)        # own contact scatter = g_out - g_mix
+                t = self._tmp.setdefault(("c", side), torch.empty_like(own))
+                ops += [dist.P2POp(dist.isend, own, peer), dist.P2POp(dist.irecv, t, peer)]
+                pend.append((self.r.halo(1, side), t))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+            for v, t in pend:
+                v.add_(t)
+
     def substep(self, f):
         self.r.begin(f)
         self._exchange(0)
+        if self.r.has_contact():
+            self.r.mid(f)
+            self._exchange_contact()
         self.r.end(f)
 
     def substep_grad(self, f):
         self.r.grad_begin(f)
         self._exchange(3)
+        if self.r.has_contact():
+            self.r.grad_mid(f)
+            self._exchange(4)
         self.r.grad_end(f)
+
+    def _allreduce(self, a):
+        import torch
+        t = torch.as_tensor(np.asarray(a, dtype=np.float64), device=f"cuda:{self.device}")
+        self.dist.all_reduce(t)
+        return t.cpu().numpy()
+
+    def ext_f(self, i):
+        """Contact wrench on primitive i summed over the ranks (each rank accumulates its own particles' reactions)."""
+        return self._allreduce(self.primitives[i].get_ext_f())
+
+    def primitive_state_grad(self, i, f0, f1):
+        return self._allreduce(self.primitives[i].get_all_states_grad(f0, f_end=f1))
 
     def step(self, s0, count):
         for f in range(s0, s0 + count):

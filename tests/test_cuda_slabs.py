@@ -50,3 +50,48 @@ def test_choose_bounds_balances_particles():
     for R in (2, 4, 8):
         b = choose_bounds(x, R, 256)
         assert b[0] == 0 and b[-1] == 64 and all(b[i + 1] - b[i] >= 2 for i in range(R))
+
+
+def test_slab_cluster_with_forecast_contact_across_the_boundary():
+    """A sphere primitive sitting on the slab boundary: the contact scatter into g_out and its adjoint are exchanged, the
+    wrench and the primitive-state adjoint are sums over ranks -- all equal to the single-handle run."""
+    from softmac_b200.engine import MPMSimulator, Primitives, Mesh
+    from softmac_b200.slabs import SlabCluster
+    rng = np.random.default_rng(23)
+    n, steps, n_grid = 12000, 6, 64
+    center = np.array([0.5, 0.3, 0.5])
+    st = scenes.contact_rollout_state(n, rng, center, width=0.16)
+    tab = scenes.sphere_table()
+    cfg = sim_cfg(n, n_grid=n_grid, max_steps=steps + 2)
+    s13 = np.concatenate([center, [1, 0, 0, 0], [0.0, 0.2, 0.0], [0, 0, 0.3]])
+
+    def make_prims():
+        m = Mesh(sdf=dict(sdf=tab["sdf"], normal=tab["normal"], position=(tab["lower"], tab["upper"]), dx=tab["dx"]), cfg=dict(friction=0.5),
+                 max_timesteps=steps + 2)
+        p = Primitives(primitives=[m], max_timesteps=steps + 2)
+        p.initialize()
+        return p
+
+    pr = make_prims()
+    ref = MPMSimulator(cfg, pr, env_dt=1e-3, sort_every=3)
+    pr[0].set_all_states(0, s13, f_end=steps + 2)
+    ref.reset(st); pr[0].clear_ext_f()
+    clu = SlabCluster(cfg, 2, st, make_primitives=make_prims, env_dt=1e-3, sort_every=3)
+    b = clu.bounds[1] * 4 / n_grid
+    assert abs(b - 0.5) < 0.05                                     # the boundary cuts through the contact region
+    clu.set_primitive_state(0, 0, steps + 2, s13); clu.clear_ext_f()
+    for f in range(steps):
+        ref.substep(f); clu.substep(f)
+    a, r = clu.get_state(steps), ref.get_state(steps)
+    assert rel_l2(a[:, :3], r[:, :3]) <= 1e-6 and rel_l2(a[:, 3:6], r[:, 3:6]) <= 5e-5
+    fe = pr[0].get_ext_f()
+    assert np.abs(fe).max() > 0 and rel_l2(clu.ext_f(0), fe) <= 1e-4
+    g = rng.normal(size=(n, 3)); ext = rng.normal(size=6) * 1e-3
+    ref.clear_all_gradients(); ref.add_x_grad(steps, g); clu.add_x_grad(steps, g)
+    for f in range(steps - 1, -1, -1):
+        ref.substep_grad(f, ext_f_grad=[ext])
+        clu.set_ext_f_grad(0, ext); clu.substep_grad(f)
+    ga, gb = clu.get_state_grad(0), ref.get_state_grad(0)
+    assert rel_l2(ga, gb) <= 2e-4 and cosine(ga, gb) >= 0.99999
+    pa, pb = clu.primitive_state_grad(0, 0, steps), pr[0].get_all_states_grad(0, f_end=steps)
+    assert np.abs(pb).max() > 0 and rel_l2(pa, pb) <= 1e-3
