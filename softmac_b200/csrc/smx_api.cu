@@ -539,6 +539,16 @@ int smx_create(const smx_config* cfg, smx_sim** out) {
     CK(cudaMalloc(&s->action, nc * 3 * sizeof(float))); CK(cudaMemsetAsync(s->action, 0, nc * 3 * sizeof(float), s->stream));
     CK(cudaMalloc(&s->action_grad, nc * 3 * sizeof(double))); CK(cudaMemsetAsync(s->action_grad, 0, nc * 3 * sizeof(double), s->stream));
     CK(cudaEventCreate(&s->ev0)); CK(cudaEventCreate(&s->ev1));
+    {   // the staged scatter kernels want 8 CTAs x 28 KB of shared memory per SM: ask for the largest carve-out
+        int co = cudaSharedmemCarveoutMaxShared;
+        cudaFuncSetAttribute(k_p2g<0, true>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+        cudaFuncSetAttribute(k_p2g<1, true>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+        cudaFuncSetAttribute(k_p2g<2, true>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+        cudaFuncSetAttribute(k_p2g<4, true>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+        cudaFuncSetAttribute(k_p2g<5, true>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+        cudaFuncSetAttribute(k_g2p_grad<true>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+        cudaGetLastError();
+    }
     CK(cudaStreamSynchronize(s->stream));
     *out = s;
     return SMX_OK;

@@ -72,7 +72,7 @@ __device__ __forceinline__ uint32_t node_index(int i, int j, int k, int nb);
 struct WarpStage {
     float4 val[32 * 27];    // [lane][offset]; row stride 27 float4 -> conflict-free 128-bit stores
     uint32_t key[32];       // packed base cell of each run
-    uint32_t start[33];     // first lane of each run (+ sentinel)
+    uint8_t start[36];      // first lane of each run (+ sentinel); bytes, so that 8 CTAs x 2 warps fit the 227 KB of an SM
 };
 __device__ __forceinline__ uint32_t pack_base(int bx, int by, int bz, int bt = 0) { return (uint32_t)bx | ((uint32_t)by << 8) | ((uint32_t)bz << 16) | ((uint32_t)bt << 24); }
 
@@ -91,7 +91,7 @@ __device__ __forceinline__ void warp_stage_flush(WarpStage& st, uint32_t key, bo
     unsigned heads = __ballot_sync(0xffffffffu, head);
     int nruns = __popc(heads);
     int rank = __popc(heads & ((1u << lane) - 1u));
-    if (head) { st.start[rank] = lane; st.key[rank] = k; }
+    if (head) { st.start[rank] = (uint8_t)lane; st.key[rank] = k; }
     if (lane == 0) st.start[nruns] = 32;
     __syncwarp();
     int ntasks = nruns * 27;
