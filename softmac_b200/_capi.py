@@ -123,10 +123,16 @@ def lib():
     """Load (once) and return the shared library.  Never falls back to a CPU implementation."""
     global _lib
     if _lib is None:
+        if not os.path.exists(LIB_PATH) and not os.environ.get("SMX_LIB"):
+            try:                            # a fresh checkout: compile the CUDA library in-tree (never a CPU substitute)
+                from . import build as _build
+                _build.build()
+            except Exception as e:          # noqa: BLE001
+                raise ImportError(
+                    f"{LIB_PATH} is missing and could not be built ({e}); build it with `python -m softmac_b200.build` "
+                    "(nvcc, sm_100a). softmac_b200 has no CPU fallback.") from e
         if not os.path.exists(LIB_PATH):
-            raise ImportError(
-                f"{LIB_PATH} is missing: build it with `python -m softmac_b200.build` (nvcc, sm_100a). "
-                "softmac_b200 has no CPU fallback.")
+            raise ImportError(f"{LIB_PATH} is missing. softmac_b200 has no CPU fallback.")
         L = C.CDLL(LIB_PATH)
         for name, args in _SIGS.items():
             fn = getattr(L, name)
