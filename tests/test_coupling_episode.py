@@ -85,3 +85,59 @@ def test_episode_action_gradient_cosine():
     c = cosine(gg, go)
     assert np.abs(go).max() > 0 and c >= 0.999, (c, gg, go)
     assert rel_l2(gg, go) <= 2e-2
+
+
+def build_pour(backend, n=3000, env_steps=10):
+    """demo_pour-shaped coupling (softmac/config/demo_pour_config.py:8-29,57-67): liquid (ptype 2, co-rotated), env_dt == dt so
+    substeps = 1 (life = 1, rigid coupling after EVERY substep), a free-floating "glass" that feels the contact wrench and a
+    "bowl" with enable_external_force = False (its wrench is ignored, rigid_simulator.py:96), 6-dof force/torque actions."""
+    from softmac_b200.engine.taichi_env import TaichiEnv
+    from softmac_b200.engine.rigid_simulator import RigidSimulator
+    from softmac_b200.engine.losses import PointwiseLoss
+    from softmac_b200.config import CfgNode
+    rng = np.random.default_rng(9)
+    n_grid, dt, substeps = 32, 2e-4, 1
+    max_steps = env_steps + 3
+    c = np.array([0.5, 0.3, 0.5])
+    x = scenes.contact_rollout_state(n, rng, c, radius=0.06, width=0.08, speed=0.3)[:, :3]
+    tab = scenes.sphere_table(radius=0.06, dx=0.01, margin=0.04)
+    tab32 = {k: (np.asarray(v, dtype=np.float32).astype(np.float64) if k in ("sdf", "normal", "lower", "upper") else v) for k, v in tab.items()}
+    params = [(0.1, 666.), (1.0, 666.)]                     # glass, bowl friction (demo_pour_config.py:57-67)
+    kw = dict(E=3e3, nu=0.2, gravity=(0., -9.8, 0.), ground_friction=0., material_model=0, ptype=2, collision_type=2)
+    if backend == "oracle":
+        from oracle_backend import OracleMPMSimulator
+        sim = OracleMPMSimulator(n, n_grid, max_steps, dt, substeps, tables=[tab32, tab32], prim_params=params, **kw)
+        prims = sim.primitives
+        prims[1].enable_external_force = False
+    else:
+        from softmac_b200.engine import MPMSimulator, Primitives, Mesh
+        ms = [Mesh(sdf=dict(sdf=tab32["sdf"], normal=tab32["normal"], position=(tab32["lower"], tab32["upper"]), dx=tab["dx"]),
+                   cfg=dict(friction=fr, enable_external_force=(i == 0)), max_timesteps=max_steps) for i, (fr, so) in enumerate(params)]
+        prims = Primitives(primitives=ms, max_timesteps=max_steps)
+        cfg = sim_cfg(n, n_grid=n_grid, max_steps=max_steps, dt=dt, ground_friction=0., ptype=2)
+        sim = MPMSimulator(cfg, prims, env_dt=dt)
+        assert sim.substeps == 1
+        prims.initialize()
+    bodies = [dict(joint="free", origin=tuple(c), mass=2.2687, inertia=0.02, gravity=False),
+              dict(joint="free", origin=tuple(c + [0.0, -0.2, 0.0]), mass=4.0084, inertia=0.05, gravity=False)]
+    rcfg = CfgNode(gravity=(0., 0., 0.), init_state=(), bodies=bodies)
+    rigid = RigidSimulator(rcfg, prims, substeps=substeps, env_dt=dt)
+    env = TaichiEnv(sim, prims, rigid, x, loss=PointwiseLoss(sim, x + np.array([0.0, -0.01, 0.0])), control_mode="rigid")
+    return env
+
+
+@pytest.mark.gpu
+def test_pour_like_episode_action_gradient_cosine():
+    env_steps = 10
+    rng = np.random.default_rng(4)
+    actions = np.zeros((env_steps, 12))
+    actions[:, :6] = np.array([0.02, 0.0, 0.05, 0.0, 30.0, 0.0]) * (1 + 0.1 * rng.normal(size=(env_steps, 6)))    # torque(3), force(3) on the glass
+    frames = [env_steps, env_steps - 4]
+    lo, go, ro, so = run_episode(build_pour("oracle", env_steps=env_steps), actions, frames)
+    lg, gg, rg, sg = run_episode(build_pour("cuda", env_steps=env_steps), actions, frames)
+    assert abs(lg - lo) <= 1e-4 * abs(lo)
+    assert rel_l2(rg, ro) <= 1e-5 and rel_l2(sg[:, :3], so[:, :3]) <= 1e-5
+    assert np.abs(ro[:6]).max() > 0                       # the glass moved (actions + contact wrench), the bowl's wrench was ignored
+    assert np.abs(go[:, :6]).max() > 0 and np.abs(go[:, 6:]).max() == 0 and np.abs(gg[:, 6:]).max() == 0
+    c = cosine(gg[:, :6], go[:, :6])
+    assert c >= 0.999, (c, gg[:, :6], go[:, :6])
