@@ -75,6 +75,7 @@ typedef struct {
 #define SMX_FLAG_NO_GRID_CKPT 8    /* adjoint re-runs P2G + grid update instead of restoring the per-substep grid checkpoint */
 #define SMX_FLAG_EXTERNAL_STREAM 16 /* run on smx_config.stream even when it is NULL (the legacy default stream): lets torch ops on the
                                      same stream interleave with the kernels without extra synchronisation (slab halo exchange) */
+#define SMX_FLAG_NO_FUSION 32       /* smx_step launches G2P and the next P2G separately instead of the fused G2P2G kernel */
 #define SMX_FLAG_DIRECT_RED 4     /* one L2 reduction per particle and node instead of the warp-aggregated scatter (ablation) */
 
 /* lifetime ------------------------------------------------------------------------------------- */

@@ -343,10 +343,12 @@ static int ensure_ckpt(smx_sim* s, int f) {
     return SMX_OK;
 }
 
-static int forward_p2g(smx_sim* s, int f, bool write_F, bool accumulate) {
+static int forward_p2g(smx_sim* s, int f, bool write_F, bool accumulate, bool fuse_prev_g2p = false) {
     const Params& P = s->P;
     Order& o = s->orders[s->order_of[f]];
-    const float* fin = s->frame_ptr(f);
+    float* fin = s->frame_ptr(f);
+    const float* fprev = fuse_prev_g2p ? s->frame_ptr(f - 1) : nullptr;
+    const float4* gprev = fuse_prev_g2p ? s->g_out : nullptr;
     float* fout = write_F ? s->frame_ptr(f + 1) : nullptr;
     PrimSet ps = s->primset();
     const int* cslot = nullptr;
@@ -358,9 +360,9 @@ static int forward_p2g(smx_sim* s, int f, bool write_F, bool accumulate) {
     }
     if (P.n > 0) {
         TRY(dispatch_mat(P.material, P.ptype, [&](auto mat) {
-            if (s->cfg.flags & SMX_FLAG_DIRECT_RED) k_p2g<decltype(mat)::value, false><<<nblk(P.n, SMX_TPB_SC), SMX_TPB_SC, 0, s->stream>>>(P, ps, f, fin, fout, s->g_in, cslot, s->action, accumulate ? 1 : 0);
-            else k_p2g<decltype(mat)::value, true><<<nblk(P.n, SMX_TPB_SC), SMX_TPB_SC, 0, s->stream>>>(P, ps, f, fin, fout, s->g_in, cslot, s->action, accumulate ? 1 : 0);
-            CKLN(s, "k_p2g"); return (int)SMX_OK;
+            if (s->cfg.flags & SMX_FLAG_DIRECT_RED) k_p2g<decltype(mat)::value, false><<<nblk(P.n, SMX_TPB_SC), SMX_TPB_SC, 0, s->stream>>>(P, ps, f, fin, fout, s->g_in, cslot, s->action, accumulate ? 1 : 0, fprev, gprev);
+            else k_p2g<decltype(mat)::value, true><<<nblk(P.n, SMX_TPB_SC), SMX_TPB_SC, 0, s->stream>>>(P, ps, f, fin, fout, s->g_in, cslot, s->action, accumulate ? 1 : 0, fprev, gprev);
+            CKLN(s, fprev ? "k_g2p2g" : "k_p2g"); return (int)SMX_OK;
         }));
     }
     if (write_F && s->cfg.rigid_velocity_control && !s->prims.empty()) {
@@ -1095,8 +1097,40 @@ int smx_stream(smx_sim* s, void** stream) {
     return SMX_OK;
 }
 
+// `count` consecutive substeps.  Between two substeps that share an ordering the G2P of the first is fused into the P2G
+// of the second ("G2P2G": one launch, frame f's x, v, C go from registers straight into the next scatter); results are
+// identical to calling smx_substep in a loop.  Disabled by SMX_FLAG_NO_FUSION, in slab mode and with velocity control.
 int smx_step(smx_sim* s, int32_t s0, int32_t count) {
-    for (int i = 0; i < count; i++) TRY(smx_substep(s, s0 + i));
+    if (!s) return fail(SMX_ERR_ARG, "smx_step: null simulator");
+    bool fuse_ok = !(s->cfg.flags & SMX_FLAG_NO_FUSION) && !s->slab && !s->cfg.rigid_velocity_control && s->P.n > 0;
+    if (!fuse_ok || count < 2) {
+        for (int i = 0; i < count; i++) TRY(smx_substep(s, s0 + i));
+        return SMX_OK;
+    }
+    bool pending_g2p = false;           // G2P of substep f-1 still to be done (fused into the P2G of f)
+    for (int i = 0; i < count; i++) {
+        int f = s0 + i;
+        if (!pending_g2p) TRY(smx_substep_begin(s, f));
+        else {
+            // the part of smx_substep_begin after the checks, with the previous G2P folded into the P2G launch
+            TRY(check_frame(s, f, "smx_step"));
+            if (f + 1 >= s->cfg.max_steps) return fail(SMX_ERR_RANGE, "smx_step: substep %d would write frame %d >= max_steps %d", f, f + 1, s->cfg.max_steps);
+            CK(cudaSetDevice(s->cfg.device));
+            s->order_of[f + 1] = s->order_of[f]; s->trans_from[f + 1] = -1;
+            s->ckpt_order[f] = -1; s->ckpt_order[f + 1] = -1;
+            TRY(forward_p2g(s, f, true, true, true));
+            pending_g2p = false;
+        }
+        TRY(smx_substep_mid(s, f));
+        s->mid_done = -1;
+        TRY(forward_grid_save_contact(s, f));
+        s->last_fwd = f;
+        bool resort_next = s->cfg.sort_every > 0 && (f + 1) % s->cfg.sort_every == 0 && !(s->cfg.flags & SMX_FLAG_NO_SORT);
+        bool last = (i == count - 1);
+        if (!last && !resort_next && f + 2 < s->cfg.max_steps && !s->ckpt_dirty) { pending_g2p = true; continue; }
+        k_g2p<<<nblk(s->P.n, SMX_TPB), SMX_TPB, 0, s->stream>>>(s->P, s->frame_ptr(f), s->frame_ptr(f + 1), s->g_out); CKLN(s, "k_g2p");
+        if (resort_next) TRY(resort(s, f + 1, true));
+    }
     return SMX_OK;
 }
 int smx_step_grad(smx_sim* s, int32_t s1, int32_t count) {

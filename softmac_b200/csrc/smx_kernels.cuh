@@ -277,21 +277,66 @@ __device__ __forceinline__ V3 particle_impulses(const Params& P, const PrimSet& 
     return imp;
 }
 
+// G2P gather of one particle (mpm_simulator.py:299-318): new velocity and APIC matrix from the 27 nodes of its stencil
+__device__ __forceinline__ void g2p_gather(const Params& P, const Stencil& s, const float4* __restrict__ g_out, V3& nv, M3& Cn) {
+    nv = v3(0, 0, 0);
+    M3 B = m3_zero();       // sum w g (x) offset
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int b = 0; b < 3; b++) {
+            // row sums over c first: R0 = sum wz g, Rz = sum c wz g
+            const float4* gp = g_out + (s.ox[a] + s.oy[b]);
+            float4 g0 = gp[s.oz[0]], g1 = gp[s.oz[1]], g2 = gp[s.oz[2]];
+            float w1 = s.wz[1], w2 = s.wz[2], w0 = s.wz[0];
+            V3 R0 = v3(fmaf(w2, g2.x, fmaf(w1, g1.x, w0 * g0.x)), fmaf(w2, g2.y, fmaf(w1, g1.y, w0 * g0.y)), fmaf(w2, g2.z, fmaf(w1, g1.z, w0 * g0.z)));
+            V3 Rz = v3(fmaf(2.f * w2, g2.x, w1 * g1.x), fmaf(2.f * w2, g2.y, w1 * g1.y), fmaf(2.f * w2, g2.z, w1 * g1.z));
+            float wab = s.wx[a] * s.wy[b];
+            V3 r0 = wab * R0;
+            nv += r0;
+            if (a) { B.m[0] += a * r0.x; B.m[3] += a * r0.y; B.m[6] += a * r0.z; }
+            if (b) { B.m[1] += b * r0.x; B.m[4] += b * r0.y; B.m[7] += b * r0.z; }
+            B.m[2] = fmaf(wab, Rz.x, B.m[2]); B.m[5] = fmaf(wab, Rz.y, B.m[5]); B.m[8] = fmaf(wab, Rz.z, B.m[8]);
+        }
+    float k4 = 4.f * P.inv_dx;
+    float f3[3] = {s.fx, s.fy, s.fz}, n3[3] = {nv.x, nv.y, nv.z};
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) Cn.m[3 * r + c] = k4 * (B.m[3 * r + c] - n3[r] * f3[c]);
+}
+
 // ------------------------------------------------------------------------------------------------
 // P2G: F_tmp, SVD, plasticity, stress, APIC scatter.  One thread per particle slot.
+// FUSED: the G2P of the PREVIOUS substep runs first in the same thread ("G2P2G"): x, v, C of frame f are produced from
+// frame f-1 and g_out, written to the checkpoint, and consumed from registers (fprev / g_prev non-null).
 // STAGED: warp-aggregated scatter through shared memory (default); otherwise one REDG per node.
 // ------------------------------------------------------------------------------------------------
 template <int MAT, bool STAGED>
-__global__ void __launch_bounds__(SMX_TPB_SC, 8) k_p2g(Params P, PrimSet ps, int f, const float* __restrict__ fin, float* __restrict__ fout,
+__global__ void __launch_bounds__(SMX_TPB_SC, 8) k_p2g(Params P, PrimSet ps, int f, float* __restrict__ fin, float* __restrict__ fout,
                                                     float4* __restrict__ g_in, const int* __restrict__ ctrl_slot,
-                                                    const float* __restrict__ action, int accumulate) {
+                                                    const float* __restrict__ action, int accumulate,
+                                                    const float* __restrict__ fprev, const float4* __restrict__ g_prev) {
     __shared__ WarpStage stage[STAGED ? SMX_TPB_SC / 32 : 1];
     int j = blockIdx.x * SMX_TPB_SC + threadIdx.x;
     bool live = j < P.n;
     int jj = live ? j : P.n - 1;
     V3 x, v; M3 F, C;
-    load_state(fin, P.stride, jj, x, v, F, C);
     int bt = batch_of(P, jj);
+    if (fprev) {        // fused G2P of substep f-1: frame f-1 -> x, v, C of frame f
+        V3 xo = v3(fprev[jj], fprev[P.stride + jj], fprev[2 * P.stride + jj]);
+        Stencil so = make_stencil(xo.x, xo.y, xo.z, P, bt);
+        g2p_gather(P, so, g_prev, v, C);
+        x = xo + P.dt * v;
+#pragma unroll
+        for (int i = 0; i < 9; i++) F.m[i] = fin[(6 + i) * P.stride + jj];
+        if (live) {
+            fin[j] = x.x; fin[P.stride + j] = x.y; fin[2 * P.stride + j] = x.z;
+            fin[3 * P.stride + j] = v.x; fin[4 * P.stride + j] = v.y; fin[5 * P.stride + j] = v.z;
+#pragma unroll
+            for (int i = 0; i < 9; i++) fin[(15 + i) * P.stride + j] = C.m[i];
+        }
+    } else load_state(fin, P.stride, jj, x, v, F, C);
     V3 imp = particle_impulses(P, ps, f, jj, bt, live, x, v, ctrl_slot, action, accumulate != 0);
     Stencil s = make_stencil(x.x, x.y, x.z, P, bt);
     if (live) {
@@ -467,31 +512,10 @@ __global__ void __launch_bounds__(SMX_TPB) k_g2p(Params P, const float* __restri
     if (j >= P.n) return;
     V3 x = v3(fin[j], fin[P.stride + j], fin[2 * P.stride + j]);
     Stencil s = make_stencil(x.x, x.y, x.z, P, batch_of(P, j));
-    V3 nv = v3(0, 0, 0);
-    M3 B = m3_zero();       // sum w g (x) offset
+    V3 nv; M3 Cn;
+    g2p_gather(P, s, g_out, nv, Cn);
 #pragma unroll
-    for (int a = 0; a < 3; a++)
-#pragma unroll
-        for (int b = 0; b < 3; b++) {
-            // row sums over c first: R0 = sum wz g, Rz = sum c wz g
-            const float4* gp = g_out + (s.ox[a] + s.oy[b]);
-            float4 g0 = gp[s.oz[0]], g1 = gp[s.oz[1]], g2 = gp[s.oz[2]];
-            float w1 = s.wz[1], w2 = s.wz[2], w0 = s.wz[0];
-            V3 R0 = v3(fmaf(w2, g2.x, fmaf(w1, g1.x, w0 * g0.x)), fmaf(w2, g2.y, fmaf(w1, g1.y, w0 * g0.y)), fmaf(w2, g2.z, fmaf(w1, g1.z, w0 * g0.z)));
-            V3 Rz = v3(fmaf(2.f * w2, g2.x, w1 * g1.x), fmaf(2.f * w2, g2.y, w1 * g1.y), fmaf(2.f * w2, g2.z, w1 * g1.z));
-            float wab = s.wx[a] * s.wy[b];
-            V3 r0 = wab * R0;
-            nv += r0;
-            if (a) { B.m[0] += a * r0.x; B.m[3] += a * r0.y; B.m[6] += a * r0.z; }
-            if (b) { B.m[1] += b * r0.x; B.m[4] += b * r0.y; B.m[7] += b * r0.z; }
-            B.m[2] = fmaf(wab, Rz.x, B.m[2]); B.m[5] = fmaf(wab, Rz.y, B.m[5]); B.m[8] = fmaf(wab, Rz.z, B.m[8]);
-        }
-    float k4 = 4.f * P.inv_dx;
-    float f3[3] = {s.fx, s.fy, s.fz}, n3[3] = {nv.x, nv.y, nv.z};
-#pragma unroll
-    for (int r = 0; r < 3; r++)
-#pragma unroll
-        for (int c = 0; c < 3; c++) fout[(15 + 3 * r + c) * P.stride + j] = k4 * (B.m[3 * r + c] - n3[r] * f3[c]);
+    for (int i = 0; i < 9; i++) fout[(15 + i) * P.stride + j] = Cn.m[i];
     fout[3 * P.stride + j] = nv.x; fout[4 * P.stride + j] = nv.y; fout[5 * P.stride + j] = nv.z;
     fout[j] = x.x + P.dt * nv.x; fout[P.stride + j] = x.y + P.dt * nv.y; fout[2 * P.stride + j] = x.z + P.dt * nv.z;
 }

@@ -415,3 +415,37 @@ def mo_rollout(orc, st, steps):
         orc.substep(0)
         orc.set_frame(0, orc.get_frame(1))
     return orc.get_frame(0)
+
+
+def test_fused_step_matches_substep_loop():
+    """smx_step fuses the G2P of substep f into the P2G of substep f+1 (G2P2G); frames, wrench and adjoints must equal the
+    plain substep loop (SMX_FLAG_NO_FUSION) -- up to the fp32 summation order of the scatter."""
+    center = np.array([0.5, 0.3, 0.5])
+    steps = 9
+
+    def run(flags, use_step):
+        rng = np.random.default_rng(300)
+        pair = Pair(5000, tables=[scenes.sphere_table()], prim_params=[(0.5, 666.)], max_steps=steps + 2, sort_every=4, flags=flags, n_control=1)
+        s13 = np.concatenate([center, [1, 0, 0, 0], [0.0, 0.2, 0.0], [0, 0, 0.3]])
+        pair.prims[0].set_all_states(0, s13, f_end=steps + 2)
+        pair.gpu.reset(scenes.contact_rollout_state(5000, rng, center))
+        pair.gpu.set_control_idx(np.zeros(5000, dtype=np.int32))
+        pair.gpu.set_action(np.array([[3.0, -2.0, 1.0]]))
+        pair.prims[0].clear_ext_f()
+        if use_step:
+            pair.gpu.step(0, steps)
+        else:
+            for f in range(steps):
+                pair.gpu.substep(f)
+        frames = [pair.gpu.get_state(f) for f in (1, 4, 5, steps)]
+        fe = pair.prims[0].get_ext_f()
+        pair.gpu.clear_all_gradients()
+        pair.gpu.add_x_grad(steps, rng.normal(size=(5000, 3)))
+        pair.gpu.step_grad(steps, steps)
+        return frames, fe, pair.gpu.get_state_grad(0)
+
+    (fa, ea, ga), (fb, eb, gb) = run(0, True), run(32, False)
+    for a, b in zip(fa, fb):
+        assert_state_close(a, b, tol=2e-5)
+    assert np.abs(ea).max() > 0 and rel_l2(ea, eb) <= 1e-4
+    assert rel_l2(ga, gb) <= 1e-4
