@@ -77,6 +77,7 @@ typedef struct {
                                      same stream interleave with the kernels without extra synchronisation (slab halo exchange) */
 #define SMX_FLAG_NO_FUSION 32       /* smx_step launches G2P and the next P2G separately instead of the fused G2P2G kernel */
 #define SMX_FLAG_DIRECT_RED 4     /* one L2 reduction per particle and node instead of the warp-aggregated scatter (ablation) */
+#define SMX_FLAG_NO_SVD_REC 64    /* do not keep the per-substep SVD records (64 B per particle and substep); the adjoint repeats the SVD */
 
 /* lifetime ------------------------------------------------------------------------------------- */
 int smx_create(const smx_config* cfg, smx_sim** out);
@@ -217,7 +218,8 @@ int smx_get_grid(smx_sim* sim, float* g_in, float* g_out);
 /* counters[0] = particles clamped into the grid, [1] = particles that left the active-block region,
  * [2] = number of re-sorts, [3] = active blocks of the current ordering */
 int smx_get_counters(smx_sim* sim, int64_t out[4]);
-/* device pointer of component c (0..23, get_state column order) of frame f in storage order (fp32, n floats) */
+/* device pointer of component c (0..23, get_state column order) of frame f in storage order: the frame is six float4
+ * planes, so the value of storage slot j is at ptr[4 * j] (fp32) */
 int smx_frame_component_dev(smx_sim* sim, int32_t f, int32_t c, void** ptr_dev);
 /* CUDA-event timer on the simulator's stream */
 int smx_timer_start(smx_sim* sim);

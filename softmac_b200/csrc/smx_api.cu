@@ -119,6 +119,10 @@ struct smx_sim {
     int ckpt_cap_hint = 1;
     size_t ckpt_bytes = 0;
     std::vector<long long> ckpt_order;  // uid of the ordering the record of substep f was written in (-1: none)
+    // SVD records (U, V, sigma - 1, J - 1 of the forward P2G of every substep) so that the adjoint does not repeat the SVD
+    float4* svd_pool = nullptr;
+    std::vector<long long> svd_order;   // uid of the ordering the SVD record of substep f was written in (-1: none)
+    float4* svd_rec(int f) { return svd_pool + (long long)f * SMX_RPLANES * P.stride; }
     std::vector<char> ckpt_contact;
     // adjoint ping-pong
     float *adj_cur = nullptr, *adj_nxt = nullptr;
@@ -268,7 +272,7 @@ static int resort(smx_sim* s, int f, bool keep_transition) {
     }
     TRY(build_blocks(s, no, s->frame_ptr(f), do_sort ? s->keys_b : nullptr));
     s->order_of[f] = new_order_id(s, no);
-    s->ckpt_order[f] = -1;
+    s->ckpt_order[f] = -1; s->svd_order[f] = -1;
     // keep_transition: frame f was produced by substep f-1 in the old ordering, so the adjoint has to be carried
     // back through idx; otherwise (user-written frame) the adjoint chain is cut here, as in the reference
     s->trans_from[f] = (keep_transition && do_sort) ? old_id : -1;
@@ -359,11 +363,21 @@ static int forward_p2g(smx_sim* s, int f, bool write_F, bool accumulate, bool fu
         k_check_slab<<<nblk(P.n, 256), 256, 0, s->stream>>>(P, fin, s->halo_lo ? s->slab_lo - 1 : 0, s->halo_hi ? s->slab_hi : P.nb - 1, s->counters); CKL(s);
     }
     if (P.n > 0) {
+        float4* rec = (write_F && s->svd_pool) ? s->svd_rec(f) : nullptr;
+        const bool extra = P.ctype == 1 || P.n_control > 0;
+        const int grid = nblk(P.n, SMX_TPB_SC), acc = accumulate ? 1 : 0;
         TRY(dispatch_mat(P.material, P.ptype, [&](auto mat) {
-            if (s->cfg.flags & SMX_FLAG_DIRECT_RED) k_p2g<decltype(mat)::value, false><<<nblk(P.n, SMX_TPB_SC), SMX_TPB_SC, 0, s->stream>>>(P, ps, f, fin, fout, s->g_in, cslot, s->action, accumulate ? 1 : 0, fprev, gprev);
-            else k_p2g<decltype(mat)::value, true><<<nblk(P.n, SMX_TPB_SC), SMX_TPB_SC, 0, s->stream>>>(P, ps, f, fin, fout, s->g_in, cslot, s->action, accumulate ? 1 : 0, fprev, gprev);
+            constexpr int M = decltype(mat)::value;
+            if (s->cfg.flags & SMX_FLAG_DIRECT_RED) {
+                if (extra) k_p2g<M, false, true><<<grid, SMX_TPB_SC, 0, s->stream>>>(P, ps, f, fin, fout, s->g_in, cslot, s->action, acc, fprev, gprev, rec);
+                else k_p2g<M, false, false><<<grid, SMX_TPB_SC, 0, s->stream>>>(P, ps, f, fin, fout, s->g_in, cslot, s->action, acc, fprev, gprev, rec);
+            } else {
+                if (extra) k_p2g<M, true, true><<<grid, SMX_TPB_SC, 0, s->stream>>>(P, ps, f, fin, fout, s->g_in, cslot, s->action, acc, fprev, gprev, rec);
+                else k_p2g<M, true, false><<<grid, SMX_TPB_SC, 0, s->stream>>>(P, ps, f, fin, fout, s->g_in, cslot, s->action, acc, fprev, gprev, rec);
+            }
             CKLN(s, fprev ? "k_g2p2g" : "k_p2g"); return (int)SMX_OK;
         }));
+        if (rec) s->svd_order[f] = o.uid;
     }
     if (write_F && s->cfg.rigid_velocity_control && !s->prims.empty()) {
         k_forward_kinematics<<<nblk((long long)s->prims.size() * s->B, 64), 64, 0, s->stream>>>(s->pstate, s->cfg.max_steps, (int)s->prims.size(), s->B, f, P.dt); CKL(s);
@@ -515,7 +529,13 @@ int smx_create(const smx_config* cfg, smx_sim** out) {
     s->spare_slot = T;
     size_t pool_bytes = (size_t)(T + 1) * s->frame_floats * sizeof(float);
     if (cudaMalloc(&s->pool, pool_bytes) != cudaSuccess) { cudaGetLastError(); delete s; return fail(SMX_ERR_NOMEM, "smx_create: cannot allocate %.1f MB of particle checkpoints", pool_bytes / 1e6); }
-    s->ckpt_order.assign(T, -1); s->ckpt_contact.assign(T, 0);
+    s->ckpt_order.assign(T, -1); s->ckpt_contact.assign(T, 0); s->svd_order.assign(T, -1);
+    if (cfg->material_model == 0 && cfg->ptype != 2 && !(cfg->flags & SMX_FLAG_NO_SVD_REC)) {
+        // optional: without it (flag, or not enough memory) the adjoint recomputes the SVD
+        size_t svd_bytes = (size_t)T * SMX_RPLANES * P.stride * sizeof(float4), free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        if (svd_bytes > free_b / 2 || cudaMalloc(&s->svd_pool, svd_bytes) != cudaSuccess) { cudaGetLastError(); s->svd_pool = nullptr; }
+    }
     s->ckpt_enabled = !(cfg->flags & SMX_FLAG_NO_GRID_CKPT);
     CK(cudaMalloc(&s->g_in, s->G * sizeof(float4))); CK(cudaMalloc(&s->g_out, s->G * sizeof(float4))); CK(cudaMalloc(&s->g_mix, s->G * sizeof(float4)));
     CK(cudaMalloc(&s->gg_out, s->G * sizeof(float4))); CK(cudaMalloc(&s->gg_mix, s->G * sizeof(float4)));
@@ -543,11 +563,16 @@ int smx_create(const smx_config* cfg, smx_sim** out) {
     CK(cudaEventCreate(&s->ev0)); CK(cudaEventCreate(&s->ev1));
     {   // the staged scatter kernels want 8 CTAs x 28 KB of shared memory per SM: ask for the largest carve-out
         int co = cudaSharedmemCarveoutMaxShared;
-        cudaFuncSetAttribute(k_p2g<0, true>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
-        cudaFuncSetAttribute(k_p2g<1, true>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
-        cudaFuncSetAttribute(k_p2g<2, true>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
-        cudaFuncSetAttribute(k_p2g<4, true>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
-        cudaFuncSetAttribute(k_p2g<5, true>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+        cudaFuncSetAttribute(k_p2g<0, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+        cudaFuncSetAttribute(k_p2g<1, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+        cudaFuncSetAttribute(k_p2g<2, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+        cudaFuncSetAttribute(k_p2g<4, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+        cudaFuncSetAttribute(k_p2g<5, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+        cudaFuncSetAttribute(k_p2g<0, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+        cudaFuncSetAttribute(k_p2g<1, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+        cudaFuncSetAttribute(k_p2g<2, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+        cudaFuncSetAttribute(k_p2g<4, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+        cudaFuncSetAttribute(k_p2g<5, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
         cudaFuncSetAttribute(k_g2p_grad<true>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
         cudaGetLastError();
     }
@@ -564,7 +589,7 @@ int smx_destroy(smx_sim* s) {
     for (auto& o : s->free_orders) free_order(o);
     for (auto& kv : s->seeds) cudaFree(kv.second.dev);
     for (auto& p : s->prims) { cudaFree(p.sdf_dev); cudaFree(p.nrm_dev); }
-    void* ptrs[] = {s->ch_target, s->ch_loss, s->ckpt, s->pool, s->g_in, s->g_out, s->g_mix, s->gg_out, s->gg_mix, s->g_lin, s->adj_cur, s->adj_nxt, s->stage_dev, s->keys_a, s->keys_b, s->iota, s->cub_tmp,
+    void* ptrs[] = {s->svd_pool, s->ch_target, s->ch_loss, s->ckpt, s->pool, s->g_in, s->g_out, s->g_mix, s->gg_out, s->gg_mix, s->g_lin, s->adj_cur, s->adj_nxt, s->stage_dev, s->keys_a, s->keys_b, s->iota, s->cub_tmp,
                     s->counters, s->prims_dev, s->pstate, s->pgrad, s->ext_f, s->ext_f_grad, s->abuf, s->gabuf, s->ctrl_id, s->action, s->action_grad};
     for (void* p : ptrs) cudaFree(p);
     cudaFreeHost(s->stage_host);
@@ -627,6 +652,7 @@ int smx_reset(smx_sim* s, const double* state, int32_t ncols) {
     std::fill(s->order_of.begin(), s->order_of.end(), -1);
     std::fill(s->trans_from.begin(), s->trans_from.end(), -1);
     std::fill(s->ckpt_order.begin(), s->ckpt_order.end(), -1);
+    std::fill(s->svd_order.begin(), s->svd_order.end(), -1);
     s->adj_frame = -1; s->adj_order = -1;
     s->ckpt_dirty = true;
     gc_orders(s);                       // every ordering is unreferenced now: recycle all of them
@@ -656,7 +682,7 @@ int smx_set_frame(smx_sim* s, int32_t f, const double* x, const double* v, const
     TRY(check_frame(s, f, "smx_set_frame"));
     CK(cudaSetDevice(s->cfg.device));
     TRY(ensure_order(s, f));
-    s->ckpt_order[f] = -1;
+    s->ckpt_order[f] = -1; s->svd_order[f] = -1;
     if (x) TRY(upload_cols(s, f, x, 3, 0));
     if (v) TRY(upload_cols(s, f, v, 3, 3));
     if (F) TRY(upload_cols(s, f, F, 9, 6));
@@ -689,7 +715,7 @@ int smx_copy_frame(smx_sim* s, int32_t src, int32_t dst) {
     CK(cudaSetDevice(s->cfg.device));
     if (src != dst) {
         CK(cudaMemcpyAsync(s->frame_ptr(dst), s->frame_ptr(src), s->frame_floats * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
-        s->order_of[dst] = s->order_of[src]; s->trans_from[dst] = -1; s->ckpt_order[dst] = -1;
+        s->order_of[dst] = s->order_of[src]; s->trans_from[dst] = -1; s->ckpt_order[dst] = -1; s->svd_order[dst] = -1;
         int T = s->cfg.max_steps;
         for (int b = 0; b < s->B; b++)
             for (size_t ii = 0; ii < s->prims.size(); ii++) {
@@ -938,7 +964,7 @@ int smx_substep_begin(smx_sim* s, int32_t f) {
     if (s->order_of[f] < 0) return fail(SMX_ERR_STATE, "smx_substep: frame %d has not been written (call smx_reset / smx_set_frame first)", f);
     CK(cudaSetDevice(s->cfg.device));
     s->order_of[f + 1] = s->order_of[f]; s->trans_from[f + 1] = -1;
-    s->ckpt_order[f] = -1; s->ckpt_order[f + 1] = -1;
+    s->ckpt_order[f] = -1; s->ckpt_order[f + 1] = -1; s->svd_order[f] = -1; s->svd_order[f + 1] = -1;
     if (s->ckpt_dirty) TRY(ensure_ckpt(s, f));
     return forward_p2g(s, f, true, true);
 }
@@ -1056,8 +1082,19 @@ int smx_substep_grad_end(smx_sim* s, int32_t f) {
     const int* cslot = nullptr;
     TRY(ctrl_slots(s, o, &cslot));
     if (P.n > 0) {
+        const bool use_rec = s->svd_pool && s->svd_order[f] == ord.uid;
+        const float4* rec = use_rec ? s->svd_rec(f) : nullptr;
+        const bool extra = P.ctype == 1 || P.n_control > 0;
+        const int grid = nblk(P.n, SMX_TPB);
         TRY(dispatch_mat(P.material, P.ptype, [&](auto mat) {
-            k_p2g_grad<decltype(mat)::value><<<nblk(P.n, SMX_TPB), SMX_TPB, 0, s->stream>>>(P, ps, f, fin, s->adj_cur, s->adj_nxt, s->gg_out, cslot, s->action, s->action_grad);
+            constexpr int M = decltype(mat)::value;
+            if (use_rec) {
+                if (extra) k_p2g_grad<M, true, true><<<grid, SMX_TPB, 0, s->stream>>>(P, ps, f, fin, s->adj_cur, s->adj_nxt, s->gg_out, cslot, s->action, s->action_grad, rec);
+                else k_p2g_grad<M, true, false><<<grid, SMX_TPB, 0, s->stream>>>(P, ps, f, fin, s->adj_cur, s->adj_nxt, s->gg_out, cslot, s->action, s->action_grad, rec);
+            } else {
+                if (extra) k_p2g_grad<M, false, true><<<grid, SMX_TPB, 0, s->stream>>>(P, ps, f, fin, s->adj_cur, s->adj_nxt, s->gg_out, cslot, s->action, s->action_grad, rec);
+                else k_p2g_grad<M, false, false><<<grid, SMX_TPB, 0, s->stream>>>(P, ps, f, fin, s->adj_cur, s->adj_nxt, s->gg_out, cslot, s->action, s->action_grad, rec);
+            }
             CKLN(s, "k_p2g_grad"); return (int)SMX_OK;
         }));
     }
@@ -1117,7 +1154,7 @@ int smx_step(smx_sim* s, int32_t s0, int32_t count) {
             if (f + 1 >= s->cfg.max_steps) return fail(SMX_ERR_RANGE, "smx_step: substep %d would write frame %d >= max_steps %d", f, f + 1, s->cfg.max_steps);
             CK(cudaSetDevice(s->cfg.device));
             s->order_of[f + 1] = s->order_of[f]; s->trans_from[f + 1] = -1;
-            s->ckpt_order[f] = -1; s->ckpt_order[f + 1] = -1;
+            s->ckpt_order[f] = -1; s->ckpt_order[f + 1] = -1; s->svd_order[f] = -1; s->svd_order[f + 1] = -1;
             TRY(forward_p2g(s, f, true, true, true));
             pending_g2p = false;
         }
@@ -1329,7 +1366,7 @@ int smx_get_counters(smx_sim* s, int64_t out[4]) {
 int smx_frame_component_dev(smx_sim* s, int32_t f, int32_t c, void** ptr) {
     TRY(check_frame(s, f, "smx_frame_component_dev"));
     if (!ptr || c < 0 || c >= 24) return fail(SMX_ERR_ARG, "smx_frame_component_dev: bad component");
-    *ptr = s->frame_ptr(f) + (long long)c * s->P.stride;
+    *ptr = s->frame_ptr(f) + comp_pos(c) / 4 * 4 * s->P.stride + comp_pos(c) % 4;       // element j at ptr[4 * j]
     return SMX_OK;
 }
 int smx_timer_start(smx_sim* s) {

@@ -1,8 +1,14 @@
 // smx_kernels.cuh -- hand-written sm_100a kernels of the MLS-MPM substep and of its adjoint.
 //
 // Data layout (all fp32 in HBM):
-//   particle frame  : SoA [24][stride] in get_state column order (x0..2 v3..5 F6..14 C15..23), particles
-//                     physically sorted by block-major cell key, so a warp's 32 particles share ~4 cells
+//   particle frame  : six float4 PLANES [6][stride]: (x0 x1 x2 v0) (v1 v2 C0 C1) (C2..C5) (C6 C7 C8 F0) (F1..F4) (F5..F8),
+//                     i.e. storage position of get_state column c (x0..2 v3..5 F6..14 C15..23) = comp_pos(c); one 16-byte
+//                     load/store per plane and lane (512 contiguous bytes per warp).  x, v, C (written by G2P) come first,
+//                     F (written by P2G) last; particles are physically sorted by block-major cell key, so a warp's 32
+//                     particles share ~4 cells
+//   SVD record      : four float4 planes [4][stride] per substep: (u0 | u1.x) (u1.yz | v0.xy) (v0.z | v1) (e0 e1 e2 J-1):
+//                     the first two columns of U and V (the third is their cross product), sigma - 1 and det(F_tmp) - 1 of
+//                     the forward P2G, so that the adjoint does not repeat the Jacobi SVD
 //   grid            : float4 per node, BLOCK-MAJOR: 4x4x4-node blocks are contiguous 1 KB chunks
 //                     g_in  = (momentum xyz, mass)          target of P2G        (mpm_simulator.py:261-262)
 //                     g_out = (velocity xyz, active flag)   source of G2P        (:296-297, :403-404, :443)
@@ -51,6 +57,26 @@ __device__ __forceinline__ double* pgrad_at(const PrimSet& ps, int b, int i, int
 __device__ __forceinline__ double* ext_f_at(const PrimSet& ps, int b, int i) { return ps.ext_f + ((size_t)b * SMX_MAXP + i) * 6; }
 __device__ __forceinline__ const float* ext_f_grad_at(const PrimSet& ps, int b, int i) { return ps.ext_f_grad + ((size_t)b * SMX_MAXP + i) * 6; }
 __device__ __forceinline__ int batch_of(const Params& P, int j) { return P.nbatch > 1 ? j / P.npb : 0; }
+
+// ---- particle-frame layout -------------------------------------------------------------------------------------------
+#define SMX_NPLANES 6       // float4 planes per particle frame
+#define SMX_RPLANES 4       // float4 planes per SVD record
+// get_state column (x0..2 v3..5 F6..14 C15..23) -> storage position (x v C F)
+__host__ __device__ __forceinline__ int comp_pos(int c) { return c < 6 ? c : (c < 15 ? c + 9 : c - 9); }
+__device__ __forceinline__ long long comp_index(long long stride, int j, int c) {
+    int p = comp_pos(c);
+    return (((long long)(p >> 2) * stride + j) << 2) + (p & 3);
+}
+__device__ __forceinline__ float4 ld_plane(const float* __restrict__ fr, long long stride, int j, int p) {
+    return __ldg(reinterpret_cast<const float4*>(fr) + ((long long)p * stride + j));
+}
+__device__ __forceinline__ void st_plane(float* __restrict__ fr, long long stride, int j, int p, float4 v) {
+    reinterpret_cast<float4*>(fr)[(long long)p * stride + j] = v;
+}
+__device__ __forceinline__ V3 load_x(const float* __restrict__ fr, long long stride, int j) {
+    float4 a = ld_plane(fr, stride, j, 0);
+    return v3(a.x, a.y, a.z);
+}
 
 #define SMX_TPB 128         // gather-type particle kernels
 #define SMX_TPB_SC 64       // scatter-type particle kernels (two warps: 2 x 13.8 KB of staging)
@@ -120,7 +146,7 @@ __device__ __forceinline__ void warp_stage_flush(WarpStage& st, uint32_t key, bo
 
 // quadratic B-spline stencil of one particle (mpm_simulator.py:215-217)
 struct Stencil {
-    int ox[3], oy[3], oz[3];    // block-major address contributions per axis offset
+    uint32_t ox[3], oy[3], oz[3];   // block-major address contributions per axis offset (unsigned: one IMAD.WIDE.U32 per node address)
     int bx, by, bz;
     float fx, fy, fz;
     float wx[3], wy[3], wz[3];
@@ -152,9 +178,9 @@ __device__ __forceinline__ Stencil make_stencil(float x, float y, float z, const
 #pragma unroll
     for (int a = 0; a < 3; a++) {
         int i = s.bx + a, j = s.by + a, k = s.bz + a;
-        s.ox[a] = bt * P.Gb + ((i >> 2) * P.nb * P.nb) * 64 + ((i & 3) << 4);
-        s.oy[a] = ((j >> 2) * P.nb) * 64 + ((j & 3) << 2);
-        s.oz[a] = (k >> 2) * 64 + (k & 3);
+        s.ox[a] = (uint32_t)(bt * P.Gb + ((i >> 2) * P.nb * P.nb) * 64 + ((i & 3) << 4));
+        s.oy[a] = (uint32_t)(((j >> 2) * P.nb) * 64 + ((j & 3) << 2));
+        s.oz[a] = (uint32_t)((k >> 2) * 64 + (k & 3));
     }
     return s;
 }
@@ -209,10 +235,12 @@ __device__ __forceinline__ M3 compute_Et(const M3& C, const M3& F, float dt) {
     for (int i = 0; i < 9; i++) Et.m[i] = fmaf(dt, C.m[i] + CE.m[i], EF.m[i]);
     return Et;
 }
-template <int MAT>
+// REC: m.svd and m.Jm1 were loaded from the SVD record of the forward pass (co-rotated plastic / elastic only)
+template <int MAT, bool REC = false>
 __device__ __forceinline__ void material_update(const M3& Et, const Params& P, Material& m) {
     constexpr int model = MAT / 3, ptype = MAT % 3;
-    m.Jm1 = det_minus_one(Et);
+    constexpr bool rec = REC && model == 0 && ptype != 2;
+    if (!rec) m.Jm1 = det_minus_one(Et);
     m.J = 1.f + m.Jm1;
     M3 Ftmp = Et; Ftmp.m[0] += 1.f; Ftmp.m[4] += 1.f; Ftmp.m[8] += 1.f;
     if (model == 0) {
@@ -221,7 +249,7 @@ __device__ __forceinline__ void material_update(const M3& Et, const Params& P, M
             m.newF = scale(c, m3_identity());
             m.D = m3_zero();
         } else {
-            m.svd = svd_dev(Et);
+            if (!rec) m.svd = svd_dev(Et);
             if (ptype == 0) {             // plastic: clip sigma to [1-2e-3, 1+3e-3] (:226-229)
                 float g0 = fminf(fmaxf(m.svd.e[0], -2e-3f), 3e-3f), g1 = fminf(fmaxf(m.svd.e[1], -2e-3f), 3e-3f),
                       g2 = fminf(fmaxf(m.svd.e[2], -2e-3f), 3e-3f);
@@ -250,11 +278,58 @@ __device__ __forceinline__ void material_update(const M3& Et, const Params& P, M
     }
 }
 
+// unpack the six planes of one particle
+__device__ __forceinline__ void unpack_state(const float4& p0, const float4& p1, const float4& p2, const float4& p3, const float4& p4, const float4& p5,
+                                             V3& x, V3& v, M3& F, M3& C) {
+    x = v3(p0.x, p0.y, p0.z); v = v3(p0.w, p1.x, p1.y);
+    C.m[0] = p1.z; C.m[1] = p1.w; C.m[2] = p2.x; C.m[3] = p2.y; C.m[4] = p2.z; C.m[5] = p2.w; C.m[6] = p3.x; C.m[7] = p3.y; C.m[8] = p3.z;
+    F.m[0] = p3.w; F.m[1] = p4.x; F.m[2] = p4.y; F.m[3] = p4.z; F.m[4] = p4.w; F.m[5] = p5.x; F.m[6] = p5.y; F.m[7] = p5.z; F.m[8] = p5.w;
+}
 __device__ __forceinline__ void load_state(const float* __restrict__ fr, long long stride, int j, V3& x, V3& v, M3& F, M3& C) {
-    x = v3(fr[j], fr[stride + j], fr[2 * stride + j]);
-    v = v3(fr[3 * stride + j], fr[4 * stride + j], fr[5 * stride + j]);
-#pragma unroll
-    for (int i = 0; i < 9; i++) { F.m[i] = fr[(6 + i) * stride + j]; C.m[i] = fr[(15 + i) * stride + j]; }
+    const float4* b = reinterpret_cast<const float4*>(fr) + j;
+    float4 p0 = __ldg(b), p1 = __ldg(b + stride), p2 = __ldg(b + 2 * stride), p3 = __ldg(b + 3 * stride), p4 = __ldg(b + 4 * stride), p5 = __ldg(b + 5 * stride);
+    unpack_state(p0, p1, p2, p3, p4, p5, x, v, F, C);
+}
+// x, v, C of a frame (planes 0..2 and the first three components of plane 3; F0 in plane 3.w belongs to P2G)
+__device__ __forceinline__ void store_xvC(float* __restrict__ fr, long long stride, int j, V3 x, V3 v, const M3& C) {
+    float4* b = reinterpret_cast<float4*>(fr) + j;
+    b[0] = make_float4(x.x, x.y, x.z, v.x);
+    b[stride] = make_float4(v.y, v.z, C.m[0], C.m[1]);
+    b[2 * stride] = make_float4(C.m[2], C.m[3], C.m[4], C.m[5]);
+    float* q = reinterpret_cast<float*>(b + 3 * stride);
+    *reinterpret_cast<float2*>(q) = make_float2(C.m[6], C.m[7]);
+    q[2] = C.m[8];
+}
+// F of a frame (plane 3.w and planes 4, 5)
+__device__ __forceinline__ void store_F(float* __restrict__ fr, long long stride, int j, const M3& F) {
+    float4* b = reinterpret_cast<float4*>(fr) + j;
+    reinterpret_cast<float*>(b + 3 * stride)[3] = F.m[0];
+    b[4 * stride] = make_float4(F.m[1], F.m[2], F.m[3], F.m[4]);
+    b[5 * stride] = make_float4(F.m[5], F.m[6], F.m[7], F.m[8]);
+}
+__device__ __forceinline__ M3 load_F(const float* __restrict__ fr, long long stride, int j) {
+    const float4* b = reinterpret_cast<const float4*>(fr) + j;
+    float f0 = __ldg(reinterpret_cast<const float*>(b + 3 * stride) + 3);
+    float4 p4 = __ldg(b + 4 * stride), p5 = __ldg(b + 5 * stride);
+    M3 F; F.m[0] = f0; F.m[1] = p4.x; F.m[2] = p4.y; F.m[3] = p4.z; F.m[4] = p4.w; F.m[5] = p5.x; F.m[6] = p5.y; F.m[7] = p5.z; F.m[8] = p5.w;
+    return F;
+}
+// SVD record of the forward P2G (see the layout comment at the top)
+__device__ __forceinline__ void store_svd_rec(float4* __restrict__ rec, long long stride, int j, const Svd& sv, float Jm1) {
+    float4* b = rec + j;
+    b[0] = make_float4(sv.U.m[0], sv.U.m[3], sv.U.m[6], sv.U.m[1]);
+    b[stride] = make_float4(sv.U.m[4], sv.U.m[7], sv.V.m[0], sv.V.m[3]);
+    b[2 * stride] = make_float4(sv.V.m[6], sv.V.m[1], sv.V.m[4], sv.V.m[7]);
+    b[3 * stride] = make_float4(sv.e[0], sv.e[1], sv.e[2], Jm1);
+}
+__device__ __forceinline__ void load_svd_rec(const float4* __restrict__ rec, long long stride, int j, Svd& sv, float& Jm1) {
+    const float4* b = rec + j;
+    float4 a = __ldg(b), c = __ldg(b + stride), d = __ldg(b + 2 * stride), e = __ldg(b + 3 * stride);
+    V3 u0 = v3(a.x, a.y, a.z), u1 = v3(a.w, c.x, c.y), v0 = v3(c.z, c.w, d.x), v1 = v3(d.y, d.z, d.w);
+    V3 u2 = cross(u0, u1), v2 = cross(v0, v1);       // U, V are proper rotations
+    sv.U.m[0] = u0.x; sv.U.m[3] = u0.y; sv.U.m[6] = u0.z; sv.U.m[1] = u1.x; sv.U.m[4] = u1.y; sv.U.m[7] = u1.z; sv.U.m[2] = u2.x; sv.U.m[5] = u2.y; sv.U.m[8] = u2.z;
+    sv.V.m[0] = v0.x; sv.V.m[3] = v0.y; sv.V.m[6] = v0.z; sv.V.m[1] = v1.x; sv.V.m[4] = v1.y; sv.V.m[7] = v1.z; sv.V.m[2] = v2.x; sv.V.m[5] = v2.y; sv.V.m[8] = v2.z;
+    sv.e[0] = e.x; sv.e[1] = e.y; sv.e[2] = e.z; Jm1 = e.w;
 }
 
 // particle-contact impulses (collision_type == 1, :203-206) and the control impulse (:209-213)
@@ -286,8 +361,8 @@ __device__ __forceinline__ void g2p_gather(const Params& P, const Stencil& s, co
 #pragma unroll
         for (int b = 0; b < 3; b++) {
             // row sums over c first: R0 = sum wz g, Rz = sum c wz g
-            const float4* gp = g_out + (s.ox[a] + s.oy[b]);
-            float4 g0 = gp[s.oz[0]], g1 = gp[s.oz[1]], g2 = gp[s.oz[2]];
+            const uint32_t oab = s.ox[a] + s.oy[b];
+            float4 g0 = g_out[oab + s.oz[0]], g1 = g_out[oab + s.oz[1]], g2 = g_out[oab + s.oz[2]];
             float w1 = s.wz[1], w2 = s.wz[2], w0 = s.wz[0];
             V3 R0 = v3(fmaf(w2, g2.x, fmaf(w1, g1.x, w0 * g0.x)), fmaf(w2, g2.y, fmaf(w1, g1.y, w0 * g0.y)), fmaf(w2, g2.z, fmaf(w1, g1.z, w0 * g0.z)));
             V3 Rz = v3(fmaf(2.f * w2, g2.x, w1 * g1.x), fmaf(2.f * w2, g2.y, w1 * g1.y), fmaf(2.f * w2, g2.z, w1 * g1.z));
@@ -312,40 +387,40 @@ __device__ __forceinline__ void g2p_gather(const Params& P, const Stencil& s, co
 // frame f-1 and g_out, written to the checkpoint, and consumed from registers (fprev / g_prev non-null).
 // STAGED: warp-aggregated scatter through shared memory (default); otherwise one REDG per node.
 // ------------------------------------------------------------------------------------------------
-template <int MAT, bool STAGED>
+template <int MAT, bool STAGED, bool EXTRA>
 __global__ void __launch_bounds__(SMX_TPB_SC, 8) k_p2g(Params P, PrimSet ps, int f, float* __restrict__ fin, float* __restrict__ fout,
                                                     float4* __restrict__ g_in, const int* __restrict__ ctrl_slot,
                                                     const float* __restrict__ action, int accumulate,
-                                                    const float* __restrict__ fprev, const float4* __restrict__ g_prev) {
+                                                    const float* __restrict__ fprev, const float4* __restrict__ g_prev, float4* __restrict__ rec) {
+    // EXTRA: particle-contact impulses (collision_type == 1) and / or particle control forces are present
     __shared__ WarpStage stage[STAGED ? SMX_TPB_SC / 32 : 1];
+    constexpr bool has_svd = (MAT / 3 == 0) && (MAT % 3 != 2);
     int j = blockIdx.x * SMX_TPB_SC + threadIdx.x;
     bool live = j < P.n;
     int jj = live ? j : P.n - 1;
     V3 x, v; M3 F, C;
     int bt = batch_of(P, jj);
     if (fprev) {        // fused G2P of substep f-1: frame f-1 -> x, v, C of frame f
-        V3 xo = v3(fprev[jj], fprev[P.stride + jj], fprev[2 * P.stride + jj]);
+        V3 xo = load_x(fprev, P.stride, jj);
         Stencil so = make_stencil(xo.x, xo.y, xo.z, P, bt);
         g2p_gather(P, so, g_prev, v, C);
         x = xo + P.dt * v;
-#pragma unroll
-        for (int i = 0; i < 9; i++) F.m[i] = fin[(6 + i) * P.stride + jj];
-        if (live) {
-            fin[j] = x.x; fin[P.stride + j] = x.y; fin[2 * P.stride + j] = x.z;
-            fin[3 * P.stride + j] = v.x; fin[4 * P.stride + j] = v.y; fin[5 * P.stride + j] = v.z;
-#pragma unroll
-            for (int i = 0; i < 9; i++) fin[(15 + i) * P.stride + j] = C.m[i];
+        {   // F of frame f was written by the previous P2G launch (plain loads: this kernel writes the same planes)
+            const float4* b = reinterpret_cast<const float4*>(fin) + jj;
+            float f0 = reinterpret_cast<const float*>(b + 3 * P.stride)[3];
+            float4 p4 = b[4 * P.stride], p5 = b[5 * P.stride];
+            F.m[0] = f0; F.m[1] = p4.x; F.m[2] = p4.y; F.m[3] = p4.z; F.m[4] = p4.w; F.m[5] = p5.x; F.m[6] = p5.y; F.m[7] = p5.z; F.m[8] = p5.w;
         }
+        if (live) store_xvC(fin, P.stride, j, x, v, C);
     } else load_state(fin, P.stride, jj, x, v, F, C);
-    V3 imp = particle_impulses(P, ps, f, jj, bt, live, x, v, ctrl_slot, action, accumulate != 0);
+    V3 imp = v3(0, 0, 0);
+    if (EXTRA) imp = particle_impulses(P, ps, f, jj, bt, live, x, v, ctrl_slot, action, accumulate != 0);
     Stencil s = make_stencil(x.x, x.y, x.z, P, bt);
     if (live) {
         Material m;
         material_update<MAT>(compute_Et(C, F, P.dt), P, m);
-        if (fout) {
-#pragma unroll
-            for (int i = 0; i < 9; i++) fout[(6 + i) * P.stride + j] = m.newF.m[i];
-        }
+        if (fout) store_F(fout, P.stride, j, m.newF);
+        if (has_svd && rec) store_svd_rec(rec, P.stride, j, m.svd, m.Jm1);
         // affine' = (cs*stress + p_mass*C) * dx ; value(node) = w * (q0 + affine' * offset), q0 = p_mass*v + imp - affine' * fx
         M3 A;
 #pragma unroll
@@ -453,7 +528,7 @@ __global__ void __launch_bounds__(SMX_TPB) k_contact(Params P, PrimSet ps, int f
     int j = blockIdx.x * SMX_TPB + threadIdx.x;
     bool live = j < P.n;
     int jj = live ? j : P.n - 1;
-    V3 x = v3(fin[jj], fin[P.stride + jj], fin[2 * P.stride + jj]);
+    V3 x = load_x(fin, P.stride, jj);
     int bt = batch_of(P, jj);
     // cheap reject: is the particle within reach of any enabled primitive?
     bool near = false;
@@ -510,14 +585,11 @@ __global__ void __launch_bounds__(SMX_TPB) k_contact(Params P, PrimSet ps, int f
 __global__ void __launch_bounds__(SMX_TPB) k_g2p(Params P, const float* __restrict__ fin, float* __restrict__ fout, const float4* __restrict__ g_out) {
     int j = blockIdx.x * SMX_TPB + threadIdx.x;
     if (j >= P.n) return;
-    V3 x = v3(fin[j], fin[P.stride + j], fin[2 * P.stride + j]);
+    V3 x = load_x(fin, P.stride, j);
     Stencil s = make_stencil(x.x, x.y, x.z, P, batch_of(P, j));
     V3 nv; M3 Cn;
     g2p_gather(P, s, g_out, nv, Cn);
-#pragma unroll
-    for (int i = 0; i < 9; i++) fout[(15 + i) * P.stride + j] = Cn.m[i];
-    fout[3 * P.stride + j] = nv.x; fout[4 * P.stride + j] = nv.y; fout[5 * P.stride + j] = nv.z;
-    fout[j] = x.x + P.dt * nv.x; fout[P.stride + j] = x.y + P.dt * nv.y; fout[2 * P.stride + j] = x.z + P.dt * nv.z;
+    store_xvC(fout, P.stride, j, x + P.dt * nv, nv, Cn);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -531,15 +603,17 @@ __global__ void __launch_bounds__(SMX_TPB_SC, 8) k_g2p_grad(Params P, const floa
     int j = blockIdx.x * SMX_TPB_SC + threadIdx.x;
     bool live = j < P.n;
     int jj = live ? j : P.n - 1;
-    V3 x = v3(fin[jj], fin[P.stride + jj], fin[2 * P.stride + jj]);
+    V3 x = load_x(fin, P.stride, jj);
     int bt = batch_of(P, jj);
     Stencil s = make_stencil(x.x, x.y, x.z, P, bt);
     if (live) {
-        V3 gx1 = v3(ain[j], ain[P.stride + j], ain[2 * P.stride + j]);
-        V3 gnv = v3(ain[3 * P.stride + j], ain[4 * P.stride + j], ain[5 * P.stride + j]) + P.dt * gx1;
-        M3 gC;
-#pragma unroll
-        for (int i = 0; i < 9; i++) gC.m[i] = ain[(15 + i) * P.stride + j];
+        V3 gx1, gnv; M3 gC;
+        {
+            float4 a0 = ld_plane(ain, P.stride, j, 0), a1 = ld_plane(ain, P.stride, j, 1), a2 = ld_plane(ain, P.stride, j, 2), a3 = ld_plane(ain, P.stride, j, 3);
+            gx1 = v3(a0.x, a0.y, a0.z);
+            gnv = v3(a0.w, a1.x, a1.y) + P.dt * gx1;
+            gC.m[0] = a1.z; gC.m[1] = a1.w; gC.m[2] = a2.x; gC.m[3] = a2.y; gC.m[4] = a2.z; gC.m[5] = a2.w; gC.m[6] = a3.x; gC.m[7] = a3.y; gC.m[8] = a3.z;
+        }
         float dwx[3], dwy[3], dwz[3];
         axis_dweights(s.fx, dwx); axis_dweights(s.fy, dwy); axis_dweights(s.fz, dwz);
         float k4 = 4.f * P.inv_dx;
@@ -561,7 +635,7 @@ __global__ void __launch_bounds__(SMX_TPB_SC, 8) k_g2p_grad(Params P, const floa
 #pragma unroll
                 for (int c = 0; c < 3; c++) {
                     V3 q = qb + (float)c * c2;
-                    int node = s.ox[a] + s.oy[b] + s.oz[c];
+                    uint32_t node = s.ox[a] + s.oy[b] + s.oz[c];
                     float4 g = g_out[node];
                     float w = wab * s.wz[c];
                     if (STAGED) row[a * 9 + b * 3 + c] = make_float4(w * q.x, w * q.y, w * q.z, 0.f);
@@ -578,7 +652,8 @@ __global__ void __launch_bounds__(SMX_TPB_SC, 8) k_g2p_grad(Params P, const floa
         }
         // d dpos = k4 * w * gC^T g  ->  d fx -= sum = K^T S0
         gfx -= Tmulv(K, S0);
-        aout[j] = gx1.x + P.inv_dx * gfx.x; aout[P.stride + j] = gx1.y + P.inv_dx * gfx.y; aout[2 * P.stride + j] = gx1.z + P.inv_dx * gfx.z;
+        // partial d x of frame f (the contact adjoint and P2G adjoint add theirs); the rest of the plane is written by P2G adjoint
+        st_plane(aout, P.stride, j, 0, make_float4(gx1.x + P.inv_dx * gfx.x, gx1.y + P.inv_dx * gfx.y, gx1.z + P.inv_dx * gfx.z, 0.f));
     }
     if (STAGED) warp_stage_flush(stage[threadIdx.x >> 5], pack_base(s.bx, s.by, s.bz, bt), live, gg_out, P.nb, P.Gb);
 }
@@ -593,7 +668,7 @@ __global__ void __launch_bounds__(SMX_TPB) k_contact_grad(Params P, PrimSet ps, 
     int j = blockIdx.x * SMX_TPB + threadIdx.x;
     bool live = j < P.n;
     int jj = live ? j : P.n - 1;
-    V3 x = v3(fin[jj], fin[P.stride + jj], fin[2 * P.stride + jj]);
+    V3 x = load_x(fin, P.stride, jj);
     int bt = batch_of(P, jj);
     bool near = false;
     for (int i = 0; i < P.np; i++) {
@@ -673,7 +748,7 @@ __global__ void __launch_bounds__(SMX_TPB) k_contact_grad(Params P, PrimSet ps, 
         for (int b = 0; b < 3; b++)
 #pragma unroll
             for (int c = 0; c < 3; c++) {
-                int node = s.ox[a] + s.oy[b] + s.oz[c];
+                uint32_t node = s.ox[a] + s.oy[b] + s.oz[c];
                 float4 gm = g_mix[node];
                 float w = s.wx[a] * s.wy[b] * s.wz[c];
                 red_add_f4(gg_mix + node, w * gvtmp.x, w * gvtmp.y, w * gvtmp.z, 0.f);
@@ -682,7 +757,12 @@ __global__ void __launch_bounds__(SMX_TPB) k_contact_grad(Params P, PrimSet ps, 
                 gfx.y = fmaf(gw, s.wx[a] * dwy[b] * s.wz[c], gfx.y);
                 gfx.z = fmaf(gw, s.wx[a] * s.wy[b] * dwz[c], gfx.z);
             }
-    aout[j] += gxc.x + P.inv_dx * gfx.x; aout[P.stride + j] += gxc.y + P.inv_dx * gfx.y; aout[2 * P.stride + j] += gxc.z + P.inv_dx * gfx.z;
+    {
+        float4* ap = reinterpret_cast<float4*>(aout) + j;
+        float4 a = *ap;
+        a.x += gxc.x + P.inv_dx * gfx.x; a.y += gxc.y + P.inv_dx * gfx.y; a.z += gxc.z + P.inv_dx * gfx.z;
+        *ap = a;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -746,27 +826,31 @@ __global__ void __launch_bounds__(256) k_grid_grad(Params P, PrimSet ps, int f, 
 //   aout = adjoint of frame f: x holds the partial from g2p/contact grads; v, F, C are written
 // ------------------------------------------------------------------------------------------------
 #ifndef SMX_P2GG_MINB
-#define SMX_P2GG_MINB 3   // measured on B200: 3 (168 regs, no spills) 150 us < 4 (128 regs) 153 us < 5 (96 regs) 166 us < 6 (80 regs) 193 us
+#define SMX_P2GG_MINB 4
 #endif
-template <int MAT>
+// REC:   U, V, sigma - 1 and J - 1 come from the SVD record written by the forward P2G (no Jacobi sweeps here)
+// EXTRA: particle-contact impulses (collision_type == 1) and / or particle control forces are present
+template <int MAT, bool REC, bool EXTRA>
 __global__ void __launch_bounds__(SMX_TPB, SMX_P2GG_MINB) k_p2g_grad(Params P, PrimSet ps, int f, const float* __restrict__ fin, const float* __restrict__ ain,
                                                       float* __restrict__ aout, const float4* __restrict__ gg, const int* __restrict__ ctrl_slot,
-                                                      const float* __restrict__ action, double* __restrict__ action_grad) {
+                                                      const float* __restrict__ action, double* __restrict__ action_grad, const float4* __restrict__ rec) {
     constexpr int model = MAT / 3, ptype = MAT % 3;
+    constexpr bool corot = model == 0 && ptype != 2;
     int j = blockIdx.x * SMX_TPB + threadIdx.x;
     bool live = j < P.n;
     int jj = live ? j : P.n - 1;
     V3 x, v; M3 F, C;
     load_state(fin, P.stride, jj, x, v, F, C);
     int bt = batch_of(P, jj);
-    V3 imp = particle_impulses(P, ps, f, jj, bt, live, x, v, ctrl_slot, action, false);
+    V3 imp = v3(0, 0, 0);
+    if (EXTRA) imp = particle_impulses(P, ps, f, jj, bt, live, x, v, ctrl_slot, action, false);
     Material m;
     M3 Et = compute_Et(C, F, P.dt);
-    material_update<MAT>(Et, P, m);
+    if (REC && corot) load_svd_rec(rec, P.stride, jj, m.svd, m.Jm1);
+    material_update<MAT, REC>(Et, P, m);
     M3 A;
 #pragma unroll
     for (int i = 0; i < 9; i++) A.m[i] = (P.cs * m.stress.m[i] + P.p_mass * C.m[i]) * P.dx;
-    // (an L1 prefetch of the 27 gather nodes before the SVD was measured on B200: 148 -> 158 us, so it is not used)
     Stencil s = make_stencil(x.x, x.y, x.z, P, bt);
     float dwx[3], dwy[3], dwz[3];
     axis_dweights(s.fx, dwx); axis_dweights(s.fy, dwy); axis_dweights(s.fz, dwz);
@@ -781,13 +865,13 @@ __global__ void __launch_bounds__(SMX_TPB, SMX_P2GG_MINB) k_p2g_grad(Params P, P
         for (int b = 0; b < 3; b++) {
             V3 qb = qa + (float)b * c1;
             float wab = s.wx[a] * s.wy[b];
-            const float4* gp = gg + (s.ox[a] + s.oy[b]);
+            const uint32_t oab = s.ox[a] + s.oy[b];
             float G0 = 0.f, G1 = 0.f;       // sum_c gw wz[c], sum_c gw dwz[c]
             V3 R0 = v3(0, 0, 0), Rz = v3(0, 0, 0);
 #pragma unroll
             for (int c = 0; c < 3; c++) {
                 V3 q = qb + (float)c * c2;      // value scattered to this node, per unit weight
-                float4 g = gp[s.oz[c]];
+                float4 g = gg[oab + s.oz[c]];
                 float gw = fmaf(g.x, q.x, fmaf(g.y, q.y, fmaf(g.z, q.z, g.w * P.p_mass)));
                 G0 = fmaf(gw, s.wz[c], G0); G1 = fmaf(gw, dwz[c], G1);
                 float wz = s.wz[c];
@@ -817,9 +901,7 @@ __global__ void __launch_bounds__(SMX_TPB, SMX_P2GG_MINB) k_p2g_grad(Params P, P
     V3 gx = P.inv_dx * gfx, gv = P.p_mass * S0, gimp = S0;
     M3 gC = scale(P.p_mass, gaff);
     M3 gstress = scale(P.cs, gaff);
-    M3 gnewF;
-#pragma unroll
-    for (int i = 0; i < 9; i++) gnewF.m[i] = ain[(6 + i) * P.stride + jj];
+    M3 gnewF = load_F(ain, P.stride, jj);
     float tr = trace(gstress), gJ = 0.f;
     M3 gFtmp = m3_zero();
     if (model == 0) {
@@ -827,46 +909,48 @@ __global__ void __launch_bounds__(SMX_TPB, SMX_P2GG_MINB) k_p2g_grad(Params P, P
         if (ptype == 2) {
             gJ += (1.f / 3.f) * cbrtf(m.J) / m.J * trace(gnewF);       // d/dJ J^(1/3); mu == 0 so R carries nothing
         } else {
-            // stress = 2 mu D newF^T, D = newF - R
-            M3 gA = scale(2.f * P.mu, mul(gstress, m.newF));
-            gnewF = add(gnewF, add(scale(2.f * P.mu, Tmul(gstress, m.D)), gA));
-            // folded svd_grad (mpm_simulator.py:140-157): see DESIGN.md "SVD adjoint in divided-difference form"
+            // stress = 2 mu D newF^T, D = newF - R, newF = U diag(1 + g) V^T, D = U diag(g) V^T (g = clipped sigma - 1).
+            // Everything is carried in the singular frame:  Gh = U^T gstress U,  N = U^T gnewF V, and with s = 1 + g
+            //   M1 = U^T (gnewF + 2 mu gstress^T D + 2 mu gstress newF) V = N + 2 mu (Gh^T diag(g) + Gh diag(s))
+            //   M2 = U^T (d R) V = -2 mu Gh diag(s)
+            // followed by the folded svd_grad (mpm_simulator.py:140-157): see DESIGN.md "SVD adjoint in divided-difference form"
             const M3 &U = m.svd.U, &V = m.svd.V;
             const float* e = m.svd.e;
-            M3 M2 = scale(-1.f, mul(Tmul(U, gA), V));      // U^T (d R) V, d R = -gA
-            M3 inner = m3_zero();
-            if (ptype == 0) {
-                M3 M1 = mul(Tmul(U, gnewF), V);
-                float g3[3];
+            float g3[3];
 #pragma unroll
-                for (int i = 0; i < 3; i++) g3[i] = fminf(fmaxf(e[i], -2e-3f), 3e-3f);
+            for (int i = 0; i < 3; i++) g3[i] = ptype == 0 ? fminf(fmaxf(e[i], -2e-3f), 3e-3f) : e[i];
+            M3 Gh = mul(Tmul(U, gstress), U);
+            M3 M1 = mul(Tmul(U, gnewF), V), M2;
+            float mu2 = 2.f * P.mu;
 #pragma unroll
-                for (int i = 0; i < 3; i++) {
-                    // min(max(sig, lo), hi): gradient reaches sig iff lo < sig and max(sig, lo) < hi
-                    inner.m[4 * i] = (e[i] > -2e-3f && e[i] < 3e-3f) ? M1.m[4 * i] : 0.f;
+            for (int i = 0; i < 3; i++)
 #pragma unroll
-                    for (int jx = 0; jx < 3; jx++) {
-                        if (jx == i) continue;
-                        float de = e[jx] - e[i], dg = g3[jx] - g3[i];
-                        float K = __fdividef(1.f, clamp_ref(de * (2.f + e[i] + e[jx])));
+                for (int jx = 0; jx < 3; jx++) {
+                    float gs = mu2 * Gh.m[3 * i + jx] * (1.f + g3[jx]);
+                    M2.m[3 * i + jx] = -gs;
+                    M1.m[3 * i + jx] += fmaf(mu2 * Gh.m[3 * jx + i], g3[jx], gs);
+                }
+            M3 inner;
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                // plastic: min(max(sig, lo), hi): gradient reaches sig iff lo < sig and max(sig, lo) < hi;  elastic: new_F = F_tmp
+                inner.m[4 * i] = (ptype == 1 || (e[i] > -2e-3f && e[i] < 3e-3f)) ? M1.m[4 * i] : 0.f;
+#pragma unroll
+                for (int jx = 0; jx < 3; jx++) {
+                    if (jx == i) continue;
+                    float de = e[jx] - e[i];
+                    float K = __fdividef(1.f, clamp_ref(de * (2.f + e[i] + e[jx])));
+                    if (ptype == 0) {
+                        float dg = g3[jx] - g3[i];
                         float P1 = dg + de + (g3[jx] * e[jx] - g3[i] * e[i]);
                         float Q1 = dg - de + (g3[jx] * e[i] - g3[i] * e[jx]);
                         inner.m[3 * i + jx] = K * (M1.m[3 * i + jx] * P1 + M1.m[3 * jx + i] * Q1 + (M2.m[3 * i + jx] - M2.m[3 * jx + i]) * de);
+                    } else {
+                        inner.m[3 * i + jx] = M1.m[3 * i + jx] + K * (M2.m[3 * i + jx] - M2.m[3 * jx + i]) * de;
                     }
                 }
-            } else {
-                gFtmp = gnewF;      // elastic: new_F = F_tmp
-#pragma unroll
-                for (int i = 0; i < 3; i++)
-#pragma unroll
-                    for (int jx = 0; jx < 3; jx++) {
-                        if (jx == i) continue;
-                        float de = e[jx] - e[i];
-                        float K = __fdividef(1.f, clamp_ref(de * (2.f + e[i] + e[jx])));
-                        inner.m[3 * i + jx] = K * (M2.m[3 * i + jx] - M2.m[3 * jx + i]) * de;
-                    }
             }
-            gFtmp = add(gFtmp, mulT(mul(U, inner), V));
+            gFtmp = mulT(mul(U, inner), V);
         }
     } else {
         M3 sym;
@@ -885,32 +969,39 @@ __global__ void __launch_bounds__(SMX_TPB, SMX_P2GG_MINB) k_p2g_grad(Params P, P
     }
     // compute_F_tmp.grad: dC += dt * gFtmp F^T ; dF = (I + dt C)^T gFtmp
     gC = add(gC, scale(P.dt, mulT(gFtmp, F)));
-    M3 Aq = scale(P.dt, C); Aq.m[0] += 1.f; Aq.m[4] += 1.f; Aq.m[8] += 1.f;
-    M3 gF = Tmul(Aq, gFtmp);
+    M3 gF = add(gFtmp, scale(P.dt, Tmul(C, gFtmp)));
     // control and particle-contact adjoints
-    if (P.n_control > 0 && live) {
-        int ci = ctrl_slot[jj];
-        if (ci >= 0) {
-            ci += bt * P.n_control;
-            float k = 6e-4f * P.dt;
-            atomicAdd(action_grad + 3 * ci, (double)(k * gimp.x)); atomicAdd(action_grad + 3 * ci + 1, (double)(k * gimp.y));
-            atomicAdd(action_grad + 3 * ci + 2, (double)(k * gimp.z));
+    if (EXTRA) {
+        if (P.n_control > 0 && live) {
+            int ci = ctrl_slot[jj];
+            if (ci >= 0) {
+                ci += bt * P.n_control;
+                float k = 6e-4f * P.dt;
+                atomicAdd(action_grad + 3 * ci, (double)(k * gimp.x)); atomicAdd(action_grad + 3 * ci + 1, (double)(k * gimp.y));
+                atomicAdd(action_grad + 3 * ci + 2, (double)(k * gimp.z));
+            }
         }
-    }
-    if (P.ctype == 1) {
-        for (int i = P.np - 1; i >= 0; i--) {
-            if (!ps.prims[i].enabled) continue;
-            PrimState S = load_prim_state(pstate_at(ps, bt, i, f));
-            PrimGrad G = prim_grad_zero();
-            if (live) collide_particle_adj(ps.prims[i], S, x, v, P.dt, gimp, ext_f_grad_at(ps, bt, i), gx, gv, G);
-            commit_prim_grad(pgrad_at(ps, bt, i, f), G, live, bt);
+        if (P.ctype == 1) {
+            for (int i = P.np - 1; i >= 0; i--) {
+                if (!ps.prims[i].enabled) continue;
+                PrimState S = load_prim_state(pstate_at(ps, bt, i, f));
+                PrimGrad G = prim_grad_zero();
+                if (live) collide_particle_adj(ps.prims[i], S, x, v, P.dt, gimp, ext_f_grad_at(ps, bt, i), gx, gv, G);
+                commit_prim_grad(pgrad_at(ps, bt, i, f), G, live, bt);
+            }
         }
     }
     if (!live) return;
-    aout[j] += gx.x; aout[P.stride + j] += gx.y; aout[2 * P.stride + j] += gx.z;
-    aout[3 * P.stride + j] = gv.x; aout[4 * P.stride + j] = gv.y; aout[5 * P.stride + j] = gv.z;
-#pragma unroll
-    for (int i = 0; i < 9; i++) { aout[(6 + i) * P.stride + j] = gF.m[i]; aout[(15 + i) * P.stride + j] = gC.m[i]; }
+    {
+        float4* b = reinterpret_cast<float4*>(aout) + j;
+        float4 a0 = b[0];       // partial d x from the G2P / contact adjoints
+        b[0] = make_float4(a0.x + gx.x, a0.y + gx.y, a0.z + gx.z, gv.x);
+        b[P.stride] = make_float4(gv.y, gv.z, gC.m[0], gC.m[1]);
+        b[2 * P.stride] = make_float4(gC.m[2], gC.m[3], gC.m[4], gC.m[5]);
+        b[3 * P.stride] = make_float4(gC.m[6], gC.m[7], gC.m[8], gF.m[0]);
+        b[4 * P.stride] = make_float4(gF.m[1], gF.m[2], gF.m[3], gF.m[4]);
+        b[5 * P.stride] = make_float4(gF.m[5], gF.m[6], gF.m[7], gF.m[8]);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -920,45 +1011,51 @@ __global__ void k_keys(Params P, const float* __restrict__ fr, uint32_t* __restr
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= P.n) return;
     int clamped;
-    keys[j] = (uint32_t)(batch_of(P, j) * P.Gb) + cell_key(fr[j], fr[P.stride + j], fr[2 * P.stride + j], P.inv_dx, P.ng, P.nb, &clamped);
+    V3 xq = load_x(fr, P.stride, j);
+    keys[j] = (uint32_t)(batch_of(P, j) * P.Gb) + cell_key(xq.x, xq.y, xq.z, P.inv_dx, P.ng, P.nb, &clamped);
     if (iota) iota[j] = j;
     if (clamped && counters) atomicAdd(counters, 1ull);
 }
-// dst[c][j] = src[c][idx[j]] for all 24 components
+// dst[plane][j] = src[plane][idx[j]] for all six planes
 __global__ void k_gather_frame(int n, long long stride, const float* __restrict__ src, float* __restrict__ dst, const uint32_t* __restrict__ idx) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     uint32_t i = idx[j];
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* d4 = reinterpret_cast<float4*>(dst);
 #pragma unroll
-    for (int c = 0; c < 24; c++) dst[c * stride + j] = src[c * stride + i];
+    for (int c = 0; c < SMX_NPLANES; c++) d4[c * stride + j] = s4[c * stride + i];
 }
 // dst[c][idx[j]] = src[c][j]  (inverse of the above; used to carry an adjoint back across a re-sort)
 __global__ void k_scatter_frame(int n, long long stride, const float* __restrict__ src, float* __restrict__ dst, const uint32_t* __restrict__ idx) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     uint32_t i = idx[j];
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* d4 = reinterpret_cast<float4*>(dst);
 #pragma unroll
-    for (int c = 0; c < 24; c++) dst[c * stride + i] = src[c * stride + j];
+    for (int c = 0; c < SMX_NPLANES; c++) d4[c * stride + i] = s4[c * stride + j];
 }
 __global__ void k_compose_perm(int n, const uint32_t* __restrict__ old_perm, const uint32_t* __restrict__ idx, uint32_t* __restrict__ new_perm) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j < n) new_perm[j] = old_perm ? old_perm[idx[j]] : idx[j];
 }
-// staging (n, ncomp) AoS in particle-id order  <->  frame SoA in storage order
+// staging (n, ncomp) AoS in particle-id order, get_state columns c0.. <->  frame planes in storage order
 __global__ void k_upload(int n, long long stride, const float* __restrict__ aos, int ncomp, int c0, float* __restrict__ fr, const uint32_t* __restrict__ perm, int accumulate) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     uint32_t p = perm ? perm[j] : j;
     for (int c = 0; c < ncomp; c++) {
         float v = aos[(size_t)p * ncomp + c];
-        if (accumulate) fr[(c0 + c) * stride + j] += v; else fr[(c0 + c) * stride + j] = v;
+        long long k = comp_index(stride, j, c0 + c);
+        if (accumulate) fr[k] += v; else fr[k] = v;
     }
 }
 __global__ void k_download(int n, long long stride, float* __restrict__ aos, int ncomp, int c0, const float* __restrict__ fr, const uint32_t* __restrict__ perm) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     uint32_t p = perm ? perm[j] : j;
-    for (int c = 0; c < ncomp; c++) aos[(size_t)p * ncomp + c] = fr[(c0 + c) * stride + j];
+    for (int c = 0; c < ncomp; c++) aos[(size_t)p * ncomp + c] = fr[comp_index(stride, j, c0 + c)];
 }
 __global__ void k_permute_i32(int n, const int* __restrict__ src, int* __restrict__ dst, const uint32_t* __restrict__ perm) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -986,9 +1083,10 @@ __global__ void k_mark_blocks(Params P, const float* __restrict__ fr, int margin
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= P.n) return;
     int b[3];
-    b[0] = clampi((int)(fr[j] * P.inv_dx - 0.5f), 0, P.ng - 3);
-    b[1] = clampi((int)(fr[P.stride + j] * P.inv_dx - 0.5f), 0, P.ng - 3);
-    b[2] = clampi((int)(fr[2 * P.stride + j] * P.inv_dx - 0.5f), 0, P.ng - 3);
+    V3 xq = load_x(fr, P.stride, j);
+    b[0] = clampi((int)(xq.x * P.inv_dx - 0.5f), 0, P.ng - 3);
+    b[1] = clampi((int)(xq.y * P.inv_dx - 0.5f), 0, P.ng - 3);
+    b[2] = clampi((int)(xq.z * P.inv_dx - 0.5f), 0, P.ng - 3);
     int lo[3], hi[3];
     for (int d = 0; d < 3; d++) { lo[d] = max(b[d] - margin, 0) >> 2; hi[d] = min(b[d] + 2 + margin, P.ng - 1) >> 2; }
     for (int i = lo[0]; i <= hi[0]; i++)
@@ -1053,7 +1151,7 @@ __global__ void k_mark_column(uint32_t* __restrict__ flags, int nb, int col) {
 __global__ void k_check_slab(Params P, const float* __restrict__ fr, int lo_col, int hi_col, unsigned long long* counters) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= P.n) return;
-    int b0 = clampi((int)(fr[j] * P.inv_dx - 0.5f), 0, P.ng - 3);
+    int b0 = clampi((int)(load_x(fr, P.stride, j).x * P.inv_dx - 0.5f), 0, P.ng - 3);
     if ((b0 >> 2) < lo_col || ((b0 + 2) >> 2) > hi_col) atomicAdd(counters + 1, 1ull);
 }
 __global__ void k_compact_blocks(int nblk, const uint32_t* __restrict__ flags, uint32_t* __restrict__ list, int* __restrict__ count) {
@@ -1077,8 +1175,9 @@ __global__ void __launch_bounds__(256) k_clear_blocks(const uint32_t* __restrict
 __global__ void k_check_active(Params P, const float* __restrict__ fr, const uint32_t* __restrict__ flags, unsigned long long* counters) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= P.n) return;
-    int b0 = clampi((int)(fr[j] * P.inv_dx - 0.5f), 0, P.ng - 3), b1 = clampi((int)(fr[P.stride + j] * P.inv_dx - 0.5f), 0, P.ng - 3),
-        b2 = clampi((int)(fr[2 * P.stride + j] * P.inv_dx - 0.5f), 0, P.ng - 3);
+    V3 xq = load_x(fr, P.stride, j);
+    int b0 = clampi((int)(xq.x * P.inv_dx - 0.5f), 0, P.ng - 3), b1 = clampi((int)(xq.y * P.inv_dx - 0.5f), 0, P.ng - 3),
+        b2 = clampi((int)(xq.z * P.inv_dx - 0.5f), 0, P.ng - 3);
     bool ok = true;
     for (int i = b0 >> 2; i <= (b0 + 2) >> 2; i++)
         for (int jj = b1 >> 2; jj <= (b1 + 2) >> 2; jj++)
@@ -1120,7 +1219,8 @@ __global__ void __launch_bounds__(128) k_chamfer(Params P, const float* __restri
     if (pass == 0) {
         bool live = t < P.n;
         int j = live ? t : P.n - 1;
-        float x = fr[j], y = fr[P.stride + j], z = fr[2 * P.stride + j];
+        V3 xq = load_x(fr, P.stride, j);
+        float x = xq.x, y = xq.y, z = xq.z;
         float best = 3.0e38f; int bi = 0;
         for (int base = 0; base < m; base += SMX_CH_TILE) {
             int cnt = min(SMX_CH_TILE, m - base);
@@ -1154,7 +1254,8 @@ __global__ void __launch_bounds__(128) k_chamfer(Params P, const float* __restri
         int j0 = b * P.npb, j1 = j0 + P.npb;
         {
             for (int j = j0; j < j1; j++) {     // particle coordinates are read straight from the frame (L1/L2 resident, warp-uniform address)
-                float dx = fr[j] - tx, dy = fr[P.stride + j] - ty, dz = fr[2 * P.stride + j] - tz;
+                V3 xq = load_x(fr, P.stride, j);
+                float dx = xq.x - tx, dy = xq.y - ty, dz = xq.z - tz;
                 float d = dx * dx + dy * dy + dz * dz;
                 uint32_t id = perm ? perm[j] : (uint32_t)j;
                 if (d < best || (d == best && id < bid)) { best = d; bid = id; bj = j; }
@@ -1162,7 +1263,8 @@ __global__ void __launch_bounds__(128) k_chamfer(Params P, const float* __restri
         }
         float part = 0.f;
         if (live && P.npb > 0) {
-            float dx = fr[bj] - tx, dy = fr[P.stride + bj] - ty, dz = fr[2 * P.stride + bj] - tz;
+            V3 xq = load_x(fr, P.stride, bj);
+            float dx = xq.x - tx, dy = xq.y - ty, dz = xq.z - tz;
             atomicAdd(seed + (size_t)bid * ncols, 2.f * weight * dx); atomicAdd(seed + (size_t)bid * ncols + 1, 2.f * weight * dy);
             atomicAdd(seed + (size_t)bid * ncols + 2, 2.f * weight * dz);
             part = dx * dx + dy * dy + dz * dz;
