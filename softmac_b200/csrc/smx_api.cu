@@ -91,6 +91,7 @@ struct smx_sim {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     int sm_count = 148;
+    int pf_sc = 0, pf_g = 0, pf_g2p = 0;   // L2 prefetch distances (particles): one wave of resident CTAs of the scatter / gather kernels
     int B = 1;                          // batched independent rollouts
     // spatial slab decomposition (one rank of several): owned x-block columns [slab_lo, slab_hi), neighbours present?
     bool slab = false, halo_lo = false, halo_hi = false;
@@ -369,11 +370,11 @@ static int forward_p2g(smx_sim* s, int f, bool write_F, bool accumulate, bool fu
         TRY(dispatch_mat(P.material, P.ptype, [&](auto mat) {
             constexpr int M = decltype(mat)::value;
             if (s->cfg.flags & SMX_FLAG_DIRECT_RED) {
-                if (extra) k_p2g<M, false, true><<<grid, SMX_TPB_SC, 0, s->stream>>>(P, ps, f, fin, fout, s->g_in, cslot, s->action, acc, fprev, gprev, rec);
-                else k_p2g<M, false, false><<<grid, SMX_TPB_SC, 0, s->stream>>>(P, ps, f, fin, fout, s->g_in, cslot, s->action, acc, fprev, gprev, rec);
+                if (extra) k_p2g<M, false, true><<<grid, SMX_TPB_SC, 0, s->stream>>>(P, ps, f, fin, fout, s->g_in, cslot, s->action, acc, fprev, gprev, rec, s->pf_sc);
+                else k_p2g<M, false, false><<<grid, SMX_TPB_SC, 0, s->stream>>>(P, ps, f, fin, fout, s->g_in, cslot, s->action, acc, fprev, gprev, rec, s->pf_sc);
             } else {
-                if (extra) k_p2g<M, true, true><<<grid, SMX_TPB_SC, 0, s->stream>>>(P, ps, f, fin, fout, s->g_in, cslot, s->action, acc, fprev, gprev, rec);
-                else k_p2g<M, true, false><<<grid, SMX_TPB_SC, 0, s->stream>>>(P, ps, f, fin, fout, s->g_in, cslot, s->action, acc, fprev, gprev, rec);
+                if (extra) k_p2g<M, true, true><<<grid, SMX_TPB_SC, 0, s->stream>>>(P, ps, f, fin, fout, s->g_in, cslot, s->action, acc, fprev, gprev, rec, s->pf_sc);
+                else k_p2g<M, true, false><<<grid, SMX_TPB_SC, 0, s->stream>>>(P, ps, f, fin, fout, s->g_in, cslot, s->action, acc, fprev, gprev, rec, s->pf_sc);
             }
             CKLN(s, fprev ? "k_g2p2g" : "k_p2g"); return (int)SMX_OK;
         }));
@@ -497,6 +498,8 @@ int smx_create(const smx_config* cfg, smx_sim** out) {
     s->cfg = *cfg;
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, cfg->device));
     s->sm_count = prop.multiProcessorCount;
+    s->pf_sc = s->sm_count * SMX_SC_MINB * SMX_TPB_SC; s->pf_g = s->sm_count * SMX_P2GG_MINB * SMX_TPB; s->pf_g2p = s->sm_count * 8 * SMX_TPB;
+    if (getenv("SMX_NO_PREFETCH")) s->pf_sc = s->pf_g = s->pf_g2p = 1 << 30;
     if (cfg->stream || (cfg->flags & SMX_FLAG_EXTERNAL_STREAM)) s->stream = (cudaStream_t)cfg->stream;   // NULL + flag: the legacy default stream
     else { CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)); s->own_stream = true; }
     Params& P = s->P;
@@ -985,7 +988,7 @@ int smx_substep_end(smx_sim* s, int32_t f) {
     s->mid_done = -1;
     TRY(forward_grid_save_contact(s, f));
     s->last_fwd = f;
-    if (s->P.n > 0) { k_g2p<<<nblk(s->P.n, SMX_TPB), SMX_TPB, 0, s->stream>>>(s->P, s->frame_ptr(f), s->frame_ptr(f + 1), s->g_out); CKLN(s, "k_g2p"); }
+    if (s->P.n > 0) { k_g2p<<<nblk(s->P.n, SMX_TPB), SMX_TPB, 0, s->stream>>>(s->P, s->frame_ptr(f), s->frame_ptr(f + 1), s->g_out, s->pf_g2p); CKLN(s, "k_g2p"); }
     if (s->cfg.sort_every > 0 && (f + 1) % s->cfg.sort_every == 0 && !(s->cfg.flags & SMX_FLAG_NO_SORT)) TRY(resort(s, f + 1, true));
     return SMX_OK;
 }
@@ -1041,8 +1044,8 @@ int smx_substep_grad_begin(smx_sim* s, int32_t f) {
     s->g_in_clean_uid = -1;             // g_in now holds substep f's values
     const float* fin = s->frame_ptr(f);
     if (P.n > 0) {
-        if (s->cfg.flags & SMX_FLAG_DIRECT_RED) k_g2p_grad<false><<<nblk(P.n, SMX_TPB_SC), SMX_TPB_SC, 0, s->stream>>>(P, fin, s->adj_cur, s->adj_nxt, s->g_out, s->gg_out);
-        else k_g2p_grad<true><<<nblk(P.n, SMX_TPB_SC), SMX_TPB_SC, 0, s->stream>>>(P, fin, s->adj_cur, s->adj_nxt, s->g_out, s->gg_out);
+        if (s->cfg.flags & SMX_FLAG_DIRECT_RED) k_g2p_grad<false><<<nblk(P.n, SMX_TPB_SC), SMX_TPB_SC, 0, s->stream>>>(P, fin, s->adj_cur, s->adj_nxt, s->g_out, s->gg_out, s->pf_sc);
+        else k_g2p_grad<true><<<nblk(P.n, SMX_TPB_SC), SMX_TPB_SC, 0, s->stream>>>(P, fin, s->adj_cur, s->adj_nxt, s->g_out, s->gg_out, s->pf_sc);
         CKLN(s, "k_g2p_grad");
     }
     s->grad_pending = f;
@@ -1089,11 +1092,11 @@ int smx_substep_grad_end(smx_sim* s, int32_t f) {
         TRY(dispatch_mat(P.material, P.ptype, [&](auto mat) {
             constexpr int M = decltype(mat)::value;
             if (use_rec) {
-                if (extra) k_p2g_grad<M, true, true><<<grid, SMX_TPB, 0, s->stream>>>(P, ps, f, fin, s->adj_cur, s->adj_nxt, s->gg_out, cslot, s->action, s->action_grad, rec);
-                else k_p2g_grad<M, true, false><<<grid, SMX_TPB, 0, s->stream>>>(P, ps, f, fin, s->adj_cur, s->adj_nxt, s->gg_out, cslot, s->action, s->action_grad, rec);
+                if (extra) k_p2g_grad<M, true, true><<<grid, SMX_TPB, 0, s->stream>>>(P, ps, f, fin, s->adj_cur, s->adj_nxt, s->gg_out, cslot, s->action, s->action_grad, rec, s->pf_g);
+                else k_p2g_grad<M, true, false><<<grid, SMX_TPB, 0, s->stream>>>(P, ps, f, fin, s->adj_cur, s->adj_nxt, s->gg_out, cslot, s->action, s->action_grad, rec, s->pf_g);
             } else {
-                if (extra) k_p2g_grad<M, false, true><<<grid, SMX_TPB, 0, s->stream>>>(P, ps, f, fin, s->adj_cur, s->adj_nxt, s->gg_out, cslot, s->action, s->action_grad, rec);
-                else k_p2g_grad<M, false, false><<<grid, SMX_TPB, 0, s->stream>>>(P, ps, f, fin, s->adj_cur, s->adj_nxt, s->gg_out, cslot, s->action, s->action_grad, rec);
+                if (extra) k_p2g_grad<M, false, true><<<grid, SMX_TPB, 0, s->stream>>>(P, ps, f, fin, s->adj_cur, s->adj_nxt, s->gg_out, cslot, s->action, s->action_grad, rec, s->pf_g);
+                else k_p2g_grad<M, false, false><<<grid, SMX_TPB, 0, s->stream>>>(P, ps, f, fin, s->adj_cur, s->adj_nxt, s->gg_out, cslot, s->action, s->action_grad, rec, s->pf_g);
             }
             CKLN(s, "k_p2g_grad"); return (int)SMX_OK;
         }));
@@ -1165,7 +1168,7 @@ int smx_step(smx_sim* s, int32_t s0, int32_t count) {
         bool resort_next = s->cfg.sort_every > 0 && (f + 1) % s->cfg.sort_every == 0 && !(s->cfg.flags & SMX_FLAG_NO_SORT);
         bool last = (i == count - 1);
         if (!last && !resort_next && f + 2 < s->cfg.max_steps && !s->ckpt_dirty) { pending_g2p = true; continue; }
-        k_g2p<<<nblk(s->P.n, SMX_TPB), SMX_TPB, 0, s->stream>>>(s->P, s->frame_ptr(f), s->frame_ptr(f + 1), s->g_out); CKLN(s, "k_g2p");
+        k_g2p<<<nblk(s->P.n, SMX_TPB), SMX_TPB, 0, s->stream>>>(s->P, s->frame_ptr(f), s->frame_ptr(f + 1), s->g_out, s->pf_g2p); CKLN(s, "k_g2p");
         if (resort_next) TRY(resort(s, f + 1, true));
     }
     return SMX_OK;

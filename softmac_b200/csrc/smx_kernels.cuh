@@ -73,13 +73,24 @@ __device__ __forceinline__ float4 ld_plane(const float* __restrict__ fr, long lo
 __device__ __forceinline__ void st_plane(float* __restrict__ fr, long long stride, int j, int p, float4 v) {
     reinterpret_cast<float4*>(fr)[(long long)p * stride + j] = v;
 }
+// L2 prefetch of planes [p0, p1) of particle slot j (issued one wave of CTAs ahead of the loads: the streaming frame data
+// then arrives from L2 instead of HBM when its CTA starts)
+#ifndef SMX_PF_WAVE
+#define SMX_PF_WAVE 1
+#endif
+__device__ __forceinline__ void prefetch_planes(const void* fr, long long stride, long long j, long long n, int p0, int p1) {
+    if (!SMX_PF_WAVE || j >= n) return;
+    const float4* b = reinterpret_cast<const float4*>(fr) + j;
+    for (int p = p0; p < p1; p++) asm volatile("prefetch.global.L2 [%0];" ::"l"(b + p * stride));
+}
 __device__ __forceinline__ V3 load_x(const float* __restrict__ fr, long long stride, int j) {
     float4 a = ld_plane(fr, stride, j, 0);
     return v3(a.x, a.y, a.z);
 }
 
 #define SMX_TPB 128         // gather-type particle kernels
-#define SMX_TPB_SC 64       // scatter-type particle kernels (two warps: 2 x 13.8 KB of staging)
+#define SMX_TPB_SC 96       // scatter-type particle kernels (three warps x 14.6 KB of staging; five CTAs per SM)
+#define SMX_SC_MINB 5
 
 __device__ __forceinline__ void red_add_f4(float4* addr, float a, float b, float c, float d) {
     // one 16-byte reduction (SASS: REDG.E.ADD.F32x4) instead of four scalar atomics
@@ -89,16 +100,15 @@ __device__ __forceinline__ void red_add_f4(float4* addr, float a, float b, float
 // ------------------------------------------------------------------------------------------------
 // Warp-level aggregation of the 27-node scatter.  Particles are stored sorted by cell, so the 32
 // particles of a warp fall into a handful of runs with the same base cell.  Every lane parks its 27
-// float4 contributions in shared memory; the warp then re-partitions the work as (run, node offset)
-// tasks, each task sums one node's contributions over its run in particle order and issues ONE
-// REDG.E.ADD.F32x4.  With ~8 particles per cell this cuts the L2 reductions ~7x (27 per particle ->
-// 27 per run) and makes the within-run summation order deterministic.
+// float4 contributions and its 9 per-axis node offsets in shared memory; then lane o < 27 owns stencil
+// node o and walks the warp's particles in order, run by run (the run boundaries come from one ballot,
+// so the walk is warp-uniform: no divergence, conflict-free 128-bit shared loads), and issues ONE
+// REDG.E.ADD.F32x4 per run and node.  With ~8 particles per cell this cuts the L2 reductions ~7x
+// (27 per particle -> 27 per run) and makes the within-run summation order deterministic.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t node_index(int i, int j, int k, int nb);
 struct WarpStage {
     float4 val[32 * 27];    // [lane][offset]; row stride 27 float4 -> conflict-free 128-bit stores
-    uint32_t key[32];       // packed base cell of each run
-    uint8_t start[36];      // first lane of each run (+ sentinel); bytes, so that 8 CTAs x 2 warps fit the 227 KB of an SM
+    uint32_t off[32 * 9];   // [lane][ox0..2 oy0..2 oz0..2]: block-major node offsets per axis
 };
 __device__ __forceinline__ uint32_t pack_base(int bx, int by, int bz, int bt = 0) { return (uint32_t)bx | ((uint32_t)by << 8) | ((uint32_t)bz << 16) | ((uint32_t)bt << 24); }
 
@@ -109,38 +119,43 @@ __device__ __forceinline__ void add_f4(float4& a, const float4& b) {
     a = make_float4(lo.x, lo.y, hi.x, hi.y);
 }
 
-__device__ __forceinline__ void warp_stage_flush(WarpStage& st, uint32_t key, bool live, float4* __restrict__ grid, int nb, int Gb) {
+struct Stencil;
+__device__ __forceinline__ void warp_stage_flush(WarpStage& st, const uint32_t* ox, const uint32_t* oy, const uint32_t* oz, uint32_t key, bool live,
+                                                 float4* __restrict__ grid) {
     const unsigned lane = threadIdx.x & 31;
+    {
+        uint32_t* my = st.off + lane * 9;
+#pragma unroll
+        for (int a = 0; a < 3; a++) { my[a] = ox[a]; my[3 + a] = oy[a]; my[6 + a] = oz[a]; }
+    }
     uint32_t k = live ? key : 0xffffffffu;
     uint32_t prev = __shfl_up_sync(0xffffffffu, k, 1);
     bool head = (lane == 0) || (k != prev);
     unsigned heads = __ballot_sync(0xffffffffu, head);
-    int nruns = __popc(heads);
-    int rank = __popc(heads & ((1u << lane) - 1u));
-    if (head) { st.start[rank] = (uint8_t)lane; st.key[rank] = k; }
-    if (lane == 0) st.start[nruns] = 32;
+    unsigned alive = __ballot_sync(0xffffffffu, live);
     __syncwarp();
-    int ntasks = nruns * 27;
-    for (int t = lane; t < ntasks; t += 32) {
-        int r = t / 27, o = t - 27 * r;
-        uint32_t kk = st.key[r];
-        if (kk == 0xffffffffu) continue;
-        int p0 = st.start[r], p1 = st.start[r + 1];
-        const float4* src = st.val + p0 * 27 + o;
-        float4 acc = src[0];
+    if (lane >= 27) return;
+    const int a = lane / 9, b = (lane / 3) % 3, c = lane % 3;
+    const float4* src = st.val + lane;
+    unsigned h = heads;
+    while (h) {                                     // warp-uniform: one trip per run
+        int p0 = __ffs(h) - 1;
+        h &= h - 1;
+        int p1 = h ? __ffs(h) - 1 : 32;
+        if (!((alive >> p0) & 1u)) break;           // the tail run of slots past the last particle
+        const float4* q = src + p0 * 27;
+        float4 acc = q[0], acc2 = make_float4(0.f, 0.f, 0.f, 0.f);
         int cnt = p1 - p0 - 1;
-        src += 27;
-        // two independent accumulators, four particles per trip
-        float4 acc2 = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (; cnt >= 4; cnt -= 4, src += 4 * 27) {
-            float4 v0 = src[0], v1 = src[27], v2 = src[54], v3 = src[81];
+        q += 27;
+        for (; cnt >= 4; cnt -= 4, q += 4 * 27) {   // two independent accumulators, four particles per trip
+            float4 v0 = q[0], v1 = q[27], v2 = q[54], v3 = q[81];
             add_f4(acc, v0); add_f4(acc2, v1); add_f4(acc, v2); add_f4(acc2, v3);
         }
-        if (cnt >= 2) { float4 v0 = src[0], v1 = src[27]; add_f4(acc, v0); add_f4(acc2, v1); src += 2 * 27; cnt -= 2; }
-        if (cnt >= 1) { float4 v0 = src[0]; add_f4(acc, v0); }
+        if (cnt >= 2) { float4 v0 = q[0], v1 = q[27]; add_f4(acc, v0); add_f4(acc2, v1); q += 2 * 27; cnt -= 2; }
+        if (cnt >= 1) { float4 v0 = q[0]; add_f4(acc, v0); }
         add_f4(acc, acc2);
-        int a = o / 9, b = (o - 9 * a) / 3, c = o - 9 * a - 3 * b;
-        atomicAdd(grid + ((kk >> 24) * (uint32_t)Gb + node_index((int)(kk & 0xffu) + a, (int)((kk >> 8) & 0xffu) + b, (int)((kk >> 16) & 0xffu) + c, nb)), acc);
+        const uint32_t* o = st.off + p0 * 9;
+        atomicAdd(grid + (o[a] + o[3 + b] + o[6 + c]), acc);
     }
 }
 
@@ -388,16 +403,17 @@ __device__ __forceinline__ void g2p_gather(const Params& P, const Stencil& s, co
 // STAGED: warp-aggregated scatter through shared memory (default); otherwise one REDG per node.
 // ------------------------------------------------------------------------------------------------
 template <int MAT, bool STAGED, bool EXTRA>
-__global__ void __launch_bounds__(SMX_TPB_SC, 8) k_p2g(Params P, PrimSet ps, int f, float* __restrict__ fin, float* __restrict__ fout,
+__global__ void __launch_bounds__(SMX_TPB_SC, SMX_SC_MINB) k_p2g(Params P, PrimSet ps, int f, float* __restrict__ fin, float* __restrict__ fout,
                                                     float4* __restrict__ g_in, const int* __restrict__ ctrl_slot,
                                                     const float* __restrict__ action, int accumulate,
-                                                    const float* __restrict__ fprev, const float4* __restrict__ g_prev, float4* __restrict__ rec) {
+                                                    const float* __restrict__ fprev, const float4* __restrict__ g_prev, float4* __restrict__ rec, int pf_dist) {
     // EXTRA: particle-contact impulses (collision_type == 1) and / or particle control forces are present
     __shared__ WarpStage stage[STAGED ? SMX_TPB_SC / 32 : 1];
     constexpr bool has_svd = (MAT / 3 == 0) && (MAT % 3 != 2);
     int j = blockIdx.x * SMX_TPB_SC + threadIdx.x;
     bool live = j < P.n;
     int jj = live ? j : P.n - 1;
+    if (!fprev) prefetch_planes(fin, P.stride, (long long)j + pf_dist, P.n, 0, SMX_NPLANES);
     V3 x, v; M3 F, C;
     int bt = batch_of(P, jj);
     if (fprev) {        // fused G2P of substep f-1: frame f-1 -> x, v, C of frame f
@@ -445,7 +461,7 @@ __global__ void __launch_bounds__(SMX_TPB_SC, 8) k_p2g(Params P, PrimSet ps, int
             }
         }
     }
-    if (STAGED) warp_stage_flush(stage[threadIdx.x >> 5], pack_base(s.bx, s.by, s.bz, bt), live, g_in, P.nb, P.Gb);
+    if (STAGED) warp_stage_flush(stage[threadIdx.x >> 5], s.ox, s.oy, s.oz, pack_base(s.bx, s.by, s.bz, bt), live, g_in);
 }
 
 // boundary_condition (mpm_simulator.py:268-281); mask bit d cleared where component d was zeroed
@@ -582,9 +598,10 @@ __global__ void __launch_bounds__(SMX_TPB) k_contact(Params P, PrimSet ps, int f
 // ------------------------------------------------------------------------------------------------
 // G2P: gather v, C (APIC) and advect.  Writes x, v, C of frame f+1.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SMX_TPB) k_g2p(Params P, const float* __restrict__ fin, float* __restrict__ fout, const float4* __restrict__ g_out) {
+__global__ void __launch_bounds__(SMX_TPB) k_g2p(Params P, const float* __restrict__ fin, float* __restrict__ fout, const float4* __restrict__ g_out, int pf_dist) {
     int j = blockIdx.x * SMX_TPB + threadIdx.x;
     if (j >= P.n) return;
+    prefetch_planes(fin, P.stride, (long long)j + pf_dist, P.n, 0, 1);
     V3 x = load_x(fin, P.stride, j);
     Stencil s = make_stencil(x.x, x.y, x.z, P, batch_of(P, j));
     V3 nv; M3 Cn;
@@ -597,12 +614,14 @@ __global__ void __launch_bounds__(SMX_TPB) k_g2p(Params P, const float* __restri
 //   ain  = adjoint of frame f+1 (x 0..2, v 3..5, C 15..23), aout = adjoint of frame f (x written here)
 // ------------------------------------------------------------------------------------------------
 template <bool STAGED>
-__global__ void __launch_bounds__(SMX_TPB_SC, 8) k_g2p_grad(Params P, const float* __restrict__ fin, const float* __restrict__ ain,
-                                                         float* __restrict__ aout, const float4* __restrict__ g_out, float4* __restrict__ gg_out) {
+__global__ void __launch_bounds__(SMX_TPB_SC, SMX_SC_MINB) k_g2p_grad(Params P, const float* __restrict__ fin, const float* __restrict__ ain,
+                                                         float* __restrict__ aout, const float4* __restrict__ g_out, float4* __restrict__ gg_out, int pf_dist) {
     __shared__ WarpStage stage[STAGED ? SMX_TPB_SC / 32 : 1];
     int j = blockIdx.x * SMX_TPB_SC + threadIdx.x;
     bool live = j < P.n;
     int jj = live ? j : P.n - 1;
+    prefetch_planes(fin, P.stride, (long long)j + pf_dist, P.n, 0, 1);
+    prefetch_planes(ain, P.stride, (long long)j + pf_dist, P.n, 0, 4);
     V3 x = load_x(fin, P.stride, jj);
     int bt = batch_of(P, jj);
     Stencil s = make_stencil(x.x, x.y, x.z, P, bt);
@@ -655,7 +674,7 @@ __global__ void __launch_bounds__(SMX_TPB_SC, 8) k_g2p_grad(Params P, const floa
         // partial d x of frame f (the contact adjoint and P2G adjoint add theirs); the rest of the plane is written by P2G adjoint
         st_plane(aout, P.stride, j, 0, make_float4(gx1.x + P.inv_dx * gfx.x, gx1.y + P.inv_dx * gfx.y, gx1.z + P.inv_dx * gfx.z, 0.f));
     }
-    if (STAGED) warp_stage_flush(stage[threadIdx.x >> 5], pack_base(s.bx, s.by, s.bz, bt), live, gg_out, P.nb, P.Gb);
+    if (STAGED) warp_stage_flush(stage[threadIdx.x >> 5], s.ox, s.oy, s.oz, pack_base(s.bx, s.by, s.bz, bt), live, gg_out);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -833,20 +852,30 @@ __global__ void __launch_bounds__(256) k_grid_grad(Params P, PrimSet ps, int f, 
 template <int MAT, bool REC, bool EXTRA>
 __global__ void __launch_bounds__(SMX_TPB, SMX_P2GG_MINB) k_p2g_grad(Params P, PrimSet ps, int f, const float* __restrict__ fin, const float* __restrict__ ain,
                                                       float* __restrict__ aout, const float4* __restrict__ gg, const int* __restrict__ ctrl_slot,
-                                                      const float* __restrict__ action, double* __restrict__ action_grad, const float4* __restrict__ rec) {
+                                                      const float* __restrict__ action, double* __restrict__ action_grad, const float4* __restrict__ rec, int pf_dist) {
     constexpr int model = MAT / 3, ptype = MAT % 3;
     constexpr bool corot = model == 0 && ptype != 2;
     int j = blockIdx.x * SMX_TPB + threadIdx.x;
     bool live = j < P.n;
     int jj = live ? j : P.n - 1;
+    {
+        long long jp = (long long)j + pf_dist;
+        prefetch_planes(fin, P.stride, jp, P.n, 0, SMX_NPLANES);
+        if (REC && corot) prefetch_planes(rec, P.stride, jp, P.n, 0, SMX_RPLANES);
+        prefetch_planes(ain, P.stride, jp, P.n, 3, SMX_NPLANES);
+        prefetch_planes(aout, P.stride, jp, P.n, 0, 1);
+    }
     V3 x, v; M3 F, C;
     load_state(fin, P.stride, jj, x, v, F, C);
+    Material m;
+    if (REC && corot) load_svd_rec(rec, P.stride, jj, m.svd, m.Jm1);
+    // every streaming load is issued up front (they are all in flight together); the adjoint inputs are consumed last
+    M3 gnewF = load_F(ain, P.stride, jj);
+    const float4 gx_part = reinterpret_cast<const float4*>(aout)[jj];      // partial d x from the G2P / contact adjoints
     int bt = batch_of(P, jj);
     V3 imp = v3(0, 0, 0);
     if (EXTRA) imp = particle_impulses(P, ps, f, jj, bt, live, x, v, ctrl_slot, action, false);
-    Material m;
     M3 Et = compute_Et(C, F, P.dt);
-    if (REC && corot) load_svd_rec(rec, P.stride, jj, m.svd, m.Jm1);
     material_update<MAT, REC>(Et, P, m);
     M3 A;
 #pragma unroll
@@ -901,7 +930,6 @@ __global__ void __launch_bounds__(SMX_TPB, SMX_P2GG_MINB) k_p2g_grad(Params P, P
     V3 gx = P.inv_dx * gfx, gv = P.p_mass * S0, gimp = S0;
     M3 gC = scale(P.p_mass, gaff);
     M3 gstress = scale(P.cs, gaff);
-    M3 gnewF = load_F(ain, P.stride, jj);
     float tr = trace(gstress), gJ = 0.f;
     M3 gFtmp = m3_zero();
     if (model == 0) {
@@ -994,8 +1022,7 @@ __global__ void __launch_bounds__(SMX_TPB, SMX_P2GG_MINB) k_p2g_grad(Params P, P
     if (!live) return;
     {
         float4* b = reinterpret_cast<float4*>(aout) + j;
-        float4 a0 = b[0];       // partial d x from the G2P / contact adjoints
-        b[0] = make_float4(a0.x + gx.x, a0.y + gx.y, a0.z + gx.z, gv.x);
+        b[0] = make_float4(gx_part.x + gx.x, gx_part.y + gx.y, gx_part.z + gx.z, gv.x);
         b[P.stride] = make_float4(gv.y, gv.z, gC.m[0], gC.m[1]);
         b[2 * P.stride] = make_float4(gC.m[2], gC.m[3], gC.m[4], gC.m[5]);
         b[3 * P.stride] = make_float4(gC.m[6], gC.m[7], gC.m[8], gF.m[0]);
