@@ -77,6 +77,8 @@ typedef struct {
                                      same stream interleave with the kernels without extra synchronisation (slab halo exchange) */
 #define SMX_FLAG_NO_FUSION 32       /* smx_step launches G2P and the next P2G separately instead of the fused G2P2G kernel */
 #define SMX_FLAG_DIRECT_RED 4     /* one L2 reduction per particle and node instead of the warp-aggregated scatter (ablation) */
+#define SMX_FLAG_NO_TMA 128       /* particle kernels read their streaming planes straight from HBM instead of the persistent,
+                                     TMA-staged (cp.async.bulk + mbarrier, double-buffered) variants (ablation) */
 #define SMX_FLAG_NO_SVD_REC 64    /* do not keep the per-substep SVD records (64 B per particle and substep); the adjoint repeats the SVD */
 
 /* lifetime ------------------------------------------------------------------------------------- */

@@ -19,6 +19,7 @@ SMX_FLAG_NO_GRID_CKPT = 8
 SMX_FLAG_EXTERNAL_STREAM = 16
 SMX_FLAG_NO_FUSION = 32
 SMX_FLAG_NO_SVD_REC = 64
+SMX_FLAG_NO_TMA = 128
 
 
 class SmxConfig(C.Structure):

@@ -108,7 +108,10 @@ struct smx_sim {
     long long next_uid = 1;
     // grid
     size_t G = 0;
-    float4 *g_in = nullptr, *g_out = nullptr, *g_mix = nullptr, *gg_out = nullptr, *gg_mix = nullptr, *g_lin = nullptr;
+    float4 *g_in = nullptr, *g_out = nullptr, *g_mix = nullptr, *gg_out = nullptr, *gg_out_b = nullptr, *gg_mix = nullptr, *g_lin = nullptr;
+    // adjoint grid of substep f: double-buffered by parity so that k_grid_grad(f) can already clear the one of substep f-1
+    float4* gg_of(int f) { return (slab || !(f & 1)) ? gg_out : gg_out_b; }
+    int bwd_prepared = -1; long long bwd_prepared_uid = -1;   // substep whose g_out / g_mix / cleared gg are already in place (by k_grid_grad of the next substep)
     // grid checkpoints (g_in, g_out[, g_mix] on the active blocks of every substep) so that the adjoint does not
     // re-run P2G and the grid update (north_star: "per-substep state buffers resident in HBM rather than recomputed")
     float4* ckpt = nullptr;
@@ -360,6 +363,7 @@ static int forward_p2g(smx_sim* s, int f, bool write_F, bool accumulate, bool fu
     TRY(ctrl_slots(s, s->order_of[f], &cslot));
     if (s->g_in_clean_uid != o.uid) TRY(clear_grids(s, o, s->g_in, nullptr, nullptr));
     s->g_in_clean_uid = -1;             // P2G is about to write it
+    s->bwd_prepared = -1;
     if (s->slab && P.n > 0) {
         k_check_slab<<<nblk(P.n, 256), 256, 0, s->stream>>>(P, fin, s->halo_lo ? s->slab_lo - 1 : 0, s->halo_hi ? s->slab_hi : P.nb - 1, s->counters); CKL(s);
     }
@@ -541,7 +545,8 @@ int smx_create(const smx_config* cfg, smx_sim** out) {
     }
     s->ckpt_enabled = !(cfg->flags & SMX_FLAG_NO_GRID_CKPT);
     CK(cudaMalloc(&s->g_in, s->G * sizeof(float4))); CK(cudaMalloc(&s->g_out, s->G * sizeof(float4))); CK(cudaMalloc(&s->g_mix, s->G * sizeof(float4)));
-    CK(cudaMalloc(&s->gg_out, s->G * sizeof(float4))); CK(cudaMalloc(&s->gg_mix, s->G * sizeof(float4)));
+    CK(cudaMalloc(&s->gg_out, s->G * sizeof(float4))); CK(cudaMalloc(&s->gg_out_b, s->G * sizeof(float4))); CK(cudaMalloc(&s->gg_mix, s->G * sizeof(float4)));
+    CK(cudaMemsetAsync(s->gg_out_b, 0, s->G * sizeof(float4), s->stream));
     CK(cudaMemsetAsync(s->g_in, 0, s->G * sizeof(float4), s->stream)); CK(cudaMemsetAsync(s->g_out, 0, s->G * sizeof(float4), s->stream));
     CK(cudaMemsetAsync(s->g_mix, 0, s->G * sizeof(float4), s->stream)); CK(cudaMemsetAsync(s->gg_out, 0, s->G * sizeof(float4), s->stream));
     CK(cudaMemsetAsync(s->gg_mix, 0, s->G * sizeof(float4), s->stream));
@@ -592,7 +597,7 @@ int smx_destroy(smx_sim* s) {
     for (auto& o : s->free_orders) free_order(o);
     for (auto& kv : s->seeds) cudaFree(kv.second.dev);
     for (auto& p : s->prims) { cudaFree(p.sdf_dev); cudaFree(p.nrm_dev); }
-    void* ptrs[] = {s->svd_pool, s->ch_target, s->ch_loss, s->ckpt, s->pool, s->g_in, s->g_out, s->g_mix, s->gg_out, s->gg_mix, s->g_lin, s->adj_cur, s->adj_nxt, s->stage_dev, s->keys_a, s->keys_b, s->iota, s->cub_tmp,
+    void* ptrs[] = {s->svd_pool, s->ch_target, s->ch_loss, s->ckpt, s->pool, s->g_in, s->g_out, s->g_mix, s->gg_out, s->gg_out_b, s->gg_mix, s->g_lin, s->adj_cur, s->adj_nxt, s->stage_dev, s->keys_a, s->keys_b, s->iota, s->cub_tmp,
                     s->counters, s->prims_dev, s->pstate, s->pgrad, s->ext_f, s->ext_f_grad, s->abuf, s->gabuf, s->ctrl_id, s->action, s->action_grad};
     for (void* p : ptrs) cudaFree(p);
     cudaFreeHost(s->stage_host);
@@ -1031,21 +1036,26 @@ int smx_substep_grad_begin(smx_sim* s, int32_t f) {
     Order& ord = s->orders[o];
     bool contact = s->has_contact();
     PrimSet ps = s->primset();
-    if (s->ckpt && s->ckpt_order[f] == ord.uid && (bool)s->ckpt_contact[f] == contact) {
+    float4* gg = s->gg_of(f);
+    const bool have_rec = s->ckpt && s->ckpt_order[f] == ord.uid && (bool)s->ckpt_contact[f] == contact;
+    if (have_rec && s->bwd_prepared == f && s->bwd_prepared_uid == ord.uid) {
+        // nothing to do: k_grid_grad of substep f+1 restored g_out (/ g_mix) and cleared the adjoint grids; g_in is read from the record
+    } else if (have_rec) {
         // restore g_in / g_out (/ g_mix) and zero the adjoint grids of the same blocks in one launch
         k_ckpt_copy<<<grid_blocks_launch(s), 256, 0, s->stream>>>(s->dense ? nullptr : ord.blocks, ord.nblocks, s->B * s->P.nb3, s->ckpt_cap, s->ckpt + (size_t)f * s->ckpt_rec,
-                                                                 s->g_in, s->g_out, contact ? s->g_mix : nullptr, 1, s->counters, s->gg_out, contact ? s->gg_mix : nullptr);
+                                                                 s->g_in, s->g_out, contact ? s->g_mix : nullptr, 1, s->counters, gg, contact ? s->gg_mix : nullptr);
         CKLN(s, "ckpt_restore");
     } else {
         if (s->slab) return fail(SMX_ERR_STATE, "smx_substep_grad: slab decomposition needs the grid checkpoint of substep %d (run it forward in this handle; do not set SMX_FLAG_NO_GRID_CKPT)", f);
         TRY(forward_to_grid(s, f, false, false));
-        TRY(clear_grids(s, ord, s->gg_out, contact ? s->gg_mix : nullptr, nullptr));
+        TRY(clear_grids(s, ord, gg, contact ? s->gg_mix : nullptr, nullptr));
     }
-    s->g_in_clean_uid = -1;             // g_in now holds substep f's values
+    s->g_in_clean_uid = -1;             // g_in now holds substep f's values (or stale ones when the record is used directly)
+    s->bwd_prepared = -1;
     const float* fin = s->frame_ptr(f);
     if (P.n > 0) {
-        if (s->cfg.flags & SMX_FLAG_DIRECT_RED) k_g2p_grad<false><<<nblk(P.n, SMX_TPB_SC), SMX_TPB_SC, 0, s->stream>>>(P, fin, s->adj_cur, s->adj_nxt, s->g_out, s->gg_out, s->pf_sc);
-        else k_g2p_grad<true><<<nblk(P.n, SMX_TPB_SC), SMX_TPB_SC, 0, s->stream>>>(P, fin, s->adj_cur, s->adj_nxt, s->g_out, s->gg_out, s->pf_sc);
+        if (s->cfg.flags & SMX_FLAG_DIRECT_RED) k_g2p_grad<false><<<nblk(P.n, SMX_TPB_SC), SMX_TPB_SC, 0, s->stream>>>(P, fin, s->adj_cur, s->adj_nxt, s->g_out, gg, s->pf_sc);
+        else k_g2p_grad<true><<<nblk(P.n, SMX_TPB_SC), SMX_TPB_SC, 0, s->stream>>>(P, fin, s->adj_cur, s->adj_nxt, s->g_out, gg, s->pf_sc);
         CKLN(s, "k_g2p_grad");
     }
     s->grad_pending = f;
@@ -1061,7 +1071,7 @@ int smx_substep_grad_mid(smx_sim* s, int32_t f) {
     if (s->has_contact() && P.n > 0) {
         PrimSet ps = s->primset();
         float life = 1.0f / (float)(P.substeps - f % P.substeps);
-        k_contact_grad<<<nblk(P.n, SMX_TPB), SMX_TPB, 0, s->stream>>>(P, ps, f, life, s->frame_ptr(f), s->adj_nxt, s->g_mix, s->gg_out, s->gg_mix); CKLN(s, "k_contact_grad");
+        k_contact_grad<<<nblk(P.n, SMX_TPB), SMX_TPB, 0, s->stream>>>(P, ps, f, life, s->frame_ptr(f), s->adj_nxt, s->g_mix, s->gg_of(f), s->gg_mix); CKLN(s, "k_contact_grad");
     }
     s->grad_mid_done = f;
     return SMX_OK;
@@ -1078,7 +1088,20 @@ int smx_substep_grad_end(smx_sim* s, int32_t f) {
     bool contact = s->has_contact();
     PrimSet ps = s->primset();
     const float* fin = s->frame_ptr(f);
-    k_grid_grad<<<grid_blocks_launch(s), 256, 0, s->stream>>>(P, ps, f, s->dense ? nullptr : ord.blocks, ord.nblocks, s->g_in, s->gg_out, contact ? s->gg_mix : nullptr); CKLN(s, "k_grid_grad");
+    float4* gg = s->gg_of(f);
+    {
+        // g_in comes straight from the grid checkpoint when there is one; and when substep f-1 shares the ordering and has a
+        // record too, this launch also prepares its adjoint (restore of g_out / g_mix, clear of the other adjoint grid)
+        const bool have_rec = s->ckpt && s->ckpt_order[f] == ord.uid && (bool)s->ckpt_contact[f] == contact;
+        const bool prep = have_rec && !s->slab && !(s->cfg.flags & SMX_FLAG_NO_FUSION) && f > 0 && s->order_of[f - 1] == o && s->ckpt_order[f - 1] == ord.uid &&
+                          (bool)s->ckpt_contact[f - 1] == contact && s->trans_from[f] < 0;
+        const float4* rec_in = have_rec ? s->ckpt + (size_t)f * s->ckpt_rec : nullptr;
+        const float4* rec_prev = prep ? s->ckpt + (size_t)(f - 1) * s->ckpt_rec : nullptr;
+        k_grid_grad<<<grid_blocks_launch(s), 256, 0, s->stream>>>(P, ps, f, s->dense ? nullptr : ord.blocks, ord.nblocks, s->g_in, gg, contact ? s->gg_mix : nullptr,
+                                                                 rec_in, rec_prev, s->ckpt_cap, contact ? 1 : 0, s->g_out, s->g_mix, s->gg_of(f - 1));
+        CKLN(s, "k_grid_grad");
+        s->bwd_prepared = prep ? f - 1 : -1; s->bwd_prepared_uid = ord.uid;
+    }
     if (s->cfg.rigid_velocity_control && !s->prims.empty()) {
         k_forward_kinematics_grad<<<nblk((long long)s->prims.size() * s->B, 64), 64, 0, s->stream>>>(s->pstate, s->pgrad, s->cfg.max_steps, (int)s->prims.size(), s->B, f, P.dt); CKL(s);
     }
@@ -1088,16 +1111,24 @@ int smx_substep_grad_end(smx_sim* s, int32_t f) {
         const bool use_rec = s->svd_pool && s->svd_order[f] == ord.uid;
         const float4* rec = use_rec ? s->svd_rec(f) : nullptr;
         const bool extra = P.ctype == 1 || P.n_control > 0;
-        const int grid = nblk(P.n, SMX_TPB);
+        const bool tiled = !(s->cfg.flags & SMX_FLAG_NO_TMA);
         TRY(dispatch_mat(P.material, P.ptype, [&](auto mat) {
             constexpr int M = decltype(mat)::value;
-            if (use_rec) {
-                if (extra) k_p2g_grad<M, true, true><<<grid, SMX_TPB, 0, s->stream>>>(P, ps, f, fin, s->adj_cur, s->adj_nxt, s->gg_out, cslot, s->action, s->action_grad, rec, s->pf_g);
-                else k_p2g_grad<M, true, false><<<grid, SMX_TPB, 0, s->stream>>>(P, ps, f, fin, s->adj_cur, s->adj_nxt, s->gg_out, cslot, s->action, s->action_grad, rec, s->pf_g);
-            } else {
-                if (extra) k_p2g_grad<M, false, true><<<grid, SMX_TPB, 0, s->stream>>>(P, ps, f, fin, s->adj_cur, s->adj_nxt, s->gg_out, cslot, s->action, s->action_grad, rec, s->pf_g);
-                else k_p2g_grad<M, false, false><<<grid, SMX_TPB, 0, s->stream>>>(P, ps, f, fin, s->adj_cur, s->adj_nxt, s->gg_out, cslot, s->action, s->action_grad, rec, s->pf_g);
-            }
+            auto go = [&](auto rec_c, auto extra_c) {
+                constexpr bool R = decltype(rec_c)::value, E = decltype(extra_c)::value;
+                if (tiled) {
+                    // persistent CTAs, double-buffered TMA staging of the streaming planes
+                    const int ntiles = nblk(P.n, SMX_TPB), grid = std::min(ntiles, s->sm_count * SMX_P2GG_MINB);
+                    const size_t smem = (size_t)2 * SMX_P2GG_NPL(M, R) * SMX_TPB * sizeof(float4);
+                    static bool attr_set = false;
+                    if (!attr_set) { cudaFuncSetAttribute(k_p2g_grad_tiled<M, R, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+                    k_p2g_grad_tiled<M, R, E><<<grid, SMX_TPB, smem, s->stream>>>(P, ps, f, fin, s->adj_cur, s->adj_nxt, gg, cslot, s->action, s->action_grad, rec, ntiles);
+                } else {
+                    k_p2g_grad<M, R, E><<<nblk(P.n, SMX_TPB), SMX_TPB, 0, s->stream>>>(P, ps, f, fin, s->adj_cur, s->adj_nxt, gg, cslot, s->action, s->action_grad, rec, s->pf_g);
+                }
+            };
+            if (use_rec) { if (extra) go(std::true_type(), std::true_type()); else go(std::true_type(), std::false_type()); }
+            else { if (extra) go(std::false_type(), std::true_type()); else go(std::false_type(), std::false_type()); }
             CKLN(s, "k_p2g_grad"); return (int)SMX_OK;
         }));
     }

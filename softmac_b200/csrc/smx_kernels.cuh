@@ -159,6 +159,55 @@ __device__ __forceinline__ void warp_stage_flush(WarpStage& st, const uint32_t* 
     }
 }
 
+// Three-component variant (adjoint of G2P: nothing is scattered into the mass slot): xy and z are staged in separate arrays
+// (8-byte and 4-byte accesses, both conflict-free), 25 % less shared-memory traffic and 17 % less shared memory per warp.
+struct WarpStage3 {
+    float2 xy[32 * 27];     // [lane][offset]
+    float z[32 * 27];
+    uint32_t off[32 * 9];
+};
+__device__ __forceinline__ void warp_stage_flush3(WarpStage3& st, const uint32_t* ox, const uint32_t* oy, const uint32_t* oz, uint32_t key, bool live,
+                                                  float4* __restrict__ grid) {
+    const unsigned lane = threadIdx.x & 31;
+    {
+        uint32_t* my = st.off + lane * 9;
+#pragma unroll
+        for (int a = 0; a < 3; a++) { my[a] = ox[a]; my[3 + a] = oy[a]; my[6 + a] = oz[a]; }
+    }
+    uint32_t k = live ? key : 0xffffffffu;
+    uint32_t prev = __shfl_up_sync(0xffffffffu, k, 1);
+    bool head = (lane == 0) || (k != prev);
+    unsigned heads = __ballot_sync(0xffffffffu, head);
+    unsigned alive = __ballot_sync(0xffffffffu, live);
+    __syncwarp();
+    if (lane >= 27) return;
+    const int a = lane / 9, b = (lane / 3) % 3, c = lane % 3;
+    unsigned h = heads;
+    while (h) {                                     // warp-uniform: one trip per run
+        int p0 = __ffs(h) - 1;
+        h &= h - 1;
+        int p1 = h ? __ffs(h) - 1 : 32;
+        if (!((alive >> p0) & 1u)) break;
+        const float2* q = st.xy + p0 * 27 + lane;
+        const float* r = st.z + p0 * 27 + lane;
+        float2 acc = q[0], acc2 = make_float2(0.f, 0.f);
+        float az = r[0], az2 = 0.f;
+        int cnt = p1 - p0 - 1;
+        q += 27; r += 27;
+        for (; cnt >= 4; cnt -= 4, q += 4 * 27, r += 4 * 27) {
+            float2 v0 = q[0], v1 = q[27], v2 = q[54], v3 = q[81];
+            float z0 = r[0], z1 = r[27], z2 = r[54], z3 = r[81];
+            acc = __fadd2_rn(acc, v0); acc2 = __fadd2_rn(acc2, v1); acc = __fadd2_rn(acc, v2); acc2 = __fadd2_rn(acc2, v3);
+            az += z0; az2 += z1; az += z2; az2 += z3;
+        }
+        if (cnt >= 2) { acc = __fadd2_rn(acc, q[0]); acc2 = __fadd2_rn(acc2, q[27]); az += r[0]; az2 += r[27]; q += 2 * 27; r += 2 * 27; cnt -= 2; }
+        if (cnt >= 1) { acc = __fadd2_rn(acc, q[0]); az += r[0]; }
+        acc = __fadd2_rn(acc, acc2); az += az2;
+        const uint32_t* o = st.off + p0 * 9;
+        atomicAdd(grid + (o[a] + o[3 + b] + o[6 + c]), make_float4(acc.x, acc.y, az, 0.f));
+    }
+}
+
 // quadratic B-spline stencil of one particle (mpm_simulator.py:215-217)
 struct Stencil {
     uint32_t ox[3], oy[3], oz[3];   // block-major address contributions per axis offset (unsigned: one IMAD.WIDE.U32 per node address)
@@ -305,6 +354,23 @@ __device__ __forceinline__ void load_state(const float* __restrict__ fr, long lo
     float4 p0 = __ldg(b), p1 = __ldg(b + stride), p2 = __ldg(b + 2 * stride), p3 = __ldg(b + 3 * stride), p4 = __ldg(b + 4 * stride), p5 = __ldg(b + 5 * stride);
     unpack_state(p0, p1, p2, p3, p4, p5, x, v, F, C);
 }
+// loaders on a per-particle base pointer b (plane p at b[p * stride]); SM: the planes were staged in shared memory by a bulk copy
+template <bool SM> __device__ __forceinline__ float4 ld4(const float4* p) { if (SM) return *p; else return __ldg(p); }
+// re-read of a staged plane that the compiler must not merge with an earlier read (keeps the value out of registers in between)
+__device__ __forceinline__ float4 lds4_again(const float4* p) {
+    float4 r;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+    return r;
+}
+template <bool SM> __device__ __forceinline__ void load_state_b(const float4* b, long long stride, V3& x, V3& v, M3& F, M3& C) {
+    float4 p0 = ld4<SM>(b), p1 = ld4<SM>(b + stride), p2 = ld4<SM>(b + 2 * stride), p3 = ld4<SM>(b + 3 * stride), p4 = ld4<SM>(b + 4 * stride), p5 = ld4<SM>(b + 5 * stride);
+    unpack_state(p0, p1, p2, p3, p4, p5, x, v, F, C);
+}
+template <bool SM> __device__ __forceinline__ M3 load_F_b(const float4* b, long long stride) {
+    float4 p3 = ld4<SM>(b + 3 * stride), p4 = ld4<SM>(b + 4 * stride), p5 = ld4<SM>(b + 5 * stride);
+    M3 F; F.m[0] = p3.w; F.m[1] = p4.x; F.m[2] = p4.y; F.m[3] = p4.z; F.m[4] = p4.w; F.m[5] = p5.x; F.m[6] = p5.y; F.m[7] = p5.z; F.m[8] = p5.w;
+    return F;
+}
 // x, v, C of a frame (planes 0..2 and the first three components of plane 3; F0 in plane 3.w belongs to P2G)
 __device__ __forceinline__ void store_xvC(float* __restrict__ fr, long long stride, int j, V3 x, V3 v, const M3& C) {
     float4* b = reinterpret_cast<float4*>(fr) + j;
@@ -337,9 +403,8 @@ __device__ __forceinline__ void store_svd_rec(float4* __restrict__ rec, long lon
     b[2 * stride] = make_float4(sv.V.m[6], sv.V.m[1], sv.V.m[4], sv.V.m[7]);
     b[3 * stride] = make_float4(sv.e[0], sv.e[1], sv.e[2], Jm1);
 }
-__device__ __forceinline__ void load_svd_rec(const float4* __restrict__ rec, long long stride, int j, Svd& sv, float& Jm1) {
-    const float4* b = rec + j;
-    float4 a = __ldg(b), c = __ldg(b + stride), d = __ldg(b + 2 * stride), e = __ldg(b + 3 * stride);
+template <bool SM> __device__ __forceinline__ void load_svd_rec_b(const float4* b, long long stride, Svd& sv, float& Jm1) {
+    float4 a = ld4<SM>(b), c = ld4<SM>(b + stride), d = ld4<SM>(b + 2 * stride), e = ld4<SM>(b + 3 * stride);
     V3 u0 = v3(a.x, a.y, a.z), u1 = v3(a.w, c.x, c.y), v0 = v3(c.z, c.w, d.x), v1 = v3(d.y, d.z, d.w);
     V3 u2 = cross(u0, u1), v2 = cross(v0, v1);       // U, V are proper rotations
     sv.U.m[0] = u0.x; sv.U.m[3] = u0.y; sv.U.m[6] = u0.z; sv.U.m[1] = u1.x; sv.U.m[4] = u1.y; sv.U.m[7] = u1.z; sv.U.m[2] = u2.x; sv.U.m[5] = u2.y; sv.U.m[8] = u2.z;
@@ -613,10 +678,13 @@ __global__ void __launch_bounds__(SMX_TPB) k_g2p(Params P, const float* __restri
 // adjoint of G2P: scatter d g_out, accumulate d x through the weights.
 //   ain  = adjoint of frame f+1 (x 0..2, v 3..5, C 15..23), aout = adjoint of frame f (x written here)
 // ------------------------------------------------------------------------------------------------
+#ifndef SMX_G2PG_MINB
+#define SMX_G2PG_MINB 6     // 3 warps x 11.5 KB of staging per CTA: six CTAs per SM when the kernel stays within 112 registers
+#endif
 template <bool STAGED>
-__global__ void __launch_bounds__(SMX_TPB_SC, SMX_SC_MINB) k_g2p_grad(Params P, const float* __restrict__ fin, const float* __restrict__ ain,
+__global__ void __launch_bounds__(SMX_TPB_SC, SMX_G2PG_MINB) k_g2p_grad(Params P, const float* __restrict__ fin, const float* __restrict__ ain,
                                                          float* __restrict__ aout, const float4* __restrict__ g_out, float4* __restrict__ gg_out, int pf_dist) {
-    __shared__ WarpStage stage[STAGED ? SMX_TPB_SC / 32 : 1];
+    __shared__ WarpStage3 stage[STAGED ? SMX_TPB_SC / 32 : 1];
     int j = blockIdx.x * SMX_TPB_SC + threadIdx.x;
     bool live = j < P.n;
     int jj = live ? j : P.n - 1;
@@ -641,7 +709,8 @@ __global__ void __launch_bounds__(SMX_TPB_SC, SMX_SC_MINB) k_g2p_grad(Params P, 
         V3 q0 = gnv - mulv(K, v3(s.fx, s.fy, s.fz));
         V3 c0 = v3(K.m[0], K.m[3], K.m[6]), c1 = v3(K.m[1], K.m[4], K.m[7]), c2 = v3(K.m[2], K.m[5], K.m[8]);
         V3 gfx = v3(0, 0, 0), S0 = v3(0, 0, 0);     // S0 = sum w * g (for d dpos)
-        float4* row = STAGED ? stage[threadIdx.x >> 5].val + (threadIdx.x & 31) * 27 : nullptr;
+        float2* row_xy = STAGED ? stage[threadIdx.x >> 5].xy + (threadIdx.x & 31) * 27 : nullptr;
+        float* row_z = STAGED ? stage[threadIdx.x >> 5].z + (threadIdx.x & 31) * 27 : nullptr;
 #pragma unroll
         for (int a = 0; a < 3; a++) {
             V3 qa = q0 + (float)a * c0;
@@ -657,7 +726,7 @@ __global__ void __launch_bounds__(SMX_TPB_SC, SMX_SC_MINB) k_g2p_grad(Params P, 
                     uint32_t node = s.ox[a] + s.oy[b] + s.oz[c];
                     float4 g = g_out[node];
                     float w = wab * s.wz[c];
-                    if (STAGED) row[a * 9 + b * 3 + c] = make_float4(w * q.x, w * q.y, w * q.z, 0.f);
+                    if (STAGED) { row_xy[a * 9 + b * 3 + c] = make_float2(w * q.x, w * q.y); row_z[a * 9 + b * 3 + c] = w * q.z; }
                     else red_add_f4(gg_out + node, w * q.x, w * q.y, w * q.z, 0.f);
                     float gw = fmaf(g.x, q.x, fmaf(g.y, q.y, g.z * q.z));       // d weight
                     G0 = fmaf(gw, s.wz[c], G0); G1 = fmaf(gw, dwz[c], G1);
@@ -674,7 +743,7 @@ __global__ void __launch_bounds__(SMX_TPB_SC, SMX_SC_MINB) k_g2p_grad(Params P, 
         // partial d x of frame f (the contact adjoint and P2G adjoint add theirs); the rest of the plane is written by P2G adjoint
         st_plane(aout, P.stride, j, 0, make_float4(gx1.x + P.inv_dx * gfx.x, gx1.y + P.inv_dx * gfx.y, gx1.z + P.inv_dx * gfx.z, 0.f));
     }
-    if (STAGED) warp_stage_flush(stage[threadIdx.x >> 5], s.ox, s.oy, s.oz, pack_base(s.bx, s.by, s.bz, bt), live, gg_out);
+    if (STAGED) warp_stage_flush3(stage[threadIdx.x >> 5], s.ox, s.oy, s.oz, pack_base(s.bx, s.by, s.bz, bt), live, gg_out);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -787,19 +856,33 @@ __global__ void __launch_bounds__(SMX_TPB) k_contact_grad(Params P, PrimSet ps, 
 // ------------------------------------------------------------------------------------------------
 // adjoint of the grid update (grid_op.grad / grid_op_mixed1.grad): gg_out <- (d g_in xyz, d mass) in place.
 // ------------------------------------------------------------------------------------------------
+// Fused with it (launch count): rec_in != nullptr reads g_in straight from the grid checkpoint of substep f, and rec_prev != nullptr
+// prepares the adjoint of substep f-1 (same ordering): g_out (/ g_mix) <- its checkpoint, the OTHER adjoint grid gg_next <- 0
+// (gg_out is double-buffered by substep parity because the P2G adjoint of substep f still reads this one), gg_mix <- 0 in place.
 __global__ void __launch_bounds__(256) k_grid_grad(Params P, PrimSet ps, int f, const uint32_t* __restrict__ blocks, const int* __restrict__ nblocks,
-                                                   const float4* __restrict__ g_in, float4* __restrict__ gg_out, const float4* __restrict__ gg_mix) {
+                                                   const float4* __restrict__ g_in, float4* __restrict__ gg_out, float4* __restrict__ gg_mix,
+                                                   const float4* __restrict__ rec_in, const float4* __restrict__ rec_prev, int cap, int prev_mix,
+                                                   float4* __restrict__ g_out, float4* __restrict__ g_mix, float4* __restrict__ gg_next) {
     int total = blocks ? *nblocks : P.nbatch * P.nb3;
     for (int bi = blockIdx.x * 4 + (threadIdx.x >> 6); bi < total; bi += gridDim.x * 4) {
         uint32_t node = (blocks ? blocks[bi] : (uint32_t)bi) * 64u + (threadIdx.x & 63);
-        float4 g = g_in[node];
+        const size_t slot = (size_t)bi * 64 + (threadIdx.x & 63);
+        float4 g = rec_in ? rec_in[slot] : g_in[node];
+        if (rec_prev) {         // records are only used when every active block fits (bi < cap)
+            g_out[node] = rec_prev[(size_t)cap * 64 + slot];
+            if (prev_mix) g_mix[node] = rec_prev[(size_t)2 * cap * 64 + slot];
+            gg_next[node] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         bool on = g.w > 1e-10f;
         int i, j, k;
         int bt = P.nbatch > 1 ? (int)(node / (uint32_t)P.Gb) : 0;
         node_coords(node - (uint32_t)(bt * P.Gb), P.nb, i, j, k);
         float4 go = gg_out[node];
         V3 gv = v3(go.x, go.y, go.z);
-        if (gg_mix) { float4 gm = gg_mix[node]; gv += v3(gm.x, gm.y, gm.z); }
+        if (gg_mix) {
+            float4 gm = gg_mix[node]; gv += v3(gm.x, gm.y, gm.z);
+            if (rec_prev) gg_mix[node] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         float inv = on ? 1.f / g.w : 0.f;
         V3 v = v3(inv * g.x + P.dt * P.gx, inv * g.y + P.dt * P.gy, inv * g.z + P.dt * P.gz);
         float gmass = 0.f;
@@ -847,31 +930,45 @@ __global__ void __launch_bounds__(256) k_grid_grad(Params P, PrimSet ps, int f, 
 #ifndef SMX_P2GG_MINB
 #define SMX_P2GG_MINB 4
 #endif
+// ---- TMA bulk copies (cp.async.bulk, 1-D) signalled on an mbarrier: staging of the streaming particle planes ----------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes),
+                 "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { while (!mbar_try_wait(bar, parity)) {} }
+
 // REC:   U, V, sigma - 1 and J - 1 come from the SVD record written by the forward P2G (no Jacobi sweeps here)
 // EXTRA: particle-contact impulses (collision_type == 1) and / or particle control forces are present
-template <int MAT, bool REC, bool EXTRA>
-__global__ void __launch_bounds__(SMX_TPB, SMX_P2GG_MINB) k_p2g_grad(Params P, PrimSet ps, int f, const float* __restrict__ fin, const float* __restrict__ ain,
-                                                      float* __restrict__ aout, const float4* __restrict__ gg, const int* __restrict__ ctrl_slot,
-                                                      const float* __restrict__ action, double* __restrict__ action_grad, const float4* __restrict__ rec, int pf_dist) {
+// SM:    the streaming planes of this particle were staged in shared memory (k_p2g_grad_tiled); otherwise they are read from HBM
+// fb / rb / ab: per-particle base pointers of the frame, the SVD record and the adjoint of frame f+1 (plane p at base[p * stride])
+template <int MAT, bool REC, bool EXTRA, bool SM>
+__device__ __forceinline__ void p2g_grad_particle(const Params& P, const PrimSet& ps, int f, int j, int jj, bool live, const float4* fb, long long fs,
+                                                  const float4* rb, long long rs, const float4* ab, long long astr, float4 gx_part, float* __restrict__ aout,
+                                                  const float4* __restrict__ gg, const int* __restrict__ ctrl_slot, const float* __restrict__ action,
+                                                  double* __restrict__ action_grad) {
     constexpr int model = MAT / 3, ptype = MAT % 3;
     constexpr bool corot = model == 0 && ptype != 2;
-    int j = blockIdx.x * SMX_TPB + threadIdx.x;
-    bool live = j < P.n;
-    int jj = live ? j : P.n - 1;
-    {
-        long long jp = (long long)j + pf_dist;
-        prefetch_planes(fin, P.stride, jp, P.n, 0, SMX_NPLANES);
-        if (REC && corot) prefetch_planes(rec, P.stride, jp, P.n, 0, SMX_RPLANES);
-        prefetch_planes(ain, P.stride, jp, P.n, 3, SMX_NPLANES);
-        prefetch_planes(aout, P.stride, jp, P.n, 0, 1);
-    }
     V3 x, v; M3 F, C;
-    load_state(fin, P.stride, jj, x, v, F, C);
+    load_state_b<SM>(fb, fs, x, v, F, C);
     Material m;
-    if (REC && corot) load_svd_rec(rec, P.stride, jj, m.svd, m.Jm1);
+    if (REC && corot) load_svd_rec_b<SM>(rb, rs, m.svd, m.Jm1);
     // every streaming load is issued up front (they are all in flight together); the adjoint inputs are consumed last
-    M3 gnewF = load_F(ain, P.stride, jj);
-    const float4 gx_part = reinterpret_cast<const float4*>(aout)[jj];      // partial d x from the G2P / contact adjoints
+    M3 gnewF;
+    if (!SM) gnewF = load_F_b<false>(ab, astr);
     int bt = batch_of(P, jj);
     V3 imp = v3(0, 0, 0);
     if (EXTRA) imp = particle_impulses(P, ps, f, jj, bt, live, x, v, ctrl_slot, action, false);
@@ -930,6 +1027,12 @@ __global__ void __launch_bounds__(SMX_TPB, SMX_P2GG_MINB) k_p2g_grad(Params P, P
     V3 gx = P.inv_dx * gfx, gv = P.p_mass * S0, gimp = S0;
     M3 gC = scale(P.p_mass, gaff);
     M3 gstress = scale(P.cs, gaff);
+    if (SM) {       // staged in shared memory: read the late inputs only now, and F, C again (not carried through the gather loop)
+        float4 p1 = lds4_again(fb + fs), p2 = lds4_again(fb + 2 * fs), p3 = lds4_again(fb + 3 * fs), p4 = lds4_again(fb + 4 * fs), p5 = lds4_again(fb + 5 * fs);
+        C.m[0] = p1.z; C.m[1] = p1.w; C.m[2] = p2.x; C.m[3] = p2.y; C.m[4] = p2.z; C.m[5] = p2.w; C.m[6] = p3.x; C.m[7] = p3.y; C.m[8] = p3.z;
+        F.m[0] = p3.w; F.m[1] = p4.x; F.m[2] = p4.y; F.m[3] = p4.z; F.m[4] = p4.w; F.m[5] = p5.x; F.m[6] = p5.y; F.m[7] = p5.z; F.m[8] = p5.w;
+        gnewF = load_F_b<true>(ab, astr);
+    }
     float tr = trace(gstress), gJ = 0.f;
     M3 gFtmp = m3_zero();
     if (model == 0) {
@@ -992,6 +1095,7 @@ __global__ void __launch_bounds__(SMX_TPB, SMX_P2GG_MINB) k_p2g_grad(Params P, P
         else gFtmp = gnewF;
     }
     {
+        if (SM) Et = compute_Et(C, F, P.dt);       // recomputed from the re-read C, F
         M3 Ftmp = Et; Ftmp.m[0] += 1.f; Ftmp.m[4] += 1.f; Ftmp.m[8] += 1.f;
         gFtmp = add(gFtmp, scale(gJ, cofactor(Ftmp)));
     }
@@ -1019,8 +1123,7 @@ __global__ void __launch_bounds__(SMX_TPB, SMX_P2GG_MINB) k_p2g_grad(Params P, P
             }
         }
     }
-    if (!live) return;
-    {
+    if (live) {
         float4* b = reinterpret_cast<float4*>(aout) + j;
         b[0] = make_float4(gx_part.x + gx.x, gx_part.y + gx.y, gx_part.z + gx.z, gv.x);
         b[P.stride] = make_float4(gv.y, gv.z, gC.m[0], gC.m[1]);
@@ -1028,6 +1131,76 @@ __global__ void __launch_bounds__(SMX_TPB, SMX_P2GG_MINB) k_p2g_grad(Params P, P
         b[3 * P.stride] = make_float4(gC.m[6], gC.m[7], gC.m[8], gF.m[0]);
         b[4 * P.stride] = make_float4(gF.m[1], gF.m[2], gF.m[3], gF.m[4]);
         b[5 * P.stride] = make_float4(gF.m[5], gF.m[6], gF.m[7], gF.m[8]);
+    }
+}
+
+// one thread per particle slot, planes read straight from HBM (ablation: SMX_FLAG_NO_TMA)
+template <int MAT, bool REC, bool EXTRA>
+__global__ void __launch_bounds__(SMX_TPB, SMX_P2GG_MINB) k_p2g_grad(Params P, PrimSet ps, int f, const float* __restrict__ fin, const float* __restrict__ ain,
+                                                      float* __restrict__ aout, const float4* __restrict__ gg, const int* __restrict__ ctrl_slot,
+                                                      const float* __restrict__ action, double* __restrict__ action_grad, const float4* __restrict__ rec, int pf_dist) {
+    constexpr bool corot = (MAT / 3 == 0) && (MAT % 3 != 2);
+    int j = blockIdx.x * SMX_TPB + threadIdx.x;
+    bool live = j < P.n;
+    int jj = live ? j : P.n - 1;
+    {
+        long long jp = (long long)j + pf_dist;
+        prefetch_planes(fin, P.stride, jp, P.n, 0, SMX_NPLANES);
+        if (REC && corot) prefetch_planes(rec, P.stride, jp, P.n, 0, SMX_RPLANES);
+        prefetch_planes(ain, P.stride, jp, P.n, 3, SMX_NPLANES);
+        prefetch_planes(aout, P.stride, jp, P.n, 0, 1);
+    }
+    const float4 gx_part = reinterpret_cast<const float4*>(aout)[jj];      // partial d x from the G2P / contact adjoints
+    p2g_grad_particle<MAT, REC, EXTRA, false>(P, ps, f, j, jj, live, reinterpret_cast<const float4*>(fin) + jj, P.stride, rec + jj, P.stride,
+                                              reinterpret_cast<const float4*>(ain) + jj, P.stride, gx_part, aout, gg, ctrl_slot, action, action_grad);
+}
+
+// Persistent, software-pipelined variant: every CTA walks tiles of SMX_TPB particle slots; while tile i is being processed the
+// streaming planes of tile i+1 (frame f: 6, adjoint of F[f+1]: 3, SVD record: 4 -- each a contiguous 2 KB row) are brought into
+// the other half of a double buffer by TMA bulk copies (cp.async.bulk) that complete on an mbarrier, so no warp ever waits for HBM.
+#define SMX_P2GG_NPL(MAT, REC) (((MAT) / 3 == 0 && (MAT) % 3 != 2 && (REC)) ? 13 : 9)
+template <int MAT, bool REC, bool EXTRA>
+__global__ void __launch_bounds__(SMX_TPB, SMX_P2GG_MINB) k_p2g_grad_tiled(Params P, PrimSet ps, int f, const float* __restrict__ fin, const float* __restrict__ ain,
+                                                            float* __restrict__ aout, const float4* __restrict__ gg, const int* __restrict__ ctrl_slot,
+                                                            const float* __restrict__ action, double* __restrict__ action_grad, const float4* __restrict__ rec, int ntiles) {
+    constexpr int NPL = SMX_P2GG_NPL(MAT, REC);
+    extern __shared__ __align__(128) float4 smx_dyn_smem[];
+    __shared__ uint64_t bar[2];
+    float4* buf = smx_dyn_smem;         // [2][NPL][SMX_TPB]
+    const int tid = threadIdx.x;
+    if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_init_fence(); }
+    __syncthreads();
+    auto issue = [&](int tile, int stage) {     // one thread: arm the barrier with the byte count, then one bulk copy per plane row
+        const long long base = (long long)tile * SMX_TPB;
+        const uint32_t bytes = (uint32_t)min((long long)SMX_TPB, (long long)P.n - base) * 16u;
+        float4* dst = buf + stage * NPL * SMX_TPB;
+        mbar_expect_tx(&bar[stage], bytes * NPL);
+        const float4* f4 = reinterpret_cast<const float4*>(fin) + base;
+        const float4* a4 = reinterpret_cast<const float4*>(ain) + base;
+#pragma unroll
+        for (int p = 0; p < 6; p++) bulk_g2s(dst + p * SMX_TPB, f4 + p * P.stride, bytes, &bar[stage]);
+#pragma unroll
+        for (int p = 0; p < 3; p++) bulk_g2s(dst + (6 + p) * SMX_TPB, a4 + (3 + p) * P.stride, bytes, &bar[stage]);
+        if (NPL == 13) {
+#pragma unroll
+            for (int p = 0; p < 4; p++) bulk_g2s(dst + (9 + p) * SMX_TPB, rec + base + p * P.stride, bytes, &bar[stage]);
+        }
+    };
+    int tile = blockIdx.x;
+    if (tid == 0 && tile < ntiles) issue(tile, 0);
+    for (int it = 0; tile < ntiles; tile += gridDim.x, it++) {
+        const int stage = it & 1;
+        // the other stage was released by the __syncthreads that ended the previous trip
+        if (tid == 0 && tile + (int)gridDim.x < ntiles) issue(tile + gridDim.x, stage ^ 1);
+        int j = tile * SMX_TPB + tid;
+        bool live = j < P.n;
+        int jj = live ? j : P.n - 1;
+        const float4 gx_part = reinterpret_cast<const float4*>(aout)[jj];  // partial d x from the G2P / contact adjoints (needed last)
+        mbar_wait(&bar[stage], (it >> 1) & 1);
+        const float4* sb = buf + stage * NPL * SMX_TPB + (jj - tile * SMX_TPB);
+        p2g_grad_particle<MAT, REC, EXTRA, true>(P, ps, f, j, jj, live, sb, SMX_TPB, sb + 9 * SMX_TPB, SMX_TPB, sb + 3 * SMX_TPB, SMX_TPB, gx_part, aout, gg,
+                                                 ctrl_slot, action, action_grad);
+        __syncthreads();
     }
 }
 
