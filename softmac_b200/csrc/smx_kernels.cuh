@@ -286,7 +286,6 @@ __device__ __forceinline__ void commit_prim_grad(double* g13, const PrimGrad& G,
 // ------------------------------------------------------------------------------------------------
 struct Material {
     M3 newF;        // F[f+1]
-    M3 D;           // new_F - R (co-rotated) -- accurate small matrix
     M3 stress;      // before the cs prefactor
     float J, Jm1;
     Svd svd;        // valid for co-rotated plastic / elastic
@@ -308,29 +307,28 @@ __device__ __forceinline__ void material_update(const M3& Et, const Params& P, M
     m.J = 1.f + m.Jm1;
     M3 Ftmp = Et; Ftmp.m[0] += 1.f; Ftmp.m[4] += 1.f; Ftmp.m[8] += 1.f;
     if (model == 0) {
+        float iso = P.lam * m.J * m.Jm1;
         if (ptype == 2) {                 // liquid: mu == 0, R never contributes; skip the SVD
             float c = cbrtf(m.J);
             m.newF = scale(c, m3_identity());
-            m.D = m3_zero();
+            m.stress = m3_zero();
+            m.stress.m[0] = iso; m.stress.m[4] = iso; m.stress.m[8] = iso;
         } else {
             if (!rec) m.svd = svd_dev(Et);
+            float g0 = m.svd.e[0], g1 = m.svd.e[1], g2 = m.svd.e[2];
+            m.newF = Ftmp;
             if (ptype == 0) {             // plastic: clip sigma to [1-2e-3, 1+3e-3] (:226-229)
-                float g0 = fminf(fmaxf(m.svd.e[0], -2e-3f), 3e-3f), g1 = fminf(fmaxf(m.svd.e[1], -2e-3f), 3e-3f),
-                      g2 = fminf(fmaxf(m.svd.e[2], -2e-3f), 3e-3f);
-                m.D = udvt(m.svd.U, g0, g1, g2, m.svd.V);                       // new_F - R = U (Sc - I) V^T
+                g0 = fminf(fmaxf(g0, -2e-3f), 3e-3f); g1 = fminf(fmaxf(g1, -2e-3f), 3e-3f); g2 = fminf(fmaxf(g2, -2e-3f), 3e-3f);
                 // new_F = F_tmp + U (Sc - S) V^T: exactly F_tmp when nothing is clipped (skipped warp-wide in that case)
                 bool clipped = (g0 != m.svd.e[0]) | (g1 != m.svd.e[1]) | (g2 != m.svd.e[2]);
-                m.newF = Ftmp;
                 if (__any_sync(__activemask(), clipped))
                     m.newF = add(Ftmp, udvt(m.svd.U, g0 - m.svd.e[0], g1 - m.svd.e[1], g2 - m.svd.e[2], m.svd.V));
-            } else {                      // elastic
-                m.D = udvt(m.svd.U, m.svd.e[0], m.svd.e[1], m.svd.e[2], m.svd.V);
-                m.newF = Ftmp;
             }
+            // stress = 2 mu (new_F - R) new_F^T + lam J (J - 1) I with new_F = U Sc V^T, R = U V^T (:234-236)
+            //        = U diag(2 mu g (1 + g) + lam J (J - 1)) U^T,  g = Sc - 1: symmetric, and accurate because g is carried, not Sc
+            float mu2 = 2.f * P.mu;
+            m.stress = udut(m.svd.U, fmaf(mu2 * g0, 1.f + g0, iso), fmaf(mu2 * g1, 1.f + g1, iso), fmaf(mu2 * g2, 1.f + g2, iso));
         }
-        m.stress = scale(2.f * P.mu, mulT(m.D, m.newF));
-        float iso = P.lam * m.J * m.Jm1;
-        m.stress.m[0] += iso; m.stress.m[4] += iso; m.stress.m[8] += iso;
     } else {                              // neo-Hookean (:237-245)
         if (ptype == 2) {
             float sq = sqrtf(m.J);

@@ -199,6 +199,20 @@ __device__ __forceinline__ M3 udvt(const M3& U, float d0, float d1, float d2, co
     return mulT(T, V);
 }
 
+// U diag(d) U^T (symmetric)
+__device__ __forceinline__ M3 udut(const M3& U, float d0, float d1, float d2) {
+    float t0 = U.m[0] * d0, t1 = U.m[1] * d1, t2 = U.m[2] * d2, t3 = U.m[3] * d0, t4 = U.m[4] * d1, t5 = U.m[5] * d2, t6 = U.m[6] * d0, t7 = U.m[7] * d1,
+          t8 = U.m[8] * d2;
+    M3 S;
+    S.m[0] = fmaf(t0, U.m[0], fmaf(t1, U.m[1], t2 * U.m[2]));
+    S.m[4] = fmaf(t3, U.m[3], fmaf(t4, U.m[4], t5 * U.m[5]));
+    S.m[8] = fmaf(t6, U.m[6], fmaf(t7, U.m[7], t8 * U.m[8]));
+    S.m[1] = S.m[3] = fmaf(t0, U.m[3], fmaf(t1, U.m[4], t2 * U.m[5]));
+    S.m[2] = S.m[6] = fmaf(t0, U.m[6], fmaf(t1, U.m[7], t2 * U.m[8]));
+    S.m[5] = S.m[7] = fmaf(t3, U.m[6], fmaf(t4, U.m[7], t5 * U.m[8]));
+    return S;
+}
+
 // mpm_simulator.py:184-192
 __device__ __forceinline__ float clamp_ref(float a) { return a >= 0.f ? fmaxf(a, 1e-6f) : fminf(a, -1e-6f); }
 
