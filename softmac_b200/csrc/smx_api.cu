@@ -527,6 +527,7 @@ int smx_create(const smx_config* cfg, smx_sim** out) {
     P.material = cfg->material_model; P.ptype = cfg->ptype; P.ctype = cfg->collision_type; P.substeps = cfg->substeps; P.n_control = cfg->n_control; P.np = 0;
     s->dense = (cfg->flags & SMX_FLAG_DENSE_GRID) || (cfg->flags & SMX_FLAG_NO_SORT) || cfg->sort_every <= 0;
     P.Gb = P.ng * P.ng * P.ng; P.nb3 = P.nb * P.nb * P.nb;
+    P.dbg = getenv("SMX_DBG") ? atoi(getenv("SMX_DBG")) : 0;
     s->G = (size_t)B * P.Gb;
     s->B = B;
     s->frame_floats = 24 * P.stride;

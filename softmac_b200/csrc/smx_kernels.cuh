@@ -40,6 +40,7 @@ struct Params {
     float gx, gy, gz;       // gravity
     int sticky;             // ground_friction >= 10
     int material, ptype, ctype, substeps, n_control, np;
+    int dbg;                // timing experiments only (SMX_DBG): 1 skip the reductions of the flush, 2 skip the flush walk, 4 skip staging stores
     int nbatch, npb, Gb, nb3;   // independent rollouts batched in one handle: count, particles per batch, nodes and blocks per batch
 };
 
@@ -119,43 +120,52 @@ __device__ __forceinline__ void add_f4(float4& a, const float4& b) {
     a = make_float4(lo.x, lo.y, hi.x, hi.y);
 }
 
-struct Stencil;
-__device__ __forceinline__ void warp_stage_flush(WarpStage& st, const uint32_t* ox, const uint32_t* oy, const uint32_t* oz, uint32_t key, bool live,
-                                                 float4* __restrict__ grid) {
+// Common head of the flush: park the node offsets, find the runs.  heads bit p: slot p starts a run; alive bit p: slot p holds a particle.
+__device__ __forceinline__ void flush_prologue(uint32_t* off, const uint32_t* ox, const uint32_t* oy, const uint32_t* oz, uint32_t key, bool live,
+                                               unsigned& heads, unsigned& alive) {
     const unsigned lane = threadIdx.x & 31;
-    {
-        uint32_t* my = st.off + lane * 9;
+    uint32_t* my = off + lane * 9;
 #pragma unroll
-        for (int a = 0; a < 3; a++) { my[a] = ox[a]; my[3 + a] = oy[a]; my[6 + a] = oz[a]; }
-    }
+    for (int a = 0; a < 3; a++) { my[a] = ox[a]; my[3 + a] = oy[a]; my[6 + a] = oz[a]; }
     uint32_t k = live ? key : 0xffffffffu;
     uint32_t prev = __shfl_up_sync(0xffffffffu, k, 1);
     bool head = (lane == 0) || (k != prev);
-    unsigned heads = __ballot_sync(0xffffffffu, head);
-    unsigned alive = __ballot_sync(0xffffffffu, live);
+    heads = __ballot_sync(0xffffffffu, head);
+    alive = __ballot_sync(0xffffffffu, live);
     __syncwarp();
-    if (lane >= 27) return;
-    const int a = lane / 9, b = (lane / 3) % 3, c = lane % 3;
+}
+// The walk is fully unrolled over the 32 slots in batches of 8: the eight 128-bit loads of a batch are in flight together, the
+// additions follow in slot order, and after the last slot of a run (a warp-uniform test on the ballot) the lane issues its reduction.
+__device__ __forceinline__ void warp_stage_flush(WarpStage& st, const uint32_t* ox, const uint32_t* oy, const uint32_t* oz, uint32_t key, bool live,
+                                                 float4* __restrict__ grid, int dbg = 0) {
+    unsigned heads, alive;
+    flush_prologue(st.off, ox, oy, oz, key, live, heads, alive);
+    const unsigned lane = threadIdx.x & 31;
+    if (lane >= 27 || (dbg & 2)) return;
+    const int a = lane / 9, b = 3 + (lane / 3) % 3, c = 6 + lane % 3;
     const float4* src = st.val + lane;
-    unsigned h = heads;
-    while (h) {                                     // warp-uniform: one trip per run
-        int p0 = __ffs(h) - 1;
-        h &= h - 1;
-        int p1 = h ? __ffs(h) - 1 : 32;
-        if (!((alive >> p0) & 1u)) break;           // the tail run of slots past the last particle
-        const float4* q = src + p0 * 27;
-        float4 acc = q[0], acc2 = make_float4(0.f, 0.f, 0.f, 0.f);
-        int cnt = p1 - p0 - 1;
-        q += 27;
-        for (; cnt >= 4; cnt -= 4, q += 4 * 27) {   // two independent accumulators, four particles per trip
-            float4 v0 = q[0], v1 = q[27], v2 = q[54], v3 = q[81];
-            add_f4(acc, v0); add_f4(acc2, v1); add_f4(acc, v2); add_f4(acc2, v3);
+    const int nl = __popc(alive);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int p0 = 0;
+#pragma unroll
+    for (int base = 0; base < 32; base += 8) {
+        if (base >= nl) break;
+        float4 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = src[(base + i) * 27];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int p = base + i;
+            add_f4(acc, v[i]);
+            if (p == 31 || ((heads >> (p + 1)) & 1u)) {        // last slot of its run
+                if (((alive >> p) & 1u) && !(dbg & 1)) {
+                    const uint32_t* o = st.off + p0 * 9;
+                    atomicAdd(grid + (o[a] + o[b] + o[c]), acc);
+                }
+                acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                p0 = p + 1;
+            }
         }
-        if (cnt >= 2) { float4 v0 = q[0], v1 = q[27]; add_f4(acc, v0); add_f4(acc2, v1); q += 2 * 27; cnt -= 2; }
-        if (cnt >= 1) { float4 v0 = q[0]; add_f4(acc, v0); }
-        add_f4(acc, acc2);
-        const uint32_t* o = st.off + p0 * 9;
-        atomicAdd(grid + (o[a] + o[3 + b] + o[6 + c]), acc);
     }
 }
 
@@ -167,44 +177,37 @@ struct WarpStage3 {
     uint32_t off[32 * 9];
 };
 __device__ __forceinline__ void warp_stage_flush3(WarpStage3& st, const uint32_t* ox, const uint32_t* oy, const uint32_t* oz, uint32_t key, bool live,
-                                                  float4* __restrict__ grid) {
+                                                  float4* __restrict__ grid, int dbg = 0) {
+    unsigned heads, alive;
+    flush_prologue(st.off, ox, oy, oz, key, live, heads, alive);
     const unsigned lane = threadIdx.x & 31;
-    {
-        uint32_t* my = st.off + lane * 9;
+    if (lane >= 27 || (dbg & 2)) return;
+    const int a = lane / 9, b = 3 + (lane / 3) % 3, c = 6 + lane % 3;
+    const float2* sxy = st.xy + lane;
+    const float* sz = st.z + lane;
+    const int nl = __popc(alive);
+    float2 acc = make_float2(0.f, 0.f);
+    float az = 0.f;
+    int p0 = 0;
 #pragma unroll
-        for (int a = 0; a < 3; a++) { my[a] = ox[a]; my[3 + a] = oy[a]; my[6 + a] = oz[a]; }
-    }
-    uint32_t k = live ? key : 0xffffffffu;
-    uint32_t prev = __shfl_up_sync(0xffffffffu, k, 1);
-    bool head = (lane == 0) || (k != prev);
-    unsigned heads = __ballot_sync(0xffffffffu, head);
-    unsigned alive = __ballot_sync(0xffffffffu, live);
-    __syncwarp();
-    if (lane >= 27) return;
-    const int a = lane / 9, b = (lane / 3) % 3, c = lane % 3;
-    unsigned h = heads;
-    while (h) {                                     // warp-uniform: one trip per run
-        int p0 = __ffs(h) - 1;
-        h &= h - 1;
-        int p1 = h ? __ffs(h) - 1 : 32;
-        if (!((alive >> p0) & 1u)) break;
-        const float2* q = st.xy + p0 * 27 + lane;
-        const float* r = st.z + p0 * 27 + lane;
-        float2 acc = q[0], acc2 = make_float2(0.f, 0.f);
-        float az = r[0], az2 = 0.f;
-        int cnt = p1 - p0 - 1;
-        q += 27; r += 27;
-        for (; cnt >= 4; cnt -= 4, q += 4 * 27, r += 4 * 27) {
-            float2 v0 = q[0], v1 = q[27], v2 = q[54], v3 = q[81];
-            float z0 = r[0], z1 = r[27], z2 = r[54], z3 = r[81];
-            acc = __fadd2_rn(acc, v0); acc2 = __fadd2_rn(acc2, v1); acc = __fadd2_rn(acc, v2); acc2 = __fadd2_rn(acc2, v3);
-            az += z0; az2 += z1; az += z2; az2 += z3;
+    for (int base = 0; base < 32; base += 8) {
+        if (base >= nl) break;
+        float2 v[8]; float z[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) { v[i] = sxy[(base + i) * 27]; z[i] = sz[(base + i) * 27]; }
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int p = base + i;
+            acc = __fadd2_rn(acc, v[i]); az += z[i];
+            if (p == 31 || ((heads >> (p + 1)) & 1u)) {        // last slot of its run
+                if (((alive >> p) & 1u) && !(dbg & 1)) {
+                    const uint32_t* o = st.off + p0 * 9;
+                    atomicAdd(grid + (o[a] + o[b] + o[c]), make_float4(acc.x, acc.y, az, 0.f));
+                }
+                acc = make_float2(0.f, 0.f); az = 0.f;
+                p0 = p + 1;
+            }
         }
-        if (cnt >= 2) { acc = __fadd2_rn(acc, q[0]); acc2 = __fadd2_rn(acc2, q[27]); az += r[0]; az2 += r[27]; q += 2 * 27; r += 2 * 27; cnt -= 2; }
-        if (cnt >= 1) { acc = __fadd2_rn(acc, q[0]); az += r[0]; }
-        acc = __fadd2_rn(acc, acc2); az += az2;
-        const uint32_t* o = st.off + p0 * 9;
-        atomicAdd(grid + (o[a] + o[3 + b] + o[6 + c]), make_float4(acc.x, acc.y, az, 0.f));
     }
 }
 
@@ -524,7 +527,7 @@ __global__ void __launch_bounds__(SMX_TPB_SC, SMX_SC_MINB) k_p2g(Params P, PrimS
             }
         }
     }
-    if (STAGED) warp_stage_flush(stage[threadIdx.x >> 5], s.ox, s.oy, s.oz, pack_base(s.bx, s.by, s.bz, bt), live, g_in);
+    if (STAGED) warp_stage_flush(stage[threadIdx.x >> 5], s.ox, s.oy, s.oz, pack_base(s.bx, s.by, s.bz, bt), live, g_in, P.dbg);
 }
 
 // boundary_condition (mpm_simulator.py:268-281); mask bit d cleared where component d was zeroed
@@ -741,7 +744,7 @@ __global__ void __launch_bounds__(SMX_TPB_SC, SMX_G2PG_MINB) k_g2p_grad(Params P
         // partial d x of frame f (the contact adjoint and P2G adjoint add theirs); the rest of the plane is written by P2G adjoint
         st_plane(aout, P.stride, j, 0, make_float4(gx1.x + P.inv_dx * gfx.x, gx1.y + P.inv_dx * gfx.y, gx1.z + P.inv_dx * gfx.z, 0.f));
     }
-    if (STAGED) warp_stage_flush3(stage[threadIdx.x >> 5], s.ox, s.oy, s.oz, pack_base(s.bx, s.by, s.bz, bt), live, gg_out);
+    if (STAGED) warp_stage_flush3(stage[threadIdx.x >> 5], s.ox, s.oy, s.oz, pack_base(s.bx, s.by, s.bz, bt), live, gg_out, P.dbg);
 }
 
 // ------------------------------------------------------------------------------------------------
