@@ -56,7 +56,7 @@ def parse():
     ap.add_argument("--variant", default="A", choices=["A", "B"])
     ap.add_argument("--init", default="rest", choices=["rest", "stressed"], help="rest: the reference generator (v=0, F=I, C=0); stressed: same x with F = I + 0.01 N(0,1), v = 0.3 N(0,1), C = N(0,1) (every particle needs full SVD sweeps and clips plastically)")
     ap.add_argument("--batch", type=int, default=1, help="independent rollouts batched in one handle (per GPU)")
-    ap.add_argument("--sort-every", type=int, default=16)
+    ap.add_argument("--sort-every", type=int, default=32)
     ap.add_argument("--flags", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

@@ -292,6 +292,34 @@ def test_grid_checkpoint_and_recompute_adjoints_agree():
     assert rel_l2(ga, gb) <= 1e-5 and rel_l2(pa, pb) <= 1e-4
 
 
+@pytest.mark.parametrize("flags", [64, 128, 64 + 128])
+@pytest.mark.parametrize("ptype", [0, 1])
+def test_svd_record_and_tma_staging_do_not_change_the_adjoint(flags, ptype):
+    """The adjoint normally takes U, V, sigma - 1, J - 1 from the SVD record written by the forward P2G and runs the persistent
+    TMA-staged P2G-adjoint kernel; SMX_FLAG_NO_SVD_REC (64) repeats the Jacobi SVD, SMX_FLAG_NO_TMA (128) reads the planes
+    straight from HBM.  Same gradients (plastic state stressed enough that the sigma clip is active)."""
+    def run(fl):
+        rng = np.random.default_rng(266)
+        n, steps = 6000, 6
+        pair = Pair(n, max_steps=8, sort_every=3, flags=fl, ptype=ptype)
+        st = scenes.blob_state(n, rng)
+        st[:, 6:15] += 0.01 * rng.normal(size=(n, 9))
+        st[:, 15:24] = rng.normal(size=(n, 9))
+        pair.gpu.reset(np.asarray(st, dtype=np.float32).astype(np.float64))
+        for f in range(steps):
+            pair.gpu.substep(f)
+        pair.gpu.clear_all_gradients()
+        pair.gpu.add_state_grad(steps, rng.normal(size=(n, 24)))
+        for f in range(steps - 1, -1, -1):
+            pair.gpu.substep_grad(f)
+        return pair.gpu.get_state(steps), pair.gpu.get_state_grad(0)
+
+    (sa, ga), (sb, gb) = run(0), run(flags)
+    assert np.abs(ga).max() > 0
+    assert_state_close(sa, sb, tol=2e-5)         # forward is identical up to the order of the L2 reductions
+    assert rel_l2(gb, ga) <= 2e-5 and cosine(gb, ga) >= 1 - 1e-9
+
+
 def test_api_quirks_and_errors():
     from softmac_b200._capi import SmxError
     rng = np.random.default_rng(270)
@@ -353,6 +381,17 @@ def test_properties_at_full_size():
         sim.substep_grad(f)
     assert np.all(sim.get_state_grad(0) == 0)
     assert sim.counters()["clamped"] == 0 and sim.counters()["left_active_region"] == 0
+    # the adjoint is linear in its seed: seed 2 g gives twice the gradient of seed g (up to the order of the L2 reductions)
+    g = np.ascontiguousarray(st[:, :3] - st[:, :3].mean(0))
+    grads = []
+    for scale in (1.0, 2.0):
+        sim.clear_all_gradients()
+        sim.add_x_grad(4, scale * g)
+        for f in range(3, -1, -1):
+            sim.substep_grad(f)
+        grads.append(sim.get_state_grad(0))
+    assert np.abs(grads[0]).max() > 0 and np.all(np.isfinite(grads[0]))
+    assert rel_l2(2.0 * grads[0], grads[1]) <= 1e-5
 
 
 def test_velocity_control_forward_kinematics_and_action_grad():
