@@ -38,8 +38,8 @@ DT = 1e-4                   # see module docstring
 ALGO_BYTES_STEP = 480.0     # 192 B forward + 288 B backward per particle-substep (fp32 storage)
 # algorithmic HBM bytes per particle of each particle kernel (DESIGN.md "Kernels"): frame components read + written
 # DRAM traffic per launch of the particle kernels from the ncu --set full capture of this round
-# (profiles/r1_v3_ncu_full_particle_kernels.csv and r1_v1_...: dram__bytes_read.sum + dram__bytes_write.sum)
-NCU_TRAFFIC = {"k_p2g_grad": 146.6e6 + 72.0e6, "k_p2g": 98.6e6 + 17.4e6, "k_g2p": 14.6e6 + 5.9e6, "k_g2p_grad": 77.1e6 + 4.6e6}
+# (profiles/r1c_ncu_full_particle_kernels.csv: dram__bytes_read.sum + dram__bytes_write.sum; k_g2p from r1_v3_...)
+NCU_TRAFFIC = {"k_p2g_grad": 226.6e6 + 64.4e6, "k_p2g": 79.7e6 + 119.1e6, "k_g2p": 14.6e6 + 5.9e6, "k_g2p_grad": 85.1e6 + 6.4e6}
 KERNEL_BYTES = {"k_p2g": 96 + 36, "k_g2p": 12 + 60, "k_g2p_grad": 12 + 60 + 12, "k_p2g_grad": 96 + 36 + 12 + 96,
                 "k_p2g(recompute)": 96}
 
@@ -367,7 +367,7 @@ def kernel_roofline(sim, args, S):
     achieved = KERNEL_BYTES[top] * args.n * args.batch / (avg[top] * 1e-3) / 1e9
     traffic = NCU_TRAFFIC.get(top) if (args.n == 1_000_000 and args.batch == 1) else None
     return {"bound": "hbm", "kernel": top, "achieved": achieved, "unit": "GB/s", "traffic": traffic,
-            "traffic_source": "ncu --set full capture of this kernel at this size (profiles/r1_v3_ncu_full_particle_kernels.csv), bytes per launch" if traffic else None,
+            "traffic_source": "ncu --set full capture of this kernel at this size (profiles/r1c_ncu_full_particle_kernels.csv), bytes per launch" if traffic else None,
             "algorithmic_bytes_per_launch": KERNEL_BYTES[top] * args.n * args.batch, "avg_launch_ms": avg[top],
             "share_of_substep_pair": avg[top] / total if total > 0 else None,
             "kernel_ms": avg, "how": "CUDA events around each launch on the simulator stream, 8 forward + 8 backward substeps after the timed region"}
