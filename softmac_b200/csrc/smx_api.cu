@@ -85,6 +85,7 @@ struct HostPrim { PrimDev d; float* sdf_dev = nullptr; float4* nrm_dev = nullptr
 
 }  // namespace
 
+#define SMX_IO_CHUNKS 16
 struct smx_sim {
     smx_config cfg;
     Params P;
@@ -137,6 +138,7 @@ struct smx_sim {
     long long g_in_clean_uid = -1;      // ordering whose active blocks of g_in are known to be zero (k_grid_op re-zeroes them)
     struct Seed { float* dev = nullptr; int ncols = 24; };
     std::map<int, Seed> seeds;          // frame -> device (n, 3 | 24) fp32 AoS in particle-id order
+    std::multimap<size_t, float*> seed_pool;    // released seed buffers by size: clear_grads / add_*_grad never call cudaMalloc / cudaFree in the steady state
     // primitives
     std::vector<HostPrim> prims;
     PrimDev* prims_dev = nullptr;
@@ -151,6 +153,7 @@ struct smx_sim {
     unsigned long long* counters = nullptr;
     long long n_resorts = 0, last_ckpt_overflow = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev_chunk[SMX_IO_CHUNKS] = {};  // pipelined host <-> device staging
     long long launches = 0;
     bool prof = false;
     std::vector<std::pair<const char*, cudaEvent_t>> marks;
@@ -168,6 +171,13 @@ struct smx_sim {
 };
 
 static inline int nblk(long long n, int t) { return (int)((n + t - 1) / t); }
+static int seed_alloc(smx_sim* s, size_t bytes, float** out) {
+    auto it = s->seed_pool.find(bytes);
+    if (it != s->seed_pool.end()) { *out = it->second; s->seed_pool.erase(it); return SMX_OK; }
+    if (cudaMalloc(out, bytes) != cudaSuccess) { cudaGetLastError(); g_err[0] = 0; snprintf(g_err, sizeof g_err, "cannot allocate a %.1f MB adjoint seed buffer", bytes / 1e6); return SMX_ERR_NOMEM; }
+    return SMX_OK;
+}
+static void seed_release(smx_sim* s, float* p, size_t bytes) { if (p) s->seed_pool.insert({bytes, p}); }
 static inline size_t prim_slot_of(int b, int id) { return (size_t)b * SMX_MAXP + id; }
 
 // profiling: an event after every launch of a profiled substep (smx_profile_substep)
@@ -435,18 +445,66 @@ static int check_prim(smx_sim* s, int id, const char* what) {
     return SMX_OK;
 }
 
+// Pipelined staging: host f64 -> pinned fp32 -> device in SMX_IO_CHUNKS pieces, the conversion of piece k+1 (host threads)
+// overlapping the H2D copy of piece k; and the reverse for read-back (the conversion of piece k overlaps the D2H copy of k+1).
+// `fill(dst, i0, i1)` writes staging elements [i0, i1).  The caller has synchronised the stream (staging buffer reuse).
+static size_t io_chunk(size_t cnt) {
+    static const bool single = getenv("SMX_IO_SINGLE_CHUNK") != nullptr;      // ablation: one conversion, then one copy
+    if (single) return std::max<size_t>(cnt, 1);
+    size_t chunk = (cnt + SMX_IO_CHUNKS - 1) / SMX_IO_CHUNKS;
+    return std::max<size_t>((chunk + 1023) / 1024 * 1024, 1 << 16);
+}
+template <typename Fill>
+static int h2d_pipelined(smx_sim* s, size_t cnt, Fill&& fill) {
+    size_t chunk = io_chunk(cnt);
+    for (size_t i0 = 0; i0 < cnt; i0 += chunk) {
+        size_t i1 = std::min(cnt, i0 + chunk);
+        fill(s->stage_host, i0, i1);
+        CK(cudaMemcpyAsync(s->stage_dev + i0, s->stage_host + i0, (i1 - i0) * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    }
+    return SMX_OK;
+}
+static int d2h_pipelined(smx_sim* s, size_t cnt, double* host) {
+    // measured on the B200 host (16 threads, 96 MB): overlapping the conversion with the copy is SLOWER for read-back (9.1 vs 7.9 ms:
+    // the first-touch page faults of the caller's fresh f64 array compete with the DMA), so one piece unless SMX_IO_D2H_CHUNKS is set
+    static const bool piecewise = getenv("SMX_IO_D2H_CHUNKS") != nullptr;
+    size_t chunk = piecewise ? io_chunk(cnt) : std::max<size_t>(cnt, 1);
+    int k = 0;
+    for (size_t i0 = 0; i0 < cnt; i0 += chunk, k++) {
+        size_t i1 = std::min(cnt, i0 + chunk);
+        CK(cudaMemcpyAsync(s->stage_host + i0, s->stage_dev + i0, (i1 - i0) * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+        CK(cudaEventRecord(s->ev_chunk[k], s->stream));
+    }
+    // one parallel region for all pieces (the worker threads stay hot): thread 0 waits for the copy of piece k, then everybody converts it
+    const int nchunks = k;
+    const float* src = s->stage_host;
+    cudaError_t err = cudaSuccess;
+    #pragma omp parallel num_threads(smx_host_threads())
+    {
+        for (int c = 0; c < nchunks; c++) {
+            #pragma omp master
+            { cudaError_t e = cudaEventSynchronize(s->ev_chunk[c]); if (e != cudaSuccess) err = e; }
+            #pragma omp barrier
+            const long long i0 = (long long)c * (long long)chunk, i1 = (long long)std::min(cnt, (size_t)i0 + chunk);
+            #pragma omp for schedule(static) nowait
+            for (long long i = i0; i < i1; i++) host[i] = (double)src[i];
+        }
+    }
+    if (err != cudaSuccess) return fail(SMX_ERR_CUDA, "cudaEventSynchronize failed: %s", cudaGetErrorString(err));
+    return SMX_OK;
+}
+
 // host (n, ncomp) f64 in id order -> frame components [c0, c0+ncomp) in storage order
 static int upload_cols(smx_sim* s, int f, const double* host, int ncomp, int c0) {
     int n = s->P.n;
     if (n == 0) return SMX_OK;
     size_t cnt = (size_t)n * ncomp;
     CK(cudaStreamSynchronize(s->stream));       // staging buffer reuse
-    {
-        float* dst = s->stage_host;
+    auto fill = [&](float* dst, size_t i0, size_t i1) {
         #pragma omp parallel for schedule(static) num_threads(smx_host_threads())
-        for (long long i = 0; i < (long long)cnt; i++) dst[i] = (float)host[i];
-    }
-    CK(cudaMemcpyAsync(s->stage_dev, s->stage_host, cnt * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+        for (long long i = (long long)i0; i < (long long)i1; i++) dst[i] = (float)host[i];
+    };
+        TRY(h2d_pipelined(s, cnt, fill));
     const uint32_t* perm = s->orders[s->order_of[f]].perm;
     k_upload<<<nblk(n, 256), 256, 0, s->stream>>>(n, s->P.stride, s->stage_dev, ncomp, c0, s->frame_ptr(f), perm, 0); CKL(s);
     return SMX_OK;
@@ -456,14 +514,7 @@ static int download_cols(smx_sim* s, const float* frame, const uint32_t* perm, d
     if (n == 0) return SMX_OK;
     size_t cnt = (size_t)n * ncomp;
     k_download<<<nblk(n, 256), 256, 0, s->stream>>>(n, s->P.stride, s->stage_dev, ncomp, c0, frame, perm); CKL(s);
-    CK(cudaMemcpyAsync(s->stage_host, s->stage_dev, cnt * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
-    CK(cudaStreamSynchronize(s->stream));
-    {
-        const float* src = s->stage_host;
-        #pragma omp parallel for schedule(static) num_threads(smx_host_threads())
-        for (long long i = 0; i < (long long)cnt; i++) host[i] = (double)src[i];
-    }
-    return SMX_OK;
+    return d2h_pipelined(s, cnt, host);
 }
 static int ensure_order(smx_sim* s, int f) {
     if (s->order_of[f] >= 0) return SMX_OK;
@@ -570,6 +621,7 @@ int smx_create(const smx_config* cfg, smx_sim** out) {
     CK(cudaMalloc(&s->action, nc * 3 * sizeof(float))); CK(cudaMemsetAsync(s->action, 0, nc * 3 * sizeof(float), s->stream));
     CK(cudaMalloc(&s->action_grad, nc * 3 * sizeof(double))); CK(cudaMemsetAsync(s->action_grad, 0, nc * 3 * sizeof(double), s->stream));
     CK(cudaEventCreate(&s->ev0)); CK(cudaEventCreate(&s->ev1));
+    for (int i = 0; i < SMX_IO_CHUNKS; i++) CK(cudaEventCreateWithFlags(&s->ev_chunk[i], cudaEventDisableTiming));
     {   // the staged scatter kernels want 8 CTAs x 28 KB of shared memory per SM: ask for the largest carve-out
         int co = cudaSharedmemCarveoutMaxShared;
         cudaFuncSetAttribute(k_p2g<0, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
@@ -597,6 +649,7 @@ int smx_destroy(smx_sim* s) {
     for (auto& o : s->orders) if (o.live) free_order(o);
     for (auto& o : s->free_orders) free_order(o);
     for (auto& kv : s->seeds) cudaFree(kv.second.dev);
+    for (auto& kv : s->seed_pool) cudaFree(kv.second);
     for (auto& p : s->prims) { cudaFree(p.sdf_dev); cudaFree(p.nrm_dev); }
     void* ptrs[] = {s->svd_pool, s->ch_target, s->ch_loss, s->ckpt, s->pool, s->g_in, s->g_out, s->g_mix, s->gg_out, s->gg_out_b, s->gg_mix, s->g_lin, s->adj_cur, s->adj_nxt, s->stage_dev, s->keys_a, s->keys_b, s->iota, s->cub_tmp,
                     s->counters, s->prims_dev, s->pstate, s->pgrad, s->ext_f, s->ext_f_grad, s->abuf, s->gabuf, s->ctrl_id, s->action, s->action_grad};
@@ -604,6 +657,7 @@ int smx_destroy(smx_sim* s) {
     cudaFreeHost(s->stage_host);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
+    for (int i = 0; i < SMX_IO_CHUNKS; i++) if (s->ev_chunk[i]) cudaEventDestroy(s->ev_chunk[i]);
     if (s->own_stream) cudaStreamDestroy(s->stream);
     delete s;
     return SMX_OK;
@@ -667,21 +721,20 @@ int smx_reset(smx_sim* s, const double* state, int32_t ncols) {
     gc_orders(s);                       // every ordering is unreferenced now: recycle all of them
     int n = s->P.n;
     Order root; s->order_of[0] = new_order_id(s, root);
-    {
-        float* stage = s->stage_host;
-        #pragma omp parallel for schedule(static) num_threads(smx_host_threads())
-        for (long long p = 0; p < (long long)n; p++) {
-            float* r = stage + 24 * p;
-            if (ncols == 24) for (int c = 0; c < 24; c++) r[c] = (float)state[24 * p + c];
-            else {
-                for (int c = 0; c < 24; c++) r[c] = 0.f;
-                r[0] = (float)state[3 * p]; r[1] = (float)state[3 * p + 1]; r[2] = (float)state[3 * p + 2];
-                r[6] = r[10] = r[14] = 1.f;
-            }
-        }
-    }
     if (n > 0) {
-        CK(cudaMemcpyAsync(s->stage_dev, s->stage_host, (size_t)n * 24 * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+        auto fill = [&](float* stage, size_t i0, size_t i1) {     // element ranges (a chunk may end inside a row)
+            if (ncols == 24) {
+                #pragma omp parallel for schedule(static) num_threads(smx_host_threads())
+                for (long long i = (long long)i0; i < (long long)i1; i++) stage[i] = (float)state[i];
+            } else {
+                #pragma omp parallel for schedule(static) num_threads(smx_host_threads())
+                for (long long i = (long long)i0; i < (long long)i1; i++) {
+                    long long p = i / 24; int c = (int)(i - 24 * p);
+                    stage[i] = c < 3 ? (float)state[3 * p + c] : ((c == 6 || c == 10 || c == 14) ? 1.f : 0.f);
+                }
+            }
+        };
+        TRY(h2d_pipelined(s, (size_t)n * 24, fill));
         k_upload<<<nblk(n, 256), 256, 0, s->stream>>>(n, s->P.stride, s->stage_dev, 24, 0, s->frame_ptr(0), nullptr, 0); CKL(s);
     }
     return resort(s, 0, false);
@@ -1217,26 +1270,25 @@ static int add_seed(smx_sim* s, int f, const double* g, int ncols) {
     CK(cudaSetDevice(s->cfg.device));
     CK(cudaStreamSynchronize(s->stream));
     size_t cnt = (size_t)n * ncols;
-    {
-        float* dst = s->stage_host;
+    auto fill = [&](float* dst, size_t i0, size_t i1) {
         #pragma omp parallel for schedule(static) num_threads(smx_host_threads())
-        for (long long i = 0; i < (long long)cnt; i++) dst[i] = (float)g[i];
-    }
-    CK(cudaMemcpyAsync(s->stage_dev, s->stage_host, cnt * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+        for (long long i = (long long)i0; i < (long long)i1; i++) dst[i] = (float)g[i];
+    };
+        TRY(h2d_pipelined(s, cnt, fill));
     auto it = s->seeds.find(f);
     if (it != s->seeds.end() && it->second.ncols < ncols) {
         // widen an x-only seed to the full 24 columns
         float* d = nullptr;
-        CK(cudaMalloc(&d, (size_t)n * 24 * sizeof(float)));
+        TRY(seed_alloc(s, (size_t)n * 24 * sizeof(float), &d));
         CK(cudaMemsetAsync(d, 0, (size_t)n * 24 * sizeof(float), s->stream));
         CK(cudaMemcpy2DAsync(d, 24 * sizeof(float), it->second.dev, 3 * sizeof(float), 3 * sizeof(float), n, cudaMemcpyDeviceToDevice, s->stream));
         CK(cudaStreamSynchronize(s->stream));
-        cudaFree(it->second.dev);
+        seed_release(s, it->second.dev, (size_t)n * 3 * sizeof(float));
         it->second.dev = d; it->second.ncols = 24;
     }
     if (it == s->seeds.end()) {
         smx_sim::Seed sd; sd.ncols = ncols;
-        CK(cudaMalloc(&sd.dev, cnt * sizeof(float)));
+        TRY(seed_alloc(s, cnt * sizeof(float), &sd.dev));
         CK(cudaMemcpyAsync(sd.dev, s->stage_dev, cnt * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
         s->seeds[f] = sd;
     } else if (it->second.ncols == ncols) {
@@ -1283,7 +1335,7 @@ int smx_chamfer_loss(smx_sim* s, int32_t f, double weight, double* loss_out) {
     auto it = s->seeds.find(f);
     if (it == s->seeds.end()) {         // create an x-only seed buffer for this frame
         smx_sim::Seed sd; sd.ncols = 3;
-        CK(cudaMalloc(&sd.dev, (size_t)n * 3 * sizeof(float)));
+        TRY(seed_alloc(s, (size_t)n * 3 * sizeof(float), &sd.dev));
         CK(cudaMemsetAsync(sd.dev, 0, (size_t)n * 3 * sizeof(float), s->stream));
         s->seeds[f] = sd;
         it = s->seeds.find(f);
@@ -1322,7 +1374,7 @@ int smx_clear_grads(smx_sim* s) {
     if (!s) return fail(SMX_ERR_ARG, "smx_clear_grads: null simulator");
     CK(cudaSetDevice(s->cfg.device));
     CK(cudaStreamSynchronize(s->stream));
-    for (auto& kv : s->seeds) cudaFree(kv.second.dev);
+    for (auto& kv : s->seeds) seed_release(s, kv.second.dev, (size_t)s->P.n * kv.second.ncols * sizeof(float));
     s->seeds.clear();
     s->adj_frame = -1; s->adj_order = -1;
     int T = s->cfg.max_steps;
