@@ -92,6 +92,7 @@ struct smx_sim {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     int sm_count = 148;
+    bool pdl = true;
     int pf_sc = 0, pf_g = 0, pf_g2p = 0;   // L2 prefetch distances (particles): one wave of resident CTAs of the scatter / gather kernels
     int B = 1;                          // batched independent rollouts
     // spatial slab decomposition (one rank of several): owned x-block columns [slab_lo, slab_hi), neighbours present?
@@ -170,7 +171,13 @@ struct smx_sim {
     }
 };
 
+struct smx_sim;
 static inline int nblk(long long n, int t) { return (int)((n + t - 1) / t); }
+// Programmatic dependent launch for the kernels of the substep sequence: the next kernel's CTAs may become resident while the
+// last CTAs of the previous one drain (every such kernel starts with griddepcontrol.wait, so it touches no data before its
+// predecessor has completed and flushed).  SMX_NO_PDL=1 launches them with plain stream serialisation (ablation).
+template <typename... KArgs, typename... Args>
+static void launch_pdl(smx_sim* s, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args);
 static int seed_alloc(smx_sim* s, size_t bytes, float** out) {
     auto it = s->seed_pool.find(bytes);
     if (it != s->seed_pool.end()) { *out = it->second; s->seed_pool.erase(it); return SMX_OK; }
@@ -179,6 +186,16 @@ static int seed_alloc(smx_sim* s, size_t bytes, float** out) {
 }
 static void seed_release(smx_sim* s, float* p, size_t bytes) { if (p) s->seed_pool.insert({bytes, p}); }
 static inline size_t prim_slot_of(int b, int id) { return (size_t)b * SMX_MAXP + id; }
+template <typename... KArgs, typename... Args>
+static void launch_pdl(smx_sim* s, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = s->pdl ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);       // errors are picked up by CKLN (cudaGetLastError)
+}
 
 // profiling: an event after every launch of a profiled substep (smx_profile_substep)
 static int prof_mark(smx_sim* s, const char* name) {
@@ -384,11 +401,11 @@ static int forward_p2g(smx_sim* s, int f, bool write_F, bool accumulate, bool fu
         TRY(dispatch_mat(P.material, P.ptype, [&](auto mat) {
             constexpr int M = decltype(mat)::value;
             if (s->cfg.flags & SMX_FLAG_DIRECT_RED) {
-                if (extra) k_p2g<M, false, true><<<grid, SMX_TPB_SC, 0, s->stream>>>(P, ps, f, fin, fout, s->g_in, cslot, s->action, acc, fprev, gprev, rec, s->pf_sc);
-                else k_p2g<M, false, false><<<grid, SMX_TPB_SC, 0, s->stream>>>(P, ps, f, fin, fout, s->g_in, cslot, s->action, acc, fprev, gprev, rec, s->pf_sc);
+                if (extra) launch_pdl(s, k_p2g<M, false, true>, grid, SMX_TPB_SC, 0, P, ps, f, fin, fout, s->g_in, cslot, s->action, acc, fprev, gprev, rec, s->pf_sc);
+                else launch_pdl(s, k_p2g<M, false, false>, grid, SMX_TPB_SC, 0, P, ps, f, fin, fout, s->g_in, cslot, s->action, acc, fprev, gprev, rec, s->pf_sc);
             } else {
-                if (extra) k_p2g<M, true, true><<<grid, SMX_TPB_SC, 0, s->stream>>>(P, ps, f, fin, fout, s->g_in, cslot, s->action, acc, fprev, gprev, rec, s->pf_sc);
-                else k_p2g<M, true, false><<<grid, SMX_TPB_SC, 0, s->stream>>>(P, ps, f, fin, fout, s->g_in, cslot, s->action, acc, fprev, gprev, rec, s->pf_sc);
+                if (extra) launch_pdl(s, k_p2g<M, true, true>, grid, SMX_TPB_SC, 0, P, ps, f, fin, fout, s->g_in, cslot, s->action, acc, fprev, gprev, rec, s->pf_sc);
+                else launch_pdl(s, k_p2g<M, true, false>, grid, SMX_TPB_SC, 0, P, ps, f, fin, fout, s->g_in, cslot, s->action, acc, fprev, gprev, rec, s->pf_sc);
             }
             CKLN(s, fprev ? "k_g2p2g" : "k_p2g"); return (int)SMX_OK;
         }));
@@ -407,13 +424,13 @@ static int forward_grid(smx_sim* s, int f, bool accumulate, bool checkpoint) {
     bool save = checkpoint && s->ckpt && (!contact || s->ckpt_narr == 3);
     float4* rec = save ? s->ckpt + (size_t)f * s->ckpt_rec : nullptr;
     // checkpoint == forward pass proper: also save the grid record and re-zero g_in for the next substep's P2G
-    k_grid_op<<<grid_blocks_launch(s), 256, 0, s->stream>>>(P, ps, f, s->dense ? nullptr : o.blocks, o.nblocks, s->g_in, s->g_out, contact ? s->g_mix : nullptr,
+    launch_pdl(s, k_grid_op, grid_blocks_launch(s), 256, 0, P, ps, f, s->dense ? nullptr : o.blocks, o.nblocks, s->g_in, s->g_out, contact ? s->g_mix : nullptr,
                                                            accumulate ? 1 : 0, rec, s->ckpt_cap, contact ? 0 : 1, checkpoint ? 1 : 0, s->counters);
     CKLN(s, "k_grid_op");
     if (checkpoint) s->g_in_clean_uid = o.uid;
     if (contact && P.n > 0) {
         float life = 1.0f / (float)(P.substeps - f % P.substeps);      // mpm_simulator.py:425 (f32 in the reference too)
-        k_contact<<<nblk(P.n, SMX_TPB), SMX_TPB, 0, s->stream>>>(P, ps, f, life, s->frame_ptr(f), s->g_mix, s->g_out, accumulate ? 1 : 0); CKLN(s, "k_contact");
+        launch_pdl(s, k_contact, nblk(P.n, SMX_TPB), SMX_TPB, 0, P, ps, f, life, s->frame_ptr(f), s->g_mix, s->g_out, accumulate ? 1 : 0); CKLN(s, "k_contact");
     }
     if (save && !contact) { s->ckpt_order[f] = o.uid; s->ckpt_contact[f] = 0; }
     return SMX_OK;
@@ -422,8 +439,8 @@ static int forward_grid(smx_sim* s, int f, bool accumulate, bool checkpoint) {
 static int forward_grid_save_contact(smx_sim* s, int f) {
     Order& o = s->orders[s->order_of[f]];
     if (!(s->has_contact() && s->ckpt && s->ckpt_narr == 3)) return SMX_OK;
-    k_ckpt_copy<<<grid_blocks_launch(s), 256, 0, s->stream>>>(s->dense ? nullptr : o.blocks, o.nblocks, s->B * s->P.nb3, s->ckpt_cap, s->ckpt + (size_t)f * s->ckpt_rec,
-                                                             nullptr, s->g_out, s->g_mix, 0, s->counters);
+    launch_pdl(s, k_ckpt_copy, grid_blocks_launch(s), 256, 0, s->dense ? nullptr : o.blocks, o.nblocks, s->B * s->P.nb3, s->ckpt_cap, s->ckpt + (size_t)f * s->ckpt_rec,
+                                                             nullptr, s->g_out, s->g_mix, 0, s->counters, nullptr, nullptr);
     CKLN(s, "ckpt_save");
     s->ckpt_order[f] = o.uid; s->ckpt_contact[f] = 1;
     return SMX_OK;
@@ -554,6 +571,7 @@ int smx_create(const smx_config* cfg, smx_sim** out) {
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, cfg->device));
     s->sm_count = prop.multiProcessorCount;
     s->pf_sc = s->sm_count * SMX_SC_MINB * SMX_TPB_SC; s->pf_g = s->sm_count * SMX_P2GG_MINB * SMX_TPB; s->pf_g2p = s->sm_count * 8 * SMX_TPB;
+    s->pdl = getenv("SMX_NO_PDL") == nullptr;
     if (getenv("SMX_NO_PREFETCH")) s->pf_sc = s->pf_g = s->pf_g2p = 1 << 30;
     if (cfg->stream || (cfg->flags & SMX_FLAG_EXTERNAL_STREAM)) s->stream = (cudaStream_t)cfg->stream;   // NULL + flag: the legacy default stream
     else { CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)); s->own_stream = true; }
@@ -1047,7 +1065,7 @@ int smx_substep_end(smx_sim* s, int32_t f) {
     s->mid_done = -1;
     TRY(forward_grid_save_contact(s, f));
     s->last_fwd = f;
-    if (s->P.n > 0) { k_g2p<<<nblk(s->P.n, SMX_TPB), SMX_TPB, 0, s->stream>>>(s->P, s->frame_ptr(f), s->frame_ptr(f + 1), s->g_out, s->pf_g2p); CKLN(s, "k_g2p"); }
+    if (s->P.n > 0) { launch_pdl(s, k_g2p, nblk(s->P.n, SMX_TPB), SMX_TPB, 0, s->P, s->frame_ptr(f), s->frame_ptr(f + 1), s->g_out, s->pf_g2p); CKLN(s, "k_g2p"); }
     if (s->cfg.sort_every > 0 && (f + 1) % s->cfg.sort_every == 0 && !(s->cfg.flags & SMX_FLAG_NO_SORT)) TRY(resort(s, f + 1, true));
     return SMX_OK;
 }
@@ -1096,7 +1114,7 @@ int smx_substep_grad_begin(smx_sim* s, int32_t f) {
         // nothing to do: k_grid_grad of substep f+1 restored g_out (/ g_mix) and cleared the adjoint grids; g_in is read from the record
     } else if (have_rec) {
         // restore g_in / g_out (/ g_mix) and zero the adjoint grids of the same blocks in one launch
-        k_ckpt_copy<<<grid_blocks_launch(s), 256, 0, s->stream>>>(s->dense ? nullptr : ord.blocks, ord.nblocks, s->B * s->P.nb3, s->ckpt_cap, s->ckpt + (size_t)f * s->ckpt_rec,
+        launch_pdl(s, k_ckpt_copy, grid_blocks_launch(s), 256, 0, s->dense ? nullptr : ord.blocks, ord.nblocks, s->B * s->P.nb3, s->ckpt_cap, s->ckpt + (size_t)f * s->ckpt_rec,
                                                                  s->g_in, s->g_out, contact ? s->g_mix : nullptr, 1, s->counters, gg, contact ? s->gg_mix : nullptr);
         CKLN(s, "ckpt_restore");
     } else {
@@ -1108,8 +1126,8 @@ int smx_substep_grad_begin(smx_sim* s, int32_t f) {
     s->bwd_prepared = -1;
     const float* fin = s->frame_ptr(f);
     if (P.n > 0) {
-        if (s->cfg.flags & SMX_FLAG_DIRECT_RED) k_g2p_grad<false><<<nblk(P.n, SMX_TPB_SC), SMX_TPB_SC, 0, s->stream>>>(P, fin, s->adj_cur, s->adj_nxt, s->g_out, gg, s->pf_sc);
-        else k_g2p_grad<true><<<nblk(P.n, SMX_TPB_SC), SMX_TPB_SC, 0, s->stream>>>(P, fin, s->adj_cur, s->adj_nxt, s->g_out, gg, s->pf_sc);
+        if (s->cfg.flags & SMX_FLAG_DIRECT_RED) launch_pdl(s, k_g2p_grad<false>, nblk(P.n, SMX_TPB_SC), SMX_TPB_SC, 0, P, fin, s->adj_cur, s->adj_nxt, s->g_out, gg, s->pf_sc);
+        else launch_pdl(s, k_g2p_grad<true>, nblk(P.n, SMX_TPB_SC), SMX_TPB_SC, 0, P, fin, s->adj_cur, s->adj_nxt, s->g_out, gg, s->pf_sc);
         CKLN(s, "k_g2p_grad");
     }
     s->grad_pending = f;
@@ -1125,7 +1143,7 @@ int smx_substep_grad_mid(smx_sim* s, int32_t f) {
     if (s->has_contact() && P.n > 0) {
         PrimSet ps = s->primset();
         float life = 1.0f / (float)(P.substeps - f % P.substeps);
-        k_contact_grad<<<nblk(P.n, SMX_TPB), SMX_TPB, 0, s->stream>>>(P, ps, f, life, s->frame_ptr(f), s->adj_nxt, s->g_mix, s->gg_of(f), s->gg_mix); CKLN(s, "k_contact_grad");
+        launch_pdl(s, k_contact_grad, nblk(P.n, SMX_TPB), SMX_TPB, 0, P, ps, f, life, s->frame_ptr(f), s->adj_nxt, s->g_mix, s->gg_of(f), s->gg_mix); CKLN(s, "k_contact_grad");
     }
     s->grad_mid_done = f;
     return SMX_OK;
@@ -1151,7 +1169,7 @@ int smx_substep_grad_end(smx_sim* s, int32_t f) {
                           (bool)s->ckpt_contact[f - 1] == contact && s->trans_from[f] < 0;
         const float4* rec_in = have_rec ? s->ckpt + (size_t)f * s->ckpt_rec : nullptr;
         const float4* rec_prev = prep ? s->ckpt + (size_t)(f - 1) * s->ckpt_rec : nullptr;
-        k_grid_grad<<<grid_blocks_launch(s), 256, 0, s->stream>>>(P, ps, f, s->dense ? nullptr : ord.blocks, ord.nblocks, s->g_in, gg, contact ? s->gg_mix : nullptr,
+        launch_pdl(s, k_grid_grad, grid_blocks_launch(s), 256, 0, P, ps, f, s->dense ? nullptr : ord.blocks, ord.nblocks, s->g_in, gg, contact ? s->gg_mix : nullptr,
                                                                  rec_in, rec_prev, s->ckpt_cap, contact ? 1 : 0, s->g_out, s->g_mix, s->gg_of(f - 1));
         CKLN(s, "k_grid_grad");
         s->bwd_prepared = prep ? f - 1 : -1; s->bwd_prepared_uid = ord.uid;
@@ -1176,9 +1194,9 @@ int smx_substep_grad_end(smx_sim* s, int32_t f) {
                     const size_t smem = (size_t)2 * SMX_P2GG_NPL(M, R) * SMX_TPB * sizeof(float4);
                     static bool attr_set = false;
                     if (!attr_set) { cudaFuncSetAttribute(k_p2g_grad_tiled<M, R, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
-                    k_p2g_grad_tiled<M, R, E><<<grid, SMX_TPB, smem, s->stream>>>(P, ps, f, fin, s->adj_cur, s->adj_nxt, gg, cslot, s->action, s->action_grad, rec, ntiles);
+                    launch_pdl(s, k_p2g_grad_tiled<M, R, E>, grid, SMX_TPB, smem, P, ps, f, fin, s->adj_cur, s->adj_nxt, gg, cslot, s->action, s->action_grad, rec, ntiles);
                 } else {
-                    k_p2g_grad<M, R, E><<<nblk(P.n, SMX_TPB), SMX_TPB, 0, s->stream>>>(P, ps, f, fin, s->adj_cur, s->adj_nxt, gg, cslot, s->action, s->action_grad, rec, s->pf_g);
+                    launch_pdl(s, k_p2g_grad<M, R, E>, nblk(P.n, SMX_TPB), SMX_TPB, 0, P, ps, f, fin, s->adj_cur, s->adj_nxt, gg, cslot, s->action, s->action_grad, rec, s->pf_g);
                 }
             };
             if (use_rec) { if (extra) go(std::true_type(), std::true_type()); else go(std::true_type(), std::false_type()); }
@@ -1253,7 +1271,7 @@ int smx_step(smx_sim* s, int32_t s0, int32_t count) {
         bool resort_next = s->cfg.sort_every > 0 && (f + 1) % s->cfg.sort_every == 0 && !(s->cfg.flags & SMX_FLAG_NO_SORT);
         bool last = (i == count - 1);
         if (!last && !resort_next && f + 2 < s->cfg.max_steps && !s->ckpt_dirty) { pending_g2p = true; continue; }
-        k_g2p<<<nblk(s->P.n, SMX_TPB), SMX_TPB, 0, s->stream>>>(s->P, s->frame_ptr(f), s->frame_ptr(f + 1), s->g_out, s->pf_g2p); CKLN(s, "k_g2p");
+        launch_pdl(s, k_g2p, nblk(s->P.n, SMX_TPB), SMX_TPB, 0, s->P, s->frame_ptr(f), s->frame_ptr(f + 1), s->g_out, s->pf_g2p); CKLN(s, "k_g2p");
         if (resort_next) TRY(resort(s, f + 1, true));
     }
     return SMX_OK;
@@ -1420,8 +1438,8 @@ int smx_get_grid(smx_sim* s, float* g_in, float* g_out) {
         if (!s->ckpt || s->order_of[f] < 0 || s->ckpt_order[f] != s->orders[s->order_of[f]].uid)
             return fail(SMX_ERR_STATE, "smx_get_grid: g_in of substep %d was not retained (grid checkpoints disabled)", f);
         Order& o = s->orders[s->order_of[f]];
-        k_ckpt_copy<<<grid_blocks_launch(s), 256, 0, s->stream>>>(s->dense ? nullptr : o.blocks, o.nblocks, s->B * s->P.nb3, s->ckpt_cap, s->ckpt + (size_t)f * s->ckpt_rec,
-                                                                 s->g_in, nullptr, nullptr, 1, s->counters);
+        launch_pdl(s, k_ckpt_copy, grid_blocks_launch(s), 256, 0, s->dense ? nullptr : o.blocks, o.nblocks, s->B * s->P.nb3, s->ckpt_cap, s->ckpt + (size_t)f * s->ckpt_rec,
+                                                                 s->g_in, nullptr, nullptr, 1, s->counters, nullptr, nullptr);
         CKL(s);
         s->g_in_clean_uid = -1;
     }

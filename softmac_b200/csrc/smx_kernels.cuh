@@ -89,6 +89,13 @@ __device__ __forceinline__ V3 load_x(const float* __restrict__ fr, long long str
     return v3(a.x, a.y, a.z);
 }
 
+// Programmatic dependent launch: let the next kernel of the stream be scheduled early, then wait until the previous one has
+// completed and flushed its memory.  Both are no-ops for a kernel that was not launched with the PDL attribute.
+__device__ __forceinline__ void pdl_prologue() {
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 #define SMX_TPB 128         // gather-type particle kernels
 #define SMX_TPB_SC 96       // scatter-type particle kernels (three warps x 14.6 KB of staging; five CTAs per SM)
 #define SMX_SC_MINB 5
@@ -473,6 +480,7 @@ __global__ void __launch_bounds__(SMX_TPB_SC, SMX_SC_MINB) k_p2g(Params P, PrimS
                                                     float4* __restrict__ g_in, const int* __restrict__ ctrl_slot,
                                                     const float* __restrict__ action, int accumulate,
                                                     const float* __restrict__ fprev, const float4* __restrict__ g_prev, float4* __restrict__ rec, int pf_dist) {
+    pdl_prologue();
     // EXTRA: particle-contact impulses (collision_type == 1) and / or particle control forces are present
     __shared__ WarpStage stage[STAGED ? SMX_TPB_SC / 32 : 1];
     constexpr bool has_svd = (MAT / 3 == 0) && (MAT % 3 != 2);
@@ -480,19 +488,21 @@ __global__ void __launch_bounds__(SMX_TPB_SC, SMX_SC_MINB) k_p2g(Params P, PrimS
     bool live = j < P.n;
     int jj = live ? j : P.n - 1;
     if (!fprev) prefetch_planes(fin, P.stride, (long long)j + pf_dist, P.n, 0, SMX_NPLANES);
+    else { prefetch_planes(fprev, P.stride, (long long)j + pf_dist, P.n, 0, 1); prefetch_planes(fin, P.stride, (long long)j + pf_dist, P.n, 3, SMX_NPLANES); }
     V3 x, v; M3 F, C;
     int bt = batch_of(P, jj);
     if (fprev) {        // fused G2P of substep f-1: frame f-1 -> x, v, C of frame f
         V3 xo = load_x(fprev, P.stride, jj);
-        Stencil so = make_stencil(xo.x, xo.y, xo.z, P, bt);
-        g2p_gather(P, so, g_prev, v, C);
-        x = xo + P.dt * v;
-        {   // F of frame f was written by the previous P2G launch (plain loads: this kernel writes the same planes)
+        {   // F of frame f was written by the previous P2G launch (plain loads: this kernel writes the same planes); issued before
+            // the gather so that the HBM latency overlaps the 27 grid loads
             const float4* b = reinterpret_cast<const float4*>(fin) + jj;
             float f0 = reinterpret_cast<const float*>(b + 3 * P.stride)[3];
             float4 p4 = b[4 * P.stride], p5 = b[5 * P.stride];
             F.m[0] = f0; F.m[1] = p4.x; F.m[2] = p4.y; F.m[3] = p4.z; F.m[4] = p4.w; F.m[5] = p5.x; F.m[6] = p5.y; F.m[7] = p5.z; F.m[8] = p5.w;
         }
+        Stencil so = make_stencil(xo.x, xo.y, xo.z, P, bt);
+        g2p_gather(P, so, g_prev, v, C);
+        x = xo + P.dt * v;
         if (live) store_xvC(fin, P.stride, j, x, v, C);
     } else load_state(fin, P.stride, jj, x, v, F, C);
     V3 imp = v3(0, 0, 0);
@@ -560,6 +570,7 @@ __global__ void __launch_bounds__(256) k_grid_op(Params P, PrimSet ps, int f, co
                                                  float4* __restrict__ g_in, float4* __restrict__ g_out, float4* __restrict__ g_mix,
                                                  int accumulate, float4* __restrict__ rec, int cap, int save_out, int zero_in,
                                                  unsigned long long* __restrict__ counters) {
+    pdl_prologue();
     int total = blocks ? *nblocks : P.nbatch * P.nb3;
     if (rec && total > cap && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(counters + 2, 1ull);   // record does not fit
     for (int bi = blockIdx.x * 4 + (threadIdx.x >> 6); bi < total; bi += gridDim.x * 4) {
@@ -607,6 +618,7 @@ __global__ void __launch_bounds__(256) k_grid_op(Params P, PrimSet ps, int f, co
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SMX_TPB) k_contact(Params P, PrimSet ps, int f, float life, const float* __restrict__ fin,
                                                      const float4* __restrict__ g_mix, float4* __restrict__ g_out, int accumulate) {
+    pdl_prologue();
     int j = blockIdx.x * SMX_TPB + threadIdx.x;
     bool live = j < P.n;
     int jj = live ? j : P.n - 1;
@@ -665,6 +677,7 @@ __global__ void __launch_bounds__(SMX_TPB) k_contact(Params P, PrimSet ps, int f
 // G2P: gather v, C (APIC) and advect.  Writes x, v, C of frame f+1.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SMX_TPB) k_g2p(Params P, const float* __restrict__ fin, float* __restrict__ fout, const float4* __restrict__ g_out, int pf_dist) {
+    pdl_prologue();
     int j = blockIdx.x * SMX_TPB + threadIdx.x;
     if (j >= P.n) return;
     prefetch_planes(fin, P.stride, (long long)j + pf_dist, P.n, 0, 1);
@@ -685,6 +698,7 @@ __global__ void __launch_bounds__(SMX_TPB) k_g2p(Params P, const float* __restri
 template <bool STAGED>
 __global__ void __launch_bounds__(SMX_TPB_SC, SMX_G2PG_MINB) k_g2p_grad(Params P, const float* __restrict__ fin, const float* __restrict__ ain,
                                                          float* __restrict__ aout, const float4* __restrict__ g_out, float4* __restrict__ gg_out, int pf_dist) {
+    pdl_prologue();
     __shared__ WarpStage3 stage[STAGED ? SMX_TPB_SC / 32 : 1];
     int j = blockIdx.x * SMX_TPB_SC + threadIdx.x;
     bool live = j < P.n;
@@ -754,6 +768,7 @@ __global__ void __launch_bounds__(SMX_TPB_SC, SMX_G2PG_MINB) k_g2p_grad(Params P
 __global__ void __launch_bounds__(SMX_TPB) k_contact_grad(Params P, PrimSet ps, int f, float life, const float* __restrict__ fin,
                                                           float* __restrict__ aout, const float4* __restrict__ g_mix,
                                                           const float4* __restrict__ gg_out, float4* __restrict__ gg_mix) {
+    pdl_prologue();
     int j = blockIdx.x * SMX_TPB + threadIdx.x;
     bool live = j < P.n;
     int jj = live ? j : P.n - 1;
@@ -864,6 +879,7 @@ __global__ void __launch_bounds__(256) k_grid_grad(Params P, PrimSet ps, int f, 
                                                    const float4* __restrict__ g_in, float4* __restrict__ gg_out, float4* __restrict__ gg_mix,
                                                    const float4* __restrict__ rec_in, const float4* __restrict__ rec_prev, int cap, int prev_mix,
                                                    float4* __restrict__ g_out, float4* __restrict__ g_mix, float4* __restrict__ gg_next) {
+    pdl_prologue();
     int total = blocks ? *nblocks : P.nbatch * P.nb3;
     for (int bi = blockIdx.x * 4 + (threadIdx.x >> 6); bi < total; bi += gridDim.x * 4) {
         uint32_t node = (blocks ? blocks[bi] : (uint32_t)bi) * 64u + (threadIdx.x & 63);
@@ -1140,6 +1156,7 @@ template <int MAT, bool REC, bool EXTRA>
 __global__ void __launch_bounds__(SMX_TPB, SMX_P2GG_MINB) k_p2g_grad(Params P, PrimSet ps, int f, const float* __restrict__ fin, const float* __restrict__ ain,
                                                       float* __restrict__ aout, const float4* __restrict__ gg, const int* __restrict__ ctrl_slot,
                                                       const float* __restrict__ action, double* __restrict__ action_grad, const float4* __restrict__ rec, int pf_dist) {
+    pdl_prologue();
     constexpr bool corot = (MAT / 3 == 0) && (MAT % 3 != 2);
     int j = blockIdx.x * SMX_TPB + threadIdx.x;
     bool live = j < P.n;
@@ -1164,6 +1181,7 @@ template <int MAT, bool REC, bool EXTRA>
 __global__ void __launch_bounds__(SMX_TPB, SMX_P2GG_MINB) k_p2g_grad_tiled(Params P, PrimSet ps, int f, const float* __restrict__ fin, const float* __restrict__ ain,
                                                             float* __restrict__ aout, const float4* __restrict__ gg, const int* __restrict__ ctrl_slot,
                                                             const float* __restrict__ action, double* __restrict__ action_grad, const float4* __restrict__ rec, int ntiles) {
+    pdl_prologue();
     constexpr int NPL = SMX_P2GG_NPL(MAT, REC);
     extern __shared__ __align__(128) float4 smx_dyn_smem[];
     __shared__ uint64_t bar[2];
@@ -1320,6 +1338,7 @@ __global__ void k_mark_blocks_sorted(Params P, const uint32_t* __restrict__ keys
 __global__ void __launch_bounds__(256) k_ckpt_copy(const uint32_t* __restrict__ blocks, const int* __restrict__ nblocks, int nb3, int cap,
                                                     float4* __restrict__ rec, float4* __restrict__ a, float4* __restrict__ b, float4* __restrict__ c, int restore,
                                                     unsigned long long* __restrict__ counters, float4* __restrict__ zero_a = nullptr, float4* __restrict__ zero_b = nullptr) {
+    pdl_prologue();
     int total = blocks ? *nblocks : nb3;
     if (total > cap) {      // record does not fit: flagged, the host falls back to recomputation (counters[2])
         if (blockIdx.x == 0 && threadIdx.x == 0 && !restore) atomicAdd(counters + 2, 1ull);

@@ -12,6 +12,13 @@ grip_palm_contact.npz : 2500 grip particles (fp32-rounded), the palm SDF (fp32) 
                         5 substeps (substeps = 5 => life = 1/5 .. 1), demo_grip material (plastic, corotated, E 3e3,
                         nu 0.2, gravity -9.8, sticky floor, mixed contact, softness 666, friction 0.001), then the adjoint
                         of a dense seed x_bar[5] = x[5] - mean and a wrench seed.
+reference_rest_states.npz : the reference's own simulated states, copied as data (fp32): the full demo_grip initial state
+                        (10000 x 24: plasticine that the REFERENCE simulator let settle on the sticky floor, residual rms velocity
+                        1.3e-3 m/s, all singular values of F inside the plastic clip [0.998, 1.003]) and the demo_pour initial state
+                        (5000 x 24 liquid at rest in the glass).  These are the only outputs of the reference simulator that ship
+                        with the repository; tests/test_reference_states.py uses them as a (weak) pin: a state the reference
+                        produced as a rest state must be a rest state of the oracle and of the CUDA path under the demo's
+                        material parameters, and must stop being one when the parameters are wrong.
 """
 import os
 import pickle
@@ -25,8 +32,16 @@ sys.path.insert(0, ROOT)
 REF = "/root/reference/softmac"
 
 
+def reference_states():
+    grip = np.load(os.path.join(REF, "envs/grip/grip_mpm_init_state.npy")).astype(np.float32)
+    pour = np.load(os.path.join(REF, "envs/pour/pour_mpm_init_state_corotated.npy")).astype(np.float32)
+    np.savez_compressed(os.path.join(HERE, "reference_rest_states.npz"), grip=grip, pour=pour)
+    print("reference_rest_states.npz", grip.shape, pour.shape)
+
+
 def main():
     from oracle import mpm_oracle as mo
+    reference_states()
     st = np.load(os.path.join(REF, "envs/grip/grip_mpm_init_state.npy"))
     rng = np.random.default_rng(0)
     sel = np.sort(rng.choice(len(st), 2500, replace=False))
