@@ -676,7 +676,10 @@ __global__ void __launch_bounds__(SMX_TPB) k_contact(Params P, PrimSet ps, int f
 // ------------------------------------------------------------------------------------------------
 // G2P: gather v, C (APIC) and advect.  Writes x, v, C of frame f+1.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SMX_TPB) k_g2p(Params P, const float* __restrict__ fin, float* __restrict__ fout, const float4* __restrict__ g_out, int pf_dist) {
+#ifndef SMX_G2P_MINB
+#define SMX_G2P_MINB 8
+#endif
+__global__ void __launch_bounds__(SMX_TPB, SMX_G2P_MINB) k_g2p(Params P, const float* __restrict__ fin, float* __restrict__ fout, const float4* __restrict__ g_out, int pf_dist) {
     pdl_prologue();
     int j = blockIdx.x * SMX_TPB + threadIdx.x;
     if (j >= P.n) return;
