@@ -126,6 +126,10 @@ struct smx_sim {
     size_t ckpt_bytes = 0;
     std::vector<long long> ckpt_order;  // uid of the ordering the record of substep f was written in (-1: none)
     // SVD records (U, V, sigma - 1, J - 1 of the forward P2G of every substep) so that the adjoint does not repeat the SVD
+    // per-substep "within reach of a primitive" bits of the forecast contact kernel (one word per warp of 32 slots)
+    uint32_t* near_pool = nullptr;
+    std::vector<long long> near_order;  // uid of the ordering the bits of substep f were written in (-1: none)
+    size_t near_words() const { return ((size_t)std::max(P.n, 1) + 31) / 32; }
     float4* svd_pool = nullptr;
     std::vector<long long> svd_order;   // uid of the ordering the SVD record of substep f was written in (-1: none)
     float4* svd_rec(int f) { return svd_pool + (long long)f * SMX_RPLANES * P.stride; }
@@ -303,7 +307,7 @@ static int resort(smx_sim* s, int f, bool keep_transition) {
     }
     TRY(build_blocks(s, no, s->frame_ptr(f), do_sort ? s->keys_b : nullptr));
     s->order_of[f] = new_order_id(s, no);
-    s->ckpt_order[f] = -1; s->svd_order[f] = -1;
+    s->ckpt_order[f] = -1; s->svd_order[f] = -1; s->near_order[f] = -1;
     // keep_transition: frame f was produced by substep f-1 in the old ordering, so the adjoint has to be carried
     // back through idx; otherwise (user-written frame) the adjoint chain is cut here, as in the reference
     s->trans_from[f] = (keep_transition && do_sort) ? old_id : -1;
@@ -430,7 +434,10 @@ static int forward_grid(smx_sim* s, int f, bool accumulate, bool checkpoint) {
     if (checkpoint) s->g_in_clean_uid = o.uid;
     if (contact && P.n > 0) {
         float life = 1.0f / (float)(P.substeps - f % P.substeps);      // mpm_simulator.py:425 (f32 in the reference too)
-        launch_pdl(s, k_contact, nblk(P.n, SMX_TPB), SMX_TPB, 0, P, ps, f, life, s->frame_ptr(f), s->g_mix, s->g_out, accumulate ? 1 : 0); CKLN(s, "k_contact");
+        if (!s->near_pool && cudaMalloc(&s->near_pool, (size_t)s->cfg.max_steps * s->near_words() * sizeof(uint32_t)) != cudaSuccess) { cudaGetLastError(); s->near_pool = nullptr; }
+        uint32_t* near = s->near_pool ? s->near_pool + (size_t)f * s->near_words() : nullptr;
+        launch_pdl(s, k_contact, nblk(P.n, SMX_TPB), SMX_TPB, 0, P, ps, f, life, s->frame_ptr(f), s->g_mix, s->g_out, accumulate ? 1 : 0, near); CKLN(s, "k_contact");
+        s->near_order[f] = near ? o.uid : -1;
     }
     if (save && !contact) { s->ckpt_order[f] = o.uid; s->ckpt_contact[f] = 0; }
     return SMX_OK;
@@ -606,7 +613,7 @@ int smx_create(const smx_config* cfg, smx_sim** out) {
     s->spare_slot = T;
     size_t pool_bytes = (size_t)(T + 1) * s->frame_floats * sizeof(float);
     if (cudaMalloc(&s->pool, pool_bytes) != cudaSuccess) { cudaGetLastError(); delete s; return fail(SMX_ERR_NOMEM, "smx_create: cannot allocate %.1f MB of particle checkpoints", pool_bytes / 1e6); }
-    s->ckpt_order.assign(T, -1); s->ckpt_contact.assign(T, 0); s->svd_order.assign(T, -1);
+    s->ckpt_order.assign(T, -1); s->ckpt_contact.assign(T, 0); s->svd_order.assign(T, -1); s->near_order.assign(T, -1);
     if (cfg->material_model == 0 && cfg->ptype != 2 && !(cfg->flags & SMX_FLAG_NO_SVD_REC)) {
         // optional: without it (flag, or not enough memory) the adjoint recomputes the SVD
         size_t svd_bytes = (size_t)T * SMX_RPLANES * P.stride * sizeof(float4), free_b = 0, total_b = 0;
@@ -669,7 +676,7 @@ int smx_destroy(smx_sim* s) {
     for (auto& kv : s->seeds) cudaFree(kv.second.dev);
     for (auto& kv : s->seed_pool) cudaFree(kv.second);
     for (auto& p : s->prims) { cudaFree(p.sdf_dev); cudaFree(p.nrm_dev); }
-    void* ptrs[] = {s->svd_pool, s->ch_target, s->ch_loss, s->ckpt, s->pool, s->g_in, s->g_out, s->g_mix, s->gg_out, s->gg_out_b, s->gg_mix, s->g_lin, s->adj_cur, s->adj_nxt, s->stage_dev, s->keys_a, s->keys_b, s->iota, s->cub_tmp,
+    void* ptrs[] = {s->near_pool, s->svd_pool, s->ch_target, s->ch_loss, s->ckpt, s->pool, s->g_in, s->g_out, s->g_mix, s->gg_out, s->gg_out_b, s->gg_mix, s->g_lin, s->adj_cur, s->adj_nxt, s->stage_dev, s->keys_a, s->keys_b, s->iota, s->cub_tmp,
                     s->counters, s->prims_dev, s->pstate, s->pgrad, s->ext_f, s->ext_f_grad, s->abuf, s->gabuf, s->ctrl_id, s->action, s->action_grad};
     for (void* p : ptrs) cudaFree(p);
     cudaFreeHost(s->stage_host);
@@ -722,6 +729,7 @@ int smx_set_primitive_contact(smx_sim* s, int32_t id, int32_t enabled) {
     TRY(check_prim(s, id, "smx_set_primitive_contact"));
     s->prims[id].d.enabled = enabled ? 1 : 0;
     s->ckpt_dirty = true;
+    std::fill(s->near_order.begin(), s->near_order.end(), -1);
     return sync_prims(s);
 }
 
@@ -734,6 +742,7 @@ int smx_reset(smx_sim* s, const double* state, int32_t ncols) {
     std::fill(s->trans_from.begin(), s->trans_from.end(), -1);
     std::fill(s->ckpt_order.begin(), s->ckpt_order.end(), -1);
     std::fill(s->svd_order.begin(), s->svd_order.end(), -1);
+    std::fill(s->near_order.begin(), s->near_order.end(), -1);
     s->adj_frame = -1; s->adj_order = -1;
     s->ckpt_dirty = true;
     gc_orders(s);                       // every ordering is unreferenced now: recycle all of them
@@ -762,7 +771,7 @@ int smx_set_frame(smx_sim* s, int32_t f, const double* x, const double* v, const
     TRY(check_frame(s, f, "smx_set_frame"));
     CK(cudaSetDevice(s->cfg.device));
     TRY(ensure_order(s, f));
-    s->ckpt_order[f] = -1; s->svd_order[f] = -1;
+    s->ckpt_order[f] = -1; s->svd_order[f] = -1; s->near_order[f] = -1;
     if (x) TRY(upload_cols(s, f, x, 3, 0));
     if (v) TRY(upload_cols(s, f, v, 3, 3));
     if (F) TRY(upload_cols(s, f, F, 9, 6));
@@ -795,7 +804,7 @@ int smx_copy_frame(smx_sim* s, int32_t src, int32_t dst) {
     CK(cudaSetDevice(s->cfg.device));
     if (src != dst) {
         CK(cudaMemcpyAsync(s->frame_ptr(dst), s->frame_ptr(src), s->frame_floats * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
-        s->order_of[dst] = s->order_of[src]; s->trans_from[dst] = -1; s->ckpt_order[dst] = -1; s->svd_order[dst] = -1;
+        s->order_of[dst] = s->order_of[src]; s->trans_from[dst] = -1; s->ckpt_order[dst] = -1; s->svd_order[dst] = -1; s->near_order[dst] = -1;
         int T = s->cfg.max_steps;
         for (int b = 0; b < s->B; b++)
             for (size_t ii = 0; ii < s->prims.size(); ii++) {
@@ -825,6 +834,7 @@ static int set_prim_state(smx_sim* s, int b0, int b1, int id, int f0, int f1, co
     CK(cudaSetDevice(s->cfg.device));
     std::vector<float> h((size_t)(f1 - f0) * 13);
     for (int f = 0; f < f1 - f0; f++) for (int c = 0; c < 13; c++) h[(size_t)f * 13 + c] = (float)s13[c];
+    for (int f = f0; f < f1; f++) s->near_order[f] = -1;        // the recorded reach bits of these substeps are stale
     for (int b = b0; b < b1; b++)
         CK(cudaMemcpyAsync(s->pstate + (prim_slot(s, b, id) * s->cfg.max_steps + f0) * 13, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, s->stream));
     CK(cudaStreamSynchronize(s->stream));
@@ -950,6 +960,7 @@ int smx_set_primitive_states_all(smx_sim* s, int32_t f0, int32_t f1, const doubl
     CK(cudaStreamSynchronize(s->stream));
     for (size_t i = 0; i < cnt; i++) s->stage_host[i] = (float)st[i];
     CK(cudaMemcpyAsync(s->stage_dev, s->stage_host, cnt * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    for (int f = f0; f < f1; f++) s->near_order[f] = -1;
     long long nt = (long long)s->B * np * (f1 - f0);
     k_fill_prim_states<<<nblk(nt, 128), 128, 0, s->stream>>>(s->pstate, s->stage_dev, s->cfg.max_steps, np, s->B, f0, f1); CKL(s);
     return SMX_OK;
@@ -1044,7 +1055,7 @@ int smx_substep_begin(smx_sim* s, int32_t f) {
     if (s->order_of[f] < 0) return fail(SMX_ERR_STATE, "smx_substep: frame %d has not been written (call smx_reset / smx_set_frame first)", f);
     CK(cudaSetDevice(s->cfg.device));
     s->order_of[f + 1] = s->order_of[f]; s->trans_from[f + 1] = -1;
-    s->ckpt_order[f] = -1; s->ckpt_order[f + 1] = -1; s->svd_order[f] = -1; s->svd_order[f + 1] = -1;
+    s->ckpt_order[f] = -1; s->ckpt_order[f + 1] = -1; s->svd_order[f] = -1; s->near_order[f] = -1; s->svd_order[f + 1] = -1;
     if (s->ckpt_dirty) TRY(ensure_ckpt(s, f));
     return forward_p2g(s, f, true, true);
 }
@@ -1143,7 +1154,8 @@ int smx_substep_grad_mid(smx_sim* s, int32_t f) {
     if (s->has_contact() && P.n > 0) {
         PrimSet ps = s->primset();
         float life = 1.0f / (float)(P.substeps - f % P.substeps);
-        launch_pdl(s, k_contact_grad, nblk(P.n, SMX_TPB), SMX_TPB, 0, P, ps, f, life, s->frame_ptr(f), s->adj_nxt, s->g_mix, s->gg_of(f), s->gg_mix); CKLN(s, "k_contact_grad");
+        const uint32_t* near = (s->near_pool && s->near_order[f] == s->orders[s->order_of[f]].uid) ? s->near_pool + (size_t)f * s->near_words() : nullptr;
+        launch_pdl(s, k_contact_grad, nblk(P.n, SMX_TPB), SMX_TPB, 0, P, ps, f, life, s->frame_ptr(f), s->adj_nxt, s->g_mix, s->gg_of(f), s->gg_mix, near); CKLN(s, "k_contact_grad");
     }
     s->grad_mid_done = f;
     return SMX_OK;
@@ -1260,7 +1272,7 @@ int smx_step(smx_sim* s, int32_t s0, int32_t count) {
             if (f + 1 >= s->cfg.max_steps) return fail(SMX_ERR_RANGE, "smx_step: substep %d would write frame %d >= max_steps %d", f, f + 1, s->cfg.max_steps);
             CK(cudaSetDevice(s->cfg.device));
             s->order_of[f + 1] = s->order_of[f]; s->trans_from[f + 1] = -1;
-            s->ckpt_order[f] = -1; s->ckpt_order[f + 1] = -1; s->svd_order[f] = -1; s->svd_order[f + 1] = -1;
+            s->ckpt_order[f] = -1; s->ckpt_order[f + 1] = -1; s->svd_order[f] = -1; s->near_order[f] = -1; s->svd_order[f + 1] = -1;
             TRY(forward_p2g(s, f, true, true, true));
             pending_g2p = false;
         }

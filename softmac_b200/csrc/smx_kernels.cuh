@@ -617,7 +617,8 @@ __global__ void __launch_bounds__(256) k_grid_op(Params P, PrimSet ps, int f, co
 // scatter -2 w (v_tmp - v_tgt) into g_out where the node is active; reduce the wrench per body.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SMX_TPB) k_contact(Params P, PrimSet ps, int f, float life, const float* __restrict__ fin,
-                                                     const float4* __restrict__ g_mix, float4* __restrict__ g_out, int accumulate) {
+                                                     const float4* __restrict__ g_mix, float4* __restrict__ g_out, int accumulate,
+                                                     uint32_t* __restrict__ near_mask) {
     pdl_prologue();
     int j = blockIdx.x * SMX_TPB + threadIdx.x;
     bool live = j < P.n;
@@ -631,7 +632,10 @@ __global__ void __launch_bounds__(SMX_TPB) k_contact(Params P, PrimSet ps, int f
         PrimState S = load_prim_state(pstate_at(ps, bt, i, f));
         near |= live && (prim_sdf(ps.prims[i], S, x) <= 5e-3f);
     }
-    if (!__any_sync(0xffffffffu, near)) return;
+    const unsigned near_bits = __ballot_sync(0xffffffffu, near);
+    // one word per warp, kept per substep: the adjoint kernel skips the SDF look-ups of every warp that has no particle in reach
+    if (near_mask && (threadIdx.x & 31) == 0) near_mask[j >> 5] = near_bits;
+    if (!near_bits) return;
     Stencil s = make_stencil(x.x, x.y, x.z, P, bt);
     V3 vtmp = v3(0, 0, 0);
     uint32_t onmask = 0;
@@ -770,20 +774,28 @@ __global__ void __launch_bounds__(SMX_TPB_SC, SMX_G2PG_MINB) k_g2p_grad(Params P
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SMX_TPB) k_contact_grad(Params P, PrimSet ps, int f, float life, const float* __restrict__ fin,
                                                           float* __restrict__ aout, const float4* __restrict__ g_mix,
-                                                          const float4* __restrict__ gg_out, float4* __restrict__ gg_mix) {
+                                                          const float4* __restrict__ gg_out, float4* __restrict__ gg_mix,
+                                                          const uint32_t* __restrict__ near_mask) {
     pdl_prologue();
     int j = blockIdx.x * SMX_TPB + threadIdx.x;
     bool live = j < P.n;
     int jj = live ? j : P.n - 1;
+    bool near = false;
+    if (near_mask) {            // recorded by k_contact of the same substep: most warps leave after one 4-byte load
+        const unsigned bits = near_mask[j >> 5];
+        if (!bits) return;
+        near = (bits >> (threadIdx.x & 31)) & 1u;
+    }
     V3 x = load_x(fin, P.stride, jj);
     int bt = batch_of(P, jj);
-    bool near = false;
-    for (int i = 0; i < P.np; i++) {
-        if (!ps.prims[i].enabled) continue;
-        PrimState S = load_prim_state(pstate_at(ps, bt, i, f));
-        near |= live && (prim_sdf(ps.prims[i], S, x) <= 5e-3f);
+    if (!near_mask) {
+        for (int i = 0; i < P.np; i++) {
+            if (!ps.prims[i].enabled) continue;
+            PrimState S = load_prim_state(pstate_at(ps, bt, i, f));
+            near |= live && (prim_sdf(ps.prims[i], S, x) <= 5e-3f);
+        }
+        if (!__any_sync(0xffffffffu, near)) return;
     }
-    if (!__any_sync(0xffffffffu, near)) return;
     Stencil s = make_stencil(x.x, x.y, x.z, P, bt);
     float dwx[3], dwy[3], dwz[3];
     axis_dweights(s.fx, dwx); axis_dweights(s.fy, dwy); axis_dweights(s.fz, dwz);
