@@ -92,7 +92,7 @@ struct smx_sim {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     int sm_count = 148;
-    bool pdl = true;
+    bool pdl = true, pdl_grid = false;
     int pf_sc = 0, pf_g = 0, pf_g2p = 0;   // L2 prefetch distances (particles): one wave of resident CTAs of the scatter / gather kernels
     int B = 1;                          // batched independent rollouts
     // spatial slab decomposition (one rank of several): owned x-block columns [slab_lo, slab_hi), neighbours present?
@@ -130,6 +130,8 @@ struct smx_sim {
     uint32_t* near_pool = nullptr;
     std::vector<long long> near_order;  // uid of the ordering the bits of substep f were written in (-1: none)
     size_t near_words() const { return ((size_t)std::max(P.n, 1) + 31) / 32; }
+    size_t near_rec() const { return 32 + 2 * near_words(); }     // counter (padded) + reach bits + work list, per substep
+    uint32_t* near_of(int f) { return near_pool + (size_t)f * near_rec(); }
     float4* svd_pool = nullptr;
     std::vector<long long> svd_order;   // uid of the ordering the SVD record of substep f was written in (-1: none)
     float4* svd_rec(int f) { return svd_pool + (long long)f * SMX_RPLANES * P.stride; }
@@ -428,15 +430,22 @@ static int forward_grid(smx_sim* s, int f, bool accumulate, bool checkpoint) {
     bool save = checkpoint && s->ckpt && (!contact || s->ckpt_narr == 3);
     float4* rec = save ? s->ckpt + (size_t)f * s->ckpt_rec : nullptr;
     // checkpoint == forward pass proper: also save the grid record and re-zero g_in for the next substep's P2G
-    launch_pdl(s, k_grid_op, grid_blocks_launch(s), 256, 0, P, ps, f, s->dense ? nullptr : o.blocks, o.nblocks, s->g_in, s->g_out, contact ? s->g_mix : nullptr,
-                                                           accumulate ? 1 : 0, rec, s->ckpt_cap, contact ? 0 : 1, checkpoint ? 1 : 0, s->counters);
+    uint32_t* near = nullptr;
+    if (contact && P.n > 0) {
+        if (!s->near_pool && cudaMalloc(&s->near_pool, (size_t)s->cfg.max_steps * s->near_rec() * sizeof(uint32_t)) != cudaSuccess) { cudaGetLastError(); s->near_pool = nullptr; }
+        near = s->near_pool ? s->near_of(f) : nullptr;
+    }
+    { const bool saved_pdl = s->pdl; s->pdl = s->pdl && s->pdl_grid;
+    if (P.ctype == 0) launch_pdl(s, k_grid_op<true>, grid_blocks_launch(s), 256, 0, P, ps, f, s->dense ? nullptr : o.blocks, o.nblocks, s->g_in, s->g_out, contact ? s->g_mix : nullptr,
+                                                           accumulate ? 1 : 0, rec, s->ckpt_cap, contact ? 0 : 1, checkpoint ? 1 : 0, s->counters, near);
+    else launch_pdl(s, k_grid_op<false>, grid_blocks_launch(s), 256, 0, P, ps, f, s->dense ? nullptr : o.blocks, o.nblocks, s->g_in, s->g_out, contact ? s->g_mix : nullptr,
+                                                           accumulate ? 1 : 0, rec, s->ckpt_cap, contact ? 0 : 1, checkpoint ? 1 : 0, s->counters, near);
+    s->pdl = saved_pdl; }
     CKLN(s, "k_grid_op");
     if (checkpoint) s->g_in_clean_uid = o.uid;
     if (contact && P.n > 0) {
         float life = 1.0f / (float)(P.substeps - f % P.substeps);      // mpm_simulator.py:425 (f32 in the reference too)
-        if (!s->near_pool && cudaMalloc(&s->near_pool, (size_t)s->cfg.max_steps * s->near_words() * sizeof(uint32_t)) != cudaSuccess) { cudaGetLastError(); s->near_pool = nullptr; }
-        uint32_t* near = s->near_pool ? s->near_pool + (size_t)f * s->near_words() : nullptr;
-        launch_pdl(s, k_contact, nblk(P.n, SMX_TPB), SMX_TPB, 0, P, ps, f, life, s->frame_ptr(f), s->g_mix, s->g_out, accumulate ? 1 : 0, near); CKLN(s, "k_contact");
+        launch_pdl(s, k_contact, nblk(P.n, SMX_TPB), SMX_TPB, 0, P, ps, f, life, s->frame_ptr(f), s->g_mix, s->g_out, accumulate ? 1 : 0, near, (int)s->near_words()); CKLN(s, "k_contact");
         s->near_order[f] = near ? o.uid : -1;
     }
     if (save && !contact) { s->ckpt_order[f] = o.uid; s->ckpt_contact[f] = 0; }
@@ -579,6 +588,9 @@ int smx_create(const smx_config* cfg, smx_sim** out) {
     s->sm_count = prop.multiProcessorCount;
     s->pf_sc = s->sm_count * SMX_SC_MINB * SMX_TPB_SC; s->pf_g = s->sm_count * SMX_P2GG_MINB * SMX_TPB; s->pf_g2p = s->sm_count * 8 * SMX_TPB;
     s->pdl = getenv("SMX_NO_PDL") == nullptr;
+    // the grid kernels are launched with plain stream serialisation: at 32 registers all their CTAs become resident next to the
+    // draining particle kernel and PDL then costs 10 % (measured 3.47 vs 3.84 G/s); SMX_PDL_GRID=1 turns it on for experiments
+    s->pdl_grid = getenv("SMX_PDL_GRID") != nullptr;
     if (getenv("SMX_NO_PREFETCH")) s->pf_sc = s->pf_g = s->pf_g2p = 1 << 30;
     if (cfg->stream || (cfg->flags & SMX_FLAG_EXTERNAL_STREAM)) s->stream = (cudaStream_t)cfg->stream;   // NULL + flag: the legacy default stream
     else { CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)); s->own_stream = true; }
@@ -1154,8 +1166,15 @@ int smx_substep_grad_mid(smx_sim* s, int32_t f) {
     if (s->has_contact() && P.n > 0) {
         PrimSet ps = s->primset();
         float life = 1.0f / (float)(P.substeps - f % P.substeps);
-        const uint32_t* near = (s->near_pool && s->near_order[f] == s->orders[s->order_of[f]].uid) ? s->near_pool + (size_t)f * s->near_words() : nullptr;
-        launch_pdl(s, k_contact_grad, nblk(P.n, SMX_TPB), SMX_TPB, 0, P, ps, f, life, s->frame_ptr(f), s->adj_nxt, s->g_mix, s->gg_of(f), s->gg_mix, near); CKLN(s, "k_contact_grad");
+        const uint32_t* near = (s->near_pool && s->near_order[f] == s->orders[s->order_of[f]].uid) ? s->near_of(f) : nullptr;
+        if (near) {
+            const int nwords = (int)s->near_words();
+            const int grid = s->sm_count * 2;
+            launch_pdl(s, k_contact_grad_sparse, grid, SMX_TPB, 0, P, ps, f, life, s->frame_ptr(f), s->adj_nxt, s->g_mix, s->gg_of(f), s->gg_mix, near, nwords);
+        } else {
+            launch_pdl(s, k_contact_grad, nblk(P.n, SMX_TPB), SMX_TPB, 0, P, ps, f, life, s->frame_ptr(f), s->adj_nxt, s->g_mix, s->gg_of(f), s->gg_mix);
+        }
+        CKLN(s, "k_contact_grad");
     }
     s->grad_mid_done = f;
     return SMX_OK;
@@ -1181,8 +1200,12 @@ int smx_substep_grad_end(smx_sim* s, int32_t f) {
                           (bool)s->ckpt_contact[f - 1] == contact && s->trans_from[f] < 0;
         const float4* rec_in = have_rec ? s->ckpt + (size_t)f * s->ckpt_rec : nullptr;
         const float4* rec_prev = prep ? s->ckpt + (size_t)(f - 1) * s->ckpt_rec : nullptr;
-        launch_pdl(s, k_grid_grad, grid_blocks_launch(s), 256, 0, P, ps, f, s->dense ? nullptr : ord.blocks, ord.nblocks, s->g_in, gg, contact ? s->gg_mix : nullptr,
+        { const bool saved_pdl = s->pdl; s->pdl = s->pdl && s->pdl_grid;
+        if (P.ctype == 0) launch_pdl(s, k_grid_grad<true>, grid_blocks_launch(s), 256, 0, P, ps, f, s->dense ? nullptr : ord.blocks, ord.nblocks, s->g_in, gg, contact ? s->gg_mix : nullptr,
                                                                  rec_in, rec_prev, s->ckpt_cap, contact ? 1 : 0, s->g_out, s->g_mix, s->gg_of(f - 1));
+        else launch_pdl(s, k_grid_grad<false>, grid_blocks_launch(s), 256, 0, P, ps, f, s->dense ? nullptr : ord.blocks, ord.nblocks, s->g_in, gg, contact ? s->gg_mix : nullptr,
+                                                                 rec_in, rec_prev, s->ckpt_cap, contact ? 1 : 0, s->g_out, s->g_mix, s->gg_of(f - 1));
+        s->pdl = saved_pdl; }
         CKLN(s, "k_grid_grad");
         s->bwd_prepared = prep ? f - 1 : -1; s->bwd_prepared_uid = ord.uid;
     }
