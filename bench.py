@@ -300,7 +300,7 @@ def run_cuda(args, rank, world, local_rank):
             sim.add_x_grad(S, seed)             # H2D: seed
             sim.step(0, S)
             sim.step_grad(S, S)
-            g0 = sim.get_state_grad(0)          # D2H: adjoint of the initial state
+            xg, vg = sim.get_grad(0)            # D2H: the reference's own read-out, MPMSimulator.get_grad(f) -> (x_bar, v_bar)
             if dist:
                 dist.all_reduce(gsum)
             barrier()
@@ -310,7 +310,8 @@ def run_cuda(args, rank, world, local_rank):
         if dist:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e = {"value": world * args.batch * args.n * S / float(t.item()), "unit": UNIT, "h2d_bytes_per_step": args.batch * (args.n * 24 * 4 + args.n * 3 * 4),
-               "d2h_bytes_per_step": args.batch * args.n * 24 * 4, "checksum": float(np.abs(g0).sum())}
+               "d2h_bytes_per_step": args.batch * args.n * 6 * 4, "checksum": float(np.abs(xg).sum() + np.abs(vg).sum()),
+               "api": "reset(state (n,24) f64) + add_x_grad + step + step_grad + get_grad(0) -> (x_bar, v_bar) f64"}
 
     if rank == 0:
         peak, peak_src = peaks()

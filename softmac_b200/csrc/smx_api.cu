@@ -542,6 +542,9 @@ static int upload_cols(smx_sim* s, int f, const double* host, int ncomp, int c0)
     k_upload<<<nblk(n, 256), 256, 0, s->stream>>>(n, s->P.stride, s->stage_dev, ncomp, c0, s->frame_ptr(f), perm, 0); CKL(s);
     return SMX_OK;
 }
+static void launch_plain_download(smx_sim* s, const float* frame, const uint32_t* perm, int ncomp, int c0) {
+    k_download<<<nblk(s->P.n, 256), 256, 0, s->stream>>>(s->P.n, s->P.stride, s->stage_dev, ncomp, c0, frame, perm);
+}
 static int download_cols(smx_sim* s, const float* frame, const uint32_t* perm, double* host, int ncomp, int c0) {
     int n = s->P.n;
     if (n == 0) return SMX_OK;
@@ -1418,9 +1421,27 @@ int smx_get_state_grad(smx_sim* s, int32_t f, double* out24) {
 int smx_get_grad(smx_sim* s, int32_t f, double* xg, double* vg) {
     TRY(check_frame(s, f, "smx_get_grad"));
     if (!xg || !vg) return fail(SMX_ERR_ARG, "smx_get_grad: null output");
-    std::vector<double> tmp((size_t)std::max(s->P.n, 1) * 24);
-    TRY(smx_get_state_grad(s, f, tmp.data()));
-    for (size_t p = 0; p < (size_t)s->P.n; p++) for (int c = 0; c < 3; c++) { xg[3 * p + c] = tmp[24 * p + c]; vg[3 * p + c] = tmp[24 * p + 3 + c]; }
+    CK(cudaSetDevice(s->cfg.device));
+    // MPMSimulator.get_grad (mpm_simulator.py:561-574): only the x and v columns travel (2 x n x 3 fp32 over PCIe)
+    const float* adj = s->adj_cur;
+    int order = s->adj_order;
+    if (s->adj_frame != f) {
+        if (s->order_of[f] < 0) return fail(SMX_ERR_STATE, "smx_get_grad: frame %d has not been written", f);
+        CK(cudaMemsetAsync(s->adj_nxt, 0, s->frame_floats * sizeof(float), s->stream));
+        TRY(apply_seed(s, f, s->adj_nxt, s->order_of[f]));
+        adj = s->adj_nxt; order = s->order_of[f];
+    }
+    // x and v are adjacent get_state columns (0..5): one gather kernel, one copy, then the split into the two host arrays
+    const int n = s->P.n;
+    if (n == 0) return SMX_OK;
+    launch_plain_download(s, adj, s->orders[order].perm, 6, 0);
+    CKL(s);
+    CK(cudaMemcpyAsync(s->stage_host, s->stage_dev, (size_t)n * 6 * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    const float* src = s->stage_host;
+    #pragma omp parallel for schedule(static) num_threads(smx_host_threads())
+    for (long long p = 0; p < (long long)n; p++)
+        for (int c = 0; c < 3; c++) { xg[3 * p + c] = (double)src[6 * p + c]; vg[3 * p + c] = (double)src[6 * p + 3 + c]; }
     return SMX_OK;
 }
 int smx_clear_grads(smx_sim* s) {

@@ -320,6 +320,27 @@ def test_svd_record_and_tma_staging_do_not_change_the_adjoint(flags, ptype):
     assert rel_l2(gb, ga) <= 2e-5 and cosine(gb, ga) >= 1 - 1e-9
 
 
+def test_get_grad_is_the_xv_part_of_the_state_adjoint():
+    """MPMSimulator.get_grad(f) -> (x.grad[f], v.grad[f]) (mpm_simulator.py:561-574), after a backward pass and for a frame that
+    only holds its loss seed."""
+    rng = np.random.default_rng(267)
+    n, steps = 3000, 4
+    pair = Pair(n, max_steps=8, sort_every=2)
+    pair.gpu.reset(scenes.blob_state(n, rng))
+    for f in range(steps):
+        pair.gpu.substep(f)
+    pair.gpu.clear_all_gradients()
+    pair.gpu.add_state_grad(steps, rng.normal(size=(n, 24)))
+    xs, vs = pair.gpu.get_grad(steps)                  # no backward step yet: just the seed
+    g = pair.gpu.get_state_grad(steps)
+    assert np.array_equal(xs, g[:, :3]) and np.array_equal(vs, g[:, 3:6]) and np.abs(xs).max() > 0
+    for f in range(steps - 1, -1, -1):
+        pair.gpu.substep_grad(f)
+    xg, vg = pair.gpu.get_grad(0)
+    g = pair.gpu.get_state_grad(0)
+    assert np.array_equal(xg, g[:, :3]) and np.array_equal(vg, g[:, 3:6]) and np.abs(vg).max() > 0
+
+
 def test_api_quirks_and_errors():
     from softmac_b200._capi import SmxError
     rng = np.random.default_rng(270)
