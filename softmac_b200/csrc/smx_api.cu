@@ -1228,11 +1228,11 @@ int smx_substep_grad_end(smx_sim* s, int32_t f) {
                 constexpr bool R = decltype(rec_c)::value, E = decltype(extra_c)::value;
                 if (tiled) {
                     // persistent CTAs, double-buffered TMA staging of the streaming planes
-                    const int ntiles = nblk(P.n, SMX_TPB), grid = std::min(ntiles, s->sm_count * SMX_P2GG_MINB);
-                    const size_t smem = (size_t)2 * SMX_P2GG_NPL(M, R) * SMX_TPB * sizeof(float4);
+                    const int ntiles = nblk(P.n, SMX_P2GG_TPB), grid = std::min(ntiles, s->sm_count * SMX_P2GG_TILED_MINB);
+                    const size_t smem = (size_t)2 * SMX_P2GG_NPL(M, R) * SMX_P2GG_TPB * sizeof(float4);
                     static bool attr_set = false;
                     if (!attr_set) { cudaFuncSetAttribute(k_p2g_grad_tiled<M, R, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
-                    launch_pdl(s, k_p2g_grad_tiled<M, R, E>, grid, SMX_TPB, smem, P, ps, f, fin, s->adj_cur, s->adj_nxt, gg, cslot, s->action, s->action_grad, rec, ntiles);
+                    launch_pdl(s, k_p2g_grad_tiled<M, R, E>, grid, SMX_P2GG_TPB, smem, P, ps, f, fin, s->adj_cur, s->adj_nxt, gg, cslot, s->action, s->action_grad, rec, ntiles);
                 } else {
                     launch_pdl(s, k_p2g_grad<M, R, E>, nblk(P.n, SMX_TPB), SMX_TPB, 0, P, ps, f, fin, s->adj_cur, s->adj_nxt, gg, cslot, s->action, s->action_grad, rec, s->pf_g);
                 }

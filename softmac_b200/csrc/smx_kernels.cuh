@@ -1220,36 +1220,40 @@ __global__ void __launch_bounds__(SMX_TPB, SMX_P2GG_MINB) k_p2g_grad(Params P, P
                                               reinterpret_cast<const float4*>(ain) + jj, P.stride, gx_part, aout, gg, ctrl_slot, action, action_grad);
 }
 
-// Persistent, software-pipelined variant: every CTA walks tiles of SMX_TPB particle slots; while tile i is being processed the
+#ifndef SMX_P2GG_TPB
+#define SMX_P2GG_TPB 128            // tile of the persistent P2G adjoint (particle slots per CTA trip)
+#endif
+#define SMX_P2GG_TILED_MINB (512 / SMX_P2GG_TPB)
+// Persistent, software-pipelined variant: every CTA walks tiles of SMX_P2GG_TPB particle slots; while tile i is being processed the
 // streaming planes of tile i+1 (frame f: 6, adjoint of F[f+1]: 3, SVD record: 4 -- each a contiguous 2 KB row) are brought into
 // the other half of a double buffer by TMA bulk copies (cp.async.bulk) that complete on an mbarrier, so no warp ever waits for HBM.
 #define SMX_P2GG_NPL(MAT, REC) (((MAT) / 3 == 0 && (MAT) % 3 != 2 && (REC)) ? 13 : 9)
 template <int MAT, bool REC, bool EXTRA>
-__global__ void __launch_bounds__(SMX_TPB, SMX_P2GG_MINB) k_p2g_grad_tiled(Params P, PrimSet ps, int f, const float* __restrict__ fin, const float* __restrict__ ain,
+__global__ void __launch_bounds__(SMX_P2GG_TPB, SMX_P2GG_TILED_MINB) k_p2g_grad_tiled(Params P, PrimSet ps, int f, const float* __restrict__ fin, const float* __restrict__ ain,
                                                             float* __restrict__ aout, const float4* __restrict__ gg, const int* __restrict__ ctrl_slot,
                                                             const float* __restrict__ action, double* __restrict__ action_grad, const float4* __restrict__ rec, int ntiles) {
     pdl_prologue();
     constexpr int NPL = SMX_P2GG_NPL(MAT, REC);
     extern __shared__ __align__(128) float4 smx_dyn_smem[];
     __shared__ uint64_t bar[2];
-    float4* buf = smx_dyn_smem;         // [2][NPL][SMX_TPB]
+    float4* buf = smx_dyn_smem;         // [2][NPL][SMX_P2GG_TPB]
     const int tid = threadIdx.x;
     if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_init_fence(); }
     __syncthreads();
     auto issue = [&](int tile, int stage) {     // one thread: arm the barrier with the byte count, then one bulk copy per plane row
-        const long long base = (long long)tile * SMX_TPB;
-        const uint32_t bytes = (uint32_t)min((long long)SMX_TPB, (long long)P.n - base) * 16u;
-        float4* dst = buf + stage * NPL * SMX_TPB;
+        const long long base = (long long)tile * SMX_P2GG_TPB;
+        const uint32_t bytes = (uint32_t)min((long long)SMX_P2GG_TPB, (long long)P.n - base) * 16u;
+        float4* dst = buf + stage * NPL * SMX_P2GG_TPB;
         mbar_expect_tx(&bar[stage], bytes * NPL);
         const float4* f4 = reinterpret_cast<const float4*>(fin) + base;
         const float4* a4 = reinterpret_cast<const float4*>(ain) + base;
 #pragma unroll
-        for (int p = 0; p < 6; p++) bulk_g2s(dst + p * SMX_TPB, f4 + p * P.stride, bytes, &bar[stage]);
+        for (int p = 0; p < 6; p++) bulk_g2s(dst + p * SMX_P2GG_TPB, f4 + p * P.stride, bytes, &bar[stage]);
 #pragma unroll
-        for (int p = 0; p < 3; p++) bulk_g2s(dst + (6 + p) * SMX_TPB, a4 + (3 + p) * P.stride, bytes, &bar[stage]);
+        for (int p = 0; p < 3; p++) bulk_g2s(dst + (6 + p) * SMX_P2GG_TPB, a4 + (3 + p) * P.stride, bytes, &bar[stage]);
         if (NPL == 13) {
 #pragma unroll
-            for (int p = 0; p < 4; p++) bulk_g2s(dst + (9 + p) * SMX_TPB, rec + base + p * P.stride, bytes, &bar[stage]);
+            for (int p = 0; p < 4; p++) bulk_g2s(dst + (9 + p) * SMX_P2GG_TPB, rec + base + p * P.stride, bytes, &bar[stage]);
         }
     };
     int tile = blockIdx.x;
@@ -1258,13 +1262,13 @@ __global__ void __launch_bounds__(SMX_TPB, SMX_P2GG_MINB) k_p2g_grad_tiled(Param
         const int stage = it & 1;
         // the other stage was released by the __syncthreads that ended the previous trip
         if (tid == 0 && tile + (int)gridDim.x < ntiles) issue(tile + gridDim.x, stage ^ 1);
-        int j = tile * SMX_TPB + tid;
+        int j = tile * SMX_P2GG_TPB + tid;
         bool live = j < P.n;
         int jj = live ? j : P.n - 1;
         const float4 gx_part = reinterpret_cast<const float4*>(aout)[jj];  // partial d x from the G2P / contact adjoints (needed last)
         mbar_wait(&bar[stage], (it >> 1) & 1);
-        const float4* sb = buf + stage * NPL * SMX_TPB + (jj - tile * SMX_TPB);
-        p2g_grad_particle<MAT, REC, EXTRA, true>(P, ps, f, j, jj, live, sb, SMX_TPB, sb + 9 * SMX_TPB, SMX_TPB, sb + 3 * SMX_TPB, SMX_TPB, gx_part, aout, gg,
+        const float4* sb = buf + stage * NPL * SMX_P2GG_TPB + (jj - tile * SMX_P2GG_TPB);
+        p2g_grad_particle<MAT, REC, EXTRA, true>(P, ps, f, j, jj, live, sb, SMX_P2GG_TPB, sb + 9 * SMX_P2GG_TPB, SMX_P2GG_TPB, sb + 3 * SMX_P2GG_TPB, SMX_P2GG_TPB, gx_part, aout, gg,
                                                  ctrl_slot, action, action_grad);
         __syncthreads();
     }
