@@ -157,7 +157,7 @@ __device__ __forceinline__ void warp_stage_flush(WarpStage& st, const uint32_t* 
     const int nl = __popc(alive);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     int p0 = 0;
-#pragma unroll
+#pragma unroll 1     // four trips of eight unrolled slots: the fully unrolled walk (1000 instructions) stalled on instruction fetch
     for (int base = 0; base < 32; base += 8) {
         if (base >= nl) break;
         float4 v[8];
@@ -199,7 +199,7 @@ __device__ __forceinline__ void warp_stage_flush3(WarpStage3& st, const uint32_t
     float2 acc = make_float2(0.f, 0.f);
     float az = 0.f;
     int p0 = 0;
-#pragma unroll
+#pragma unroll 1     // four trips of eight unrolled slots: the fully unrolled walk (1000 instructions) stalled on instruction fetch
     for (int base = 0; base < 32; base += 8) {
         if (base >= nl) break;
         float2 v[8]; float z[8];
