@@ -415,6 +415,36 @@ def test_properties_at_full_size():
     assert rel_l2(2.0 * grads[0], grads[1]) <= 1e-5
 
 
+def test_properties_at_the_largest_baseline_size():
+    """BASELINE config 5 sizes (8M particles, 256^3) in one handle: sort contract, mass conservation, free-fall momentum and the
+    linearity of the adjoint, i.e. the same size-independent properties as at 1M."""
+    from softmac_b200.engine import MPMSimulator
+    from harness import sim_cfg
+    n = 8_000_000
+    cfg = sim_cfg(n, n_grid=256, max_steps=5, ground_friction=20., dt=5e-5)
+    sim = MPMSimulator(cfg, env_dt=2.5e-4)
+    st = scenes.cube_state(n)
+    sim.reset(st)
+    keys = sim.sort_keys(0)
+    assert np.all(np.diff(keys.astype(np.int64)) >= 0)
+    sim.step(0, 3)
+    g_in, g_out = sim.get_grid()
+    p_mass = (1 / 256 * 0.5) ** 2
+    assert abs(g_in[:, 3].astype(np.float64).sum() / (n * p_mass) - 1) < 1e-5
+    v3 = sim.get_v(3)
+    assert np.allclose(v3.mean(0), [0, -9.8 * 3 * 5e-5, 0], atol=2e-7)          # three substeps of free fall
+    g = np.ascontiguousarray(st[:, :3] - st[:, :3].mean(0))
+    grads = []
+    for scale in (1.0, -0.5):
+        sim.clear_all_gradients()
+        sim.add_x_grad(3, scale * g)
+        sim.step_grad(3, 3)
+        grads.append(sim.get_grad(0))
+    assert np.abs(grads[0][0]).max() > 0 and np.all(np.isfinite(grads[0][1]))
+    assert rel_l2(-0.5 * grads[0][0], grads[1][0]) <= 1e-5 and rel_l2(-0.5 * grads[0][1], grads[1][1]) <= 1e-5
+    assert sim.counters()["clamped"] == 0 and sim.counters()["left_active_region"] == 0
+
+
 def test_velocity_control_forward_kinematics_and_action_grad():
     """rigid_velocity_control: Primitive.set_action writes v, w of `substeps` frames, forward_kinematics integrates the pose
     inside every substep (mpm_simulator.py:329-331, primitive_base.py:280-304) and get_action_grad collects the adjoint."""
