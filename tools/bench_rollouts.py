@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--env-steps", type=int, default=40)
     ap.add_argument("--substeps", type=int, default=5)
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--sort-every", type=int, default=None, help="re-bin + re-sort period in substeps (default: the simulator's max(substeps, 4))")
     args = ap.parse_args()
     import torch
     import scenes
@@ -53,7 +54,7 @@ def main():
     ms = [Mesh(sdf=dict(sdf=tab["sdf"], normal=tab["normal"], position=(tab["lower"], tab["upper"]), dx=tab["dx"]), cfg=dict(friction=0.3), max_timesteps=max_steps)
           for _ in range(2)]
     prims = Primitives(primitives=ms, max_timesteps=max_steps)
-    sim = MPMSimulator(sim_cfg(n, n_grid=n_grid, max_steps=max_steps, dt=dt), prims, env_dt=dt * S, n_batch=B, device=local)
+    sim = MPMSimulator(sim_cfg(n, n_grid=n_grid, max_steps=max_steps, dt=dt), prims, env_dt=dt * S, n_batch=B, device=local, sort_every=args.sort_every)
     bodies = [dict(joint="prismatic", axis=(1, 0, 0), origin=(0.5 - 0.138, 0.12, 0.5), mass=1.0, gravity=False),
               dict(joint="prismatic", axis=(1, 0, 0), origin=(0.5 + 0.138, 0.12, 0.5), mass=1.0, gravity=False)]
     rcfg = CfgNode(gravity=(0., 0., 0.), init_state=(0., 0., 0.3, -0.3), bodies=bodies)
