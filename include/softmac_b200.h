@@ -148,6 +148,40 @@ int smx_get_primitive_state_grads_all(smx_sim* sim, int32_t f0, int32_t f1, doub
 int smx_set_primitive_action(smx_sim* sim, int32_t id, int32_t s, int32_t n, const double* a6);
 int smx_get_primitive_action_grad(smx_sim* sim, int32_t id, int32_t s, int32_t n, double* out6);
 
+/* Device-resident rigid coupling for articulated bodies whose joints are all fixed or prismatic (the gripper of demo_grip).
+ * Replaces, for that case, the per-env-step host round trip of RigidSimulator.step / set_ext_state / step_grad /
+ * get_ext_state_grad (softmac/engine/rigid_simulator.py:85-220): the bridge reads primitive.ext_f / substeps in float32
+ * (:92-93), ignores wrenches below 1e-10 or of primitives with enable_external_force == False (:96), advances the bodies, and
+ * writes pose + twist into the next `substeps` primitive frames in float32 (:185, :200-201); backwards it sums
+ * get_all_states_grad over those frames (:207-216), emits the action gradient and set_ext_f_grad(. / substeps) (:166-168).
+ * With affine body dynamics  s' = s As + a Aa + w Aw + c,  pose_i = pose0_i + s' M_i  all of that is one small kernel per env
+ * step on the simulator's stream: no synchronisation inside an episode.  All matrices row-major f64:
+ * As (state_dim, state_dim), Aa (action_dim, state_dim), Aw (6 * n_primitives, state_dim), c (state_dim),
+ * M (n_primitives, state_dim, 13), pose0 (n_primitives, 13), enable (n_primitives), init_state (state_dim). */
+typedef struct {
+    int32_t state_dim, action_dim;
+    int32_t max_env_steps;        /* env steps kept (states, actions, action gradients, wrench masks) */
+    int32_t fp32_bridge;          /* truncate the wrench to float32 as the Jade bridge does (rigid_simulator.py:92) */
+    double ext_grad_scale;        /* RigidSimulator.ext_grad_scale (rigid_simulator.py:148) */
+    const double *As, *Aa, *Aw, *c, *M, *pose0, *init_state;
+    const int32_t* enable;
+} smx_rigid_linear;
+int smx_rigid_linear_create(smx_sim* sim, const smx_rigid_linear* desc);
+/* RigidSimulator.reset: every rollout back to init_state, poses of frames [0, substeps) written, wrench cleared */
+int smx_rigid_linear_reset(smx_sim* sim);
+/* actions of env step k for every rollout, [n_batch][action_dim] */
+int smx_rigid_linear_set_actions(smx_sim* sim, int32_t k, const double* actions);
+/* RigidSimulator.step(k) after the substeps of env step k; RigidSimulator.step_grad(k) before their adjoints */
+int smx_rigid_linear_step(smx_sim* sim, int32_t k);
+int smx_rigid_linear_step_grad(smx_sim* sim, int32_t k);
+/* state_grad += get_ext_state_grad(0) at the end of TaichiEnv.backward (taichi_env.py:149-150) */
+int smx_rigid_linear_finish(smx_sim* sim);
+/* read-out (blocking): rigid state after k env steps [n_batch][state_dim]; action gradients of env steps [k0, k1)
+ * [k1 - k0][n_batch][action_dim]; adjoint of the initial rigid state [n_batch][state_dim] */
+int smx_rigid_linear_get_states(smx_sim* sim, int32_t k, double* out);
+int smx_rigid_linear_get_action_grads(smx_sim* sim, int32_t k0, int32_t k1, double* out);
+int smx_rigid_linear_get_state_grad(smx_sim* sim, double* out);
+
 /* particle-force control ("mpm" control mode) --------------------------------------------------- */
 /* MPMSimulator.set_action(action (n_control,3)); also zeroes action.grad (mpm_simulator.py:579-592).
  * With n_batch > 1 the array is (n_batch * n_control, 3), batch-major (likewise smx_get_action_grad). */

@@ -33,6 +33,17 @@ class SmxConfig(C.Structure):
     ]
 
 
+class SmxRigidLinear(C.Structure):
+    """smx_rigid_linear of include/softmac_b200.h."""
+    _fields_ = [
+        ("state_dim", C.c_int32), ("action_dim", C.c_int32), ("max_env_steps", C.c_int32), ("fp32_bridge", C.c_int32),
+        ("ext_grad_scale", C.c_double),
+        ("As", C.POINTER(C.c_double)), ("Aa", C.POINTER(C.c_double)), ("Aw", C.POINTER(C.c_double)), ("c", C.POINTER(C.c_double)),
+        ("M", C.POINTER(C.c_double)), ("pose0", C.POINTER(C.c_double)), ("init_state", C.POINTER(C.c_double)),
+        ("enable", C.POINTER(C.c_int32)),
+    ]
+
+
 class SmxError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"libsoftmac_b200 error {code}: {msg}")
@@ -83,6 +94,15 @@ _SIGS = {
     "smx_get_primitive_state_grads_all": [vp, C.c_int32, C.c_int32, dp],
     "smx_set_primitive_action": [vp, C.c_int32, C.c_int32, C.c_int32, dp],
     "smx_get_primitive_action_grad": [vp, C.c_int32, C.c_int32, C.c_int32, dp],
+    "smx_rigid_linear_create": [vp, vp],
+    "smx_rigid_linear_reset": [vp],
+    "smx_rigid_linear_set_actions": [vp, C.c_int32, dp],
+    "smx_rigid_linear_step": [vp, C.c_int32],
+    "smx_rigid_linear_step_grad": [vp, C.c_int32],
+    "smx_rigid_linear_finish": [vp],
+    "smx_rigid_linear_get_states": [vp, C.c_int32, dp],
+    "smx_rigid_linear_get_action_grads": [vp, C.c_int32, C.c_int32, dp],
+    "smx_rigid_linear_get_state_grad": [vp, dp],
     "smx_set_action": [vp, dp],
     "smx_set_control_idx": [vp, ip],
     "smx_get_action_grad": [vp, dp],

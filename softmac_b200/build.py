@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib", "libsoftmac_b200.so")
 SOURCES = [os.path.join(CSRC, "smx_api.cu")]
-HEADERS = [os.path.join(CSRC, h) for h in ("smx_math.cuh", "smx_contact.cuh", "smx_kernels.cuh")] + \
+HEADERS = [os.path.join(CSRC, h) for h in ("smx_math.cuh", "smx_contact.cuh", "smx_kernels.cuh", "smx_sdf.cuh", "smx_rigid.cuh")] + \
           [os.path.join(os.path.dirname(HERE), "include", "softmac_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--use_fast_math=false",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-g", "-Xcompiler", "-fopenmp", "-shared", "--extended-lambda", "-Xptxas", "-v"]

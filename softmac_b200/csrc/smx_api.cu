@@ -18,6 +18,7 @@
 #include "../../include/softmac_b200.h"
 #include "smx_kernels.cuh"
 #include "smx_sdf.cuh"
+#include "smx_rigid.cuh"
 
 #include <execinfo.h>
 #include <signal.h>
@@ -151,6 +152,9 @@ struct smx_sim {
     PrimDev* prims_dev = nullptr;
     float* pstate = nullptr; double* pgrad = nullptr; double* ext_f = nullptr; float* ext_f_grad = nullptr;
     float* abuf = nullptr; double* gabuf = nullptr;     // velocity-control action buffers [np][T][6]
+    // device-resident affine rigid coupling (smx_rigid_linear_*): one f64 arena holding the matrices and the per-env-step series
+    bool rig_on = false; RigidLin rig = {}; double* rig_arena = nullptr; int* rig_enable = nullptr; unsigned char* rig_masks = nullptr;
+    std::vector<double> rig_init;
     // control
     int* ctrl_id = nullptr; int ctrl_version = 0; float* action = nullptr; double* action_grad = nullptr;
     // staging / sort scratch
@@ -692,7 +696,8 @@ int smx_destroy(smx_sim* s) {
     for (auto& kv : s->seed_pool) cudaFree(kv.second);
     for (auto& p : s->prims) { cudaFree(p.sdf_dev); cudaFree(p.nrm_dev); }
     void* ptrs[] = {s->near_pool, s->svd_pool, s->ch_target, s->ch_loss, s->ckpt, s->pool, s->g_in, s->g_out, s->g_mix, s->gg_out, s->gg_out_b, s->gg_mix, s->g_lin, s->adj_cur, s->adj_nxt, s->stage_dev, s->keys_a, s->keys_b, s->iota, s->cub_tmp,
-                    s->counters, s->prims_dev, s->pstate, s->pgrad, s->ext_f, s->ext_f_grad, s->abuf, s->gabuf, s->ctrl_id, s->action, s->action_grad};
+                    s->counters, s->prims_dev, s->pstate, s->pgrad, s->ext_f, s->ext_f_grad, s->abuf, s->gabuf, s->ctrl_id, s->action, s->action_grad,
+                    s->rig_arena, s->rig_enable, s->rig_masks};
     for (void* p : ptrs) cudaFree(p);
     cudaFreeHost(s->stage_host);
     if (s->ev0) cudaEventDestroy(s->ev0);
@@ -1058,6 +1063,125 @@ int smx_get_action_grad(smx_sim* s, double* out) {
     if (s->cfg.n_control <= 0) return fail(SMX_ERR_STATE, "smx_get_action_grad: simulator was created with n_control == 0");
     CK(cudaSetDevice(s->cfg.device));
     CK(cudaMemcpyAsync(out, s->action_grad, (size_t)s->B * s->cfg.n_control * 3 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return SMX_OK;
+}
+
+// ---- device-resident rigid coupling (fixed / prismatic joints): RigidSimulator.step / step_grad on the simulator's stream ------------
+int smx_rigid_linear_create(smx_sim* s, const smx_rigid_linear* d) {
+    if (!s || !d) return fail(SMX_ERR_ARG, "smx_rigid_linear_create: null argument");
+    const int np = (int)s->prims.size(), sd = d->state_dim, ad = d->action_dim, K = d->max_env_steps, B = s->B;
+    if (np == 0) return fail(SMX_ERR_STATE, "smx_rigid_linear_create: the simulator has no primitives");
+    if (sd < 1 || sd > SMX_RIG_MAXS || ad < 0 || ad > SMX_RIG_MAXA || K < 1) return fail(SMX_ERR_RANGE, "smx_rigid_linear_create: state_dim in [1, %d], action_dim in [0, %d], max_env_steps >= 1", SMX_RIG_MAXS, SMX_RIG_MAXA);
+    if (!d->As || !d->Aw || !d->c || !d->M || !d->pose0 || !d->enable || !d->init_state || (ad > 0 && !d->Aa)) return fail(SMX_ERR_ARG, "smx_rigid_linear_create: null matrix");
+    if (s->cfg.rigid_velocity_control) return fail(SMX_ERR_STATE, "smx_rigid_linear_create: not available with rigid velocity control");
+    CK(cudaSetDevice(s->cfg.device));
+    CK(cudaStreamSynchronize(s->stream));
+    cudaFree(s->rig_arena); cudaFree(s->rig_enable); cudaFree(s->rig_masks); s->rig_arena = nullptr; s->rig_enable = nullptr; s->rig_masks = nullptr; s->rig_on = false;
+    const size_t nAs = (size_t)sd * sd, nAa = (size_t)ad * sd, nAw = (size_t)6 * np * sd, nc = sd, nM = (size_t)np * sd * 13, np0 = (size_t)np * 13;
+    const size_t nst = (size_t)(K + 1) * B * sd, nact = (size_t)K * B * std::max(ad, 1), nsg = (size_t)B * sd;
+    const size_t consts = nAs + nAa + nAw + nc + nM + np0, total = consts + nst + 2 * nact + nsg;
+    CK(cudaMalloc(&s->rig_arena, total * sizeof(double)));
+    CK(cudaMalloc(&s->rig_enable, np * sizeof(int)));
+    CK(cudaMalloc(&s->rig_masks, (size_t)K * B * np));
+    std::vector<double> h(consts);
+    size_t o = 0;
+    auto put = [&](const double* src, size_t n) { if (n) memcpy(h.data() + o, src, n * sizeof(double)); size_t at = o; o += n; return at; };
+    const size_t oAs = put(d->As, nAs), oAa = put(d->Aa, nAa), oAw = put(d->Aw, nAw), oc = put(d->c, nc), oM = put(d->M, nM), op0 = put(d->pose0, np0);
+    CK(cudaMemcpy(s->rig_arena, h.data(), consts * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemset(s->rig_arena + consts, 0, (total - consts) * sizeof(double)));
+    std::vector<int> en(np); for (int i = 0; i < np; i++) en[i] = d->enable[i] ? 1 : 0;
+    CK(cudaMemcpy(s->rig_enable, en.data(), np * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemset(s->rig_masks, 0, (size_t)K * B * np));
+    RigidLin& R = s->rig;
+    R.sd = sd; R.ad = ad; R.np = np; R.B = B; R.S = std::max(s->cfg.substeps, 1); R.T = s->cfg.max_steps; R.K = K; R.fp32 = d->fp32_bridge ? 1 : 0;
+    R.scale = d->ext_grad_scale;
+    double* a = s->rig_arena;
+    R.As = a + oAs; R.Aa = a + oAa; R.Aw = a + oAw; R.c = a + oc; R.M = a + oM; R.pose0 = a + op0; R.enable = s->rig_enable;
+    R.states = a + consts; R.actions = R.states + nst; R.action_grad = R.actions + nact; R.state_grad = R.action_grad + nact; R.masks = s->rig_masks;
+    s->rig_init.assign(d->init_state, d->init_state + sd);
+    s->rig_on = true;
+    return SMX_OK;
+}
+static int rig_check(smx_sim* s, int k, const char* what) {
+    if (!s) return fail(SMX_ERR_ARG, "%s: null simulator", what);
+    if (!s->rig_on) return fail(SMX_ERR_STATE, "%s: smx_rigid_linear_create has not been called", what);
+    if (k < 0 || k >= s->rig.K) return fail(SMX_ERR_RANGE, "%s: env step %d outside [0, %d)", what, k, s->rig.K);
+    return SMX_OK;
+}
+// RigidSimulator.reset (rigid_simulator.py:360-369): state 0 = init_state for every rollout, poses of frames [0, substeps), wrench and adjoints cleared
+int smx_rigid_linear_reset(smx_sim* s) {
+    TRY(rig_check(s, 0, "smx_rigid_linear_reset"));
+    CK(cudaSetDevice(s->cfg.device));
+    RigidLin& R = s->rig;
+    std::vector<double> h((size_t)R.B * R.sd);
+    for (int b = 0; b < R.B; b++) for (int i = 0; i < R.sd; i++) h[(size_t)b * R.sd + i] = s->rig_init[i];
+    CK(cudaMemcpyAsync(R.states, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    CK(cudaMemsetAsync(R.state_grad, 0, (size_t)R.B * R.sd * sizeof(double), s->stream));
+    CK(cudaMemsetAsync(R.action_grad, 0, (size_t)R.K * R.B * std::max(R.ad, 1) * sizeof(double), s->stream));
+    const int f1 = std::min(R.S, s->cfg.max_steps);
+    for (int f = 0; f < f1; f++) s->near_order[f] = -1;
+    k_rigid_linear_step<<<R.B, 128, 0, s->stream>>>(R, 0, 0, 0, f1, s->ext_f, s->ext_f_grad, s->pstate); CKLN(s, "rigid");
+    return SMX_OK;
+}
+int smx_rigid_linear_set_actions(smx_sim* s, int32_t k, const double* actions) {
+    TRY(rig_check(s, k, "smx_rigid_linear_set_actions"));
+    if (s->rig.ad == 0) return SMX_OK;
+    if (!actions) return fail(SMX_ERR_ARG, "smx_rigid_linear_set_actions: null input");
+    CK(cudaSetDevice(s->cfg.device));
+    // pageable source: staged by the runtime before the call returns, no stream synchronisation
+    CK(cudaMemcpyAsync(s->rig.actions + (size_t)k * s->B * s->rig.ad, actions, (size_t)s->B * s->rig.ad * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    return SMX_OK;
+}
+int smx_rigid_linear_step(smx_sim* s, int32_t k) {
+    TRY(rig_check(s, k, "smx_rigid_linear_step"));
+    CK(cudaSetDevice(s->cfg.device));
+    RigidLin& R = s->rig;
+    const int f0 = std::min((k + 1) * R.S, s->cfg.max_steps), f1 = std::min((k + 2) * R.S, s->cfg.max_steps);
+    for (int f = f0; f < f1; f++) s->near_order[f] = -1;
+    k_rigid_linear_step<<<R.B, 128, 0, s->stream>>>(R, k, 1, f0, f1, s->ext_f, s->ext_f_grad, s->pstate); CKLN(s, "rigid");
+    return SMX_OK;
+}
+int smx_rigid_linear_step_grad(smx_sim* s, int32_t k) {
+    TRY(rig_check(s, k, "smx_rigid_linear_step_grad"));
+    CK(cudaSetDevice(s->cfg.device));
+    RigidLin& R = s->rig;
+    const int f0 = std::min((k + 1) * R.S, s->cfg.max_steps), f1 = std::min((k + 2) * R.S, s->cfg.max_steps);
+    k_rigid_linear_step_grad<<<R.B, 128, 0, s->stream>>>(R, k, 0, f0, f1, s->pgrad, s->ext_f_grad); CKLN(s, "rigid_grad");
+    return SMX_OK;
+}
+int smx_rigid_linear_finish(smx_sim* s) {
+    TRY(rig_check(s, 0, "smx_rigid_linear_finish"));
+    CK(cudaSetDevice(s->cfg.device));
+    RigidLin& R = s->rig;
+    k_rigid_linear_step_grad<<<R.B, 128, 0, s->stream>>>(R, 0, 1, 0, std::min(R.S, s->cfg.max_steps), s->pgrad, s->ext_f_grad); CKLN(s, "rigid_grad");
+    return SMX_OK;
+}
+int smx_rigid_linear_get_states(smx_sim* s, int32_t k, double* out) {
+    if (!s || !s->rig_on) return fail(SMX_ERR_STATE, "smx_rigid_linear_get_states: smx_rigid_linear_create has not been called");
+    if (!out) return fail(SMX_ERR_ARG, "smx_rigid_linear_get_states: null output");
+    if (k < 0 || k > s->rig.K) return fail(SMX_ERR_RANGE, "smx_rigid_linear_get_states: state index %d outside [0, %d]", k, s->rig.K);
+    CK(cudaSetDevice(s->cfg.device));
+    CK(cudaMemcpyAsync(out, s->rig.states + (size_t)k * s->B * s->rig.sd, (size_t)s->B * s->rig.sd * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return SMX_OK;
+}
+int smx_rigid_linear_get_action_grads(smx_sim* s, int32_t k0, int32_t k1, double* out) {
+    if (!s || !s->rig_on) return fail(SMX_ERR_STATE, "smx_rigid_linear_get_action_grads: smx_rigid_linear_create has not been called");
+    if (!out) return fail(SMX_ERR_ARG, "smx_rigid_linear_get_action_grads: null output");
+    if (k0 < 0 || k1 > s->rig.K || k0 >= k1) return fail(SMX_ERR_RANGE, "smx_rigid_linear_get_action_grads: env steps [%d, %d) outside [0, %d)", k0, k1, s->rig.K);
+    if (s->rig.ad == 0) return SMX_OK;
+    CK(cudaSetDevice(s->cfg.device));
+    const size_t row = (size_t)s->B * s->rig.ad;
+    CK(cudaMemcpyAsync(out, s->rig.action_grad + k0 * row, (k1 - k0) * row * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return SMX_OK;
+}
+int smx_rigid_linear_get_state_grad(smx_sim* s, double* out) {
+    if (!s || !s->rig_on) return fail(SMX_ERR_STATE, "smx_rigid_linear_get_state_grad: smx_rigid_linear_create has not been called");
+    if (!out) return fail(SMX_ERR_ARG, "smx_rigid_linear_get_state_grad: null output");
+    CK(cudaSetDevice(s->cfg.device));
+    CK(cudaMemcpyAsync(out, s->rig.state_grad, (size_t)s->B * s->rig.sd * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
     return SMX_OK;
 }

@@ -9,7 +9,9 @@ rollouts and primitives (``smx_*_all``) instead of B x P small ones.  Every roll
 """
 import numpy as np
 
-from .._capi import lib, check, d_ptr
+import ctypes as C
+
+from .._capi import lib, check, d_ptr, as_d, SmxRigidLinear
 
 
 class _ExtF:
@@ -164,11 +166,64 @@ class LinearBatchedRigid:
         self.state_grad = self.state_grad + np.einsum("bpk,psk->bs", pose_grads0, self.M)
 
 
+class DeviceLinearRigid:
+    """LinearBatchedRigid moved onto the GPU (smx_rigid_linear_*, softmac_b200/csrc/smx_rigid.cuh): the same constant matrices,
+    one small kernel per env step on the simulator's stream, so an episode runs without a single host <-> device round trip
+    of the coupling (wrench, poses, state adjoints and wrench adjoints never leave the device; rigid_simulator.py:85-220)."""
+
+    def __init__(self, vec, sim, max_env_steps):
+        self.vec, self.sim, self.h, self.K = vec, sim, sim._h, int(max_env_steps)
+        self.B, self.sd, self.ad, self.P = vec.B, vec.sd, vec.ad, vec.P
+        keep = [as_d(vec.As), as_d(vec.Aa), as_d(vec.Aw), as_d(vec.c), as_d(vec.M), as_d(vec.pose0), as_d(vec.p.init_state),
+                np.ascontiguousarray(vec.enable, dtype=np.int32)]
+        d = SmxRigidLinear()
+        d.state_dim, d.action_dim, d.max_env_steps, d.fp32_bridge = self.sd, self.ad, self.K, int(bool(vec.fp32))
+        d.ext_grad_scale = float(vec.p.ext_grad_scale)
+        d.As, d.Aa, d.Aw, d.c, d.M, d.pose0, d.init_state = [d_ptr(a) for a in keep[:7]]
+        d.enable = keep[7].ctypes.data_as(C.POINTER(C.c_int32))
+        check(lib().smx_rigid_linear_create(self.h, C.byref(d)))
+
+    def reset(self):
+        check(lib().smx_rigid_linear_reset(self.h))
+
+    def step(self, k, actions):
+        if self.ad:
+            a = np.zeros((self.B, self.ad)) if actions is None else as_d(actions, (self.B, self.ad))
+            check(lib().smx_rigid_linear_set_actions(self.h, int(k), d_ptr(a)))
+        check(lib().smx_rigid_linear_step(self.h, int(k)))
+
+    def step_grad(self, k):
+        check(lib().smx_rigid_linear_step_grad(self.h, int(k)))
+
+    def finish(self):
+        check(lib().smx_rigid_linear_finish(self.h))
+
+    def action_grads(self, k0, k1):
+        """(B, k1 - k0, action_dim)"""
+        out = np.zeros((k1 - k0, self.B, self.ad))
+        if self.ad and k1 > k0:
+            check(lib().smx_rigid_linear_get_action_grads(self.h, int(k0), int(k1), d_ptr(out)))
+        return np.ascontiguousarray(out.transpose(1, 0, 2))
+
+    def states(self, k):
+        out = np.zeros((self.B, self.sd))
+        check(lib().smx_rigid_linear_get_states(self.h, int(k), d_ptr(out)))
+        return out
+
+    @property
+    def state_grad(self):
+        out = np.zeros((self.B, self.sd))
+        check(lib().smx_rigid_linear_get_state_grad(self.h, d_ptr(out)))
+        return out
+
+
 class BatchedTaichiEnv:
-    def __init__(self, simulator, primitives, make_rigid, init_particles, loss=None, vectorize=True):
+    def __init__(self, simulator, primitives, make_rigid, init_particles, loss=None, vectorize=True, device_rigid=False):
         """make_rigid(b, views) -> a rigid simulator (RigidSimulator surface) for rollout b talking to `views`.
         vectorize: when every joint of the stand-in is fixed / prismatic, advance all rollouts with LinearBatchedRigid
-        (numpy matmuls) instead of B Python bridges."""
+        (numpy matmuls) instead of B Python bridges.
+        device_rigid: run that affine bridge on the GPU (DeviceLinearRigid): no host round trip per env step; ``step_grad``
+        then returns None and ``backward`` reads all action gradients once at the end."""
         self.simulator, self.primitives, self.loss = simulator, primitives, loss
         self.B, self.substeps = simulator.n_batch, simulator.substeps
         self.buf = CouplingBuffer(simulator, primitives)
@@ -180,6 +235,11 @@ class BatchedTaichiEnv:
             self.rigid += [make_rigid(b, self.buf.views[b]) for b in range(1, self.B)]
         self.init_particles = np.asarray(init_particles, dtype=np.float64)
         self.action_list = []
+        self.dev = None
+        if device_rigid:
+            if not self.vec:
+                raise ValueError("device_rigid needs a stand-in whose joints are all fixed or prismatic")
+            self.dev = DeviceLinearRigid(self.vec, simulator, max(simulator.max_steps // max(self.substeps, 1), 1))
         primitives.initialize()
         simulator.initialize()
         self.reset()
@@ -187,7 +247,9 @@ class BatchedTaichiEnv:
     def reset(self):
         self.primitives.reset()
         self.simulator.reset(self.init_particles)
-        if self.vec:
+        if self.dev:
+            self.dev.reset()
+        elif self.vec:
             self.vec.reset()
             self._push_poses(self.vec.poses(), 0, self.substeps)
         else:
@@ -204,8 +266,11 @@ class BatchedTaichiEnv:
         sim.cur = start + self.substeps
         self.action_list.append(np.asarray(actions, dtype=np.float64))
         sim.step(start, self.substeps)
-        self.buf.pull_ext_f()
         k = start // self.substeps
+        if self.dev:
+            self.dev.step(k, actions)
+            return
+        self.buf.pull_ext_f()
         if self.vec:
             self._push_poses(self.vec.step(actions, self.buf.ext_f), (k + 1) * self.substeps, (k + 2) * self.substeps)
             return
@@ -224,6 +289,10 @@ class BatchedTaichiEnv:
         start = sim.cur
         sim.cur = start - self.substeps
         k = sim.cur // self.substeps
+        if self.dev:
+            self.dev.step_grad(k)
+            sim.step_grad(start, self.substeps)
+            return None
         # rigid.step_grad(k) pulls the primitive-state adjoints of env step k+1 (frames [(k+1) sub, (k+2) sub))
         self.buf.pull_state_grads((k + 1) * self.substeps, (k + 2) * self.substeps)
         if self.vec:
@@ -248,6 +317,11 @@ class BatchedTaichiEnv:
         for r in self.rigid:
             r.state_grad = np.zeros(r.state_dim)
         total = self.simulator.cur // self.substeps
+        if self.dev:
+            for s in range(total - 1, -1, -1):
+                self.step_grad(self.action_list[s])
+            self.dev.finish()
+            return self.dev.action_grads(0, total)
         out = []
         for s in range(total - 1, -1, -1):
             out = [self.step_grad(self.action_list[s])] + out
@@ -261,4 +335,6 @@ class BatchedTaichiEnv:
 
     def rigid_states(self):
         """(B, state_dim) current rigid states."""
+        if self.dev:
+            return self.dev.states(len(self.action_list))
         return self.vec.states[-1].copy() if self.vec else np.stack([r.states[-1] for r in self.rigid])

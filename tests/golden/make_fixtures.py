@@ -115,3 +115,16 @@ def reference_sdf_tables():
 
 if __name__ == "__main__" and "--sdf" in sys.argv:
     reference_sdf_tables()
+
+
+def demo_targets():
+    """tests/golden/demo_targets.npz: the Chamfer target point sets of demo_grip / demo_pour (cfg.ENV.loss.target_path,
+    demo_grip_config.py / demo_pour_config.py), copied as data in fp32 -- inputs of tools/bench_demo.py (BASELINE configs 1, 2)."""
+    grip = np.load(os.path.join(REF, "envs/grip/grip_mpm_target_position.npy")).astype(np.float32)
+    pour = np.load(os.path.join(REF, "envs/pour/pour_mpm_target_position_corotated.npy")).astype(np.float32)
+    np.savez_compressed(os.path.join(HERE, "demo_targets.npz"), grip=grip, pour=pour)
+    print("demo_targets.npz", grip.shape, pour.shape)
+
+
+if __name__ == "__main__" and "--targets" in sys.argv:
+    demo_targets()

@@ -143,6 +143,58 @@ def test_batched_env_matches_single_rollout_envs():
         assert np.abs(g1).max() > 0 and rel_l2(gb[b], g1) <= 1e-3, (gb[b], g1)
 
 
+def test_device_resident_rigid_coupling_matches_host_bridge():
+    """smx_rigid_linear_* (the affine rigid bridge on the GPU, no host round trip per env step) == LinearBatchedRigid on the host:
+    same particle states, rigid states, action gradients and adjoint of the initial rigid state; one rollout's fingers carry a
+    primitive whose wrench is ignored (enable_external_force = False, rigid_simulator.py:96)."""
+    from softmac_b200.engine import MPMSimulator, Primitives, Mesh
+    from softmac_b200.engine.batched_env import BatchedTaichiEnv
+    from softmac_b200.engine.rigid_simulator import RigidSimulator
+    from softmac_b200.config import CfgNode
+    n, B, env_steps, substeps = 2000, 3, 5, 5
+    n_grid, dt = 32, 2e-4
+    max_steps = env_steps * substeps + substeps + 2
+    rng = np.random.default_rng(6)
+    x = ((rng.random((n, 3)) * 2 - 1) * 0.05 + np.array([0.5, 0.3, 0.5])).astype(np.float32).astype(np.float64)
+    tab = scenes.sphere_table(radius=0.06, dx=0.01, margin=0.04)
+    bodies = [dict(joint="prismatic", axis=(1, 0, 0), origin=(0.5 - 0.108, 0.3, 0.5), mass=1.0, gravity=False),
+              dict(joint="prismatic", axis=(1, 0, 0), origin=(0.5 + 0.108, 0.3, 0.5), mass=1.5, gravity=False),
+              dict(joint="fixed", origin=(0.5, 0.3 + 0.105, 0.5))]
+    rcfg = CfgNode(gravity=(0., 0., 0.), init_state=(0., 0., 0.4, -0.4), bodies=bodies)
+    target = x + np.array([0.0, 0.01, 0.0])
+    actions = np.stack([np.tile([40.0, -40.0], (env_steps, 1)), np.tile([10.0, -70.0], (env_steps, 1)), np.tile([0.0, 0.0], (env_steps, 1))])
+
+    def run(device_rigid):
+        ms = [Mesh(sdf=dict(sdf=tab["sdf"], normal=tab["normal"], position=(tab["lower"], tab["upper"]), dx=tab["dx"]),
+                   cfg=dict(friction=0.3, enable_external_force=(i != 2)), max_timesteps=max_steps) for i in range(3)]
+        prims = Primitives(primitives=ms, max_timesteps=max_steps)
+        sim = MPMSimulator(sim_cfg(n, n_grid=n_grid, max_steps=max_steps, dt=dt), prims, env_dt=dt * substeps, n_batch=B)
+        env = BatchedTaichiEnv(sim, prims, lambda b, views: RigidSimulator(rcfg, views, substeps=substeps, env_dt=dt * substeps), x,
+                               device_rigid=device_rigid)
+        out = []
+        for it in range(2):                                                 # the second episode checks reset()
+            env.reset()
+            sim.clear_all_gradients()
+            for k in range(env_steps):
+                env.step(actions[:, k])
+            f_end = env_steps * substeps
+            xs = sim.get_x(f_end).reshape(B, n, 3)
+            sim.add_x_grad(f_end, (xs - target).reshape(B * n, 3))
+            g = env.backward()
+            sg = env.dev.state_grad if env.dev else env.vec.state_grad
+            out.append((xs, g, env.rigid_states(), np.array(sg)))
+        assert rel_l2(out[0][1], out[1][1]) <= 1e-4                       # episodes differ only by the order of the float atomics
+        return out[1]
+
+    xh, gh, rh, sh = run(False)
+    xd, gd, rd, sd = run(True)
+    assert gh.shape == gd.shape == (B, env_steps, 2) and np.abs(gh[:2]).max() > 0
+    assert rel_l2(xd, xh) <= 1e-6
+    assert rel_l2(rd, rh) <= 1e-7
+    assert rel_l2(gd, gh) <= 1e-4, (gd, gh)
+    assert rel_l2(sd, sh) <= 1e-4, (sd, sh)
+
+
 def test_device_chamfer_loss_matches_host_restatement():
     """smx_chamfer_loss vs the numpy restatement of loss_grip.py:45-68 (value and seed), single and batched handles."""
     from softmac_b200.engine import MPMSimulator

@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""BASELINE configs 1 and 2 as SURVEY.md section 8(d) defines them: the demo_grip and demo_pour episodes, forward + backward.
+
+  python tools/bench_demo.py --config grip [--env-steps 400] [--batch 1] [--reps 2] [--parity-env-steps 80]
+  python tools/bench_demo.py --config pour [--env-steps 3000] [--parity-env-steps 200]
+
+grip (softmac/config/demo_grip_config.py:9-55, demo_grip.py:117-150): the reference's own initial state (10 000 particles of
+    plasticine at rest, 64^3 grid, dt 2e-4, 5 substeps per env step), the three primitives of gripper.urdf (SDF tables built
+    on the GPU from the OBJs; contact disabled on the palm), actions 0.3 * [1, -1], 400 env steps = 2000 substeps, Chamfer
+    loss against the reference's target point set at frames 1500 .. 2000 step 20 (26 frames).
+pour (demo_pour_config.py:9-67, demo_pour.py:141-187): the reference's initial state (5 000 liquid particles at rest in the
+    glass, + (0, 0.04, 0)), dt = env_dt = 1e-3 (ONE substep per env step: the rigid coupling runs after every substep),
+    E 22, free-slip floor, glass (friction 0.1, feels the wrench) + bowl (friction 1, wrench ignored), 3000 env steps,
+    PourLoss weights (1, 1e4, 1) at frames 2000 .. 3000 step 20 (51 frames), the lift-and-tilt action schedule of
+    demo_pour.py:100-105.
+Jade is replaced by the stand-in rigid integrator (softmac_b200/engine/rigid_simulator.py; gravity on the bodies off, so the
+reference's adjust_action_with_ext_force is not needed) -- stated in the output.  Inputs are the reference's data fixtures copied
+as fp32 (tests/golden/reference_rest_states.npz, demo_targets.npz, tests/assets/*).
+
+Arms:
+  drop-in : softmac_b200.engine.taichi_env.TaichiEnv -- the reference's control flow line for line (one substep() call per
+            substep, one coupling call per primitive).
+  batched : BatchedTaichiEnv with --batch rollouts in one handle (smx_step / smx_step_grad per env step, one coupling transfer
+            for all primitives) -- the fast path of this build.
+  device  : `batched` with the rigid bridge itself on the GPU (smx_rigid_linear_*, fixed / prismatic joints only: grip): no host
+            round trip and no stream synchronisation inside the episode.
+  parity  : the SAME env loop, stand-in and host Chamfer loss driven by the f64 oracle and by the CUDA simulator on a shorter
+            episode with a stronger action (so that contact happens): loss, final particle positions, rigid state and the
+            action-gradient cosine (BASELINE.json: >= 0.999 over an episode).  The oracle leg is also the CPU baseline.
+Metric: particle-substeps/s, forward + backward = n * substeps / (t_forward + t_backward) with the stand-in's own dynamics
+(numpy, not part of this build) subtracted and the loss evaluation excluded; wall clock around synchronised phases.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+GOLD = os.path.join(ROOT, "tests", "golden")
+ASSETS = os.path.join(ROOT, "tests", "assets")
+
+
+class StandinClock:
+    """Accumulates the time spent inside the rigid stand-in's own dynamics (``_advance`` / ``_jac``), re-entrancy aware."""
+
+    def __init__(self):
+        self.t, self.depth = 0.0, 0
+
+    def wrap(self, fn):
+        def inner(*a, **k):
+            self.depth += 1
+            t0 = time.perf_counter() if self.depth == 1 else 0.0
+            try:
+                return fn(*a, **k)
+            finally:
+                if self.depth == 1:
+                    self.t += time.perf_counter() - t0
+                self.depth -= 1
+        return inner
+
+    def attach(self, rigid):
+        rigid._advance = self.wrap(rigid._advance)
+        rigid._jac = self.wrap(rigid._jac)
+        rigid._pose = self.wrap(rigid._pose)
+
+
+class TreeChamfer:
+    """ChamferLoss (softmac_b200/engine/losses.py, loss_grip.py:45-68) with exact nearest neighbours from a k-d tree instead of the
+    O(N^2) numpy distance matrix (10 s per frame at 10 000 points); used for BOTH backends of the parity leg."""
+
+    def __init__(self, simulator, target):
+        from scipy.spatial import cKDTree
+        self.sim, self.target, self.tree = simulator, np.asarray(target, dtype=np.float64), cKDTree(np.asarray(target, dtype=np.float64))
+
+    def initialize(self):
+        pass
+
+    reset = initialize
+
+    def compute_loss(self, f):
+        from scipy.spatial import cKDTree
+        x, t = self.sim.get_x(f), self.target
+        i_cur, i_tar = self.tree.query(x)[1], cKDTree(x).query(t)[1]
+        d1, d2 = x - t[i_cur], x[i_tar] - t
+        g = 2 * d1
+        np.add.at(g, i_tar, 2 * d2)
+        self.sim.add_x_grad(f, g)
+        return {"loss": float((d1 * d1).sum() + (d2 * d2).sum())}
+
+
+def scene(config):
+    rest = np.load(os.path.join(GOLD, "reference_rest_states.npz"))
+    tgt = np.load(os.path.join(GOLD, "demo_targets.npz"))
+    if config == "grip":
+        st = rest["grip"].astype(np.float64)
+        return dict(n=len(st), n_grid=64, dt=2e-4, env_dt=1e-3, substeps=5, state=st, target=tgt["grip"].astype(np.float64),
+                    sim=dict(E=3e3, nu=0.2, gravity=(0., -9.8, 0.), ground_friction=20., material_model=0, ptype=0, collision_type=2),
+                    prims=[dict(friction=0.001, urdf_path=os.path.join(ASSETS, "gripper", "gripper.urdf"), enable_external_force=True)],
+                    contact=[False, True, True], rigid_init=(0., 0., 0., 0.), loss_weight=(1., 0., 0.), loss_start=1500, loss_cls="GripLoss")
+    st = rest["pour"].astype(np.float64)
+    st[:, 1] += np.float32(0.04)
+    st = st.astype(np.float32).astype(np.float64)
+    init = (0., 0., 0., 0.7, 0.23488457 + 0.04 + 0.04, 0.5, 0., 0., 0., 0.34, 0.08737724 + 0.04, 0.5) + (0.,) * 12
+    return dict(n=len(st), n_grid=64, dt=1e-3, env_dt=1e-3, substeps=1, state=st, target=tgt["pour"].astype(np.float64),
+                sim=dict(E=22., nu=0.2, gravity=(0., -9.8, 0.), ground_friction=0., material_model=0, ptype=2, collision_type=2),
+                prims=[dict(friction=0.1, urdf_path=os.path.join(ASSETS, "glass", "glass.urdf"), enable_external_force=True),
+                       dict(friction=1.0, urdf_path=os.path.join(ASSETS, "bowl", "bowl.urdf"), enable_external_force=False)],
+                contact=[True, True], rigid_init=init, loss_weight=(1., 1e4, 1.), loss_start=2000, loss_cls="PourLoss",
+                inertia=[0.0343, 0.0348])
+
+
+def actions_for(config, env_steps, strength=1.0):
+    if config == "grip":
+        return np.tile(0.3 * strength * np.array([1.0, -1.0]), (env_steps, 1))                     # demo_grip.py:86 (choice 2)
+    a = np.zeros((env_steps, 12))                                                                   # demo_pour.py:100-105 (choice 1),
+    k = lambda frac: int(round(frac * env_steps))                                                   # scaled to the episode length
+    a[:k(1 / 6), 3:6] = strength * np.array([0.0, 0.9, 0.0])
+    a[k(1 / 6):k(1 / 3), 3:6] = strength * np.array([0.0, -0.9, 0.0])
+    a[k(1 / 6):k(1 / 2), :3] = strength * np.array([0.0, 0.0, 0.05])
+    a[k(1 / 2):k(5 / 6), :3] = strength * np.array([0.0, 0.0, -0.05])
+    return a
+
+
+def rigid_bodies(sc):
+    from softmac_b200.engine.rigid_simulator import bodies_from_urdf
+    bodies = []
+    for c in sc["prims"]:
+        bodies += bodies_from_urdf(c["urdf_path"])
+    for b, I in zip(bodies, sc.get("inertia", [])):
+        b["inertia"] = I
+    return bodies
+
+
+def build_cuda(sc, env_steps, batch=1, cache_dir=None, mode="dropin", loss="device", sort_every=None):
+    from harness import sim_cfg
+    from softmac_b200.config import CfgNode
+    from softmac_b200.engine import MPMSimulator, Primitives
+    from softmac_b200.engine.taichi_env import TaichiEnv
+    from softmac_b200.engine.batched_env import BatchedTaichiEnv
+    from softmac_b200.engine.rigid_simulator import RigidSimulator
+    from softmac_b200.engine import losses
+    S = sc["substeps"]
+    max_steps = env_steps * S + S + 2
+    prims = Primitives([CfgNode(**c) for c in sc["prims"]], max_timesteps=max_steps, cache_dir=cache_dir)
+    k = sc["sim"]
+    cfg = sim_cfg(sc["n"], n_grid=sc["n_grid"], max_steps=max_steps, dt=sc["dt"], E=k["E"], nu=k["nu"], gravity=k["gravity"],
+                  ground_friction=k["ground_friction"], material_model=k["material_model"], ptype=k["ptype"], collision_type=k["collision_type"])
+    sim = MPMSimulator(cfg, prims, env_dt=sc["env_dt"], n_batch=batch, sort_every=sort_every)
+    assert sim.substeps == S, (sim.substeps, S)
+    sim.primitives_contact = sc["contact"]
+    rcfg = CfgNode(gravity=(0., 0., 0.), init_state=sc["rigid_init"], bodies=rigid_bodies(sc))
+    clock = StandinClock()
+
+    def make_rigid(b, views):
+        r = RigidSimulator(rcfg, views, substeps=S, env_dt=sc["env_dt"])
+        clock.attach(r)
+        return r
+    if loss == "device":
+        L = getattr(losses, sc["loss_cls"])(dict(weight=sc["loss_weight"]), sim)
+        L.set_target(sc["target"])
+        L.initialize()
+    else:
+        L = TreeChamfer(sim, sc["target"])
+    if mode == "dropin":
+        assert batch == 1
+        env = TaichiEnv(sim, prims, make_rigid(0, prims), sc["state"], loss=L, control_mode="rigid")
+    else:
+        env = BatchedTaichiEnv(sim, prims, make_rigid, np.tile(sc["state"], (batch, 1)), loss=L, device_rigid=(mode == "device"))
+    return env, sim, prims, clock, L
+
+
+def build_oracle(sc, env_steps, tables):
+    from oracle_backend import OracleMPMSimulator
+    from softmac_b200.config import CfgNode
+    from softmac_b200.engine.taichi_env import TaichiEnv
+    from softmac_b200.engine.rigid_simulator import RigidSimulator
+    from softmac_b200.engine import losses
+    S = sc["substeps"]
+    max_steps = env_steps * S + S + 2
+    params = []
+    for c in sc["prims"]:
+        from softmac_b200.engine.primitive.primitives import Primitives
+        params += [(c["friction"], 666.)] * len(Primitives.load_info_from_urdf(c["urdf_path"])[0])
+    sim = OracleMPMSimulator(sc["n"], sc["n_grid"], max_steps, sc["dt"], S, tables=tables, prim_params=params, **sc["sim"])
+    enable = []
+    for c in sc["prims"]:
+        enable += [c["enable_external_force"]] * len(Primitives.load_info_from_urdf(c["urdf_path"])[0])
+    for i, p in enumerate(sim.primitives):
+        p.enable_external_force = enable[i]
+        sim.sim.set_primitive_enabled(i, bool(sc["contact"][i]))
+    rcfg = CfgNode(gravity=(0., 0., 0.), init_state=sc["rigid_init"], bodies=rigid_bodies(sc))
+    clock = StandinClock()
+    rigid = RigidSimulator(rcfg, sim.primitives, substeps=S, env_dt=sc["env_dt"])
+    clock.attach(rigid)
+    env = TaichiEnv(sim, sim.primitives, rigid, sc["state"], loss=TreeChamfer(sim, sc["target"]), control_mode="rigid")
+    return env, sim, clock
+
+
+def tables_of(prims):
+    """The SDF tables the CUDA primitives hold, fp32-rounded (what the device sees), in the oracle's layout."""
+    r32 = lambda a: np.asarray(a, dtype=np.float32).astype(np.float64)
+    return [dict(sdf=r32(p.sdf_table), normal=r32(p.normal_table), lower=r32(p.sdf_lower), upper=r32(p.sdf_upper), dx=p.sdf_dx) for p in prims]
+
+
+def episode(env, sim, clock, actions, loss_frames, batched, sync, clear=True):
+    """One epoch of the demo loop (demo_grip.py:131-160): reset, forward, loss, backward.  Returns timings and results."""
+    t = {}
+    t0 = time.perf_counter()
+    if clear and hasattr(sim, "clear_all_gradients"):
+        sim.clear_all_gradients()
+    env.reset()
+    sync(); t["prepare"] = time.perf_counter() - t0
+    c0 = clock.t
+    t0 = time.perf_counter()
+    for a in actions:
+        env.step(np.tile(a, (env.B, 1)) if batched else a)
+    sync(); t["forward"] = time.perf_counter() - t0
+    t["standin_forward"] = clock.t - c0
+    t0 = time.perf_counter()
+    total = 0.0
+    for f in loss_frames:
+        total += env.loss.compute_loss(f)["loss"]
+    sync(); t["loss"] = time.perf_counter() - t0
+    c0 = clock.t
+    t0 = time.perf_counter()
+    grad = env.backward()
+    sync(); t["backward"] = time.perf_counter() - t0
+    t["standin_backward"] = clock.t - c0
+    return t, total, np.asarray(grad)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", choices=("grip", "pour"), default="grip")
+    ap.add_argument("--env-steps", type=int, default=None)
+    ap.add_argument("--batch", type=int, default=1, help="rollouts batched in one handle for the `batched` arm")
+    ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--parity-env-steps", type=int, default=None, help="0: skip the oracle leg")
+    ap.add_argument("--parity-strength", type=float, default=None, help="action multiplier of the parity leg")
+    ap.add_argument("--arms", default=None, help="comma list of dropin, batched, device (default: all that apply)")
+    ap.add_argument("--sort-every", type=int, default=None)
+    ap.add_argument("--cache-dir", default=os.path.join(ROOT, "gpurun_out", "sdf_cache"))
+    args = ap.parse_args()
+    sc = scene(args.config)
+    S, n = sc["substeps"], sc["n"]
+    K = args.env_steps or (400 if args.config == "grip" else 3000)
+    loss_frames = list(range(min(sc["loss_start"], (K * S * 3) // 4), K * S + 1, 20))
+    out = {"workload": f"demo_{args.config} episode (BASELINE config {1 if args.config == 'grip' else 2})", "n_particles": n, "n_grid": sc["n_grid"],
+           "env_steps": K, "substeps_per_env_step": S, "dt": sc["dt"], "loss_frames": len(loss_frames),
+           "rigid": "stand-in integrator (Jade not installable); its own numpy dynamics are subtracted from the timings", "arms": {}}
+    tables = None
+    arms = args.arms or ("dropin,batched,device" if args.config == "grip" else "dropin,batched")
+    for arm in [a for a in arms.split(",") if a]:
+        B = args.batch if arm in ("batched", "device") else 1
+        env, sim, prims, clock, L = build_cuda(sc, K, batch=B, cache_dir=args.cache_dir, mode=arm, sort_every=args.sort_every)
+        tables = tables or tables_of(prims)
+        acts = actions_for(args.config, K)
+        best = None
+        for r in range(args.reps + 1):
+            l0 = sim.launch_count()
+            t, loss, grad = episode(env, sim, clock, acts, loss_frames, arm != "dropin", sim.synchronize)
+            t["launches"] = sim.launch_count() - l0
+            if r > 0 and (best is None or t["forward"] + t["backward"] < best[0]["forward"] + best[0]["backward"]):
+                best = (t, loss, grad)
+        t, loss, grad = best
+        sim_s = t["forward"] + t["backward"] - t["standin_forward"] - t["standin_backward"]
+        out["arms"][arm] = {"rollouts_in_handle": B, "seconds": {k: round(v, 5) if isinstance(v, float) else v for k, v in t.items()},
+                            "episode_s_fwd_bwd_minus_standin": sim_s, "particle_substeps_per_s_fwd_bwd": B * n * K * S / sim_s,
+                            "rollouts_per_s": B / (t["forward"] + t["backward"] + t["loss"] + t["prepare"]),
+                            "us_per_substep_pair": 1e6 * sim_s / (K * S), "loss": loss, "grad_norm": float(np.linalg.norm(grad)),
+                            "grad_finite": bool(np.isfinite(grad).all()), "counters": sim.counters()}
+        del env, sim, prims, L
+    # ---- parity + CPU baseline: oracle vs CUDA on a shorter episode with a stronger action ------------------------
+    Kp = args.parity_env_steps if args.parity_env_steps is not None else (80 if args.config == "grip" else 150)
+    if Kp > 0:
+        from harness import cosine, rel_l2
+        from oracle import mpm_oracle as mo
+        strength = args.parity_strength or (50.0 if args.config == "grip" else 8.0)
+        acts = actions_for(args.config, Kp, strength)
+        frames = list(range((Kp * S * 3) // 4, Kp * S + 1, 20)) or [Kp * S]
+        envg, simg, primsg, clockg, _ = build_cuda(sc, Kp, cache_dir=args.cache_dir, mode="dropin", loss="host")
+        tables = tables_of(primsg)
+        tg, lg, gg = episode(envg, simg, clockg, acts, frames, False, simg.synchronize)
+        xg, rg = simg.get_state(Kp * S), envg.rigid_simulator.states[-1].copy()
+        envo, simo, clocko = build_oracle(sc, Kp, tables)
+        to, lo, go = episode(envo, simo, clocko, acts, frames, False, lambda: None)
+        xo, ro = simo.get_state(Kp * S), envo.rigid_simulator.states[-1].copy()
+        na = 6 if args.config == "pour" else go.shape[1]
+        cpu_s = to["forward"] + to["backward"] - to["standin_forward"] - to["standin_backward"]
+        out["parity"] = {"env_steps": Kp, "substeps": Kp * S, "action_strength": strength, "loss_frames": len(frames),
+                         "loss_rel_err": abs(lg - lo) / max(abs(lo), 1e-300), "x_rel_l2": rel_l2(xg[:, :3], xo[:, :3]), "v_rel_l2": rel_l2(xg[:, 3:6], xo[:, 3:6]),
+                         "F_rel_l2": rel_l2(xg[:, 6:15], xo[:, 6:15]), "rigid_state_rel_l2": rel_l2(rg, ro),
+                         "action_grad_cosine": cosine(gg[:, :na], go[:, :na]), "action_grad_rel_l2": rel_l2(gg[:, :na], go[:, :na]),
+                         "action_grad_norm_oracle": float(np.linalg.norm(go[:, :na])), "rigid_moved": float(np.abs(ro - np.asarray(envo.rigid_simulator.init_state)).max()),
+                         "tolerance": "BASELINE.json: action-gradient cosine >= 0.999 over an episode"}
+        out["cpu_baseline"] = {"value": n * Kp * S / cpu_s, "unit": "particle-substeps/s fwd+bwd", "cores": mo.num_threads(), "kind": "port",
+                               "sample": f"{Kp} env steps of the same scene (f64 OpenMP restatement of the Taichi kernels), stand-in dynamics subtracted",
+                               "seconds": {k: round(v, 4) for k, v in to.items()}}
+        out["parity"]["pass"] = bool(out["parity"]["action_grad_cosine"] >= 0.999 and out["parity"]["action_grad_norm_oracle"] > 0)
+    print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--substeps", type=int, default=5)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--sort-every", type=int, default=None, help="re-bin + re-sort period in substeps (default: the simulator's max(substeps, 4))")
+    ap.add_argument("--device-rigid", action="store_true", help="run the (affine) rigid bridge on the GPU: no host round trip per env step")
     args = ap.parse_args()
     import torch
     import scenes
@@ -58,7 +59,7 @@ def main():
     bodies = [dict(joint="prismatic", axis=(1, 0, 0), origin=(0.5 - 0.138, 0.12, 0.5), mass=1.0, gravity=False),
               dict(joint="prismatic", axis=(1, 0, 0), origin=(0.5 + 0.138, 0.12, 0.5), mass=1.0, gravity=False)]
     rcfg = CfgNode(gravity=(0., 0., 0.), init_state=(0., 0., 0.3, -0.3), bodies=bodies)
-    env = BatchedTaichiEnv(sim, prims, lambda b, views: RigidSimulator(rcfg, views, substeps=S, env_dt=dt * S), x)
+    env = BatchedTaichiEnv(sim, prims, lambda b, views: RigidSimulator(rcfg, views, substeps=S, env_dt=dt * S), x, device_rigid=args.device_rigid)
     target = x * np.array([0.8, 1.1, 1.0]) + np.array([0.1, 0.0, 0.0])
     acts = np.stack([np.tile(0.3 * np.array([1.0, -1.0]) * (1 + 0.1 * np.random.default_rng(k).normal()) * 100, (K, 1)) for k in mine])   # (B, K, 2)
 
@@ -91,7 +92,7 @@ def main():
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
     if rank == 0:
         T = float(t.item())
-        print(json.dumps({"workload": "grip-like rollouts (config 4)", "rollouts": args.rollouts, "n_gpus": ws, "rollouts_per_gpu": B, "n_particles": n,
+        print(json.dumps({"workload": "grip-like rollouts (config 4)", "rollouts": args.rollouts, "n_gpus": ws, "rollouts_per_gpu": B, "device_rigid": bool(args.device_rigid), "n_particles": n,
                           "env_steps": K, "substeps": S, "episode_s": T, "rollouts_per_s": args.rollouts / T,
                           "particle_substeps_per_s_fwd_bwd": args.rollouts * n * K * S / T, "grad_norm": float(np.linalg.norm(gmean)),
                           "loss_mean_local": float(np.mean(loss)), "counters": sim.counters()}), flush=True)
