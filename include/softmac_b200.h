@@ -148,23 +148,27 @@ int smx_get_primitive_state_grads_all(smx_sim* sim, int32_t f0, int32_t f1, doub
 int smx_set_primitive_action(smx_sim* sim, int32_t id, int32_t s, int32_t n, const double* a6);
 int smx_get_primitive_action_grad(smx_sim* sim, int32_t id, int32_t s, int32_t n, double* out6);
 
-/* Device-resident rigid coupling for articulated bodies whose joints are all fixed or prismatic (the gripper of demo_grip).
- * Replaces, for that case, the per-env-step host round trip of RigidSimulator.step / set_ext_state / step_grad /
- * get_ext_state_grad (softmac/engine/rigid_simulator.py:85-220): the bridge reads primitive.ext_f / substeps in float32
- * (:92-93), ignores wrenches below 1e-10 or of primitives with enable_external_force == False (:96), advances the bodies, and
- * writes pose + twist into the next `substeps` primitive frames in float32 (:185, :200-201); backwards it sums
- * get_all_states_grad over those frames (:207-216), emits the action gradient and set_ext_f_grad(. / substeps) (:166-168).
- * With affine body dynamics  s' = s As + a Aa + w Aw + c,  pose_i = pose0_i + s' M_i  all of that is one small kernel per env
- * step on the simulator's stream: no synchronisation inside an episode.  All matrices row-major f64:
- * As (state_dim, state_dim), Aa (action_dim, state_dim), Aw (6 * n_primitives, state_dim), c (state_dim),
- * M (n_primitives, state_dim, 13), pose0 (n_primitives, 13), enable (n_primitives), init_state (state_dim). */
+/* Device-resident rigid coupling: the stand-in rigid integrator (bodies on fixed, prismatic or free joints -- the gripper of
+ * demo_grip, the glass and bowl of demo_pour) behind the RigidSimulator interface, on the GPU.
+ * Replaces the per-env-step host round trip of RigidSimulator.step / set_ext_state / step_grad / get_ext_state_grad
+ * (softmac/engine/rigid_simulator.py:85-220): the bridge reads primitive.ext_f / substeps in float32 (:92-93), ignores
+ * wrenches below 1e-10 or of primitives with enable_external_force == False (:96), advances the bodies, and writes pose +
+ * twist into the next `substeps` primitive frames in float32 (:185, :200-201); backwards it sums get_all_states_grad over
+ * those frames (:207-216), emits the action gradient and set_ext_f_grad(. / substeps) (:166-168).
+ * The integrator is affine,  s' = s As + a Aa + w Aw + c,  and the pose map of a body is closed form (its Jacobian by
+ * central differences, eps 1e-6, as the host bridge takes it), so all of that is one small kernel per env step on the
+ * simulator's stream: no synchronisation inside an episode.  State layout: [q (state_dim / 2), q_dot (state_dim / 2)],
+ * the dofs of primitive i's body at dof_offset_i (prismatic: 1; free: 3 exponential coordinates + 3 translations).
+ * Row-major f64: As (state_dim, state_dim), Aa (action_dim, state_dim), Aw (6 * n_primitives, state_dim), c (state_dim),
+ * body (n_primitives, 10) = origin(3) quat0(4, w first) axis(3); int32: joint (n_primitives, 2) = (type: 0 fixed,
+ * 1 prismatic, 2 free; dof_offset), enable (n_primitives); init_state (state_dim). */
 typedef struct {
     int32_t state_dim, action_dim;
     int32_t max_env_steps;        /* env steps kept (states, actions, action gradients, wrench masks) */
     int32_t fp32_bridge;          /* truncate the wrench to float32 as the Jade bridge does (rigid_simulator.py:92) */
     double ext_grad_scale;        /* RigidSimulator.ext_grad_scale (rigid_simulator.py:148) */
-    const double *As, *Aa, *Aw, *c, *M, *pose0, *init_state;
-    const int32_t* enable;
+    const double *As, *Aa, *Aw, *c, *body, *init_state;
+    const int32_t *joint, *enable;
 } smx_rigid_linear;
 int smx_rigid_linear_create(smx_sim* sim, const smx_rigid_linear* desc);
 /* RigidSimulator.reset: every rollout back to init_state, poses of frames [0, substeps) written, wrench cleared */

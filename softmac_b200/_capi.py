@@ -39,8 +39,8 @@ class SmxRigidLinear(C.Structure):
         ("state_dim", C.c_int32), ("action_dim", C.c_int32), ("max_env_steps", C.c_int32), ("fp32_bridge", C.c_int32),
         ("ext_grad_scale", C.c_double),
         ("As", C.POINTER(C.c_double)), ("Aa", C.POINTER(C.c_double)), ("Aw", C.POINTER(C.c_double)), ("c", C.POINTER(C.c_double)),
-        ("M", C.POINTER(C.c_double)), ("pose0", C.POINTER(C.c_double)), ("init_state", C.POINTER(C.c_double)),
-        ("enable", C.POINTER(C.c_int32)),
+        ("body", C.POINTER(C.c_double)), ("init_state", C.POINTER(C.c_double)),
+        ("joint", C.POINTER(C.c_int32)), ("enable", C.POINTER(C.c_int32)),
     ]
 
 

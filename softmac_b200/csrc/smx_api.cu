@@ -857,7 +857,9 @@ static int set_prim_state(smx_sim* s, int b0, int b1, int id, int f0, int f1, co
     for (int f = f0; f < f1; f++) s->near_order[f] = -1;        // the recorded reach bits of these substeps are stale
     for (int b = b0; b < b1; b++)
         CK(cudaMemcpyAsync(s->pstate + (prim_slot(s, b, id) * s->cfg.max_steps + f0) * 13, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, s->stream));
-    CK(cudaStreamSynchronize(s->stream));
+    // small pageable sources are staged by the runtime before the call returns: the per-env-step pose hand-over of the rigid bridge
+    // (rigid_simulator.py:200-201) does not drain the stream; a bulk fill (reset of all frames) still does
+    if (h.size() * sizeof(float) > 32768) CK(cudaStreamSynchronize(s->stream));
     return SMX_OK;
 }
 int smx_set_primitive_state(smx_sim* s, int32_t id, int32_t f0, int32_t f1, const double* s13) {
@@ -932,8 +934,9 @@ static int set_ext_f_grad(smx_sim* s, int b0, int b1, int id, const double* g6) 
     if (!g6) return fail(SMX_ERR_ARG, "smx_set_ext_f_grad: null input");
     CK(cudaSetDevice(s->cfg.device));
     float h[6]; for (int i = 0; i < 6; i++) h[i] = (float)g6[i];
+    // pageable source: the runtime stages it before the call returns, so no stream synchronisation is needed (the reference calls
+    // this once per primitive and substep in the backward pass, mpm_simulator.py:344-346)
     for (int b = b0; b < b1; b++) CK(cudaMemcpyAsync(s->ext_f_grad + 6 * prim_slot(s, b, id), h, sizeof h, cudaMemcpyHostToDevice, s->stream));
-    CK(cudaStreamSynchronize(s->stream));
     return SMX_OK;
 }
 int smx_set_ext_f_grad(smx_sim* s, int32_t id, const double* g6) { TRY(check_prim(s, id, "smx_set_ext_f_grad")); return set_ext_f_grad(s, 0, s->B, id, g6); }
@@ -1067,37 +1070,42 @@ int smx_get_action_grad(smx_sim* s, double* out) {
     return SMX_OK;
 }
 
-// ---- device-resident rigid coupling (fixed / prismatic joints): RigidSimulator.step / step_grad on the simulator's stream ------------
+// ---- device-resident rigid coupling (fixed / prismatic / free joints): RigidSimulator.step / step_grad on the simulator's stream ------------
 int smx_rigid_linear_create(smx_sim* s, const smx_rigid_linear* d) {
     if (!s || !d) return fail(SMX_ERR_ARG, "smx_rigid_linear_create: null argument");
     const int np = (int)s->prims.size(), sd = d->state_dim, ad = d->action_dim, K = d->max_env_steps, B = s->B;
     if (np == 0) return fail(SMX_ERR_STATE, "smx_rigid_linear_create: the simulator has no primitives");
     if (sd < 1 || sd > SMX_RIG_MAXS || ad < 0 || ad > SMX_RIG_MAXA || K < 1) return fail(SMX_ERR_RANGE, "smx_rigid_linear_create: state_dim in [1, %d], action_dim in [0, %d], max_env_steps >= 1", SMX_RIG_MAXS, SMX_RIG_MAXA);
-    if (!d->As || !d->Aw || !d->c || !d->M || !d->pose0 || !d->enable || !d->init_state || (ad > 0 && !d->Aa)) return fail(SMX_ERR_ARG, "smx_rigid_linear_create: null matrix");
+    if (!d->As || !d->Aw || !d->c || !d->body || !d->joint || !d->enable || !d->init_state || (ad > 0 && !d->Aa)) return fail(SMX_ERR_ARG, "smx_rigid_linear_create: null matrix");
     if (s->cfg.rigid_velocity_control) return fail(SMX_ERR_STATE, "smx_rigid_linear_create: not available with rigid velocity control");
     CK(cudaSetDevice(s->cfg.device));
     CK(cudaStreamSynchronize(s->stream));
     cudaFree(s->rig_arena); cudaFree(s->rig_enable); cudaFree(s->rig_masks); s->rig_arena = nullptr; s->rig_enable = nullptr; s->rig_masks = nullptr; s->rig_on = false;
-    const size_t nAs = (size_t)sd * sd, nAa = (size_t)ad * sd, nAw = (size_t)6 * np * sd, nc = sd, nM = (size_t)np * sd * 13, np0 = (size_t)np * 13;
+    for (int i = 0; i < np; i++) {
+        const int jt = d->joint[2 * i], o = d->joint[2 * i + 1], nd = jt == 0 ? 0 : (jt == 1 ? 1 : 6);
+        if (jt < 0 || jt > 2 || o < 0 || 2 * (o + nd) > sd || (sd & 1)) return fail(SMX_ERR_RANGE, "smx_rigid_linear_create: joint %d of primitive %d (dof offset %d) does not fit state_dim %d", jt, i, o, sd);
+    }
+    const size_t nAs = (size_t)sd * sd, nAa = (size_t)ad * sd, nAw = (size_t)6 * np * sd, nc = sd, nbody = (size_t)np * 10;
     const size_t nst = (size_t)(K + 1) * B * sd, nact = (size_t)K * B * std::max(ad, 1), nsg = (size_t)B * sd;
-    const size_t consts = nAs + nAa + nAw + nc + nM + np0, total = consts + nst + 2 * nact + nsg;
+    const size_t consts = nAs + nAa + nAw + nc + nbody, total = consts + nst + 2 * nact + nsg;
     CK(cudaMalloc(&s->rig_arena, total * sizeof(double)));
-    CK(cudaMalloc(&s->rig_enable, np * sizeof(int)));
+    CK(cudaMalloc(&s->rig_enable, 3 * np * sizeof(int)));
     CK(cudaMalloc(&s->rig_masks, (size_t)K * B * np));
     std::vector<double> h(consts);
     size_t o = 0;
     auto put = [&](const double* src, size_t n) { if (n) memcpy(h.data() + o, src, n * sizeof(double)); size_t at = o; o += n; return at; };
-    const size_t oAs = put(d->As, nAs), oAa = put(d->Aa, nAa), oAw = put(d->Aw, nAw), oc = put(d->c, nc), oM = put(d->M, nM), op0 = put(d->pose0, np0);
+    const size_t oAs = put(d->As, nAs), oAa = put(d->Aa, nAa), oAw = put(d->Aw, nAw), oc = put(d->c, nc), obody = put(d->body, nbody);
     CK(cudaMemcpy(s->rig_arena, h.data(), consts * sizeof(double), cudaMemcpyHostToDevice));
     CK(cudaMemset(s->rig_arena + consts, 0, (total - consts) * sizeof(double)));
-    std::vector<int> en(np); for (int i = 0; i < np; i++) en[i] = d->enable[i] ? 1 : 0;
-    CK(cudaMemcpy(s->rig_enable, en.data(), np * sizeof(int), cudaMemcpyHostToDevice));
+    std::vector<int> en(3 * np);          // enable (np) then joint (np, 2)
+    for (int i = 0; i < np; i++) { en[i] = d->enable[i] ? 1 : 0; en[np + 2 * i] = d->joint[2 * i]; en[np + 2 * i + 1] = d->joint[2 * i + 1]; }
+    CK(cudaMemcpy(s->rig_enable, en.data(), en.size() * sizeof(int), cudaMemcpyHostToDevice));
     CK(cudaMemset(s->rig_masks, 0, (size_t)K * B * np));
     RigidLin& R = s->rig;
     R.sd = sd; R.ad = ad; R.np = np; R.B = B; R.S = std::max(s->cfg.substeps, 1); R.T = s->cfg.max_steps; R.K = K; R.fp32 = d->fp32_bridge ? 1 : 0;
     R.scale = d->ext_grad_scale;
     double* a = s->rig_arena;
-    R.As = a + oAs; R.Aa = a + oAa; R.Aw = a + oAw; R.c = a + oc; R.M = a + oM; R.pose0 = a + op0; R.enable = s->rig_enable;
+    R.As = a + oAs; R.Aa = a + oAa; R.Aw = a + oAw; R.c = a + oc; R.body = a + obody; R.enable = s->rig_enable; R.joint = s->rig_enable + np;
     R.states = a + consts; R.actions = R.states + nst; R.action_grad = R.actions + nact; R.state_grad = R.action_grad + nact; R.masks = s->rig_masks;
     s->rig_init.assign(d->init_state, d->init_state + sd);
     s->rig_on = true;

@@ -1,5 +1,5 @@
-// smx_rigid.cuh -- device-resident rigid coupling for articulated bodies whose joints are all fixed or prismatic
-// (the gripper of demo_grip).  SURVEY.md 8f row 3: removes the per-env-step host round trip of the rigid bridge.
+// smx_rigid.cuh -- device-resident rigid coupling for bodies on fixed, prismatic or free joints (the gripper of demo_grip, the
+// glass and bowl of demo_pour).  SURVEY.md 8f row 3: removes the per-env-step host round trip of the rigid bridge.
 //
 // What the reference does once per env step on the host (softmac/engine/rigid_simulator.py):
 //   step          :85-137   read primitive.ext_f / substeps (float32, :92-93), ignore wrenches below 1e-10 or of primitives with
@@ -7,12 +7,15 @@
 //   set_ext_state :176-203  write pose + twist of every primitive into the next `substeps` frames (float32, :185, :200-201)
 //   step_grad     :139-174  state_grad += sum over those frames of get_all_states_grad . d pose / d state (:207-216), action
 //                           gradient, wrench adjoint / substeps -> set_ext_f_grad (:166-168), state_grad <- state_grad . ds'/ds
-// For fixed / prismatic joints the stand-in integrator is affine in (state, action, wrench):
-//   s' = s As + a Aa + w Aw + c          pose_i = pose0_i + s' M_i
-// so the whole bridge is a handful of small constant matrices and runs here as one tiny kernel per env step on the simulator's
-// stream: no device->host read of the wrench, no host->device write of the poses, no stream synchronisation inside an episode.
-// One CTA per batched rollout; all arithmetic in f64 like the host bridge (softmac_b200/engine/batched_env.py:LinearBatchedRigid,
-// which stays as the checker of this path in tests/test_cuda_batch.py).
+// The stand-in integrator (semi-implicit Euler, softmac_b200/engine/rigid_simulator.py) is affine in (state, action, wrench) for
+// all three joint types:
+//   s' = s As + a Aa + w Aw + c
+// and the pose map state -> [x(3) q(4) v(3) w(3)] of a body is closed form (rigid_pose below; nonlinear for free joints: exponential
+// coordinates -> quaternion, twist rotated into the body frame).  Its Jacobian is taken by central differences in f64 exactly as the
+// host bridge does (eps 1e-6).  So the whole bridge is a few small constant matrices plus one closed-form map and runs here as one
+// tiny kernel per env step on the simulator's stream: no device->host read of the wrench, no host->device write of the poses, no
+// stream synchronisation inside an episode.  One CTA per batched rollout; all arithmetic in f64 like the host bridge, which stays
+// as the checker of this path (tests/test_cuda_batch.py).
 #pragma once
 #include "smx_contact.cuh"
 
@@ -24,11 +27,57 @@ namespace smx {
 struct RigidLin {
     int sd, ad, np, B, S, T, K, fp32;
     double scale;                                   // ext_grad_scale (rigid_simulator.py:83, :148)
-    const double *As, *Aa, *Aw, *c, *M, *pose0;     // (sd,sd) (ad,sd) (6 np,sd) (sd) (np,sd,13) (np,13), row-major
+    const double *As, *Aa, *Aw, *c;                 // (sd,sd) (ad,sd) (6 np,sd) (sd), row-major
+    const double* body;                             // (np,10): origin(3) quat0(4, w first) axis(3) of the body behind primitive i
+    const int* joint;                               // (np,2): joint type (0 fixed, 1 prismatic, 2 free), offset of its dofs in the state
     const int* enable;                              // (np) enable_external_force
     double *states, *actions, *action_grad, *state_grad;    // [K+1][B][sd] [K][B][ad] [K][B][ad] [B][sd]
     unsigned char* masks;                           // [K][B][np]: wrench of env step k was fed to the bodies
 };
+
+__device__ __forceinline__ void rig_qmul(const double* a, const double* b, double* o) {
+    o[0] = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+    o[1] = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+    o[2] = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1];
+    o[3] = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
+}
+__device__ __forceinline__ void rig_qrot(const double* q, const double* v, double* o) {       // v + 2 (q_w (q_v x v) + q_v x (q_v x v))
+    const double ux = q[2] * v[2] - q[3] * v[1], uy = q[3] * v[0] - q[1] * v[2], uz = q[1] * v[1] - q[2] * v[0];
+    o[0] = v[0] + 2 * (q[0] * ux + q[2] * uz - q[3] * uy);
+    o[1] = v[1] + 2 * (q[0] * uy + q[3] * ux - q[1] * uz);
+    o[2] = v[2] + 2 * (q[0] * uz + q[1] * uy - q[2] * ux);
+}
+// pose + twist of one body from the rigid state: [x(3) q(4) v(3) w(3)], position / quaternion in the world, body-frame twist
+// (what the Jade bridge reads back per body, rigid_simulator.py:176-186); h = sd / 2 separates positions from velocities.
+// `bump` / `delta` perturb state entry `bump` for the central differences of the adjoint.
+__device__ void rigid_pose(const double* __restrict__ body, int joint, int o, int h, const double* __restrict__ s, int bump, double delta, double* out) {
+    auto S = [&](int i) { return s[i] + (i == bump ? delta : 0.0); };
+    const double* org = body; const double* q0 = body + 3; const double* ax = body + 7;
+    if (joint == 0) {
+        for (int i = 0; i < 3; i++) out[i] = org[i];
+        for (int i = 0; i < 4; i++) out[3 + i] = q0[i];
+        for (int i = 7; i < 13; i++) out[i] = 0.0;
+    } else if (joint == 1) {
+        double aw[3]; rig_qrot(q0, ax, aw);
+        const double q = S(o), qd = S(h + o);
+        for (int i = 0; i < 3; i++) out[i] = org[i] + aw[i] * q;
+        for (int i = 0; i < 4; i++) out[3 + i] = q0[i];
+        for (int i = 0; i < 3; i++) { out[7 + i] = ax[i] * qd; out[10 + i] = 0.0; }
+    } else {
+        const double e[3] = {S(o), S(o + 1), S(o + 2)};
+        const double th = sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
+        double qe[4];
+        if (th < 1e-12) { qe[0] = 1.0; qe[1] = 0.5 * e[0]; qe[2] = 0.5 * e[1]; qe[3] = 0.5 * e[2]; }
+        else { const double sn = sin(0.5 * th) / th; qe[0] = cos(0.5 * th); qe[1] = sn * e[0]; qe[2] = sn * e[1]; qe[3] = sn * e[2]; }
+        double q[4]; rig_qmul(qe, q0, q);
+        const double inv[4] = {q[0], -q[1], -q[2], -q[3]};
+        const double wv[3] = {S(h + o), S(h + o + 1), S(h + o + 2)}, lv[3] = {S(h + o + 3), S(h + o + 4), S(h + o + 5)};
+        for (int i = 0; i < 3; i++) out[i] = org[i] + S(o + 3 + i);
+        for (int i = 0; i < 4; i++) out[3 + i] = q[i];
+        rig_qrot(inv, lv, out + 7);
+        rig_qrot(inv, wv, out + 10);
+    }
+}
 
 // advance == 1: env step k (after its substeps ran): wrench -> s[k+1], poses of frames [f0, f1), wrench cleared.
 // advance == 0: poses of state k only (reset: k = 0, frames [0, substeps)), wrench cleared.
@@ -66,11 +115,12 @@ __global__ void __launch_bounds__(128) k_rigid_linear_step(RigidLin R, int k, in
         }
     } else if (t < R.sd) sn[t] = s[t];
     __syncthreads();
+    __shared__ double pose[SMX_MAXP * 13];
+    if (t < R.np) rigid_pose(R.body + 10 * t, R.joint[2 * t], R.joint[2 * t + 1], R.sd / 2, sn, -1, 0.0, pose + 13 * t);
+    __syncthreads();
     for (int e = t; e < R.np * 13; e += blockDim.x) {
         const int p = e / 13, q = e % 13;
-        double acc = R.pose0[e];
-        for (int i = 0; i < R.sd; i++) acc += sn[i] * R.M[((size_t)p * R.sd + i) * 13 + q];
-        const float v = (float)acc;                 // the bridge hands poses over in float32 (rigid_simulator.py:185)
+        const float v = (float)pose[e];             // the bridge hands poses over in float32 (rigid_simulator.py:185)
         float* dst = pstate + (((size_t)b * SMX_MAXP + p) * R.T) * 13 + q;
         for (int f = f0; f < f1; f++) dst[(size_t)f * 13] = v;
     }
@@ -90,13 +140,25 @@ __global__ void __launch_bounds__(128) k_rigid_linear_step_grad(RigidLin R, int 
         for (int f = f0; f < f1; f++) acc += src[(size_t)f * 13];
         pg[e] = acc;
     }
-    if (t < R.sd) g[t] = R.state_grad[(size_t)b * R.sd + t];
+    __shared__ double sk[SMX_RIG_MAXS];
+    // the poses of frames [f0, f1) were produced from the state AFTER env step k (state k + 1); the initial ones from state 0
+    if (t < R.sd) { g[t] = R.state_grad[(size_t)b * R.sd + t]; g2[t] = g[t]; sk[t] = R.states[((size_t)(finish ? 0 : k + 1) * R.B + b) * R.sd + t]; }
     __syncthreads();
-    if (t < R.sd) {
-        double acc = 0;
-        for (int p = 0; p < R.np; p++)
-            for (int q = 0; q < 13; q++) acc += pg[p * 13 + q] * R.M[((size_t)p * R.sd + t) * 13 + q];
-        g2[t] = g[t] + (finish ? 1.0 : R.scale) * acc;
+    {   // one thread per (primitive, own state entry): d pose / d state by central differences (eps 1e-6, as the host bridge)
+        const int p = t / 12, l = t % 12;
+        if (p < R.np) {
+            const int joint = R.joint[2 * p], o = R.joint[2 * p + 1], h = R.sd / 2;
+            const int ndof = joint == 0 ? 0 : (joint == 1 ? 1 : 6);
+            if (l < 2 * ndof) {
+                const int i = l < ndof ? o + l : h + o + (l - ndof);
+                double hi[13], lo[13];
+                rigid_pose(R.body + 10 * p, joint, o, h, sk, i, 1e-6, hi);
+                rigid_pose(R.body + 10 * p, joint, o, h, sk, i, -1e-6, lo);
+                double acc = 0;
+                for (int q = 0; q < 13; q++) acc += pg[p * 13 + q] * (hi[q] - lo[q]) / 2e-6;
+                g2[i] = g[i] + (finish ? 1.0 : R.scale) * acc;      // every state entry belongs to exactly one body: no race
+            }
+        }
     }
     __syncthreads();
     if (finish) {

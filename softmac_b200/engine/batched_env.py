@@ -167,20 +167,32 @@ class LinearBatchedRigid:
 
 
 class DeviceLinearRigid:
-    """LinearBatchedRigid moved onto the GPU (smx_rigid_linear_*, softmac_b200/csrc/smx_rigid.cuh): the same constant matrices,
-    one small kernel per env step on the simulator's stream, so an episode runs without a single host <-> device round trip
-    of the coupling (wrench, poses, state adjoints and wrench adjoints never leave the device; rigid_simulator.py:85-220)."""
+    """The rigid stand-in moved onto the GPU (smx_rigid_linear_*, softmac_b200/csrc/smx_rigid.cuh): fixed, prismatic and free
+    joints; the integrator's constant matrices (``RigidSimulator._advance`` is affine in state, action and wrench) plus the
+    closed-form pose map of every body, one small kernel per env step on the simulator's stream, so an episode runs without a
+    single host <-> device round trip of the coupling (wrench, poses, state adjoints and wrench adjoints never leave the
+    device; rigid_simulator.py:85-220)."""
 
-    def __init__(self, vec, sim, max_env_steps):
-        self.vec, self.sim, self.h, self.K = vec, sim, sim._h, int(max_env_steps)
-        self.B, self.sd, self.ad, self.P = vec.B, vec.sd, vec.ad, vec.P
-        keep = [as_d(vec.As), as_d(vec.Aa), as_d(vec.Aw), as_d(vec.c), as_d(vec.M), as_d(vec.pose0), as_d(vec.p.init_state),
-                np.ascontiguousarray(vec.enable, dtype=np.int32)]
+    JOINT = {"fixed": 0, "prismatic": 1, "free": 2}
+
+    def __init__(self, proto, sim, n_batch, max_env_steps):
+        self.p, self.sim, self.h, self.K = proto, sim, sim._h, int(max_env_steps)
+        self.B, self.sd, self.ad, self.P = int(n_batch), proto.state_dim, proto.action_dim, proto.n_primitive
+        s0, a0, w0 = np.zeros(self.sd), np.zeros(self.ad), np.zeros(6 * self.P)
+        c = proto._advance(s0, a0, w0)                                               # s' = s As + a Aa + w Aw + c (exactly affine: eps = 1)
+        As = proto._jac(lambda x: proto._advance(x, a0, w0), s0, eps=1.0).T
+        Aa = proto._jac(lambda x: proto._advance(s0, x, w0), a0, eps=1.0).T if self.ad else np.zeros((0, self.sd))
+        Aw = proto._jac(lambda x: proto._advance(s0, a0, x), w0, eps=1.0).T
+        body = np.array([np.concatenate([b.origin, b.quat0, b.axis]) for b in proto.bodies])
+        joint = np.array([[self.JOINT[b.joint], int(proto.offsets[i])] for i, b in enumerate(proto.bodies)], dtype=np.int32)
+        enable = np.array([bool(proto.primitives[i].enable_external_force) for i in range(self.P)], dtype=np.int32)
+        keep = [as_d(As), as_d(Aa), as_d(Aw), as_d(c), as_d(body), as_d(proto.init_state)]
         d = SmxRigidLinear()
-        d.state_dim, d.action_dim, d.max_env_steps, d.fp32_bridge = self.sd, self.ad, self.K, int(bool(vec.fp32))
-        d.ext_grad_scale = float(vec.p.ext_grad_scale)
-        d.As, d.Aa, d.Aw, d.c, d.M, d.pose0, d.init_state = [d_ptr(a) for a in keep[:7]]
-        d.enable = keep[7].ctypes.data_as(C.POINTER(C.c_int32))
+        d.state_dim, d.action_dim, d.max_env_steps, d.fp32_bridge = self.sd, self.ad, self.K, int(bool(proto.fp32_bridge))
+        d.ext_grad_scale = float(proto.ext_grad_scale)
+        d.As, d.Aa, d.Aw, d.c, d.body, d.init_state = [d_ptr(a) for a in keep]
+        d.joint = np.ascontiguousarray(joint).ctypes.data_as(C.POINTER(C.c_int32))
+        d.enable = enable.ctypes.data_as(C.POINTER(C.c_int32))
         check(lib().smx_rigid_linear_create(self.h, C.byref(d)))
 
     def reset(self):
@@ -222,14 +234,16 @@ class BatchedTaichiEnv:
         """make_rigid(b, views) -> a rigid simulator (RigidSimulator surface) for rollout b talking to `views`.
         vectorize: when every joint of the stand-in is fixed / prismatic, advance all rollouts with LinearBatchedRigid
         (numpy matmuls) instead of B Python bridges.
-        device_rigid: run that affine bridge on the GPU (DeviceLinearRigid): no host round trip per env step; ``step_grad``
-        then returns None and ``backward`` reads all action gradients once at the end."""
+        device_rigid: run the stand-in on the GPU (DeviceLinearRigid; fixed / prismatic / free joints): no host round trip per
+        env step; ``step_grad`` then returns None and ``backward`` reads all action gradients once at the end."""
         self.simulator, self.primitives, self.loss = simulator, primitives, loss
         self.B, self.substeps = simulator.n_batch, simulator.substeps
         self.buf = CouplingBuffer(simulator, primitives)
         self.rigid = [make_rigid(0, self.buf.views[0])]
         self.vec = None
-        if vectorize and hasattr(self.rigid[0], "bodies") and all(b.joint in ("fixed", "prismatic") for b in self.rigid[0].bodies):
+        if device_rigid:
+            pass                                # one prototype bridge is enough: it only supplies the matrices and body descriptors
+        elif vectorize and hasattr(self.rigid[0], "bodies") and all(b.joint in ("fixed", "prismatic") for b in self.rigid[0].bodies):
             self.vec = LinearBatchedRigid(self.rigid[0], self.B)
         else:
             self.rigid += [make_rigid(b, self.buf.views[b]) for b in range(1, self.B)]
@@ -237,9 +251,9 @@ class BatchedTaichiEnv:
         self.action_list = []
         self.dev = None
         if device_rigid:
-            if not self.vec:
-                raise ValueError("device_rigid needs a stand-in whose joints are all fixed or prismatic")
-            self.dev = DeviceLinearRigid(self.vec, simulator, max(simulator.max_steps // max(self.substeps, 1), 1))
+            if not hasattr(self.rigid[0], "bodies"):
+                raise ValueError("device_rigid needs the stand-in rigid simulator (bodies on fixed / prismatic / free joints)")
+            self.dev = DeviceLinearRigid(self.rigid[0], simulator, self.B, max(simulator.max_steps // max(self.substeps, 1), 1))
         primitives.initialize()
         simulator.initialize()
         self.reset()
@@ -312,11 +326,11 @@ class BatchedTaichiEnv:
         return np.stack(grads)
 
     def backward(self):
+        total = self.simulator.cur // self.substeps
         if self.vec:
             self.vec.state_grad = np.zeros((self.B, self.vec.sd))
         for r in self.rigid:
             r.state_grad = np.zeros(r.state_dim)
-        total = self.simulator.cur // self.substeps
         if self.dev:
             for s in range(total - 1, -1, -1):
                 self.step_grad(self.action_list[s])

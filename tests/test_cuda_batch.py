@@ -143,10 +143,12 @@ def test_batched_env_matches_single_rollout_envs():
         assert np.abs(g1).max() > 0 and rel_l2(gb[b], g1) <= 1e-3, (gb[b], g1)
 
 
-def test_device_resident_rigid_coupling_matches_host_bridge():
-    """smx_rigid_linear_* (the affine rigid bridge on the GPU, no host round trip per env step) == LinearBatchedRigid on the host:
-    same particle states, rigid states, action gradients and adjoint of the initial rigid state; one rollout's fingers carry a
-    primitive whose wrench is ignored (enable_external_force = False, rigid_simulator.py:96)."""
+@pytest.mark.parametrize("joints", ["prismatic", "free"])
+def test_device_resident_rigid_coupling_matches_host_bridge(joints):
+    """smx_rigid_linear_* (the rigid stand-in on the GPU, no host round trip per env step) == the host bridges: same particle
+    states, rigid states, action gradients and adjoint of the initial rigid state.  "prismatic": two fingers + a fixed body whose
+    wrench is ignored (enable_external_force = False, rigid_simulator.py:96), checked against LinearBatchedRigid; "free": two
+    free-floating bodies with spin (demo_pour's joints: the pose map is nonlinear), checked against one Python bridge per rollout."""
     from softmac_b200.engine import MPMSimulator, Primitives, Mesh
     from softmac_b200.engine.batched_env import BatchedTaichiEnv
     from softmac_b200.engine.rigid_simulator import RigidSimulator
@@ -157,16 +159,26 @@ def test_device_resident_rigid_coupling_matches_host_bridge():
     rng = np.random.default_rng(6)
     x = ((rng.random((n, 3)) * 2 - 1) * 0.05 + np.array([0.5, 0.3, 0.5])).astype(np.float32).astype(np.float64)
     tab = scenes.sphere_table(radius=0.06, dx=0.01, margin=0.04)
-    bodies = [dict(joint="prismatic", axis=(1, 0, 0), origin=(0.5 - 0.108, 0.3, 0.5), mass=1.0, gravity=False),
-              dict(joint="prismatic", axis=(1, 0, 0), origin=(0.5 + 0.108, 0.3, 0.5), mass=1.5, gravity=False),
-              dict(joint="fixed", origin=(0.5, 0.3 + 0.105, 0.5))]
-    rcfg = CfgNode(gravity=(0., 0., 0.), init_state=(0., 0., 0.4, -0.4), bodies=bodies)
+    if joints == "prismatic":
+        bodies = [dict(joint="prismatic", axis=(1, 0, 0), origin=(0.5 - 0.108, 0.3, 0.5), mass=1.0, gravity=False),
+                  dict(joint="prismatic", axis=(1, 0, 0), origin=(0.5 + 0.108, 0.3, 0.5), mass=1.5, gravity=False),
+                  dict(joint="fixed", origin=(0.5, 0.3 + 0.105, 0.5))]
+        init = (0., 0., 0.4, -0.4)
+        actions = np.stack([np.tile([40.0, -40.0], (env_steps, 1)), np.tile([10.0, -70.0], (env_steps, 1)), np.tile([0.0, 0.0], (env_steps, 1))])
+        enable = [True, True, False]
+    else:
+        bodies = [dict(joint="free", origin=(0.5 - 0.106, 0.3, 0.5), quat=(0.9238795, 0.0, 0.3826834, 0.0), mass=1.0, inertia=0.02, gravity=True),
+                  dict(joint="free", origin=(0.5 + 0.106, 0.3, 0.5), mass=2.0, inertia=0.05, gravity=False)]
+        init = (0.1, -0.2, 0.05, 0.0, 0.0, 0.0) + (0.0,) * 6 + (3.0, 1.0, -2.0, 0.4, 0.0, 0.0) + (0.0, 0.5, 0.0, -0.4, 0.0, 0.0)
+        a0 = np.array([0.02, 0.0, 0.05, 30.0, 5.0, 0.0, 0.0, 0.01, 0.0, -40.0, 0.0, 3.0])
+        actions = np.stack([np.tile(a0 * sc, (env_steps, 1)) for sc in (1.0, -0.5, 0.0)])
+        enable = [True, False]
+    rcfg = CfgNode(gravity=(0., -9.8, 0.), init_state=init, bodies=bodies)
     target = x + np.array([0.0, 0.01, 0.0])
-    actions = np.stack([np.tile([40.0, -40.0], (env_steps, 1)), np.tile([10.0, -70.0], (env_steps, 1)), np.tile([0.0, 0.0], (env_steps, 1))])
 
     def run(device_rigid):
         ms = [Mesh(sdf=dict(sdf=tab["sdf"], normal=tab["normal"], position=(tab["lower"], tab["upper"]), dx=tab["dx"]),
-                   cfg=dict(friction=0.3, enable_external_force=(i != 2)), max_timesteps=max_steps) for i in range(3)]
+                   cfg=dict(friction=0.3, enable_external_force=enable[i]), max_timesteps=max_steps) for i in range(len(bodies))]
         prims = Primitives(primitives=ms, max_timesteps=max_steps)
         sim = MPMSimulator(sim_cfg(n, n_grid=n_grid, max_steps=max_steps, dt=dt), prims, env_dt=dt * substeps, n_batch=B)
         env = BatchedTaichiEnv(sim, prims, lambda b, views: RigidSimulator(rcfg, views, substeps=substeps, env_dt=dt * substeps), x,
@@ -181,14 +193,14 @@ def test_device_resident_rigid_coupling_matches_host_bridge():
             xs = sim.get_x(f_end).reshape(B, n, 3)
             sim.add_x_grad(f_end, (xs - target).reshape(B * n, 3))
             g = env.backward()
-            sg = env.dev.state_grad if env.dev else env.vec.state_grad
+            sg = env.dev.state_grad if env.dev else (env.vec.state_grad if env.vec else np.stack([r.state_grad for r in env.rigid]))
             out.append((xs, g, env.rigid_states(), np.array(sg)))
         assert rel_l2(out[0][1], out[1][1]) <= 1e-4                       # episodes differ only by the order of the float atomics
         return out[1]
 
     xh, gh, rh, sh = run(False)
     xd, gd, rd, sd = run(True)
-    assert gh.shape == gd.shape == (B, env_steps, 2) and np.abs(gh[:2]).max() > 0
+    assert gh.shape == gd.shape == (B, env_steps, actions.shape[2]) and np.abs(gh[:2]).max() > 0
     assert rel_l2(xd, xh) <= 1e-6
     assert rel_l2(rd, rh) <= 1e-7
     assert rel_l2(gd, gh) <= 1e-4, (gd, gh)

@@ -22,8 +22,8 @@ Arms:
             substep, one coupling call per primitive).
   batched : BatchedTaichiEnv with --batch rollouts in one handle (smx_step / smx_step_grad per env step, one coupling transfer
             for all primitives) -- the fast path of this build.
-  device  : `batched` with the rigid bridge itself on the GPU (smx_rigid_linear_*, fixed / prismatic joints only: grip): no host
-            round trip and no stream synchronisation inside the episode.
+  device  : `batched` with the rigid bridge itself on the GPU (smx_rigid_linear_*: fixed / prismatic / free joints): no host round
+            trip and no stream synchronisation inside the episode.
   parity  : the SAME env loop, stand-in and host Chamfer loss driven by the f64 oracle and by the CUDA simulator on a shorter
             episode with a stronger action (so that contact happens): loss, final particle positions, rigid state and the
             action-gradient cosine (BASELINE.json: >= 0.999 over an episode).  The oracle leg is also the CPU baseline.
@@ -255,7 +255,7 @@ def main():
            "env_steps": K, "substeps_per_env_step": S, "dt": sc["dt"], "loss_frames": len(loss_frames),
            "rigid": "stand-in integrator (Jade not installable); its own numpy dynamics are subtracted from the timings", "arms": {}}
     tables = None
-    arms = args.arms or ("dropin,batched,device" if args.config == "grip" else "dropin,batched")
+    arms = args.arms or "dropin,batched,device"
     for arm in [a for a in arms.split(",") if a]:
         B = args.batch if arm in ("batched", "device") else 1
         env, sim, prims, clock, L = build_cuda(sc, K, batch=B, cache_dir=args.cache_dir, mode=arm, sort_every=args.sort_every)
