@@ -137,7 +137,7 @@ def rigid_bodies(sc):
     return bodies
 
 
-def build_cuda(sc, env_steps, batch=1, cache_dir=None, mode="dropin", loss="device", sort_every=None):
+def build_cuda(sc, env_steps, batch=1, cache_dir=None, mode="dropin", loss="device", sort_every=None, device=0):
     from harness import sim_cfg
     from softmac_b200.config import CfgNode
     from softmac_b200.engine import MPMSimulator, Primitives
@@ -147,11 +147,11 @@ def build_cuda(sc, env_steps, batch=1, cache_dir=None, mode="dropin", loss="devi
     from softmac_b200.engine import losses
     S = sc["substeps"]
     max_steps = env_steps * S + S + 2
-    prims = Primitives([CfgNode(**c) for c in sc["prims"]], max_timesteps=max_steps, cache_dir=cache_dir)
+    prims = Primitives([CfgNode(**c) for c in sc["prims"]], max_timesteps=max_steps, cache_dir=cache_dir, device=device)
     k = sc["sim"]
     cfg = sim_cfg(sc["n"], n_grid=sc["n_grid"], max_steps=max_steps, dt=sc["dt"], E=k["E"], nu=k["nu"], gravity=k["gravity"],
                   ground_friction=k["ground_friction"], material_model=k["material_model"], ptype=k["ptype"], collision_type=k["collision_type"])
-    sim = MPMSimulator(cfg, prims, env_dt=sc["env_dt"], n_batch=batch, sort_every=sort_every)
+    sim = MPMSimulator(cfg, prims, env_dt=sc["env_dt"], n_batch=batch, sort_every=sort_every, device=device)
     assert sim.substeps == S, (sim.substeps, S)
     sim.primitives_contact = sc["contact"]
     rcfg = CfgNode(gravity=(0., 0., 0.), init_state=sc["rigid_init"], bodies=rigid_bodies(sc))
@@ -218,8 +218,9 @@ def episode(env, sim, clock, actions, loss_frames, batched, sync, clear=True):
     sync(); t["prepare"] = time.perf_counter() - t0
     c0 = clock.t
     t0 = time.perf_counter()
-    for a in actions:
-        env.step(np.tile(a, (env.B, 1)) if batched else a)
+    for k in range(actions.shape[-2]):
+        a = actions[..., k, :]                                       # (ad,) or, per rollout, (B, ad)
+        env.step((a if a.ndim == 2 else np.tile(a, (env.B, 1))) if batched else a)
     sync(); t["forward"] = time.perf_counter() - t0
     t["standin_forward"] = clock.t - c0
     t0 = time.perf_counter()
@@ -235,6 +236,49 @@ def episode(env, sim, clock, actions, loss_frames, batched, sync, clear=True):
     return t, total, np.asarray(grad)
 
 
+def sharded_rollouts(args, sc, K):
+    """BASELINE config 4 on the real demo scene: args.rollouts episodes, round-robin over the ranks, B = rollouts / world per handle."""
+    import torch
+    from softmac_b200 import rollouts
+    rank, ws, local = rollouts.init()
+    if torch.cuda.is_available():
+        torch.cuda.set_device(local)
+    mine = rollouts.shard(args.rollouts, rank, ws)
+    S, n, B = sc["substeps"], sc["n"], len(mine)
+    loss_frames = list(range(min(sc["loss_start"], (K * S * 3) // 4), K * S + 1, 20))
+    env, sim, prims, clock, L = build_cuda(sc, K, batch=B, cache_dir=os.path.join(args.cache_dir, f"rank{rank}"), mode="device",
+                                           sort_every=args.sort_every, device=local)
+    base = actions_for(args.config, K)
+    acts = np.stack([base * (1 + 0.1 * np.random.default_rng(k).normal()) for k in mine])           # (B, K, ad)
+    times, gmean, loss = [], None, 0.0
+    for r in range(args.reps + 1):
+        if ws > 1:
+            torch.distributed.barrier()
+        sim.synchronize()
+        t0 = time.perf_counter()
+        t, loss, grad = episode(env, sim, clock, acts, loss_frames, True, sim.synchronize)
+        gmean = rollouts.allreduce_gradients(grad, args.rollouts)
+        sim.synchronize()
+        if ws > 1:
+            torch.distributed.barrier()
+        if r > 0:
+            times.append((time.perf_counter() - t0, t["forward"] + t["backward"], t["loss"]))
+    best = min(times)
+    red = torch.tensor(list(best), dtype=torch.float64, device="cuda" if torch.cuda.is_available() else "cpu")
+    if ws > 1:
+        torch.distributed.all_reduce(red, op=torch.distributed.ReduceOp.MAX)
+    if rank == 0:
+        T, Tsim, Tloss = [float(v) for v in red.tolist()]
+        print(json.dumps({"workload": f"{args.rollouts} demo_{args.config} rollouts (BASELINE config 4), perturbed action sequences, gradient all-reduce",
+                          "n_gpus": ws, "rollouts": args.rollouts, "rollouts_per_handle": B, "n_particles": n, "env_steps": K, "substeps_per_env_step": S,
+                          "loss_frames": len(loss_frames), "episode_s": T, "fwd_bwd_s": Tsim, "loss_s": Tloss, "rollouts_per_s": args.rollouts / T,
+                          "particle_substeps_per_s_fwd_bwd": args.rollouts * n * K * S / Tsim, "mean_grad_norm": float(np.linalg.norm(gmean)),
+                          "loss_local": loss, "sort_every": args.sort_every, "counters": sim.counters(),
+                          "timing": "wall clock around synchronised phases, max over ranks; fwd_bwd excludes reset and the Chamfer loss"}), flush=True)
+    if ws > 1:
+        torch.distributed.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", choices=("grip", "pour"), default="grip")
@@ -245,11 +289,16 @@ def main():
     ap.add_argument("--parity-strength", type=float, default=None, help="action multiplier of the parity leg")
     ap.add_argument("--arms", default=None, help="comma list of dropin, batched, device (default: all that apply)")
     ap.add_argument("--sort-every", type=int, default=None)
+    ap.add_argument("--rollouts", type=int, default=0, help="BASELINE config 4: this many rollouts with perturbed action sequences "
+                    "0.3 [1, -1] (1 + 0.1 xi_k), sharded over the ranks of a torchrun launch (one handle per GPU, device-resident rigid "
+                    "coupling), action gradients all-reduced (mean) at the end of the episode")
     ap.add_argument("--cache-dir", default=os.path.join(ROOT, "gpurun_out", "sdf_cache"))
     args = ap.parse_args()
     sc = scene(args.config)
     S, n = sc["substeps"], sc["n"]
     K = args.env_steps or (400 if args.config == "grip" else 3000)
+    if args.rollouts:
+        return sharded_rollouts(args, sc, K)
     loss_frames = list(range(min(sc["loss_start"], (K * S * 3) // 4), K * S + 1, 20))
     out = {"workload": f"demo_{args.config} episode (BASELINE config {1 if args.config == 'grip' else 2})", "n_particles": n, "n_grid": sc["n_grid"],
            "env_steps": K, "substeps_per_env_step": S, "dt": sc["dt"], "loss_frames": len(loss_frames),
