@@ -247,6 +247,15 @@ int smx_get_grad(smx_sim* sim, int32_t f, double* xg, double* vg);
 /* ti.ad.clear_all_gradients() restricted to this path (demo_grip.py:135) */
 int smx_clear_grads(smx_sim* sim);
 
+/* device-resident variants for particle migration between slab ranks (softmac_b200/slabs.py): (n, 24) fp32 rows in
+ * particle-id order, get_state layout, in DEVICE memory; ordered on the simulator's stream, no host round trip.
+ * smx_reset_dev == smx_reset, smx_get_state_dev == smx_get_state, smx_get_state_grad_dev == smx_get_state_grad,
+ * smx_add_state_grad_dev == smx_add_state_grad. */
+int smx_reset_dev(smx_sim* sim, const float* rows_dev);
+int smx_get_state_dev(smx_sim* sim, int32_t f, float* out_dev);
+int smx_get_state_grad_dev(smx_sim* sim, int32_t f, float* out_dev);
+int smx_add_state_grad_dev(smx_sim* sim, int32_t f, const float* g24_dev);
+
 /* introspection for tests, benches and zero-copy consumers -------------------------------------- */
 /* sort key of every particle of frame f in STORAGE order, and the storage permutation (slot -> particle id).
  * Contract: perm == numpy.argsort(key_in_previous_order, kind="stable") composed over re-sorts. */

@@ -124,6 +124,10 @@ _SIGS = {
     "smx_set_chamfer_target": [vp, dp, C.c_int32],
     "smx_chamfer_loss": [vp, C.c_int32, C.c_double, dp],
     "smx_get_state_grad": [vp, C.c_int32, dp],
+    "smx_reset_dev": [vp, vp],
+    "smx_get_state_dev": [vp, C.c_int32, vp],
+    "smx_get_state_grad_dev": [vp, C.c_int32, vp],
+    "smx_add_state_grad_dev": [vp, C.c_int32, vp],
     "smx_get_grad": [vp, C.c_int32, dp, dp],
     "smx_clear_grads": [vp],
     "smx_get_sort_keys": [vp, C.c_int32, up],

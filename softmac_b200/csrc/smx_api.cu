@@ -753,11 +753,7 @@ int smx_set_primitive_contact(smx_sim* s, int32_t id, int32_t enabled) {
     return sync_prims(s);
 }
 
-int smx_reset(smx_sim* s, const double* state, int32_t ncols) {
-    if (!s || !state) return fail(SMX_ERR_ARG, "smx_reset: null argument");
-    if (ncols != 3 && ncols != 24) return fail(SMX_ERR_ARG, "smx_reset: state must have 3 or 24 columns, got %d", ncols);
-    CK(cudaSetDevice(s->cfg.device));
-    CK(cudaStreamSynchronize(s->stream));
+static void reset_bookkeeping(smx_sim* s) {
     std::fill(s->order_of.begin(), s->order_of.end(), -1);
     std::fill(s->trans_from.begin(), s->trans_from.end(), -1);
     std::fill(s->ckpt_order.begin(), s->ckpt_order.end(), -1);
@@ -766,6 +762,13 @@ int smx_reset(smx_sim* s, const double* state, int32_t ncols) {
     s->adj_frame = -1; s->adj_order = -1;
     s->ckpt_dirty = true;
     gc_orders(s);                       // every ordering is unreferenced now: recycle all of them
+}
+int smx_reset(smx_sim* s, const double* state, int32_t ncols) {
+    if (!s || !state) return fail(SMX_ERR_ARG, "smx_reset: null argument");
+    if (ncols != 3 && ncols != 24) return fail(SMX_ERR_ARG, "smx_reset: state must have 3 or 24 columns, got %d", ncols);
+    CK(cudaSetDevice(s->cfg.device));
+    CK(cudaStreamSynchronize(s->stream));
+    reset_bookkeeping(s);
     int n = s->P.n;
     Order root; s->order_of[0] = new_order_id(s, root);
     if (n > 0) {
@@ -785,6 +788,41 @@ int smx_reset(smx_sim* s, const double* state, int32_t ncols) {
         k_upload<<<nblk(n, 256), 256, 0, s->stream>>>(n, s->P.stride, s->stage_dev, 24, 0, s->frame_ptr(0), nullptr, 0); CKL(s);
     }
     return resort(s, 0, false);
+}
+// smx_reset with the (n, 24) fp32 rows already on the device (particle migration between slab ranks: no host round trip)
+int smx_reset_dev(smx_sim* s, const float* rows_dev) {
+    if (!s || (!rows_dev && s->P.n > 0)) return fail(SMX_ERR_ARG, "smx_reset_dev: null argument");
+    CK(cudaSetDevice(s->cfg.device));
+    CK(cudaStreamSynchronize(s->stream));       // orderings are recycled below
+    reset_bookkeeping(s);
+    const int n = s->P.n;
+    Order root; s->order_of[0] = new_order_id(s, root);
+    if (n > 0) { k_upload<<<nblk(n, 256), 256, 0, s->stream>>>(n, s->P.stride, rows_dev, 24, 0, s->frame_ptr(0), nullptr, 0); CKL(s); }
+    return resort(s, 0, false);
+}
+// frame f / its adjoint as (n, 24) fp32 rows in particle-id order, written to DEVICE memory on the simulator's stream (no sync)
+int smx_get_state_dev(smx_sim* s, int32_t f, float* out_dev) {
+    TRY(check_frame(s, f, "smx_get_state_dev"));
+    if (!out_dev && s->P.n > 0) return fail(SMX_ERR_ARG, "smx_get_state_dev: null output");
+    if (s->order_of[f] < 0) return fail(SMX_ERR_STATE, "smx_get_state_dev: frame %d has not been written", f);
+    CK(cudaSetDevice(s->cfg.device));
+    if (s->P.n > 0) { k_download<<<nblk(s->P.n, 256), 256, 0, s->stream>>>(s->P.n, s->P.stride, out_dev, 24, 0, s->frame_ptr(f), s->orders[s->order_of[f]].perm); CKL(s); }
+    return SMX_OK;
+}
+int smx_get_state_grad_dev(smx_sim* s, int32_t f, float* out_dev) {
+    TRY(check_frame(s, f, "smx_get_state_grad_dev"));
+    if (!out_dev && s->P.n > 0) return fail(SMX_ERR_ARG, "smx_get_state_grad_dev: null output");
+    CK(cudaSetDevice(s->cfg.device));
+    if (s->P.n == 0) return SMX_OK;
+    if (s->adj_frame != f) {            // no backward step has produced this frame's adjoint: it is just the loss seed (if any)
+        if (s->order_of[f] < 0) return fail(SMX_ERR_STATE, "smx_get_state_grad_dev: frame %d has not been written", f);
+        CK(cudaMemsetAsync(s->adj_nxt, 0, s->frame_floats * sizeof(float), s->stream));
+        TRY(apply_seed(s, f, s->adj_nxt, s->order_of[f]));
+        k_download<<<nblk(s->P.n, 256), 256, 0, s->stream>>>(s->P.n, s->P.stride, out_dev, 24, 0, s->adj_nxt, s->orders[s->order_of[f]].perm); CKL(s);
+    } else {
+        k_download<<<nblk(s->P.n, 256), 256, 0, s->stream>>>(s->P.n, s->P.stride, out_dev, 24, 0, s->adj_cur, s->orders[s->adj_order].perm); CKL(s);
+    }
+    return SMX_OK;
 }
 
 int smx_set_frame(smx_sim* s, int32_t f, const double* x, const double* v, const double* F, const double* C) {
@@ -1452,6 +1490,7 @@ int smx_step_grad(smx_sim* s, int32_t s1, int32_t count) {
 }
 
 // ---- adjoint seeds / read-out ---------------------------------------------------------------------
+static int add_seed_dev(smx_sim* s, int f, const float* src_dev, int ncols);
 static int add_seed(smx_sim* s, int f, const double* g, int ncols) {
     int n = s->P.n;
     if (n == 0) return SMX_OK;
@@ -1463,6 +1502,13 @@ static int add_seed(smx_sim* s, int f, const double* g, int ncols) {
         for (long long i = (long long)i0; i < (long long)i1; i++) dst[i] = (float)g[i];
     };
         TRY(h2d_pipelined(s, cnt, fill));
+    return add_seed_dev(s, f, s->stage_dev, ncols);
+}
+// accumulate (n, ncols) fp32 rows that are already on the device into the loss seed of frame f
+static int add_seed_dev(smx_sim* s, int f, const float* src_dev, int ncols) {
+    int n = s->P.n;
+    if (n == 0) return SMX_OK;
+    size_t cnt = (size_t)n * ncols;
     auto it = s->seeds.find(f);
     if (it != s->seeds.end() && it->second.ncols < ncols) {
         // widen an x-only seed to the full 24 columns
@@ -1477,12 +1523,12 @@ static int add_seed(smx_sim* s, int f, const double* g, int ncols) {
     if (it == s->seeds.end()) {
         smx_sim::Seed sd; sd.ncols = ncols;
         TRY(seed_alloc(s, cnt * sizeof(float), &sd.dev));
-        CK(cudaMemcpyAsync(sd.dev, s->stage_dev, cnt * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
+        CK(cudaMemcpyAsync(sd.dev, src_dev, cnt * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
         s->seeds[f] = sd;
     } else if (it->second.ncols == ncols) {
-        k_axpy<<<nblk((long long)cnt, 256), 256, 0, s->stream>>>((long long)cnt, it->second.dev, s->stage_dev); CKL(s);
+        k_axpy<<<nblk((long long)cnt, 256), 256, 0, s->stream>>>((long long)cnt, it->second.dev, src_dev); CKL(s);
     } else {    // stored 24 columns, adding 3
-        k_add_cols<<<nblk(n, 256), 256, 0, s->stream>>>(n, it->second.dev, 24, s->stage_dev, 3); CKL(s);
+        k_add_cols<<<nblk(n, 256), 256, 0, s->stream>>>(n, it->second.dev, 24, src_dev, 3); CKL(s);
     }
     CK(cudaStreamSynchronize(s->stream));
     return SMX_OK;
@@ -1491,6 +1537,12 @@ int smx_add_state_grad(smx_sim* s, int32_t f, const double* g24) {
     TRY(check_frame(s, f, "smx_add_state_grad"));
     if (!g24) return fail(SMX_ERR_ARG, "smx_add_state_grad: null input");
     return add_seed(s, f, g24, 24);
+}
+int smx_add_state_grad_dev(smx_sim* s, int32_t f, const float* g24_dev) {
+    TRY(check_frame(s, f, "smx_add_state_grad_dev"));
+    if (!g24_dev && s->P.n > 0) return fail(SMX_ERR_ARG, "smx_add_state_grad_dev: null input");
+    CK(cudaSetDevice(s->cfg.device));
+    return add_seed_dev(s, f, g24_dev, 24);
 }
 int smx_add_x_grad(smx_sim* s, int32_t f, const double* g3) {
     TRY(check_frame(s, f, "smx_add_x_grad"));

@@ -18,8 +18,15 @@ into g_out, so after it every rank adds the neighbour's part of (g_out - g_mix) 
 kernel gathers gg_out (complete after the first halo sum) and scatters into gg_mix, whose halo is then summed too.
 Wrenches and primitive-state adjoints are per-rank partial sums and are reduced when read.
 
-Not implemented in round 1: particle migration between ranks (ownership is fixed at reset; a particle may drift up
-to two cells out of its slab before the counters flag it).
+Particle migration (``MigratingSlabCluster`` / ``DistSlab(migrate_every=E)``): ownership is re-established every E substeps.
+A rank is then a SEQUENCE of simulator handles, one per epoch of E substeps; at an epoch boundary the rows of the last frame
+are taken on the device (``smx_get_state_dev``), the particles whose base cell left the slab are sent to the x-neighbour
+(24 floats + the global id per particle), and the next epoch's handle is reset from [staying | received-from-lo |
+received-from-hi] rows without a host round trip (``smx_reset_dev``).  In the backward pass the adjoint of the first frame of
+an epoch is split the same way, the received parts travel back to the rank that sent those particles, and the reassembled
+rows become a loss seed of the previous epoch's last frame (``smx_add_state_grad_dev``): the chain rule across a migration is
+a permutation.  Without migration (``SlabCluster`` / ``DistSlab``) ownership is fixed at reset and a particle may drift up to
+two cells out of its slab before the counters flag it.  Migration with primitives is not built (variant A of config 5 has none).
 """
 import ctypes as C
 
@@ -300,3 +307,212 @@ class DistSlab:
         out[torch.as_tensor(self.r.ids, device=out.device)] = torch.as_tensor(self.sim.get_state(f), device=out.device)
         self.dist.all_reduce(out)
         return out.cpu().numpy()
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# particle migration: a rank as a sequence of epoch handles
+# ------------------------------------------------------------------------------------------------------------------------
+class _Epoch:
+    """The particles one rank owns during the substeps [f0, f0 + E): a simulator handle reset from device rows."""
+
+    def __init__(self, cfg, rank, bounds, rows, gid, f0, epoch_len, device, use_torch_stream, sim_kw):
+        import copy
+        import torch
+        from .engine.mpm_simulator import MPMSimulator
+        self.f0, self.E, self.n, self.gid, self.device = f0, epoch_len, int(rows.shape[0]), gid, device
+        if self.n == 0:
+            raise RuntimeError(f"slab rank {rank} owns no particles in the epoch starting at substep {f0}")
+        c = copy.deepcopy(cfg)
+        c.n_particles, c.max_steps = self.n, epoch_len + 2
+        kw = dict(sim_kw)
+        stream = torch.cuda.current_stream(device).cuda_stream if use_torch_stream else None
+        flags = kw.pop("flags", 0) | (SMX_FLAG_EXTERNAL_STREAM if use_torch_stream else 0)
+        self.sim = MPMSimulator(c, (), device=device, stream=stream or None, flags=flags, **kw)
+        n_ranks = len(bounds) - 1
+        self.lo, self.hi, self.nb = bounds[rank], bounds[rank + 1], int(128 * cfg.quality * 0.5) // 4
+        check(lib().smx_set_slab(self.sim._h, self.lo, self.hi, int(rank > 0), int(rank < n_ranks - 1)))
+        rows = rows.contiguous()
+        check(lib().smx_reset_dev(self.sim._h, rows.data_ptr()))
+        self.parts = None           # (idx_stay, idx_lo, idx_hi, n_recv_lo, n_recv_hi): how this epoch's rows came out of the previous one
+        self.primitives = ()
+        self._views = {}
+
+    halo = SlabRank.halo
+
+    def rows_dev(self, local_f, grad=False):
+        import torch
+        out = torch.empty((self.n, 24), dtype=torch.float32, device=f"cuda:{self.device}")
+        fn = lib().smx_get_state_grad_dev if grad else lib().smx_get_state_dev
+        check(fn(self.sim._h, int(local_f), out.data_ptr()))
+        return out
+
+
+class MigratingSlabRank:
+    def __init__(self, cfg, rank, bounds, state, migrate_every, device=0, use_torch_stream=True, **sim_kw):
+        import torch
+        self.cfg, self.rank, self.bounds, self.E = cfg, rank, list(bounds), int(migrate_every)
+        self.n_ranks, self.device, self.use_torch_stream, self.sim_kw = len(bounds) - 1, device, use_torch_stream, sim_kw
+        self.n_grid = int(128 * cfg.quality * 0.5)
+        st = np.asarray(state, dtype=np.float64)
+        if st.shape[1] == 3:
+            full = np.zeros((len(st), 24)); full[:, :3] = st; full[:, 6] = full[:, 10] = full[:, 14] = 1
+            st = full
+        col = np.clip((st[:, 0].astype(np.float32) * np.float32(self.n_grid) - np.float32(0.5)).astype(np.int32), 0, self.n_grid - 3) >> 2
+        ids = np.nonzero((col >= bounds[rank]) & (col < bounds[rank + 1]))[0]
+        dev = f"cuda:{device}"
+        rows = torch.as_tensor(st[ids].astype(np.float32), device=dev)
+        self.epochs = [_Epoch(cfg, rank, bounds, rows, torch.as_tensor(ids, device=dev), 0, self.E, device, use_torch_stream, sim_kw)]
+        self.migrated = 0
+
+    # epoch of substep f (input frame f) / of frame f (the latest epoch that holds it)
+    def epoch_of_substep(self, f):
+        return self.epochs[f // self.E]
+
+    def epoch_of_frame(self, f):
+        return self.epochs[min(f // self.E, len(self.epochs) - 1)]
+
+    def needs_epoch(self, f):
+        return f // self.E >= len(self.epochs)
+
+    # forward migration, phase 1: rows of the last frame of the current epoch, split by the slab the base cell lies in
+    def split_last(self):
+        import torch
+        ep = self.epochs[-1]
+        rows = ep.rows_dev(self.E)
+        col = torch.clamp((rows[:, 0] * float(self.n_grid) - 0.5).to(torch.int32), 0, self.n_grid - 3) >> 2
+        go_lo = (col < ep.lo) if self.rank > 0 else torch.zeros_like(col, dtype=torch.bool)
+        go_hi = (col >= ep.hi) if self.rank < self.n_ranks - 1 else torch.zeros_like(col, dtype=torch.bool)
+        idx = torch.arange(ep.n, device=rows.device)
+        self._pend = (rows, idx[~(go_lo | go_hi)], idx[go_lo], idx[go_hi])
+        rows_lo, rows_hi = rows[self._pend[2]], rows[self._pend[3]]
+        return (rows_lo, ep.gid[self._pend[2]]), (rows_hi, ep.gid[self._pend[3]])
+
+    # phase 2: the next epoch from [staying | received from lo | received from hi]
+    def start_epoch(self, recv_lo, recv_hi):
+        import torch
+        ep = self.epochs[-1]
+        rows, i_stay, i_lo, i_hi = self._pend
+        new_rows = torch.cat([rows[i_stay], recv_lo[0], recv_hi[0]])
+        new_gid = torch.cat([ep.gid[i_stay], recv_lo[1], recv_hi[1]])
+        ne = _Epoch(self.cfg, self.rank, self.bounds, new_rows, new_gid, ep.f0 + self.E, self.E, self.device, self.use_torch_stream, self.sim_kw)
+        ne.parts = (i_stay, i_lo, i_hi, int(recv_lo[0].shape[0]), int(recv_hi[0].shape[0]))
+        self.migrated += int(i_lo.numel() + i_hi.numel())
+        self.epochs.append(ne)
+        self._pend = None
+
+    # backward migration, phase 1: adjoint of the first frame of epoch e, parts that go back to the neighbours
+    def split_first_grad(self, e):
+        ep = self.epochs[e]
+        g = ep.rows_dev(0, grad=True)
+        i_stay, i_lo, i_hi, n_rlo, n_rhi = ep.parts
+        ns = int(i_stay.numel())
+        self._pend_b = (g[:ns], e)
+        return g[ns:ns + n_rlo], g[ns + n_rlo:ns + n_rlo + n_rhi]
+
+    # phase 2: seed of the last frame of epoch e - 1
+    def seed_previous(self, back_lo, back_hi):
+        import torch
+        g_stay, e = self._pend_b
+        i_stay, i_lo, i_hi, _, _ = self.epochs[e].parts
+        prev = self.epochs[e - 1]
+        G = torch.zeros((prev.n, 24), dtype=torch.float32, device=g_stay.device)
+        G[i_stay] = g_stay
+        G[i_lo] = back_lo
+        G[i_hi] = back_hi
+        check(lib().smx_add_state_grad_dev(prev.sim._h, self.E, G.contiguous().data_ptr()))
+        self._pend_b = None
+
+
+class _MigratingBase:
+    """Epoch bookkeeping shared by the emulated cluster and the NCCL rank."""
+
+    def _local(self, f):
+        return f % self.E
+
+
+class MigratingSlabCluster(_MigratingBase):
+    """All ranks in ONE process on one device, with particle migration every `migrate_every` substeps (tests / single GPU)."""
+
+    def __init__(self, cfg, n_ranks, state, migrate_every, device=0, **sim_kw):
+        n_grid = int(128 * cfg.quality * 0.5)
+        self.n, self.E = len(state), int(migrate_every)
+        self.bounds = choose_bounds(np.asarray(state)[:, 0], n_ranks, n_grid)
+        self.ranks = [MigratingSlabRank(cfg, r, self.bounds, state, migrate_every, device=device, **sim_kw) for r in range(n_ranks)]
+        self._bwd_epoch = None
+
+    def _exchange(self, eps, which):
+        for r in range(len(eps) - 1):
+            a, b = eps[r].halo(which, "hi"), eps[r + 1].halo(which, "lo")
+            t = a + b
+            a.copy_(t); b.copy_(t)
+
+    def _migrate(self):
+        import torch
+        sends = [r.split_last() for r in self.ranks]
+        R = len(self.ranks)
+        dev = sends[0][0][0].device
+        empty = (torch.empty((0, 24), dtype=torch.float32, device=dev), torch.empty((0,), dtype=torch.int64, device=dev))
+        for r, rk in enumerate(self.ranks):
+            rk.start_epoch(sends[r - 1][1] if r > 0 else empty, sends[r + 1][0] if r < R - 1 else empty)
+
+    def substep(self, f):
+        if self.ranks[0].needs_epoch(f):
+            self._migrate()
+        eps = [r.epoch_of_substep(f) for r in self.ranks]
+        lf = self._local(f)
+        for ep in eps:
+            check(lib().smx_substep_begin(ep.sim._h, lf))
+        self._exchange(eps, 0)
+        for ep in eps:
+            check(lib().smx_substep_end(ep.sim._h, lf))
+        self._bwd_epoch = None
+
+    def substep_grad(self, f):
+        e = f // self.E
+        if self._bwd_epoch is not None and e == self._bwd_epoch - 1:        # crossing an epoch boundary backwards
+            R = len(self.ranks)
+            parts = [r.split_first_grad(e + 1) for r in self.ranks]          # (to lo neighbour, to hi neighbour)
+            for r, rk in enumerate(self.ranks):
+                # what rank r sent to r-1 came back as r-1's "received from hi" part, and symmetrically
+                back_lo = parts[r - 1][1] if r > 0 else parts[r][0][:0]
+                back_hi = parts[r + 1][0] if r < R - 1 else parts[r][0][:0]
+                rk.seed_previous(back_lo, back_hi)
+        self._bwd_epoch = e
+        eps = [r.epochs[e] for r in self.ranks]
+        lf = self._local(f)
+        for ep in eps:
+            check(lib().smx_substep_grad_begin(ep.sim._h, lf))
+        self._exchange(eps, 3)
+        for ep in eps:
+            check(lib().smx_substep_grad_end(ep.sim._h, lf))
+
+    def _gather(self, f, grad):
+        out = np.zeros((self.n, 24))
+        for r in self.ranks:
+            ep = r.epoch_of_frame(f)
+            lf = f - ep.f0
+            out[ep.gid.cpu().numpy()] = ep.sim.get_state_grad(lf) if grad else ep.sim.get_state(lf)
+        return out
+
+    def get_state(self, f):
+        return self._gather(f, False)
+
+    def get_state_grad(self, f):
+        return self._gather(f, True)
+
+    def add_x_grad(self, f, g):
+        for r in self.ranks:
+            ep = r.epoch_of_frame(f)
+            ep.sim.add_x_grad(f - ep.f0, np.asarray(g)[ep.gid.cpu().numpy()])
+
+    def clear_all_gradients(self):
+        for r in self.ranks:
+            for ep in r.epochs:
+                ep.sim.clear_all_gradients()
+        self._bwd_epoch = None
+
+    def counters(self):
+        return [ep.sim.counters() for r in self.ranks for ep in r.epochs]
+
+    def migrated(self):
+        return sum(r.migrated for r in self.ranks)

@@ -43,6 +43,47 @@ def test_slab_cluster_matches_single_handle(n_ranks):
         assert c["left_active_region"] == 0 and c["clamped"] == 0
 
 
+@pytest.mark.parametrize("n_ranks", [2, 3])
+def test_slab_cluster_with_particle_migration(n_ranks):
+    """Material streaming through the slab boundaries at 0.26 cells per substep: ownership is re-established every 4 substeps
+    (rows handed to the x-neighbour on the device, adjoints handed back in the backward pass); states and the adjoint of frame 0
+    must equal the single-handle run, and particles must actually have changed rank."""
+    from softmac_b200.engine import MPMSimulator
+    from softmac_b200.slabs import MigratingSlabCluster
+    rng = np.random.default_rng(29)
+    n, steps, n_grid, E = 20000, 12, 64, 4
+    st = scenes.blob_state(n, rng, center=(0.45, 0.3, 0.5), width=0.5, vel=0.5, Fdev=0.003, Cdev=0.5)
+    st[:, 1] = 0.3 + (st[:, 1] - 0.3) * 0.3
+    st[:, 3] += 20.0                                            # +x drift: 3 cells over the rollout
+    st = st.astype(np.float32).astype(np.float64)
+    cfg = sim_cfg(n, n_grid=n_grid, max_steps=steps + 2)
+    ref = MPMSimulator(cfg, (), env_dt=1e-3, sort_every=2)
+    ref.reset(st)
+    clu = MigratingSlabCluster(cfg, n_ranks, st, E, env_dt=1e-3, sort_every=2)
+    for f in range(steps):
+        ref.substep(f)
+        clu.substep(f)
+    assert clu.migrated() > 100 and all(len(r.epochs) == steps // E for r in clu.ranks)
+    assert sum(r.epochs[-1].n for r in clu.ranks) == n
+    a, b = clu.get_state(steps), ref.get_state(steps)
+    assert rel_l2(a[:, :3], b[:, :3]) <= 1e-6
+    assert rel_l2(a[:, 3:6], b[:, 3:6]) <= 2e-5
+    assert rel_l2(a[:, 6:], b[:, 6:]) <= 2e-5
+    mid = clu.get_state(E + 1)                                  # a frame of the second epoch, read back in global particle order
+    assert rel_l2(mid[:, :3], ref.get_state(E + 1)[:, :3]) <= 1e-6
+    g, g2 = rng.normal(size=(n, 3)), rng.normal(size=(n, 3))
+    ref.clear_all_gradients(); ref.add_x_grad(steps, g); ref.add_x_grad(2 * E, g2)
+    clu.clear_all_gradients(); clu.add_x_grad(steps, g); clu.add_x_grad(2 * E, g2)      # one seed on an epoch boundary
+    for f in range(steps - 1, -1, -1):
+        ref.substep_grad(f)
+        clu.substep_grad(f)
+    ga, gb = clu.get_state_grad(0), ref.get_state_grad(0)
+    assert np.abs(gb).max() > 0
+    assert rel_l2(ga, gb) <= 1e-4 and cosine(ga, gb) >= 0.99999
+    for c in clu.counters():
+        assert c["left_active_region"] == 0 and c["clamped"] == 0
+
+
 def test_choose_bounds_balances_particles():
     from softmac_b200.slabs import choose_bounds
     rng = np.random.default_rng(0)
