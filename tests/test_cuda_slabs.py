@@ -68,7 +68,9 @@ def test_slab_cluster_with_particle_migration(n_ranks):
     a, b = clu.get_state(steps), ref.get_state(steps)
     assert rel_l2(a[:, :3], b[:, :3]) <= 1e-6
     assert rel_l2(a[:, 3:6], b[:, 3:6]) <= 2e-5
-    assert rel_l2(a[:, 6:], b[:, 6:]) <= 2e-5
+    assert rel_l2(a[:, 6:15], b[:, 6:15]) <= 2e-5
+    # C = 4 inv_dx sum w v (x) dpos cancels a 20 m/s drift in fp32: its rounding error scales with |v| / dx, not with |C|
+    assert rel_l2(a[:, 15:], b[:, 15:], floor=np.linalg.norm(b[:, 3:6]) * n_grid) <= 2e-5
     mid = clu.get_state(E + 1)                                  # a frame of the second epoch, read back in global particle order
     assert rel_l2(mid[:, :3], ref.get_state(E + 1)[:, :3]) <= 1e-6
     g, g2 = rng.normal(size=(n, 3)), rng.normal(size=(n, 3))
