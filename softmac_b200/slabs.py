@@ -363,6 +363,24 @@ class MigratingSlabRank:
         rows = torch.as_tensor(st[ids].astype(np.float32), device=dev)
         self.epochs = [_Epoch(cfg, rank, bounds, rows, torch.as_tensor(ids, device=dev), 0, self.E, device, use_torch_stream, sim_kw)]
         self.migrated = 0
+        self._pool = {}             # particle count -> idle epoch handles (a repeated rollout re-uses them: no cudaMalloc / cudaFree)
+
+    def rewind(self):
+        """Back to the first epoch (its frames are kept); the later handles go to the pool."""
+        for ep in self.epochs[1:]:
+            self._pool.setdefault(ep.n, []).append(ep)
+        del self.epochs[1:]
+        self.migrated = 0
+
+    def _new_epoch(self, rows, gid, f0):
+        idle = self._pool.get(int(rows.shape[0]))
+        if idle:
+            ep = idle.pop()
+            ep.f0, ep.gid = f0, gid
+            ep.sim.clear_all_gradients()
+            check(lib().smx_reset_dev(ep.sim._h, rows.contiguous().data_ptr()))
+            return ep
+        return _Epoch(self.cfg, self.rank, self.bounds, rows, gid, f0, self.E, self.device, self.use_torch_stream, self.sim_kw)
 
     # epoch of substep f (input frame f) / of frame f (the latest epoch that holds it)
     def epoch_of_substep(self, f):
@@ -394,7 +412,7 @@ class MigratingSlabRank:
         rows, i_stay, i_lo, i_hi = self._pend
         new_rows = torch.cat([rows[i_stay], recv_lo[0], recv_hi[0]])
         new_gid = torch.cat([ep.gid[i_stay], recv_lo[1], recv_hi[1]])
-        ne = _Epoch(self.cfg, self.rank, self.bounds, new_rows, new_gid, ep.f0 + self.E, self.E, self.device, self.use_torch_stream, self.sim_kw)
+        ne = self._new_epoch(new_rows, new_gid, ep.f0 + self.E)
         ne.parts = (i_stay, i_lo, i_hi, int(recv_lo[0].shape[0]), int(recv_hi[0].shape[0]))
         self.migrated += int(i_lo.numel() + i_hi.numel())
         self.epochs.append(ne)
@@ -516,3 +534,157 @@ class MigratingSlabCluster(_MigratingBase):
 
     def migrated(self):
         return sum(r.migrated for r in self.ranks)
+
+
+def exchange_rows(dist, rank, world, send_lo, send_hi):
+    """Variable-size hand-over of particle rows to the two x-neighbours.  send_* = (rows (k, 24) float32, gid (k,) int64);
+    returns (recv_lo, recv_hi) in the same form.  One message of counts, then one payload per neighbour: 24 floats + the global
+    id (int32 bit pattern in a 25th float column) per particle."""
+    import torch
+    dev = send_lo[0].device
+    peers = [(rank - 1, send_lo), (rank + 1, send_hi)]
+    cnt_out = {p: torch.tensor([snd[0].shape[0]], dtype=torch.int64, device=dev) for p, snd in peers if 0 <= p < world}
+    cnt_in = {p: torch.zeros(1, dtype=torch.int64, device=dev) for p in cnt_out}
+    ops = []
+    for p in cnt_out:
+        ops += [dist.P2POp(dist.isend, cnt_out[p], p), dist.P2POp(dist.irecv, cnt_in[p], p)]
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    pay_out, pay_in, ops = {}, {}, []
+    for p, snd in peers:
+        if not (0 <= p < world):
+            continue
+        k_out, k_in = int(snd[0].shape[0]), int(cnt_in[p].item())
+        if k_out:
+            pay_out[p] = torch.cat([snd[0].to(torch.float32), snd[1].to(torch.int32).view(torch.float32).reshape(-1, 1)], dim=1).contiguous()
+            ops.append(dist.P2POp(dist.isend, pay_out[p], p))
+        if k_in:
+            pay_in[p] = torch.empty((k_in, 25), dtype=torch.float32, device=dev)
+            ops.append(dist.P2POp(dist.irecv, pay_in[p], p))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+
+    def unpack(p):
+        if p not in pay_in:
+            return torch.empty((0, 24), dtype=torch.float32, device=dev), torch.empty((0,), dtype=torch.int64, device=dev)
+        t = pay_in[p]
+        return t[:, :24].contiguous(), t[:, 24].contiguous().view(torch.int32).to(torch.int64)
+    return unpack(rank - 1), unpack(rank + 1)
+
+
+def exchange_back(dist, rank, world, to_lo, to_hi, n_from_lo, n_from_hi):
+    """Backward counterpart: the adjoint rows of the particles received from a neighbour travel back to it; the sizes are known
+    on both sides from the forward hand-over (n_from_* = what this rank SENT to that neighbour then)."""
+    import torch
+    dev, ops, got = to_lo.device, [], {}
+    for p, snd, k_in in ((rank - 1, to_lo, n_from_lo), (rank + 1, to_hi, n_from_hi)):
+        if not (0 <= p < world):
+            continue
+        if snd.shape[0]:
+            ops.append(dist.P2POp(dist.isend, snd.contiguous(), p))
+        if k_in:
+            got[p] = torch.empty((k_in, 24), dtype=torch.float32, device=dev)
+            ops.append(dist.P2POp(dist.irecv, got[p], p))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    empty = torch.empty((0, 24), dtype=torch.float32, device=dev)
+    return got.get(rank - 1, empty), got.get(rank + 1, empty)
+
+
+class DistMigratingSlab(_MigratingBase):
+    """One rank per process (torchrun, NCCL) with particle migration every `migrate_every` substeps."""
+
+    def __init__(self, cfg, state, migrate_every, device=None, **sim_kw):
+        import torch
+        import torch.distributed as dist
+        self.dist = dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.device = torch.cuda.current_device() if device is None else device
+        n_grid = int(128 * cfg.quality * 0.5)
+        self.n, self.E = len(state), int(migrate_every)
+        self.bounds = choose_bounds(np.asarray(state)[:, 0], self.world, n_grid)
+        self.r = MigratingSlabRank(cfg, self.rank, self.bounds, state, migrate_every, device=self.device, **sim_kw)
+        self._tmp = {}
+        self._bwd_epoch = None
+
+    def _exchange(self, ep, which):
+        import torch
+        dist, ops, pend = self.dist, [], []
+        for side, peer in (("lo", self.rank - 1), ("hi", self.rank + 1)):
+            if 0 <= peer < self.world:
+                v = ep.halo(which, side)
+                t = self._tmp.setdefault((which, side), torch.empty_like(v))
+                ops += [dist.P2POp(dist.isend, v, peer), dist.P2POp(dist.irecv, t, peer)]
+                pend.append((v, t))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+            for v, t in pend:
+                v.add_(t)
+
+    def substep(self, f):
+        if self.r.needs_epoch(f):
+            send_lo, send_hi = self.r.split_last()
+            self.r.start_epoch(*exchange_rows(self.dist, self.rank, self.world, send_lo, send_hi))
+        ep, lf = self.r.epoch_of_substep(f), self._local(f)
+        check(lib().smx_substep_begin(ep.sim._h, lf))
+        self._exchange(ep, 0)
+        check(lib().smx_substep_end(ep.sim._h, lf))
+        self._bwd_epoch = None
+
+    def substep_grad(self, f):
+        e = f // self.E
+        if self._bwd_epoch is not None and e == self._bwd_epoch - 1:
+            to_lo, to_hi = self.r.split_first_grad(e + 1)
+            _, i_lo, i_hi, _, _ = self.r.epochs[e + 1].parts
+            self.r.seed_previous(*exchange_back(self.dist, self.rank, self.world, to_lo, to_hi, int(i_lo.numel()), int(i_hi.numel())))
+        self._bwd_epoch = e
+        ep, lf = self.r.epochs[e], self._local(f)
+        check(lib().smx_substep_grad_begin(ep.sim._h, lf))
+        self._exchange(ep, 3)
+        check(lib().smx_substep_grad_end(ep.sim._h, lf))
+
+    def step(self, s0, count):
+        for f in range(s0, s0 + count):
+            self.substep(f)
+
+    def step_grad(self, s1, count):
+        for f in range(s1 - 1, s1 - 1 - count, -1):
+            self.substep_grad(f)
+
+    def add_x_grad(self, f, g_global):
+        ep = self.r.epoch_of_frame(f)
+        ep.sim.add_x_grad(f - ep.f0, np.asarray(g_global)[ep.gid.cpu().numpy()])
+
+    def add_state_grad_dev(self, f, g_global_dev):
+        """Loss seed of frame f from a device tensor (n_global, 24) float32 in global particle order: gathered by the current
+        owners' ids and accumulated on the device (no host round trip)."""
+        ep = self.r.epoch_of_frame(f)
+        G = g_global_dev[ep.gid].contiguous()
+        check(lib().smx_add_state_grad_dev(ep.sim._h, int(f - ep.f0), G.data_ptr()))
+
+    def clear_all_gradients(self):
+        for ep in self.r.epochs:
+            ep.sim.clear_all_gradients()
+        self._bwd_epoch = None
+
+    def rewind(self):
+        self.r.rewind()
+        self._bwd_epoch = None
+
+    def gather_state(self, f):
+        import torch
+        ep = self.r.epoch_of_frame(f)
+        out = torch.zeros((self.n, 24), dtype=torch.float64, device=f"cuda:{self.device}")
+        out[ep.gid] = torch.as_tensor(ep.sim.get_state(f - ep.f0), device=out.device)
+        self.dist.all_reduce(out)
+        return out.cpu().numpy()
+
+    def migrated(self):
+        import torch
+        t = torch.tensor([float(self.r.migrated)], dtype=torch.float64, device=f"cuda:{self.device}")
+        self.dist.all_reduce(t)
+        return int(t.item())

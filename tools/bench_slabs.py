@@ -29,13 +29,16 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--sort-every", type=int, default=16)
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--migrate-every", type=int, default=0, help="re-establish particle ownership every E substeps (particle migration "
+                    "between slab ranks over NCCL P2P); 0: ownership fixed at reset")
+    ap.add_argument("--drift", type=float, default=0.0, help="add this x-velocity (m/s) to every particle so that material streams through the slab boundaries")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
     import scenes
     from harness import sim_cfg, rel_l2
     from softmac_b200 import rollouts
-    from softmac_b200.slabs import DistSlab
+    from softmac_b200.slabs import DistSlab, DistMigratingSlab
     rank, ws, local = rollouts.init()
     torch.cuda.set_device(local)
     if args.check:
@@ -46,8 +49,13 @@ def main():
     st = scenes.cube_state(args.n)                                              # same on every rank (np.random.seed(0))
     if args.check:
         st[:, 3:6] = 0.5 * np.random.default_rng(1).normal(size=(args.n, 3)).astype(np.float32)
+    if args.drift:
+        st[:, 3] += np.float32(args.drift)
     seed = st[:, :3] - st[:, :3].mean(0)
-    if ws > 1:
+    E = args.migrate_every
+    if ws > 1 and E:
+        sl = DistMigratingSlab(cfg, st, E, env_dt=5 * dt, sort_every=args.sort_every)
+    elif ws > 1:
         sl = DistSlab(cfg, st, env_dt=5 * dt, sort_every=args.sort_every)
     else:
         from softmac_b200.slabs import SlabCluster
@@ -63,14 +71,30 @@ def main():
             def add_x_grad(self, f, g): sim.add_x_grad(f, g)
         sl, the_sim = _One(), sim
         sl.sim = sim
-    sim = sl.sim
-    sim.copyframe(0, S + 1)
-    sl.add_x_grad(S, seed)
+    migrating = ws > 1 and E > 0
+    if migrating:
+        sim = sl.r.epochs[0].sim                    # first epoch: its spare frame E + 1 keeps the initial state
+        sim.copyframe(0, E + 1)
 
-    def step():
-        sim.copyframe(S + 1, 0)
-        sl.step(0, S)
-        sl.step_grad(S, S)
+        seed_dev = torch.zeros((args.n, 24), dtype=torch.float32, device="cuda")      # the dense seed, resident like the states
+        seed_dev[:, :3] = torch.as_tensor(seed.astype(np.float32), device="cuda")
+
+        def step():
+            sl.rewind()
+            sl.clear_all_gradients()
+            sim.copyframe(E + 1, 0)
+            sl.step(0, S)
+            sl.add_state_grad_dev(S, seed_dev)          # the owners of the last frame differ from those at reset
+            sl.step_grad(S, S)
+    else:
+        sim = sl.sim
+        sim.copyframe(0, S + 1)
+        sl.add_x_grad(S, seed)
+
+        def step():
+            sim.copyframe(S + 1, 0)
+            sl.step(0, S)
+            sl.step_grad(S, S)
 
     times = []
     for r in range(args.reps + 2):
@@ -91,6 +115,10 @@ def main():
     out = {"workload": f"slab decomposition (config 5): {args.n} particles, {args.n_grid}^3, {S} substeps fwd + {S} bwd", "n_gpus": ws,
            "ms_per_step": T * 1e3, "particle_substeps_per_s_fwd_bwd": args.n * S / T, "scaling": "strong", "local_particles": int(sim.n_particles),
            "counters": sim.counters()}
+    if migrating:
+        out["migrate_every"] = E
+        out["migrated_particles_per_step"] = sl.migrated()
+        out["local_particles_last_epoch"] = int(sl.r.epochs[-1].n)
     if args.check and ws > 1:
         got = sl.gather_state(S)
         if rank == 0:
