@@ -315,11 +315,12 @@ class DistSlab:
 class _Epoch:
     """The particles one rank owns during the substeps [f0, f0 + E): a simulator handle reset from device rows."""
 
-    def __init__(self, cfg, rank, bounds, rows, gid, f0, epoch_len, device, use_torch_stream, sim_kw):
+    def __init__(self, cfg, rank, bounds, rows, gid, f0, epoch_len, device, use_torch_stream, sim_kw, make_primitives=None):
         import copy
         import torch
         from .engine.mpm_simulator import MPMSimulator
         self.f0, self.E, self.n, self.gid, self.device = f0, epoch_len, int(rows.shape[0]), gid, device
+        self.primitives = make_primitives() if make_primitives else ()
         if self.n == 0:
             raise RuntimeError(f"slab rank {rank} owns no particles in the epoch starting at substep {f0}")
         c = copy.deepcopy(cfg)
@@ -327,17 +328,25 @@ class _Epoch:
         kw = dict(sim_kw)
         stream = torch.cuda.current_stream(device).cuda_stream if use_torch_stream else None
         flags = kw.pop("flags", 0) | (SMX_FLAG_EXTERNAL_STREAM if use_torch_stream else 0)
-        self.sim = MPMSimulator(c, (), device=device, stream=stream or None, flags=flags, **kw)
+        self.sim = MPMSimulator(c, self.primitives, device=device, stream=stream or None, flags=flags, **kw)
         n_ranks = len(bounds) - 1
         self.lo, self.hi, self.nb = bounds[rank], bounds[rank + 1], int(128 * cfg.quality * 0.5) // 4
         check(lib().smx_set_slab(self.sim._h, self.lo, self.hi, int(rank > 0), int(rank < n_ranks - 1)))
         rows = rows.contiguous()
         check(lib().smx_reset_dev(self.sim._h, rows.data_ptr()))
         self.parts = None           # (idx_stay, idx_lo, idx_hi, n_recv_lo, n_recv_hi): how this epoch's rows came out of the previous one
-        self.primitives = ()
         self._views = {}
 
     halo = SlabRank.halo
+    has_contact = SlabRank.has_contact
+
+    def load_primitive_states(self, series):
+        """series[i]: {global frame: s13}; this handle holds the local frames [0, E + 2) = global [f0, f0 + E + 2)."""
+        for i, frames in enumerate(series):
+            for g, s13 in frames.items():
+                if self.f0 <= g < self.f0 + self.E + 2:
+                    self.primitives[i].set_all_states(g - self.f0, s13)
+            self.primitives[i].clear_ext_f()
 
     def rows_dev(self, local_f, grad=False):
         import torch
@@ -348,9 +357,12 @@ class _Epoch:
 
 
 class MigratingSlabRank:
-    def __init__(self, cfg, rank, bounds, state, migrate_every, device=0, use_torch_stream=True, **sim_kw):
+    def __init__(self, cfg, rank, bounds, state, migrate_every, device=0, use_torch_stream=True, make_primitives=None, **sim_kw):
         import torch
         self.cfg, self.rank, self.bounds, self.E = cfg, rank, list(bounds), int(migrate_every)
+        self.make_primitives = make_primitives
+        self.series = []            # per primitive: {global frame: s13}, replayed into every new epoch handle
+        self.ext_carry = None       # wrench accumulated by earlier epoch handles since the last clear_ext_f
         self.n_ranks, self.device, self.use_torch_stream, self.sim_kw = len(bounds) - 1, device, use_torch_stream, sim_kw
         self.n_grid = int(128 * cfg.quality * 0.5)
         st = np.asarray(state, dtype=np.float64)
@@ -361,7 +373,9 @@ class MigratingSlabRank:
         ids = np.nonzero((col >= bounds[rank]) & (col < bounds[rank + 1]))[0]
         dev = f"cuda:{device}"
         rows = torch.as_tensor(st[ids].astype(np.float32), device=dev)
-        self.epochs = [_Epoch(cfg, rank, bounds, rows, torch.as_tensor(ids, device=dev), 0, self.E, device, use_torch_stream, sim_kw)]
+        self.epochs = [_Epoch(cfg, rank, bounds, rows, torch.as_tensor(ids, device=dev), 0, self.E, device, use_torch_stream, sim_kw, make_primitives)]
+        self.series = [dict() for _ in self.epochs[0].primitives]
+        self.ext_carry = np.zeros((len(self.series), 6))
         self.migrated = 0
         self._pool = {}             # particle count -> idle epoch handles (a repeated rollout re-uses them: no cudaMalloc / cudaFree)
 
@@ -379,8 +393,41 @@ class MigratingSlabRank:
             ep.f0, ep.gid = f0, gid
             ep.sim.clear_all_gradients()
             check(lib().smx_reset_dev(ep.sim._h, rows.contiguous().data_ptr()))
-            return ep
-        return _Epoch(self.cfg, self.rank, self.bounds, rows, gid, f0, self.E, self.device, self.use_torch_stream, self.sim_kw)
+        else:
+            ep = _Epoch(self.cfg, self.rank, self.bounds, rows, gid, f0, self.E, self.device, self.use_torch_stream, self.sim_kw, self.make_primitives)
+        if self.series:
+            for i in range(len(self.series)):               # the wrench accumulated so far stays with this rank
+                self.ext_carry[i] += self.epochs[-1].primitives[i].get_ext_f()
+            ep.load_primitive_states(self.series)
+        return ep
+
+    # primitive plumbing (global frames) --------------------------------------------------------------------------
+    def set_primitive_state(self, i, f0, f1, s13):
+        s13 = np.asarray(s13, dtype=np.float64)
+        for g in range(f0, f1):
+            self.series[i][g] = s13
+        for ep in self.epochs:
+            a, b = max(f0, ep.f0), min(f1, ep.f0 + self.E + 2)
+            if a < b:
+                ep.primitives[i].set_all_states(a - ep.f0, s13, f_end=b - ep.f0)
+
+    def clear_ext_f(self):
+        self.ext_carry[:] = 0
+        for p in self.epochs[-1].primitives:
+            p.clear_ext_f()
+
+    def ext_f(self, i):
+        return self.ext_carry[i] + self.epochs[-1].primitives[i].get_ext_f()
+
+    def primitive_state_grad(self, i, f0, f1):
+        """Sum over the global frames [f0, f1) of this rank's part of the primitive-state adjoint (frame g is collided against by
+        substep g, which ran in epoch g // E)."""
+        out = np.zeros(13)
+        for e, ep in enumerate(self.epochs):
+            a, b = max(f0, e * self.E), min(f1, (e + 1) * self.E)
+            if a < b:
+                out += ep.primitives[i].get_all_states_grad(a - ep.f0, f_end=b - ep.f0)
+        return out
 
     # epoch of substep f (input frame f) / of frame f (the latest epoch that holds it)
     def epoch_of_substep(self, f):
@@ -451,12 +498,39 @@ class _MigratingBase:
 class MigratingSlabCluster(_MigratingBase):
     """All ranks in ONE process on one device, with particle migration every `migrate_every` substeps (tests / single GPU)."""
 
-    def __init__(self, cfg, n_ranks, state, migrate_every, device=0, **sim_kw):
+    def __init__(self, cfg, n_ranks, state, migrate_every, device=0, make_primitives=None, **sim_kw):
         n_grid = int(128 * cfg.quality * 0.5)
         self.n, self.E = len(state), int(migrate_every)
         self.bounds = choose_bounds(np.asarray(state)[:, 0], n_ranks, n_grid)
-        self.ranks = [MigratingSlabRank(cfg, r, self.bounds, state, migrate_every, device=device, **sim_kw) for r in range(n_ranks)]
+        self.ranks = [MigratingSlabRank(cfg, r, self.bounds, state, migrate_every, device=device, make_primitives=make_primitives, **sim_kw)
+                      for r in range(n_ranks)]
         self._bwd_epoch = None
+
+    def _exchange_contact(self, eps):
+        for r in range(len(eps) - 1):
+            L, R = eps[r], eps[r + 1]
+            da = L.halo(1, "hi") - L.halo(2, "hi")          # own contact scatter = g_out - g_mix
+            db = R.halo(1, "lo") - R.halo(2, "lo")
+            L.halo(1, "hi").add_(db); R.halo(1, "lo").add_(da)
+
+    def set_primitive_state(self, i, f0, f1, s13):
+        for r in self.ranks:
+            r.set_primitive_state(i, f0, f1, s13)
+
+    def clear_ext_f(self):
+        for r in self.ranks:
+            r.clear_ext_f()
+
+    def ext_f(self, i):
+        return sum(r.ext_f(i) for r in self.ranks)
+
+    def set_ext_f_grad(self, i, g):
+        for r in self.ranks:
+            for ep in r.epochs:
+                ep.primitives[i].set_ext_f_grad(g)
+
+    def primitive_state_grad(self, i, f0, f1):
+        return sum(r.primitive_state_grad(i, f0, f1) for r in self.ranks)
 
     def _exchange(self, eps, which):
         for r in range(len(eps) - 1):
@@ -481,6 +555,10 @@ class MigratingSlabCluster(_MigratingBase):
         for ep in eps:
             check(lib().smx_substep_begin(ep.sim._h, lf))
         self._exchange(eps, 0)
+        if eps[0].has_contact():
+            for ep in eps:
+                check(lib().smx_substep_mid(ep.sim._h, lf))
+            self._exchange_contact(eps)
         for ep in eps:
             check(lib().smx_substep_end(ep.sim._h, lf))
         self._bwd_epoch = None
@@ -501,6 +579,10 @@ class MigratingSlabCluster(_MigratingBase):
         for ep in eps:
             check(lib().smx_substep_grad_begin(ep.sim._h, lf))
         self._exchange(eps, 3)
+        if eps[0].has_contact():
+            for ep in eps:
+                check(lib().smx_substep_grad_mid(ep.sim._h, lf))
+            self._exchange(eps, 4)
         for ep in eps:
             check(lib().smx_substep_grad_end(ep.sim._h, lf))
 
