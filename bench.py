@@ -60,6 +60,7 @@ def parse():
     ap.add_argument("--flags", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-e2e-pipeline", action="store_true", help="e2e arm on one handle only (no overlap of host I/O with the kernels of the other handle)")
     ap.add_argument("--cpu-sample-substeps", type=int, default=2)
     return ap.parse_args()
 
@@ -220,6 +221,16 @@ def cpu_baseline(args):
             "sample": f"{S} substeps forward + {S} backward at {args.n} particles, median of {reps} (variant A, f64 OpenMP restatement of the Taichi kernels)"}
 
 
+def P2(args, S):
+    """A second primitive container for the second handle of the pipelined end-to-end arm (variant B)."""
+    from softmac_b200.engine import Primitives, Mesh
+    t = variant_b_table()
+    m = Mesh(sdf=dict(sdf=t["sdf"], normal=t["normal"], position=(t["lower"], t["upper"]), dx=t["dx"]), cfg=dict(friction=0.5), max_timesteps=S + 2)
+    m.softness[None] = 666.
+    m.set_all_states(0, np.array(VARIANT_B_POSE), f_end=S + 2)
+    return Primitives(primitives=[m], max_timesteps=S + 2)
+
+
 # ------------------------------------------------------------------------------------------------------------
 def run_cuda(args, rank, world, local_rank):
     import torch
@@ -312,6 +323,47 @@ def run_cuda(args, rank, world, local_rank):
         e2e = {"value": world * args.batch * args.n * S / float(t.item()), "unit": UNIT, "h2d_bytes_per_step": args.batch * (args.n * 24 * 4 + args.n * 3 * 4),
                "d2h_bytes_per_step": args.batch * args.n * 6 * 4, "checksum": float(np.abs(xg).sum() + np.abs(vg).sum()),
                "api": "reset(state (n,24) f64) + add_x_grad + step + step_grad + get_grad(0) -> (x_bar, v_bar) f64"}
+        if not args.no_e2e_pipeline:
+            # The same calls, every step with its own host -> device upload and device -> host read-back, on TWO handles (two streams):
+            # while the kernels of step k run on one handle, the host converts / uploads the inputs of step k+1 into the other and reads
+            # back the result of step k-1 -- independent rollouts, the way config 4 runs them.
+            sim2 = MPMSimulator(cfg, Primitives(primitives=[], max_timesteps=S + 2) if not prims else P2(args, S), env_dt=5 * DT, device=local_rank,
+                                sort_every=args.sort_every, flags=args.flags, n_batch=args.batch)
+            pair = [sim, sim2]
+
+            def enqueue(h):
+                h.reset(st)
+                h.clear_all_gradients()
+                h.add_x_grad(S, seed)
+                h.step(0, S)
+                h.step_grad(S, S)
+
+            def sync_all():
+                barrier(); sim2.synchronize()
+            K = max(10, 2 * reps)
+            chk = 0.0
+            for r in range(2):                      # one warm-up pass, one timed pass of K steps
+                sync_all()
+                t0 = time.perf_counter()
+                enqueue(pair[0])
+                for k in range(1, K):
+                    enqueue(pair[k % 2])
+                    xg, vg = pair[(k - 1) % 2].get_grad(0)
+                xg, vg = pair[(K - 1) % 2].get_grad(0)
+                if dist:
+                    dist.all_reduce(gsum)
+                sync_all()
+                tp = (time.perf_counter() - t0) / K
+                chk = float(np.abs(xg).sum() + np.abs(vg).sum())
+            t = torch.tensor([tp], device="cuda", dtype=torch.float64)
+            if dist:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e["sequential_value"] = e2e["value"]
+            e2e["value"] = world * args.batch * args.n * S / float(t.item())
+            e2e["mode"] = (f"two handles, software-pipelined over {K} steps: upload of step k+1 and read-back of step k-1 overlap the kernels of step k; "
+                           "every step still uploads its own inputs and reads back its own result; sequential_value = one handle, one step at a time")
+            e2e["pipelined_checksum"] = chk
+            del sim2
 
     if rank == 0:
         peak, peak_src = peaks()
