@@ -240,6 +240,8 @@ def run_cuda(args, rank, world, local_rank):
     if world > 1:
         import torch.distributed as dist_
         dist = dist_
+        # NCCL prints its version banner (and any NCCL_DEBUG output) on stdout: keep stdout for the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/nccl_debug.%h.%p.log")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     S = args.substeps
     cfg = workload_cfg(args, S + 2)
