@@ -333,11 +333,13 @@ def run_cuda(args, rank, world, local_rank):
                                 sort_every=args.sort_every, flags=args.flags, n_batch=args.batch)
             pair = [sim, sim2]
 
-            def enqueue(h):
+            def start(h):                           # upload + forward substeps (asynchronous)
                 h.reset(st)
                 h.clear_all_gradients()
                 h.add_x_grad(S, seed)
                 h.step(0, S)
+
+            def finish(h):                          # backward substeps (waits for the forward: one look at the checkpoint counter)
                 h.step_grad(S, S)
 
             def sync_all():
@@ -347,10 +349,11 @@ def run_cuda(args, rank, world, local_rank):
             for r in range(2):                      # one warm-up pass, one timed pass of K steps
                 sync_all()
                 t0 = time.perf_counter()
-                enqueue(pair[0])
+                start(pair[0]); finish(pair[0])
                 for k in range(1, K):
-                    enqueue(pair[k % 2])
-                    xg, vg = pair[(k - 1) % 2].get_grad(0)
+                    start(pair[k % 2])                              # host conversion + H2D of step k overlap the backward of step k-1
+                    xg, vg = pair[(k - 1) % 2].get_grad(0)          # D2H + conversion of step k-1 overlap the forward of step k
+                    finish(pair[k % 2])
                 xg, vg = pair[(K - 1) % 2].get_grad(0)
                 if dist:
                     dist.all_reduce(gsum)
