@@ -124,6 +124,8 @@ struct smx_sim {
     bool ckpt_enabled = true, ckpt_dirty = true;
     unsigned long long ckpt_overflow_seen = 0;
     int ckpt_cap_hint = 1;
+    int* ckpt_need = nullptr;           // [max_steps] blocks the grid record of substep f needed (written by the saving kernel)
+    int ckpt_need_max = 0;              // largest need seen by a backward pass: sizes the arena at the next reset
     size_t ckpt_bytes = 0;
     std::vector<long long> ckpt_order;  // uid of the ordering the record of substep f was written in (-1: none)
     // SVD records (U, V, sigma - 1, J - 1 of the forward P2G of every substep) so that the adjoint does not repeat the SVD
@@ -375,7 +377,8 @@ static int ensure_ckpt(smx_sim* s, int f) {
         CK(cudaStreamSynchronize(s->stream));
         CK(cudaMemcpy(&nbk, o.nblocks, sizeof(int), cudaMemcpyDeviceToHost));
     }
-    int cap = (int)std::min<long long>(total, (long long)s->ckpt_cap_hint * (nbk + nbk / 2) + 64);
+    long long want = std::max<long long>((long long)s->ckpt_cap_hint * (nbk + nbk / 2) + 64, (long long)s->ckpt_need_max + s->ckpt_need_max / 8 + 64);
+    int cap = (int)std::min<long long>(total, want);
     int narr = s->has_contact() ? 3 : 2;
     if (s->ckpt && cap <= s->ckpt_cap && narr <= s->ckpt_narr) return SMX_OK;
     if (s->ckpt) { CK(cudaStreamSynchronize(s->stream)); cudaFree(s->ckpt); s->ckpt = nullptr; }
@@ -441,9 +444,9 @@ static int forward_grid(smx_sim* s, int f, bool accumulate, bool checkpoint) {
     }
     { const bool saved_pdl = s->pdl; s->pdl = s->pdl && s->pdl_grid;
     if (P.ctype == 0) launch_pdl(s, k_grid_op<true>, grid_blocks_launch(s), 256, 0, P, ps, f, s->dense ? nullptr : o.blocks, o.nblocks, s->g_in, s->g_out, contact ? s->g_mix : nullptr,
-                                                           accumulate ? 1 : 0, rec, s->ckpt_cap, contact ? 0 : 1, checkpoint ? 1 : 0, s->counters, near);
+                                                           accumulate ? 1 : 0, rec, s->ckpt_cap, contact ? 0 : 1, checkpoint ? 1 : 0, s->counters, near, s->ckpt_need + f);
     else launch_pdl(s, k_grid_op<false>, grid_blocks_launch(s), 256, 0, P, ps, f, s->dense ? nullptr : o.blocks, o.nblocks, s->g_in, s->g_out, contact ? s->g_mix : nullptr,
-                                                           accumulate ? 1 : 0, rec, s->ckpt_cap, contact ? 0 : 1, checkpoint ? 1 : 0, s->counters, near);
+                                                           accumulate ? 1 : 0, rec, s->ckpt_cap, contact ? 0 : 1, checkpoint ? 1 : 0, s->counters, near, s->ckpt_need + f);
     s->pdl = saved_pdl; }
     CKLN(s, "k_grid_op");
     if (checkpoint) s->g_in_clean_uid = o.uid;
@@ -460,7 +463,7 @@ static int forward_grid_save_contact(smx_sim* s, int f) {
     Order& o = s->orders[s->order_of[f]];
     if (!(s->has_contact() && s->ckpt && s->ckpt_narr == 3)) return SMX_OK;
     launch_pdl(s, k_ckpt_copy, grid_blocks_launch(s), 256, 0, s->dense ? nullptr : o.blocks, o.nblocks, s->B * s->P.nb3, s->ckpt_cap, s->ckpt + (size_t)f * s->ckpt_rec,
-                                                             nullptr, s->g_out, s->g_mix, 0, s->counters, nullptr, nullptr);
+                                                             nullptr, s->g_out, s->g_mix, 0, s->counters, nullptr, nullptr, s->ckpt_need + f);
     CKLN(s, "ckpt_save");
     s->ckpt_order[f] = o.uid; s->ckpt_contact[f] = 1;
     return SMX_OK;
@@ -653,6 +656,7 @@ int smx_create(const smx_config* cfg, smx_sim** out) {
     CK(cub::DeviceRadixSort::SortPairs(nullptr, s->cub_bytes, s->keys_a, s->keys_b, s->iota, s->iota, std::max(n, 1), 0, 32, s->stream));
     CK(cudaMalloc(&s->cub_tmp, s->cub_bytes));
     CK(cudaMalloc(&s->counters, 4 * sizeof(unsigned long long))); CK(cudaMemsetAsync(s->counters, 0, 4 * sizeof(unsigned long long), s->stream));
+    CK(cudaMalloc(&s->ckpt_need, (size_t)s->cfg.max_steps * sizeof(int))); CK(cudaMemsetAsync(s->ckpt_need, 0, (size_t)s->cfg.max_steps * sizeof(int), s->stream));
     CK(cudaMalloc(&s->prims_dev, SMX_MAXP * sizeof(PrimDev)));
     CK(cudaMalloc(&s->pstate, (size_t)B * SMX_MAXP * T * 13 * sizeof(float))); CK(cudaMemsetAsync(s->pstate, 0, (size_t)B * SMX_MAXP * T * 13 * sizeof(float), s->stream));
     CK(cudaMalloc(&s->pgrad, (size_t)B * SMX_MAXP * T * 13 * sizeof(double))); CK(cudaMemsetAsync(s->pgrad, 0, (size_t)B * SMX_MAXP * T * 13 * sizeof(double), s->stream));
@@ -697,7 +701,7 @@ int smx_destroy(smx_sim* s) {
     for (auto& p : s->prims) { cudaFree(p.sdf_dev); cudaFree(p.nrm_dev); }
     void* ptrs[] = {s->near_pool, s->svd_pool, s->ch_target, s->ch_loss, s->ckpt, s->pool, s->g_in, s->g_out, s->g_mix, s->gg_out, s->gg_out_b, s->gg_mix, s->g_lin, s->adj_cur, s->adj_nxt, s->stage_dev, s->keys_a, s->keys_b, s->iota, s->cub_tmp,
                     s->counters, s->prims_dev, s->pstate, s->pgrad, s->ext_f, s->ext_f_grad, s->abuf, s->gabuf, s->ctrl_id, s->action, s->action_grad,
-                    s->rig_arena, s->rig_enable, s->rig_masks};
+                    s->rig_arena, s->rig_enable, s->rig_masks, s->ckpt_need};
     for (void* p : ptrs) cudaFree(p);
     cudaFreeHost(s->stage_host);
     if (s->ev0) cudaEventDestroy(s->ev0);
@@ -761,6 +765,7 @@ static void reset_bookkeeping(smx_sim* s) {
     std::fill(s->near_order.begin(), s->near_order.end(), -1);
     s->adj_frame = -1; s->adj_order = -1;
     s->ckpt_dirty = true;
+    if (s->ckpt_need) cudaMemsetAsync(s->ckpt_need, 0, (size_t)s->cfg.max_steps * sizeof(int), s->stream);
     gc_orders(s);                       // every ordering is unreferenced now: recycle all of them
 }
 int smx_reset(smx_sim* s, const double* state, int32_t ncols) {
@@ -1284,9 +1289,15 @@ int smx_substep_grad_begin(smx_sim* s, int32_t f) {
         CK(cudaStreamSynchronize(s->stream));
         CK(cudaMemcpy(&ov, s->counters + 2, sizeof ov, cudaMemcpyDeviceToHost));
         if (ov != s->ckpt_overflow_seen) {
+            // some record did not fit (the active region grew): the substeps whose record is incomplete recompute their grid in the
+            // adjoint, the others keep using theirs; the arena is sized for the largest need at the next reset
             s->ckpt_overflow_seen = ov;
-            std::fill(s->ckpt_order.begin(), s->ckpt_order.end(), -1);      // recompute instead; grow the arena at the next reset
-            s->ckpt_cap_hint = 2;
+            std::vector<int> need(s->cfg.max_steps, 0);
+            CK(cudaMemcpy(need.data(), s->ckpt_need, need.size() * sizeof(int), cudaMemcpyDeviceToHost));
+            for (int g = 0; g < s->cfg.max_steps; g++) {
+                if (need[g] > s->ckpt_cap) s->ckpt_order[g] = -1;
+                s->ckpt_need_max = std::max(s->ckpt_need_max, need[g]);
+            }
         }
     }
     if (s->adj_frame != f + 1) {        // start of a backward pass: the adjoint of frame f+1 is its loss seed
@@ -1311,7 +1322,7 @@ int smx_substep_grad_begin(smx_sim* s, int32_t f) {
     } else if (have_rec) {
         // restore g_in / g_out (/ g_mix) and zero the adjoint grids of the same blocks in one launch
         launch_pdl(s, k_ckpt_copy, grid_blocks_launch(s), 256, 0, s->dense ? nullptr : ord.blocks, ord.nblocks, s->B * s->P.nb3, s->ckpt_cap, s->ckpt + (size_t)f * s->ckpt_rec,
-                                                                 s->g_in, s->g_out, contact ? s->g_mix : nullptr, 1, s->counters, gg, contact ? s->gg_mix : nullptr);
+                                                                 s->g_in, s->g_out, contact ? s->g_mix : nullptr, 1, s->counters, gg, contact ? s->gg_mix : nullptr, nullptr);
         CKLN(s, "ckpt_restore");
     } else {
         if (s->slab) return fail(SMX_ERR_STATE, "smx_substep_grad: slab decomposition needs the grid checkpoint of substep %d (run it forward in this handle; do not set SMX_FLAG_NO_GRID_CKPT)", f);
@@ -1679,7 +1690,7 @@ int smx_get_grid(smx_sim* s, float* g_in, float* g_out) {
             return fail(SMX_ERR_STATE, "smx_get_grid: g_in of substep %d was not retained (grid checkpoints disabled)", f);
         Order& o = s->orders[s->order_of[f]];
         launch_pdl(s, k_ckpt_copy, grid_blocks_launch(s), 256, 0, s->dense ? nullptr : o.blocks, o.nblocks, s->B * s->P.nb3, s->ckpt_cap, s->ckpt + (size_t)f * s->ckpt_rec,
-                                                                 s->g_in, nullptr, nullptr, 1, s->counters, nullptr, nullptr);
+                                                                 s->g_in, nullptr, nullptr, 1, s->counters, nullptr, nullptr, nullptr);
         CKL(s);
         s->g_in_clean_uid = -1;
     }

@@ -574,11 +574,12 @@ template <bool GC>
 __global__ void __launch_bounds__(256) k_grid_op(Params P, PrimSet ps, int f, const uint32_t* __restrict__ blocks, const int* __restrict__ nblocks,
                                                  float4* __restrict__ g_in, float4* __restrict__ g_out, float4* __restrict__ g_mix,
                                                  int accumulate, float4* __restrict__ rec, int cap, int save_out, int zero_in,
-                                                 unsigned long long* __restrict__ counters, uint32_t* __restrict__ near_count) {
+                                                 unsigned long long* __restrict__ counters, uint32_t* __restrict__ near_count, int* __restrict__ need = nullptr) {
     pdl_prologue();
     if (near_count && blockIdx.x == 0 && threadIdx.x == 0) *near_count = 0u;        // work list of the contact kernel that follows
     int total = blocks ? *nblocks : P.nbatch * P.nb3;
     if (rec && total > cap && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(counters + 2, 1ull);   // record does not fit
+    if (rec && need && blockIdx.x == 0 && threadIdx.x == 0) *need = total;          // blocks this substep's record needs (host: which substeps fit)
     for (int bi = blockIdx.x * 4 + (threadIdx.x >> 6); bi < total; bi += gridDim.x * 4) {
         uint32_t node = (blocks ? blocks[bi] : (uint32_t)bi) * 64u + (threadIdx.x & 63);
         float4 g = g_in[node];
@@ -1388,9 +1389,11 @@ __global__ void k_mark_blocks_sorted(Params P, const uint32_t* __restrict__ keys
 // record layout: [array][active-block slot][64 nodes]; `cap` = blocks reserved per array
 __global__ void __launch_bounds__(256) k_ckpt_copy(const uint32_t* __restrict__ blocks, const int* __restrict__ nblocks, int nb3, int cap,
                                                     float4* __restrict__ rec, float4* __restrict__ a, float4* __restrict__ b, float4* __restrict__ c, int restore,
-                                                    unsigned long long* __restrict__ counters, float4* __restrict__ zero_a = nullptr, float4* __restrict__ zero_b = nullptr) {
+                                                    unsigned long long* __restrict__ counters, float4* __restrict__ zero_a = nullptr, float4* __restrict__ zero_b = nullptr,
+                                                    int* __restrict__ need = nullptr) {
     pdl_prologue();
     int total = blocks ? *nblocks : nb3;
+    if (need && !restore && blockIdx.x == 0 && threadIdx.x == 0) *need = total;
     if (total > cap) {      // record does not fit: flagged, the host falls back to recomputation (counters[2])
         if (blockIdx.x == 0 && threadIdx.x == 0 && !restore) atomicAdd(counters + 2, 1ull);
         total = cap;

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import scenes
-from harness import Pair, rel_l2, cosine, prim_states_for
+from harness import Pair, rel_l2, cosine, prim_states_for, sim_cfg
 
 pytestmark = pytest.mark.gpu
 
@@ -290,6 +290,41 @@ def test_grid_checkpoint_and_recompute_adjoints_agree():
     (ga, pa), (gb, pb) = run(0), run(8)
     assert np.abs(ga).max() > 0 and np.abs(pa).max() > 0
     assert rel_l2(ga, gb) <= 1e-5 and rel_l2(pa, pb) <= 1e-4
+
+
+def test_grid_checkpoint_overflow_invalidates_only_the_substeps_that_did_not_fit():
+    """An exploding blob: the active region outgrows the checkpoint arena (sized from the first substep) halfway through the rollout.
+    The substeps whose record did not fit recompute their grid in the adjoint, the earlier ones keep restoring theirs (fewer
+    launches than recomputing everything), the gradient equals the all-recompute run, and after the next reset the arena is large
+    enough for every substep."""
+    from softmac_b200.engine import MPMSimulator
+    n, steps = 6000, 16
+    rng = np.random.default_rng(77)
+    st = scenes.blob_state(n, rng, center=(0.5, 0.5, 0.5), width=0.08, vel=0.0, Fdev=0.0, Cdev=0.0)
+    st[:, 3:6] = 40.0 * (st[:, :3] - 0.5) / 0.04                       # radial burst: +-8 cells in 16 substeps
+    st = st.astype(np.float32).astype(np.float64)
+    seed = rng.normal(size=(n, 3))
+
+    def run(fl, episodes=1):
+        sim = MPMSimulator(sim_cfg(n, n_grid=64, max_steps=steps + 2, gravity=(0., 0., 0.)), (), env_dt=1e-3, sort_every=2, flags=fl)
+        out = []
+        for _ in range(episodes):
+            sim.reset(st)
+            for f in range(steps):
+                sim.substep(f)
+            blocks = sim.counters()["active_blocks"]
+            sim.clear_all_gradients(); sim.add_x_grad(steps, seed)
+            l0 = sim.launch_count()
+            for f in range(steps - 1, -1, -1):
+                sim.substep_grad(f)
+            out.append((sim.get_state_grad(0), sim.launch_count() - l0, blocks))
+        return out
+
+    (g_rec, l_rec, blocks), (g_rec2, l_rec2, _) = run(0, episodes=2)
+    (g_all, l_all, _), = run(8)
+    assert blocks > 170                                                  # started from <= 64 active blocks: the first arena held <= 160
+    assert np.abs(g_all).max() > 0 and rel_l2(g_rec, g_all) <= 1e-5 and rel_l2(g_rec2, g_all) <= 1e-5
+    assert l_rec2 < l_rec < l_all                                        # partial fallback < full recomputation; none after the arena grew
 
 
 @pytest.mark.parametrize("flags", [64, 128, 64 + 128])
