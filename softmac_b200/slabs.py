@@ -679,7 +679,7 @@ def exchange_back(dist, rank, world, to_lo, to_hi, n_from_lo, n_from_hi):
 class DistMigratingSlab(_MigratingBase):
     """One rank per process (torchrun, NCCL) with particle migration every `migrate_every` substeps."""
 
-    def __init__(self, cfg, state, migrate_every, device=None, **sim_kw):
+    def __init__(self, cfg, state, migrate_every, device=None, make_primitives=None, **sim_kw):
         import torch
         import torch.distributed as dist
         self.dist = dist
@@ -688,9 +688,47 @@ class DistMigratingSlab(_MigratingBase):
         n_grid = int(128 * cfg.quality * 0.5)
         self.n, self.E = len(state), int(migrate_every)
         self.bounds = choose_bounds(np.asarray(state)[:, 0], self.world, n_grid)
-        self.r = MigratingSlabRank(cfg, self.rank, self.bounds, state, migrate_every, device=self.device, **sim_kw)
+        self.r = MigratingSlabRank(cfg, self.rank, self.bounds, state, migrate_every, device=self.device, make_primitives=make_primitives, **sim_kw)
         self._tmp = {}
         self._bwd_epoch = None
+
+    def _exchange_contact(self, ep):
+        import torch
+        dist, ops, pend = self.dist, [], []
+        for side, peer in (("lo", self.rank - 1), ("hi", self.rank + 1)):
+            if 0 <= peer < self.world:
+                own = ep.halo(1, side) - ep.halo(2, side)            # own contact scatter = g_out - g_mix
+                t = self._tmp.setdefault(("c", side), torch.empty_like(own))
+                ops += [dist.P2POp(dist.isend, own, peer), dist.P2POp(dist.irecv, t, peer)]
+                pend.append((ep.halo(1, side), t))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+            for v, t in pend:
+                v.add_(t)
+
+    def _allreduce(self, a):
+        import torch
+        t = torch.as_tensor(np.asarray(a, dtype=np.float64), device=f"cuda:{self.device}")
+        self.dist.all_reduce(t)
+        return t.cpu().numpy()
+
+    # primitives: states replicated on every rank, wrench and primitive-state adjoints are sums over ranks (and epochs)
+    def set_primitive_state(self, i, f0, f1, s13):
+        self.r.set_primitive_state(i, f0, f1, s13)
+
+    def clear_ext_f(self):
+        self.r.clear_ext_f()
+
+    def ext_f(self, i):
+        return self._allreduce(self.r.ext_f(i))
+
+    def set_ext_f_grad(self, i, g):
+        for ep in self.r.epochs:
+            ep.primitives[i].set_ext_f_grad(g)
+
+    def primitive_state_grad(self, i, f0, f1):
+        return self._allreduce(self.r.primitive_state_grad(i, f0, f1))
 
     def _exchange(self, ep, which):
         import torch
@@ -714,6 +752,9 @@ class DistMigratingSlab(_MigratingBase):
         ep, lf = self.r.epoch_of_substep(f), self._local(f)
         check(lib().smx_substep_begin(ep.sim._h, lf))
         self._exchange(ep, 0)
+        if ep.has_contact():
+            check(lib().smx_substep_mid(ep.sim._h, lf))
+            self._exchange_contact(ep)
         check(lib().smx_substep_end(ep.sim._h, lf))
         self._bwd_epoch = None
 
@@ -727,6 +768,9 @@ class DistMigratingSlab(_MigratingBase):
         ep, lf = self.r.epochs[e], self._local(f)
         check(lib().smx_substep_grad_begin(ep.sim._h, lf))
         self._exchange(ep, 3)
+        if ep.has_contact():
+            check(lib().smx_substep_grad_mid(ep.sim._h, lf))
+            self._exchange(ep, 4)
         check(lib().smx_substep_grad_end(ep.sim._h, lf))
 
     def step(self, s0, count):

@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--migrate-every", type=int, default=0, help="re-establish particle ownership every E substeps (particle migration "
                     "between slab ranks over NCCL P2P); 0: ownership fixed at reset")
+    ap.add_argument("--sphere", action="store_true", help="(with --check) a sphere primitive on the slab boundary: forecast contact, wrench summed over ranks")
     ap.add_argument("--drift", type=float, default=0.0, help="add this x-velocity (m/s) to every particle so that material streams through the slab boundaries")
     args = ap.parse_args()
     import torch
@@ -53,10 +54,26 @@ def main():
         st[:, 3] += np.float32(args.drift)
     seed = st[:, :3] - st[:, :3].mean(0)
     E = args.migrate_every
+    make_prims, s13 = None, None
+    if args.sphere:
+        from softmac_b200.engine import Primitives, Mesh
+        tab = scenes.sphere_table()
+        s13 = np.concatenate([[0.5, 0.3 - 0.39 / 2 - 0.05, 0.5], [1, 0, 0, 0], [0.0, 0.2, 0.0], [0, 0, 0.3]])     # just under the cube, moving up into it
+
+        def make_prims():
+            m = Mesh(sdf=dict(sdf=tab["sdf"], normal=tab["normal"], position=(tab["lower"], tab["upper"]), dx=tab["dx"]), cfg=dict(friction=0.5), max_timesteps=S + 2)
+            p = Primitives(primitives=[m], max_timesteps=S + 2)
+            p.initialize()
+            return p
     if ws > 1 and E:
-        sl = DistMigratingSlab(cfg, st, E, env_dt=5 * dt, sort_every=args.sort_every)
+        sl = DistMigratingSlab(cfg, st, E, env_dt=5 * dt, sort_every=args.sort_every, make_primitives=make_prims)
     elif ws > 1:
-        sl = DistSlab(cfg, st, env_dt=5 * dt, sort_every=args.sort_every)
+        sl = DistSlab(cfg, st, env_dt=5 * dt, sort_every=args.sort_every, make_primitives=make_prims)
+    if args.sphere and ws > 1:
+        if E:
+            sl.set_primitive_state(0, 0, S + 2, s13); sl.clear_ext_f()
+        else:
+            sl.primitives[0].set_all_states(0, s13, f_end=S + 2); sl.primitives[0].clear_ext_f()
     else:
         from softmac_b200.slabs import SlabCluster
         sl = None
@@ -121,11 +138,29 @@ def main():
         out["local_particles_last_epoch"] = int(sl.r.epochs[-1].n)
     if args.check and ws > 1:
         got = sl.gather_state(S)
+        if args.sphere:                 # the timed loop ran forward + backward several times: one clean forward for the wrench
+            if migrating:
+                sl.rewind(); sl.clear_all_gradients(); sim.copyframe(E + 1, 0)
+            else:
+                sim.copyframe(S + 1, 0)
+            sl.clear_ext_f() if migrating else sl.primitives[0].clear_ext_f()
+            sl.step(0, S)
+            wrench = sl.ext_f(0)
+            got = sl.gather_state(S)
         if rank == 0:
-            ref = MPMSimulator(cfg, (), env_dt=5 * dt, sort_every=args.sort_every, device=local)
+            pr = make_prims() if args.sphere else ()
+            ref = MPMSimulator(cfg, pr, env_dt=5 * dt, sort_every=args.sort_every, device=local)
+            if args.sphere:
+                pr[0].set_all_states(0, s13, f_end=S + 2)
             ref.reset(st)
+            if args.sphere:
+                pr[0].clear_ext_f()
             ref.step(0, S)
             r = ref.get_state(S)
+            if args.sphere:
+                fe = pr[0].get_ext_f()
+                out["check_wrench_rel_l2"] = rel_l2(wrench, fe); out["wrench_norm"] = float(np.linalg.norm(fe))
+                assert out["wrench_norm"] > 0 and out["check_wrench_rel_l2"] <= 1e-3, out
             out["check_rel_l2_x"] = rel_l2(got[:, :3], r[:, :3]); out["check_rel_l2_v"] = rel_l2(got[:, 3:6], r[:, 3:6])
             out["check_rel_l2_F"] = rel_l2(got[:, 6:15], r[:, 6:15])
             assert out["check_rel_l2_x"] <= 1e-6 and out["check_rel_l2_v"] <= 5e-5 and out["check_rel_l2_F"] <= 5e-5, out
