@@ -5,7 +5,8 @@ The reference builds everything from a yacs cfg (URDF + trimesh primitives, Jade
 of scope, so the components are passed in: any simulator with the ``MPMSimulator``
 surface, a ``Primitives`` container, a rigid simulator with the ``RigidSimulator`` surface and an optional loss with
 ``compute_loss(f)`` / ``seed(f)``.  The control flow -- which is what couples the MPM hot path to the rigid
-simulator -- is the reference's, line for line (taichi_env.py:93-151).
+simulator -- is the reference's (taichi_env.py:93-151); the only change is that the substeps of an env step go down in one
+native call (``simulator.step`` / ``step_grad``) when the simulator offers it and no per-substep MPM action is involved.
 """
 import numpy as np
 
@@ -50,8 +51,12 @@ class TaichiEnv:
         mpm_action = action if self.control_mode == "mpm" else None
         rigid_action = action if self.control_mode == "rigid" else None
         self.action_list.append(action)
-        for s in range(start, self.simulator.cur):
-            self.simulator.substep(s, mpm_action)
+        if mpm_action is None and hasattr(self.simulator, "step"):
+            # the same substeps in ONE native call (smx_step: identical results, the G2P of a substep fused into the next P2G)
+            self.simulator.step(start, self.substeps)
+        else:
+            for s in range(start, self.simulator.cur):
+                self.simulator.substep(s, mpm_action)
         self.rigid_simulator.step(start // self.substeps, rigid_action)
         if self._is_copy:
             self.simulator.copyframe(self.simulator.cur, 0)
@@ -70,10 +75,17 @@ class TaichiEnv:
         rigid_action = action if self.control_mode == "rigid" else None
         rigid_action_grad, ext_f_grad_list = self.rigid_simulator.step_grad(self.simulator.cur // self.substeps, rigid_action)
         mpm_action_grad = np.zeros(np.shape(action)) if action is not None else None
-        for s in range(start - 1, self.simulator.cur - 1, -1):
-            tmp = self.simulator.substep_grad(s, action=mpm_action, ext_f_grad=ext_f_grad_list if ext_f_grad_list else None)
-            if tmp is not None:
-                mpm_action_grad += tmp
+        if mpm_action is None and hasattr(self.simulator, "step_grad"):
+            # substep_grad re-sends the same wrench adjoint before every substep (mpm_simulator.py:344-346): once is enough
+            if ext_f_grad_list:
+                for i in range(self.simulator.n_primitive):
+                    self.simulator.primitives[i].set_ext_f_grad(ext_f_grad_list[i])
+            self.simulator.step_grad(start, self.substeps)
+        else:
+            for s in range(start - 1, self.simulator.cur - 1, -1):
+                tmp = self.simulator.substep_grad(s, action=mpm_action, ext_f_grad=ext_f_grad_list if ext_f_grad_list else None)
+                if tmp is not None:
+                    mpm_action_grad += tmp
         if action is None:
             return None
         return mpm_action_grad if self.control_mode == "mpm" else rigid_action_grad
