@@ -1593,8 +1593,9 @@ int smx_chamfer_loss(smx_sim* s, int32_t f, double weight, double* loss_out) {
     }
     CK(cudaMemsetAsync(s->ch_loss, 0, sizeof(double), s->stream));
     const uint32_t* perm = s->orders[s->order_of[f]].perm;
-    k_chamfer<<<nblk(n, 128), 128, 0, s->stream>>>(s->P, s->frame_ptr(f), perm, s->ch_target, s->ch_m, (float)weight, it->second.dev, it->second.ncols, s->ch_loss, 0); CKL(s);
-    k_chamfer<<<nblk((long long)s->B * s->ch_m, 128), 128, 0, s->stream>>>(s->P, s->frame_ptr(f), perm, s->ch_target, s->ch_m, (float)weight, it->second.dev, it->second.ncols, s->ch_loss, 1); CKL(s);
+    const int per_cta = 128 / SMX_CH_SPLIT;        // queries per CTA (SMX_CH_SPLIT lanes share one query)
+    k_chamfer<<<dim3(nblk(s->P.npb, per_cta), s->B), 128, 0, s->stream>>>(s->P, s->frame_ptr(f), perm, s->ch_target, s->ch_m, (float)weight, it->second.dev, it->second.ncols, s->ch_loss, 0); CKL(s);
+    k_chamfer<<<dim3(nblk(s->ch_m, per_cta), s->B), 128, 0, s->stream>>>(s->P, s->frame_ptr(f), perm, s->ch_target, s->ch_m, (float)weight, it->second.dev, it->second.ncols, s->ch_loss, 1); CKL(s);
     CK(cudaMemcpyAsync(loss_out, s->ch_loss, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
     return SMX_OK;

@@ -1486,67 +1486,69 @@ __global__ void k_sum_prim_grads(const double* __restrict__ pgrad, double* __res
 // seed: (n, ncols) AoS in particle-id order (the library's loss-seed buffer of the frame), accumulated with atomics.
 // ------------------------------------------------------------------------------------------------
 #define SMX_CH_TILE 512
+#define SMX_CH_SPLIT 8      // lanes that share one query: each scans every 8th candidate, then a (distance, index) min over the 8 lanes
+// lexicographic (distance, index) minimum over the SMX_CH_SPLIT lanes of a query group: equal to a serial scan in index order with
+// a strict `<` (the smallest index among equal distances wins)
+__device__ __forceinline__ void chamfer_group_min(float& best, uint32_t& bi) {
+#pragma unroll
+    for (int o = SMX_CH_SPLIT / 2; o > 0; o >>= 1) {
+        float d = __shfl_xor_sync(0xffffffffu, best, o);
+        uint32_t i = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (d < best || (d == best && i < bi)) { best = d; bi = i; }
+    }
+}
+// grid: (ceil(queries / 16), nbatch).  pass 0: queries = the particles of rollout blockIdx.y, candidates = the m targets;
+// pass 1: queries = the m targets, candidates = the particles of rollout blockIdx.y (index = particle id: ties go to the smallest id).
 __global__ void __launch_bounds__(128) k_chamfer(Params P, const float* __restrict__ fr, const uint32_t* __restrict__ perm, const float* __restrict__ tgt, int m,
                                                  float weight, float* __restrict__ seed, int ncols, double* __restrict__ loss, int pass) {
     __shared__ float4 tile[SMX_CH_TILE];
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pass == 0) {
-        bool live = t < P.n;
-        int j = live ? t : P.n - 1;
-        V3 xq = load_x(fr, P.stride, j);
-        float x = xq.x, y = xq.y, z = xq.z;
-        float best = 3.0e38f; int bi = 0;
-        for (int base = 0; base < m; base += SMX_CH_TILE) {
-            int cnt = min(SMX_CH_TILE, m - base);
-            __syncthreads();
-            for (int e = threadIdx.x; e < cnt; e += blockDim.x) tile[e] = make_float4(tgt[3 * (base + e)], tgt[3 * (base + e) + 1], tgt[3 * (base + e) + 2], 0.f);
-            __syncthreads();
-            for (int e = 0; e < cnt; e++) {
-                float dx = x - tile[e].x, dy = y - tile[e].y, dz = z - tile[e].z;
-                float d = dx * dx + dy * dy + dz * dz;
-                if (d < best) { best = d; bi = base + e; }
+    const int b = blockIdx.y, part = threadIdx.x % SMX_CH_SPLIT;
+    const int q = blockIdx.x * (128 / SMX_CH_SPLIT) + threadIdx.x / SMX_CH_SPLIT;     // query handled by this group of lanes
+    const int j0 = b * P.npb;
+    const int nq = pass == 0 ? P.npb : m, nc = pass == 0 ? m : P.npb;
+    const bool live = q < nq;
+    const int qq = live ? q : nq - 1;
+    float x, y, z;
+    if (pass == 0) { V3 xq = load_x(fr, P.stride, j0 + qq); x = xq.x; y = xq.y; z = xq.z; }
+    else { x = tgt[3 * qq]; y = tgt[3 * qq + 1]; z = tgt[3 * qq + 2]; }
+    float best = 3.0e38f; uint32_t bi = 0xffffffffu; int bslot = 0;
+    for (int base = 0; base < nc; base += SMX_CH_TILE) {
+        const int cnt = min(SMX_CH_TILE, nc - base);
+        __syncthreads();
+        for (int e = threadIdx.x; e < cnt; e += blockDim.x) {
+            if (pass == 0) tile[e] = make_float4(tgt[3 * (base + e)], tgt[3 * (base + e) + 1], tgt[3 * (base + e) + 2], __uint_as_float((uint32_t)(base + e)));
+            else {
+                V3 c = load_x(fr, P.stride, j0 + base + e);
+                tile[e] = make_float4(c.x, c.y, c.z, __uint_as_float(perm ? perm[j0 + base + e] : (uint32_t)(j0 + base + e)));
             }
         }
-        float part = 0.f;
-        if (live) {
-            uint32_t id = perm ? perm[j] : (uint32_t)j;
-            float dx = x - tgt[3 * bi], dy = y - tgt[3 * bi + 1], dz = z - tgt[3 * bi + 2];
-            atomicAdd(seed + (size_t)id * ncols, 2.f * weight * dx); atomicAdd(seed + (size_t)id * ncols + 1, 2.f * weight * dy);
-            atomicAdd(seed + (size_t)id * ncols + 2, 2.f * weight * dz);
-            part = dx * dx + dy * dy + dz * dz;
+        __syncthreads();
+        for (int e = part; e < cnt; e += SMX_CH_SPLIT) {
+            const float4 c = tile[e];
+            const float dx = x - c.x, dy = y - c.y, dz = z - c.z;
+            const float d = dx * dx + dy * dy + dz * dz;
+            const uint32_t id = __float_as_uint(c.w);
+            if (d < best || (d == best && id < bi)) { best = d; bi = id; bslot = base + e; }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-        if ((threadIdx.x & 31) == 0) atomicAdd(loss, (double)(weight * part));
-    } else {
-        // one thread per (batch, target): nearest particle of that batch; ties go to the smallest particle id
-        bool live = t < P.nbatch * m;
-        int tt = live ? t : 0;
-        int b = tt / m, i = tt - b * m;
-        float tx = tgt[3 * i], ty = tgt[3 * i + 1], tz = tgt[3 * i + 2];
-        float best = 3.0e38f; uint32_t bid = 0xffffffffu; int bj = 0;
-        int j0 = b * P.npb, j1 = j0 + P.npb;
-        {
-            for (int j = j0; j < j1; j++) {     // particle coordinates are read straight from the frame (L1/L2 resident, warp-uniform address)
-                V3 xq = load_x(fr, P.stride, j);
-                float dx = xq.x - tx, dy = xq.y - ty, dz = xq.z - tz;
-                float d = dx * dx + dy * dy + dz * dz;
-                uint32_t id = perm ? perm[j] : (uint32_t)j;
-                if (d < best || (d == best && id < bid)) { best = d; bid = id; bj = j; }
-            }
-        }
-        float part = 0.f;
-        if (live && P.npb > 0) {
-            V3 xq = load_x(fr, P.stride, bj);
-            float dx = xq.x - tx, dy = xq.y - ty, dz = xq.z - tz;
-            atomicAdd(seed + (size_t)bid * ncols, 2.f * weight * dx); atomicAdd(seed + (size_t)bid * ncols + 1, 2.f * weight * dy);
-            atomicAdd(seed + (size_t)bid * ncols + 2, 2.f * weight * dz);
-            part = dx * dx + dy * dy + dz * dz;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-        if ((threadIdx.x & 31) == 0) atomicAdd(loss, (double)(weight * part));
     }
+    // which lane holds the winner: after the group minimum every lane knows (best, bi); the owner contributes the seed
+    const float my_best = best; const uint32_t my_bi = bi;
+    chamfer_group_min(best, bi);
+    float partial = 0.f;
+    if (live && nc > 0 && my_best == best && my_bi == bi) {
+        // pass 0: d loss / d x_q = 2 w (x_q - t_nn);  pass 1: d loss / d x_nn = 2 w (x_nn - t_q)
+        float cx, cy, cz; uint32_t row;
+        if (pass == 0) { cx = tgt[3 * bslot]; cy = tgt[3 * bslot + 1]; cz = tgt[3 * bslot + 2]; row = perm ? perm[j0 + q] : (uint32_t)(j0 + q); }
+        else { V3 c = load_x(fr, P.stride, j0 + bslot); cx = c.x; cy = c.y; cz = c.z; row = bi; }
+        const float sgn = pass == 0 ? 1.f : -1.f;
+        const float dx = sgn * (x - cx), dy = sgn * (y - cy), dz = sgn * (z - cz);
+        atomicAdd(seed + (size_t)row * ncols, 2.f * weight * dx); atomicAdd(seed + (size_t)row * ncols + 1, 2.f * weight * dy);
+        atomicAdd(seed + (size_t)row * ncols + 2, 2.f * weight * dz);
+        partial = dx * dx + dy * dy + dz * dz;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) partial += __shfl_xor_sync(0xffffffffu, partial, o);
+    if ((threadIdx.x & 31) == 0 && partial != 0.f) atomicAdd(loss, (double)(weight * partial));
 }
 // Primitive.forward_kinematics and its adjoint (primitive_base.py:280-283, primitive_utils.py:20-40); one thread
 __global__ void k_forward_kinematics(float* __restrict__ pstate, int T, int np, int nbatch, int f, float dt) {
