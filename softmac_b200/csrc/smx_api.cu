@@ -126,6 +126,7 @@ struct smx_sim {
     int ckpt_cap_hint = 1;
     int* ckpt_need = nullptr;           // [max_steps] blocks the grid record of substep f needed (written by the saving kernel)
     int ckpt_need_max = 0;              // largest need seen by a backward pass: sizes the arena at the next reset
+    int defer_save = -1;                // substep whose post-contact g_out / g_mix are saved by the NEXT substep's k_grid_op (smx_step)
     size_t ckpt_bytes = 0;
     std::vector<long long> ckpt_order;  // uid of the ordering the record of substep f was written in (-1: none)
     // SVD records (U, V, sigma - 1, J - 1 of the forward P2G of every substep) so that the adjoint does not repeat the SVD
@@ -442,13 +443,18 @@ static int forward_grid(smx_sim* s, int f, bool accumulate, bool checkpoint) {
         if (!s->near_pool && cudaMalloc(&s->near_pool, (size_t)s->cfg.max_steps * s->near_rec() * sizeof(uint32_t)) != cudaSuccess) { cudaGetLastError(); s->near_pool = nullptr; }
         near = s->near_pool ? s->near_of(f) : nullptr;
     }
+    // the previous substep of a fused smx_step sequence left its post-contact record to this launch (same ordering, same block list)
+    float4* rec_prev = nullptr;
+    if (checkpoint && s->defer_save == f - 1 && f > 0 && s->ckpt && s->order_of[f - 1] == s->order_of[f]) rec_prev = s->ckpt + (size_t)(f - 1) * s->ckpt_rec;
     { const bool saved_pdl = s->pdl; s->pdl = s->pdl && s->pdl_grid;
     if (P.ctype == 0) launch_pdl(s, k_grid_op<true>, grid_blocks_launch(s), 256, 0, P, ps, f, s->dense ? nullptr : o.blocks, o.nblocks, s->g_in, s->g_out, contact ? s->g_mix : nullptr,
-                                                           accumulate ? 1 : 0, rec, s->ckpt_cap, contact ? 0 : 1, checkpoint ? 1 : 0, s->counters, near, s->ckpt_need + f);
+                                                           accumulate ? 1 : 0, rec, s->ckpt_cap, contact ? 0 : 1, checkpoint ? 1 : 0, s->counters, near, s->ckpt_need + f, rec_prev);
     else launch_pdl(s, k_grid_op<false>, grid_blocks_launch(s), 256, 0, P, ps, f, s->dense ? nullptr : o.blocks, o.nblocks, s->g_in, s->g_out, contact ? s->g_mix : nullptr,
-                                                           accumulate ? 1 : 0, rec, s->ckpt_cap, contact ? 0 : 1, checkpoint ? 1 : 0, s->counters, near, s->ckpt_need + f);
+                                                           accumulate ? 1 : 0, rec, s->ckpt_cap, contact ? 0 : 1, checkpoint ? 1 : 0, s->counters, near, s->ckpt_need + f, rec_prev);
     s->pdl = saved_pdl; }
     CKLN(s, "k_grid_op");
+    if (rec_prev) { s->ckpt_order[f - 1] = o.uid; s->ckpt_contact[f - 1] = 1; }
+    if (checkpoint) s->defer_save = -1;
     if (checkpoint) s->g_in_clean_uid = o.uid;
     if (contact && P.n > 0) {
         float life = 1.0f / (float)(P.substeps - f % P.substeps);      // mpm_simulator.py:425 (f32 in the reference too)
@@ -765,6 +771,7 @@ static void reset_bookkeeping(smx_sim* s) {
     std::fill(s->near_order.begin(), s->near_order.end(), -1);
     s->adj_frame = -1; s->adj_order = -1;
     s->ckpt_dirty = true;
+    s->defer_save = -1;
     if (s->ckpt_need) cudaMemsetAsync(s->ckpt_need, 0, (size_t)s->cfg.max_steps * sizeof(int), s->stream);
     gc_orders(s);                       // every ordering is unreferenced now: recycle all of them
 }
@@ -1485,11 +1492,15 @@ int smx_step(smx_sim* s, int32_t s0, int32_t count) {
         }
         TRY(smx_substep_mid(s, f));
         s->mid_done = -1;
-        TRY(forward_grid_save_contact(s, f));
         s->last_fwd = f;
         bool resort_next = s->cfg.sort_every > 0 && (f + 1) % s->cfg.sort_every == 0 && !(s->cfg.flags & SMX_FLAG_NO_SORT);
         bool last = (i == count - 1);
-        if (!last && !resort_next && f + 2 < s->cfg.max_steps && !s->ckpt_dirty) { pending_g2p = true; continue; }
+        const bool fuse_next = !last && !resort_next && f + 2 < s->cfg.max_steps && !s->ckpt_dirty;
+        // with contact the record of g_out / g_mix can only be taken after the contact scatter: when the next substep follows in this
+        // call with the same ordering, its k_grid_op saves them just before overwriting them (no copy launch); otherwise copy now
+        if (fuse_next && s->has_contact() && s->ckpt && s->ckpt_narr == 3) s->defer_save = f;
+        else TRY(forward_grid_save_contact(s, f));
+        if (fuse_next) { pending_g2p = true; continue; }
         launch_pdl(s, k_g2p, nblk(s->P.n, SMX_TPB), SMX_TPB, 0, s->P, s->frame_ptr(f), s->frame_ptr(f + 1), s->g_out, s->pf_g2p); CKLN(s, "k_g2p");
         if (resort_next) TRY(resort(s, f + 1, true));
     }

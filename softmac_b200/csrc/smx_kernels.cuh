@@ -574,7 +574,10 @@ template <bool GC>
 __global__ void __launch_bounds__(256) k_grid_op(Params P, PrimSet ps, int f, const uint32_t* __restrict__ blocks, const int* __restrict__ nblocks,
                                                  float4* __restrict__ g_in, float4* __restrict__ g_out, float4* __restrict__ g_mix,
                                                  int accumulate, float4* __restrict__ rec, int cap, int save_out, int zero_in,
-                                                 unsigned long long* __restrict__ counters, uint32_t* __restrict__ near_count, int* __restrict__ need = nullptr) {
+                                                 unsigned long long* __restrict__ counters, uint32_t* __restrict__ near_count, int* __restrict__ need = nullptr,
+                                                 float4* __restrict__ rec_prev = nullptr) {
+    // rec_prev: grid record of the PREVIOUS substep (same ordering): its g_out / g_mix (final after that substep's contact scatter) are
+    // saved here, node by node, just before this substep overwrites them -- instead of a separate copy launch
     pdl_prologue();
     if (near_count && blockIdx.x == 0 && threadIdx.x == 0) *near_count = 0u;        // work list of the contact kernel that follows
     int total = blocks ? *nblocks : P.nbatch * P.nb3;
@@ -607,6 +610,11 @@ __global__ void __launch_bounds__(256) k_grid_op(Params P, PrimSet ps, int f, co
             int mask;
             v = boundary_condition(i, j, k, v, P, mask);
             o = make_float4(v.x, v.y, v.z, 1.f);
+        }
+        if (rec_prev && bi < cap) {
+            size_t slot = (size_t)bi * 64 + (threadIdx.x & 63);
+            rec_prev[(size_t)cap * 64 + slot] = g_out[node];
+            if (g_mix) rec_prev[(size_t)2 * cap * 64 + slot] = g_mix[node];
         }
         g_out[node] = o;
         if (g_mix) g_mix[node] = o;
