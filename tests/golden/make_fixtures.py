@@ -128,3 +128,40 @@ def demo_targets():
 
 if __name__ == "__main__" and "--targets" in sys.argv:
     demo_targets()
+
+
+def demo_meshes():
+    """tests/golden/demo_meshes.npz: the collision meshes and rigid-body parameters of the demo_grip / demo_pour assets as ARRAYS
+    (vertices f64, triangles int32; joint type / origin / axis / mass per body read from the URDFs) -- the inputs
+    tests/scenes.py:write_demo_assets turns back into OBJ + URDF files in a scratch directory for the URDF-driven builders."""
+    import xml.etree.ElementTree as ET
+    from oracle.sdf_builder import load_obj
+    out = {}
+    for name, urdf in (("gripper", "assets/gripper/gripper.urdf"), ("glass", "assets/glass/glass.urdf"), ("bowl", "assets/bowl/bowl.urdf")):
+        root = ET.parse(os.path.join(REF, urdf)).getroot()
+        joints = {j.find("child").attrib["link"]: j for j in root.findall("joint")}
+        links, meshes = [], {}
+        for link in root.findall("link"):
+            m = link.find("collision/geometry/mesh")
+            if m is None:
+                continue
+            fn = m.attrib["filename"]
+            if fn not in meshes:
+                V, Fc = load_obj(os.path.join(REF, os.path.dirname(urdf), fn))
+                meshes[fn] = len(meshes)
+                out[f"{name}_mesh{meshes[fn]}_V"], out[f"{name}_mesh{meshes[fn]}_F"] = V, Fc.astype(np.int32)
+            j = joints[link.attrib["name"]]
+            org = [float(v) for v in j.find("origin").attrib.get("xyz", "0 0 0").split()]
+            ax = [float(v) for v in j.find("axis").attrib["xyz"].split()] if j.find("axis") is not None else [1.0, 0.0, 0.0]
+            jt = {"fixed": 0, "prismatic": 1, "floating": 2}[j.attrib["type"]]
+            parent = j.find("parent").attrib["link"]
+            mass = float(link.find("inertial/mass").attrib["value"])
+            rgba = [float(v) for v in link.find("visual/material/color").attrib["rgba"].split()]
+            links.append([jt, meshes[fn], 0 if parent == "world" else 1] + org + ax + [mass] + rgba)
+        out[f"{name}_links"] = np.array(links)      # rows: joint type, mesh index, parent (0 world / 1 first link), origin xyz, axis xyz, mass, rgba
+    np.savez_compressed(os.path.join(HERE, "demo_meshes.npz"), **out)
+    print("demo_meshes.npz", {k: v.shape for k, v in out.items()})
+
+
+if __name__ == "__main__" and "--meshes" in sys.argv:
+    demo_meshes()

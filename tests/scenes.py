@@ -84,3 +84,40 @@ def contact_rollout_state(n, rng, sphere_center, radius=0.08, gap=5e-4, width=0.
     Cm = 0.5 * rng.normal(size=(n, 3, 3))
     st = np.hstack([x, v, F.reshape(n, 9), Cm.reshape(n, 9)])
     return st.astype(np.float32).astype(np.float64)
+
+
+def write_demo_assets(dirpath):
+    """Materialises the demo_grip / demo_pour rigid assets (gripper = palm + two fingers, glass, bowl) as OBJ + URDF files under
+    `dirpath` from the arrays in tests/golden/demo_meshes.npz (collision meshes and per-body joint type / origin / axis / mass, read
+    off the reference's assets by tests/golden/make_fixtures.py --meshes), for the URDF-driven builders (``Primitives(cfgs)``,
+    ``bodies_from_urdf``).  Returns {"gripper": urdf path, "glass": ..., "bowl": ...}."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "demo_meshes.npz"))
+    out = {}
+    for name in ("gripper", "glass", "bowl"):
+        d = os.path.join(dirpath, name)
+        os.makedirs(d, exist_ok=True)
+        k = 0
+        while f"{name}_mesh{k}_V" in z.files:
+            V, F = z[f"{name}_mesh{k}_V"], z[f"{name}_mesh{k}_F"]
+            with open(os.path.join(d, f"mesh{k}.obj"), "w") as fh:
+                fh.write("".join("v %.17g %.17g %.17g\n" % tuple(v) for v in V))
+                fh.write("".join("f %d %d %d\n" % tuple(f + 1) for f in F))
+            k += 1
+        links = z[f"{name}_links"]
+        xml = ['<?xml version="1.0" ?>', f'<robot name="{name}">', '  <link name="world"/>']
+        for i, row in enumerate(links):
+            jt, mesh, parent = int(row[0]), int(row[1]), int(row[2])
+            org, ax, mass, rgba = row[3:6], row[6:9], row[9], row[10:14]
+            xml += [f'  <joint name="joint{i}" type="{("fixed", "prismatic", "floating")[jt]}">',
+                    f'    <parent link="{"world" if parent == 0 else "link0"}"/> <child link="link{i}"/>',
+                    '    <origin xyz="%.17g %.17g %.17g" rpy="0 0 0"/> <axis xyz="%.17g %.17g %.17g"/>' % (*org, *ax), '  </joint>',
+                    f'  <link name="link{i}">', '    <inertial> <mass value="%.17g"/> </inertial>' % mass,
+                    f'    <visual> <geometry> <mesh filename="mesh{mesh}.obj"/> </geometry> <material name="m{i}"> '
+                    '<color rgba="%.6g %.6g %.6g %.6g"/> </material> </visual>' % tuple(rgba),
+                    f'    <collision> <geometry> <mesh filename="mesh{mesh}.obj"/> </geometry> </collision>', '  </link>']
+        xml.append('</robot>')
+        out[name] = os.path.join(d, f"{name}.urdf")
+        with open(out[name], "w") as fh:
+            fh.write("\n".join(xml) + "\n")
+    return out

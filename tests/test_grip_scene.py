@@ -11,7 +11,7 @@ import pytest
 from harness import sim_cfg
 
 pytestmark = pytest.mark.gpu
-ASSETS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "assets", "gripper")
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def test_grip_like_episode_from_urdf(tmp_path):
@@ -20,8 +20,9 @@ def test_grip_like_episode_from_urdf(tmp_path):
     from softmac_b200.engine.taichi_env import TaichiEnv
     from softmac_b200.engine.rigid_simulator import RigidSimulator, bodies_from_urdf
     from softmac_b200.engine.losses import ChamferLoss
-    urdf = os.path.join(ASSETS, "gripper.urdf")
-    G = np.load(os.path.join(os.path.dirname(ASSETS), "..", "golden", "grip_palm_contact.npz"))
+    import scenes
+    urdf = scenes.write_demo_assets(str(tmp_path / "assets"))["gripper"]      # palm + two fingers from tests/golden/demo_meshes.npz
+    G = np.load(os.path.join(GOLDEN, "grip_palm_contact.npz"))
     x0 = G["state0"].astype(np.float64)                      # 2500 particles of the reference's grip initial state
     n, env_steps, substeps, dt = len(x0), 6, 5, 2e-4
     max_steps = env_steps * substeps + substeps + 2

@@ -15,7 +15,8 @@ pour (demo_pour_config.py:9-67, demo_pour.py:141-187): the reference's initial s
     demo_pour.py:100-105.
 Jade is replaced by the stand-in rigid integrator (softmac_b200/engine/rigid_simulator.py; gravity on the bodies off, so the
 reference's adjust_action_with_ext_force is not needed) -- stated in the output.  Inputs are the reference's data fixtures copied
-as fp32 (tests/golden/reference_rest_states.npz, demo_targets.npz, tests/assets/*).
+as fp32 / arrays (tests/golden/reference_rest_states.npz, demo_targets.npz, demo_meshes.npz; OBJ + URDF files are written from the
+latter into a scratch directory by tests/scenes.py:write_demo_assets).
 
 Arms:
   drop-in : softmac_b200.engine.taichi_env.TaichiEnv -- the reference's control flow line for line (one substep() call per
@@ -43,7 +44,17 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
     if p not in sys.path:
         sys.path.insert(0, p)
 GOLD = os.path.join(ROOT, "tests", "golden")
-ASSETS = os.path.join(ROOT, "tests", "assets")
+_ASSETS = None
+
+
+def assets():
+    """OBJ + URDF files of the gripper, glass and bowl, written once per process into a scratch directory from tests/golden/demo_meshes.npz."""
+    global _ASSETS
+    if _ASSETS is None:
+        import tempfile
+        import scenes
+        _ASSETS = scenes.write_demo_assets(tempfile.mkdtemp(prefix="smx_demo_assets_"))
+    return _ASSETS
 
 
 class StandinClock:
@@ -101,7 +112,7 @@ def scene(config):
         st = rest["grip"].astype(np.float64)
         return dict(n=len(st), n_grid=64, dt=2e-4, env_dt=1e-3, substeps=5, state=st, target=tgt["grip"].astype(np.float64),
                     sim=dict(E=3e3, nu=0.2, gravity=(0., -9.8, 0.), ground_friction=20., material_model=0, ptype=0, collision_type=2),
-                    prims=[dict(friction=0.001, urdf_path=os.path.join(ASSETS, "gripper", "gripper.urdf"), enable_external_force=True)],
+                    prims=[dict(friction=0.001, urdf_path=assets()["gripper"], enable_external_force=True)],
                     contact=[False, True, True], rigid_init=(0., 0., 0., 0.), loss_weight=(1., 0., 0.), loss_start=1500, loss_cls="GripLoss")
     st = rest["pour"].astype(np.float64)
     st[:, 1] += np.float32(0.04)
@@ -109,8 +120,8 @@ def scene(config):
     init = (0., 0., 0., 0.7, 0.23488457 + 0.04 + 0.04, 0.5, 0., 0., 0., 0.34, 0.08737724 + 0.04, 0.5) + (0.,) * 12
     return dict(n=len(st), n_grid=64, dt=1e-3, env_dt=1e-3, substeps=1, state=st, target=tgt["pour"].astype(np.float64),
                 sim=dict(E=22., nu=0.2, gravity=(0., -9.8, 0.), ground_friction=0., material_model=0, ptype=2, collision_type=2),
-                prims=[dict(friction=0.1, urdf_path=os.path.join(ASSETS, "glass", "glass.urdf"), enable_external_force=True),
-                       dict(friction=1.0, urdf_path=os.path.join(ASSETS, "bowl", "bowl.urdf"), enable_external_force=False)],
+                prims=[dict(friction=0.1, urdf_path=assets()["glass"], enable_external_force=True),
+                       dict(friction=1.0, urdf_path=assets()["bowl"], enable_external_force=False)],
                 contact=[True, True], rigid_init=init, loss_weight=(1., 1e4, 1.), loss_start=2000, loss_cls="PourLoss",
                 inertia=[0.0343, 0.0348])
 
