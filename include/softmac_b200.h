@@ -147,6 +147,9 @@ int smx_get_primitive_state_grads_all(smx_sim* sim, int32_t f0, int32_t f1, doub
 /* velocity-control mode: Primitive.set_action(s, n, a6) / get_action_grad(s, n) (primitive_base.py:285-319) */
 int smx_set_primitive_action(smx_sim* sim, int32_t id, int32_t s, int32_t n, const double* a6);
 int smx_get_primitive_action_grad(smx_sim* sim, int32_t id, int32_t s, int32_t n, double* out6);
+/* Primitive.reset(): clear_all_states (state series AND their adjoints, primitive_base.py:236-246), clear_ext_f (:183-187) and
+ * clear_action_buffer (:321-326) in one call, for every batched rollout */
+int smx_reset_primitive(smx_sim* sim, int32_t id);
 
 /* Device-resident rigid coupling: the stand-in rigid integrator (bodies on fixed, prismatic or free joints -- the gripper of
  * demo_grip, the glass and bowl of demo_pour) behind the RigidSimulator interface, on the GPU.

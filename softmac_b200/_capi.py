@@ -94,6 +94,7 @@ _SIGS = {
     "smx_get_primitive_state_grads_all": [vp, C.c_int32, C.c_int32, dp],
     "smx_set_primitive_action": [vp, C.c_int32, C.c_int32, C.c_int32, dp],
     "smx_get_primitive_action_grad": [vp, C.c_int32, C.c_int32, C.c_int32, dp],
+    "smx_reset_primitive": [vp, C.c_int32],
     "smx_rigid_linear_create": [vp, vp],
     "smx_rigid_linear_reset": [vp],
     "smx_rigid_linear_set_actions": [vp, C.c_int32, dp],

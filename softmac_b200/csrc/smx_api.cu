@@ -12,6 +12,7 @@
 #include <cmath>
 #include <vector>
 #include <map>
+#include <set>
 #include <string>
 #include <algorithm>
 
@@ -104,6 +105,7 @@ struct smx_sim {
     float* pool = nullptr;
     long long frame_floats = 0;
     std::vector<int> slot_of, order_of, trans_from;
+    std::vector<int> age_of;            // substeps run since the ordering of frame f was binned (re-sort when it reaches sort_every: also in copy mode, where frame indices never grow)
     int spare_slot = 0;
     std::vector<Order> orders;
     std::vector<Order> free_orders;     // recycled device buffers
@@ -169,6 +171,7 @@ struct smx_sim {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t ev_chunk[SMX_IO_CHUNKS] = {};  // pipelined host <-> device staging
     long long launches = 0;
+    std::set<const void*> smem_optin;   // kernels whose dynamic shared-memory limit was raised on this handle's device
     bool prof = false;
     std::vector<std::pair<const char*, cudaEvent_t>> marks;
 
@@ -316,6 +319,7 @@ static int resort(smx_sim* s, int f, bool keep_transition) {
     }
     TRY(build_blocks(s, no, s->frame_ptr(f), do_sort ? s->keys_b : nullptr));
     s->order_of[f] = new_order_id(s, no);
+    s->age_of[f] = 0;
     s->ckpt_order[f] = -1; s->svd_order[f] = -1; s->near_order[f] = -1;
     // keep_transition: frame f was produced by substep f-1 in the old ordering, so the adjoint has to be carried
     // back through idx; otherwise (user-written frame) the adjoint chain is cut here, as in the reference
@@ -587,6 +591,7 @@ extern "C" {
 
 const char* smx_last_error(void) { return g_err; }
 
+static int create_body(smx_sim* s, const smx_config* cfg);
 int smx_create(const smx_config* cfg, smx_sim** out) {
     if (!cfg || !out) return fail(SMX_ERR_ARG, "smx_create: null argument");
     if (cfg->n_particles < 0 || cfg->n_grid < 8 || cfg->n_grid % 4 || cfg->max_steps < 2) return fail(SMX_ERR_ARG, "smx_create: need n_particles >= 0, n_grid >= 8 and a multiple of 4, max_steps >= 2");
@@ -600,6 +605,12 @@ int smx_create(const smx_config* cfg, smx_sim** out) {
     CK(cudaSetDevice(cfg->device));
     smx_sim* s = new smx_sim();
     s->cfg = *cfg;
+    const int rc = create_body(s, cfg);
+    if (rc != SMX_OK) { smx_destroy(s); return rc; }     // frees whatever was allocated before the failure (g_err keeps the message)
+    *out = s;
+    return SMX_OK;
+}
+static int create_body(smx_sim* s, const smx_config* cfg) {
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, cfg->device));
     s->sm_count = prop.multiProcessorCount;
     s->pf_sc = s->sm_count * SMX_SC_MINB * SMX_TPB_SC; s->pf_g = s->sm_count * SMX_P2GG_MINB * SMX_TPB; s->pf_g2p = s->sm_count * 8 * SMX_TPB;
@@ -613,10 +624,10 @@ int smx_create(const smx_config* cfg, smx_sim** out) {
     Params& P = s->P;
     int n = cfg->n_particles;
     const int B = std::max(cfg->n_batch, 1);
-    if (B > 255) { delete s; return fail(SMX_ERR_ARG, "smx_create: at most 255 batched rollouts per handle"); }
-    if (cfg->n_grid > 256) { delete s; return fail(SMX_ERR_ARG, "smx_create: n_grid <= 256 (8-bit base-cell packing of the staged scatter)"); }
-    if ((long long)B * cfg->n_particles > 2000000000LL) { delete s; return fail(SMX_ERR_ARG, "smx_create: n_batch * n_particles too large"); }
-    if ((long long)B * cfg->n_grid * cfg->n_grid * cfg->n_grid >= (1LL << 31)) { delete s; return fail(SMX_ERR_ARG, "smx_create: n_batch * n_grid^3 must stay below 2^31 (32-bit node indices)"); }
+    if (B > 255) return fail(SMX_ERR_ARG, "smx_create: at most 255 batched rollouts per handle");
+    if (cfg->n_grid > 256) return fail(SMX_ERR_ARG, "smx_create: n_grid <= 256 (8-bit base-cell packing of the staged scatter)");
+    if ((long long)B * cfg->n_particles > 2000000000LL) return fail(SMX_ERR_ARG, "smx_create: n_batch * n_particles too large");
+    if ((long long)B * cfg->n_grid * cfg->n_grid * cfg->n_grid >= (1LL << 31)) return fail(SMX_ERR_ARG, "smx_create: n_batch * n_grid^3 must stay below 2^31 (32-bit node indices)");
     P.nbatch = B; P.npb = cfg->n_particles;
     n = B * cfg->n_particles;           // total particle slots of the handle
     P.n = n; P.stride = ((long long)std::max(n, 1) + 31) / 32 * 32;
@@ -636,11 +647,11 @@ int smx_create(const smx_config* cfg, smx_sim** out) {
     s->B = B;
     s->frame_floats = 24 * P.stride;
     int T = cfg->max_steps;
-    s->slot_of.resize(T); s->order_of.assign(T, -1); s->trans_from.assign(T, -1);
+    s->slot_of.resize(T); s->order_of.assign(T, -1); s->trans_from.assign(T, -1); s->age_of.assign(T, 0);
     for (int f = 0; f < T; f++) s->slot_of[f] = f;
     s->spare_slot = T;
     size_t pool_bytes = (size_t)(T + 1) * s->frame_floats * sizeof(float);
-    if (cudaMalloc(&s->pool, pool_bytes) != cudaSuccess) { cudaGetLastError(); delete s; return fail(SMX_ERR_NOMEM, "smx_create: cannot allocate %.1f MB of particle checkpoints", pool_bytes / 1e6); }
+    if (cudaMalloc(&s->pool, pool_bytes) != cudaSuccess) { cudaGetLastError(); return fail(SMX_ERR_NOMEM, "smx_create: cannot allocate %.1f MB of particle checkpoints", pool_bytes / 1e6); }
     s->ckpt_order.assign(T, -1); s->ckpt_contact.assign(T, 0); s->svd_order.assign(T, -1); s->near_order.assign(T, -1);
     if (cfg->material_model == 0 && cfg->ptype != 2 && !(cfg->flags & SMX_FLAG_NO_SVD_REC)) {
         // optional: without it (flag, or not enough memory) the adjoint recomputes the SVD
@@ -692,7 +703,6 @@ int smx_create(const smx_config* cfg, smx_sim** out) {
         cudaGetLastError();
     }
     CK(cudaStreamSynchronize(s->stream));
-    *out = s;
     return SMX_OK;
 }
 
@@ -766,6 +776,7 @@ int smx_set_primitive_contact(smx_sim* s, int32_t id, int32_t enabled) {
 static void reset_bookkeeping(smx_sim* s) {
     std::fill(s->order_of.begin(), s->order_of.end(), -1);
     std::fill(s->trans_from.begin(), s->trans_from.end(), -1);
+    std::fill(s->age_of.begin(), s->age_of.end(), 0);
     std::fill(s->ckpt_order.begin(), s->ckpt_order.end(), -1);
     std::fill(s->svd_order.begin(), s->svd_order.end(), -1);
     std::fill(s->near_order.begin(), s->near_order.end(), -1);
@@ -874,7 +885,7 @@ int smx_copy_frame(smx_sim* s, int32_t src, int32_t dst) {
     CK(cudaSetDevice(s->cfg.device));
     if (src != dst) {
         CK(cudaMemcpyAsync(s->frame_ptr(dst), s->frame_ptr(src), s->frame_floats * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
-        s->order_of[dst] = s->order_of[src]; s->trans_from[dst] = -1; s->ckpt_order[dst] = -1; s->svd_order[dst] = -1; s->near_order[dst] = -1;
+        s->order_of[dst] = s->order_of[src]; s->age_of[dst] = s->age_of[src]; s->trans_from[dst] = -1; s->ckpt_order[dst] = -1; s->svd_order[dst] = -1; s->near_order[dst] = -1;
         int T = s->cfg.max_steps;
         for (int b = 0; b < s->B; b++)
             for (size_t ii = 0; ii < s->prims.size(); ii++) {
@@ -904,7 +915,7 @@ static int set_prim_state(smx_sim* s, int b0, int b1, int id, int f0, int f1, co
     CK(cudaSetDevice(s->cfg.device));
     std::vector<float> h((size_t)(f1 - f0) * 13);
     for (int f = 0; f < f1 - f0; f++) for (int c = 0; c < 13; c++) h[(size_t)f * 13 + c] = (float)s13[c];
-    for (int f = f0; f < f1; f++) s->near_order[f] = -1;        // the recorded reach bits of these substeps are stale
+    for (int f = f0; f < f1; f++) { s->near_order[f] = -1; s->ckpt_order[f] = -1; }   // reach bits and the grid record (post-contact g_out) of these substeps are stale
     for (int b = b0; b < b1; b++)
         CK(cudaMemcpyAsync(s->pstate + (prim_slot(s, b, id) * s->cfg.max_steps + f0) * 13, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, s->stream));
     // small pageable sources are staged by the runtime before the call returns: the per-env-step pose hand-over of the rigid bridge
@@ -1079,16 +1090,37 @@ int smx_get_primitive_action_grad(smx_sim* s, int32_t id, int32_t st, int32_t n,
     int T = s->cfg.max_steps;
     if (st < 0 || n < 1 || (long long)(st + 1) * n > T) return fail(SMX_ERR_RANGE, "smx_get_primitive_action_grad: frames outside [0, %d)", T);
     CK(cudaSetDevice(s->cfg.device));
-    // set_velocity_from_action_kernel.grad accumulates into action_buffer.grad[s] (primitive_base.py:298-319)
+    // set_velocity_from_action_kernel.grad accumulates into action_buffer.grad[s] (primitive_base.py:298-319); the action is shared
+    // by every batched rollout, so its gradient is the sum over batches (kept in batch 0's action_buffer.grad)
     std::vector<double> h((size_t)n * 13); double g[6];
-    CK(cudaMemcpyAsync(h.data(), s->pgrad + ((size_t)id * T + (size_t)st * n) * 13, h.size() * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     CK(cudaMemcpyAsync(g, s->gabuf + ((size_t)id * T + st) * 6, sizeof g, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
-    for (int j = 0; j < n; j++) for (int k = 0; k < 3; k++) { g[3 + k] += h[(size_t)j * 13 + 7 + k]; g[k] += h[(size_t)j * 13 + 10 + k]; }
+    for (int b = 0; b < s->B; b++) {
+        CK(cudaMemcpyAsync(h.data(), s->pgrad + ((size_t)prim_slot(s, b, id) * T + (size_t)st * n) * 13, h.size() * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+        CK(cudaStreamSynchronize(s->stream));
+        for (int j = 0; j < n; j++) for (int k = 0; k < 3; k++) { g[3 + k] += h[(size_t)j * 13 + 7 + k]; g[k] += h[(size_t)j * 13 + 10 + k]; }
+    }
     CK(cudaMemcpyAsync(s->gabuf + ((size_t)id * T + st) * 6, g, sizeof g, cudaMemcpyHostToDevice, s->stream));
     CK(cudaStreamSynchronize(s->stream));
     for (int i = 0; i < 6; i++) out6[i] = g[i];
     return SMX_OK;
+}
+// Primitive.reset of the reference (primitive_base.py:236-246, 267-275, 321-326): zero the state series and their adjoints, the
+// velocity-control action buffer and its adjoint, the wrench and its adjoint -- for every batch of the handle
+int smx_reset_primitive(smx_sim* s, int32_t id) {
+    TRY(check_prim(s, id, "smx_reset_primitive"));
+    CK(cudaSetDevice(s->cfg.device));
+    const size_t T = (size_t)s->cfg.max_steps;
+    for (int b = 0; b < s->B; b++) {
+        const size_t ps = prim_slot(s, b, id);
+        CK(cudaMemsetAsync(s->pstate + ps * T * 13, 0, T * 13 * sizeof(float), s->stream));
+        CK(cudaMemsetAsync(s->pgrad + ps * T * 13, 0, T * 13 * sizeof(double), s->stream));
+        CK(cudaMemsetAsync(s->abuf + ps * T * 6, 0, T * 6 * sizeof(float), s->stream));
+        CK(cudaMemsetAsync(s->gabuf + ps * T * 6, 0, T * 6 * sizeof(double), s->stream));
+    }
+    std::fill(s->near_order.begin(), s->near_order.end(), -1);
+    std::fill(s->ckpt_order.begin(), s->ckpt_order.end(), -1);
+    return clear_ext_f(s, 0, s->B, id);
 }
 
 // ---- control ------------------------------------------------------------------------------------
@@ -1251,7 +1283,7 @@ int smx_substep_begin(smx_sim* s, int32_t f) {
     if (f + 1 >= s->cfg.max_steps) return fail(SMX_ERR_RANGE, "smx_substep: substep %d would write frame %d >= max_steps %d", f, f + 1, s->cfg.max_steps);
     if (s->order_of[f] < 0) return fail(SMX_ERR_STATE, "smx_substep: frame %d has not been written (call smx_reset / smx_set_frame first)", f);
     CK(cudaSetDevice(s->cfg.device));
-    s->order_of[f + 1] = s->order_of[f]; s->trans_from[f + 1] = -1;
+    s->order_of[f + 1] = s->order_of[f]; s->trans_from[f + 1] = -1; s->age_of[f + 1] = s->age_of[f] + 1;
     s->ckpt_order[f] = -1; s->ckpt_order[f + 1] = -1; s->svd_order[f] = -1; s->near_order[f] = -1; s->svd_order[f + 1] = -1;
     if (s->ckpt_dirty) TRY(ensure_ckpt(s, f));
     return forward_p2g(s, f, true, true);
@@ -1274,7 +1306,7 @@ int smx_substep_end(smx_sim* s, int32_t f) {
     TRY(forward_grid_save_contact(s, f));
     s->last_fwd = f;
     if (s->P.n > 0) { launch_pdl(s, k_g2p, nblk(s->P.n, SMX_TPB), SMX_TPB, 0, s->P, s->frame_ptr(f), s->frame_ptr(f + 1), s->g_out, s->pf_g2p); CKLN(s, "k_g2p"); }
-    if (s->cfg.sort_every > 0 && (f + 1) % s->cfg.sort_every == 0 && !(s->cfg.flags & SMX_FLAG_NO_SORT)) TRY(resort(s, f + 1, true));
+    if (s->cfg.sort_every > 0 && s->age_of[f + 1] >= s->cfg.sort_every && !(s->cfg.flags & SMX_FLAG_NO_SORT)) TRY(resort(s, f + 1, true));
     return SMX_OK;
 }
 int smx_substep(smx_sim* s, int32_t f) {
@@ -1418,8 +1450,8 @@ int smx_substep_grad_end(smx_sim* s, int32_t f) {
                     // persistent CTAs, double-buffered TMA staging of the streaming planes
                     const int ntiles = nblk(P.n, SMX_P2GG_TPB), grid = std::min(ntiles, s->sm_count * SMX_P2GG_TILED_MINB);
                     const size_t smem = (size_t)2 * SMX_P2GG_NPL(M, R) * SMX_P2GG_TPB * sizeof(float4);
-                    static bool attr_set = false;
-                    if (!attr_set) { cudaFuncSetAttribute(k_p2g_grad_tiled<M, R, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+                    // the opt-in above 48 KB is per device: remembered per handle (a process may hold handles on several GPUs)
+                    if (s->smem_optin.insert((const void*)k_p2g_grad_tiled<M, R, E>).second) cudaFuncSetAttribute(k_p2g_grad_tiled<M, R, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                     launch_pdl(s, k_p2g_grad_tiled<M, R, E>, grid, SMX_P2GG_TPB, smem, P, ps, f, fin, s->adj_cur, s->adj_nxt, gg, cslot, s->action, s->action_grad, rec, ntiles);
                 } else {
                     launch_pdl(s, k_p2g_grad<M, R, E>, nblk(P.n, SMX_TPB), SMX_TPB, 0, P, ps, f, fin, s->adj_cur, s->adj_nxt, gg, cslot, s->action, s->action_grad, rec, s->pf_g);
@@ -1485,7 +1517,7 @@ int smx_step(smx_sim* s, int32_t s0, int32_t count) {
             TRY(check_frame(s, f, "smx_step"));
             if (f + 1 >= s->cfg.max_steps) return fail(SMX_ERR_RANGE, "smx_step: substep %d would write frame %d >= max_steps %d", f, f + 1, s->cfg.max_steps);
             CK(cudaSetDevice(s->cfg.device));
-            s->order_of[f + 1] = s->order_of[f]; s->trans_from[f + 1] = -1;
+            s->order_of[f + 1] = s->order_of[f]; s->trans_from[f + 1] = -1; s->age_of[f + 1] = s->age_of[f] + 1;
             s->ckpt_order[f] = -1; s->ckpt_order[f + 1] = -1; s->svd_order[f] = -1; s->near_order[f] = -1; s->svd_order[f + 1] = -1;
             TRY(forward_p2g(s, f, true, true, true));
             pending_g2p = false;
@@ -1493,7 +1525,7 @@ int smx_step(smx_sim* s, int32_t s0, int32_t count) {
         TRY(smx_substep_mid(s, f));
         s->mid_done = -1;
         s->last_fwd = f;
-        bool resort_next = s->cfg.sort_every > 0 && (f + 1) % s->cfg.sort_every == 0 && !(s->cfg.flags & SMX_FLAG_NO_SORT);
+        bool resort_next = s->cfg.sort_every > 0 && s->age_of[f + 1] >= s->cfg.sort_every && !(s->cfg.flags & SMX_FLAG_NO_SORT);
         bool last = (i == count - 1);
         const bool fuse_next = !last && !resort_next && f + 2 < s->cfg.max_steps && !s->ckpt_dirty;
         // with contact the record of g_out / g_mix can only be taken after the contact scatter: when the next substep follows in this

@@ -163,8 +163,11 @@ class _ChamferPoseVelLoss:
                 out["vel_loss"] = vw * val
                 g += vw * gv
             self.rigid_control.add_all_states_grad(f, g)
-        out["loss"] = out["chamfer_loss"] + out["pose_loss"] + out["vel_loss"]
-        self.loss += out["loss"]
+        # the reference returns the CUMULATIVE field under 'loss' (sum_up_loss_kernel does `self.loss[None] +=`, loss_grip.py:92-95,
+        # and _extract_loss returns self.loss[None], :139-146; demo_grip.py:152 assigns, not adds); 'frame_loss' is this frame's share
+        out["frame_loss"] = out["chamfer_loss"] + out["pose_loss"] + out["vel_loss"]
+        self.loss += out["frame_loss"]
+        out["loss"] = self.loss
         return out
 
     def clear(self):
@@ -242,8 +245,9 @@ class _PoseVelContactLoss:
                 self.sim.add_x_grad(f, cw * gx)
         if np.any(g):
             self.rigid.add_all_states_grad(f, g)
-        out["loss"] = out["pose_loss"] + out["vel_loss"] + out["contact_loss"]
-        self.loss += out["loss"]
+        out["frame_loss"] = out["pose_loss"] + out["vel_loss"] + out["contact_loss"]
+        self.loss += out["frame_loss"]
+        out["loss"] = self.loss          # cumulative, as the reference's loss field (loss_door.py:71-75, 110-117)
         return out
 
     def clear(self):

@@ -8,8 +8,7 @@ softmac/engine/taichi_env.py:38) state writes are buffered on the host.
 """
 import numpy as np
 
-from .. import _bind
-from ..._capi import lib, check, as_d, d_ptr
+from ..._capi import lib, check, as_d, d_ptr, ip
 
 
 class _ScalarField:
@@ -123,7 +122,7 @@ class Primitive:
             sdf, nrm = as_d(self.sdf_table), as_d(self.normal_table)
             res = np.ascontiguousarray(sdf.shape, dtype=np.int32)
             lo, up = as_d(self.sdf_lower), as_d(self.sdf_upper)
-            pid = check(L.smx_add_primitive(sim_handle, d_ptr(sdf), d_ptr(nrm), res.ctypes.data_as(_bind.ip), d_ptr(lo), d_ptr(up),
+            pid = check(L.smx_add_primitive(sim_handle, d_ptr(sdf), d_ptr(nrm), res.ctypes.data_as(ip), d_ptr(lo), d_ptr(up),
                                             float(self.sdf_dx), self.friction[None], self.softness[None], int(contact_enabled)))
         self._sim, self._id = sim_handle, pid
         for f, s13 in sorted(self._pending.items()):
@@ -195,8 +194,9 @@ class Primitive:
         if self._sim is None:
             self._pending.clear()
             return
-        z = np.zeros(13)
-        check(lib().smx_set_primitive_state(self._sim, self._id, 0, self.max_timesteps, d_ptr(z)))
+        # state series, their adjoints, the action buffer and its adjoint, over the frames the handle holds (the reference clears
+        # [0, max_timesteps) of its own fields, primitive_base.py:236-246; here the series live in the simulator, sized max_steps)
+        check(lib().smx_reset_primitive(self._sim, self._id))
 
     def initialize(self):
         self.friction[None] = self.cfg.get("friction", 0.9)

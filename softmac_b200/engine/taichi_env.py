@@ -104,5 +104,9 @@ class TaichiEnv:
     def compute_loss(self, f=None, **kwargs):
         assert self.loss is not None
         if f is None:
-            f = 0 if self._is_copy else self.simulator.cur
+            if self._is_copy:                       # taichi_env.py:155-157: rolling mode evaluates frame 0 from a cleared loss
+                self.loss.clear() if hasattr(self.loss, "clear") else None
+                f = 0
+            else:
+                f = self.simulator.cur
         return self.loss.compute_loss(f, **kwargs)

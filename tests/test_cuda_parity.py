@@ -574,3 +574,47 @@ def test_fused_step_matches_substep_loop():
         assert_state_close(a, b, tol=2e-5)
     assert np.abs(ea).max() > 0 and rel_l2(ea, eb) <= 1e-4
     assert rel_l2(ga, gb) <= 1e-4
+
+
+def test_copy_mode_resorts_by_age_not_by_frame_index():
+    """TaichiEnv.set_copy(True) (taichi_env.py:106-115): step `substeps` substeps from frame 0, copyframe(cur, 0), cur = 0 -- frame
+    indices never reach sort_every = max(substeps, 4) when substeps < 4 (demo_pour has 1).  The re-sort is triggered by the number
+    of substeps since the last binning, so a blob flying several cells stays inside its active-block list and equals the oracle."""
+    rng = np.random.default_rng(910)
+    n, substeps, env_steps = 3000, 2, 40
+    pair = Pair(n, max_steps=substeps + 2, substeps=substeps, gravity=(0., 0., 0.), n_grid=32)      # default sort_every = 4
+    st = scenes.blob_state(n, rng, center=(0.3, 0.5, 0.5), width=0.10, vel=0.05, Fdev=0.002, Cdev=0.2)
+    st[:, 3] += 8.0                                     # 8 m/s along x: 80 substeps * 2e-4 * 8 = 0.128 = 4.1 cells of the 32^3 grid
+    pair.reset(st)
+    for k in range(env_steps):
+        for f in range(substeps):
+            pair.substep(f)
+        last = pair.orc.get_frame(substeps)
+        pair.orc.set_frame(0, last)                     # the oracle has no orderings: copyframe is a plain copy
+        pair.gpu.copyframe(substeps, 0)
+    c = pair.gpu.counters()
+    assert c["resorts"] >= env_steps * substeps // 4 - 1, c
+    assert c["left_active_region"] == 0 and c["clamped"] == 0, c
+    ref, got = pair.orc.get_frame(0), pair.gpu.get_state(0)
+    assert np.abs(ref[:, 0] - st[:, 0]).min() > 0.1    # the blob did move four cells
+    assert rel_l2(got[:, :3], ref[:, :3]) <= 1e-5
+    assert rel_l2(got[:, 3:6], ref[:, 3:6]) <= 1e-3
+    assert rel_l2(got[:, 6:15], ref[:, 6:15]) <= 1e-4
+
+
+def test_primitive_reset_clears_adjoints_and_action_buffer():
+    """Primitive.reset() (primitive_base.py:236-246, 267-275, 321-326) zeroes the state series, their adjoints, the action buffer and
+    the wrench; a Primitive built with the default max_timesteps (2048) on a simulator with fewer frames must not raise."""
+    from softmac_b200.engine import MPMSimulator, Primitives, Mesh
+    t = scenes.sphere_table()
+    m = Mesh(sdf=dict(sdf=t["sdf"], normal=t["normal"], position=(t["lower"], t["upper"]), dx=t["dx"]), cfg=dict(friction=0.5), rigid_velocity_control=True)
+    prims = Primitives(primitives=[m], rigid_velocity_control=True)
+    sim = MPMSimulator(sim_cfg(64, max_steps=16), prims, env_dt=1e-3, rigid_velocity_control=True)
+    m.set_all_states(0, np.arange(1.0, 14.0), f_end=16)
+    m.add_all_states_grad(3, np.ones(13))
+    m.set_action(1, 5, np.arange(6.0))
+    assert np.abs(m.get_all_states_grad(0, f_end=16)).sum() > 0
+    m.reset()                                           # default max_timesteps 2048 > max_steps 16
+    assert np.abs(m.get_all_states(5)).max() == 0 and np.abs(m.get_all_states_grad(0, f_end=16)).max() == 0
+    assert np.abs(m.get_action_grad(1, 5)).max() == 0 and np.abs(m.get_ext_f()).max() == 0
+    del sim

@@ -237,7 +237,8 @@ def episode(env, sim, clock, actions, loss_frames, batched, sync, clear=True):
     t0 = time.perf_counter()
     total = 0.0
     for f in loss_frames:
-        total += env.loss.compute_loss(f)["loss"]
+        info = env.loss.compute_loss(f)
+        total += info.get("frame_loss", info["loss"])       # the mirror classes return the cumulative field under 'loss', as the reference
     sync(); t["loss"] = time.perf_counter() - t0
     c0 = clock.t
     t0 = time.perf_counter()
