@@ -27,23 +27,27 @@ def stale():
     return any(os.path.getmtime(p) > t for p in SOURCES + HEADERS)
 
 
-def build(force=False, verbose=False):
-    if not force and not stale():
+def build(force=False, verbose=False, extra=(), out=None):
+    """extra / out: ablation builds (`python -m softmac_b200.build --out lib/variant.so -DSMX_...`), loaded with SMX_LIB=..."""
+    if out is None and not force and not stale():
         return LIB
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
-    flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
-    cmd = [nvcc()] + flags + ["-o", LIB] + SOURCES
+    flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"] + list(extra)
+    target = out or LIB
+    cmd = [nvcc()] + flags + ["-o", target] + SOURCES
     r = subprocess.run(cmd, capture_output=True, text=True)
     log = r.stdout + r.stderr
-    with open(os.path.join(HERE, "lib", "build.log"), "w") as f:
+    with open(os.path.join(HERE, "lib", "build.log") if out is None else target + ".log", "w") as f:
         f.write(" ".join(cmd) + "\n" + log)
     if r.returncode != 0:
         sys.stderr.write(log)
         raise RuntimeError("nvcc failed building libsoftmac_b200.so")
     if verbose:
         print(log)
-    return LIB
+    return target
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    a = sys.argv[1:]
+    out = a[a.index("--out") + 1] if "--out" in a else None
+    print(build(force="--force" in a, verbose=out is None, extra=[x for x in a if x.startswith("-D")], out=out))

@@ -95,7 +95,7 @@ struct smx_sim {
     bool own_stream = false;
     int sm_count = 148;
     bool pdl = true, pdl_grid = false;
-    int pf_sc = 0, pf_g = 0, pf_g2p = 0;   // L2 prefetch distances (particles): one wave of resident CTAs of the scatter / gather kernels
+    int pf_sc = 0, pf_g = 0, pf_g2p = 0, pf_g2pg = 0;   // L2 prefetch distances (particles): one wave of resident CTAs of the scatter / gather kernels
     int B = 1;                          // batched independent rollouts
     // spatial slab decomposition (one rank of several): owned x-block columns [slab_lo, slab_hi), neighbours present?
     bool slab = false, halo_lo = false, halo_hi = false;
@@ -418,13 +418,19 @@ static int forward_p2g(smx_sim* s, int f, bool write_F, bool accumulate, bool fu
         const int grid = nblk(P.n, SMX_TPB_SC), acc = accumulate ? 1 : 0;
         TRY(dispatch_mat(P.material, P.ptype, [&](auto mat) {
             constexpr int M = decltype(mat)::value;
-            if (s->cfg.flags & SMX_FLAG_DIRECT_RED) {
-                if (extra) launch_pdl(s, k_p2g<M, false, true>, grid, SMX_TPB_SC, 0, P, ps, f, fin, fout, s->g_in, cslot, s->action, acc, fprev, gprev, rec, s->pf_sc);
-                else launch_pdl(s, k_p2g<M, false, false>, grid, SMX_TPB_SC, 0, P, ps, f, fin, fout, s->g_in, cslot, s->action, acc, fprev, gprev, rec, s->pf_sc);
-            } else {
-                if (extra) launch_pdl(s, k_p2g<M, true, true>, grid, SMX_TPB_SC, 0, P, ps, f, fin, fout, s->g_in, cslot, s->action, acc, fprev, gprev, rec, s->pf_sc);
-                else launch_pdl(s, k_p2g<M, true, false>, grid, SMX_TPB_SC, 0, P, ps, f, fin, fout, s->g_in, cslot, s->action, acc, fprev, gprev, rec, s->pf_sc);
-            }
+            auto go = [&](auto staged_c, auto extra_c) {
+                constexpr bool ST = decltype(staged_c)::value, EX = decltype(extra_c)::value;
+                const size_t smem = ST ? (size_t)(SMX_TPB_SC / 32) * sizeof(WarpStage) : 0;
+                // more than 48 KB of dynamic shared memory needs the per-device opt-in (remembered per handle)
+                if (ST && s->smem_optin.insert((const void*)k_p2g<M, ST, EX>).second) {
+                    cudaFuncSetAttribute(k_p2g<M, ST, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    cudaFuncSetAttribute(k_p2g<M, ST, EX>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+                }
+                launch_pdl(s, k_p2g<M, ST, EX>, grid, SMX_TPB_SC, smem, P, ps, f, fin, fout, s->g_in, cslot, s->action, acc, fprev, gprev, rec, s->pf_sc);
+            };
+            const bool staged = !(s->cfg.flags & SMX_FLAG_DIRECT_RED);
+            if (staged) { if (extra) go(std::true_type(), std::true_type()); else go(std::true_type(), std::false_type()); }
+            else { if (extra) go(std::false_type(), std::true_type()); else go(std::false_type(), std::false_type()); }
             CKLN(s, fprev ? "k_g2p2g" : "k_p2g"); return (int)SMX_OK;
         }));
         if (rec) s->svd_order[f] = o.uid;
@@ -613,12 +619,12 @@ int smx_create(const smx_config* cfg, smx_sim** out) {
 static int create_body(smx_sim* s, const smx_config* cfg) {
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, cfg->device));
     s->sm_count = prop.multiProcessorCount;
-    s->pf_sc = s->sm_count * SMX_SC_MINB * SMX_TPB_SC; s->pf_g = s->sm_count * SMX_P2GG_MINB * SMX_TPB; s->pf_g2p = s->sm_count * 8 * SMX_TPB;
+    s->pf_sc = s->sm_count * SMX_SC_MINB * SMX_TPB_SC; s->pf_g = s->sm_count * SMX_P2GG_MINB * SMX_TPB; s->pf_g2p = s->sm_count * 8 * SMX_TPB; s->pf_g2pg = s->sm_count * SMX_G2PG_MINB * SMX_TPB_G2PG;
     s->pdl = getenv("SMX_NO_PDL") == nullptr;
     // the grid kernels are launched with plain stream serialisation: at 32 registers all their CTAs become resident next to the
     // draining particle kernel and PDL then costs 10 % (measured 3.47 vs 3.84 G/s); SMX_PDL_GRID=1 turns it on for experiments
     s->pdl_grid = getenv("SMX_PDL_GRID") != nullptr;
-    if (getenv("SMX_NO_PREFETCH")) s->pf_sc = s->pf_g = s->pf_g2p = 1 << 30;
+    if (getenv("SMX_NO_PREFETCH")) s->pf_sc = s->pf_g = s->pf_g2p = s->pf_g2pg = 1 << 30;
     if (cfg->stream || (cfg->flags & SMX_FLAG_EXTERNAL_STREAM)) s->stream = (cudaStream_t)cfg->stream;   // NULL + flag: the legacy default stream
     else { CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)); s->own_stream = true; }
     Params& P = s->P;
@@ -687,21 +693,9 @@ static int create_body(smx_sim* s, const smx_config* cfg) {
     CK(cudaMalloc(&s->action_grad, nc * 3 * sizeof(double))); CK(cudaMemsetAsync(s->action_grad, 0, nc * 3 * sizeof(double), s->stream));
     CK(cudaEventCreate(&s->ev0)); CK(cudaEventCreate(&s->ev1));
     for (int i = 0; i < SMX_IO_CHUNKS; i++) CK(cudaEventCreateWithFlags(&s->ev_chunk[i], cudaEventDisableTiming));
-    {   // the staged scatter kernels want 8 CTAs x 28 KB of shared memory per SM: ask for the largest carve-out
-        int co = cudaSharedmemCarveoutMaxShared;
-        cudaFuncSetAttribute(k_p2g<0, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
-        cudaFuncSetAttribute(k_p2g<1, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
-        cudaFuncSetAttribute(k_p2g<2, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
-        cudaFuncSetAttribute(k_p2g<4, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
-        cudaFuncSetAttribute(k_p2g<5, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
-        cudaFuncSetAttribute(k_p2g<0, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
-        cudaFuncSetAttribute(k_p2g<1, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
-        cudaFuncSetAttribute(k_p2g<2, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
-        cudaFuncSetAttribute(k_p2g<4, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
-        cudaFuncSetAttribute(k_p2g<5, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
-        cudaFuncSetAttribute(k_g2p_grad<true>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
-        cudaGetLastError();
-    }
+    // the staged G2P adjoint wants 7 CTAs x 31 KB of shared memory per SM: ask for the largest carve-out (k_p2g: at its first launch)
+    cudaFuncSetAttribute(k_g2p_grad<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaGetLastError();
     CK(cudaStreamSynchronize(s->stream));
     return SMX_OK;
 }
@@ -1372,8 +1366,14 @@ int smx_substep_grad_begin(smx_sim* s, int32_t f) {
     s->bwd_prepared = -1;
     const float* fin = s->frame_ptr(f);
     if (P.n > 0) {
-        if (s->cfg.flags & SMX_FLAG_DIRECT_RED) launch_pdl(s, k_g2p_grad<false>, nblk(P.n, SMX_TPB_SC), SMX_TPB_SC, 0, P, fin, s->adj_cur, s->adj_nxt, s->g_out, gg, s->pf_sc);
-        else launch_pdl(s, k_g2p_grad<true>, nblk(P.n, SMX_TPB_SC), SMX_TPB_SC, 0, P, fin, s->adj_cur, s->adj_nxt, s->g_out, gg, s->pf_sc);
+#ifdef SMX_G2PG_F4
+        const size_t g2pg_smem = (size_t)(SMX_TPB_G2PG / 32) * sizeof(WarpStage);
+        if (s->smem_optin.insert((const void*)k_g2p_grad<true>).second) cudaFuncSetAttribute(k_g2p_grad<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g2pg_smem);
+#else
+        const size_t g2pg_smem = 0;
+#endif
+        if (s->cfg.flags & SMX_FLAG_DIRECT_RED) launch_pdl(s, k_g2p_grad<false>, nblk(P.n, SMX_TPB_G2PG), SMX_TPB_G2PG, 0, P, fin, s->adj_cur, s->adj_nxt, s->g_out, gg, s->pf_g2pg);
+        else launch_pdl(s, k_g2p_grad<true>, nblk(P.n, SMX_TPB_G2PG), SMX_TPB_G2PG, g2pg_smem, P, fin, s->adj_cur, s->adj_nxt, s->g_out, gg, s->pf_g2pg);
         CKLN(s, "k_g2p_grad");
     }
     s->grad_pending = f;

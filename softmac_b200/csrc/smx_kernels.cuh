@@ -100,8 +100,15 @@ __device__ __forceinline__ void pdl_prologue() {
 }
 
 #define SMX_TPB 128         // gather-type particle kernels
-#define SMX_TPB_SC 96       // scatter-type particle kernels (three warps x 14.6 KB of staging; five CTAs per SM)
-#define SMX_SC_MINB 5
+#ifndef SMX_TPB_SC
+#define SMX_TPB_SC 128      // P2G: four warps x 13.6 KB of staging, four CTAs per SM at 128 registers (16 warps)
+#endif
+#ifndef SMX_SC_MINB
+#define SMX_SC_MINB 4
+#endif
+#ifndef SMX_TPB_G2PG
+#define SMX_TPB_G2PG 96     // G2P adjoint: three warps x 10.3 KB of staging, seven CTAs per SM at <= 96 registers (21 warps)
+#endif
 
 __device__ __forceinline__ void red_add_f4(float4* addr, float a, float b, float c, float d) {
     // one 16-byte reduction (SASS: REDG.E.ADD.F32x4) instead of four scalar atomics
@@ -119,7 +126,7 @@ __device__ __forceinline__ void red_add_f4(float4* addr, float a, float b, float
 // ------------------------------------------------------------------------------------------------
 struct WarpStage {
     float4 val[32 * 27];    // [lane][offset]; row stride 27 float4 -> conflict-free 128-bit stores
-    uint32_t off[32 * 9];   // [lane][ox0..2 oy0..2 oz0..2]: block-major node offsets per axis
+    uint32_t key[32];       // [lane] packed base cell (pack_base) of the slot: the owning lane rebuilds its node address per run
 };
 __device__ __forceinline__ uint32_t pack_base(int bx, int by, int bz, int bt = 0) { return (uint32_t)bx | ((uint32_t)by << 8) | ((uint32_t)bz << 16) | ((uint32_t)bt << 24); }
 
@@ -130,32 +137,37 @@ __device__ __forceinline__ void add_f4(float4& a, const float4& b) {
     a = make_float4(lo.x, lo.y, hi.x, hi.y);
 }
 
-// Common head of the flush: park the node offsets, find the runs.  heads bit p: slot p starts a run; alive bit p: slot p holds a particle.
-__device__ __forceinline__ void flush_prologue(uint32_t* off, const uint32_t* ox, const uint32_t* oy, const uint32_t* oz, uint32_t key, bool live,
-                                               unsigned& heads, unsigned& alive) {
+// Common head of the flush: park the packed base cells, find the runs.  ends bit p: slot p is the last of its run; alive bit p: slot p
+// holds a particle.
+__device__ __forceinline__ void flush_prologue(uint32_t* keys, uint32_t key, bool live, unsigned& ends, unsigned& alive) {
     const unsigned lane = threadIdx.x & 31;
-    uint32_t* my = off + lane * 9;
-#pragma unroll
-    for (int a = 0; a < 3; a++) { my[a] = ox[a]; my[3 + a] = oy[a]; my[6 + a] = oz[a]; }
+    keys[lane] = key;
     uint32_t k = live ? key : 0xffffffffu;
     uint32_t prev = __shfl_up_sync(0xffffffffu, k, 1);
     bool head = (lane == 0) || (k != prev);
-    heads = __ballot_sync(0xffffffffu, head);
+    ends = (__ballot_sync(0xffffffffu, head) >> 1) | 0x80000000u;
     alive = __ballot_sync(0xffffffffu, live);
     __syncwarp();
 }
-// The walk is fully unrolled over the 32 slots in batches of 8: the eight 128-bit loads of a batch are in flight together, the
-// additions follow in slot order, and after the last slot of a run (a warp-uniform test on the ballot) the lane issues its reduction.
-__device__ __forceinline__ void warp_stage_flush(WarpStage& st, const uint32_t* ox, const uint32_t* oy, const uint32_t* oz, uint32_t key, bool live,
-                                                 float4* __restrict__ grid, int dbg = 0) {
-    unsigned heads, alive;
-    flush_prologue(st.off, ox, oy, oz, key, live, heads, alive);
+// node (bx + a, by + b, bz + c) of the run whose first slot carries `key`, as a block-major index (see node_index / make_stencil)
+__device__ __forceinline__ uint32_t run_node(uint32_t key, int a, int b, int c, int nb, int Gb) {
+    const int i = (int)(key & 255u) + a, j = (int)((key >> 8) & 255u) + b, k = (int)((key >> 16) & 255u) + c;
+    return (uint32_t)((int)(key >> 24) * Gb + (((i >> 2) * nb + (j >> 2)) * nb + (k >> 2)) * 64 + (((i & 3) << 4) | ((j & 3) << 2) | (k & 3)));
+}
+// The walk is unrolled over the 32 slots in batches of 8: the eight 128-bit loads of a batch are in flight together and the additions
+// alternate between two accumulators (two dependent chains instead of one).  A batch without a run end (one warp-uniform test of
+// the ballot) is eight plain additions; otherwise the run ends are tested slot by slot against immediate bits, and after the last
+// slot of a run the lane issues its reduction.
+__device__ __forceinline__ void warp_stage_flush(WarpStage& st, uint32_t key, bool live, float4* __restrict__ grid, int nb, int Gb, int dbg = 0) {
+    unsigned ends, alive;
+    flush_prologue(st.key, key, live, ends, alive);
     const unsigned lane = threadIdx.x & 31;
     if (lane >= 27 || (dbg & 2)) return;
-    const int a = lane / 9, b = 3 + (lane / 3) % 3, c = 6 + lane % 3;
+    const int a = lane / 9, b = (lane / 3) % 3, c = lane % 3;
     const float4* src = st.val + lane;
     const int nl = __popc(alive);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 acc0 = zero, acc1 = zero;
     int p0 = 0;
 #pragma unroll 1     // four trips of eight unrolled slots: the fully unrolled walk (1000 instructions) stalled on instruction fetch
     for (int base = 0; base < 32; base += 8) {
@@ -163,59 +175,68 @@ __device__ __forceinline__ void warp_stage_flush(WarpStage& st, const uint32_t* 
         float4 v[8];
 #pragma unroll
         for (int i = 0; i < 8; i++) v[i] = src[(base + i) * 27];
+        const unsigned e8 = (ends >> base) & 0xffu, l8 = (alive >> base) & 0xffu;
+        if (e8 == 0u) {
+#pragma unroll
+            for (int i = 0; i < 8; i += 2) { add_f4(acc0, v[i]); add_f4(acc1, v[i + 1]); }
+            continue;
+        }
 #pragma unroll
         for (int i = 0; i < 8; i++) {
-            const int p = base + i;
-            add_f4(acc, v[i]);
-            if (p == 31 || ((heads >> (p + 1)) & 1u)) {        // last slot of its run
-                if (((alive >> p) & 1u) && !(dbg & 1)) {
-                    const uint32_t* o = st.off + p0 * 9;
-                    atomicAdd(grid + (o[a] + o[b] + o[c]), acc);
+            add_f4((i & 1) ? acc1 : acc0, v[i]);
+            if (e8 & (1u << i)) {                               // last slot of its run
+                if ((l8 & (1u << i)) && !(dbg & 1)) {
+                    add_f4(acc0, acc1);
+                    atomicAdd(grid + run_node(st.key[p0], a, b, c, nb, Gb), acc0);
                 }
-                acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                p0 = p + 1;
+                acc0 = zero; acc1 = zero;
+                p0 = base + i + 1;
             }
         }
     }
 }
 
 // Three-component variant (adjoint of G2P: nothing is scattered into the mass slot): xy and z are staged in separate arrays
-// (8-byte and 4-byte accesses, both conflict-free), 25 % less shared-memory traffic and 17 % less shared memory per warp.
+// (8-byte and 4-byte accesses, both conflict-free), 25 % less shared-memory traffic and 25 % less shared memory per warp.
 struct WarpStage3 {
     float2 xy[32 * 27];     // [lane][offset]
     float z[32 * 27];
-    uint32_t off[32 * 9];
+    uint32_t key[32];
 };
-__device__ __forceinline__ void warp_stage_flush3(WarpStage3& st, const uint32_t* ox, const uint32_t* oy, const uint32_t* oz, uint32_t key, bool live,
-                                                  float4* __restrict__ grid, int dbg = 0) {
-    unsigned heads, alive;
-    flush_prologue(st.off, ox, oy, oz, key, live, heads, alive);
+__device__ __forceinline__ void warp_stage_flush3(WarpStage3& st, uint32_t key, bool live, float4* __restrict__ grid, int nb, int Gb, int dbg = 0) {
+    unsigned ends, alive;
+    flush_prologue(st.key, key, live, ends, alive);
     const unsigned lane = threadIdx.x & 31;
     if (lane >= 27 || (dbg & 2)) return;
-    const int a = lane / 9, b = 3 + (lane / 3) % 3, c = 6 + lane % 3;
+    const int a = lane / 9, b = (lane / 3) % 3, c = lane % 3;
     const float2* sxy = st.xy + lane;
     const float* sz = st.z + lane;
     const int nl = __popc(alive);
-    float2 acc = make_float2(0.f, 0.f);
-    float az = 0.f;
+    float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+    float az0 = 0.f, az1 = 0.f;
     int p0 = 0;
-#pragma unroll 1     // four trips of eight unrolled slots: the fully unrolled walk (1000 instructions) stalled on instruction fetch
+#pragma unroll 1
     for (int base = 0; base < 32; base += 8) {
         if (base >= nl) break;
         float2 v[8]; float z[8];
 #pragma unroll
         for (int i = 0; i < 8; i++) { v[i] = sxy[(base + i) * 27]; z[i] = sz[(base + i) * 27]; }
+        const unsigned e8 = (ends >> base) & 0xffu, l8 = (alive >> base) & 0xffu;
+        if (e8 == 0u) {
+#pragma unroll
+            for (int i = 0; i < 8; i += 2) { acc0 = __fadd2_rn(acc0, v[i]); az0 += z[i]; acc1 = __fadd2_rn(acc1, v[i + 1]); az1 += z[i + 1]; }
+            continue;
+        }
 #pragma unroll
         for (int i = 0; i < 8; i++) {
-            const int p = base + i;
-            acc = __fadd2_rn(acc, v[i]); az += z[i];
-            if (p == 31 || ((heads >> (p + 1)) & 1u)) {        // last slot of its run
-                if (((alive >> p) & 1u) && !(dbg & 1)) {
-                    const uint32_t* o = st.off + p0 * 9;
-                    atomicAdd(grid + (o[a] + o[b] + o[c]), make_float4(acc.x, acc.y, az, 0.f));
+            if (i & 1) { acc1 = __fadd2_rn(acc1, v[i]); az1 += z[i]; } else { acc0 = __fadd2_rn(acc0, v[i]); az0 += z[i]; }
+            if (e8 & (1u << i)) {                               // last slot of its run
+                if ((l8 & (1u << i)) && !(dbg & 1)) {
+                    acc0 = __fadd2_rn(acc0, acc1);
+                    atomicAdd(grid + run_node(st.key[p0], a, b, c, nb, Gb), make_float4(acc0.x, acc0.y, az0 + az1, 0.f));
                 }
-                acc = make_float2(0.f, 0.f); az = 0.f;
-                p0 = p + 1;
+                acc0 = make_float2(0.f, 0.f); acc1 = acc0; az0 = 0.f; az1 = 0.f;
+                p0 = base + i + 1;
             }
         }
     }
@@ -485,7 +506,8 @@ __global__ void __launch_bounds__(SMX_TPB_SC, SMX_SC_MINB) k_p2g(Params P, PrimS
                                                     const float* __restrict__ fprev, const float4* __restrict__ g_prev, float4* __restrict__ rec, int pf_dist) {
     pdl_prologue();
     // EXTRA: particle-contact impulses (collision_type == 1) and / or particle control forces are present
-    __shared__ WarpStage stage[STAGED ? SMX_TPB_SC / 32 : 1];
+    extern __shared__ __align__(128) float4 smx_dyn_smem[];     // STAGED: one WarpStage per warp (more than the 48 KB static limit)
+    WarpStage* stage = reinterpret_cast<WarpStage*>(smx_dyn_smem);
     constexpr bool has_svd = (MAT / 3 == 0) && (MAT % 3 != 2);
     int j = blockIdx.x * SMX_TPB_SC + threadIdx.x;
     bool live = j < P.n;
@@ -540,7 +562,7 @@ __global__ void __launch_bounds__(SMX_TPB_SC, SMX_SC_MINB) k_p2g(Params P, PrimS
             }
         }
     }
-    if (STAGED) warp_stage_flush(stage[threadIdx.x >> 5], s.ox, s.oy, s.oz, pack_base(s.bx, s.by, s.bz, bt), live, g_in, P.dbg);
+    if (STAGED) warp_stage_flush(stage[threadIdx.x >> 5], pack_base(s.bx, s.by, s.bz, bt), live, g_in, P.nb, P.Gb, P.dbg);
 }
 
 // boundary_condition (mpm_simulator.py:268-281); mask bit d cleared where component d was zeroed
@@ -719,14 +741,19 @@ __global__ void __launch_bounds__(SMX_TPB, SMX_G2P_MINB) k_g2p(Params P, const f
 //   ain  = adjoint of frame f+1 (x 0..2, v 3..5, C 15..23), aout = adjoint of frame f (x written here)
 // ------------------------------------------------------------------------------------------------
 #ifndef SMX_G2PG_MINB
-#define SMX_G2PG_MINB 6     // 3 warps x 11.5 KB of staging per CTA: six CTAs per SM when the kernel stays within 112 registers
+#define SMX_G2PG_MINB 6     // 18 warps; 7 CTAs (21 warps, 80 registers) measured slower: 80.7 vs 76.2 us
 #endif
 template <bool STAGED>
-__global__ void __launch_bounds__(SMX_TPB_SC, SMX_G2PG_MINB) k_g2p_grad(Params P, const float* __restrict__ fin, const float* __restrict__ ain,
+__global__ void __launch_bounds__(SMX_TPB_G2PG, SMX_G2PG_MINB) k_g2p_grad(Params P, const float* __restrict__ fin, const float* __restrict__ ain,
                                                          float* __restrict__ aout, const float4* __restrict__ g_out, float4* __restrict__ gg_out, int pf_dist) {
     pdl_prologue();
-    __shared__ WarpStage3 stage[STAGED ? SMX_TPB_SC / 32 : 1];
-    int j = blockIdx.x * SMX_TPB_SC + threadIdx.x;
+#ifdef SMX_G2PG_F4
+    extern __shared__ __align__(128) float4 smx_dyn_smem[];
+    WarpStage* stage = reinterpret_cast<WarpStage*>(smx_dyn_smem);
+#else
+    __shared__ WarpStage3 stage[STAGED ? SMX_TPB_G2PG / 32 : 1];
+#endif
+    int j = blockIdx.x * SMX_TPB_G2PG + threadIdx.x;
     bool live = j < P.n;
     int jj = live ? j : P.n - 1;
     prefetch_planes(fin, P.stride, (long long)j + pf_dist, P.n, 0, 1);
@@ -750,8 +777,12 @@ __global__ void __launch_bounds__(SMX_TPB_SC, SMX_G2PG_MINB) k_g2p_grad(Params P
         V3 q0 = gnv - mulv(K, v3(s.fx, s.fy, s.fz));
         V3 c0 = v3(K.m[0], K.m[3], K.m[6]), c1 = v3(K.m[1], K.m[4], K.m[7]), c2 = v3(K.m[2], K.m[5], K.m[8]);
         V3 gfx = v3(0, 0, 0), S0 = v3(0, 0, 0);     // S0 = sum w * g (for d dpos)
+#ifdef SMX_G2PG_F4
+        float4* row = STAGED ? stage[threadIdx.x >> 5].val + (threadIdx.x & 31) * 27 : nullptr;
+#else
         float2* row_xy = STAGED ? stage[threadIdx.x >> 5].xy + (threadIdx.x & 31) * 27 : nullptr;
         float* row_z = STAGED ? stage[threadIdx.x >> 5].z + (threadIdx.x & 31) * 27 : nullptr;
+#endif
 #pragma unroll
         for (int a = 0; a < 3; a++) {
             V3 qa = q0 + (float)a * c0;
@@ -767,7 +798,11 @@ __global__ void __launch_bounds__(SMX_TPB_SC, SMX_G2PG_MINB) k_g2p_grad(Params P
                     uint32_t node = s.ox[a] + s.oy[b] + s.oz[c];
                     float4 g = g_out[node];
                     float w = wab * s.wz[c];
+#ifdef SMX_G2PG_F4
+                    if (STAGED) row[a * 9 + b * 3 + c] = make_float4(w * q.x, w * q.y, w * q.z, 0.f);
+#else
                     if (STAGED) { row_xy[a * 9 + b * 3 + c] = make_float2(w * q.x, w * q.y); row_z[a * 9 + b * 3 + c] = w * q.z; }
+#endif
                     else red_add_f4(gg_out + node, w * q.x, w * q.y, w * q.z, 0.f);
                     float gw = fmaf(g.x, q.x, fmaf(g.y, q.y, g.z * q.z));       // d weight
                     G0 = fmaf(gw, s.wz[c], G0); G1 = fmaf(gw, dwz[c], G1);
@@ -784,7 +819,11 @@ __global__ void __launch_bounds__(SMX_TPB_SC, SMX_G2PG_MINB) k_g2p_grad(Params P
         // partial d x of frame f (the contact adjoint and P2G adjoint add theirs); the rest of the plane is written by P2G adjoint
         st_plane(aout, P.stride, j, 0, make_float4(gx1.x + P.inv_dx * gfx.x, gx1.y + P.inv_dx * gfx.y, gx1.z + P.inv_dx * gfx.z, 0.f));
     }
-    if (STAGED) warp_stage_flush3(stage[threadIdx.x >> 5], s.ox, s.oy, s.oz, pack_base(s.bx, s.by, s.bz, bt), live, gg_out, P.dbg);
+#ifdef SMX_G2PG_F4
+    if (STAGED) warp_stage_flush(stage[threadIdx.x >> 5], pack_base(s.bx, s.by, s.bz, bt), live, gg_out, P.nb, P.Gb, P.dbg);
+#else
+    if (STAGED) warp_stage_flush3(stage[threadIdx.x >> 5], pack_base(s.bx, s.by, s.bz, bt), live, gg_out, P.nb, P.Gb, P.dbg);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
