@@ -145,6 +145,8 @@ struct smx_sim {
     // adjoint ping-pong
     float *adj_cur = nullptr, *adj_nxt = nullptr;
     int adj_frame = -1, adj_order = -1;
+    bool adj_partial = false;           // inside smx_step_grad: adj_cur holds only the F planes of frame adj_frame (fused backward launches)
+    bool bwd_fusion = true;             // P2G adjoint (f) + G2P adjoint (f-1) in one launch inside smx_step_grad (SMX_NO_BWD_FUSION=1: off)
     int grad_pending = -1, mid_done = -1, grad_mid_done = -1;
     float* ch_target = nullptr; int ch_m = 0; double* ch_loss = nullptr;   // Chamfer target cloud (m,3) and loss accumulator
     int last_fwd = -1;
@@ -624,6 +626,7 @@ static int create_body(smx_sim* s, const smx_config* cfg) {
     // the grid kernels are launched with plain stream serialisation: at 32 registers all their CTAs become resident next to the
     // draining particle kernel and PDL then costs 10 % (measured 3.47 vs 3.84 G/s); SMX_PDL_GRID=1 turns it on for experiments
     s->pdl_grid = getenv("SMX_PDL_GRID") != nullptr;
+    s->bwd_fusion = getenv("SMX_NO_BWD_FUSION") == nullptr;
     if (getenv("SMX_NO_PREFETCH")) s->pf_sc = s->pf_g = s->pf_g2p = s->pf_g2pg = 1 << 30;
     if (cfg->stream || (cfg->flags & SMX_FLAG_EXTERNAL_STREAM)) s->stream = (cudaStream_t)cfg->stream;   // NULL + flag: the legacy default stream
     else { CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)); s->own_stream = true; }
@@ -1402,7 +1405,20 @@ int smx_substep_grad_mid(smx_sim* s, int32_t f) {
     s->grad_mid_done = f;
     return SMX_OK;
 }
-int smx_substep_grad_end(smx_sim* s, int32_t f) {
+// P2G adjoint of substep f and G2P adjoint of substep f-1 may share a launch when f-1 runs in the same ordering, both have their grid
+// record (so that k_grid_grad of f also restores g_out of f-1 and clears its adjoint grid) and no loss seed enters at frame f
+static bool can_fuse_bwd(smx_sim* s, int f) {
+    if (!s->bwd_fusion || f < 1 || s->slab || (s->cfg.flags & (SMX_FLAG_NO_FUSION | SMX_FLAG_DIRECT_RED)) || s->P.n <= 0) return false;
+    const int o = s->order_of[f];
+    if (o < 0 || s->order_of[f - 1] != o || s->trans_from[f] >= 0) return false;
+    const Order& ord = s->orders[o];
+    const bool contact = s->has_contact();
+    auto have = [&](int g) { return s->ckpt && s->ckpt_order[g] == ord.uid && (bool)s->ckpt_contact[g] == contact; };
+    return have(f) && have(f - 1) && s->seeds.find(f) == s->seeds.end();
+}
+static int grad_end(smx_sim* s, int f, bool fuse);
+int smx_substep_grad_end(smx_sim* s, int32_t f) { return grad_end(s, f, false); }
+static int grad_end(smx_sim* s, int f, bool fuse) {
     TRY(check_frame(s, f, "smx_substep_grad"));
     if (s->grad_pending != f) return fail(SMX_ERR_STATE, "smx_substep_grad_end: smx_substep_grad_begin(%d) has not been called", f);
     if (s->grad_mid_done != f) TRY(smx_substep_grad_mid(s, f));
@@ -1431,6 +1447,7 @@ int smx_substep_grad_end(smx_sim* s, int32_t f) {
         s->pdl = saved_pdl; }
         CKLN(s, "k_grid_grad");
         s->bwd_prepared = prep ? f - 1 : -1; s->bwd_prepared_uid = ord.uid;
+        if (fuse && !prep) return fail(SMX_ERR_STATE, "internal: fused backward launch without a prepared substep %d", f - 1);
     }
     if (s->cfg.rigid_velocity_control && !s->prims.empty()) {
         k_forward_kinematics_grad<<<nblk((long long)s->prims.size() * s->B, 64), 64, 0, s->stream>>>(s->pstate, s->pgrad, s->cfg.max_steps, (int)s->prims.size(), s->B, f, P.dt); CKL(s);
@@ -1446,7 +1463,11 @@ int smx_substep_grad_end(smx_sim* s, int32_t f) {
             constexpr int M = decltype(mat)::value;
             auto go = [&](auto rec_c, auto extra_c) {
                 constexpr bool R = decltype(rec_c)::value, E = decltype(extra_c)::value;
-                if (tiled) {
+                if (fuse) {
+                    // + G2P adjoint of substep f-1: g_out of f-1 and its cleared adjoint grid were put in place by k_grid_grad above
+                    launch_pdl(s, k_p2g_grad_g2p_grad<M, R, E>, nblk(P.n, SMX_TPB), SMX_TPB, 0, P, ps, f, fin, s->adj_cur, s->adj_nxt, gg, cslot, s->action, s->action_grad, rec,
+                               (const float*)s->frame_ptr(f - 1), (const float4*)s->g_out, s->gg_of(f - 1), s->pf_g);
+                } else if (tiled) {
                     // persistent CTAs, double-buffered TMA staging of the streaming planes
                     const int ntiles = nblk(P.n, SMX_P2GG_TPB), grid = std::min(ntiles, s->sm_count * SMX_P2GG_TILED_MINB);
                     const size_t smem = (size_t)2 * SMX_P2GG_NPL(M, R) * SMX_P2GG_TPB * sizeof(float4);
@@ -1459,11 +1480,17 @@ int smx_substep_grad_end(smx_sim* s, int32_t f) {
             };
             if (use_rec) { if (extra) go(std::true_type(), std::true_type()); else go(std::true_type(), std::false_type()); }
             else { if (extra) go(std::false_type(), std::true_type()); else go(std::false_type(), std::false_type()); }
-            CKLN(s, "k_p2g_grad"); return (int)SMX_OK;
+            CKLN(s, fuse ? "k_p2g_grad+g2p_grad" : "k_p2g_grad"); return (int)SMX_OK;
         }));
     }
     std::swap(s->adj_cur, s->adj_nxt);
     s->adj_frame = f; s->adj_order = o;
+    s->adj_partial = fuse;
+    if (fuse) {         // the G2P adjoint of substep f-1 is done: what smx_substep_grad_begin(f - 1) would leave behind
+        s->g_in_clean_uid = -1; s->bwd_prepared = -1;
+        s->grad_pending = f - 1;
+        return SMX_OK;
+    }
     TRY(apply_seed(s, f, s->adj_cur, o));
     return SMX_OK;
 }
@@ -1538,8 +1565,21 @@ int smx_step(smx_sim* s, int32_t s0, int32_t count) {
     }
     return SMX_OK;
 }
+// `count` consecutive adjoint substeps s1-1 ... s1-count.  Between two substeps that share an ordering the G2P adjoint of the earlier one
+// is fused into the P2G adjoint launch of the later one (the mirror image of G2P2G in smx_step); the last substep of the call runs the
+// plain kernels, so the adjoint of frame s1-count is complete when the call returns.  Results equal smx_substep_grad in a loop.
 int smx_step_grad(smx_sim* s, int32_t s1, int32_t count) {
-    for (int i = 1; i <= count; i++) TRY(smx_substep_grad(s, s1 - i));
+    if (!s) return fail(SMX_ERR_ARG, "smx_step_grad: null simulator");
+    bool g2p_done = false;              // the G2P adjoint of the substep at hand was part of the previous launch
+    for (int i = 1; i <= count; i++) {
+        const int f = s1 - i;
+        if (!g2p_done) TRY(smx_substep_grad_begin(s, f));
+        TRY(smx_substep_grad_mid(s, f));
+        const bool fuse = i < count && can_fuse_bwd(s, f);
+        const int rc = grad_end(s, f, fuse);
+        if (rc != SMX_OK) { s->adj_frame = -1; s->adj_partial = false; s->grad_pending = -1; return rc; }
+        g2p_done = fuse;
+    }
     return SMX_OK;
 }
 

@@ -743,10 +743,63 @@ __global__ void __launch_bounds__(SMX_TPB, SMX_G2P_MINB) k_g2p(Params P, const f
 #ifndef SMX_G2PG_MINB
 #define SMX_G2PG_MINB 6     // 18 warps; 7 CTAs (21 warps, 80 registers) measured slower: 80.7 vs 76.2 us
 #endif
+// one particle of the G2P adjoint: stages (or reduces) d g_out of its 27 nodes and returns the partial d x of frame f
+//   gx1 = adjoint of x[f+1], gnv = adjoint of v[f+1] + dt * gx1, gC = adjoint of C[f+1]
+template <bool STAGED, bool F4>
+__device__ __forceinline__ V3 g2p_grad_particle(const Params& P, const Stencil& s, V3 gx1, V3 gnv, const M3& gC, const float4* __restrict__ g_out,
+                                                float4* __restrict__ gg_out, float4* row, float2* row_xy, float* row_z) {
+    float dwx[3], dwy[3], dwz[3];
+    axis_dweights(s.fx, dwx); axis_dweights(s.fy, dwy); axis_dweights(s.fz, dwz);
+    float k4 = 4.f * P.inv_dx;
+    // d g_out(node) = w * (gnv + k4 * gC * (offset - fx)) = w * (q0 + k4*gC*offset)
+    M3 K = scale(k4, gC);
+    V3 q0 = gnv - mulv(K, v3(s.fx, s.fy, s.fz));
+    V3 c0 = v3(K.m[0], K.m[3], K.m[6]), c1 = v3(K.m[1], K.m[4], K.m[7]), c2 = v3(K.m[2], K.m[5], K.m[8]);
+    V3 gfx = v3(0, 0, 0), S0 = v3(0, 0, 0);     // S0 = sum w * g (for d dpos)
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        V3 qa = q0 + (float)a * c0;
+#pragma unroll
+        for (int b = 0; b < 3; b++) {
+            V3 qb = qa + (float)b * c1;
+            float wab = s.wx[a] * s.wy[b];
+            float G0 = 0.f, G1 = 0.f;       // sum_c gw wz[c], sum_c gw dwz[c]
+            V3 R0 = v3(0, 0, 0);            // sum_c wz[c] g
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                V3 q = qb + (float)c * c2;
+                uint32_t node = s.ox[a] + s.oy[b] + s.oz[c];
+                float4 g = g_out[node];
+                float w = wab * s.wz[c];
+                if (STAGED) {
+                    if (F4) row[a * 9 + b * 3 + c] = make_float4(w * q.x, w * q.y, w * q.z, 0.f);
+                    else { row_xy[a * 9 + b * 3 + c] = make_float2(w * q.x, w * q.y); row_z[a * 9 + b * 3 + c] = w * q.z; }
+                } else red_add_f4(gg_out + node, w * q.x, w * q.y, w * q.z, 0.f);
+                float gw = fmaf(g.x, q.x, fmaf(g.y, q.y, g.z * q.z));       // d weight
+                G0 = fmaf(gw, s.wz[c], G0); G1 = fmaf(gw, dwz[c], G1);
+                R0.x = fmaf(s.wz[c], g.x, R0.x); R0.y = fmaf(s.wz[c], g.y, R0.y); R0.z = fmaf(s.wz[c], g.z, R0.z);
+            }
+            gfx.x = fmaf(dwx[a] * s.wy[b], G0, gfx.x);
+            gfx.y = fmaf(s.wx[a] * dwy[b], G0, gfx.y);
+            gfx.z = fmaf(wab, G1, gfx.z);
+            S0 += wab * R0;
+        }
+    }
+    // d dpos = k4 * w * gC^T g  ->  d fx -= sum = K^T S0
+    gfx -= Tmulv(K, S0);
+    return gx1 + P.inv_dx * gfx;
+}
+
+#ifdef SMX_G2PG_F4
+#define SMX_G2PG_F4_ON true
+#else
+#define SMX_G2PG_F4_ON false
+#endif
 template <bool STAGED>
 __global__ void __launch_bounds__(SMX_TPB_G2PG, SMX_G2PG_MINB) k_g2p_grad(Params P, const float* __restrict__ fin, const float* __restrict__ ain,
                                                          float* __restrict__ aout, const float4* __restrict__ g_out, float4* __restrict__ gg_out, int pf_dist) {
     pdl_prologue();
+    constexpr bool F4 = SMX_G2PG_F4_ON;
 #ifdef SMX_G2PG_F4
     extern __shared__ __align__(128) float4 smx_dyn_smem[];
     WarpStage* stage = reinterpret_cast<WarpStage*>(smx_dyn_smem);
@@ -769,55 +822,14 @@ __global__ void __launch_bounds__(SMX_TPB_G2PG, SMX_G2PG_MINB) k_g2p_grad(Params
             gnv = v3(a0.w, a1.x, a1.y) + P.dt * gx1;
             gC.m[0] = a1.z; gC.m[1] = a1.w; gC.m[2] = a2.x; gC.m[3] = a2.y; gC.m[4] = a2.z; gC.m[5] = a2.w; gC.m[6] = a3.x; gC.m[7] = a3.y; gC.m[8] = a3.z;
         }
-        float dwx[3], dwy[3], dwz[3];
-        axis_dweights(s.fx, dwx); axis_dweights(s.fy, dwy); axis_dweights(s.fz, dwz);
-        float k4 = 4.f * P.inv_dx;
-        // d g_out(node) = w * (gnv + k4 * gC * (offset - fx)) = w * (q0 + k4*gC*offset)
-        M3 K = scale(k4, gC);
-        V3 q0 = gnv - mulv(K, v3(s.fx, s.fy, s.fz));
-        V3 c0 = v3(K.m[0], K.m[3], K.m[6]), c1 = v3(K.m[1], K.m[4], K.m[7]), c2 = v3(K.m[2], K.m[5], K.m[8]);
-        V3 gfx = v3(0, 0, 0), S0 = v3(0, 0, 0);     // S0 = sum w * g (for d dpos)
+        const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
 #ifdef SMX_G2PG_F4
-        float4* row = STAGED ? stage[threadIdx.x >> 5].val + (threadIdx.x & 31) * 27 : nullptr;
+        V3 gxp = g2p_grad_particle<STAGED, F4>(P, s, gx1, gnv, gC, g_out, gg_out, STAGED ? stage[w].val + l * 27 : nullptr, nullptr, nullptr);
 #else
-        float2* row_xy = STAGED ? stage[threadIdx.x >> 5].xy + (threadIdx.x & 31) * 27 : nullptr;
-        float* row_z = STAGED ? stage[threadIdx.x >> 5].z + (threadIdx.x & 31) * 27 : nullptr;
+        V3 gxp = g2p_grad_particle<STAGED, F4>(P, s, gx1, gnv, gC, g_out, gg_out, nullptr, STAGED ? stage[w].xy + l * 27 : nullptr, STAGED ? stage[w].z + l * 27 : nullptr);
 #endif
-#pragma unroll
-        for (int a = 0; a < 3; a++) {
-            V3 qa = q0 + (float)a * c0;
-#pragma unroll
-            for (int b = 0; b < 3; b++) {
-                V3 qb = qa + (float)b * c1;
-                float wab = s.wx[a] * s.wy[b];
-                float G0 = 0.f, G1 = 0.f;       // sum_c gw wz[c], sum_c gw dwz[c]
-                V3 R0 = v3(0, 0, 0);            // sum_c wz[c] g
-#pragma unroll
-                for (int c = 0; c < 3; c++) {
-                    V3 q = qb + (float)c * c2;
-                    uint32_t node = s.ox[a] + s.oy[b] + s.oz[c];
-                    float4 g = g_out[node];
-                    float w = wab * s.wz[c];
-#ifdef SMX_G2PG_F4
-                    if (STAGED) row[a * 9 + b * 3 + c] = make_float4(w * q.x, w * q.y, w * q.z, 0.f);
-#else
-                    if (STAGED) { row_xy[a * 9 + b * 3 + c] = make_float2(w * q.x, w * q.y); row_z[a * 9 + b * 3 + c] = w * q.z; }
-#endif
-                    else red_add_f4(gg_out + node, w * q.x, w * q.y, w * q.z, 0.f);
-                    float gw = fmaf(g.x, q.x, fmaf(g.y, q.y, g.z * q.z));       // d weight
-                    G0 = fmaf(gw, s.wz[c], G0); G1 = fmaf(gw, dwz[c], G1);
-                    R0.x = fmaf(s.wz[c], g.x, R0.x); R0.y = fmaf(s.wz[c], g.y, R0.y); R0.z = fmaf(s.wz[c], g.z, R0.z);
-                }
-                gfx.x = fmaf(dwx[a] * s.wy[b], G0, gfx.x);
-                gfx.y = fmaf(s.wx[a] * dwy[b], G0, gfx.y);
-                gfx.z = fmaf(wab, G1, gfx.z);
-                S0 += wab * R0;
-            }
-        }
-        // d dpos = k4 * w * gC^T g  ->  d fx -= sum = K^T S0
-        gfx -= Tmulv(K, S0);
         // partial d x of frame f (the contact adjoint and P2G adjoint add theirs); the rest of the plane is written by P2G adjoint
-        st_plane(aout, P.stride, j, 0, make_float4(gx1.x + P.inv_dx * gfx.x, gx1.y + P.inv_dx * gfx.y, gx1.z + P.inv_dx * gfx.z, 0.f));
+        st_plane(aout, P.stride, j, 0, make_float4(gxp.x, gxp.y, gxp.z, 0.f));
     }
 #ifdef SMX_G2PG_F4
     if (STAGED) warp_stage_flush(stage[threadIdx.x >> 5], pack_base(s.bx, s.by, s.bz, bt), live, gg_out, P.nb, P.Gb, P.dbg);
@@ -1067,11 +1079,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { whil
 // EXTRA: particle-contact impulses (collision_type == 1) and / or particle control forces are present
 // SM:    the streaming planes of this particle were staged in shared memory (k_p2g_grad_tiled); otherwise they are read from HBM
 // fb / rb / ab: per-particle base pointers of the frame, the SVD record and the adjoint of frame f+1 (plane p at base[p * stride])
-template <int MAT, bool REC, bool EXTRA, bool SM>
+// FUSE:  the adjoints of x, v, C of frame f are returned in registers (gxo, gvo, gCo) for the G2P adjoint of substep f-1 that follows in
+//        the same thread; only the planes that carry the adjoint of F (3, 4, 5) are stored
+template <int MAT, bool REC, bool EXTRA, bool SM, bool FUSE = false>
 __device__ __forceinline__ void p2g_grad_particle(const Params& P, const PrimSet& ps, int f, int j, int jj, bool live, const float4* fb, long long fs,
                                                   const float4* rb, long long rs, const float4* ab, long long astr, float4 gx_part, float* __restrict__ aout,
                                                   const float4* __restrict__ gg, const int* __restrict__ ctrl_slot, const float* __restrict__ action,
-                                                  double* __restrict__ action_grad) {
+                                                  double* __restrict__ action_grad, V3* gxo = nullptr, V3* gvo = nullptr, M3* gCo = nullptr) {
     constexpr int model = MAT / 3, ptype = MAT % 3;
     constexpr bool corot = model == 0 && ptype != 2;
     V3 x, v; M3 F, C;
@@ -1235,11 +1249,14 @@ __device__ __forceinline__ void p2g_grad_particle(const Params& P, const PrimSet
             }
         }
     }
+    if (FUSE) { *gxo = v3(gx_part.x + gx.x, gx_part.y + gx.y, gx_part.z + gx.z); *gvo = gv; *gCo = gC; }
     if (live) {
         float4* b = reinterpret_cast<float4*>(aout) + j;
-        b[0] = make_float4(gx_part.x + gx.x, gx_part.y + gx.y, gx_part.z + gx.z, gv.x);
-        b[P.stride] = make_float4(gv.y, gv.z, gC.m[0], gC.m[1]);
-        b[2 * P.stride] = make_float4(gC.m[2], gC.m[3], gC.m[4], gC.m[5]);
+        if (!FUSE) {
+            b[0] = make_float4(gx_part.x + gx.x, gx_part.y + gx.y, gx_part.z + gx.z, gv.x);
+            b[P.stride] = make_float4(gv.y, gv.z, gC.m[0], gC.m[1]);
+            b[2 * P.stride] = make_float4(gC.m[2], gC.m[3], gC.m[4], gC.m[5]);
+        }
         b[3 * P.stride] = make_float4(gC.m[6], gC.m[7], gC.m[8], gF.m[0]);
         b[4 * P.stride] = make_float4(gF.m[1], gF.m[2], gF.m[3], gF.m[4]);
         b[5 * P.stride] = make_float4(gF.m[5], gF.m[6], gF.m[7], gF.m[8]);
@@ -1266,6 +1283,52 @@ __global__ void __launch_bounds__(SMX_TPB, SMX_P2GG_MINB) k_p2g_grad(Params P, P
     const float4 gx_part = reinterpret_cast<const float4*>(aout)[jj];      // partial d x from the G2P / contact adjoints
     p2g_grad_particle<MAT, REC, EXTRA, false>(P, ps, f, j, jj, live, reinterpret_cast<const float4*>(fin) + jj, P.stride, rec + jj, P.stride,
                                               reinterpret_cast<const float4*>(ain) + jj, P.stride, gx_part, aout, gg, ctrl_slot, action, action_grad);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Backward counterpart of G2P2G: the P2G adjoint of substep f and the G2P adjoint of substep f-1 in ONE thread per particle slot
+// (same ordering, no loss seed on frame f).  The adjoints of x, v, C of frame f go from registers straight into the scatter of
+// d g_out of substep f-1: they are neither written to nor re-read from HBM (-112 B per particle), and the pair costs one launch.
+//   ain  : adjoint buffer of frame f+1 (planes 3.w, 4, 5 = adjoint of F are read); its plane 0 RECEIVES the partial d x of frame
+//          f-1 (it is the `aout` of the next adjoint substep)
+//   aout : adjoint buffer of frame f: plane 0 holds the partial d x of frame f (read), planes 3, 4, 5 are written
+//   g_prev / gg_prev : g_out of substep f-1 (restored by k_grid_grad of substep f) and its cleared adjoint grid
+// ------------------------------------------------------------------------------------------------
+#ifndef SMX_FUSEB_MINB
+#define SMX_FUSEB_MINB 4
+#endif
+template <int MAT, bool REC, bool EXTRA>
+__global__ void __launch_bounds__(SMX_TPB, SMX_FUSEB_MINB) k_p2g_grad_g2p_grad(Params P, PrimSet ps, int f, const float* __restrict__ fin, float* ain, float* __restrict__ aout,
+                                                                  const float4* __restrict__ gg, const int* __restrict__ ctrl_slot, const float* __restrict__ action,
+                                                                  double* __restrict__ action_grad, const float4* __restrict__ rec, const float* __restrict__ fprev,
+                                                                  const float4* __restrict__ g_prev, float4* __restrict__ gg_prev, int pf_dist) {
+    pdl_prologue();
+    constexpr bool corot = (MAT / 3 == 0) && (MAT % 3 != 2);
+    __shared__ WarpStage3 stage[SMX_TPB / 32];
+    int j = blockIdx.x * SMX_TPB + threadIdx.x;
+    bool live = j < P.n;
+    int jj = live ? j : P.n - 1;
+    {
+        long long jp = (long long)j + pf_dist;
+        prefetch_planes(fin, P.stride, jp, P.n, 0, SMX_NPLANES);
+        if (REC && corot) prefetch_planes(rec, P.stride, jp, P.n, 0, SMX_RPLANES);
+        prefetch_planes(ain, P.stride, jp, P.n, 3, SMX_NPLANES);
+        prefetch_planes(aout, P.stride, jp, P.n, 0, 1);
+        prefetch_planes(fprev, P.stride, jp, P.n, 0, 1);
+    }
+    const float4 gx_part = reinterpret_cast<const float4*>(aout)[jj];      // partial d x of frame f from the G2P / contact adjoints of substep f
+    const V3 xp = load_x(fprev, P.stride, jj);                             // x of frame f-1 (needed last; issued with the other streaming loads)
+    V3 gx, gv; M3 gC;
+    p2g_grad_particle<MAT, REC, EXTRA, false, true>(P, ps, f, j, jj, live, reinterpret_cast<const float4*>(fin) + jj, P.stride, rec + jj, P.stride,
+                                                    reinterpret_cast<const float4*>(ain) + jj, P.stride, gx_part, aout, gg, ctrl_slot, action, action_grad, &gx, &gv, &gC);
+    const int bt = batch_of(P, jj);
+    Stencil s = make_stencil(xp.x, xp.y, xp.z, P, bt);
+    if (live) {
+        const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+        V3 gxp = g2p_grad_particle<true, false>(P, s, gx, gv + P.dt * gx, gC, g_prev, gg_prev, nullptr, stage[w].xy + l * 27, stage[w].z + l * 27);
+        st_plane(ain, P.stride, j, 0, make_float4(gxp.x, gxp.y, gxp.z, 0.f));
+    }
+    warp_stage_flush3(stage[threadIdx.x >> 5], pack_base(s.bx, s.by, s.bz, bt), live, gg_prev, P.nb, P.Gb, P.dbg);
 }
 
 #ifndef SMX_P2GG_TPB

@@ -133,6 +133,12 @@ class MPMSimulator:
         check(lib().smx_get_action_grad(self._h, d_ptr(g)))
         return g.reshape(np.shape(action)) if np.size(action) == g.size else g
 
+    def get_action_grad(self):
+        """action.grad accumulated since the last set_action (the reference returns it from substep_grad, mpm_simulator.py:376-378)."""
+        g = np.zeros((self.n_batch * self.n_control, self.dim))
+        check(lib().smx_get_action_grad(self._h, d_ptr(g)))
+        return g
+
     def step(self, s0, count):
         """`count` substeps in one native call (the inner loop of TaichiEnv.step, taichi_env.py:101-102)."""
         check(lib().smx_step(self._h, int(s0), int(count)))

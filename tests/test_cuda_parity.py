@@ -566,14 +566,24 @@ def test_fused_step_matches_substep_loop():
         fe = pair.prims[0].get_ext_f()
         pair.gpu.clear_all_gradients()
         pair.gpu.add_x_grad(steps, rng.normal(size=(5000, 3)))
-        pair.gpu.step_grad(steps, steps)
-        return frames, fe, pair.gpu.get_state_grad(0)
+        pair.gpu.add_state_grad(6, 0.3 * rng.normal(size=(5000, 24)))   # a seed inside the call: that boundary is not fused
+        pair.prims[0].set_ext_f_grad(1e-3 * rng.normal(size=6))
+        l0 = pair.gpu.launch_count()
+        if use_step:
+            pair.gpu.step_grad(steps, steps)        # P2G adjoint (f) + G2P adjoint (f-1) share a launch inside an ordering
+        else:
+            for f in range(steps - 1, -1, -1):
+                pair.gpu.substep_grad(f)
+        nl = pair.gpu.launch_count() - l0
+        return frames, fe, pair.gpu.get_state_grad(0), pair.prims[0].get_all_states_grad(0, f_end=steps), pair.gpu.get_action_grad(), nl
 
-    (fa, ea, ga), (fb, eb, gb) = run(0, True), run(32, False)
+    (fa, ea, ga, pa, aa, la), (fb, eb, gb, pb, ab, lb) = run(0, True), run(32, False)
     for a, b in zip(fa, fb):
         assert_state_close(a, b, tol=2e-5)
     assert np.abs(ea).max() > 0 and rel_l2(ea, eb) <= 1e-4
     assert rel_l2(ga, gb) <= 1e-4
+    assert np.abs(pa).max() > 0 and rel_l2(pa, pb) <= 1e-3 and np.abs(aa).max() > 0 and rel_l2(aa, ab) <= 1e-4
+    assert la <= lb - 4, (la, lb)                   # at least four of the eight boundaries were fused
 
 
 def test_copy_mode_resorts_by_age_not_by_frame_index():
