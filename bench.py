@@ -6,16 +6,28 @@ Workload (SURVEY.md 8d, config 3 "cube-1M"): 1,000,000 particles from the refere
 material, E = 3e3, nu = 0.2, gravity -9.8, sticky floor, mixed (forecast) contact model, dt = 1e-4 (SURVEY.md quotes
 2e-4 "as grip", but at dx = 1/128 the reference scheme itself is unstable there: explicit-MPM limit dt < dx/sqrt(E)
 = 1.4e-4; the f64 oracle blows up after ~20 substeps at 2e-4 -- see DESIGN.md).
-Variant A: no primitive.  Variant B (--variant B): one static rigid sphere SDF under the cube.
-One "step" = S substeps forward (smx_substep) followed by S substeps backward (smx_substep_grad) with a
-dense seed on x at the last frame; value = N_gpus * n * S / step time.
+One "step" = S substeps forward (smx_step) followed by S substeps backward (smx_step_grad) with a dense seed on x at the
+last frame; value = N_gpus * n * S / step time.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl cuda|reference] [--substeps S] [--n N] [--variant A|B]
 
-N > 1 is launched by torchrun (one rank per GPU, NCCL): every rank runs an independent rollout (weak scaling)
-and the per-rollout gradient summary is all-reduced at the end of every step, as in BASELINE config 4.
---impl reference times the CPU oracle (oracle/mpm_oracle.c: the f64 OpenMP restatement of the Taichi kernels;
-Taichi itself cannot be installed here) on a bounded sample of the same workload, on rank 0 only.
+The one JSON line carries, measured in the same run:
+  value / ms_per_step  headline arm: variant A (no primitive), rest state, inputs resident in HBM, CUDA events on the simulator stream
+  parity               CUDA vs the f64 oracle on the SAME 1M-particle inputs (2 substeps forward + the frame-0 adjoint): rel-L2 of
+                       x / v / F / C per substep and the adjoint cosine; the process exits with rc 3 when a north_star tolerance
+                       (1e-4 / 0.999) is missed
+  stressed, variant_B  the harder arms (every particle needs full Jacobi sweeps and clips plastically; a sphere under the cube:
+                       forecast contact + wrench reduction every substep), each with its own value, step_hbm_frac and parity
+  roofline             dominant kernel of the fused hot path, timed live with CUDA events; traffic from the checked-in ncu capture
+  e2e                  the same step through the public API with HOST f64 buffers (H2D / D2H inside the timed region)
+  cpu_baseline         the oracle (f64 OpenMP port of the Taichi kernels) on all host threads, bounded sample
+N > 1 (torchrun, one rank per GPU, NCCL): every rank runs an independent rollout of the headline workload (weak scaling) and the
+per-rollout gradient summary (sums and norms of x.grad / v.grad of frame 0, computed on the device) is all-reduced at the end of
+every step; then two sub-records that exercise BASELINE configs 4 and 5 on the same ranks:
+  rollouts64           64 demo_grip rollouts, 64/N per rank, action gradients all-reduced (strong scaling)
+  slab_8M              8M particles / 256^3 split into x-slabs over the N ranks, halo exchange over NCCL (strong scaling), plus a
+                       200k-particle correctness check against a single handle
+--impl reference times the CPU oracle (Taichi itself cannot be installed here) on a bounded sample of the same workload, rank 0.
 """
 import argparse
 import json
@@ -28,7 +40,7 @@ import time
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for p in (ROOT, os.path.join(ROOT, "tests")):
+for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tools")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
@@ -36,12 +48,17 @@ METRIC = "particle-substeps/sec fwd+bwd (1M p, 128^3)"
 UNIT = "particle-substeps/s"
 DT = 1e-4                   # see module docstring
 ALGO_BYTES_STEP = 480.0     # 192 B forward + 288 B backward per particle-substep (fp32 storage)
-# algorithmic HBM bytes per particle of each particle kernel (DESIGN.md "Kernels"): frame components read + written
-# DRAM traffic per launch of the particle kernels from the ncu --set full capture of this round
-# (profiles/r1c_ncu_full_particle_kernels.csv: dram__bytes_read.sum + dram__bytes_write.sum; k_g2p from r1_v3_...)
-NCU_TRAFFIC = {"k_p2g_grad": 226.6e6 + 64.4e6, "k_p2g": 79.7e6 + 119.1e6, "k_g2p": 14.6e6 + 5.9e6, "k_g2p_grad": 85.1e6 + 6.4e6}
-KERNEL_BYTES = {"k_p2g": 96 + 36, "k_g2p": 12 + 60, "k_g2p_grad": 12 + 60 + 12, "k_p2g_grad": 96 + 36 + 12 + 96,
-                "k_p2g(recompute)": 96}
+# algorithmic HBM bytes per particle of each kernel class of the fused hot path (DESIGN.md "Kernels"): the frame components the
+# kernel must read + write in its fused role (SVD records, grid checkpoints and prefetches are NOT algorithmic)
+KERNEL_BYTES = {
+    "k_g2p2g": 12 + 60 + 36 + 36,                   # G2P of f-1 (x in, x v C out) + P2G of f (F in, F out; x v C from registers)
+    "k_p2g": 96 + 36,                               # first substep of a call / after a re-sort
+    "k_g2p": 12 + 60,                               # last substep of a call / before a re-sort
+    "k_g2p_grad": 12 + 60 + 12,                     # first adjoint substep of a call
+    "k_p2g_grad": 96 + 36 + 12 + 96,                # last adjoint substep of a call
+    "k_p2g_grad+g2p_grad": 96 + 36 + 12 + 36 + 12 + 12,   # frame, F adjoint in, x partial in, F adjoint out, x of f-1 in, x partial out
+}
+NCU_JSON = os.path.join(ROOT, "profiles", "r2_ncu_kernels.json")     # per-kernel summary of the checked-in ncu --set full capture
 
 
 def parse():
@@ -53,7 +70,7 @@ def parse():
     ap.add_argument("--substeps", type=int, default=64, help="substeps forward (and backward) per step")
     ap.add_argument("--n", type=int, default=1_000_000)
     ap.add_argument("--n-grid", type=int, default=128)
-    ap.add_argument("--variant", default="A", choices=["A", "B"])
+    ap.add_argument("--variant", default="A", choices=["A", "B"], help="headline arm (the other arms are sub-records)")
     ap.add_argument("--init", default="rest", choices=["rest", "stressed"], help="rest: the reference generator (v=0, F=I, C=0); stressed: same x with F = I + 0.01 N(0,1), v = 0.3 N(0,1), C = N(0,1) (every particle needs full SVD sweeps and clips plastically)")
     ap.add_argument("--batch", type=int, default=1, help="independent rollouts batched in one handle (per GPU)")
     ap.add_argument("--sort-every", type=int, default=32)
@@ -61,7 +78,14 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-e2e-pipeline", action="store_true", help="e2e arm on one handle only (no overlap of host I/O with the kernels of the other handle)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison on the bench inputs")
+    ap.add_argument("--no-subrecords", action="store_true", help="skip the stressed / variant_B (and, N > 1, rollouts64 / slab_8M) sub-records")
     ap.add_argument("--cpu-sample-substeps", type=int, default=2)
+    ap.add_argument("--slab-particles", type=int, default=8_000_000)
+    ap.add_argument("--slab-grid", type=int, default=256)
+    ap.add_argument("--slab-substeps", type=int, default=16)
+    ap.add_argument("--rollouts", type=int, default=64)
+    ap.add_argument("--rollout-env-steps", type=int, default=400)
     return ap.parse_args()
 
 
@@ -129,10 +153,10 @@ def variant_b_table():
     return scenes.sphere_table(radius=0.10, dx=0.005, margin=0.03)
 
 
-def make_inputs(args, rank):
+def make_inputs(args, rank, init=None):
     import scenes
     st = scenes.cube_state(args.n, seed=rank)           # rank r: np.random.seed(r) (rank 0 = the reference generator's seed)
-    if getattr(args, "init", "rest") == "stressed":
+    if (init or getattr(args, "init", "rest")) == "stressed":
         rng = np.random.default_rng(1000 + rank)
         st[:, 3:6] = 0.3 * rng.normal(size=(args.n, 3))
         st[:, 6:15] += 0.01 * rng.normal(size=(args.n, 9))
@@ -142,99 +166,202 @@ def make_inputs(args, rank):
     return st, np.ascontiguousarray(seed)
 
 
+def config_dict(args, S, variant=None, init=None):
+    variant, init = variant or args.variant, init or args.init
+    return {"workload": f"cube-{args.n} variant {variant}: {args.n} particles, {args.n_grid}^3 grid, corotated plastic, mixed contact, "
+                        f"{S} substeps forward + {S} backward per step",
+            "n_particles": args.n, "rollouts_per_gpu": args.batch, "n_grid": args.n_grid, "substeps_per_step": S, "variant": variant, "init": init, "dt": DT,
+            "sort_every": args.sort_every, "parallelism": f"{args.gpus} independent rollout(s), one per GPU, gradient all-reduce" if args.gpus > 1 else "single GPU",
+            "cache": "inputs larger than L2: 96 MB per particle frame, one fresh frame per substep"}
+
+
 # ------------------------------------------------------------------------------------------------------------
+# the oracle (test infrastructure): CPU baseline and parity checker.  Never on the product path.
+# ------------------------------------------------------------------------------------------------------------
+def oracle_sim(args, S, variant):
+    from oracle import mpm_oracle as mo
+    mo.set_num_threads(os.cpu_count())          # all host threads (torchrun exports OMP_NUM_THREADS=1)
+    sim = mo.OracleSim(args.n, n_grid=args.n_grid, max_steps=S + 1, dt=DT, E=3e3, nu=0.2, gravity=(0., -9.8, 0.),
+                       ground_friction=20., material_model=0, ptype=0, collision_type=2, substeps=5)
+    if variant == "B":
+        t = variant_b_table()
+        t32 = {k: np.asarray(t[k], dtype=np.float32).astype(np.float64) for k in ("sdf", "normal", "lower", "upper")}
+        sim.add_primitive(t32["sdf"], t32["normal"], t32["lower"], t32["upper"], t["dx"], friction=0.5, softness=666.)
+        for f in range(S + 1):
+            sim.set_primitive_state(0, f, np.array(VARIANT_B_POSE))
+    return sim, mo
+
+
+def oracle_step(sim, S, st, g24):
+    sim.set_frame(0, st)
+    for f in range(S):
+        sim.substep(f)
+    sim.clear_grads(); sim.add_frame_grad(S, g24)
+    for f in range(S - 1, -1, -1):
+        sim.substep_grad(f)
+
+
 def run_reference(args, rank, world):
     """CPU arm: the oracle (kind "port") on all host threads, bounded sample per step."""
     if rank != 0:
         return
-    import scenes
-    from oracle import mpm_oracle as mo
-    mo.set_num_threads(os.cpu_count())          # all host threads (torchrun exports OMP_NUM_THREADS=1)
     S = args.cpu_sample_substeps
-    sim = mo.OracleSim(args.n, n_grid=args.n_grid, max_steps=S + 1, dt=DT, E=3e3, nu=0.2, gravity=(0., -9.8, 0.),
-                       ground_friction=20., material_model=0, ptype=0, collision_type=2, substeps=5)
-    if args.variant == "B":
-        t = variant_b_table()
-        sim.add_primitive(t["sdf"], t["normal"], t["lower"], t["upper"], t["dx"], friction=0.5, softness=666.)
-        for f in range(S + 1):
-            sim.set_primitive_state(0, f, np.array(VARIANT_B_POSE))
+    sim, mo = oracle_sim(args, S, args.variant)
     st, seed = make_inputs(args, 0)
     g24 = np.zeros((args.n, 24)); g24[:, :3] = seed
-
-    def step():
-        sim.set_frame(0, st)
-        for f in range(S):
-            sim.substep(f)
-        sim.clear_grads(); sim.add_frame_grad(S, g24)
-        for f in range(S - 1, -1, -1):
-            sim.substep_grad(f)
-
     for _ in range(args.warmup):
-        step()
+        oracle_step(sim, S, st, g24)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        step()
+        oracle_step(sim, S, st, g24)
     dt = (time.perf_counter() - t0) / args.steps
     value = args.n * S / dt
     cores = mo.num_threads()
     sample = f"{S} substeps forward + {S} backward of the {args.n}-particle workload per step (f64, OpenMP, {cores} threads)"
+    cfg = config_dict(args, S)
+    cfg["sample_of"] = f"{args.substeps}+{args.substeps} substeps per step of the cuda arm (throughput-normalised bounded sample of the same workload)"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": config_dict(args, S),
+            "config": cfg,
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                              "note": "restated ti.cpu-equivalent: Taichi 1.4.1 is not installable in this image"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
-def config_dict(args, S):
-    return {"workload": f"cube-{args.n} variant {args.variant}: {args.n} particles, {args.n_grid}^3 grid, corotated plastic, mixed contact, "
-                        f"{S} substeps forward + {S} backward per step",
-            "n_particles": args.n, "rollouts_per_gpu": args.batch, "n_grid": args.n_grid, "substeps_per_step": S, "variant": args.variant, "init": args.init, "dt": DT,
-            "sort_every": args.sort_every, "parallelism": f"{args.gpus} independent rollout(s), one per GPU, gradient all-reduce" if args.gpus > 1 else "single GPU",
-            "cache": "inputs larger than L2: 96 MB per particle frame, one fresh frame per substep"}
-
-
-def cpu_baseline(args):
-    import scenes  # noqa: F401
-    from oracle import mpm_oracle as mo
-    mo.set_num_threads(os.cpu_count())
+def parity_and_cpu(sim, args, variant, init, prims, want_cpu_time):
+    """CUDA vs oracle on the bench inputs themselves: S_c substeps forward through smx_step (the fused launches of the timed path),
+    the adjoint of frame 0 through smx_step_grad; per-substep rel-L2 of x / v / F / C and the adjoint cosine.  The same oracle run
+    is the cpu_baseline sample (timed, median of 3) when want_cpu_time."""
+    from harness import rel_l2, cosine
     S = args.cpu_sample_substeps
-    sim = mo.OracleSim(args.n, n_grid=args.n_grid, max_steps=S + 1, dt=DT, E=3e3, nu=0.2, gravity=(0., -9.8, 0.),
-                       ground_friction=20., material_model=0, ptype=0, collision_type=2, substeps=5)
-    st, seed = make_inputs(args, 0)
+    orc, mo = oracle_sim(args, S, variant)
+    st, seed = make_inputs(args, 0, init)
     g24 = np.zeros((args.n, 24)); g24[:, :3] = seed
-    reps, times = 3, []
-    for r in range(reps + 1):
-        sim.set_frame(0, st)
+    times = []
+    for r in range(4 if want_cpu_time else 1):
         t0 = time.perf_counter()
-        for f in range(S):
-            sim.substep(f)
-        sim.clear_grads(); sim.add_frame_grad(S, g24)
-        for f in range(S - 1, -1, -1):
-            sim.substep_grad(f)
+        oracle_step(orc, S, st, g24)
         if r > 0:
             times.append(time.perf_counter() - t0)
-    dt = float(np.median(times))
-    cores = mo.num_threads()
-    return {"value": args.n * S / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{S} substeps forward + {S} backward at {args.n} particles, median of {reps} (variant A, f64 OpenMP restatement of the Taichi kernels)"}
-
-
-def P2(args, S):
-    """A second primitive container for the second handle of the pipelined end-to-end arm (variant B)."""
-    from softmac_b200.engine import Primitives, Mesh
-    t = variant_b_table()
-    m = Mesh(sdf=dict(sdf=t["sdf"], normal=t["normal"], position=(t["lower"], t["upper"]), dx=t["dx"]), cfg=dict(friction=0.5), max_timesteps=S + 2)
-    m.softness[None] = 666.
-    m.set_all_states(0, np.array(VARIANT_B_POSE), f_end=S + 2)
-    return Primitives(primitives=[m], max_timesteps=S + 2)
+    sim.reset(st)
+    for p in prims:
+        p.set_all_states(0, np.array(VARIANT_B_POSE), f_end=S + 1)
+    sim.clear_all_gradients()
+    sim.add_x_grad(S, seed)
+    sim.step(0, S)
+    sim.step_grad(S, S)
+    cols = dict(x=slice(0, 3), v=slice(3, 6), F=slice(6, 15), C=slice(15, 24))
+    worst = {k: 0.0 for k in cols}
+    dx = 1.0 / args.n_grid
+    for f in range(1, S + 1):
+        ref, got = orc.get_frame(f), sim.get_state(f)
+        # quantities whose oracle norm is ~0 are measured against their natural scale (C of a rigid translation: |v| / dx; v of a
+        # body at rest: g dt), as in tests/test_cuda_parity.py
+        floors = dict(x=0.0, v=float(np.sqrt(args.n)) * 9.8 * DT, F=0.0, C=float(np.linalg.norm(ref[:, cols["v"]])) / dx)
+        for k, sl in cols.items():
+            worst[k] = max(worst[k], rel_l2(got[:, sl], ref[:, sl], floor=floors[k]))
+    go, gg = orc.get_frame_grad(0), sim.get_state_grad(0)
+    rec = {"substeps": S, "n_particles": args.n, "x": worst["x"], "v": worst["v"], "F": worst["F"], "C": worst["C"],
+           "adjoint_cosine": cosine(gg, go), "adjoint_rel_l2": rel_l2(gg, go), "adjoint_norm_oracle": float(np.linalg.norm(go)),
+           "tolerance": "north_star: per-substep rel-L2 <= 1e-4 on x/v/F/C, gradient cosine >= 0.999",
+           "oracle": "oracle/mpm_oracle.c (f64 restatement; parity to Taichi itself is unpinned, see DESIGN.md section 3)"}
+    rec["pass"] = bool(max(worst.values()) <= 1e-4 and rec["adjoint_cosine"] >= 0.999 and rec["adjoint_norm_oracle"] > 0)
+    cpu = None
+    if want_cpu_time:
+        dt = float(np.median(times))
+        cpu = {"value": args.n * S / dt, "unit": UNIT, "cores": mo.num_threads(), "kind": "port",
+               "sample": f"{S} substeps forward + {S} backward at {args.n} particles, median of 3 (variant {variant}, f64 OpenMP restatement of the Taichi kernels)"}
+    del orc
+    return rec, cpu
 
 
 # ------------------------------------------------------------------------------------------------------------
+def build_sim(args, S, variant, local_rank):
+    from softmac_b200.engine import MPMSimulator, Primitives, Mesh
+    cfg = workload_cfg(args, S + 2)
+    prims = []
+    if variant == "B":
+        t = variant_b_table()
+        m = Mesh(sdf=dict(sdf=t["sdf"], normal=t["normal"], position=(t["lower"], t["upper"]), dx=t["dx"]), cfg=dict(friction=0.5), max_timesteps=S + 2)
+        m.softness[None] = 666.
+        prims.append(m)
+    P = Primitives(primitives=prims, max_timesteps=S + 2)
+    sim = MPMSimulator(cfg, P, env_dt=5 * DT, device=local_rank, sort_every=args.sort_every, flags=args.flags, n_batch=args.batch)
+    for p in prims:
+        p.set_all_states(0, np.array(VARIANT_B_POSE), f_end=S + 2)
+    return sim, prims, cfg
+
+
+def device_arm(sim, args, S, st, seed, steps, warmup, local_rank, dist=None, sample_clocks=False):
+    """Inputs resident in HBM when the timed region starts; CUDA events on the simulator's stream; max over ranks."""
+    import torch
+    gsum = torch.zeros(16, device="cuda")
+    ext = torch.cuda.ExternalStream(sim.stream_ptr(), device=torch.device("cuda", local_rank)) if dist else None
+
+    def barrier():
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sim.synchronize()
+
+    sim.reset(st)
+    sim.copyframe(0, S + 1)             # pristine copy of the initial state, stays in HBM
+    sim.clear_all_gradients()
+    sim.add_x_grad(S, seed)             # seed buffer resident on the device
+
+    def step():
+        sim.copyframe(S + 1, 0)
+        sim.step(0, S)
+        sim.step_grad(S, S)
+        if dist:
+            # gradient all-reduce across the independent rollouts (BASELINE config 4): the summary of this rollout's frame-0 adjoint is
+            # reduced on the device by the library, then summed over the ranks by NCCL -- stream-ordered, no host synchronisation
+            sim.grad_summary_dev(0, gsum.data_ptr())
+            torch.cuda.current_stream().wait_stream(ext)
+            dist.all_reduce(gsum)
+            ext.wait_stream(torch.cuda.current_stream())
+
+    for _ in range(warmup):
+        step()
+    barrier()
+    l0 = sim.launch_count()
+    clocks = ClockSampler(local_rank) if sample_clocks else None
+    if clocks:
+        clocks.start()
+    sim.timer_start()
+    for _ in range(steps):
+        step()
+    ms = sim.timer_stop()
+    barrier()
+    clk = clocks.stop() if clocks else None
+    launches = sim.launch_count() - l0
+    t_dev = torch.tensor([ms / steps], device="cuda", dtype=torch.float64)
+    if dist:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+    return float(t_dev.item()), int(launches), clk, [float(v) for v in gsum.tolist()]
+
+
+def sub_record(args, S, variant, init, local_rank, peak):
+    """A harder arm measured in the same run (device-resident, fewer steps), with its own parity check."""
+    sim, prims, _ = build_sim(args, S, variant, local_rank)
+    st, seed = make_inputs(args, 0, init)
+    if args.batch > 1:
+        st, seed = np.tile(st, (args.batch, 1)), np.tile(seed, (args.batch, 1))
+    steps, warmup = max(3, args.steps // 2), max(3, min(args.warmup, 3))
+    ms_step, launches, _, _ = device_arm(sim, args, S, st, seed, steps, warmup, local_rank)
+    value = args.batch * args.n * S / (ms_step * 1e-3)
+    rec = {"value": value, "unit": UNIT, "ms_per_step": ms_step, "steps": steps, "warmup": warmup, "step_hbm_frac": ALGO_BYTES_STEP * value / (peak * 1e9),
+           "gpu_launches": launches, "config": config_dict(args, S, variant, init), "counters": sim.counters()}
+    if not args.no_parity and args.batch == 1:
+        rec["parity"], _ = parity_and_cpu(sim, args, variant, init, prims, False)
+    del sim
+    return rec
+
+
 def run_cuda(args, rank, world, local_rank):
     import torch
-    from softmac_b200.engine import MPMSimulator, Primitives, Mesh
+    from softmac_b200.engine import MPMSimulator, Primitives
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
@@ -244,21 +371,11 @@ def run_cuda(args, rank, world, local_rank):
         os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/nccl_debug.%h.%p.log")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     S = args.substeps
-    cfg = workload_cfg(args, S + 2)
-    prims = []
-    if args.variant == "B":
-        t = variant_b_table()
-        m = Mesh(sdf=dict(sdf=t["sdf"], normal=t["normal"], position=(t["lower"], t["upper"]), dx=t["dx"]), cfg=dict(friction=0.5), max_timesteps=S + 2)
-        m.softness[None] = 666.
-        prims.append(m)
-    P = Primitives(primitives=prims, max_timesteps=S + 2)
-    sim = MPMSimulator(cfg, P, env_dt=5 * DT, device=local_rank, sort_every=args.sort_every, flags=args.flags, n_batch=args.batch)
-    for p in prims:
-        p.set_all_states(0, np.array(VARIANT_B_POSE), f_end=S + 2)
+    peak, peak_src = peaks()
+    sim, prims, cfg = build_sim(args, S, args.variant, local_rank)
     st, seed = make_inputs(args, rank)
     if args.batch > 1:
         st, seed = np.tile(st, (args.batch, 1)), np.tile(seed, (args.batch, 1))
-    gsum = torch.zeros(16, device="cuda")
 
     def barrier():
         if dist:
@@ -267,37 +384,11 @@ def run_cuda(args, rank, world, local_rank):
         sim.synchronize()
 
     # ---- device-resident arm: inputs already in HBM when the timed region starts -------------------------------
-    sim.reset(st)
-    sim.copyframe(0, S + 1)             # pristine copy of the initial state, stays in HBM
-    sim.add_x_grad(S, seed)             # seed buffer resident on the device
-
-    def device_step():
-        sim.copyframe(S + 1, 0)
-        sim.step(0, S)
-        sim.step_grad(S, S)
-        if dist:
-            dist.all_reduce(gsum)       # gradient all-reduce across rollouts (BASELINE config 4)
-
-    for _ in range(args.warmup):
-        device_step()
-    barrier()
-    l0 = sim.launch_count()
-    clocks = ClockSampler(local_rank); clocks.start()
-    sim.timer_start()
-    for _ in range(args.steps):
-        device_step()
-    ms = sim.timer_stop()
-    barrier()
-    clk = clocks.stop()
-    launches = sim.launch_count() - l0
-    t_dev = torch.tensor([ms / args.steps], device="cuda", dtype=torch.float64)
-    if dist:
-        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
-    ms_step = float(t_dev.item())
+    ms_step, launches, clk, gsum = device_arm(sim, args, S, st, seed, args.steps, args.warmup, local_rank, dist, sample_clocks=True)
     value = world * args.batch * args.n * S / (ms_step * 1e-3)
     counters = sim.counters()
 
-    # ---- per-kernel durations (CUDA events on the simulator's stream), one extra step --------------------------
+    # ---- per-kernel durations of the fused hot path (CUDA events on the simulator's stream), one extra step ----
     roof = kernel_roofline(sim, args, S)
 
     # ---- end-to-end arm: host buffers in, host result out, through the public API ------------------------------
@@ -314,8 +405,6 @@ def run_cuda(args, rank, world, local_rank):
             sim.step(0, S)
             sim.step_grad(S, S)
             xg, vg = sim.get_grad(0)            # D2H: the reference's own read-out, MPMSimulator.get_grad(f) -> (x_bar, v_bar)
-            if dist:
-                dist.all_reduce(gsum)
             barrier()
             if r > 0:
                 times.append(time.perf_counter() - t0)
@@ -329,8 +418,7 @@ def run_cuda(args, rank, world, local_rank):
             # The same calls, every step with its own host -> device upload and device -> host read-back, on TWO handles (two streams):
             # while the kernels of step k run on one handle, the host converts / uploads the inputs of step k+1 into the other and reads
             # back the result of step k-1 -- independent rollouts, the way config 4 runs them.
-            sim2 = MPMSimulator(cfg, Primitives(primitives=[], max_timesteps=S + 2) if not prims else P2(args, S), env_dt=5 * DT, device=local_rank,
-                                sort_every=args.sort_every, flags=args.flags, n_batch=args.batch)
+            sim2, prims2, _ = build_sim(args, S, args.variant, local_rank)
             pair = [sim, sim2]
 
             def start(h):                           # upload + forward substeps (asynchronous)
@@ -355,8 +443,6 @@ def run_cuda(args, rank, world, local_rank):
                     xg, vg = pair[(k - 1) % 2].get_grad(0)          # D2H + conversion of step k-1 overlap the forward of step k
                     finish(pair[k % 2])
                 xg, vg = pair[(K - 1) % 2].get_grad(0)
-                if dist:
-                    dist.all_reduce(gsum)
                 sync_all()
                 tp = (time.perf_counter() - t0) / K
                 chk = float(np.abs(xg).sum() + np.abs(vg).sum())
@@ -368,72 +454,119 @@ def run_cuda(args, rank, world, local_rank):
             e2e["mode"] = (f"two handles, software-pipelined over {K} steps: upload of step k+1 and read-back of step k-1 overlap the kernels of step k; "
                            "every step still uploads its own inputs and reads back its own result; sequential_value = one handle, one step at a time")
             e2e["pipelined_checksum"] = chk
-            del sim2
+            del sim2, prims2
 
+    # ---- parity on the bench inputs + CPU baseline (rank 0; the oracle is the checker, never the thing measured) ----
+    parity = cpu = None
+    if rank == 0 and args.batch == 1 and not (args.no_parity and args.no_cpu_baseline):
+        parity, cpu = parity_and_cpu(sim, args, args.variant, args.init, prims, not args.no_cpu_baseline)
+        if args.no_parity:
+            parity = None
+    del sim
+
+    # ---- harder arms of the same workload, same run (rank 0 only: single-GPU numbers) ----------------------------
+    subs = {}
+    if rank == 0 and not args.no_subrecords:
+        if not (args.init == "stressed" and args.variant == "A"):
+            subs["stressed"] = sub_record(args, S, "A", "stressed", local_rank, peak)
+        if args.variant != "B":
+            subs["variant_B"] = sub_record(args, S, "B", "rest", local_rank, peak)
+    if dist:
+        dist.barrier()
+
+    # ---- BASELINE configs 4 and 5 on the same ranks (N > 1) ----------------------------------------------------
+    if dist and not args.no_subrecords:
+        import bench_demo
+        import bench_slabs
+        try:
+            rec = bench_demo.rollouts_record(bench_demo.scene("grip"), "grip", args.rollout_env_steps, args.rollouts, rank, world, local_rank, reps=2, sort_every=25)
+        except Exception as e:                      # noqa: BLE001  (a failing sub-record must not take the headline line with it)
+            rec = {"error": repr(e)[:300]}
+        if rank == 0:
+            subs["rollouts64"] = rec
+        dist.barrier()
+        try:
+            rec = bench_slabs.slab_record(args.slab_particles, args.slab_grid, args.slab_substeps, rank, world, local_rank, reps=2, sort_every=16)
+            chk = bench_slabs.slab_record(200_000, 64, 8, rank, world, local_rank, reps=1, sort_every=16, check=True)
+            if rank == 0:
+                rec["check_200k"] = {k: v for k, v in chk.items() if k.startswith("check_") or k in ("n_gpus", "workload")}
+        except Exception as e:                      # noqa: BLE001
+            rec = {"error": repr(e)[:300]}
+        if rank == 0:
+            subs["slab_8M"] = rec
+        dist.barrier()
+
+    ok = True
     if rank == 0:
-        peak, peak_src = peaks()
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": config_dict(args, S), "clocks": clk, "gpu_launches": int(launches),
                 "step_hbm_frac": ALGO_BYTES_STEP * value / world / (peak * 1e9), "counters": counters}
+        if dist:
+            line["allreduce"] = {"what": "sum over ranks of [sum x.grad(3), sum v.grad(3), |x.grad|^2, |v.grad|^2, particles] of frame 0 of every rank's rollout, "
+                                         "reduced on the device (smx_grad_summary_dev) and all-reduced with NCCL every step", "last": gsum[:9]}
         if roof:
             roof.update({"peak": peak, "peak_source": peak_src, "frac": roof["achieved"] / peak})
             line["roofline"] = roof
         if e2e:
             line["e2e"] = e2e
-        if not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(args)
+        if parity:
+            line["parity"] = parity
+        if cpu:
+            line["cpu_baseline"] = cpu
+        line.update(subs)
+        fails = [k for k in ("parity",) if line.get(k) and not line[k]["pass"]] + \
+                [k for k in ("stressed", "variant_B") if line.get(k, {}).get("parity") and not line[k]["parity"]["pass"]]
+        if fails:
+            line["parity_failed"] = fails
+            ok = False
         print(json.dumps(line), flush=True)
     if dist:
         dist.destroy_process_group()
+    if not ok:
+        sys.exit(3)
+
+
+def ncu_traffic():
+    """{kernel class: DRAM bytes per launch, ...} from the checked-in ncu --set full capture of the shipped library."""
+    if not os.path.exists(NCU_JSON):
+        return {}, None
+    d = json.load(open(NCU_JSON))
+    return d.get("kernels", {}), d.get("source")
 
 
 def kernel_roofline(sim, args, S):
-    """Times each kernel class of one forward and one backward substep with CUDA events on the launching stream
-    (smx_timer_*), by running the substep loop of the step with profiling splits.  Returns the dominant kernel."""
+    """Times each kernel class of the FUSED hot path (smx_step / smx_step_grad, what the timed region runs) with CUDA events on the
+    launching stream, one extra step after the timed region.  Returns the dominant kernel with its algorithmic bytes."""
     try:
-        from softmac_b200 import _capi
-        L = _capi.lib()
-        if not hasattr(L, "smx_profile_substep"):
-            return None
-    except Exception:
+        sim.copyframe(S + 1, 0)
+        fw = sim.profile_step(0, S, False)
+        bw = sim.profile_step(S, S, True)
+    except Exception:                               # noqa: BLE001
         return None
-    import ctypes as C
-    names = (C.c_char_p * 32)()
-    ms = (C.c_float * 32)()
-    cnt = C.c_int(0)
     tot = {}
-    L.smx_profile_substep.argtypes = [_capi.vp, C.c_int32, C.c_int32, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.POINTER(C.c_int)]
-    L.smx_profile_substep.restype = C.c_int
-    nprof = min(8, S)
-
-    def prof(f, mode):
-        _capi.check(L.smx_profile_substep(sim._h, f, mode, names, ms, C.byref(cnt)))
-        for i in range(cnt.value):
-            key = names[i].decode() + ("(recompute)" if mode == 1 and names[i].decode() in ("k_p2g", "k_grid_op", "k_contact") else "")
-            tot.setdefault(key, []).append(ms[i])
-
-    sim.copyframe(S + 1, 0)
-    for f in range(S):
-        if S // 2 <= f < S // 2 + nprof or S <= nprof:
-            prof(f, 0)
-        else:
-            sim.substep(f)
-    for f in range(S - 1, -1, -1):
-        if S // 2 <= f < S // 2 + nprof or S <= nprof:
-            prof(f, 1)
-        else:
-            sim.substep_grad(f)
-    avg = {k: float(np.mean(v)) for k, v in tot.items()}
-    total = sum(avg.values())
-    top = max((k for k in avg if k in KERNEL_BYTES), key=lambda k: avg[k])
+    for d in (fw, bw):
+        for k, (ms, n) in d.items():
+            a = tot.setdefault(k, [0.0, 0])
+            a[0] += ms; a[1] += n
+    avg = {k: v[0] / max(v[1], 1) for k, v in tot.items()}
+    total_ms = sum(v[0] for v in tot.values())
+    cand = [k for k in tot if k in KERNEL_BYTES]
+    if not cand:
+        return None
+    top = max(cand, key=lambda k: tot[k][0])        # largest share of the step
     achieved = KERNEL_BYTES[top] * args.n * args.batch / (avg[top] * 1e-3) / 1e9
-    traffic = NCU_TRAFFIC.get(top) if (args.n == 1_000_000 and args.batch == 1) else None
-    return {"bound": "hbm", "kernel": top, "achieved": achieved, "unit": "GB/s", "traffic": traffic,
-            "traffic_source": "ncu --set full capture of this kernel at this size (profiles/r1c_ncu_full_particle_kernels.csv), bytes per launch" if traffic else None,
+    ncu, ncu_src = ncu_traffic()
+    tr = ncu.get(top) if (args.n == 1_000_000 and args.batch == 1) else None
+    return {"bound": "hbm", "kernel": top, "achieved": achieved, "unit": "GB/s",
+            "traffic": tr["dram_bytes"] if tr else None,
+            "traffic_source": (ncu_src + " (dram__bytes_read.sum + dram__bytes_write.sum per launch)") if tr else None,
+            "l2_red_sectors_per_launch": tr.get("lts_red_sectors") if tr else None,
             "algorithmic_bytes_per_launch": KERNEL_BYTES[top] * args.n * args.batch, "avg_launch_ms": avg[top],
-            "share_of_substep_pair": avg[top] / total if total > 0 else None,
-            "kernel_ms": avg, "how": "CUDA events around each launch on the simulator stream, 8 forward + 8 backward substeps after the timed region"}
+            "share_of_step": tot[top][0] / total_ms if total_ms > 0 else None,
+            "kernel_ms": avg, "kernel_launches": {k: v[1] for k, v in tot.items()}, "kernel_total_ms": {k: v[0] for k, v in tot.items()},
+            "kernel_frac": {k: KERNEL_BYTES[k] * args.n * args.batch / (avg[k] * 1e-3) / 1e9 / peaks()[0] for k in cand},
+            "how": f"CUDA events after every launch of one smx_step(0, {S}) + smx_step_grad({S}, {S}) on the simulator stream, after the timed region"}
 
 
 def main():

@@ -286,6 +286,13 @@ int smx_build_sdf_table(const double* vertices, int32_t nv, const int32_t* faces
 /* runs smx_substep (backward == 0) or smx_substep_grad (backward != 0) of substep f with a CUDA event after every
  * launch and returns the per-kernel-class device time: names[i] (static strings), ms[i], i < *count (<= 32) */
 int smx_profile_substep(smx_sim* sim, int32_t f, int32_t backward, const char** names, float* ms, int32_t* count);
+/* the same around smx_step(sim, f, n) (backward == 0) or smx_step_grad(sim, f, n): the fused launches of the timed hot path;
+ * launches[i] = number of marks (launches) summed into ms[i] */
+int smx_profile_step(smx_sim* sim, int32_t f, int32_t n, int32_t backward, const char** names, float* ms, int32_t* launches, int32_t* count);
+/* gradient summary of the adjoint of frame f (after a backward pass) written to 16 floats of DEVICE memory on the simulator's
+ * stream: [0..2] sum of x.grad, [3..5] sum of v.grad, [6] |x.grad|^2, [7] |v.grad|^2, [8] particles -- what a rank hands to the
+ * gradient all-reduce of independent rollouts (BASELINE config 4) without a host round trip */
+int smx_grad_summary_dev(smx_sim* sim, int32_t f, float* out16_dev);
 
 #ifdef __cplusplus
 }

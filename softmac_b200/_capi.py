@@ -140,6 +140,8 @@ _SIGS = {
     "smx_timer_stop": [vp, fp],
     "smx_launch_count": [vp],
     "smx_profile_substep": [vp, C.c_int32, C.c_int32, C.POINTER(C.c_char_p), fp, C.POINTER(C.c_int32)],
+    "smx_profile_step": [vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_char_p), fp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)],
+    "smx_grad_summary_dev": [vp, C.c_int32, vp],
     "smx_build_sdf_table": [dp, C.c_int32, ip, C.c_int32, ip, dp, C.c_double, dp, dp, C.c_int32],
     "smx_last_error": [],
 }

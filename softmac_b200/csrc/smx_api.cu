@@ -1850,13 +1850,16 @@ int smx_build_sdf_table(const double* vertices, int32_t nv, const int32_t* faces
     return SMX_OK;
 }
 
-int smx_profile_substep(smx_sim* s, int32_t f, int32_t backward, const char** names, float* ms, int32_t* count) {
-    if (!s || !names || !ms || !count) return fail(SMX_ERR_ARG, "smx_profile_substep: null argument");
+}  // extern "C"
+// shared by smx_profile_substep / smx_profile_step: run `body` with an event after every launch, sum the device time per kernel class
+template <typename Body>
+static int profile_run(smx_sim* s, const char** names, float* ms, int32_t* launches, int32_t* count, Body&& body) {
+    if (!s || !names || !ms || !count) return fail(SMX_ERR_ARG, "smx_profile_*: null argument");
     CK(cudaSetDevice(s->cfg.device));
     s->marks.clear();
     s->prof = true;
     int r = prof_mark(s, "start");
-    if (r == SMX_OK) r = backward ? smx_substep_grad(s, f) : smx_substep(s, f);
+    if (r == SMX_OK) r = body();
     s->prof = false;
     if (r != SMX_OK) { for (auto& m : s->marks) cudaEventDestroy(m.second); s->marks.clear(); return r; }
     CK(cudaStreamSynchronize(s->stream));
@@ -1866,12 +1869,32 @@ int smx_profile_substep(smx_sim* s, int32_t f, int32_t backward, const char** na
         CK(cudaEventElapsedTime(&t, s->marks[i - 1].second, s->marks[i].second));
         int k = -1;
         for (int j = 0; j < n; j++) if (!strcmp(names[j], s->marks[i].first)) k = j;
-        if (k < 0) { if (n >= 32) continue; k = n++; names[k] = s->marks[i].first; ms[k] = 0.f; }
+        if (k < 0) { if (n >= 32) continue; k = n++; names[k] = s->marks[i].first; ms[k] = 0.f; if (launches) launches[k] = 0; }
         ms[k] += t;
+        if (launches) launches[k]++;
     }
     for (auto& m : s->marks) cudaEventDestroy(m.second);
     s->marks.clear();
     *count = n;
+    return SMX_OK;
+}
+extern "C" {
+int smx_profile_substep(smx_sim* s, int32_t f, int32_t backward, const char** names, float* ms, int32_t* count) {
+    return profile_run(s, names, ms, nullptr, count, [&]() { return backward ? smx_substep_grad(s, f) : smx_substep(s, f); });
+}
+int smx_profile_step(smx_sim* s, int32_t f, int32_t n, int32_t backward, const char** names, float* ms, int32_t* launches, int32_t* count) {
+    return profile_run(s, names, ms, launches, count, [&]() { return backward ? smx_step_grad(s, f, n) : smx_step(s, f, n); });
+}
+
+// 16 floats on the device: [0..2] sum of the adjoint of x, [3..5] of v, [6] |x adjoint|^2, [7] |v adjoint|^2, [8] particle count of
+// the adjoint of frame f -- what a rank all-reduces after a rollout (stream-ordered on the simulator's stream, no host sync)
+int smx_grad_summary_dev(smx_sim* s, int32_t f, float* out16_dev) {
+    TRY(check_frame(s, f, "smx_grad_summary_dev"));
+    if (!out16_dev) return fail(SMX_ERR_ARG, "smx_grad_summary_dev: null output");
+    if (s->adj_frame != f) return fail(SMX_ERR_STATE, "smx_grad_summary_dev: no backward pass has produced the adjoint of frame %d", f);
+    CK(cudaSetDevice(s->cfg.device));
+    CK(cudaMemsetAsync(out16_dev, 0, 16 * sizeof(float), s->stream));
+    if (s->P.n > 0) { k_grad_summary<<<std::min(nblk(s->P.n, 256), s->sm_count * 8), 256, 0, s->stream>>>(s->P.n, s->P.stride, s->adj_cur, out16_dev); CKL(s); }
     return SMX_OK;
 }
 

@@ -1452,6 +1452,22 @@ __global__ void k_add_cols(int n, float* __restrict__ dst, int nd, const float* 
     if (j >= n) return;
     for (int c = 0; c < ns; c++) dst[(size_t)j * nd + c] += src[(size_t)j * ns + c];
 }
+// sums over the particles of the adjoint of x and v (planes 0 and 1 of an adjoint frame): the per-rollout gradient summary a rank
+// all-reduces (bench.py); out[0..2] x, [3..5] v, [6] |x|^2, [7] |v|^2, [8] count
+__global__ void __launch_bounds__(256) k_grad_summary(int n, long long stride, const float* __restrict__ adj, float* __restrict__ out) {
+    float a[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const float4 p0 = ld_plane(adj, stride, j, 0), p1 = ld_plane(adj, stride, j, 1);
+        a[0] += p0.x; a[1] += p0.y; a[2] += p0.z; a[3] += p0.w; a[4] += p1.x; a[5] += p1.y;
+        a[6] += p0.x * p0.x + p0.y * p0.y + p0.z * p0.z; a[7] += p0.w * p0.w + p1.x * p1.x + p1.y * p1.y; a[8] += 1.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a[i] += __shfl_xor_sync(0xffffffffu, a[i], o);
+        if ((threadIdx.x & 31) == 0) atomicAdd(out + i, a[i]);
+    }
+}
 // block-major grid -> (i,j,k) linear order, for tests
 __global__ void k_grid_linear(int ng, int nb, const float4* __restrict__ g, float4* __restrict__ out) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;

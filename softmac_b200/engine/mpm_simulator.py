@@ -261,5 +261,21 @@ class MPMSimulator:
         check(lib().smx_timer_stop(self._h, C.byref(ms)))
         return ms.value
 
+    def stream_ptr(self):
+        """cudaStream_t of the handle (for torch.cuda.ExternalStream ordering with collectives)."""
+        p = C.c_void_p()
+        check(lib().smx_stream(self._h, C.byref(p)))
+        return p.value or 0
+
+    def grad_summary_dev(self, f, out_ptr):
+        """16-float gradient summary of the adjoint of frame f into device memory at out_ptr (stream-ordered, no host sync)."""
+        check(lib().smx_grad_summary_dev(self._h, int(f), C.c_void_p(int(out_ptr))))
+
+    def profile_step(self, f, n, backward=False):
+        """{kernel class: (total device ms, launches)} of smx_step(f, n) / smx_step_grad(f, n): CUDA events on the handle's stream."""
+        names, ms, nl, cnt = (C.c_char_p * 32)(), (C.c_float * 32)(), (C.c_int32 * 32)(), C.c_int32(0)
+        check(lib().smx_profile_step(self._h, int(f), int(n), int(bool(backward)), names, ms, nl, C.byref(cnt)))
+        return {names[i].decode(): (float(ms[i]), int(nl[i])) for i in range(cnt.value)}
+
     def launch_count(self):
         return int(lib().smx_launch_count(self._h))

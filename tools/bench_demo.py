@@ -248,45 +248,70 @@ def episode(env, sim, clock, actions, loss_frames, batched, sync, clear=True):
     return t, total, np.asarray(grad)
 
 
+def rollouts_record(sc, config, K, n_rollouts, rank, ws, local, reps=2, sort_every=None, cache_dir=None, max_per_handle=16):
+    """BASELINE config 4 on the real demo scene: n_rollouts episodes with perturbed action sequences 0.3 [1, -1] (1 + 0.1 xi_k),
+    round-robin over the ranks; a rank runs its share in waves of <= max_per_handle rollouts batched in ONE handle (device-resident
+    rigid coupling), and the action gradients are all-reduced (mean) at the end of the epoch.  The process group must exist when
+    ws > 1.  Returns the record on rank 0 (None elsewhere)."""
+    import torch
+    from softmac_b200 import rollouts
+    mine = rollouts.shard(n_rollouts, rank, ws)
+    S, n = sc["substeps"], sc["n"]
+    B = min(len(mine), max_per_handle)
+    assert len(mine) % B == 0, (len(mine), B)
+    waves = [mine[i:i + B] for i in range(0, len(mine), B)]
+    loss_frames = list(range(min(sc["loss_start"], (K * S * 3) // 4), K * S + 1, 20))
+    cache_dir = cache_dir or os.path.join(ROOT, "gpurun_out", "sdf_cache")
+    env, sim, prims, clock, L = build_cuda(sc, K, batch=B, cache_dir=os.path.join(cache_dir, f"rank{rank}"), mode="device",
+                                           sort_every=sort_every, device=local)
+    base = actions_for(config, K)
+    times, gmean, loss = [], None, 0.0
+    for r in range(reps + 1):
+        if ws > 1:
+            torch.distributed.barrier()
+        sim.synchronize()
+        t0 = time.perf_counter()
+        tsim = tloss = 0.0
+        grads = []
+        for w in waves:
+            acts = np.stack([base * (1 + 0.1 * np.random.default_rng(k).normal()) for k in w])       # (B, K, ad)
+            t, loss, grad = episode(env, sim, clock, acts, loss_frames, True, sim.synchronize)
+            tsim += t["forward"] + t["backward"]; tloss += t["loss"]
+            grads.append(np.asarray(grad))
+        gmean = rollouts.allreduce_gradients(np.concatenate(grads, axis=0), n_rollouts)     # (rollouts of this rank, K, action_dim)
+        sim.synchronize()
+        if ws > 1:
+            torch.distributed.barrier()
+        if r > 0:
+            times.append((time.perf_counter() - t0, tsim, tloss))
+    best = min(times)
+    red = torch.tensor(list(best), dtype=torch.float64, device="cuda" if torch.cuda.is_available() else "cpu")
+    if ws > 1:
+        torch.distributed.all_reduce(red, op=torch.distributed.ReduceOp.MAX)
+    counters = sim.counters()
+    del env, sim, prims, L
+    if rank != 0:
+        return None
+    T, Tsim, Tloss = [float(v) for v in red.tolist()]
+    return {"workload": f"{n_rollouts} demo_{config} rollouts (BASELINE config 4), perturbed action sequences, gradient all-reduce",
+            "n_gpus": ws, "rollouts": n_rollouts, "rollouts_per_handle": B, "waves_per_rank": len(waves), "n_particles": n, "env_steps": K,
+            "substeps_per_env_step": S, "loss_frames": len(loss_frames), "episode_s": T, "fwd_bwd_s": Tsim, "loss_s": Tloss,
+            "rollouts_per_s": n_rollouts / T, "particle_substeps_per_s_fwd_bwd": n_rollouts * n * K * S / Tsim,
+            "mean_grad_norm": float(np.linalg.norm(gmean)), "mean_grad_finite": bool(np.isfinite(gmean).all()), "loss_local": loss,
+            "sort_every": sort_every, "counters": counters, "scaling": "strong",
+            "timing": "wall clock around synchronised phases, max over ranks; fwd_bwd excludes reset and the Chamfer loss"}
+
+
 def sharded_rollouts(args, sc, K):
-    """BASELINE config 4 on the real demo scene: args.rollouts episodes, round-robin over the ranks, B = rollouts / world per handle."""
     import torch
     from softmac_b200 import rollouts
     rank, ws, local = rollouts.init()
     if torch.cuda.is_available():
         torch.cuda.set_device(local)
-    mine = rollouts.shard(args.rollouts, rank, ws)
-    S, n, B = sc["substeps"], sc["n"], len(mine)
-    loss_frames = list(range(min(sc["loss_start"], (K * S * 3) // 4), K * S + 1, 20))
-    env, sim, prims, clock, L = build_cuda(sc, K, batch=B, cache_dir=os.path.join(args.cache_dir, f"rank{rank}"), mode="device",
-                                           sort_every=args.sort_every, device=local)
-    base = actions_for(args.config, K)
-    acts = np.stack([base * (1 + 0.1 * np.random.default_rng(k).normal()) for k in mine])           # (B, K, ad)
-    times, gmean, loss = [], None, 0.0
-    for r in range(args.reps + 1):
-        if ws > 1:
-            torch.distributed.barrier()
-        sim.synchronize()
-        t0 = time.perf_counter()
-        t, loss, grad = episode(env, sim, clock, acts, loss_frames, True, sim.synchronize)
-        gmean = rollouts.allreduce_gradients(grad, args.rollouts)
-        sim.synchronize()
-        if ws > 1:
-            torch.distributed.barrier()
-        if r > 0:
-            times.append((time.perf_counter() - t0, t["forward"] + t["backward"], t["loss"]))
-    best = min(times)
-    red = torch.tensor(list(best), dtype=torch.float64, device="cuda" if torch.cuda.is_available() else "cpu")
-    if ws > 1:
-        torch.distributed.all_reduce(red, op=torch.distributed.ReduceOp.MAX)
+    rec = rollouts_record(sc, args.config, K, args.rollouts, rank, ws, local, reps=args.reps, sort_every=args.sort_every, cache_dir=args.cache_dir,
+                          max_per_handle=args.max_per_handle)
     if rank == 0:
-        T, Tsim, Tloss = [float(v) for v in red.tolist()]
-        print(json.dumps({"workload": f"{args.rollouts} demo_{args.config} rollouts (BASELINE config 4), perturbed action sequences, gradient all-reduce",
-                          "n_gpus": ws, "rollouts": args.rollouts, "rollouts_per_handle": B, "n_particles": n, "env_steps": K, "substeps_per_env_step": S,
-                          "loss_frames": len(loss_frames), "episode_s": T, "fwd_bwd_s": Tsim, "loss_s": Tloss, "rollouts_per_s": args.rollouts / T,
-                          "particle_substeps_per_s_fwd_bwd": args.rollouts * n * K * S / Tsim, "mean_grad_norm": float(np.linalg.norm(gmean)),
-                          "loss_local": loss, "sort_every": args.sort_every, "counters": sim.counters(),
-                          "timing": "wall clock around synchronised phases, max over ranks; fwd_bwd excludes reset and the Chamfer loss"}), flush=True)
+        print(json.dumps(rec), flush=True)
     if ws > 1:
         torch.distributed.destroy_process_group()
 
@@ -305,6 +330,7 @@ def main():
                     "0.3 [1, -1] (1 + 0.1 xi_k), sharded over the ranks of a torchrun launch (one handle per GPU, device-resident rigid "
                     "coupling), action gradients all-reduced (mean) at the end of the episode")
     ap.add_argument("--cache-dir", default=os.path.join(ROOT, "gpurun_out", "sdf_cache"))
+    ap.add_argument("--max-per-handle", type=int, default=16, help="with --rollouts: rollouts batched in one handle (a rank runs its share in waves)")
     args = ap.parse_args()
     sc = scene(args.config)
     S, n = sc["substeps"], sc["n"]

@@ -21,29 +21,17 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
         sys.path.insert(0, p)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--particles", dest="n", type=int, default=8_000_000)
-    ap.add_argument("--grid", dest="n_grid", type=int, default=256)
-    ap.add_argument("--substeps", type=int, default=32)
-    ap.add_argument("--reps", type=int, default=3)
-    ap.add_argument("--sort-every", type=int, default=16)
-    ap.add_argument("--check", action="store_true")
-    ap.add_argument("--migrate-every", type=int, default=0, help="re-establish particle ownership every E substeps (particle migration "
-                    "between slab ranks over NCCL P2P); 0: ownership fixed at reset")
-    ap.add_argument("--sphere", action="store_true", help="(with --check) a sphere primitive on the slab boundary: forecast contact, wrench summed over ranks")
-    ap.add_argument("--drift", type=float, default=0.0, help="add this x-velocity (m/s) to every particle so that material streams through the slab boundaries")
-    args = ap.parse_args()
+def slab_record(n, n_grid, S, rank, ws, local, reps=3, sort_every=16, check=False, migrate_every=0, sphere=False, drift=0.0):
+    """One strong-scaling measurement of the slab decomposition (the process group must exist when ws > 1).  Returns the record on
+    rank 0 (None elsewhere); with check=True the forward states are compared with a single handle on rank 0."""
+    import types
     import torch
     import torch.distributed as dist
     import scenes
     from harness import sim_cfg, rel_l2
-    from softmac_b200 import rollouts
     from softmac_b200.slabs import DistSlab, DistMigratingSlab
-    rank, ws, local = rollouts.init()
-    torch.cuda.set_device(local)
-    if args.check:
-        args.n, args.n_grid, args.substeps = 200_000, 64, 8
+    args = types.SimpleNamespace(n=n, n_grid=n_grid, substeps=S, reps=reps, sort_every=sort_every, check=check, migrate_every=migrate_every,
+                                 sphere=sphere, drift=drift)
     S = args.substeps
     dt = 2e-4 * 64 / args.n_grid * 0.5 if args.n_grid > 64 else 2e-4          # 1e-4 at 128^3, 5e-5 at 256^3 (stability: DESIGN.md section 5)
     cfg = sim_cfg(args.n, n_grid=args.n_grid, max_steps=S + 2, dt=dt)
@@ -164,6 +152,31 @@ def main():
             out["check_rel_l2_x"] = rel_l2(got[:, :3], r[:, :3]); out["check_rel_l2_v"] = rel_l2(got[:, 3:6], r[:, 3:6])
             out["check_rel_l2_F"] = rel_l2(got[:, 6:15], r[:, 6:15])
             assert out["check_rel_l2_x"] <= 1e-6 and out["check_rel_l2_v"] <= 5e-5 and out["check_rel_l2_F"] <= 5e-5, out
+    return out if rank == 0 else None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--particles", dest="n", type=int, default=8_000_000)
+    ap.add_argument("--grid", dest="n_grid", type=int, default=256)
+    ap.add_argument("--substeps", type=int, default=32)
+    ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--sort-every", type=int, default=16)
+    ap.add_argument("--check", action="store_true")
+    ap.add_argument("--migrate-every", type=int, default=0, help="re-establish particle ownership every E substeps (particle migration "
+                    "between slab ranks over NCCL P2P); 0: ownership fixed at reset")
+    ap.add_argument("--sphere", action="store_true", help="(with --check) a sphere primitive on the slab boundary: forecast contact, wrench summed over ranks")
+    ap.add_argument("--drift", type=float, default=0.0, help="add this x-velocity (m/s) to every particle so that material streams through the slab boundaries")
+    args = ap.parse_args()
+    import torch
+    import torch.distributed as dist
+    from softmac_b200 import rollouts
+    rank, ws, local = rollouts.init()
+    torch.cuda.set_device(local)
+    if args.check:
+        args.n, args.n_grid, args.substeps = 200_000, 64, 8
+    out = slab_record(args.n, args.n_grid, args.substeps, rank, ws, local, reps=args.reps, sort_every=args.sort_every, check=args.check,
+                      migrate_every=args.migrate_every, sphere=args.sphere, drift=args.drift)
     if rank == 0:
         print(json.dumps(out), flush=True)
     if ws > 1:
