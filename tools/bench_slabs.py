@@ -62,9 +62,6 @@ def slab_record(n, n_grid, S, rank, ws, local, reps=3, sort_every=16, check=Fals
             sl.set_primitive_state(0, 0, S + 2, s13); sl.clear_ext_f()
         else:
             sl.primitives[0].set_all_states(0, s13, f_end=S + 2); sl.primitives[0].clear_ext_f()
-    else:
-        from softmac_b200.slabs import SlabCluster
-        sl = None
     from softmac_b200.engine import MPMSimulator
     if ws == 1:
         sim = MPMSimulator(cfg, (), env_dt=5 * dt, sort_every=args.sort_every)
