@@ -151,20 +151,21 @@ int smx_get_primitive_action_grad(smx_sim* sim, int32_t id, int32_t s, int32_t n
  * clear_action_buffer (:321-326) in one call, for every batched rollout */
 int smx_reset_primitive(smx_sim* sim, int32_t id);
 
-/* Device-resident rigid coupling: the stand-in rigid integrator (bodies on fixed, prismatic or free joints -- the gripper of
- * demo_grip, the glass and bowl of demo_pour) behind the RigidSimulator interface, on the GPU.
+/* Device-resident rigid coupling: the stand-in rigid integrator (bodies on fixed, prismatic, revolute or free joints -- the gripper
+ * of demo_grip, the glass and bowl of demo_pour, the hinged door of demo_door) behind the RigidSimulator interface, on the GPU.
  * Replaces the per-env-step host round trip of RigidSimulator.step / set_ext_state / step_grad / get_ext_state_grad
  * (softmac/engine/rigid_simulator.py:85-220): the bridge reads primitive.ext_f / substeps in float32 (:92-93), ignores
  * wrenches below 1e-10 or of primitives with enable_external_force == False (:96), advances the bodies, and writes pose +
  * twist into the next `substeps` primitive frames in float32 (:185, :200-201); backwards it sums get_all_states_grad over
  * those frames (:207-216), emits the action gradient and set_ext_f_grad(. / substeps) (:166-168).
- * The integrator is affine,  s' = s As + a Aa + w Aw + c,  and the pose map of a body is closed form (its Jacobian by
- * central differences, eps 1e-6, as the host bridge takes it), so all of that is one small kernel per env step on the
+ * The integrator is affine,  s' = s As + a Aa + w Aw + c,  and the pose map of a body is closed form (its Jacobian in closed
+ * form for prismatic / revolute joints, by central differences, eps 1e-6, for the free joint -- as the host bridge), so all of that is one small kernel per env step on the
  * simulator's stream: no synchronisation inside an episode.  State layout: [q (state_dim / 2), q_dot (state_dim / 2)],
- * the dofs of primitive i's body at dof_offset_i (prismatic: 1; free: 3 exponential coordinates + 3 translations).
+ * the dofs of primitive i's body at dof_offset_i (prismatic: 1; revolute: 1 hinge angle about `axis` through the link origin;
+ * free: 3 exponential coordinates + 3 translations).
  * Row-major f64: As (state_dim, state_dim), Aa (action_dim, state_dim), Aw (6 * n_primitives, state_dim), c (state_dim),
  * body (n_primitives, 10) = origin(3) quat0(4, w first) axis(3); int32: joint (n_primitives, 2) = (type: 0 fixed,
- * 1 prismatic, 2 free; dof_offset), enable (n_primitives); init_state (state_dim). */
+ * 1 prismatic, 2 free, 3 revolute; dof_offset), enable (n_primitives); init_state (state_dim). */
 typedef struct {
     int32_t state_dim, action_dim;
     int32_t max_env_steps;        /* env steps kept (states, actions, action gradients, wrench masks) */
@@ -242,6 +243,11 @@ int smx_add_x_grad(smx_sim* sim, int32_t f, const double* g3);
  * accumulated into the loss seed of frame f (nearest neighbours by brute force, reference tie rule, fixed in the gradient). */
 int smx_set_chamfer_target(smx_sim* sim, const double* target, int32_t m);
 int smx_chamfer_loss(smx_sim* sim, int32_t f, double weight, double* loss_out);
+/* Contact-distance term of DoorLoss / TransportLoss on the device (softmac/engine/losses/loss_door.py:46-56, loss_transport.py:54-70):
+ * per controller group g (particle ids [g npc, (g+1) npc), npc = n_particles / n_groups) m_g = min(min_i max(|x_i - p|^2 - 0.01, 0), 1e6)
+ * with p the position of primitive prim_id at frame f; loss_out[b] = weight * sum_g m_g^2 of rollout b (n_batch values); the gradient
+ * goes into the loss seed of frame f (minimising particle, smallest id among ties) and into the primitive's position adjoint. */
+int smx_contact_distance_loss(smx_sim* sim, int32_t f, int32_t prim_id, int32_t n_groups, double weight, double* loss_out);
 /* adjoint of frame f; only the frame most recently produced by smx_substep_grad is resident
  * (no per-frame gradient arrays are kept) */
 int smx_get_state_grad(smx_sim* sim, int32_t f, double* out24);

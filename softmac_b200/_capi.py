@@ -124,6 +124,7 @@ _SIGS = {
     "smx_add_x_grad": [vp, C.c_int32, dp],
     "smx_set_chamfer_target": [vp, dp, C.c_int32],
     "smx_chamfer_loss": [vp, C.c_int32, C.c_double, dp],
+    "smx_contact_distance_loss": [vp, C.c_int32, C.c_int32, C.c_int32, C.c_double, dp],
     "smx_get_state_grad": [vp, C.c_int32, dp],
     "smx_reset_dev": [vp, vp],
     "smx_get_state_dev": [vp, C.c_int32, vp],

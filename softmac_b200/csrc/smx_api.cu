@@ -149,6 +149,7 @@ struct smx_sim {
     bool bwd_fusion = true;             // P2G adjoint (f) + G2P adjoint (f-1) in one launch inside smx_step_grad (SMX_NO_BWD_FUSION=1: off)
     int grad_pending = -1, mid_done = -1, grad_mid_done = -1;
     float* ch_target = nullptr; int ch_m = 0; double* ch_loss = nullptr;   // Chamfer target cloud (m,3) and loss accumulator
+    unsigned long long* cd_buf = nullptr; int cd_cap = 0;                 // contact-distance loss scratch: per (rollout, group) [min bits, id], winner slots, per-rollout loss
     int last_fwd = -1;
     long long g_in_clean_uid = -1;      // ordering whose active blocks of g_in are known to be zero (k_grid_op re-zeroes them)
     struct Seed { float* dev = nullptr; int ncols = 24; };
@@ -712,7 +713,7 @@ int smx_destroy(smx_sim* s) {
     for (auto& kv : s->seeds) cudaFree(kv.second.dev);
     for (auto& kv : s->seed_pool) cudaFree(kv.second);
     for (auto& p : s->prims) { cudaFree(p.sdf_dev); cudaFree(p.nrm_dev); }
-    void* ptrs[] = {s->near_pool, s->svd_pool, s->ch_target, s->ch_loss, s->ckpt, s->pool, s->g_in, s->g_out, s->g_mix, s->gg_out, s->gg_out_b, s->gg_mix, s->g_lin, s->adj_cur, s->adj_nxt, s->stage_dev, s->keys_a, s->keys_b, s->iota, s->cub_tmp,
+    void* ptrs[] = {s->near_pool, s->svd_pool, s->ch_target, s->ch_loss, s->cd_buf, s->ckpt, s->pool, s->g_in, s->g_out, s->g_mix, s->gg_out, s->gg_out_b, s->gg_mix, s->g_lin, s->adj_cur, s->adj_nxt, s->stage_dev, s->keys_a, s->keys_b, s->iota, s->cub_tmp,
                     s->counters, s->prims_dev, s->pstate, s->pgrad, s->ext_f, s->ext_f_grad, s->abuf, s->gabuf, s->ctrl_id, s->action, s->action_grad,
                     s->rig_arena, s->rig_enable, s->rig_masks, s->ckpt_need};
     for (void* p : ptrs) cudaFree(p);
@@ -1149,7 +1150,7 @@ int smx_get_action_grad(smx_sim* s, double* out) {
     return SMX_OK;
 }
 
-// ---- device-resident rigid coupling (fixed / prismatic / free joints): RigidSimulator.step / step_grad on the simulator's stream ------------
+// ---- device-resident rigid coupling (fixed / prismatic / revolute / free joints): RigidSimulator.step / step_grad on the simulator's stream ------------
 int smx_rigid_linear_create(smx_sim* s, const smx_rigid_linear* d) {
     if (!s || !d) return fail(SMX_ERR_ARG, "smx_rigid_linear_create: null argument");
     const int np = (int)s->prims.size(), sd = d->state_dim, ad = d->action_dim, K = d->max_env_steps, B = s->B;
@@ -1161,8 +1162,8 @@ int smx_rigid_linear_create(smx_sim* s, const smx_rigid_linear* d) {
     CK(cudaStreamSynchronize(s->stream));
     cudaFree(s->rig_arena); cudaFree(s->rig_enable); cudaFree(s->rig_masks); s->rig_arena = nullptr; s->rig_enable = nullptr; s->rig_masks = nullptr; s->rig_on = false;
     for (int i = 0; i < np; i++) {
-        const int jt = d->joint[2 * i], o = d->joint[2 * i + 1], nd = jt == 0 ? 0 : (jt == 1 ? 1 : 6);
-        if (jt < 0 || jt > 2 || o < 0 || 2 * (o + nd) > sd || (sd & 1)) return fail(SMX_ERR_RANGE, "smx_rigid_linear_create: joint %d of primitive %d (dof offset %d) does not fit state_dim %d", jt, i, o, sd);
+        const int jt = d->joint[2 * i], o = d->joint[2 * i + 1], nd = rig_ndof(jt);
+        if (jt < 0 || jt > 3 || o < 0 || 2 * (o + nd) > sd || (sd & 1)) return fail(SMX_ERR_RANGE, "smx_rigid_linear_create: joint %d of primitive %d (dof offset %d) does not fit state_dim %d", jt, i, o, sd);
     }
     const size_t nAs = (size_t)sd * sd, nAa = (size_t)ad * sd, nAw = (size_t)6 * np * sd, nc = sd, nbody = (size_t)np * 10;
     const size_t nst = (size_t)(K + 1) * B * sd, nact = (size_t)K * B * std::max(ad, 1), nsg = (size_t)B * sd;
@@ -1680,6 +1681,49 @@ int smx_chamfer_loss(smx_sim* s, int32_t f, double weight, double* loss_out) {
     k_chamfer<<<dim3(nblk(s->P.npb, per_cta), s->B), 128, 0, s->stream>>>(s->P, s->frame_ptr(f), perm, s->ch_target, s->ch_m, (float)weight, it->second.dev, it->second.ncols, s->ch_loss, 0); CKL(s);
     k_chamfer<<<dim3(nblk(s->ch_m, per_cta), s->B), 128, 0, s->stream>>>(s->P, s->frame_ptr(f), perm, s->ch_target, s->ch_m, (float)weight, it->second.dev, it->second.ncols, s->ch_loss, 1); CKL(s);
     CK(cudaMemcpyAsync(loss_out, s->ch_loss, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return SMX_OK;
+}
+
+// Contact-distance term of DoorLoss / TransportLoss (loss_door.py:46-56, loss_transport.py:54-70) on the device: value per rollout
+// into loss_out[n_batch]; gradient into the loss seed of frame f (minimising particle) and into the primitive's position adjoint.
+int smx_contact_distance_loss(smx_sim* s, int32_t f, int32_t prim_id, int32_t n_groups, double weight, double* loss_out) {
+    TRY(check_frame(s, f, "smx_contact_distance_loss"));
+    TRY(check_prim(s, prim_id, "smx_contact_distance_loss"));
+    if (!loss_out) return fail(SMX_ERR_ARG, "smx_contact_distance_loss: null output");
+    if (n_groups < 1 || n_groups > 64) return fail(SMX_ERR_RANGE, "smx_contact_distance_loss: n_groups in [1, 64]");
+    if (s->order_of[f] < 0) return fail(SMX_ERR_STATE, "smx_contact_distance_loss: frame %d has not been written", f);
+    CK(cudaSetDevice(s->cfg.device));
+    const int n = s->P.n, B = s->B, npc = s->P.npb / n_groups, nt = B * n_groups;
+    for (int b = 0; b < B; b++) loss_out[b] = 0.0;
+    if (n == 0 || npc == 0) return SMX_OK;
+    if (s->cd_cap < nt) {
+        CK(cudaStreamSynchronize(s->stream));
+        cudaFree(s->cd_buf); s->cd_buf = nullptr;
+        CK(cudaMalloc(&s->cd_buf, (size_t)nt * 4 * sizeof(unsigned long long)));      // [2 nt] best, [nt] slots (u32 in u64 cells), [nt >= B] loss
+        s->cd_cap = nt;
+    }
+    auto it = s->seeds.find(f);
+    if (it == s->seeds.end()) {         // create an x-only seed buffer for this frame
+        smx_sim::Seed sd; sd.ncols = 3;
+        TRY(seed_alloc(s, (size_t)n * 3 * sizeof(float), &sd.dev));
+        CK(cudaMemsetAsync(sd.dev, 0, (size_t)n * 3 * sizeof(float), s->stream));
+        s->seeds[f] = sd;
+        it = s->seeds.find(f);
+    }
+    unsigned long long* best = s->cd_buf;
+    uint32_t* slots = reinterpret_cast<uint32_t*>(s->cd_buf + 2 * (size_t)nt);
+    double* loss = reinterpret_cast<double*>(s->cd_buf + 3 * (size_t)nt);
+    CK(cudaMemsetAsync(best, 0xff, (size_t)nt * 2 * sizeof(unsigned long long), s->stream));
+    CK(cudaMemsetAsync(s->cd_buf + 2 * (size_t)nt, 0, (size_t)nt * 2 * sizeof(unsigned long long), s->stream));
+    const uint32_t* perm = s->orders[s->order_of[f]].perm;
+    const float* fr = s->frame_ptr(f);
+    const int T = s->cfg.max_steps;
+    k_contact_dist_min<<<nblk(n, 256), 256, 0, s->stream>>>(s->P, fr, perm, s->pstate, T, prim_id, f, n_groups, npc, best, 0); CKL(s);
+    k_contact_dist_min<<<nblk(n, 256), 256, 0, s->stream>>>(s->P, fr, perm, s->pstate, T, prim_id, f, n_groups, npc, best, 1); CKL(s);
+    k_contact_dist_slot<<<nblk(n, 256), 256, 0, s->stream>>>(s->P, perm, n_groups, npc, best, slots); CKL(s);
+    k_contact_dist_finish<<<nblk(nt, 64), 64, 0, s->stream>>>(s->P, fr, s->pstate, s->pgrad, T, prim_id, f, n_groups, npc, best, weight, it->second.dev, it->second.ncols, loss, slots); CKL(s);
+    CK(cudaMemcpyAsync(loss_out, loss, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
     return SMX_OK;
 }

@@ -1676,6 +1676,66 @@ __global__ void __launch_bounds__(128) k_chamfer(Params P, const float* __restri
     for (int o = 16; o > 0; o >>= 1) partial += __shfl_xor_sync(0xffffffffu, partial, o);
     if ((threadIdx.x & 31) == 0 && partial != 0.f) atomicAdd(loss, (double)(weight * partial));
 }
+// ------------------------------------------------------------------------------------------------
+// Contact-distance term of DoorLoss / TransportLoss on the device (softmac/engine/losses/loss_door.py:46-56,
+// loss_transport.py:54-70): per controller group g (particle ids [g npc, (g+1) npc) of a rollout),
+//   m_g = min(min_i max(|x_i - p|^2 - 0.01, 0), 1e6),   loss += weight * sum_g m_g^2,
+// p = position of one primitive at frame f; the gradient 2 m_g * 2 (x_i - p) goes to the minimising particle (smallest id among
+// equal minima, as numpy.argmin in the host mirror) and, negated, to the primitive position.  Distances in f64 from the fp32 frame,
+// exactly as the host mirror computes them.  pass 0: minimum of the distance bits; pass 1: smallest id that attains it; then
+// k_contact_dist_finish (one thread per (rollout, group)).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double contact_dist_of(const Params& P, const float* __restrict__ fr, int j, const float* __restrict__ ps13) {
+    V3 x = load_x(fr, P.stride, j);
+    const double dx = (double)x.x - (double)ps13[0], dy = (double)x.y - (double)ps13[1], dz = (double)x.z - (double)ps13[2];
+    return fmax(dx * dx + dy * dy + dz * dz - 0.01, 0.0);
+}
+__global__ void __launch_bounds__(256) k_contact_dist_min(Params P, const float* __restrict__ fr, const uint32_t* __restrict__ perm, const float* __restrict__ pstate,
+                                                          int T, int prim, int f, int ngroups, int npc, unsigned long long* __restrict__ best, int pass) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= P.n) return;
+    const int bt = batch_of(P, j);
+    const uint32_t id = (perm ? perm[j] : (uint32_t)j) - (uint32_t)(bt * P.npb);       // particle id inside its rollout
+    const int g = (int)(id / (uint32_t)npc);
+    if (g >= ngroups) return;                                                           // the reference loops over n_groups * npc particles only
+    const double d = contact_dist_of(P, fr, j, pstate + (((size_t)bt * SMX_MAXP + prim) * T + f) * 13);
+    unsigned long long* slot = best + 2 * ((size_t)bt * ngroups + g);
+    // non-negative doubles order like their bit patterns
+    if (pass == 0) atomicMin(slot, (unsigned long long)__double_as_longlong(d));
+    else if ((unsigned long long)__double_as_longlong(d) == slot[0]) atomicMin(slot + 1, (unsigned long long)id);
+}
+__global__ void k_contact_dist_finish(Params P, const float* __restrict__ fr, const float* __restrict__ pstate, double* __restrict__ pgrad, int T, int prim, int f, int ngroups, int npc,
+                                      const unsigned long long* __restrict__ best, double weight, float* __restrict__ seed, int ncols, double* __restrict__ loss,
+                                      uint32_t* __restrict__ slot_of_winner) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= P.nbatch * ngroups) return;
+    const int bt = t / ngroups, g = t % ngroups;
+    const double dmin = __longlong_as_double((long long)best[2 * t]);
+    const double m = fmin(dmin, 1e6);
+    atomicAdd(loss + bt, weight * m * m);
+    if (!(m > 0.0 && m < 1e6)) return;
+    const uint32_t id = (uint32_t)best[2 * t + 1];
+    const int j = (int)slot_of_winner[t];                                               // storage slot of the winner (found by k_contact_dist_slot)
+    const float* ps13 = pstate + (((size_t)bt * SMX_MAXP + prim) * T + f) * 13;
+    V3 x = load_x(fr, P.stride, j);
+    const double k = weight * 2.0 * m * 2.0;
+    const double gx = k * ((double)x.x - (double)ps13[0]), gy = k * ((double)x.y - (double)ps13[1]), gz = k * ((double)x.z - (double)ps13[2]);
+    float* row = seed + ((size_t)bt * P.npb + id) * ncols;
+    atomicAdd(row, (float)gx); atomicAdd(row + 1, (float)gy); atomicAdd(row + 2, (float)gz);
+    double* pg = pgrad + (((size_t)bt * SMX_MAXP + prim) * T + f) * 13;
+    atomicAdd(pg, -gx); atomicAdd(pg + 1, -gy); atomicAdd(pg + 2, -gz);
+}
+// storage slot of every (rollout, group) winner: the slot whose particle id equals the recorded one
+__global__ void __launch_bounds__(256) k_contact_dist_slot(Params P, const uint32_t* __restrict__ perm, int ngroups, int npc, const unsigned long long* __restrict__ best,
+                                                           uint32_t* __restrict__ slot_of_winner) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= P.n) return;
+    const int bt = batch_of(P, j);
+    const uint32_t id = (perm ? perm[j] : (uint32_t)j) - (uint32_t)(bt * P.npb);
+    const int g = (int)(id / (uint32_t)npc);
+    if (g >= ngroups) return;
+    if ((unsigned long long)id == best[2 * ((size_t)bt * ngroups + g) + 1]) slot_of_winner[bt * ngroups + g] = (uint32_t)j;
+}
 // Primitive.forward_kinematics and its adjoint (primitive_base.py:280-283, primitive_utils.py:20-40); one thread
 __global__ void k_forward_kinematics(float* __restrict__ pstate, int T, int np, int nbatch, int f, float dt) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;

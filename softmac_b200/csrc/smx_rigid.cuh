@@ -1,5 +1,5 @@
-// smx_rigid.cuh -- device-resident rigid coupling for bodies on fixed, prismatic or free joints (the gripper of demo_grip, the
-// glass and bowl of demo_pour).  SURVEY.md 8f row 3: removes the per-env-step host round trip of the rigid bridge.
+// smx_rigid.cuh -- device-resident rigid coupling for bodies on fixed, prismatic, revolute or free joints (the gripper of demo_grip,
+// the glass and bowl of demo_pour, the hinged door of demo_door: config/demo_door_config.py:31-56, assets/door/door.urdf).  SURVEY.md 8f row 3: removes the per-env-step host round trip of the rigid bridge.
 //
 // What the reference does once per env step on the host (softmac/engine/rigid_simulator.py):
 //   step          :85-137   read primitive.ext_f / substeps (float32, :92-93), ignore wrenches below 1e-10 or of primitives with
@@ -29,7 +29,7 @@ struct RigidLin {
     double scale;                                   // ext_grad_scale (rigid_simulator.py:83, :148)
     const double *As, *Aa, *Aw, *c;                 // (sd,sd) (ad,sd) (6 np,sd) (sd), row-major
     const double* body;                             // (np,10): origin(3) quat0(4, w first) axis(3) of the body behind primitive i
-    const int* joint;                               // (np,2): joint type (0 fixed, 1 prismatic, 2 free), offset of its dofs in the state
+    const int* joint;                               // (np,2): joint type (0 fixed, 1 prismatic, 2 free, 3 revolute), offset of its dofs in the state
     const int* enable;                              // (np) enable_external_force
     double *states, *actions, *action_grad, *state_grad;    // [K+1][B][sd] [K][B][ad] [K][B][ad] [B][sd]
     unsigned char* masks;                           // [K][B][np]: wrench of env step k was fed to the bodies
@@ -49,7 +49,9 @@ __device__ __forceinline__ void rig_qrot(const double* q, const double* v, doubl
 }
 // pose + twist of one body from the rigid state: [x(3) q(4) v(3) w(3)], position / quaternion in the world, body-frame twist
 // (what the Jade bridge reads back per body, rigid_simulator.py:176-186); h = sd / 2 separates positions from velocities.
-// `bump` / `delta` perturb state entry `bump` for the central differences of the adjoint.
+// `bump` / `delta` perturb state entry `bump` for the central differences of the adjoint (free joints; the other joints use the
+// closed-form Jacobian, rigid_pose_vjp).
+__host__ __device__ __forceinline__ int rig_ndof(int joint) { return joint == 0 ? 0 : (joint == 2 ? 6 : 1); }
 __device__ void rigid_pose(const double* __restrict__ body, int joint, int o, int h, const double* __restrict__ s, int bump, double delta, double* out) {
     auto S = [&](int i) { return s[i] + (i == bump ? delta : 0.0); };
     const double* org = body; const double* q0 = body + 3; const double* ax = body + 7;
@@ -63,6 +65,12 @@ __device__ void rigid_pose(const double* __restrict__ body, int joint, int o, in
         for (int i = 0; i < 3; i++) out[i] = org[i] + aw[i] * q;
         for (int i = 0; i < 4; i++) out[3 + i] = q0[i];
         for (int i = 0; i < 3; i++) { out[7 + i] = ax[i] * qd; out[10 + i] = 0.0; }
+    } else if (joint == 3) {        // hinge through the link origin: R = R0 Rot(axis, theta); body-frame twist (0, axis * omega)
+        const double th = S(o), om = S(h + o);
+        const double sn = sin(0.5 * th), qt[4] = {cos(0.5 * th), sn * ax[0], sn * ax[1], sn * ax[2]};
+        for (int i = 0; i < 3; i++) out[i] = org[i];
+        rig_qmul(q0, qt, out + 3);
+        for (int i = 0; i < 3; i++) { out[7 + i] = 0.0; out[10 + i] = ax[i] * om; }
     } else {
         const double e[3] = {S(o), S(o + 1), S(o + 2)};
         const double th = sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
@@ -77,6 +85,20 @@ __device__ void rigid_pose(const double* __restrict__ body, int joint, int o, in
         rig_qrot(inv, lv, out + 7);
         rig_qrot(inv, wv, out + 10);
     }
+}
+
+// pg (13) . d pose / d state entry for prismatic (joint 1) and revolute (joint 3) joints, closed form; vel: the entry is the joint velocity
+__device__ __forceinline__ double rigid_pose_vjp(const double* __restrict__ body, int joint, const double* __restrict__ s, int o, bool vel, const double* __restrict__ pg) {
+    const double* q0 = body + 3; const double* ax = body + 7;
+    if (joint == 1) {
+        if (vel) return pg[7] * ax[0] + pg[8] * ax[1] + pg[9] * ax[2];
+        double aw[3]; rig_qrot(q0, ax, aw);
+        return pg[0] * aw[0] + pg[1] * aw[1] + pg[2] * aw[2];
+    }
+    if (vel) return pg[10] * ax[0] + pg[11] * ax[1] + pg[12] * ax[2];
+    const double th = s[o], c = 0.5 * cos(0.5 * th), dqt[4] = {-0.5 * sin(0.5 * th), c * ax[0], c * ax[1], c * ax[2]};
+    double dq[4]; rig_qmul(q0, dqt, dq);
+    return pg[3] * dq[0] + pg[4] * dq[1] + pg[5] * dq[2] + pg[6] * dq[3];
 }
 
 // advance == 1: env step k (after its substeps ran): wrench -> s[k+1], poses of frames [f0, f1), wrench cleared.
@@ -144,18 +166,21 @@ __global__ void __launch_bounds__(128) k_rigid_linear_step_grad(RigidLin R, int 
     // the poses of frames [f0, f1) were produced from the state AFTER env step k (state k + 1); the initial ones from state 0
     if (t < R.sd) { g[t] = R.state_grad[(size_t)b * R.sd + t]; g2[t] = g[t]; sk[t] = R.states[((size_t)(finish ? 0 : k + 1) * R.B + b) * R.sd + t]; }
     __syncthreads();
-    {   // one thread per (primitive, own state entry): d pose / d state by central differences (eps 1e-6, as the host bridge)
+    {   // one thread per (primitive, own state entry): d pose / d state in closed form (prismatic, revolute) or by central differences
+        // (free joint; eps 1e-6, as the host bridge)
         const int p = t / 12, l = t % 12;
         if (p < R.np) {
             const int joint = R.joint[2 * p], o = R.joint[2 * p + 1], h = R.sd / 2;
-            const int ndof = joint == 0 ? 0 : (joint == 1 ? 1 : 6);
+            const int ndof = rig_ndof(joint);
             if (l < 2 * ndof) {
                 const int i = l < ndof ? o + l : h + o + (l - ndof);
-                double hi[13], lo[13];
-                rigid_pose(R.body + 10 * p, joint, o, h, sk, i, 1e-6, hi);
-                rigid_pose(R.body + 10 * p, joint, o, h, sk, i, -1e-6, lo);
                 double acc = 0;
-                for (int q = 0; q < 13; q++) acc += pg[p * 13 + q] * (hi[q] - lo[q]) / 2e-6;
+                if (joint == 2) {
+                    double hi[13], lo[13];
+                    rigid_pose(R.body + 10 * p, joint, o, h, sk, i, 1e-6, hi);
+                    rigid_pose(R.body + 10 * p, joint, o, h, sk, i, -1e-6, lo);
+                    for (int q = 0; q < 13; q++) acc += pg[p * 13 + q] * (hi[q] - lo[q]) / 2e-6;
+                } else acc = rigid_pose_vjp(R.body + 10 * p, joint, sk, o, l >= ndof, pg + p * 13);
                 g2[i] = g[i] + (finish ? 1.0 : R.scale) * acc;      // every state entry belongs to exactly one body: no race
             }
         }

@@ -167,13 +167,13 @@ class LinearBatchedRigid:
 
 
 class DeviceLinearRigid:
-    """The rigid stand-in moved onto the GPU (smx_rigid_linear_*, softmac_b200/csrc/smx_rigid.cuh): fixed, prismatic and free
+    """The rigid stand-in moved onto the GPU (smx_rigid_linear_*, softmac_b200/csrc/smx_rigid.cuh): fixed, prismatic, revolute and free
     joints; the integrator's constant matrices (``RigidSimulator._advance`` is affine in state, action and wrench) plus the
     closed-form pose map of every body, one small kernel per env step on the simulator's stream, so an episode runs without a
     single host <-> device round trip of the coupling (wrench, poses, state adjoints and wrench adjoints never leave the
     device; rigid_simulator.py:85-220)."""
 
-    JOINT = {"fixed": 0, "prismatic": 1, "free": 2}
+    JOINT = {"fixed": 0, "prismatic": 1, "free": 2, "revolute": 3}
 
     def __init__(self, proto, sim, n_batch, max_env_steps):
         self.p, self.sim, self.h, self.K = proto, sim, sim._h, int(max_env_steps)

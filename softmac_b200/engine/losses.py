@@ -197,6 +197,7 @@ class _PoseVelContactLoss:
         self.dim, self.n_particles, self.dtype = mpm_sim.dim, mpm_sim.n_particles, mpm_sim.dtype
         self.n_particles_per_controller = self.n_particles // self.n_groups
         self.rigid = mpm_sim.primitives[0]
+        self.device_contact = hasattr(mpm_sim, "_h")        # the CUDA simulator evaluates the contact term on the device
         self.weight = (1.0, 0.0, 0.0)
         self.target = []
         self.loss = 0.0
@@ -210,7 +211,17 @@ class _PoseVelContactLoss:
     def pose(self, s13):
         raise NotImplementedError
 
+    def contact_device(self, f, weight):
+        """The contact term on the GPU (smx_contact_distance_loss): no device->host copy of x; the seed goes straight into the
+        loss-seed buffer of frame f and into the position adjoint of primitives[0].  Returns the weighted value (summed over
+        batched rollouts)."""
+        from .._capi import lib, check, d_ptr
+        out = np.zeros(max(int(getattr(self.sim, "n_batch", 1)), 1))
+        check(lib().smx_contact_distance_loss(self.sim._h, int(f), int(getattr(self.rigid, "_id", 0)), int(self.n_groups), float(weight), d_ptr(out)))
+        return float(out.sum())
+
     def contact(self, x, pos):
+        """numpy restatement of the contact term (the checker of contact_device in tests/test_losses.py)"""
         npc = self.n_particles_per_controller
         val, gx, gp = 0.0, np.zeros_like(x), np.zeros(3)
         for k in range(self.n_groups):
@@ -238,11 +249,14 @@ class _PoseVelContactLoss:
             out["vel_loss"] = vw * val
             g += vw * gv
         if cw > 0:
-            val, gx, gpos = self.contact(self.sim.get_x(f), s13[:3])
-            out["contact_loss"] = cw * val
-            g[:3] += cw * gpos
-            if np.any(gx):
-                self.sim.add_x_grad(f, cw * gx)
+            if self.device_contact:
+                out["contact_loss"] = self.contact_device(f, cw)
+            else:
+                val, gx, gpos = self.contact(self.sim.get_x(f), s13[:3])
+                out["contact_loss"] = cw * val
+                g[:3] += cw * gpos
+                if np.any(gx):
+                    self.sim.add_x_grad(f, cw * gx)
         if np.any(g):
             self.rigid.add_all_states_grad(f, g)
         out["frame_loss"] = out["pose_loss"] + out["vel_loss"] + out["contact_loss"]

@@ -5,8 +5,10 @@ row 4); what IS on the hot path is its interface to the primitives: once per env
 wrench ``primitive.ext_f / substeps`` (rigid_simulator.py:92-93), advances the bodies, writes pose + twist of the next
 ``substeps`` frames with ``set_all_states`` (:200-201) and, in the backward pass, pulls ``get_all_states_grad`` (:207-208)
 and pushes ``ext_f_grad`` (:166-168).  This class reproduces exactly that call pattern around a tiny articulated-body
-integrator (fixed / prismatic / free joints, semi-implicit Euler) whose Jacobians are taken by central differences in
-f64 (state dimension <= 12 per body), so the coupling loop and its gradient chain can be run and tested end to end.
+integrator (fixed / prismatic / revolute / free joints, semi-implicit Euler) whose Jacobians are taken by central differences in
+f64 (state dimension <= 12 per body; closed form for fixed / prismatic / revolute joints, ``_pose_jac``), so the coupling loop and
+its gradient chain can be run and tested end to end.  The revolute joint covers the door scene (config/demo_door_config.py:31-56,
+assets/door/door.urdf: one hinge about y through the link origin).
 """
 import numpy as np
 
@@ -33,11 +35,11 @@ def _quat_rot(q, v):
 
 class Body:
     def __init__(self, joint="fixed", origin=(0, 0, 0), quat=(1, 0, 0, 0), axis=(1, 0, 0), mass=1.0, inertia=1.0, gravity=True):
-        assert joint in ("fixed", "prismatic", "free")
+        assert joint in ("fixed", "prismatic", "revolute", "free")
         self.joint, self.origin, self.quat0 = joint, np.asarray(origin, float), np.asarray(quat, float)
         self.axis = np.asarray(axis, float) / np.linalg.norm(axis)
         self.mass, self.inertia, self.gravity = float(mass), float(inertia), gravity
-        self.ndof = {"fixed": 0, "prismatic": 1, "free": 6}[joint]
+        self.ndof = {"fixed": 0, "prismatic": 1, "revolute": 1, "free": 6}[joint]
 
 
 def bodies_from_urdf(urdf_path):
@@ -65,15 +67,22 @@ def bodies_from_urdf(urdf_path):
         name = link.attrib["name"]
         j = joints.get(name)
         jt = j.attrib.get("type", "fixed") if j is not None else "floating"
-        joint = {"fixed": "fixed", "prismatic": "prismatic", "floating": "free"}.get(jt)
+        joint = {"fixed": "fixed", "prismatic": "prismatic", "floating": "free", "revolute": "revolute", "continuous": "revolute"}.get(jt)
         if joint is None:
             raise NotImplementedError(f"stand-in rigid simulator: joint type {jt!r} of link {name!r}")
         axis = (1, 0, 0)
         if j is not None and j.find("axis") is not None:
             axis = tuple(float(v) for v in j.find("axis").attrib["xyz"].split())
         mass = link.find("inertial/mass")
-        out.append(dict(joint=joint, axis=axis, origin=tuple(origin_of(name)), mass=float(mass.attrib["value"]) if mass is not None else 1.0,
-                        gravity=False))
+        spec = dict(joint=joint, axis=axis, origin=tuple(origin_of(name)), mass=float(mass.attrib["value"]) if mass is not None else 1.0,
+                    gravity=False)
+        it = link.find("inertial/inertia")
+        if joint == "revolute" and it is not None:      # moment of inertia about the hinge axis (the link frame sits on the hinge)
+            g = lambda k: float(it.attrib.get(k, 0.0))
+            I = np.array([[g("ixx"), g("ixy"), g("ixz")], [g("ixy"), g("iyy"), g("iyz")], [g("ixz"), g("iyz"), g("izz")]])
+            a = np.asarray(axis, float) / np.linalg.norm(axis)
+            spec["inertia"] = float(a @ I @ a)
+        out.append(spec)
     return out
 
 
@@ -117,6 +126,9 @@ class RigidSimulator:
         if b.joint == "prismatic":
             ax_w = _quat_rot(b.quat0, b.axis)
             return np.concatenate([b.origin + ax_w * q[0], b.quat0, b.axis * qd[0], np.zeros(3)])
+        if b.joint == "revolute":       # hinge through the link origin: R = R0 Rot(axis, theta); body-frame twist (0, axis * omega)
+            qt = np.concatenate([[np.cos(0.5 * q[0])], np.sin(0.5 * q[0]) * b.axis])
+            return np.concatenate([b.origin, _quat_mul(b.quat0, qt), np.zeros(3), b.axis * qd[0]])
         quat = _quat_mul(_exp2quat(q[:3]), b.quat0)
         inv = np.array([quat[0], -quat[1], -quat[2], -quat[3]])
         return np.concatenate([b.origin + q[3:], quat, _quat_rot(inv, qd[3:]), _quat_rot(inv, qd[:3])])
@@ -134,6 +146,13 @@ class RigidSimulator:
                 qd = state[h + o] + dt * (a[0] + ax_w @ (f + b.mass * g)) / b.mass
                 new[h + o] = qd
                 new[o] = state[o] + dt * qd
+            elif b.joint == "revolute":
+                # generalized force = hinge axis (world) . torque about the link origin; a force through the hinge does no work, and
+                # gravity has no moment about the vertical hinge of the door (a tilted hinge would make _advance non-affine: not modelled)
+                ax_w = _quat_rot(b.quat0, b.axis)
+                qd = state[h + o] + dt * (a[0] + ax_w @ tq) / b.inertia
+                new[h + o] = qd
+                new[o] = state[o] + dt * qd
             elif b.joint == "free":
                 g = self.gravity if b.gravity else 0.0
                 w = state[h + o:h + o + 3] + dt * (a[:3] + tq) / b.inertia
@@ -142,6 +161,23 @@ class RigidSimulator:
                 new[o:o + 3] = state[o:o + 3] + dt * w          # small-rotation update of the exponential coordinates
                 new[o + 3:o + 6] = state[o + 3:o + 6] + dt * v
         return new
+
+    def _pose_jac(self, state, i):
+        """d pose_i / d state, (13, state_dim): closed form for fixed / prismatic / revolute joints, central differences for the
+        free joint (exponential coordinates)."""
+        b, o, h = self.bodies[i], self.offsets[i], self.state_dim_half
+        if b.joint == "free":
+            return self._jac(lambda x: self._pose(x, i), state)
+        J = np.zeros((13, self.state_dim))
+        if b.joint == "prismatic":
+            J[0:3, o] = _quat_rot(b.quat0, b.axis)
+            J[7:10, h + o] = b.axis
+        elif b.joint == "revolute":
+            th = state[o]
+            dqt = np.concatenate([[-0.5 * np.sin(0.5 * th)], 0.5 * np.cos(0.5 * th) * b.axis])
+            J[3:7, o] = _quat_mul(b.quat0, dqt)
+            J[10:13, h + o] = b.axis
+        return J
 
     @staticmethod
     def _jac(fn, x, eps=1e-6):
@@ -198,7 +234,7 @@ class RigidSimulator:
 
     def set_ext_state(self, s):
         st = self.states[-1]
-        self.jacob_external.append([self._jac(lambda x, i=i: self._pose(x, i), st) for i in range(self.n_primitive)])
+        self.jacob_external.append([self._pose_jac(st, i) for i in range(self.n_primitive)])
         for i in range(self.n_primitive):
             pose = self._pose(st, i)
             if self.fp32_bridge:

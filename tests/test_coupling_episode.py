@@ -72,6 +72,39 @@ def test_env_loop_runs_with_oracle_backend():
         assert abs(fd - grad[idx]) <= 2e-2 * max(abs(fd), abs(grad[idx]), 1e-8), (idx, fd, grad[idx])
 
 
+def test_revolute_joint_env_loop_gradient_matches_finite_differences():
+    """The door scene's joint (config/demo_door_config.py:31-56: one hinge about the vertical axis) in the env loop on the oracle
+    backend: a slab swings into the material; the action (hinge torque) gradient from the adjoint chain -- MPM adjoint, wrench
+    coupling, closed-form pose Jacobian of the revolute joint -- against central differences of the whole episode."""
+    from softmac_b200.engine.taichi_env import TaichiEnv
+    from softmac_b200.engine.rigid_simulator import RigidSimulator
+    from softmac_b200.engine.losses import PointwiseLoss
+    from softmac_b200.config import CfgNode
+    from oracle_backend import OracleMPMSimulator
+    n, env_steps, substeps, n_grid, dt = 800, 4, 5, 32, 2e-4
+    max_steps = env_steps * substeps + substeps + 2
+    rng = np.random.default_rng(6)
+    x = ((rng.random((n, 3)) * 2 - 1) * 0.05 + np.array([0.5, 0.3, 0.5])).astype(np.float32).astype(np.float64)
+    tab = scenes.box_table(half=(0.10, 0.04, 0.03), dx=0.01, margin=0.04)
+    sim = OracleMPMSimulator(n, n_grid, max_steps, dt, substeps, tables=[tab], prim_params=[(0.3, 666.)], E=3e3, nu=0.2, gravity=(0., -9.8, 0.),
+                             ground_friction=20., material_model=0, ptype=0, collision_type=2)
+    bodies = [dict(joint="revolute", axis=(0, 1, 0), origin=(0.40, 0.3, 0.42), inertia=2e-3, gravity=False)]
+    rigid = RigidSimulator(CfgNode(gravity=(0., -9.8, 0.), init_state=(0.002, -4.0), bodies=bodies), sim.primitives, substeps=substeps,
+                           env_dt=dt * substeps, fp32_bridge=False)
+    env = TaichiEnv(sim, sim.primitives, rigid, x, loss=PointwiseLoss(sim, x + np.array([0.0, 0.01, 0.0])), control_mode="rigid")
+    actions = np.tile([-0.5], (env_steps, 1))
+    f_end = env_steps * substeps
+    loss, grad, rstate, _ = run_episode(env, actions, [f_end])
+    assert grad.shape == (env_steps, 1) and np.abs(grad[:-1]).min() > 0 and grad[-1, 0] == 0       # the last action moves frames past the loss
+    assert abs(rstate[1] + 4.0) > 0.2                                                            # the hinge felt torque and action
+    eps = 1e-2
+    for k in (0, 2):
+        ap, am = actions.copy(), actions.copy()
+        ap[k] += eps; am[k] -= eps
+        fd = (run_episode(env, ap, [f_end])[0] - run_episode(env, am, [f_end])[0]) / (2 * eps)
+        assert abs(fd - grad[k, 0]) <= 2e-2 * abs(fd), (k, fd, grad[k, 0])
+
+
 @pytest.mark.gpu
 def test_episode_action_gradient_cosine():
     env_steps, substeps = 6, 5

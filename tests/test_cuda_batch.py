@@ -143,12 +143,14 @@ def test_batched_env_matches_single_rollout_envs():
         assert np.abs(g1).max() > 0 and rel_l2(gb[b], g1) <= 1e-3, (gb[b], g1)
 
 
-@pytest.mark.parametrize("joints", ["prismatic", "free"])
+@pytest.mark.parametrize("joints", ["prismatic", "free", "revolute"])
 def test_device_resident_rigid_coupling_matches_host_bridge(joints):
     """smx_rigid_linear_* (the rigid stand-in on the GPU, no host round trip per env step) == the host bridges: same particle
     states, rigid states, action gradients and adjoint of the initial rigid state.  "prismatic": two fingers + a fixed body whose
     wrench is ignored (enable_external_force = False, rigid_simulator.py:96), checked against LinearBatchedRigid; "free": two
-    free-floating bodies with spin (demo_pour's joints: the pose map is nonlinear), checked against one Python bridge per rollout."""
+    free-floating bodies with spin (demo_pour's joints: the pose map is nonlinear), checked against one Python bridge per rollout;
+    "revolute": a hinged slab swinging into the material about a vertical axis plus a fixed body (the door scene's joint,
+    config/demo_door_config.py:31-56), closed-form pose Jacobian on both sides."""
     from softmac_b200.engine import MPMSimulator, Primitives, Mesh
     from softmac_b200.engine.batched_env import BatchedTaichiEnv
     from softmac_b200.engine.rigid_simulator import RigidSimulator
@@ -166,6 +168,16 @@ def test_device_resident_rigid_coupling_matches_host_bridge(joints):
         init = (0., 0., 0.4, -0.4)
         actions = np.stack([np.tile([40.0, -40.0], (env_steps, 1)), np.tile([10.0, -70.0], (env_steps, 1)), np.tile([0.0, 0.0], (env_steps, 1))])
         enable = [True, True, False]
+    elif joints == "revolute":
+        tab = scenes.box_table(half=(0.10, 0.04, 0.03), dx=0.01, margin=0.04)
+        # the slab lies along x beside the particle cloud (its +z face just short of the cloud's boundary z = 0.45 for x in [0.45, 0.50]: no
+        # particle starts inside it, which would eject it at sdf / dt) and swings into the cloud about the vertical hinge at its centre:
+        # z' = -x sin(theta), so omega < 0 moves the free end towards +z
+        bodies = [dict(joint="revolute", axis=(0, 1, 0), origin=(0.40, 0.3, 0.42), inertia=2e-3, gravity=False),
+                  dict(joint="fixed", origin=(0.5, 0.3 + 0.12, 0.5))]
+        init = (0.002, -4.0)
+        actions = np.stack([np.tile([-0.5], (env_steps, 1)), np.tile([0.8], (env_steps, 1)), np.tile([0.0], (env_steps, 1))])
+        enable = [True, False]
     else:
         bodies = [dict(joint="free", origin=(0.5 - 0.106, 0.3, 0.5), quat=(0.9238795, 0.0, 0.3826834, 0.0), mass=1.0, inertia=0.02, gravity=True),
                   dict(joint="free", origin=(0.5 + 0.106, 0.3, 0.5), mass=2.0, inertia=0.05, gravity=False)]

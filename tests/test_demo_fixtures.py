@@ -49,10 +49,11 @@ def test_standin_integrator_is_affine_for_every_joint_type():
     from softmac_b200.config import CfgNode
     bodies = [dict(joint="free", origin=(0.4, 0.3, 0.5), quat=(0.9238795, 0, 0.3826834, 0), mass=1.3, inertia=0.02, gravity=True),
               dict(joint="prismatic", axis=(0.6, 0.8, 0.0), origin=(0.6, 0.3, 0.5), mass=2.0, gravity=True),
-              dict(joint="fixed", origin=(0.5, 0.5, 0.5))]
-    r = RigidSimulator(CfgNode(gravity=(0, -9.8, 0), init_state=(), bodies=bodies), [_Prim(), _Prim(), _Prim()], substeps=5, env_dt=1e-3)
-    sd, ad, nw = r.state_dim, r.action_dim, 18
-    assert (sd, ad) == (14, 7)
+              dict(joint="fixed", origin=(0.5, 0.5, 0.5)),
+              dict(joint="revolute", axis=(0.0, 0.6, 0.8), origin=(0.25, 0.0, 0.3), quat=(0.9659258, 0.2588190, 0, 0), inertia=7.8e-6)]
+    r = RigidSimulator(CfgNode(gravity=(0, -9.8, 0), init_state=(), bodies=bodies), [_Prim(), _Prim(), _Prim(), _Prim()], substeps=5, env_dt=1e-3)
+    sd, ad, nw = r.state_dim, r.action_dim, 24
+    assert (sd, ad) == (16, 8)
     s0, a0, w0 = np.zeros(sd), np.zeros(ad), np.zeros(nw)
     c = r._advance(s0, a0, w0)                      # what DeviceLinearRigid.__init__ computes (eps = 1: exact for an affine map)
     As = r._jac(lambda x: r._advance(x, a0, w0), s0, eps=1.0).T
@@ -61,6 +62,36 @@ def test_standin_integrator_is_affine_for_every_joint_type():
     rng = np.random.default_rng(0)
     for _ in range(5):
         s, a, w = rng.normal(size=sd), rng.normal(size=ad), rng.normal(size=nw)
-        assert np.abs(r._advance(s, a, w) - (s @ As + a @ Aa + w @ Aw + c)).max() <= 1e-14
-    assert np.abs(Aw[12:]).max() == 0               # the fixed body ignores its wrench
-    assert c[7 + 4] < 0                             # gravity enters through the constant term (free body, y velocity)
+        ref = r._advance(s, a, w)
+        assert (np.abs(ref - (s @ As + a @ Aa + w @ Aw + c)) / np.maximum(1.0, np.abs(ref))).max() <= 1e-14
+    assert np.abs(Aw[12:18]).max() == 0             # the fixed body ignores its wrench
+    assert c[8 + 4] < 0                             # gravity enters through the constant term (free body, y velocity)
+    assert np.abs(Aw[18:21]).max() == 0 and np.abs(Aw[21:24, 8 + 7]).max() > 0      # a hinge only feels the torque about its axis
+    # closed-form pose Jacobians (fixed / prismatic / revolute) against central differences of the pose map
+    for i in (1, 2, 3):
+        for _ in range(3):
+            s = rng.normal(size=sd)
+            Ja, Jn = r._pose_jac(s, i), r._jac(lambda x: r._pose(x, i), s)
+            assert np.abs(Ja - Jn).max() <= 1e-8, (i, np.abs(Ja - Jn).max())
+    # the hinged body turns about its (body-frame) axis: R = R0 Rot(axis, theta), unit quaternion, twist (0, axis * omega)
+    s = np.zeros(sd); s[7] = 0.7; s[8 + 7] = -2.0
+    p = r._pose(s, 3)
+    assert np.allclose(p[:3], (0.25, 0.0, 0.3)) and np.isclose(np.linalg.norm(p[3:7]), 1.0)
+    assert np.allclose(p[7:10], 0) and np.allclose(p[10:13], -2.0 * np.array([0.0, 0.6, 0.8]))
+
+
+def test_door_urdf_maps_to_a_revolute_body(tmp_path):
+    """A door-like URDF (one revolute joint about y, inertia tensor on the child link; structure of assets/door/door.urdf) ->
+    one revolute Body with the moment of inertia about the hinge axis."""
+    from softmac_b200.engine.rigid_simulator import bodies_from_urdf, Body
+    urdf = """<?xml version="1.0" ?><robot name="d"><link name="world"/>
+      <joint name="j" type="revolute"><parent link="world"/><child link="leaf"/><origin xyz="0.25 0.0 0.3" rpy="0 0 0"/><axis xyz="0 1 0"/>
+        <limit lower="-3.14" upper="3.14" effort="0" velocity="6.5"/></joint>
+      <link name="leaf"><inertial><mass value="0.0125"/><inertia ixx="2.8e-06" ixy="0" ixz="0" iyy="7.9e-06" iyz="0" izz="1.1e-05"/></inertial>
+        <collision><geometry><mesh filename="leaf.obj"/></geometry></collision></link></robot>"""
+    path = tmp_path / "d.urdf"
+    path.write_text(urdf)
+    specs = bodies_from_urdf(str(path))
+    assert len(specs) == 1 and specs[0]["joint"] == "revolute" and specs[0]["axis"] == (0.0, 1.0, 0.0)
+    assert np.allclose(specs[0]["origin"], (0.25, 0.0, 0.3)) and np.isclose(specs[0]["inertia"], 7.9e-06)
+    assert Body(**specs[0]).ndof == 1

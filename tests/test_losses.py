@@ -103,3 +103,54 @@ def test_grip_loss_on_the_simulator_matches_the_numpy_restatement():
     exp[3] = 0.5 * (2 * min(0, a - 0.5) + 2 * max(0, a - 0.9)) * np.sign(st[3])
     exp[7:10] = 0.25 * 2 * st[7:10]; exp[10:13] = 0.25 * 0.2 * st[10:13]
     assert np.allclose(g13, exp, atol=1e-9)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cls_name", ["DoorLoss", "TransportLoss"])
+def test_contact_distance_term_on_the_device_matches_the_numpy_restatement(cls_name):
+    """DoorLoss / TransportLoss with weight (pose, velocity, contact): the contact term runs on the GPU (smx_contact_distance_loss);
+    value, particle seed and primitive-position adjoint against the numpy restatement (loss_door.py:46-56, loss_transport.py:54-70),
+    after a re-sort (storage order != particle id) and with the primitive far enough that the max(.., 0) is inactive."""
+    import scenes
+    from harness import Pair
+    from softmac_b200.engine import losses as L
+    rng = np.random.default_rng(17)
+    n = 1501                                            # odd: the last particle belongs to no group of TransportLoss
+    pair = Pair(n, tables=[scenes.sphere_table()], prim_params=[(0.5, 666.)], max_steps=6, sort_every=1)
+    s13 = np.concatenate([[0.5, 0.75, 0.45], [0.95, 0.1, 0.2, 0.1], [0.1, -0.2, 0.05], [0.3, 0.0, -0.4]])
+    pair.prims[0].set_all_states(0, s13, f_end=6)
+    pair.gpu.reset(scenes.blob_state(n, rng))
+    pair.gpu.substep(0); pair.gpu.substep(1)
+    f = 2
+    cls = getattr(L, cls_name)
+    loss = cls(dict(weight=(0.5, 0.25, 3.0)), pair.gpu)
+    loss.initialize()
+    if cls_name == "TransportLoss":
+        loss.set_target([0.4, 0.5, 0.6])
+    assert loss.device_contact
+    pair.gpu.clear_all_gradients()
+    info = loss.compute_loss(f)
+    x, st = pair.gpu.get_x(f), pair.prims[0].get_all_states(f)
+    val, gx, gp = loss.contact(x, st[:3])               # numpy restatement
+    assert val > 0 and np.isclose(info["contact_loss"], 3.0 * val, rtol=1e-12)
+    seed = pair.gpu.get_state_grad(f)
+    assert rel_l2(seed[:, :3], 3.0 * gx) <= 1e-6 and np.abs(seed[:, 3:]).max() == 0
+    assert np.count_nonzero(np.abs(seed[:, :3]).sum(1)) == loss.n_groups
+    g13 = pair.prims[0].get_all_states_grad(f)
+    pv, gpose = loss.pose(st)
+    vv, gvel = L._RigidTerms.velocity(st, 0.0)
+    exp = 0.5 * gpose + 0.25 * gvel
+    exp[:3] += 3.0 * gp
+    assert np.allclose(g13, exp, rtol=1e-6, atol=1e-9), (g13, exp)
+    assert np.isclose(info["loss"], 0.5 * pv + 0.25 * vv + 3.0 * val)
+    # inside the 0.1 ball around the primitive the term and its gradient vanish (max(.., 0) and the 0 < m test)
+    near = s13.copy(); near[:3] = x[7]
+    pair.prims[0].set_all_states(f, near)
+    pair.gpu.clear_all_gradients()
+    loss.clear()
+    loss.weight = (0.0, 0.0, 3.0)
+    info = loss.compute_loss(f)
+    val2 = loss.contact(x, pair.prims[0].get_all_states(f)[:3])[0]
+    assert np.isclose(info["contact_loss"], 3.0 * val2, rtol=1e-12, atol=1e-300)
+    if cls_name == "DoorLoss":
+        assert info["contact_loss"] == 0.0 and np.abs(pair.gpu.get_state_grad(f)).max() == 0

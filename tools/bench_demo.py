@@ -342,7 +342,7 @@ def main():
            "env_steps": K, "substeps_per_env_step": S, "dt": sc["dt"], "loss_frames": len(loss_frames),
            "rigid": "stand-in integrator (Jade not installable); its own numpy dynamics are subtracted from the timings", "arms": {}}
     tables = None
-    arms = args.arms or "dropin,batched,device"
+    arms = args.arms if args.arms is not None else "dropin,batched,device"      # --arms "" : parity leg only
     for arm in [a for a in arms.split(",") if a]:
         B = args.batch if arm in ("batched", "device") else 1
         env, sim, prims, clock, L = build_cuda(sc, K, batch=B, cache_dir=args.cache_dir, mode=arm, sort_every=args.sort_every)
