@@ -234,6 +234,18 @@ int smx_step(smx_sim* sim, int32_t s0, int32_t count);
 /* adjoint of substeps s1-1, s1-2, ..., s1-count (TaichiEnv.step_grad inner loop, taichi_env.py:128-131) */
 int smx_step_grad(smx_sim* sim, int32_t s1, int32_t count);
 
+/* fp32 host entry points (the optimiser's float32 tensors never pass through a host-side f64 conversion): same semantics as the f64
+ * calls they mirror -- MPMSimulator.reset / get_state / get_grad (mpm_simulator.py:448-574) and the loss seeds -- with float rows that
+ * travel as they are.  smx_host_register pins a caller buffer once (cudaHostRegister) so that these copies are plain DMA. */
+int smx_host_register(void* ptr, uint64_t bytes);
+int smx_host_unregister(void* ptr);
+int smx_reset_f32(smx_sim* sim, const float* state, int32_t ncols);
+int smx_get_state_f32(smx_sim* sim, int32_t f, float* out24);
+int smx_add_x_grad_f32(smx_sim* sim, int32_t f, const float* g3);
+int smx_add_state_grad_f32(smx_sim* sim, int32_t f, const float* g24);
+int smx_get_state_grad_f32(smx_sim* sim, int32_t f, float* out24);
+int smx_get_grad_f32(smx_sim* sim, int32_t f, float* xg, float* vg);
+
 /* adjoint seeds and read-out -------------------------------------------------------------------- */
 /* loss -> x.grad[f] (+ v, F, C .grad[f]): g24 is (n,24) in get_state layout; g3 is (n,3) */
 int smx_add_state_grad(smx_sim* sim, int32_t f, const double* g24);

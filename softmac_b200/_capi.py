@@ -126,6 +126,14 @@ _SIGS = {
     "smx_chamfer_loss": [vp, C.c_int32, C.c_double, dp],
     "smx_contact_distance_loss": [vp, C.c_int32, C.c_int32, C.c_int32, C.c_double, dp],
     "smx_get_state_grad": [vp, C.c_int32, dp],
+    "smx_host_register": [vp, C.c_uint64],
+    "smx_host_unregister": [vp],
+    "smx_reset_f32": [vp, fp, C.c_int32],
+    "smx_get_state_f32": [vp, C.c_int32, fp],
+    "smx_add_x_grad_f32": [vp, C.c_int32, fp],
+    "smx_add_state_grad_f32": [vp, C.c_int32, fp],
+    "smx_get_state_grad_f32": [vp, C.c_int32, fp],
+    "smx_get_grad_f32": [vp, C.c_int32, fp, fp],
     "smx_reset_dev": [vp, vp],
     "smx_get_state_dev": [vp, C.c_int32, vp],
     "smx_get_state_grad_dev": [vp, C.c_int32, vp],

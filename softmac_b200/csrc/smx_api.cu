@@ -810,6 +810,68 @@ int smx_reset(smx_sim* s, const double* state, int32_t ncols) {
     }
     return resort(s, 0, false);
 }
+// ---- fp32 host entry points: the caller's buffers travel as they are (no f64 <-> f32 conversion pass on the host; with buffers pinned
+// once through smx_host_register the copies are plain DMA).  Same semantics as the f64 calls they mirror.
+int smx_host_register(void* ptr, uint64_t bytes) {
+    if (!ptr || !bytes) return fail(SMX_ERR_ARG, "smx_host_register: null buffer");
+    cudaError_t e = cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return SMX_OK; }
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(SMX_ERR_CUDA, "cudaHostRegister(%llu bytes) failed: %s", (unsigned long long)bytes, cudaGetErrorString(e)); }
+    return SMX_OK;
+}
+int smx_host_unregister(void* ptr) {
+    if (!ptr) return fail(SMX_ERR_ARG, "smx_host_unregister: null buffer");
+    cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) { cudaGetLastError(); if (e != cudaErrorHostMemoryNotRegistered) return fail(SMX_ERR_CUDA, "cudaHostUnregister failed: %s", cudaGetErrorString(e)); }
+    return SMX_OK;
+}
+int smx_reset_f32(smx_sim* s, const float* state, int32_t ncols) {
+    if (!s || !state) return fail(SMX_ERR_ARG, "smx_reset_f32: null argument");
+    if (ncols != 3 && ncols != 24) return fail(SMX_ERR_ARG, "smx_reset_f32: state must have 3 or 24 columns, got %d", ncols);
+    CK(cudaSetDevice(s->cfg.device));
+    CK(cudaStreamSynchronize(s->stream));
+    reset_bookkeeping(s);
+    const int n = s->P.n;
+    Order root; s->order_of[0] = new_order_id(s, root);
+    if (n > 0) {
+        CK(cudaMemcpyAsync(s->stage_dev, state, (size_t)n * ncols * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+        if (ncols == 3) {       // x only: v = 0, F = I, C = 0 (MPMSimulator.reset, mpm_simulator.py:478-492)
+            CK(cudaMemsetAsync(s->frame_ptr(0), 0, s->frame_floats * sizeof(float), s->stream));
+            k_fill_comp<<<nblk(n, 256), 256, 0, s->stream>>>(n, s->P.stride, s->frame_ptr(0), 6, 10, 14, 1.f); CKL(s);
+        }
+        k_upload<<<nblk(n, 256), 256, 0, s->stream>>>(n, s->P.stride, s->stage_dev, ncols, 0, s->frame_ptr(0), nullptr, 0); CKL(s);
+    }
+    return resort(s, 0, false);
+}
+static int add_seed_dev(smx_sim* s, int f, const float* src_dev, int ncols);
+static int add_seed_f32(smx_sim* s, int f, const float* g, int ncols, const char* what) {
+    TRY(check_frame(s, f, what));
+    if (!g) return fail(SMX_ERR_ARG, "%s: null input", what);
+    const int n = s->P.n;
+    if (n == 0) return SMX_OK;
+    CK(cudaSetDevice(s->cfg.device));
+    CK(cudaStreamSynchronize(s->stream));       // staging buffer reuse
+    CK(cudaMemcpyAsync(s->stage_dev, g, (size_t)n * ncols * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    return add_seed_dev(s, f, s->stage_dev, ncols);
+}
+int smx_add_x_grad_f32(smx_sim* s, int32_t f, const float* g3) { return add_seed_f32(s, f, g3, 3, "smx_add_x_grad_f32"); }
+int smx_add_state_grad_f32(smx_sim* s, int32_t f, const float* g24) { return add_seed_f32(s, f, g24, 24, "smx_add_state_grad_f32"); }
+int smx_get_state_f32(smx_sim* s, int32_t f, float* out24) {
+    TRY(check_frame(s, f, "smx_get_state_f32"));
+    if (!out24) return fail(SMX_ERR_ARG, "smx_get_state_f32: null output");
+    TRY(smx_get_state_dev(s, f, s->stage_dev));
+    if (s->P.n > 0) CK(cudaMemcpyAsync(out24, s->stage_dev, (size_t)s->P.n * 24 * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return SMX_OK;
+}
+int smx_get_state_grad_f32(smx_sim* s, int32_t f, float* out24) {
+    TRY(check_frame(s, f, "smx_get_state_grad_f32"));
+    if (!out24) return fail(SMX_ERR_ARG, "smx_get_state_grad_f32: null output");
+    TRY(smx_get_state_grad_dev(s, f, s->stage_dev));
+    if (s->P.n > 0) CK(cudaMemcpyAsync(out24, s->stage_dev, (size_t)s->P.n * 24 * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return SMX_OK;
+}
 // smx_reset with the (n, 24) fp32 rows already on the device (particle migration between slab ranks: no host round trip)
 int smx_reset_dev(smx_sim* s, const float* rows_dev) {
     if (!s || (!rows_dev && s->P.n > 0)) return fail(SMX_ERR_ARG, "smx_reset_dev: null argument");
@@ -1765,6 +1827,29 @@ int smx_get_grad(smx_sim* s, int32_t f, double* xg, double* vg) {
     #pragma omp parallel for schedule(static) num_threads(smx_host_threads())
     for (long long p = 0; p < (long long)n; p++)
         for (int c = 0; c < 3; c++) { xg[3 * p + c] = (double)src[6 * p + c]; vg[3 * p + c] = (double)src[6 * p + 3 + c]; }
+    return SMX_OK;
+}
+// MPMSimulator.get_grad(f) into two caller (n, 3) fp32 arrays: two gathers, two plain copies, no conversion pass
+int smx_get_grad_f32(smx_sim* s, int32_t f, float* xg, float* vg) {
+    TRY(check_frame(s, f, "smx_get_grad_f32"));
+    if (!xg || !vg) return fail(SMX_ERR_ARG, "smx_get_grad_f32: null output");
+    CK(cudaSetDevice(s->cfg.device));
+    const float* adj = s->adj_cur;
+    int order = s->adj_order;
+    if (s->adj_frame != f) {
+        if (s->order_of[f] < 0) return fail(SMX_ERR_STATE, "smx_get_grad_f32: frame %d has not been written", f);
+        CK(cudaMemsetAsync(s->adj_nxt, 0, s->frame_floats * sizeof(float), s->stream));
+        TRY(apply_seed(s, f, s->adj_nxt, s->order_of[f]));
+        adj = s->adj_nxt; order = s->order_of[f];
+    }
+    const int n = s->P.n;
+    if (n == 0) return SMX_OK;
+    const uint32_t* perm = s->orders[order].perm;
+    k_download<<<nblk(n, 256), 256, 0, s->stream>>>(n, s->P.stride, s->stage_dev, 3, 0, adj, perm); CKL(s);
+    k_download<<<nblk(n, 256), 256, 0, s->stream>>>(n, s->P.stride, s->stage_dev + (size_t)3 * n, 3, 3, adj, perm); CKL(s);
+    CK(cudaMemcpyAsync(xg, s->stage_dev, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaMemcpyAsync(vg, s->stage_dev + (size_t)3 * n, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
     return SMX_OK;
 }
 int smx_clear_grads(smx_sim* s) {

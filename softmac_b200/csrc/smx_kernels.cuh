@@ -1432,6 +1432,12 @@ __global__ void k_upload(int n, long long stride, const float* __restrict__ aos,
         if (accumulate) fr[k] += v; else fr[k] = v;
     }
 }
+// frame components c0, c1, c2 (get_state columns) <- value (F = I of a reset from positions only)
+__global__ void k_fill_comp(int n, long long stride, float* __restrict__ fr, int c0, int c1, int c2, float value) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    fr[comp_index(stride, j, c0)] = value; fr[comp_index(stride, j, c1)] = value; fr[comp_index(stride, j, c2)] = value;
+}
 __global__ void k_download(int n, long long stride, float* __restrict__ aos, int ncomp, int c0, const float* __restrict__ fr, const uint32_t* __restrict__ perm) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;

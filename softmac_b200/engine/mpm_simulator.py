@@ -2,7 +2,10 @@
 libsoftmac_b200.so (hand-written sm_100a kernels; include/softmac_b200.h).
 
 Same constructor, attributes and methods as the reference class; numpy float64 at the boundary, fp32
-SoA checkpoints in HBM behind it.  New seams the Taichi version exposed implicitly:
+SoA checkpoints in HBM behind it.  The state / gradient calls also take float32 host arrays (no conversion
+pass; ``pin`` them once for plain DMA) and device arrays (anything with ``__cuda_array_interface__``, e.g. the
+optimiser's torch CUDA tensors): ``reset``, ``get_state``, ``get_grad``, ``get_state_grad``, ``add_x_grad``,
+``add_state_grad``.  New seams the Taichi version exposed implicitly:
 ``add_x_grad`` / ``add_state_grad`` (loss -> adjoint seeds), ``clear_all_gradients`` and a settable
 ``primitives_contact`` list.
 """
@@ -11,6 +14,30 @@ import ctypes as C
 import numpy as np
 
 from .._capi import SmxConfig, lib, check, as_d, d_ptr, vp, SMX_FLAG_DENSE_GRID, SMX_FLAG_NO_SORT  # noqa: F401
+
+fp = C.POINTER(C.c_float)
+
+
+def _f32(a):
+    """a contiguous float32 host array (the fp32 entry points take the caller's buffer as it is)"""
+    return isinstance(a, np.ndarray) and a.dtype == np.float32 and a.flags.c_contiguous
+
+
+def _dev(a):
+    """(device pointer, shape) of a float32 C-contiguous device array (torch CUDA tensor, cupy array, ...) or None"""
+    cai = getattr(a, "__cuda_array_interface__", None)
+    if cai is None:
+        return None
+    shape = tuple(int(v) for v in cai["shape"])
+    dense = tuple(4 * int(np.prod(shape[i + 1:])) for i in range(len(shape)))
+    if cai["typestr"] not in ("<f4", "=f4") or (cai.get("strides") is not None and tuple(cai["strides"]) != dense):
+        raise TypeError("device arrays handed to MPMSimulator must be float32 and C-contiguous")
+    return int(cai["data"][0]), tuple(cai["shape"])
+
+
+def _f_ptr(a):
+    return a.ctypes.data_as(fp)
+
 
 MODEL_COROTATED, MODEL_NEOHOOKEAN = 0, 1
 MAT_PLASTIC, MAT_ELASTIC, MAT_LIQUID = 0, 1, 2
@@ -147,10 +174,32 @@ class MPMSimulator:
         check(lib().smx_step_grad(self._h, int(s1), int(count)))
 
     # -- IO (mpm_simulator.py:448-574) ----------------------------------------------------------------------
-    def get_state(self, f):
+    def get_state(self, f, dtype=np.float64, out=None):
+        """(n, 24) [x v F C].  dtype float32 (or a float32 ``out``): the fp32 rows as stored, no conversion; a device ``out``
+        (``__cuda_array_interface__``) is filled on the simulator's stream without a host copy."""
+        if out is not None and _dev(out) is not None:
+            ptr, shape = _dev(out)
+            assert int(np.prod(shape)) == self.n_total * 24
+            check(lib().smx_get_state_dev(self._h, int(f), C.c_void_p(ptr)))
+            return out
+        if out is not None or np.dtype(dtype) == np.float32:
+            out = np.empty((self.n_total, 24), dtype=np.float32) if out is None else out
+            assert _f32(out) and out.size == self.n_total * 24
+            check(lib().smx_get_state_f32(self._h, int(f), _f_ptr(out)))
+            return out
         out = np.zeros((self.n_total, 24))
         check(lib().smx_get_state(self._h, int(f), d_ptr(out)))
         return out
+
+    def pin(self, *arrays):
+        """Page-lock caller float32 buffers once (cudaHostRegister) so that reset / get_grad / add_x_grad on them are plain DMA."""
+        for a in arrays:
+            assert isinstance(a, np.ndarray) and a.flags.c_contiguous
+            check(lib().smx_host_register(C.c_void_p(a.ctypes.data), a.nbytes))
+
+    def unpin(self, *arrays):
+        for a in arrays:
+            check(lib().smx_host_unregister(C.c_void_p(a.ctypes.data)))
 
     def set_state(self, f, state):
         x, v, F, Cm = [as_d(a) for a in state[:4]]
@@ -159,6 +208,16 @@ class MPMSimulator:
         check(lib().smx_set_frame(self._h, int(f), d_ptr(x), d_ptr(v), d_ptr(F), d_ptr(Cm)))
 
     def reset(self, x):
+        d = _dev(x)
+        if d is not None:               # (n_total, 24) float32 rows already on the device: no host round trip
+            assert d[1] == (self.n_total, 24), "device reset takes (n_total, 24) float32 rows"
+            check(lib().smx_reset_dev(self._h, C.c_void_p(d[0])))
+            self.cur = 0
+            return
+        if _f32(x) and x.ndim == 2 and x.shape[1] in (self.dim, 24) and x.shape[0] == self.n_total:
+            check(lib().smx_reset_f32(self._h, _f_ptr(x), int(x.shape[1])))
+            self.cur = 0
+            return
         x = as_d(x)
         assert x.ndim == 2 and x.shape[1] in (self.dim, 24)
         if x.shape[0] == self.n_particles and self.n_batch > 1:
@@ -188,21 +247,48 @@ class MPMSimulator:
     def copyframe(self, source, target):
         check(lib().smx_copy_frame(self._h, int(source), int(target)))
 
-    def get_grad(self, f):
+    def get_grad(self, f, dtype=np.float64, out=None):
+        """(x.grad[f], v.grad[f]) (mpm_simulator.py:561-574).  dtype float32 / out=(xg, vg) float32 arrays: no conversion pass."""
+        if out is not None or np.dtype(dtype) == np.float32:
+            xg, vg = out if out is not None else (np.empty((self.n_total, self.dim), dtype=np.float32), np.empty((self.n_total, self.dim), dtype=np.float32))
+            assert _f32(xg) and _f32(vg) and xg.size == vg.size == self.n_total * self.dim
+            check(lib().smx_get_grad_f32(self._h, int(f), _f_ptr(xg), _f_ptr(vg)))
+            return xg, vg
         xg, vg = np.zeros((self.n_total, self.dim)), np.zeros((self.n_total, self.dim))
         check(lib().smx_get_grad(self._h, int(f), d_ptr(xg), d_ptr(vg)))
         return xg, vg
 
     # -- adjoint seeds (what Taichi losses do by writing x.grad[f] directly) --------------------------------
     def add_x_grad(self, f, g):
+        if _f32(g) and g.size == self.n_total * self.dim:
+            check(lib().smx_add_x_grad_f32(self._h, int(f), _f_ptr(g)))
+            return
         g = as_d(g, (self.n_total, self.dim))
         check(lib().smx_add_x_grad(self._h, int(f), d_ptr(g)))
 
     def add_state_grad(self, f, g24):
+        d = _dev(g24)
+        if d is not None:
+            assert int(np.prod(d[1])) == self.n_total * 24
+            check(lib().smx_add_state_grad_dev(self._h, int(f), C.c_void_p(d[0])))
+            return
+        if _f32(g24) and g24.size == self.n_total * 24:
+            check(lib().smx_add_state_grad_f32(self._h, int(f), _f_ptr(g24)))
+            return
         g = as_d(g24, (self.n_total, 24))
         check(lib().smx_add_state_grad(self._h, int(f), d_ptr(g)))
 
-    def get_state_grad(self, f):
+    def get_state_grad(self, f, dtype=np.float64, out=None):
+        if out is not None and _dev(out) is not None:
+            ptr, shape = _dev(out)
+            assert int(np.prod(shape)) == self.n_total * 24
+            check(lib().smx_get_state_grad_dev(self._h, int(f), C.c_void_p(ptr)))
+            return out
+        if out is not None or np.dtype(dtype) == np.float32:
+            out = np.empty((self.n_total, 24), dtype=np.float32) if out is None else out
+            assert _f32(out) and out.size == self.n_total * 24
+            check(lib().smx_get_state_grad_f32(self._h, int(f), _f_ptr(out)))
+            return out
         out = np.zeros((self.n_total, 24))
         check(lib().smx_get_state_grad(self._h, int(f), d_ptr(out)))
         return out

@@ -9,7 +9,7 @@ import scenes
 from harness import sim_cfg, cosine, rel_l2
 
 
-def build(backend, n=3000, env_steps=6, substeps=5, fp32_bridge=True):
+def build(backend, n=3000, env_steps=6, substeps=5, fp32_bridge=True, finger_offset=0.108, init_state=(0., 0., 0.4, -0.4)):
     from softmac_b200.engine.taichi_env import TaichiEnv
     from softmac_b200.engine.rigid_simulator import RigidSimulator
     from softmac_b200.engine.losses import PointwiseLoss
@@ -36,9 +36,9 @@ def build(backend, n=3000, env_steps=6, substeps=5, fp32_bridge=True):
         cfg = sim_cfg(n, n_grid=n_grid, max_steps=max_steps, dt=dt)
         sim = MPMSimulator(cfg, prims, env_dt=dt * substeps)
         prims.initialize()                  # softness 666 (primitives.py:55-56)
-    bodies = [dict(joint="prismatic", axis=(1, 0, 0), origin=(0.5 - 0.108, 0.3, 0.5), mass=1.0, gravity=False),
-              dict(joint="prismatic", axis=(1, 0, 0), origin=(0.5 + 0.108, 0.3, 0.5), mass=1.0, gravity=False)]
-    rcfg = CfgNode(gravity=(0., 0., 0.), init_state=(0., 0., 0.4, -0.4), bodies=bodies)
+    bodies = [dict(joint="prismatic", axis=(1, 0, 0), origin=(0.5 - finger_offset, 0.3, 0.5), mass=1.0, gravity=False),
+              dict(joint="prismatic", axis=(1, 0, 0), origin=(0.5 + finger_offset, 0.3, 0.5), mass=1.0, gravity=False)]
+    rcfg = CfgNode(gravity=(0., 0., 0.), init_state=init_state, bodies=bodies)
     rigid = RigidSimulator(rcfg, prims, substeps=substeps, env_dt=dt * substeps, fp32_bridge=fp32_bridge)
     target = x + np.array([0.0, 0.01, 0.0])
     env = TaichiEnv(sim, prims, rigid, x, loss=PointwiseLoss(sim, target), control_mode="rigid")
@@ -118,6 +118,27 @@ def test_episode_action_gradient_cosine():
     c = cosine(gg, go)
     assert np.abs(go).max() > 0 and c >= 0.999, (c, gg, go)
     assert rel_l2(gg, go) <= 2e-2
+
+
+@pytest.mark.gpu
+def test_long_grip_like_episode_200_env_steps():
+    """200 env steps x 5 substeps = 1000 substeps (half a demo_grip episode, demo_grip.py:190-191) of a grip-like squeeze: fingers start
+    5 mm clear of the block at rest and are pushed together by force actions; loss on four late frames.  Oracle vs CUDA through the same
+    env loop: action-gradient cosine >= 0.999 over the episode (BASELINE.json north_star); the full-length demo episodes on the
+    reference's own scenes are in profiles/r2_demo_*_parity_full.json (tools/bench_demo.py --parity-env-steps 400 / 3000)."""
+    env_steps, substeps = 200, 5
+    t = np.arange(env_steps)[:, None]
+    actions = np.array([1.5, -1.5])[None, :] * (1 + 0.2 * np.sin(0.05 * t))
+    frames = [env_steps * substeps - k for k in (0, 20, 40, 60)]
+    kw = dict(n=2500, env_steps=env_steps, substeps=substeps, finger_offset=0.115, init_state=(0., 0., 0., 0.))
+    lo, go, ro, so = run_episode(build("oracle", **kw), actions, frames)
+    lg, gg, rg, sg = run_episode(build("cuda", **kw), actions, frames)
+    assert abs(ro[0]) > 0.01 and abs(ro[1]) > 0.01          # both fingers travelled (into the block)
+    assert abs(lg - lo) <= 1e-3 * abs(lo)
+    assert rel_l2(rg, ro) <= 1e-4 and rel_l2(sg[:, :3], so[:, :3]) <= 1e-4
+    c = cosine(gg, go)
+    assert np.abs(go).max() > 0 and c >= 0.999, (c, rel_l2(gg, go))
+    print(f"1000-substep episode: loss rel err {abs(lg - lo) / abs(lo):.2e}, x rel-L2 {rel_l2(sg[:, :3], so[:, :3]):.2e}, action-gradient cosine {c:.9f}, rel-L2 {rel_l2(gg, go):.2e}")
 
 
 def build_pour(backend, n=3000, env_steps=10):

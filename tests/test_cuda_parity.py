@@ -628,3 +628,64 @@ def test_primitive_reset_clears_adjoints_and_action_buffer():
     assert np.abs(m.get_all_states(5)).max() == 0 and np.abs(m.get_all_states_grad(0, f_end=16)).max() == 0
     assert np.abs(m.get_action_grad(1, 5)).max() == 0 and np.abs(m.get_ext_f()).max() == 0
     del sim
+
+
+def test_fp32_host_and_device_entry_points_equal_the_f64_calls():
+    """reset / get_state / add_x_grad / add_state_grad / get_grad / get_state_grad with float32 host arrays (smx_*_f32, buffers pinned with
+    MPMSimulator.pin) and with device arrays (__cuda_array_interface__: torch CUDA tensors -> smx_*_dev) give exactly what the float64
+    calls give: the float64 calls convert to the same fp32 rows."""
+    import torch
+    rng = np.random.default_rng(77)
+    n, S = 3000, 4
+    center = np.array([0.5, 0.3, 0.5])
+    st = scenes.contact_rollout_state(n, rng, center, speed=1.0)        # fp32-representable; rests just outside the sphere, moving into it
+    seed3 = rng.normal(size=(n, 3)).astype(np.float32)
+    seed24 = rng.normal(size=(n, 24)).astype(np.float32)
+
+    def run(mode):
+        pair = Pair(n, tables=[scenes.sphere_table()], prim_params=[(0.5, 666.)], max_steps=S + 2, sort_every=2)
+        sim = pair.gpu
+        pair.prims[0].set_all_states(0, np.concatenate([center, [1, 0, 0, 0], [0, 0.3, 0], [0, 0, 0]]), f_end=S + 2)
+        if mode == "f64":
+            sim.reset(st)
+        elif mode == "f32":
+            st32 = st.astype(np.float32)
+            sim.pin(st32)
+            sim.reset(st32)
+            sim.unpin(st32)
+        else:
+            sim.reset(torch.from_numpy(st.astype(np.float32)).cuda())
+        sim.step(0, S)
+        sim.clear_all_gradients()
+        f0 = sim.get_state(0)
+        assert np.array_equal(f0, st), mode                 # the uploaded rows are exactly the caller's
+        if mode == "f64":
+            sim.add_x_grad(S, seed3.astype(np.float64)); sim.add_state_grad(S - 1, seed24.astype(np.float64))
+            sim.step_grad(S, S)
+            return sim.get_state(S), sim.get_grad(0), sim.get_state_grad(0)
+        if mode == "f32":
+            sim.add_x_grad(S, seed3); sim.add_state_grad(S - 1, seed24)
+            sim.step_grad(S, S)
+            xg, vg = np.empty((n, 3), np.float32), np.empty((n, 3), np.float32)
+            sim.pin(xg, vg)
+            out = sim.get_state(S, dtype=np.float32), sim.get_grad(0, out=(xg, vg)), sim.get_state_grad(0, dtype=np.float32)
+            sim.unpin(xg, vg)
+            return out
+        sim.add_x_grad(S, seed3); sim.add_state_grad(S - 1, torch.from_numpy(seed24).cuda())
+        sim.step_grad(S, S)
+        a, b = torch.empty((n, 24), device="cuda"), torch.empty((n, 24), device="cuda")
+        sim.get_state(S, out=a); sim.get_state_grad(0, out=b)
+        sim.synchronize()
+        return a.cpu().numpy(), sim.get_grad(0, dtype=np.float32), b.cpu().numpy()
+
+    ref_state, (ref_xg, ref_vg), ref_adj = run("f64")
+    assert np.abs(ref_xg).max() > 0
+    for mode in ("f32", "dev"):
+        state, (xg, vg), adj = run(mode)
+        # the same kernels on the same inputs: runs differ only by the order of the float reductions in the scatters
+        assert state.dtype == np.float32 and rel_l2(state, ref_state) <= 1e-6, (mode, rel_l2(state, ref_state))
+        assert xg.dtype == np.float32 and rel_l2(xg, ref_xg) <= 1e-5 and rel_l2(vg, ref_vg) <= 1e-5, mode
+        assert rel_l2(adj, ref_adj) <= 1e-5, (mode, rel_l2(adj, ref_adj))
+        assert np.array_equal(adj[:, :3].astype(np.float32), xg) and np.array_equal(adj[:, 3:6].astype(np.float32), vg), mode
+    with pytest.raises(TypeError):
+        Pair(10).gpu.reset(torch.zeros((10, 24), device="cuda", dtype=torch.float64))
