@@ -225,6 +225,21 @@ int smx_substep_grad_mid(smx_sim* sim, int32_t s);
  * all-reduces them).  Particle migration between ranks is not implemented: particles whose stencil leaves the own
  * slab + halo are counted in counters[1]. */
 int smx_set_slab(smx_sim* sim, int32_t xb_lo, int32_t xb_hi, int32_t has_lo_neighbour, int32_t has_hi_neighbour);
+/* Halo exchange over peer memory (NVLink / NVSwitch P2P; SURVEY.md 8e "halo exchange of P2G ghost cells"): every slab rank owns ONE
+ * allocation of receive slots that its x-neighbours write into directly.  smx_slab_halo_export returns its device pointer (ranks
+ * emulated in one process) and a 64-byte CUDA IPC handle (one process per GPU: exchange the handles once, e.g. with an all-gather);
+ * smx_slab_halo_connect maps a neighbour's allocation (side 0: below xb_lo, side 1: above xb_hi; pass the pointer OR the handle).
+ * Once every neighbour is connected, smx_substep / smx_substep_grad / smx_step / smx_step_grad run the halo sums themselves, on the
+ * simulator's stream -- push of the non-empty halo blocks into the neighbour's slot, flag, wait, add -- with no host round trip, and
+ * smx_step keeps its cross-substep fusion.  smx_slab_halo_push / _add are the two halves of one exchange for ranks emulated on ONE
+ * stream (all ranks must push before any rank adds).  array: 0 g_in, 1 contact scatter into g_out, 3 adjoint grid of substep f,
+ * 4 gg_mix.  smx_slab_halo_status: out[0] exchanges that gave up waiting for a neighbour (must be 0), out[1] exchanges done,
+ * out[2] bytes of the halo allocation. */
+int smx_slab_halo_export(smx_sim* sim, void** base, void* ipc_handle64);
+int smx_slab_halo_connect(smx_sim* sim, int32_t side, void* base, const void* ipc_handle64);
+int smx_slab_halo_push(smx_sim* sim, int32_t array, int32_t f);
+int smx_slab_halo_add(smx_sim* sim, int32_t array, int32_t f);
+int smx_slab_halo_status(smx_sim* sim, int64_t out[3]);
 /* device pointer / element count of a grid array: 0 g_in, 1 g_out, 2 g_mix, 3 gg_out, 4 gg_mix (float4 per node,
  * block-major; x-block column c is the contiguous range [c*nb^2*64, (c+1)*nb^2*64), nb = n_grid/4) */
 int smx_grid_dev(smx_sim* sim, int32_t which, void** ptr_dev, int64_t* n_float4);

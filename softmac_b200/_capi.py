@@ -116,6 +116,11 @@ _SIGS = {
     "smx_substep_grad_begin": [vp, C.c_int32],
     "smx_substep_grad_end": [vp, C.c_int32],
     "smx_set_slab": [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32],
+    "smx_slab_halo_export": [vp, C.POINTER(vp), vp],
+    "smx_slab_halo_connect": [vp, C.c_int32, vp, vp],
+    "smx_slab_halo_push": [vp, C.c_int32, C.c_int32],
+    "smx_slab_halo_add": [vp, C.c_int32, C.c_int32],
+    "smx_slab_halo_status": [vp, C.POINTER(C.c_int64)],
     "smx_grid_dev": [vp, C.c_int32, C.POINTER(vp), C.POINTER(C.c_int64)],
     "smx_stream": [vp, C.POINTER(vp)],
     "smx_step": [vp, C.c_int32, C.c_int32],

@@ -115,7 +115,18 @@ struct smx_sim {
     size_t G = 0;
     float4 *g_in = nullptr, *g_out = nullptr, *g_mix = nullptr, *gg_out = nullptr, *gg_out_b = nullptr, *gg_mix = nullptr, *g_lin = nullptr;
     // adjoint grid of substep f: double-buffered by parity so that k_grid_grad(f) can already clear the one of substep f-1
-    float4* gg_of(int f) { return (slab || !(f & 1)) ? gg_out : gg_out_b; }
+    // halo exchange over peer memory (smx_slab_halo_*): receive slots + stamps + flags of both sides live in ONE allocation (`halo_mem`,
+    // IPC-exportable) that the x-neighbours write into; peer_base[side] is the neighbour's allocation as mapped here
+    int slab_checked = -1;              // last frame whose positions went through k_check_slab
+    unsigned char* halo_mem = nullptr; size_t halo_bytes = 0;
+    unsigned char* peer_base[2] = {nullptr, nullptr}; bool peer_ipc[2] = {false, false};
+    unsigned* halo_done = nullptr;      // [2] completion counters of the push kernels
+    unsigned halo_seq[2] = {0u, 0u};    // exchanges done per side (both ends count in lockstep)
+    long long halo_exchanges = 0;
+    bool peers_on() const { return slab && (!halo_lo || peer_base[0]) && (!halo_hi || peer_base[1]) && (halo_lo || halo_hi) && halo_mem; }
+    // slab mode driven phase by phase from the host (the caller exchanges the halos between the phases): no cross-substep fusion there
+    bool slab_legacy() const { return slab && !peers_on(); }
+    float4* gg_of(int f) { return (slab_legacy() || !(f & 1)) ? gg_out : gg_out_b; }
     int bwd_prepared = -1; long long bwd_prepared_uid = -1;   // substep whose g_out / g_mix / cleared gg are already in place (by k_grid_grad of the next substep)
     // grid checkpoints (g_in, g_out[, g_mix] on the active blocks of every substep) so that the adjoint does not
     // re-run P2G and the grid update (north_star: "per-substep state buffers resident in HBM rather than recomputed")
@@ -413,7 +424,12 @@ static int forward_p2g(smx_sim* s, int f, bool write_F, bool accumulate, bool fu
     s->g_in_clean_uid = -1;             // P2G is about to write it
     s->bwd_prepared = -1;
     if (s->slab && P.n > 0) {
-        k_check_slab<<<nblk(P.n, 256), 256, 0, s->stream>>>(P, fin, s->halo_lo ? s->slab_lo - 1 : 0, s->halo_hi ? s->slab_hi : P.nb - 1, s->counters); CKL(s);
+        // particles that left slab + halo are counted; with the G2P of f-1 folded into this launch x[f] does not exist yet: look at x[f-1]
+        const int cf = fprev ? f - 1 : f;
+        if (s->slab_checked != cf) {
+            k_check_slab<<<nblk(P.n, 256), 256, 0, s->stream>>>(P, fprev ? fprev : fin, s->halo_lo ? s->slab_lo - 1 : 0, s->halo_hi ? s->slab_hi : P.nb - 1, s->counters); CKL(s);
+            s->slab_checked = cf;
+        }
     }
     if (P.n > 0) {
         float4* rec = (write_F && s->svd_pool) ? s->svd_rec(f) : nullptr;
@@ -713,7 +729,8 @@ int smx_destroy(smx_sim* s) {
     for (auto& kv : s->seeds) cudaFree(kv.second.dev);
     for (auto& kv : s->seed_pool) cudaFree(kv.second);
     for (auto& p : s->prims) { cudaFree(p.sdf_dev); cudaFree(p.nrm_dev); }
-    void* ptrs[] = {s->near_pool, s->svd_pool, s->ch_target, s->ch_loss, s->cd_buf, s->ckpt, s->pool, s->g_in, s->g_out, s->g_mix, s->gg_out, s->gg_out_b, s->gg_mix, s->g_lin, s->adj_cur, s->adj_nxt, s->stage_dev, s->keys_a, s->keys_b, s->iota, s->cub_tmp,
+    for (int side = 0; side < 2; side++) if (s->peer_base[side] && s->peer_ipc[side]) cudaIpcCloseMemHandle(s->peer_base[side]);
+    void* ptrs[] = {s->halo_mem, s->halo_done, s->near_pool, s->svd_pool, s->ch_target, s->ch_loss, s->cd_buf, s->ckpt, s->pool, s->g_in, s->g_out, s->g_mix, s->gg_out, s->gg_out_b, s->gg_mix, s->g_lin, s->adj_cur, s->adj_nxt, s->stage_dev, s->keys_a, s->keys_b, s->iota, s->cub_tmp,
                     s->counters, s->prims_dev, s->pstate, s->pgrad, s->ext_f, s->ext_f_grad, s->abuf, s->gabuf, s->ctrl_id, s->action, s->action_grad,
                     s->rig_arena, s->rig_enable, s->rig_masks, s->ckpt_need};
     for (void* p : ptrs) cudaFree(p);
@@ -781,6 +798,7 @@ static void reset_bookkeeping(smx_sim* s) {
     s->adj_frame = -1; s->adj_order = -1;
     s->ckpt_dirty = true;
     s->defer_save = -1;
+    s->slab_checked = -1;
     if (s->ckpt_need) cudaMemsetAsync(s->ckpt_need, 0, (size_t)s->cfg.max_steps * sizeof(int), s->stream);
     gc_orders(s);                       // every ordering is unreferenced now: recycle all of them
 }
@@ -940,6 +958,7 @@ int smx_set_x(smx_sim* s, int32_t f, const double* x) { if (!x) return fail(SMX_
 int smx_set_v(smx_sim* s, int32_t f, const double* v) { if (!v) return fail(SMX_ERR_ARG, "smx_set_v: null input"); return smx_set_frame(s, f, nullptr, v, nullptr, nullptr); }
 
 int smx_copy_frame(smx_sim* s, int32_t src, int32_t dst) {
+    if (s) s->slab_checked = -1;
     TRY(check_frame(s, src, "smx_copy_frame")); TRY(check_frame(s, dst, "smx_copy_frame"));
     if (s->order_of[src] < 0) return fail(SMX_ERR_STATE, "smx_copy_frame: source frame %d has not been written", src);
     CK(cudaSetDevice(s->cfg.device));
@@ -1336,6 +1355,8 @@ int smx_rigid_linear_get_state_grad(smx_sim* s, double* out) {
     return SMX_OK;
 }
 
+static int halo_exchange(smx_sim* s, int which, int f);     // slab halo sum over peer memory (defined with the slab API below)
+
 // ---- the hot path -------------------------------------------------------------------------------
 // substep = begin (clear + P2G) ; [slab mode: halo exchange of g_in by the caller] ; end (grid update, contact, G2P)
 int smx_substep_begin(smx_sim* s, int32_t f) {
@@ -1371,6 +1392,10 @@ int smx_substep_end(smx_sim* s, int32_t f) {
 }
 int smx_substep(smx_sim* s, int32_t f) {
     TRY(smx_substep_begin(s, f));
+    if (s->peers_on()) {                // slab rank with connected neighbours: the halo sums run here, on the stream
+        TRY(halo_exchange(s, 0, f));
+        if (s->has_contact()) { TRY(smx_substep_mid(s, f)); TRY(halo_exchange(s, 1, f)); }
+    }
     return smx_substep_end(s, f);
 }
 
@@ -1471,7 +1496,7 @@ int smx_substep_grad_mid(smx_sim* s, int32_t f) {
 // P2G adjoint of substep f and G2P adjoint of substep f-1 may share a launch when f-1 runs in the same ordering, both have their grid
 // record (so that k_grid_grad of f also restores g_out of f-1 and clears its adjoint grid) and no loss seed enters at frame f
 static bool can_fuse_bwd(smx_sim* s, int f) {
-    if (!s->bwd_fusion || f < 1 || s->slab || (s->cfg.flags & (SMX_FLAG_NO_FUSION | SMX_FLAG_DIRECT_RED)) || s->P.n <= 0) return false;
+    if (!s->bwd_fusion || f < 1 || s->slab_legacy() || (s->cfg.flags & (SMX_FLAG_NO_FUSION | SMX_FLAG_DIRECT_RED)) || s->P.n <= 0) return false;
     const int o = s->order_of[f];
     if (o < 0 || s->order_of[f - 1] != o || s->trans_from[f] >= 0) return false;
     const Order& ord = s->orders[o];
@@ -1498,7 +1523,7 @@ static int grad_end(smx_sim* s, int f, bool fuse) {
         // g_in comes straight from the grid checkpoint when there is one; and when substep f-1 shares the ordering and has a
         // record too, this launch also prepares its adjoint (restore of g_out / g_mix, clear of the other adjoint grid)
         const bool have_rec = s->ckpt && s->ckpt_order[f] == ord.uid && (bool)s->ckpt_contact[f] == contact;
-        const bool prep = have_rec && !s->slab && !(s->cfg.flags & SMX_FLAG_NO_FUSION) && f > 0 && s->order_of[f - 1] == o && s->ckpt_order[f - 1] == ord.uid &&
+        const bool prep = have_rec && !s->slab_legacy() && !(s->cfg.flags & SMX_FLAG_NO_FUSION) && f > 0 && s->order_of[f - 1] == o && s->ckpt_order[f - 1] == ord.uid &&
                           (bool)s->ckpt_contact[f - 1] == contact && s->trans_from[f] < 0;
         const float4* rec_in = have_rec ? s->ckpt + (size_t)f * s->ckpt_rec : nullptr;
         const float4* rec_prev = prep ? s->ckpt + (size_t)(f - 1) * s->ckpt_rec : nullptr;
@@ -1559,6 +1584,10 @@ static int grad_end(smx_sim* s, int f, bool fuse) {
 }
 int smx_substep_grad(smx_sim* s, int32_t f) {
     TRY(smx_substep_grad_begin(s, f));
+    if (s->peers_on()) {
+        TRY(halo_exchange(s, 3, f));
+        if (s->has_contact()) { TRY(smx_substep_grad_mid(s, f)); TRY(halo_exchange(s, 4, f)); }
+    }
     return smx_substep_grad_end(s, f);
 }
 
@@ -1573,6 +1602,125 @@ int smx_set_slab(smx_sim* s, int32_t xb_lo, int32_t xb_hi, int32_t has_lo_neighb
     s->slab = true; s->slab_lo = xb_lo; s->slab_hi = xb_hi; s->halo_lo = has_lo_neighbour != 0; s->halo_hi = has_hi_neighbour != 0;
     return SMX_OK;
 }
+// ---- halo exchange over peer memory ---------------------------------------------------------------------------------------
+// Layout of a rank's halo allocation (identical on every rank: it only depends on nb): [flag lo | flag hi] (128 B each), then per
+// (side, slot) the block stamps (H u32, padded to 256 B), then per (side, slot) the receive slot (H x 64 float4).  H = 2 nb^2.
+struct HaloLayout {
+    size_t H, stamp_bytes, total;
+    explicit HaloLayout(int nb) { H = (size_t)2 * nb * nb; stamp_bytes = (H * 4 + 255) / 256 * 256; total = 256 + 4 * stamp_bytes + 4 * H * 64 * sizeof(float4); }
+    size_t flag(int side) const { return (size_t)side * 128; }
+    size_t stamp(int side, int slot) const { return 256 + (size_t)(side * 2 + slot) * stamp_bytes; }
+    size_t rx(int side, int slot) const { return 256 + 4 * stamp_bytes + (size_t)(side * 2 + slot) * H * 64 * sizeof(float4); }
+};
+static int halo_alloc(smx_sim* s) {
+    if (s->halo_mem) return SMX_OK;
+    if (!s->slab) return fail(SMX_ERR_STATE, "smx_slab_halo: call smx_set_slab first");
+    HaloLayout L(s->P.nb);
+    CK(cudaSetDevice(s->cfg.device));
+    CK(cudaMalloc(&s->halo_mem, L.total));
+    CK(cudaMemset(s->halo_mem, 0, L.total));
+    CK(cudaMalloc(&s->halo_done, 2 * sizeof(unsigned)));
+    CK(cudaMemset(s->halo_done, 0, 2 * sizeof(unsigned)));
+    s->halo_bytes = L.total;
+    return SMX_OK;
+}
+// this rank's halo allocation: device pointer (ranks emulated in one process connect through it) and a 64-byte IPC handle (one process per GPU)
+int smx_slab_halo_export(smx_sim* s, void** base, void* ipc_handle64) {
+    if (!s) return fail(SMX_ERR_ARG, "smx_slab_halo_export: null simulator");
+    TRY(halo_alloc(s));
+    if (base) *base = s->halo_mem;
+    if (ipc_handle64) {
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+        cudaIpcMemHandle_t h;
+        CK(cudaIpcGetMemHandle(&h, s->halo_mem));
+        memcpy(ipc_handle64, &h, 64);
+    }
+    return SMX_OK;
+}
+// side 0: the neighbour that owns the columns below slab_lo, side 1: the one above slab_hi.  Exactly one of (base, ipc_handle64).
+int smx_slab_halo_connect(smx_sim* s, int32_t side, void* base, const void* ipc_handle64) {
+    if (!s || (side != 0 && side != 1)) return fail(SMX_ERR_ARG, "smx_slab_halo_connect: bad argument");
+    if (!(side == 0 ? s->halo_lo : s->halo_hi)) return fail(SMX_ERR_STATE, "smx_slab_halo_connect: this slab has no neighbour on side %d", side);
+    if ((base != nullptr) == (ipc_handle64 != nullptr)) return fail(SMX_ERR_ARG, "smx_slab_halo_connect: pass a device pointer or an IPC handle");
+    TRY(halo_alloc(s));
+    CK(cudaSetDevice(s->cfg.device));
+    if (s->peer_base[side] && s->peer_ipc[side]) cudaIpcCloseMemHandle(s->peer_base[side]);
+    if (ipc_handle64) {
+        cudaIpcMemHandle_t h;
+        memcpy(&h, ipc_handle64, 64);
+        void* p = nullptr;
+        CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        s->peer_base[side] = (unsigned char*)p; s->peer_ipc[side] = true;
+    } else { s->peer_base[side] = (unsigned char*)base; s->peer_ipc[side] = false; }
+    return SMX_OK;
+}
+// halo arrays: 0 g_in (P2G sums), 1 g_out += neighbour's (g_out - g_mix) (contact scatter), 3 adjoint grid of substep f, 4 gg_mix
+static int halo_push(smx_sim* s, int which, int f) {
+    const int nb = s->P.nb;
+    HaloLayout L(nb);
+    float4* A = which == 0 ? s->g_in : which == 1 ? s->g_out : which == 3 ? s->gg_of(f) : s->gg_mix;
+    for (int side = 0; side < 2; side++) {
+        if (!(side == 0 ? s->halo_lo : s->halo_hi)) continue;
+        const int b = side == 0 ? s->slab_lo : s->slab_hi;
+        const size_t node0 = (size_t)(b - 1) * nb * nb * 64;
+        const unsigned seq1 = s->halo_seq[side] + 1;
+        const int slot = (int)(s->halo_seq[side] & 1u), pside = 1 - side;       // my lo neighbour receives on ITS hi side
+        unsigned char* pb = s->peer_base[side];
+        float4* prx = (float4*)(pb + L.rx(pside, slot)); uint32_t* pst = (uint32_t*)(pb + L.stamp(pside, slot)); unsigned* pfl = (unsigned*)(pb + L.flag(pside));
+        const int grid = std::min((int)((L.H + 7) / 8), s->sm_count * 4);
+        if (which == 1) k_halo_push<1><<<grid, 256, 0, s->stream>>>(A, s->g_mix, node0, (int)L.H, prx, pst, pfl, seq1, s->halo_done + side);
+        else k_halo_push<0><<<grid, 256, 0, s->stream>>>(A, nullptr, node0, (int)L.H, prx, pst, pfl, seq1, s->halo_done + side);
+        CKLN(s, "halo_push");
+    }
+    return SMX_OK;
+}
+static int halo_add(smx_sim* s, int which, int f) {
+    const int nb = s->P.nb;
+    HaloLayout L(nb);
+    float4* A = which == 0 ? s->g_in : which == 1 ? s->g_out : which == 3 ? s->gg_of(f) : s->gg_mix;
+    static const long long timeout_ns = getenv("SMX_HALO_TIMEOUT_MS") ? atoll(getenv("SMX_HALO_TIMEOUT_MS")) * 1000000ll : 2000000000ll;
+    for (int side = 0; side < 2; side++) {
+        if (!(side == 0 ? s->halo_lo : s->halo_hi)) continue;
+        const int b = side == 0 ? s->slab_lo : s->slab_hi;
+        const size_t node0 = (size_t)(b - 1) * nb * nb * 64;
+        const unsigned seq1 = s->halo_seq[side] + 1;
+        const int slot = (int)(s->halo_seq[side] & 1u);
+        k_halo_wait<<<1, 1, 0, s->stream>>>((const unsigned*)(s->halo_mem + L.flag(side)), seq1, s->counters, timeout_ns); CKLN(s, "halo_wait");
+        const int grid = std::min((int)((L.H + 7) / 8), s->sm_count * 4);
+        k_halo_add<<<grid, 256, 0, s->stream>>>(A, node0, (int)L.H, (const float4*)(s->halo_mem + L.rx(side, slot)), (const uint32_t*)(s->halo_mem + L.stamp(side, slot)), seq1); CKLN(s, "halo_add");
+        s->halo_seq[side]++;
+    }
+    s->halo_exchanges++;
+    return SMX_OK;
+}
+// the two halves of one exchange as separate calls (ranks emulated in one process on one stream must all push before anyone waits)
+int smx_slab_halo_push(smx_sim* s, int32_t which, int32_t f) {
+    if (!s || !s->peers_on()) return fail(SMX_ERR_STATE, "smx_slab_halo_push: neighbours are not connected (smx_slab_halo_connect)");
+    if (which != 0 && which != 1 && which != 3 && which != 4) return fail(SMX_ERR_RANGE, "smx_slab_halo_push: array in {0, 1, 3, 4}");
+    CK(cudaSetDevice(s->cfg.device));
+    return halo_push(s, which, f);
+}
+int smx_slab_halo_add(smx_sim* s, int32_t which, int32_t f) {
+    if (!s || !s->peers_on()) return fail(SMX_ERR_STATE, "smx_slab_halo_add: neighbours are not connected (smx_slab_halo_connect)");
+    if (which != 0 && which != 1 && which != 3 && which != 4) return fail(SMX_ERR_RANGE, "smx_slab_halo_add: array in {0, 1, 3, 4}");
+    CK(cudaSetDevice(s->cfg.device));
+    return halo_add(s, which, f);
+}
+static int halo_exchange(smx_sim* s, int which, int f) {
+    TRY(halo_push(s, which, f));
+    return halo_add(s, which, f);
+}
+// out[0]: exchanges that gave up waiting for the neighbour (must be 0), out[1]: exchanges done, out[2]: bytes of the halo allocation
+int smx_slab_halo_status(smx_sim* s, int64_t out[3]) {
+    if (!s || !out) return fail(SMX_ERR_ARG, "smx_slab_halo_status: null argument");
+    CK(cudaSetDevice(s->cfg.device));
+    unsigned long long t = 0;
+    CK(cudaMemcpyAsync(&t, s->counters + 3, sizeof t, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    out[0] = (int64_t)t; out[1] = s->halo_exchanges; out[2] = (int64_t)s->halo_bytes;
+    return SMX_OK;
+}
+
 // device pointer and size of a grid array: 0 g_in, 1 g_out, 2 g_mix, 3 gg_out, 4 gg_mix (float4 per node, block-major:
 // x-block column c is the contiguous element range [c * nb^2 * 64, (c+1) * nb^2 * 64))
 int smx_grid_dev(smx_sim* s, int32_t which, void** ptr, int64_t* n_float4) {
@@ -1590,10 +1738,11 @@ int smx_stream(smx_sim* s, void** stream) {
 
 // `count` consecutive substeps.  Between two substeps that share an ordering the G2P of the first is fused into the P2G
 // of the second ("G2P2G": one launch, frame f's x, v, C go from registers straight into the next scatter); results are
-// identical to calling smx_substep in a loop.  Disabled by SMX_FLAG_NO_FUSION, in slab mode and with velocity control.
+// identical to calling smx_substep in a loop.  Disabled by SMX_FLAG_NO_FUSION, with velocity control and for a slab rank whose halos are
+// exchanged by the caller; a slab rank with connected neighbours (smx_slab_halo_connect) keeps the fusion: its halo sums run in here.
 int smx_step(smx_sim* s, int32_t s0, int32_t count) {
     if (!s) return fail(SMX_ERR_ARG, "smx_step: null simulator");
-    bool fuse_ok = !(s->cfg.flags & SMX_FLAG_NO_FUSION) && !s->slab && !s->cfg.rigid_velocity_control && s->P.n > 0;
+    bool fuse_ok = !(s->cfg.flags & SMX_FLAG_NO_FUSION) && !s->slab_legacy() && !s->cfg.rigid_velocity_control && s->P.n > 0;
     if (!fuse_ok || count < 2) {
         for (int i = 0; i < count; i++) TRY(smx_substep(s, s0 + i));
         return SMX_OK;
@@ -1612,7 +1761,9 @@ int smx_step(smx_sim* s, int32_t s0, int32_t count) {
             TRY(forward_p2g(s, f, true, true, true));
             pending_g2p = false;
         }
+        if (s->peers_on()) TRY(halo_exchange(s, 0, f));
         TRY(smx_substep_mid(s, f));
+        if (s->peers_on() && s->has_contact()) TRY(halo_exchange(s, 1, f));
         s->mid_done = -1;
         s->last_fwd = f;
         bool resort_next = s->cfg.sort_every > 0 && s->age_of[f + 1] >= s->cfg.sort_every && !(s->cfg.flags & SMX_FLAG_NO_SORT);
@@ -1637,7 +1788,9 @@ int smx_step_grad(smx_sim* s, int32_t s1, int32_t count) {
     for (int i = 1; i <= count; i++) {
         const int f = s1 - i;
         if (!g2p_done) TRY(smx_substep_grad_begin(s, f));
+        if (s->peers_on()) TRY(halo_exchange(s, 3, f));
         TRY(smx_substep_grad_mid(s, f));
+        if (s->peers_on() && s->has_contact()) TRY(halo_exchange(s, 4, f));
         const bool fuse = i < count && can_fuse_bwd(s, f);
         const int rc = grad_end(s, f, fuse);
         if (rc != SMX_OK) { s->adj_frame = -1; s->adj_partial = false; s->grad_pending = -1; return rc; }

@@ -1548,6 +1548,72 @@ __global__ void __launch_bounds__(256) k_ckpt_copy(const uint32_t* __restrict__ 
 }
 // slab decomposition: force every block of x-block column `col` active (the halo columns exchanged with a neighbour
 // must be cleared / updated every substep even where no local particle reaches them)
+// ------------------------------------------------------------------------------------------------
+// Slab halo exchange over peer memory (NVLink / NVSwitch; the same kernels serve several ranks emulated on one device).
+// The 2-column halo range of a grid array is H = 2 nb^2 blocks of 64 nodes.  k_halo_push: one warp per halo block; a block that holds
+// anything is written straight into the NEIGHBOUR's receive slot (128-bit peer stores) and stamped with the sequence number of this
+// exchange -- empty blocks (~85 % of a halo) never travel and are never read -- then the last CTA releases the neighbour's flag
+// (system-scope store after a system fence).  k_halo_wait: ONE thread polls the own flag (so that a waiting rank occupies no SM);
+// k_halo_add: adds the stamped blocks of the own receive slot into the grid.  Slots alternate with the sequence number: the push of
+// exchange q + 2 into slot q & 1 is ordered after the neighbour's add of exchange q through the flags of exchange q + 1.
+// MODE 0: push A; MODE 1: push A - B (own contact scatter g_out - g_mix of the forecast contact model).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+template <int MODE>
+__global__ void __launch_bounds__(256) k_halo_push(const float4* __restrict__ A, const float4* __restrict__ B, size_t node0, int H, float4* __restrict__ peer_rx,
+                                                   uint32_t* __restrict__ peer_stamp, unsigned* __restrict__ peer_flag, unsigned seq1, unsigned* __restrict__ done) {
+    const int lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int hb = warp; hb < H; hb += nwarps) {
+        const size_t base = node0 + (size_t)hb * 64;
+        float4 v0 = A[base + lane], v1 = A[base + 32 + lane];
+        if (MODE == 1) {
+            const float4 b0 = B[base + lane], b1 = B[base + 32 + lane];
+            v0 = make_float4(v0.x - b0.x, v0.y - b0.y, v0.z - b0.z, 0.f); v1 = make_float4(v1.x - b1.x, v1.y - b1.y, v1.z - b1.z, 0.f);
+        }
+        const bool nz = v0.x != 0.f || v0.y != 0.f || v0.z != 0.f || v0.w != 0.f || v1.x != 0.f || v1.y != 0.f || v1.z != 0.f || v1.w != 0.f;
+        if (__any_sync(0xffffffffu, nz)) {
+            peer_rx[(size_t)hb * 64 + lane] = v0; peer_rx[(size_t)hb * 64 + 32 + lane] = v1;
+            if (lane == 0) peer_stamp[hb] = seq1;
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (atomicAdd(done, 1u) == gridDim.x - 1) {     // last CTA: everything every CTA wrote is fenced
+            *done = 0u;
+            __threadfence_system();
+            st_release_sys(peer_flag, seq1);
+        }
+    }
+}
+// counters[3] counts exchanges that gave up waiting (neighbour gone): the run is invalid then, but the GPU is not left spinning
+__global__ void k_halo_wait(const unsigned* __restrict__ flag, unsigned seq1, unsigned long long* __restrict__ counters, long long timeout_ns) {
+    long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while ((int)(ld_acquire_sys(flag) - seq1) < 0) {
+        __nanosleep(200);
+        long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (t - t0 > timeout_ns) { atomicAdd(counters + 3, 1ull); break; }
+    }
+}
+__global__ void __launch_bounds__(256) k_halo_add(float4* __restrict__ A, size_t node0, int H, const float4* __restrict__ rx, const uint32_t* __restrict__ stamp, unsigned seq1) {
+    const int lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int hb = warp; hb < H; hb += nwarps) {
+        if (__ldcg(stamp + hb) != seq1) continue;
+        const size_t base = node0 + (size_t)hb * 64;
+        const float4* r = rx + (size_t)hb * 64;                 // written by the neighbour: read past L1
+        float4 a0 = A[base + lane], a1 = A[base + 32 + lane];
+        const float4 r0 = __ldcg(r + lane), r1 = __ldcg(r + 32 + lane);
+        A[base + lane] = make_float4(a0.x + r0.x, a0.y + r0.y, a0.z + r0.z, a0.w + r0.w);
+        A[base + 32 + lane] = make_float4(a1.x + r1.x, a1.y + r1.y, a1.z + r1.z, a1.w + r1.w);
+    }
+}
 __global__ void k_mark_column(uint32_t* __restrict__ flags, int nb, int col) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < nb * nb) flags[(size_t)col * nb * nb + t] = 1u;

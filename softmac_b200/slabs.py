@@ -10,8 +10,14 @@ single contiguous 2-column range that is exchanged with one send/recv pair and s
     adjoint  : begin (restore, G2P adj)  -> sum gg_out halo  -> end (grid adjoint, P2G adj)
 
 Both ranks then hold identical, complete values on the shared columns (a + b == b + a) and update them redundantly, so
-no second (broadcast) exchange is needed.  Transport: ``torch.distributed`` P2P (NCCL over NVLink) with one process per
-GPU, or plain tensor adds for several ranks emulated in one process (tests on a single GPU).
+no second (broadcast) exchange is needed.  Transport (``peer=True``, the default of ``DistSlab``): PEER MEMORY -- every rank
+owns one allocation of receive slots that its x-neighbours write into directly over NVLink (CUDA IPC between the processes);
+the library pushes the non-empty halo blocks, flags, waits and adds on the simulator's stream inside ``smx_step`` /
+``smx_step_grad`` (``smx_slab_halo_*``), so a whole ``step(count)`` is ONE native call per rank with no host round trip, no
+NCCL call on the data path and the cross-substep fusion (G2P2G, fused adjoint pair, deferred grid records) intact;
+``torch.distributed`` only carries the IPC handles at set-up and the read-out reductions.  ``peer=False`` keeps the first
+transport: the dense 2-column range through ``torch.distributed`` P2P (NCCL) with one Python round trip per phase, or plain
+tensor adds for several ranks emulated in one process on one stream.
 
 With the forecast contact model two more halo operations are needed: the contact kernel scatters velocity corrections
 into g_out, so after it every rank adds the neighbour's part of (g_out - g_mix) on the halo; in the adjoint the contact
@@ -97,6 +103,23 @@ class SlabRank:
             self._views[key] = full[(b - 1) * col:(b + 1) * col]
         return self._views[key]
 
+    # halo exchange over peer memory --------------------------------------------------------------------------------
+    def halo_export(self):
+        """(device pointer, 64-byte CUDA IPC handle) of this rank's halo allocation."""
+        base, h = vp(), (C.c_ubyte * 64)()
+        check(lib().smx_slab_halo_export(self.sim._h, C.byref(base), C.cast(h, vp)))
+        return int(base.value), bytes(h)
+
+    def halo_connect(self, side, base=None, handle=None):
+        """side 0: the rank below, side 1: the rank above; `base` (same process) or `handle` (another process)."""
+        hb = (C.c_ubyte * 64).from_buffer_copy(handle) if handle is not None else None
+        check(lib().smx_slab_halo_connect(self.sim._h, int(side), vp(base) if base is not None else None, C.cast(hb, vp) if hb is not None else None))
+
+    def halo_status(self):
+        out = (C.c_int64 * 3)()
+        check(lib().smx_slab_halo_status(self.sim._h, out))
+        return dict(timeouts=int(out[0]), exchanges=int(out[1]), halo_bytes=int(out[2]))
+
     # phases ------------------------------------------------------------------------------------------------------
     def begin(self, f):
         check(lib().smx_substep_begin(self.sim._h, int(f)))
@@ -128,13 +151,60 @@ class SlabRank:
 class SlabCluster:
     """All ranks emulated in ONE process on one device (tests / single-GPU use): same phases, halos summed directly."""
 
-    def __init__(self, cfg, n_ranks, state, device=0, make_primitives=None, **sim_kw):
-        """make_primitives() -> a fresh Primitives container (every rank needs its own, bound to its handle)."""
+    def __init__(self, cfg, n_ranks, state, device=0, make_primitives=None, peer=False, **sim_kw):
+        """make_primitives() -> a fresh Primitives container (every rank needs its own, bound to its handle).
+        peer: the ranks exchange their halos through the library's peer-memory path (smx_slab_halo_*), every rank on a stream of its
+        own and driven by a host thread of its own -- the single-device rehearsal of one process per GPU."""
         n_grid = int(128 * cfg.quality * 0.5)
         self.n = len(state)
+        self.peer = bool(peer)
         self.bounds = choose_bounds(np.asarray(state)[:, 0], n_ranks, n_grid)
-        self.ranks = [SlabRank(cfg, r, self.bounds, state, device=device, primitives=make_primitives() if make_primitives else (), **sim_kw)
-                      for r in range(n_ranks)]
+        self.ranks = [SlabRank(cfg, r, self.bounds, state, device=device, primitives=make_primitives() if make_primitives else (),
+                               use_torch_stream=not self.peer, **sim_kw) for r in range(n_ranks)]
+        if self.peer:
+            import os
+            if os.environ.get("CUDA_MODULE_LOADING", "").upper() != "EAGER":
+                raise RuntimeError("SlabCluster(peer=True) emulates the ranks in one process: set CUDA_MODULE_LOADING=EAGER before CUDA is initialised "
+                                   "(a rank that waits on a device flag would otherwise block the lazy load of a kernel its neighbour launches for the "
+                                   "first time); one process per GPU (DistSlab) does not need it")
+            bases = [r.halo_export()[0] for r in self.ranks]
+            for i, r in enumerate(self.ranks):
+                if i > 0:
+                    r.halo_connect(0, base=bases[i - 1])
+                if i < n_ranks - 1:
+                    r.halo_connect(1, base=bases[i + 1])
+
+    def _threads(self, fn):
+        """fn(rank) on one host thread per rank (the native calls release the GIL): the ranks enqueue concurrently, as separate processes would."""
+        import threading
+        errs = []
+
+        def run(r):
+            try:
+                fn(r)
+            except Exception as e:      # noqa: BLE001
+                errs.append(e)
+        ts = [threading.Thread(target=run, args=(r,)) for r in self.ranks]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        if errs:
+            raise errs[0]
+
+    def step(self, s0, count):
+        if self.peer:
+            self._threads(lambda r: r.sim.step(s0, count))
+        else:
+            for f in range(s0, s0 + count):
+                self.substep(f)
+
+    def step_grad(self, s1, count):
+        if self.peer:
+            self._threads(lambda r: r.sim.step_grad(s1, count))
+        else:
+            for f in range(s1 - 1, s1 - 1 - count, -1):
+                self.substep_grad(f)
 
     def _exchange(self, which):
         for r in range(len(self.ranks) - 1):
@@ -150,6 +220,8 @@ class SlabCluster:
             L.halo(1, "hi").add_(db); R.halo(1, "lo").add_(da)
 
     def substep(self, f):
+        if self.peer:
+            return self._threads(lambda r: r.sim.substep(f))
         contact = self.ranks[0].has_contact()
         for r in self.ranks:
             r.begin(f)
@@ -162,6 +234,8 @@ class SlabCluster:
             r.end(f)
 
     def substep_grad(self, f):
+        if self.peer:
+            return self._threads(lambda r: r.sim.substep_grad(f))
         contact = self.ranks[0].has_contact()
         for r in self.ranks:
             r.grad_begin(f)
@@ -216,7 +290,7 @@ class SlabCluster:
 class DistSlab:
     """One rank per process (torchrun, NCCL): this process's slab + P2P halo exchange with its x-neighbours."""
 
-    def __init__(self, cfg, state, device=None, make_primitives=None, **sim_kw):
+    def __init__(self, cfg, state, device=None, make_primitives=None, peer=True, **sim_kw):
         import torch
         import torch.distributed as dist
         self.dist = dist
@@ -224,11 +298,22 @@ class DistSlab:
         self.device = torch.cuda.current_device() if device is None else device
         n_grid = int(128 * cfg.quality * 0.5)
         self.n = len(state)
+        self.peer = bool(peer) and self.world > 1
         self.bounds = choose_bounds(np.asarray(state)[:, 0], self.world, n_grid)     # deterministic: same on every rank
-        self.r = SlabRank(cfg, self.rank, self.bounds, state, device=self.device, primitives=make_primitives() if make_primitives else (), **sim_kw)
+        self.r = SlabRank(cfg, self.rank, self.bounds, state, device=self.device, primitives=make_primitives() if make_primitives else (),
+                          use_torch_stream=not self.peer, **sim_kw)
         self.primitives = self.r.primitives
         self.sim = self.r.sim
         self._tmp = {}
+        if self.peer:
+            # one all-gather of the 64-byte IPC handles; from here on the halo sums are peer-memory kernels on the simulator's stream
+            handles = [None] * self.world
+            dist.all_gather_object(handles, self.r.halo_export()[1])
+            if self.rank > 0:
+                self.r.halo_connect(0, handle=handles[self.rank - 1])
+            if self.rank < self.world - 1:
+                self.r.halo_connect(1, handle=handles[self.rank + 1])
+            dist.barrier()
 
     def _exchange(self, which):
         import torch
@@ -261,6 +346,8 @@ class DistSlab:
                 v.add_(t)
 
     def substep(self, f):
+        if self.peer:
+            return self.sim.substep(f)
         self.r.begin(f)
         self._exchange(0)
         if self.r.has_contact():
@@ -269,6 +356,8 @@ class DistSlab:
         self.r.end(f)
 
     def substep_grad(self, f):
+        if self.peer:
+            return self.sim.substep_grad(f)
         self.r.grad_begin(f)
         self._exchange(3)
         if self.r.has_contact():
@@ -290,12 +379,19 @@ class DistSlab:
         return self._allreduce(self.primitives[i].get_all_states_grad(f0, f_end=f1))
 
     def step(self, s0, count):
+        if self.peer:
+            return self.sim.step(s0, count)     # ONE native call: substeps, halo sums and fusion all inside smx_step
         for f in range(s0, s0 + count):
             self.substep(f)
 
     def step_grad(self, s1, count):
+        if self.peer:
+            return self.sim.step_grad(s1, count)
         for f in range(s1 - 1, s1 - 1 - count, -1):
             self.substep_grad(f)
+
+    def halo_status(self):
+        return self.r.halo_status() if self.peer else dict(timeouts=0, exchanges=0, halo_bytes=0)
 
     def add_x_grad(self, f, g_global):
         self.sim.add_x_grad(f, np.asarray(g_global)[self.r.ids])

@@ -1,3 +1,9 @@
+import os as _os
+
+# slab ranks emulated in ONE process (SlabCluster(peer=True)) spin on device flags: every kernel must be loaded before anyone waits, so that
+# a first launch by one rank never has to load a module while another rank's wait kernel is resident (read at CUDA initialisation)
+_os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+
 import os
 import sys
 import pytest

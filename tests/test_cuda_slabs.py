@@ -188,3 +188,94 @@ def test_migration_with_forecast_contact_across_the_boundary():
     assert rel_l2(ga, gb) <= 2e-4 and cosine(ga, gb) >= 0.99999
     pa, pb = clu.primitive_state_grad(0, 0, steps), pr[0].get_all_states_grad(0, f_end=steps)
     assert np.abs(pb).max() > 0 and rel_l2(pa, pb) <= 1e-3
+
+
+@pytest.mark.parametrize("n_ranks,fused", [(2, True), (3, True), (2, False)])
+def test_peer_memory_halo_exchange_matches_single_handle(n_ranks, fused):
+    """The library's own halo exchange (smx_slab_halo_*: push of the non-empty halo blocks into the neighbour's receive slot, flag,
+    one-thread wait, add -- all on the rank's stream): R ranks, each on its own stream and host thread, ONE native call per rank for
+    the whole rollout (`fused`: smx_step / smx_step_grad with G2P2G, the fused adjoint pair and the deferred grid records; otherwise
+    substep by substep) must reproduce the single-handle simulation, forward and adjoint; no exchange may time out."""
+    from softmac_b200.engine import MPMSimulator
+    from softmac_b200.slabs import SlabCluster
+    rng = np.random.default_rng(31)
+    n, steps, n_grid = 20000, 7, 64
+    st = scenes.blob_state(n, rng, center=(0.5, 0.3, 0.5), width=0.5, vel=0.5, Fdev=0.003, Cdev=0.5)
+    st[:, 1] = 0.3 + (st[:, 1] - 0.3) * 0.3
+    st = st.astype(np.float32).astype(np.float64)
+    cfg = sim_cfg(n, n_grid=n_grid, max_steps=steps + 2)
+    ref = MPMSimulator(cfg, (), env_dt=1e-3, sort_every=3)
+    ref.reset(st)
+    clu = SlabCluster(cfg, n_ranks, st, peer=True, env_dt=1e-3, sort_every=3)
+    ref.step(0, steps)
+    if fused:
+        clu.step(0, steps)
+    else:
+        for f in range(steps):
+            clu.substep(f)
+    a, b = clu.get_state(steps), ref.get_state(steps)
+    assert rel_l2(a[:, :3], b[:, :3]) <= 1e-6
+    assert rel_l2(a[:, 3:6], b[:, 3:6]) <= 2e-5
+    assert rel_l2(a[:, 6:], b[:, 6:]) <= 2e-5
+    g = rng.normal(size=(n, 3))
+    ref.clear_all_gradients(); ref.add_x_grad(steps, g)
+    clu.add_x_grad(steps, g)
+    ref.step_grad(steps, steps)
+    if fused:
+        clu.step_grad(steps, steps)
+    else:
+        for f in range(steps - 1, -1, -1):
+            clu.substep_grad(f)
+    ga, gb = clu.get_state_grad(0), ref.get_state_grad(0)
+    assert np.abs(gb).max() > 0
+    assert rel_l2(ga, gb) <= 1e-4 and cosine(ga, gb) >= 0.99999
+    for r in clu.ranks:
+        hs = r.halo_status()
+        assert hs["timeouts"] == 0 and hs["exchanges"] == 2 * steps, hs
+    for c in clu.counters():
+        assert c["left_active_region"] == 0 and c["clamped"] == 0 and c["resorts"] >= 2
+
+
+def test_peer_memory_halo_exchange_with_forecast_contact_across_the_boundary():
+    """Peer-memory transport with a sphere on the slab boundary: four halo sums per substep pair (g_in, the contact scatter into g_out,
+    the adjoint grid, gg_mix), inside smx_step / smx_step_grad with the deferred post-contact grid records."""
+    from softmac_b200.engine import MPMSimulator, Primitives, Mesh
+    from softmac_b200.slabs import SlabCluster
+    rng = np.random.default_rng(33)
+    n, steps, n_grid = 12000, 6, 64
+    center = np.array([0.5, 0.3, 0.5])
+    st = scenes.contact_rollout_state(n, rng, center, width=0.16)
+    tab = scenes.sphere_table()
+    cfg = sim_cfg(n, n_grid=n_grid, max_steps=steps + 2)
+    s13 = np.concatenate([center, [1, 0, 0, 0], [0.0, 0.2, 0.0], [0, 0, 0.3]])
+
+    def make_prims():
+        m = Mesh(sdf=dict(sdf=tab["sdf"], normal=tab["normal"], position=(tab["lower"], tab["upper"]), dx=tab["dx"]), cfg=dict(friction=0.5),
+                 max_timesteps=steps + 2)
+        p = Primitives(primitives=[m], max_timesteps=steps + 2)
+        p.initialize()
+        return p
+
+    pr = make_prims()
+    ref = MPMSimulator(cfg, pr, env_dt=1e-3, sort_every=3)
+    pr[0].set_all_states(0, s13, f_end=steps + 2)
+    ref.reset(st); pr[0].clear_ext_f()
+    clu = SlabCluster(cfg, 2, st, make_primitives=make_prims, peer=True, env_dt=1e-3, sort_every=3)
+    assert abs(clu.bounds[1] * 4 / n_grid - 0.5) < 0.05           # the boundary cuts through the contact region
+    clu.set_primitive_state(0, 0, steps + 2, s13); clu.clear_ext_f()
+    ref.step(0, steps); clu.step(0, steps)
+    a, r = clu.get_state(steps), ref.get_state(steps)
+    assert rel_l2(a[:, :3], r[:, :3]) <= 1e-6 and rel_l2(a[:, 3:6], r[:, 3:6]) <= 5e-5
+    fe = pr[0].get_ext_f()
+    assert np.abs(fe).max() > 0 and rel_l2(clu.ext_f(0), fe) <= 1e-4
+    g = rng.normal(size=(n, 3)); ext = rng.normal(size=6) * 1e-3
+    ref.clear_all_gradients(); ref.add_x_grad(steps, g); clu.add_x_grad(steps, g)
+    pr[0].set_ext_f_grad(ext); clu.set_ext_f_grad(0, ext)
+    ref.step_grad(steps, steps); clu.step_grad(steps, steps)
+    ga, gb = clu.get_state_grad(0), ref.get_state_grad(0)
+    assert rel_l2(ga, gb) <= 2e-4 and cosine(ga, gb) >= 0.99999
+    pa, pb = clu.primitive_state_grad(0, 0, steps), pr[0].get_all_states_grad(0, f_end=steps)
+    assert np.abs(pb).max() > 0 and rel_l2(pa, pb) <= 1e-3
+    for rk in clu.ranks:
+        hs = rk.halo_status()
+        assert hs["timeouts"] == 0 and hs["exchanges"] == 4 * steps, hs

@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""BASELINE config 5: one large scene split into x-slabs across the GPUs of a box, halo exchange over NCCL P2P.
+"""BASELINE config 5: one large scene split into x-slabs across the GPUs of a box, halo exchange over peer memory (NVLink; `--nccl`: the
+first transport, dense halos through torch.distributed P2P with one Python round trip per phase).
 
   torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/bench_slabs.py [--particles 8000000] [--grid 256] [--substeps 32]
   python tools/bench_slabs.py --check           # (under torchrun) small scene, compares against a single-handle run on rank 0
@@ -21,7 +22,7 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
         sys.path.insert(0, p)
 
 
-def slab_record(n, n_grid, S, rank, ws, local, reps=3, sort_every=16, check=False, migrate_every=0, sphere=False, drift=0.0):
+def slab_record(n, n_grid, S, rank, ws, local, reps=3, sort_every=16, check=False, migrate_every=0, sphere=False, drift=0.0, peer=True):
     """One strong-scaling measurement of the slab decomposition (the process group must exist when ws > 1).  Returns the record on
     rank 0 (None elsewhere); with check=True the forward states are compared with a single handle on rank 0."""
     import types
@@ -56,7 +57,7 @@ def slab_record(n, n_grid, S, rank, ws, local, reps=3, sort_every=16, check=Fals
     if ws > 1 and E:
         sl = DistMigratingSlab(cfg, st, E, env_dt=5 * dt, sort_every=args.sort_every, make_primitives=make_prims)
     elif ws > 1:
-        sl = DistSlab(cfg, st, env_dt=5 * dt, sort_every=args.sort_every, make_primitives=make_prims)
+        sl = DistSlab(cfg, st, env_dt=5 * dt, sort_every=args.sort_every, make_primitives=make_prims, peer=peer)
     if args.sphere and ws > 1:
         if E:
             sl.set_primitive_state(0, 0, S + 2, s13); sl.clear_ext_f()
@@ -110,6 +111,11 @@ def slab_record(n, n_grid, S, rank, ws, local, reps=3, sort_every=16, check=Fals
             dist.barrier()
         if r >= 2:
             times.append(time.perf_counter() - t0)
+        if r == 0 and ws > 1 and not migrating:         # a neighbour that never answers: stop before the timed repetitions pile up timeouts
+            bad = torch.tensor([float(sl.halo_status()["timeouts"])], dtype=torch.float64, device="cuda")
+            dist.all_reduce(bad)
+            if bad.item() > 0:
+                return {"error": "halo exchange timed out on %d exchanges in the first pass" % int(bad.item()), "n_gpus": ws} if rank == 0 else None
     t = torch.tensor([float(np.median(times))], dtype=torch.float64, device="cuda")
     if ws > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -117,6 +123,13 @@ def slab_record(n, n_grid, S, rank, ws, local, reps=3, sort_every=16, check=Fals
     out = {"workload": f"slab decomposition (config 5): {args.n} particles, {args.n_grid}^3, {S} substeps fwd + {S} bwd", "n_gpus": ws,
            "ms_per_step": T * 1e3, "particle_substeps_per_s_fwd_bwd": args.n * S / T, "scaling": "strong", "local_particles": int(sim.n_particles),
            "counters": sim.counters()}
+    if ws > 1 and not migrating:
+        hs = sl.halo_status()
+        out["transport"] = ("peer memory: non-empty halo blocks pushed into the neighbour's receive slot over NVLink, flag / wait / add kernels on the "
+                            "simulator's stream inside smx_step (one native call per rank and pass)") if sl.peer else "torch.distributed P2P (NCCL), dense 2-column halos, one Python round trip per phase"
+        out["halo"] = hs
+        if hs["timeouts"]:
+            out["error"] = "a halo exchange timed out: the numbers of this record are invalid"
     if migrating:
         out["migrate_every"] = E
         out["migrated_particles_per_step"] = sl.migrated()
@@ -163,6 +176,7 @@ def main():
     ap.add_argument("--migrate-every", type=int, default=0, help="re-establish particle ownership every E substeps (particle migration "
                     "between slab ranks over NCCL P2P); 0: ownership fixed at reset")
     ap.add_argument("--sphere", action="store_true", help="(with --check) a sphere primitive on the slab boundary: forecast contact, wrench summed over ranks")
+    ap.add_argument("--nccl", action="store_true", help="halo exchange through torch.distributed P2P (the first transport) instead of peer memory")
     ap.add_argument("--drift", type=float, default=0.0, help="add this x-velocity (m/s) to every particle so that material streams through the slab boundaries")
     args = ap.parse_args()
     import torch
@@ -173,7 +187,7 @@ def main():
     if args.check:
         args.n, args.n_grid, args.substeps = 200_000, 64, 8
     out = slab_record(args.n, args.n_grid, args.substeps, rank, ws, local, reps=args.reps, sort_every=args.sort_every, check=args.check,
-                      migrate_every=args.migrate_every, sphere=args.sphere, drift=args.drift)
+                      migrate_every=args.migrate_every, sphere=args.sphere, drift=args.drift, peer=not args.nccl)
     if rank == 0:
         print(json.dumps(out), flush=True)
     if ws > 1:
