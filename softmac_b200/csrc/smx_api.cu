@@ -1655,41 +1655,44 @@ int smx_slab_halo_connect(smx_sim* s, int32_t side, void* base, const void* ipc_
     return SMX_OK;
 }
 // halo arrays: 0 g_in (P2G sums), 1 g_out += neighbour's (g_out - g_mix) (contact scatter), 3 adjoint grid of substep f, 4 gg_mix
-static int halo_push(smx_sim* s, int which, int f) {
+static float4* halo_array(smx_sim* s, int which, int f) { return which == 0 ? s->g_in : which == 1 ? s->g_out : which == 3 ? s->gg_of(f) : s->gg_mix; }
+// push == true: the neighbours' slots / stamps / flags (what this rank writes); else this rank's own (what it waits for and adds)
+static HaloSides halo_sides(smx_sim* s, bool push) {
     const int nb = s->P.nb;
     HaloLayout L(nb);
-    float4* A = which == 0 ? s->g_in : which == 1 ? s->g_out : which == 3 ? s->gg_of(f) : s->gg_mix;
+    HaloSides hs;
     for (int side = 0; side < 2; side++) {
-        if (!(side == 0 ? s->halo_lo : s->halo_hi)) continue;
+        hs.on[side] = (side == 0 ? s->halo_lo : s->halo_hi) ? 1 : 0;
         const int b = side == 0 ? s->slab_lo : s->slab_hi;
-        const size_t node0 = (size_t)(b - 1) * nb * nb * 64;
-        const unsigned seq1 = s->halo_seq[side] + 1;
-        const int slot = (int)(s->halo_seq[side] & 1u), pside = 1 - side;       // my lo neighbour receives on ITS hi side
-        unsigned char* pb = s->peer_base[side];
-        float4* prx = (float4*)(pb + L.rx(pside, slot)); uint32_t* pst = (uint32_t*)(pb + L.stamp(pside, slot)); unsigned* pfl = (unsigned*)(pb + L.flag(pside));
-        const int grid = std::min((int)((L.H + 7) / 8), s->sm_count * 4);
-        if (which == 1) k_halo_push<1><<<grid, 256, 0, s->stream>>>(A, s->g_mix, node0, (int)L.H, prx, pst, pfl, seq1, s->halo_done + side);
-        else k_halo_push<0><<<grid, 256, 0, s->stream>>>(A, nullptr, node0, (int)L.H, prx, pst, pfl, seq1, s->halo_done + side);
-        CKLN(s, "halo_push");
+        hs.node0[side] = hs.on[side] ? (size_t)(b - 1) * nb * nb * 64 : 0;
+        hs.seq1[side] = s->halo_seq[side] + 1;
+        const int slot = (int)(s->halo_seq[side] & 1u);
+        unsigned char* base = push ? s->peer_base[side] : s->halo_mem;
+        const int at = push ? 1 - side : side;          // my lo neighbour receives on ITS hi side
+        hs.rx[side] = hs.on[side] ? (float4*)(base + L.rx(at, slot)) : nullptr;
+        hs.stamp[side] = hs.on[side] ? (uint32_t*)(base + L.stamp(at, slot)) : nullptr;
+        hs.flag[side] = hs.on[side] ? (unsigned*)(base + L.flag(at)) : nullptr;
+        hs.done[side] = s->halo_done + side;
     }
+    return hs;
+}
+static int halo_push(smx_sim* s, int which, int f) {
+    HaloLayout L(s->P.nb);
+    const HaloSides hs = halo_sides(s, true);
+    const dim3 grid(std::min((int)((L.H + 7) / 8), s->sm_count * 2), 2);
+    if (which == 1) k_halo_push<1><<<grid, 256, 0, s->stream>>>(halo_array(s, which, f), s->g_mix, (int)L.H, hs);
+    else k_halo_push<0><<<grid, 256, 0, s->stream>>>(halo_array(s, which, f), nullptr, (int)L.H, hs);
+    CKLN(s, "halo_push");
     return SMX_OK;
 }
 static int halo_add(smx_sim* s, int which, int f) {
-    const int nb = s->P.nb;
-    HaloLayout L(nb);
-    float4* A = which == 0 ? s->g_in : which == 1 ? s->g_out : which == 3 ? s->gg_of(f) : s->gg_mix;
+    HaloLayout L(s->P.nb);
     static const long long timeout_ns = getenv("SMX_HALO_TIMEOUT_MS") ? atoll(getenv("SMX_HALO_TIMEOUT_MS")) * 1000000ll : 2000000000ll;
-    for (int side = 0; side < 2; side++) {
-        if (!(side == 0 ? s->halo_lo : s->halo_hi)) continue;
-        const int b = side == 0 ? s->slab_lo : s->slab_hi;
-        const size_t node0 = (size_t)(b - 1) * nb * nb * 64;
-        const unsigned seq1 = s->halo_seq[side] + 1;
-        const int slot = (int)(s->halo_seq[side] & 1u);
-        k_halo_wait<<<1, 1, 0, s->stream>>>((const unsigned*)(s->halo_mem + L.flag(side)), seq1, s->counters, timeout_ns); CKLN(s, "halo_wait");
-        const int grid = std::min((int)((L.H + 7) / 8), s->sm_count * 4);
-        k_halo_add<<<grid, 256, 0, s->stream>>>(A, node0, (int)L.H, (const float4*)(s->halo_mem + L.rx(side, slot)), (const uint32_t*)(s->halo_mem + L.stamp(side, slot)), seq1); CKLN(s, "halo_add");
-        s->halo_seq[side]++;
-    }
+    const HaloSides hs = halo_sides(s, false);
+    k_halo_wait<<<1, 32, 0, s->stream>>>(hs, s->counters, timeout_ns); CKLN(s, "halo_wait");
+    const dim3 grid(std::min((int)((L.H + 7) / 8), s->sm_count * 2), 2);
+    k_halo_add<<<grid, 256, 0, s->stream>>>(halo_array(s, which, f), (int)L.H, hs); CKLN(s, "halo_add");
+    for (int side = 0; side < 2; side++) if (hs.on[side]) s->halo_seq[side]++;
     s->halo_exchanges++;
     return SMX_OK;
 }

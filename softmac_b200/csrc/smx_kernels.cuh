@@ -126,9 +126,10 @@ __device__ __forceinline__ void red_add_f4(float4* addr, float a, float b, float
 // ------------------------------------------------------------------------------------------------
 struct WarpStage {
     float4 val[32 * 27];    // [lane][offset]; row stride 27 float4 -> conflict-free 128-bit stores
-    uint32_t key[32];       // [lane] packed base cell (pack_base) of the slot: the owning lane rebuilds its node address per run
+    uint32_t key[32];       // [lane] block-major index of the slot's base cell: the owning lane derives its node address per run (RunNode)
 };
-__device__ __forceinline__ uint32_t pack_base(int bx, int by, int bz, int bt = 0) { return (uint32_t)bx | ((uint32_t)by << 8) | ((uint32_t)bz << 16) | ((uint32_t)bt << 24); }
+// block-major index of a stencil's base cell (batch offset included): the key of the scatter runs
+__device__ __forceinline__ uint32_t base_node(const struct Stencil& s);
 
 // packed fp32x2 add (sm_100a: one FADD2 instead of two FADD)
 __device__ __forceinline__ void add_f4(float4& a, const float4& b) {
@@ -149,11 +150,27 @@ __device__ __forceinline__ void flush_prologue(uint32_t* keys, uint32_t key, boo
     alive = __ballot_sync(0xffffffffu, live);
     __syncwarp();
 }
-// node (bx + a, by + b, bz + c) of the run whose first slot carries `key`, as a block-major index (see node_index / make_stencil)
-__device__ __forceinline__ uint32_t run_node(uint32_t key, int a, int b, int c, int nb, int Gb) {
-    const int i = (int)(key & 255u) + a, j = (int)((key >> 8) & 255u) + b, k = (int)((key >> 16) & 255u) + c;
-    return (uint32_t)((int)(key >> 24) * Gb + (((i >> 2) * nb + (j >> 2)) * nb + (k >> 2)) * 64 + (((i & 3) << 4) | ((j & 3) << 2) | (k & 3)));
-}
+// Node (bx + a, by + b, bz + c) of the run whose first slot carries `key` = the block-major index of the run's base cell (its low six
+// bits are the base's position inside its 4x4x4 block).  Stepping `a` nodes along x adds a * 16, plus (block stride - 64) when the step
+// leaves the block, i.e. when (bx & 3) + a > 3: for a = 1 that is (key & 0x30) == 0x30, for a = 2 it is key & 0x20; likewise y, z.
+// The owning lane keeps its three masks and the in-block offset: one AND + compare + predicated add per axis at a run end.
+struct RunNode {
+    uint32_t d0, mx, my, mz, wx, wy;
+    __device__ __forceinline__ RunNode(int a, int b, int c, int nb) {
+        d0 = (uint32_t)(a * 16 + b * 4 + c);
+        mx = a == 0 ? 0xffffffffu : (a == 1 ? 0x30u : 0x20u);       // all ones never matches a live key
+        my = b == 0 ? 0xffffffffu : (b == 1 ? 0x0cu : 0x08u);
+        mz = c == 0 ? 0xffffffffu : (c == 1 ? 0x03u : 0x02u);
+        wx = (uint32_t)(nb * nb * 64 - 64); wy = (uint32_t)(nb * 64 - 16);
+    }
+    __device__ __forceinline__ uint32_t operator()(uint32_t key) const {
+        uint32_t n = key + d0;
+        if ((key & mx) == mx) n += wx;
+        if ((key & my) == my) n += wy;
+        if ((key & mz) == mz) n += 60u;
+        return n;
+    }
+};
 // The walk is unrolled over the 32 slots in batches of 8: the eight 128-bit loads of a batch are in flight together and the additions
 // alternate between two accumulators (two dependent chains instead of one).  A batch without a run end (one warp-uniform test of
 // the ballot) is eight plain additions; otherwise the run ends are tested slot by slot against immediate bits, and after the last
@@ -163,7 +180,7 @@ __device__ __forceinline__ void warp_stage_flush(WarpStage& st, uint32_t key, bo
     flush_prologue(st.key, key, live, ends, alive);
     const unsigned lane = threadIdx.x & 31;
     if (lane >= 27 || (dbg & 2)) return;
-    const int a = lane / 9, b = (lane / 3) % 3, c = lane % 3;
+    const RunNode rn(lane / 9, (lane / 3) % 3, lane % 3, nb);
     const float4* src = st.val + lane;
     const int nl = __popc(alive);
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -187,7 +204,7 @@ __device__ __forceinline__ void warp_stage_flush(WarpStage& st, uint32_t key, bo
             if (e8 & (1u << i)) {                               // last slot of its run
                 if ((l8 & (1u << i)) && !(dbg & 1)) {
                     add_f4(acc0, acc1);
-                    atomicAdd(grid + run_node(st.key[p0], a, b, c, nb, Gb), acc0);
+                    atomicAdd(grid + rn(st.key[p0]), acc0);
                 }
                 acc0 = zero; acc1 = zero;
                 p0 = base + i + 1;
@@ -208,7 +225,7 @@ __device__ __forceinline__ void warp_stage_flush3(WarpStage3& st, uint32_t key, 
     flush_prologue(st.key, key, live, ends, alive);
     const unsigned lane = threadIdx.x & 31;
     if (lane >= 27 || (dbg & 2)) return;
-    const int a = lane / 9, b = (lane / 3) % 3, c = lane % 3;
+    const RunNode rn(lane / 9, (lane / 3) % 3, lane % 3, nb);
     const float2* sxy = st.xy + lane;
     const float* sz = st.z + lane;
     const int nl = __popc(alive);
@@ -233,7 +250,7 @@ __device__ __forceinline__ void warp_stage_flush3(WarpStage3& st, uint32_t key, 
             if (e8 & (1u << i)) {                               // last slot of its run
                 if ((l8 & (1u << i)) && !(dbg & 1)) {
                     acc0 = __fadd2_rn(acc0, acc1);
-                    atomicAdd(grid + run_node(st.key[p0], a, b, c, nb, Gb), make_float4(acc0.x, acc0.y, az0 + az1, 0.f));
+                    atomicAdd(grid + rn(st.key[p0]), make_float4(acc0.x, acc0.y, az0 + az1, 0.f));
                 }
                 acc0 = make_float2(0.f, 0.f); acc1 = acc0; az0 = 0.f; az1 = 0.f;
                 p0 = base + i + 1;
@@ -249,6 +266,7 @@ struct Stencil {
     float fx, fy, fz;
     float wx[3], wy[3], wz[3];
 };
+__device__ __forceinline__ uint32_t base_node(const Stencil& s) { return s.ox[0] + s.oy[0] + s.oz[0]; }
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 __device__ __forceinline__ uint32_t node_index(int i, int j, int k, int nb) {
     return (uint32_t)((((i >> 2) * nb + (j >> 2)) * nb + (k >> 2)) * 64 + (((i & 3) << 4) | ((j & 3) << 2) | (k & 3)));
@@ -562,7 +580,7 @@ __global__ void __launch_bounds__(SMX_TPB_SC, SMX_SC_MINB) k_p2g(Params P, PrimS
             }
         }
     }
-    if (STAGED) warp_stage_flush(stage[threadIdx.x >> 5], pack_base(s.bx, s.by, s.bz, bt), live, g_in, P.nb, P.Gb, P.dbg);
+    if (STAGED) warp_stage_flush(stage[threadIdx.x >> 5], base_node(s), live, g_in, P.nb, P.Gb, P.dbg);
 }
 
 // boundary_condition (mpm_simulator.py:268-281); mask bit d cleared where component d was zeroed
@@ -832,9 +850,9 @@ __global__ void __launch_bounds__(SMX_TPB_G2PG, SMX_G2PG_MINB) k_g2p_grad(Params
         st_plane(aout, P.stride, j, 0, make_float4(gxp.x, gxp.y, gxp.z, 0.f));
     }
 #ifdef SMX_G2PG_F4
-    if (STAGED) warp_stage_flush(stage[threadIdx.x >> 5], pack_base(s.bx, s.by, s.bz, bt), live, gg_out, P.nb, P.Gb, P.dbg);
+    if (STAGED) warp_stage_flush(stage[threadIdx.x >> 5], base_node(s), live, gg_out, P.nb, P.Gb, P.dbg);
 #else
-    if (STAGED) warp_stage_flush3(stage[threadIdx.x >> 5], pack_base(s.bx, s.by, s.bz, bt), live, gg_out, P.nb, P.Gb, P.dbg);
+    if (STAGED) warp_stage_flush3(stage[threadIdx.x >> 5], base_node(s), live, gg_out, P.nb, P.Gb, P.dbg);
 #endif
 }
 
@@ -1328,7 +1346,7 @@ __global__ void __launch_bounds__(SMX_TPB, SMX_FUSEB_MINB) k_p2g_grad_g2p_grad(P
         V3 gxp = g2p_grad_particle<true, false>(P, s, gx, gv + P.dt * gx, gC, g_prev, gg_prev, nullptr, stage[w].xy + l * 27, stage[w].z + l * 27);
         st_plane(ain, P.stride, j, 0, make_float4(gxp.x, gxp.y, gxp.z, 0.f));
     }
-    warp_stage_flush3(stage[threadIdx.x >> 5], pack_base(s.bx, s.by, s.bz, bt), live, gg_prev, P.nb, P.Gb, P.dbg);
+    warp_stage_flush3(stage[threadIdx.x >> 5], base_node(s), live, gg_prev, P.nb, P.Gb, P.dbg);
 }
 
 #ifndef SMX_P2GG_TPB
@@ -1564,9 +1582,24 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+// both sides of a slab in ONE launch (blockIdx.y = side; a side without a neighbour has n == 0)
+struct HaloSides {
+    size_t node0[2];            // first node of the 2-column halo range of the side
+    float4* rx[2];              // push: the NEIGHBOUR's receive slot;  add: the own receive slot
+    uint32_t* stamp[2];         // block stamps of that slot
+    unsigned* flag[2];          // push: the neighbour's flag;  wait: the own flag
+    unsigned seq1[2];
+    unsigned* done[2];          // push: own completion counter of the side
+    int on[2];
+};
 template <int MODE>
-__global__ void __launch_bounds__(256) k_halo_push(const float4* __restrict__ A, const float4* __restrict__ B, size_t node0, int H, float4* __restrict__ peer_rx,
-                                                   uint32_t* __restrict__ peer_stamp, unsigned* __restrict__ peer_flag, unsigned seq1, unsigned* __restrict__ done) {
+__global__ void __launch_bounds__(256) k_halo_push(const float4* __restrict__ A, const float4* __restrict__ B, int H, HaloSides hs) {
+    const int side = blockIdx.y;
+    if (!hs.on[side]) return;
+    const size_t node0 = hs.node0[side];
+    float4* __restrict__ peer_rx = hs.rx[side];
+    uint32_t* __restrict__ peer_stamp = hs.stamp[side];
+    const unsigned seq1 = hs.seq1[side];
     const int lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     for (int hb = warp; hb < H; hb += nwarps) {
         const size_t base = node0 + (size_t)hb * 64;
@@ -1584,25 +1617,34 @@ __global__ void __launch_bounds__(256) k_halo_push(const float4* __restrict__ A,
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
-        if (atomicAdd(done, 1u) == gridDim.x - 1) {     // last CTA: everything every CTA wrote is fenced
-            *done = 0u;
+        if (atomicAdd(hs.done[side], 1u) == gridDim.x - 1) {    // last CTA of the side: everything every CTA wrote is fenced
+            *hs.done[side] = 0u;
             __threadfence_system();
-            st_release_sys(peer_flag, seq1);
+            st_release_sys(hs.flag[side], seq1);
         }
     }
 }
-// counters[3] counts exchanges that gave up waiting (neighbour gone): the run is invalid then, but the GPU is not left spinning
-__global__ void k_halo_wait(const unsigned* __restrict__ flag, unsigned seq1, unsigned long long* __restrict__ counters, long long timeout_ns) {
+// counters[3] counts exchanges that gave up waiting (neighbour gone): the run is invalid then, but the GPU is not left spinning.
+// One thread per side.
+__global__ void k_halo_wait(HaloSides hs, unsigned long long* __restrict__ counters, long long timeout_ns) {
+    const int side = threadIdx.x;
+    if (side > 1 || !hs.on[side]) return;
     long long t0;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    while ((int)(ld_acquire_sys(flag) - seq1) < 0) {
+    while ((int)(ld_acquire_sys(hs.flag[side]) - hs.seq1[side]) < 0) {
         __nanosleep(200);
         long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         if (t - t0 > timeout_ns) { atomicAdd(counters + 3, 1ull); break; }
     }
 }
-__global__ void __launch_bounds__(256) k_halo_add(float4* __restrict__ A, size_t node0, int H, const float4* __restrict__ rx, const uint32_t* __restrict__ stamp, unsigned seq1) {
+__global__ void __launch_bounds__(256) k_halo_add(float4* __restrict__ A, int H, HaloSides hs) {
+    const int side = blockIdx.y;
+    if (!hs.on[side]) return;
+    const size_t node0 = hs.node0[side];
+    const float4* __restrict__ rx = hs.rx[side];
+    const uint32_t* __restrict__ stamp = hs.stamp[side];
+    const unsigned seq1 = hs.seq1[side];
     const int lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     for (int hb = warp; hb < H; hb += nwarps) {
         if (__ldcg(stamp + hb) != seq1) continue;
