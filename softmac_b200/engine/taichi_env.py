@@ -110,3 +110,36 @@ class TaichiEnv:
             else:
                 f = self.simulator.cur
         return self.loss.compute_loss(f, **kwargs)
+
+
+def adjust_action_with_ext_force(env, actions):
+    """``softmac/utils.py:76-113``: actions found WITHOUT external forces are corrected so that they also cancel what the bodies feel --
+    a forward rollout in which, after the substeps of env step t, the averaged contact wrench ``ext_f / substeps`` of every primitive with
+    ``enable_external_force`` plus the body's weight is subtracted from action t (layout per body: torque(3), force(3)) before the rigid
+    step.  demo_pour starts from ``get_init_actions(choice=0, adjust=True)`` (demo_pour.py:95-110): zeros, adjusted -- the glass is held
+    still against gravity and the liquid while it settles.  Leaves the env at the end of the rollout, like the reference; returns the
+    adjusted (T, action_dim) array."""
+    assert env.control_mode == "rigid" and not env._is_copy
+    rigid, sim = env.rigid_simulator, env.simulator
+    actions = np.array(actions, dtype=np.float64, copy=True)
+    gravity = np.asarray(rigid.gravity, dtype=np.float64)
+    for t in range(actions.shape[0]):
+        start = sim.cur
+        sim.cur = start + env.substeps
+        if hasattr(sim, "step"):
+            sim.step(start, env.substeps)
+        else:
+            for s in range(start, sim.cur):
+                sim.substep(s)
+        for i in range(rigid.n_primitive):
+            if not env.primitives[i].enable_external_force:
+                continue
+            ext_f = np.asarray(env.primitives[i].ext_f.to_numpy(), dtype=np.float32).astype(np.float64) / env.substeps      # FloatTensor in the reference
+            force = ext_f[:3] + rigid.bodies[i].mass * gravity
+            o = rigid.offsets[i]
+            assert rigid.bodies[i].ndof == 6, "adjust_action_with_ext_force: bodies on free joints (6 action components per body)"
+            actions[t, o:o + 3] -= ext_f[3:]
+            actions[t, o + 3:o + 6] -= force
+        rigid.step(start // env.substeps, actions[t])
+        env.action_list.append(actions[t])
+    return actions

@@ -120,6 +120,26 @@ def test_episode_action_gradient_cosine():
     assert rel_l2(gg, go) <= 2e-2
 
 
+def test_adjust_action_with_ext_force_holds_the_glass_still():
+    """demo_pour's initial actions: get_init_actions(choice=0, adjust=True) (demo_pour.py:95-110, softmac/utils.py:76-113) -- zeros corrected
+    by the measured contact wrench and the body's weight.  With body gravity ON the adjusted actions must keep the free-floating glass where
+    it is while the liquid lands on it; unadjusted zeros let it fall."""
+    from softmac_b200.engine.taichi_env import adjust_action_with_ext_force
+    env = build_pour("oracle", n=800, env_steps=12, body_gravity=True)
+    env.reset()
+    zeros = np.zeros((12, 12))
+    adj = adjust_action_with_ext_force(env, zeros)
+    held = env.rigid_simulator.states[-1].copy()
+    assert adj.shape == (12, 12) and np.abs(adj[:, 6:]).max() == 0              # the bowl ignores external forces: untouched
+    assert adj[:, 4].min() > 0.9 * 2.2687 * 9.8                                   # the glass' weight is carried by the action
+    assert np.abs(adj[:, :6] - np.array([0, 0, 0, 0, 2.2687 * 9.8, 0])).max() > 1e-6     # plus the (small) liquid wrench
+    assert np.abs(held[:6]).max() < 1e-6 and np.abs(held[12:18]).max() < 1e-4   # pose and twist of the glass stay at their initial values
+    env.reset()
+    for a in zeros:
+        env.step(a)
+    assert env.rigid_simulator.states[-1][4] < -1e-5                            # unadjusted: the glass falls (g t^2 / 2 = 2.8e-5 m)
+
+
 @pytest.mark.gpu
 def test_long_grip_like_episode_200_env_steps():
     """200 env steps x 5 substeps = 1000 substeps (half a demo_grip episode, demo_grip.py:190-191) of a grip-like squeeze: fingers start
@@ -141,7 +161,7 @@ def test_long_grip_like_episode_200_env_steps():
     print(f"1000-substep episode: loss rel err {abs(lg - lo) / abs(lo):.2e}, x rel-L2 {rel_l2(sg[:, :3], so[:, :3]):.2e}, action-gradient cosine {c:.9f}, rel-L2 {rel_l2(gg, go):.2e}")
 
 
-def build_pour(backend, n=3000, env_steps=10):
+def build_pour(backend, n=3000, env_steps=10, body_gravity=False):
     """demo_pour-shaped coupling (softmac/config/demo_pour_config.py:8-29,57-67): liquid (ptype 2, co-rotated), env_dt == dt so
     substeps = 1 (life = 1, rigid coupling after EVERY substep), a free-floating "glass" that feels the contact wrench and a
     "bowl" with enable_external_force = False (its wrench is ignored, rigid_simulator.py:96), 6-dof force/torque actions."""
@@ -172,9 +192,9 @@ def build_pour(backend, n=3000, env_steps=10):
         sim = MPMSimulator(cfg, prims, env_dt=dt)
         assert sim.substeps == 1
         prims.initialize()
-    bodies = [dict(joint="free", origin=tuple(c), mass=2.2687, inertia=0.02, gravity=False),
+    bodies = [dict(joint="free", origin=tuple(c), mass=2.2687, inertia=0.02, gravity=body_gravity),
               dict(joint="free", origin=tuple(c + [0.0, -0.2, 0.0]), mass=4.0084, inertia=0.05, gravity=False)]
-    rcfg = CfgNode(gravity=(0., 0., 0.), init_state=(), bodies=bodies)
+    rcfg = CfgNode(gravity=(0., -9.8, 0.) if body_gravity else (0., 0., 0.), init_state=(), bodies=bodies)
     rigid = RigidSimulator(rcfg, prims, substeps=substeps, env_dt=dt)
     env = TaichiEnv(sim, prims, rigid, x, loss=PointwiseLoss(sim, x + np.array([0.0, -0.01, 0.0])), control_mode="rigid")
     return env
