@@ -249,6 +249,14 @@ int smx_step(smx_sim* sim, int32_t s0, int32_t count);
 /* adjoint of substeps s1-1, s1-2, ..., s1-count (TaichiEnv.step_grad inner loop, taichi_env.py:128-131) */
 int smx_step_grad(smx_sim* sim, int32_t s1, int32_t count);
 
+/* smx_step / smx_step_grad replayed as ONE CUDA-graph launch (for scenes of ~10 k particles, where an env step is bound by the latency of its
+ * dependent launches): the call's launch sequence is captured, the handle's executable graph is updated in place with it (same topology,
+ * new frame pointers) and launched.  Calls that would allocate, synchronise or re-sort inside take the ordinary path; results are identical.
+ * smx_graph_status: out[0] calls replayed as a graph, out[1] calls on the ordinary path, out[2] re-instantiations. */
+int smx_step_graph(smx_sim* sim, int32_t s0, int32_t count);
+int smx_step_grad_graph(smx_sim* sim, int32_t s1, int32_t count);
+int smx_graph_status(smx_sim* sim, int64_t out[3]);
+
 /* fp32 host entry points (the optimiser's float32 tensors never pass through a host-side f64 conversion): same semantics as the f64
  * calls they mirror -- MPMSimulator.reset / get_state / get_grad (mpm_simulator.py:448-574) and the loss seeds -- with float rows that
  * travel as they are.  smx_host_register pins a caller buffer once (cudaHostRegister) so that these copies are plain DMA. */

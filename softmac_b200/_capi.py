@@ -125,6 +125,9 @@ _SIGS = {
     "smx_stream": [vp, C.POINTER(vp)],
     "smx_step": [vp, C.c_int32, C.c_int32],
     "smx_step_grad": [vp, C.c_int32, C.c_int32],
+    "smx_step_graph": [vp, C.c_int32, C.c_int32],
+    "smx_step_grad_graph": [vp, C.c_int32, C.c_int32],
+    "smx_graph_status": [vp, C.POINTER(C.c_int64)],
     "smx_add_state_grad": [vp, C.c_int32, dp],
     "smx_add_x_grad": [vp, C.c_int32, dp],
     "smx_set_chamfer_target": [vp, dp, C.c_int32],

@@ -117,6 +117,10 @@ struct smx_sim {
     // adjoint grid of substep f: double-buffered by parity so that k_grid_grad(f) can already clear the one of substep f-1
     // halo exchange over peer memory (smx_slab_halo_*): receive slots + stamps + flags of both sides live in ONE allocation (`halo_mem`,
     // IPC-exportable) that the x-neighbours write into; peer_base[side] is the neighbour's allocation as mapped here
+    // CUDA-graph replay of smx_step / smx_step_grad for launch-latency-bound scenes (smx_step_graph): one executable graph per direction,
+    // re-targeted to the frames of every call by a whole-graph update of the freshly captured launch sequence
+    std::map<size_t, cudaGraphExec_t> gexec[2];     // per direction, keyed by the node count of the captured sequence (its few recurring shapes)
+    long long graph_launches = 0, graph_fallbacks = 0, graph_reinstantiations = 0;
     int slab_checked = -1;              // last frame whose positions went through k_check_slab
     unsigned char* halo_mem = nullptr; size_t halo_bytes = 0;
     unsigned char* peer_base[2] = {nullptr, nullptr}; bool peer_ipc[2] = {false, false};
@@ -611,6 +615,43 @@ static int apply_seed(smx_sim* s, int f, float* adj, int order_id) {
     return SMX_OK;
 }
 
+// ---- CUDA-graph replay helpers (smx_step_graph below) ----------------------------------------------------------------------------
+static bool graph_ok_common(smx_sim* s) {
+    return s->P.n > 0 && !s->slab && !s->prof && !s->ckpt_dirty && !s->cfg.rigid_velocity_control && s->cfg.n_control == 0 &&
+           !(s->cfg.flags & (SMX_FLAG_NO_SORT | SMX_FLAG_DENSE_GRID | SMX_FLAG_NO_GRID_CKPT)) && (!s->has_contact() || s->near_pool) && s->ckpt;
+}
+template <typename Body>
+static int graph_run(smx_sim* s, int dir, Body&& body) {
+    CK(cudaSetDevice(s->cfg.device));
+    CK(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = body();
+    cudaGraph_t g = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(s->stream, &g);
+    if (rc != SMX_OK || e != cudaSuccess || !g) {
+        if (g) cudaGraphDestroy(g);
+        cudaGetLastError();
+        if (rc != SMX_OK) return rc;
+        return fail(SMX_ERR_CUDA, "smx_step_graph: stream capture failed: %s", cudaGetErrorString(e));
+    }
+    size_t nodes = 0;
+    cudaGraphGetNodes(g, nullptr, &nodes);
+    cudaGraphExec_t& ex = s->gexec[dir][nodes];
+    if (ex) {
+        cudaGraphExecUpdateResultInfo info;
+        if (cudaGraphExecUpdate(ex, g, &info) != cudaSuccess) { cudaGetLastError(); cudaGraphExecDestroy(ex); ex = nullptr; s->graph_reinstantiations++; }
+    }
+    if (!ex && cudaGraphInstantiate(&ex, g, 0) != cudaSuccess) {
+        const cudaError_t e2 = cudaGetLastError();
+        cudaGraphDestroy(g); ex = nullptr;
+        return fail(SMX_ERR_CUDA, "smx_step_graph: cudaGraphInstantiate failed: %s", cudaGetErrorString(e2));
+    }
+    const cudaError_t e3 = cudaGraphLaunch(ex, s->stream);
+    cudaGraphDestroy(g);
+    if (e3 != cudaSuccess) return fail(SMX_ERR_CUDA, "smx_step_graph: cudaGraphLaunch failed: %s", cudaGetErrorString(e3));
+    s->graph_launches++;
+    return SMX_OK;
+}
+
 // =================================================================================================
 extern "C" {
 
@@ -730,6 +771,7 @@ int smx_destroy(smx_sim* s) {
     for (auto& kv : s->seed_pool) cudaFree(kv.second);
     for (auto& p : s->prims) { cudaFree(p.sdf_dev); cudaFree(p.nrm_dev); }
     for (int side = 0; side < 2; side++) if (s->peer_base[side] && s->peer_ipc[side]) cudaIpcCloseMemHandle(s->peer_base[side]);
+    for (int d = 0; d < 2; d++) for (auto& kv : s->gexec[d]) if (kv.second) cudaGraphExecDestroy(kv.second);
     void* ptrs[] = {s->halo_mem, s->halo_done, s->near_pool, s->svd_pool, s->ch_target, s->ch_loss, s->cd_buf, s->ckpt, s->pool, s->g_in, s->g_out, s->g_mix, s->gg_out, s->gg_out_b, s->gg_mix, s->g_lin, s->adj_cur, s->adj_nxt, s->stage_dev, s->keys_a, s->keys_b, s->iota, s->cub_tmp,
                     s->counters, s->prims_dev, s->pstate, s->pgrad, s->ext_f, s->ext_f_grad, s->abuf, s->gabuf, s->ctrl_id, s->action, s->action_grad,
                     s->rig_arena, s->rig_enable, s->rig_masks, s->ckpt_need};
@@ -1799,6 +1841,44 @@ int smx_step_grad(smx_sim* s, int32_t s1, int32_t count) {
         if (rc != SMX_OK) { s->adj_frame = -1; s->adj_partial = false; s->grad_pending = -1; return rc; }
         g2p_done = fuse;
     }
+    return SMX_OK;
+}
+
+// ---- CUDA-graph replay for small scenes ------------------------------------------------------------------------------------------
+// At ~10 k particles every kernel of a substep is a single partial wave and an env step is bound by the latency of ~16 dependent launches.
+// smx_step_graph / smx_step_grad_graph capture the launch sequence of the call into a graph (stream capture: the host code below runs
+// as always, its launches are recorded instead of submitted), update the handle's executable graph with it -- same topology from call to
+// call, only the frame-dependent kernel arguments change, so cudaGraphExecUpdate patches the nodes in place -- and launch that ONE graph.
+// Calls that would allocate, synchronise or re-sort inside (the first substeps after a reset, a re-sort falling into the call, the
+// first adjoint call of a pass, slab ranks, profiling) go down the ordinary path: results are identical either way.
+int smx_step_graph(smx_sim* s, int32_t s0, int32_t count) {
+    if (!s) return fail(SMX_ERR_ARG, "smx_step_graph: null simulator");
+    bool ok = graph_ok_common(s) && count >= 1 && s0 >= 0 && s0 + count + 1 < s->cfg.max_steps && s->order_of[s0] >= 0;
+    // no re-sort may fall into the call (it recycles orderings and sizes CUB's workspace): the substeps stay in the ordering of frame s0
+    ok = ok && s->cfg.sort_every > 0 && s->age_of[s0] + count < s->cfg.sort_every;
+    if (ok && s->g_in_clean_uid != s->orders[s->order_of[s0]].uid) ok = true;   // the clear launch is captured like any other
+    if (!ok) { s->graph_fallbacks++; return smx_step(s, s0, count); }
+    return graph_run(s, 0, [&]() { return smx_step(s, s0, count); });
+}
+int smx_step_grad_graph(smx_sim* s, int32_t s1, int32_t count) {
+    if (!s) return fail(SMX_ERR_ARG, "smx_step_grad_graph: null simulator");
+    bool ok = graph_ok_common(s) && count >= 1 && s1 - count >= 0 && s1 < s->cfg.max_steps;
+    // not the first call of a backward pass (it looks at the checkpoint counters on the host), one ordering throughout, every grid record there
+    ok = ok && s->adj_frame == s1 && s->order_of[s1] >= 0 && s->adj_order == s->order_of[s1] && s->trans_from[s1] < 0;
+    if (ok) {
+        const int o = s->order_of[s1];
+        const int uid = s->orders[o].uid;
+        const bool contact = s->has_contact();
+        for (int f = s1 - 1; f >= s1 - count && ok; f--)
+            ok = s->order_of[f] == o && s->trans_from[f + 1] < 0 && s->ckpt_order[f] == uid && (bool)s->ckpt_contact[f] == contact;
+    }
+    if (!ok) { s->graph_fallbacks++; return smx_step_grad(s, s1, count); }
+    return graph_run(s, 1, [&]() { return smx_step_grad(s, s1, count); });
+}
+// out[0] calls replayed as one graph launch, out[1] calls that took the ordinary path, out[2] re-instantiations (topology changed)
+int smx_graph_status(smx_sim* s, int64_t out[3]) {
+    if (!s || !out) return fail(SMX_ERR_ARG, "smx_graph_status: null argument");
+    out[0] = s->graph_launches; out[1] = s->graph_fallbacks; out[2] = s->graph_reinstantiations;
     return SMX_OK;
 }
 

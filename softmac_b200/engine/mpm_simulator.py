@@ -90,6 +90,7 @@ class MPMSimulator:
         self.n_control = cfg.n_controllers
         self.collision_type = cfg.collision_type
         self.cur = 0
+        self.use_graphs = False         # step / step_grad as one CUDA-graph launch per call (small, launch-latency-bound scenes)
 
         c = SmxConfig()
         c.n_particles, c.n_grid, c.max_steps = self.n_particles, self.n_grid, self.max_steps
@@ -166,12 +167,24 @@ class MPMSimulator:
         check(lib().smx_get_action_grad(self._h, d_ptr(g)))
         return g
 
-    def step(self, s0, count):
-        """`count` substeps in one native call (the inner loop of TaichiEnv.step, taichi_env.py:101-102)."""
-        check(lib().smx_step(self._h, int(s0), int(count)))
+    def step(self, s0, count, graph=None):
+        """`count` substeps in one native call (the inner loop of TaichiEnv.step, taichi_env.py:101-102).  graph: replay the call as ONE
+        CUDA-graph launch (smx_step_graph; default: the simulator's `use_graphs` attribute) -- for launch-latency-bound small scenes."""
+        if self.use_graphs if graph is None else graph:
+            check(lib().smx_step_graph(self._h, int(s0), int(count)))
+        else:
+            check(lib().smx_step(self._h, int(s0), int(count)))
 
-    def step_grad(self, s1, count):
-        check(lib().smx_step_grad(self._h, int(s1), int(count)))
+    def step_grad(self, s1, count, graph=None):
+        if self.use_graphs if graph is None else graph:
+            check(lib().smx_step_grad_graph(self._h, int(s1), int(count)))
+        else:
+            check(lib().smx_step_grad(self._h, int(s1), int(count)))
+
+    def graph_status(self):
+        out = (C.c_int64 * 3)()
+        check(lib().smx_graph_status(self._h, out))
+        return dict(graph_calls=int(out[0]), plain_calls=int(out[1]), reinstantiations=int(out[2]))
 
     # -- IO (mpm_simulator.py:448-574) ----------------------------------------------------------------------
     def get_state(self, f, dtype=np.float64, out=None):

@@ -252,3 +252,51 @@ def test_device_chamfer_loss_matches_host_restatement():
         ref_g.append(s1.get_state_grad(0)[:, :3])
     assert abs(lb - ref_l) <= 1e-5 * abs(ref_l)
     assert rel_l2(gb[0], ref_g[0]) <= 1e-5 and rel_l2(gb[1], ref_g[1]) <= 1e-5
+
+
+def test_cuda_graph_replay_of_env_steps_is_identical():
+    """smx_step_graph / smx_step_grad_graph (every env step's substeps captured, patched into the handle's executable graph and launched
+    as ONE graph) == the ordinary launch sequence: same states and action gradients over an episode with re-sorts, forecast contact and the
+    device-resident rigid coupling; the calls that must take the ordinary path (first after reset, re-sort inside, first of the backward
+    pass) do so, the others are graph launches."""
+    from softmac_b200.engine import MPMSimulator, Primitives, Mesh
+    from softmac_b200.engine.batched_env import BatchedTaichiEnv
+    from softmac_b200.engine.rigid_simulator import RigidSimulator
+    from softmac_b200.config import CfgNode
+    n, B, env_steps, substeps = 2000, 2, 12, 5
+    n_grid, dt = 32, 2e-4
+    max_steps = env_steps * substeps + substeps + 2
+    rng = np.random.default_rng(8)
+    x = ((rng.random((n, 3)) * 2 - 1) * 0.05 + np.array([0.5, 0.3, 0.5])).astype(np.float32).astype(np.float64)
+    tab = scenes.sphere_table(radius=0.06, dx=0.01, margin=0.04)
+    bodies = [dict(joint="prismatic", axis=(1, 0, 0), origin=(0.5 - 0.115, 0.3, 0.5), mass=1.0, gravity=False),
+              dict(joint="prismatic", axis=(1, 0, 0), origin=(0.5 + 0.115, 0.3, 0.5), mass=1.5, gravity=False)]
+    rcfg = CfgNode(gravity=(0., 0., 0.), init_state=(0., 0., 0.3, -0.3), bodies=bodies)
+    actions = np.stack([np.tile([20.0, -20.0], (env_steps, 1)), np.tile([5.0, -30.0], (env_steps, 1))])
+    target = x + np.array([0.0, 0.01, 0.0])
+
+    def run(graphs):
+        ms = [Mesh(sdf=dict(sdf=tab["sdf"], normal=tab["normal"], position=(tab["lower"], tab["upper"]), dx=tab["dx"]), cfg=dict(friction=0.3), max_timesteps=max_steps)
+              for _ in bodies]
+        prims = Primitives(primitives=ms, max_timesteps=max_steps)
+        sim = MPMSimulator(sim_cfg(n, n_grid=n_grid, max_steps=max_steps, dt=dt), prims, env_dt=dt * substeps, n_batch=B, sort_every=15)
+        sim.use_graphs = graphs
+        env = BatchedTaichiEnv(sim, prims, lambda b, views: RigidSimulator(rcfg, views, substeps=substeps, env_dt=dt * substeps), x, device_rigid=True)
+        for it in range(2):
+            env.reset()
+            sim.clear_all_gradients()
+            for k in range(env_steps):
+                env.step(actions[:, k])
+            f_end = env_steps * substeps
+            xs = sim.get_x(f_end).reshape(B, n, 3)
+            sim.add_x_grad(f_end, (xs - target).reshape(B * n, 3))
+            g = env.backward()
+        return xs, g, env.rigid_states(), sim.graph_status(), sim.counters()
+
+    xp, gp, rp, sp, cp = run(False)
+    xg, gg, rg, sg, cg = run(True)
+    assert sp["graph_calls"] == 0 and cp["resorts"] >= 3
+    assert sg["graph_calls"] >= env_steps and sg["plain_calls"] >= 4, sg         # both episodes, forward and backward
+    assert np.abs(gp).max() > 0
+    assert rel_l2(xg, xp) <= 1e-6 and rel_l2(rg, rp) <= 1e-7
+    assert rel_l2(gg, gp) <= 1e-4, (gg, gp)

@@ -140,12 +140,32 @@ def actions_for(config, env_steps, strength=1.0):
 
 def rigid_bodies(sc):
     from softmac_b200.engine.rigid_simulator import bodies_from_urdf
-    bodies = []
+    bodies, feels = [], []
     for c in sc["prims"]:
-        bodies += bodies_from_urdf(c["urdf_path"])
+        bs = bodies_from_urdf(c["urdf_path"])
+        bodies += bs
+        feels += [bool(c["enable_external_force"])] * len(bs)
     for b, I in zip(bodies, sc.get("inertia", [])):
         b["inertia"] = I
+    if sc.get("body_gravity"):
+        # config 2 as the reference runs it: the glass feels its weight and the adjusted actions carry it.  The bowl (enable_external_force
+        # False, never adjusted) rests on Jade's floor there; the stand-in has no rigid-rigid contact, so its weight stays switched off
+        for b, f in zip(bodies, feels):
+            b["gravity"] = f
     return bodies
+
+
+def rigid_gravity(sc):
+    return (0., -9.8, 0.) if sc.get("body_gravity") else (0., 0., 0.)
+
+
+def adjusted_pour_actions(sc, env_steps, cache_dir):
+    """demo_pour's initial actions, get_init_actions(choice=0, adjust=True) (demo_pour.py:95-110, softmac/utils.py:76-113): zeros, adjusted
+    in one forward rollout of the drop-in env so that they cancel the bodies' weight and the liquid's wrench."""
+    from softmac_b200.engine.taichi_env import adjust_action_with_ext_force
+    env, sim, prims, clock, L = build_cuda(sc, env_steps, cache_dir=cache_dir, mode="dropin")
+    env.reset()
+    return adjust_action_with_ext_force(env, np.zeros((env_steps, 12)))
 
 
 def build_cuda(sc, env_steps, batch=1, cache_dir=None, mode="dropin", loss="device", sort_every=None, device=0):
@@ -165,7 +185,7 @@ def build_cuda(sc, env_steps, batch=1, cache_dir=None, mode="dropin", loss="devi
     sim = MPMSimulator(cfg, prims, env_dt=sc["env_dt"], n_batch=batch, sort_every=sort_every, device=device)
     assert sim.substeps == S, (sim.substeps, S)
     sim.primitives_contact = sc["contact"]
-    rcfg = CfgNode(gravity=(0., 0., 0.), init_state=sc["rigid_init"], bodies=rigid_bodies(sc))
+    rcfg = CfgNode(gravity=rigid_gravity(sc), init_state=sc["rigid_init"], bodies=rigid_bodies(sc))
     clock = StandinClock()
 
     def make_rigid(b, views):
@@ -205,7 +225,7 @@ def build_oracle(sc, env_steps, tables):
     for i, p in enumerate(sim.primitives):
         p.enable_external_force = enable[i]
         sim.sim.set_primitive_enabled(i, bool(sc["contact"][i]))
-    rcfg = CfgNode(gravity=(0., 0., 0.), init_state=sc["rigid_init"], bodies=rigid_bodies(sc))
+    rcfg = CfgNode(gravity=rigid_gravity(sc), init_state=sc["rigid_init"], bodies=rigid_bodies(sc))
     clock = StandinClock()
     rigid = RigidSimulator(rcfg, sim.primitives, substeps=S, env_dt=sc["env_dt"])
     clock.attach(rigid)
@@ -324,30 +344,39 @@ def main():
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--parity-env-steps", type=int, default=None, help="0: skip the oracle leg")
     ap.add_argument("--parity-strength", type=float, default=None, help="action multiplier of the parity leg")
-    ap.add_argument("--arms", default=None, help="comma list of dropin, batched, device (default: all that apply)")
+    ap.add_argument("--arms", default=None, help="comma list of dropin, batched, device, device_graph (default: all)")
     ap.add_argument("--sort-every", type=int, default=None)
     ap.add_argument("--rollouts", type=int, default=0, help="BASELINE config 4: this many rollouts with perturbed action sequences "
                     "0.3 [1, -1] (1 + 0.1 xi_k), sharded over the ranks of a torchrun launch (one handle per GPU, device-resident rigid "
                     "coupling), action gradients all-reduced (mean) at the end of the episode")
+    ap.add_argument("--pour-actions", choices=("schedule", "adjusted"), default="schedule", help="config 2: the lift-and-tilt schedule of demo_pour.py:100-105 "
+                    "with body gravity off (default), or the demo's own initial actions get_init_actions(choice=0, adjust=True): zeros adjusted against "
+                    "the bodies' weight and the liquid's wrench, body gravity ON (softmac/utils.py:76-113)")
     ap.add_argument("--cache-dir", default=os.path.join(ROOT, "gpurun_out", "sdf_cache"))
     ap.add_argument("--max-per-handle", type=int, default=16, help="with --rollouts: rollouts batched in one handle (a rank runs its share in waves)")
     args = ap.parse_args()
     sc = scene(args.config)
     S, n = sc["substeps"], sc["n"]
     K = args.env_steps or (400 if args.config == "grip" else 3000)
+    adjusted = args.config == "pour" and args.pour_actions == "adjusted"
+    if adjusted:
+        sc["body_gravity"] = True
     if args.rollouts:
         return sharded_rollouts(args, sc, K)
     loss_frames = list(range(min(sc["loss_start"], (K * S * 3) // 4), K * S + 1, 20))
     out = {"workload": f"demo_{args.config} episode (BASELINE config {1 if args.config == 'grip' else 2})", "n_particles": n, "n_grid": sc["n_grid"],
            "env_steps": K, "substeps_per_env_step": S, "dt": sc["dt"], "loss_frames": len(loss_frames),
-           "rigid": "stand-in integrator (Jade not installable); its own numpy dynamics are subtracted from the timings", "arms": {}}
+           "rigid": "stand-in integrator (Jade not installable); its own numpy dynamics are subtracted from the timings", "arms": {},
+           "actions": ("get_init_actions(choice=0, adjust=True): zeros adjusted with adjust_action_with_ext_force, body gravity on (the demo's own start)" if adjusted else
+                       ("demo_grip.py:86 (choice 2): 0.3 [1, -1]" if args.config == "grip" else "lift-and-tilt schedule of demo_pour.py:100-105 (choice 1), body gravity off"))}
     tables = None
-    arms = args.arms if args.arms is not None else "dropin,batched,device"      # --arms "" : parity leg only
+    arms = args.arms if args.arms is not None else "dropin,batched,device,device_graph"      # --arms "" : parity leg only
     for arm in [a for a in arms.split(",") if a]:
-        B = args.batch if arm in ("batched", "device") else 1
-        env, sim, prims, clock, L = build_cuda(sc, K, batch=B, cache_dir=args.cache_dir, mode=arm, sort_every=args.sort_every)
+        B = args.batch if arm in ("batched", "device", "device_graph") else 1
+        env, sim, prims, clock, L = build_cuda(sc, K, batch=B, cache_dir=args.cache_dir, mode="device" if arm == "device_graph" else arm, sort_every=args.sort_every)
+        sim.use_graphs = arm == "device_graph"         # every env step's substeps replayed as ONE CUDA-graph launch (smx_step_graph)
         tables = tables or tables_of(prims)
-        acts = actions_for(args.config, K)
+        acts = adjusted_pour_actions(sc, K, args.cache_dir) if adjusted else actions_for(args.config, K)
         best = None
         for r in range(args.reps + 1):
             l0 = sim.launch_count()
@@ -362,6 +391,8 @@ def main():
                             "rollouts_per_s": B / (t["forward"] + t["backward"] + t["loss"] + t["prepare"]),
                             "us_per_substep_pair": 1e6 * sim_s / (K * S), "loss": loss, "grad_norm": float(np.linalg.norm(grad)),
                             "grad_finite": bool(np.isfinite(grad).all()), "counters": sim.counters()}
+        if arm == "device_graph":
+            out["arms"][arm]["graph"] = sim.graph_status()
         del env, sim, prims, L
     # ---- parity + CPU baseline: oracle vs CUDA on a shorter episode with a stronger action ------------------------
     Kp = args.parity_env_steps if args.parity_env_steps is not None else (80 if args.config == "grip" else 150)
@@ -369,7 +400,7 @@ def main():
         from harness import cosine, rel_l2
         from oracle import mpm_oracle as mo
         strength = args.parity_strength or (50.0 if args.config == "grip" else 8.0)
-        acts = actions_for(args.config, Kp, strength)
+        acts = adjusted_pour_actions(sc, Kp, args.cache_dir) if adjusted else actions_for(args.config, Kp, strength)
         frames = list(range((Kp * S * 3) // 4, Kp * S + 1, 20)) or [Kp * S]
         envg, simg, primsg, clockg, _ = build_cuda(sc, Kp, cache_dir=args.cache_dir, mode="dropin", loss="host")
         tables = tables_of(primsg)
