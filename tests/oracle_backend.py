@@ -24,6 +24,12 @@ class OraclePrimitive:
     def get_all_states_grad(self, f):
         return self.sim.get_primitive_state_grad(self.i, f)
 
+    def get_all_states(self, f):
+        return self.sim.get_primitive_state(self.i, f)
+
+    def add_all_states_grad(self, f, g13):
+        self.sim.add_primitive_state_grad(self.i, f, np.asarray(g13, dtype=np.float64))
+
     def clear_ext_f(self):
         self.sim.clear_ext_f(self.i)
 
@@ -47,6 +53,7 @@ class OracleMPMSimulator:
     def __init__(self, n, n_grid, max_steps, dt, substeps, tables=(), prim_params=(), **kw):
         self.sim = mo.OracleSim(n, n_grid=n_grid, max_steps=max_steps, dt=dt, substeps=substeps, **kw)
         self.n_particles, self.substeps, self.cur, self.dim = n, substeps, 0, 3
+        self.n_control, self.dtype = int(kw.get("n_control", 0)), np.float64
         self.primitives = OraclePrimitives()
         for i, (t, (fr, so)) in enumerate(zip(tables, prim_params)):
             self.sim.add_primitive(t["sdf"], t["normal"], t["lower"], t["upper"], t["dx"], friction=fr, softness=so)
@@ -65,15 +72,24 @@ class OracleMPMSimulator:
         self.sim.clear_grads()
         self.cur = 0
 
+    def set_control_idx(self, idx):
+        self.sim.set_control_idx(np.asarray(idx))
+
     def substep(self, s, action=None):
+        if action is not None:                                  # mpm_simulator.py:321-322
+            self.sim.set_action(np.asarray(action, dtype=np.float64).reshape(self.n_control, 3))
         self.sim.substep(s)
 
     def substep_grad(self, s, action=None, ext_f_grad=None):
+        if action is not None:                                  # set_action zeroes action.grad (mpm_simulator.py:579-586)
+            self.sim.set_action(np.asarray(action, dtype=np.float64).reshape(self.n_control, 3))
         if ext_f_grad is not None:
             for i, g in enumerate(ext_f_grad):
                 self.sim.set_ext_f_grad(i, g)
         self.sim.substep_grad(s)
-        return None
+        if action is None:
+            return None
+        return self.sim.get_action_grad().reshape(np.shape(action))
 
     def get_x(self, f):
         return self.sim.get_frame(f)[:, :3]

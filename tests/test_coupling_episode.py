@@ -120,6 +120,89 @@ def test_episode_action_gradient_cosine():
     assert rel_l2(gg, go) <= 2e-2
 
 
+def build_door(backend, n=1500, env_steps=10, fp32_bridge=True):
+    """demo_door-shaped episode (config/demo_door_config.py): soft elastic material (E 50, ptype 1, no gravity, frictionless floor, dt = env_dt
+    = 1e-3 so substeps = 1) steered by ONE particle controller (control_mode "mpm", n_controllers 1, :24) against a slab hinged about the
+    vertical axis (revolute joint, door.urdf), DoorLoss with weight (pose, velocity, contact) on the hinge quaternion (loss_door.py:34-56)."""
+    from softmac_b200.engine.taichi_env import TaichiEnv
+    from softmac_b200.engine.rigid_simulator import RigidSimulator
+    from softmac_b200.engine.losses import DoorLoss
+    from softmac_b200.config import CfgNode
+    rng = np.random.default_rng(12)
+    n_grid, dt, substeps = 32, 1e-3, 1
+    max_steps = env_steps + 3
+    # the material sits at the free end of the leaf, more than 0.1 from the hinge: the contact-distance term of DoorLoss is active
+    x = ((rng.random((n, 3)) * 2 - 1) * 0.04 + np.array([0.575, 0.3, 0.5])).astype(np.float32).astype(np.float64)
+    tab = scenes.box_table(half=(0.16, 0.06, 0.03), dx=0.01, margin=0.04)
+    tab32 = {k: (np.asarray(v, dtype=np.float32).astype(np.float64) if k in ("sdf", "normal", "lower", "upper") else v) for k, v in tab.items()}
+    kw = dict(E=50., nu=0.2, gravity=(0., 0., 0.), ground_friction=0., material_model=0, ptype=1, collision_type=2)
+    if backend == "oracle":
+        from oracle_backend import OracleMPMSimulator
+        sim = OracleMPMSimulator(n, n_grid, max_steps, dt, substeps, tables=[tab32], prim_params=[(0.001, 666.)], n_control=1, **kw)
+        prims = sim.primitives
+    else:
+        from softmac_b200.engine import MPMSimulator, Primitives, Mesh
+        m = Mesh(sdf=dict(sdf=tab32["sdf"], normal=tab32["normal"], position=(tab32["lower"], tab32["upper"]), dx=tab["dx"]), cfg=dict(friction=0.001),
+                 max_timesteps=max_steps)
+        prims = Primitives(primitives=[m], max_timesteps=max_steps)
+        cfg = sim_cfg(n, n_grid=n_grid, max_steps=max_steps, dt=dt, E=50., gravity=(0., 0., 0.), ground_friction=0., ptype=1, n_control=1)
+        sim = MPMSimulator(cfg, prims, env_dt=dt)
+        assert sim.substeps == 1
+        prims.initialize()
+    sim.set_control_idx(np.zeros(n, dtype=np.int32))                            # every particle belongs to controller 0 (demo_door.py)
+    # the door leaf lies along x with its +z face 1 mm short of the material; the hinge is the vertical axis through its centre
+    bodies = [dict(joint="revolute", axis=(0, 1, 0), origin=(0.43, 0.3, 0.5 - 0.04 - 0.03 - 0.001), inertia=7.8e-6 * 50, gravity=False)]
+    rigid = RigidSimulator(CfgNode(gravity=(0., -9.8, 0.), init_state=(0., 0.), bodies=bodies), prims, substeps=substeps, env_dt=dt, fp32_bridge=fp32_bridge)
+    loss = DoorLoss(dict(weight=(1.0, 0.1, 5.0)), sim)
+    loss.initialize()
+    return TaichiEnv(sim, prims, rigid, x, loss=loss, control_mode="mpm")
+
+
+def run_door(env, actions, frames):
+    env.reset()
+    if hasattr(env.simulator, "clear_all_gradients"):
+        env.simulator.clear_all_gradients()
+    for a in actions:
+        env.step(a)
+    total = 0.0
+    for f in frames:
+        total += env.compute_loss(f)["frame_loss"]
+    return total, env.backward(), env.rigid_simulator.states[-1].copy()
+
+
+def test_door_like_episode_on_the_oracle_backend_matches_finite_differences():
+    """Particle control forces push soft material into a hinged leaf; the gradient of DoorLoss with respect to the particle actions --
+    control adjoint (mpm_simulator.py:209-213), contact wrench, revolute joint, pose / velocity / contact-distance terms -- against central
+    differences of the whole episode."""
+    env_steps = 8
+    env = build_door("oracle", n=500, env_steps=env_steps, fp32_bridge=False)    # fp32 truncation would quantise the finite differences
+    actions = np.tile([[0.0, 0.0, -600.0]], (env_steps, 1, 1))                  # (T, n_controllers, 3): push towards the leaf (-z)
+    frames = [env_steps, env_steps - 2]
+    loss, grad, rstate = run_door(env, actions, frames)
+    assert grad.shape == (env_steps, 3) or grad.shape == (env_steps, 1, 3)
+    grad = grad.reshape(env_steps, 3)
+    assert abs(rstate[0]) > 1e-5 and np.abs(grad).max() > 0                     # the door turned
+    eps = 1.0
+    for idx in ((1, 2), (3, 0)):
+        ap, am = actions.copy(), actions.copy()
+        ap[idx[0], 0, idx[1]] += eps; am[idx[0], 0, idx[1]] -= eps
+        fd = (run_door(env, ap, frames)[0] - run_door(env, am, frames)[0]) / (2 * eps)
+        assert abs(fd - grad[idx]) <= 3e-2 * max(abs(fd), abs(grad[idx]), 1e-12), (idx, fd, grad[idx])
+
+
+@pytest.mark.gpu
+def test_door_like_episode_action_gradient_cosine():
+    env_steps = 12
+    actions = np.tile([[0.0, 0.0, -600.0]], (env_steps, 1, 1)) * (1 + 0.05 * np.arange(env_steps))[:, None, None]
+    frames = [env_steps, env_steps - 3]
+    lo, go, ro = run_door(build_door("oracle", env_steps=env_steps), actions, frames)
+    lg, gg, rg = run_door(build_door("cuda", env_steps=env_steps), actions, frames)
+    assert abs(ro[0]) > 1e-5 and abs(lg - lo) <= 1e-4 * abs(lo)
+    assert rel_l2(rg, ro) <= 1e-4
+    c = cosine(gg, go)
+    assert np.abs(go).max() > 0 and c >= 0.999 and rel_l2(gg, go) <= 2e-2, (c, rel_l2(gg, go))
+
+
 def test_adjust_action_with_ext_force_holds_the_glass_still():
     """demo_pour's initial actions: get_init_actions(choice=0, adjust=True) (demo_pour.py:95-110, softmac/utils.py:76-113) -- zeros corrected
     by the measured contact wrench and the body's weight.  With body gravity ON the adjusted actions must keep the free-floating glass where
