@@ -74,6 +74,8 @@ typedef struct {
     int sticky_ground;      /* ground_friction >= 10, mpm_simulator.py:278 */
     int material_model, ptype, collision_type, substeps, n_control;
     int rigid_velocity_control;
+    int plasticity;         /* 0: sigma clip (softmac mpm_simulator.py:226-229); 1: von Mises return mapping (soft_cloth/engine/mpm_simulator.py:232) */
+    double yield_stress;    /* cfg.yield_stress (soft_cloth/engine/mpm_simulator.py:20,92) */
     int np;
     orc_prim prim[ORC_MAXP];
     double *x, *v, *C, *F, *gx, *gv, *gC, *gF;              /* [T][n][3|9] */
@@ -766,6 +768,8 @@ orc_sim *orc_create(int n_particles, int n_grid, int max_steps, double dt, doubl
     s->gaction = zalloc((size_t)(n_control > 0 ? n_control : 1)*3);
     return s;
 }
+/* soft_cloth variant of the plastic material: von Mises return mapping with cfg.yield_stress instead of the sigma clip */
+void orc_set_plasticity(orc_sim *s, int mode, double yield_stress) { s->plasticity = mode; s->yield_stress = yield_stress; }
 void orc_destroy(orc_sim *s) {
     if (!s) return;
     double *ps[] = {s->x, s->v, s->C, s->F, s->gx, s->gv, s->gC, s->gF, s->Ftmp, s->U, s->S, s->V, s->gFtmp, s->gU, s->gS, s->gV,
@@ -983,13 +987,39 @@ static inline void stencil_dw(const double *fx, double dw[3][3]) {
     for (int d = 0; d < 3; d++) { dw[0][d] = fx[d] - 1.5; dw[1][d] = -2.0*(fx[d] - 1.0); dw[2][d] = fx[d] - 0.5; }
 }
 
+/* compute_von_mises, soft_cloth/engine/mpm_simulator.py:172-189 (the softmac copy, mpm_simulator.py:166-182, lacks the 0.05 floor and is
+ * commented out at its call site :225).  S: diagonal of sig.  Returns 1 when the particle yields; then sn = exp(epsilon') and, if D is not
+ * NULL, D[k][i] = d sn_k / d S_i with Taichi's conventions: ti.max(sig, 0.05) passes its gradient to sig iff 0.05 < sig, the condition
+ * delta_gamma > 0 carries none, norm(x) = sqrt(x.x + 1e-8) (:201-202). */
+static int von_mises_sig(const orc_sim *s, const double *S, double sn[3], double D[3][3]) {
+    double sc[3], eps[3], eh[3], m = 0, q = 1e-8;
+    for (int d = 0; d < 3; d++) { sc[d] = fmax(S[4*d], 0.05); eps[d] = log(sc[d]); m += eps[d]/3; }
+    for (int d = 0; d < 3; d++) { eh[d] = eps[d] - m; q += eh[d]*eh[d]; }
+    double nrm = sqrt(q), c = s->yield_stress/(2*s->mu);
+    if (!(nrm - c > 0)) return 0;
+    for (int d = 0; d < 3; d++) sn[d] = exp(eps[d] - ((nrm - c)/nrm)*eh[d]);
+    if (D) for (int k = 0; k < 3; k++) for (int i = 0; i < 3; i++) {
+        /* eps'_k = eps_k - (1 - c/n) eh_k;  d eh_k/d eps_i = [k==i] - 1/3;  d n/d eps_i = eh_i/n (sum eh = 0) */
+        double de = (k == i) - (1 - c/nrm)*((k == i) - 1.0/3.0) - (c/(nrm*nrm*nrm))*eh[i]*eh[k];
+        D[k][i] = (0.05 < S[4*i]) ? sn[k]*de/sc[i] : 0.0;
+    }
+    return 1;
+}
+
 /* material update: F_tmp,U,S,V -> new_F, stress (before the -dt*p_vol*4*inv_dx^2 prefactor), :219-245 */
 static void material_fwd(const orc_sim *s, const double *Ftmp, const double *U, const double *S, const double *V,
                          double *newF, double *stress, double *J_out) {
     double J = det3(Ftmp);
     memcpy(newF, Ftmp, 72);
     if (s->material_model == 0) {
-        if (s->ptype == 0) {
+        if (s->ptype == 0 && s->plasticity == 1) {
+            double sn[3];
+            if (von_mises_sig(s, S, sn, NULL)) {                /* otherwise new_F stays F_tmp */
+                double Sn[9] = {0}, t[9];
+                for (int d = 0; d < 3; d++) Sn[4*d] = sn[d];
+                mm(U, Sn, t); mmT(t, V, newF);
+            }
+        } else if (s->ptype == 0) {
             double Sn[9] = {0}, t[9];
             for (int d = 0; d < 3; d++) Sn[4*d] = fmin(fmax(S[4*d], 1 - 2e-3), 1 + 3e-3);
             mm(U, Sn, t); mmT(t, V, newF);
@@ -1111,7 +1141,19 @@ static void p2g_grad(orc_sim *s, int f) {
             /* r = U V^T */
             mm(g_A, V, t); for (int i = 0; i < 9; i++) gU[i] -= t[i];
             mTm(g_A, U, t); for (int i = 0; i < 9; i++) gV[i] -= t[i];
-            if (s->ptype == 0) {
+            if (s->ptype == 0 && s->plasticity == 1) {
+                double sn[3], D[3][3];
+                if (von_mises_sig(s, S, sn, D)) {
+                    double Sn[9] = {0}, t2[9];
+                    for (int d = 0; d < 3; d++) Sn[4*d] = sn[d];
+                    mm(g_newF, V, t); mm(t, Sn, t2); for (int i = 0; i < 9; i++) gU[i] += t2[i];
+                    mTm(g_newF, U, t); mm(t, Sn, t2); for (int i = 0; i < 9; i++) gV[i] += t2[i];
+                    mTm(U, g_newF, t); mm(t, V, t2);
+                    for (int i = 0; i < 3; i++) for (int k = 0; k < 3; k++) gS[4*i] += t2[4*k]*D[k][i];
+                } else {
+                    for (int i = 0; i < 9; i++) gFtmp[i] += g_newF[i];
+                }
+            } else if (s->ptype == 0) {
                 double Sn[9] = {0}, t2[9];
                 for (int d = 0; d < 3; d++) Sn[4*d] = fmin(fmax(S[4*d], 1 - 2e-3), 1 + 3e-3);
                 mm(g_newF, V, t); mm(t, Sn, t2); for (int i = 0; i < 9; i++) gU[i] += t2[i];      /* gU += g V Sn */

@@ -39,6 +39,7 @@ def lib():
         L.orc_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, dp, C.c_double,
                                  C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         L.orc_destroy.argtypes = [vp]
+        L.orc_set_plasticity.argtypes = [vp, C.c_int, C.c_double]
         L.orc_add_primitive.restype = C.c_int
         L.orc_add_primitive.argtypes = [vp, dp, dp, ip, dp, dp, C.c_double, C.c_double, C.c_double, C.c_int]
         L.orc_set_primitive_enabled.argtypes = [vp, C.c_int, C.c_int]
@@ -99,6 +100,10 @@ class OracleSim:
         if getattr(self, "h", None):
             lib().orc_destroy(self.h)
             self.h = None
+
+    def set_plasticity(self, mode, yield_stress):
+        """mode 1: von Mises return mapping with cfg.yield_stress (soft_cloth/engine/mpm_simulator.py:232) instead of the sigma clip."""
+        lib().orc_set_plasticity(self.h, int(mode), float(yield_stress))
 
     # ---- primitives -------------------------------------------------------------------------
     def add_primitive(self, sdf=None, normal=None, lower=None, upper=None, sdf_dx=0.0, friction=0.9,

@@ -260,6 +260,23 @@ class TorchOracle:
         self.material_model, self.ptype, self.collision_type = material_model, ptype, collision_type
         self.substeps, self.n_control, self.vctrl = int(substeps), int(n_control), bool(rigid_velocity_control)
         self.prims = []
+        self.plasticity, self.yield_stress = 0, 0.0     # 1: von Mises return mapping of the soft_cloth variant (set_plasticity)
+
+    def set_plasticity(self, mode, yield_stress):
+        self.plasticity, self.yield_stress = int(mode), float(yield_stress)
+
+    def _von_mises(self, F_tmp, U, sig, V):
+        """compute_von_mises, soft_cloth/engine/mpm_simulator.py:172-189 (3-D): log-strain return mapping; F stays F_tmp unless the
+        particle yields.  norm(x) = sqrt(x.x + 1e-8) (:201-202)."""
+        sig = ti_max(sig, 0.05)
+        epsilon = torch.log(sig)
+        epsilon_hat = epsilon - (epsilon.sum(-1, keepdim=True) / 3)
+        epsilon_hat_norm = torch.sqrt(dot(epsilon_hat, epsilon_hat) + 1e-8)
+        delta_gamma = epsilon_hat_norm - self.yield_stress / (2 * self.mu)
+        yields = delta_gamma > 0
+        eps_new = epsilon - (delta_gamma / epsilon_hat_norm)[:, None] * epsilon_hat
+        F_y = U @ torch.diag_embed(torch.exp(eps_new)) @ V.transpose(-1, -2)
+        return torch.where(yields[:, None, None], F_y, F_tmp)
 
     def add_primitive(self, *a, **k):
         self.prims.append(TorchPrimitive(*a, **k))
@@ -334,7 +351,9 @@ class TorchOracle:
         new_F = F_tmp
         J = torch.linalg.det(F_tmp)
         if self.material_model == 0:
-            if self.ptype == 0:
+            if self.ptype == 0 and self.plasticity == 1:
+                new_F = self._von_mises(F_tmp, U, sig, V)
+            elif self.ptype == 0:
                 sig_new = ti_min(ti_max(sig, 1 - 2e-3), 1 + 3e-3)
                 new_F = U @ torch.diag_embed(sig_new) @ V.transpose(-1, -2)
             elif self.ptype == 2:

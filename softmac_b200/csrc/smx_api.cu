@@ -363,11 +363,13 @@ static int dispatch_mat(int material, int ptype, F&& fn) {
     int mat = material * 3 + ptype;
     switch (mat) {
         case 0: return fn(std::integral_constant<int, 0>());
+#ifndef SMX_ONLY_MAT0       // A/B variant builds (tools/gpu_variants.sh) instantiate the bench material only
         case 1: return fn(std::integral_constant<int, 1>());
         case 2: return fn(std::integral_constant<int, 2>());
         case 3: return fn(std::integral_constant<int, 4>());   // neo-Hookean "plastic" falls through to elastic (mpm_simulator.py:237-241)
         case 4: return fn(std::integral_constant<int, 4>());
         case 5: return fn(std::integral_constant<int, 5>());
+#endif
     }
     return fail(SMX_ERR_ARG, "bad material_model/ptype %d/%d", material, ptype);
 }
@@ -1595,7 +1597,7 @@ static int grad_end(smx_sim* s, int f, bool fuse) {
                 constexpr bool R = decltype(rec_c)::value, E = decltype(extra_c)::value;
                 if (fuse) {
                     // + G2P adjoint of substep f-1: g_out of f-1 and its cleared adjoint grid were put in place by k_grid_grad above
-                    launch_pdl(s, k_p2g_grad_g2p_grad<M, R, E>, nblk(P.n, SMX_TPB), SMX_TPB, 0, P, ps, f, fin, s->adj_cur, s->adj_nxt, gg, cslot, s->action, s->action_grad, rec,
+                    launch_pdl(s, k_p2g_grad_g2p_grad<M, R, E>, nblk(P.n, SMX_TPB_FB), SMX_TPB_FB, 0, P, ps, f, fin, s->adj_cur, s->adj_nxt, gg, cslot, s->action, s->action_grad, rec,
                                (const float*)s->frame_ptr(f - 1), (const float4*)s->g_out, s->gg_of(f - 1), s->pf_g);
                 } else if (tiled) {
                     // persistent CTAs, double-buffered TMA staging of the streaming planes

@@ -99,6 +99,25 @@ __device__ __forceinline__ void pdl_prologue() {
     asm volatile("griddepcontrol.launch_dependents;");
 }
 
+// Timing experiment (SMX_DBG bits 8..: step in ns): de-phase the warps that share an SM.  A PDL launch releases every resident CTA of
+// the first wave at the same instant (griddepcontrol.wait), so all warps of an SM walk through the load / gather / SVD / scatter phases
+// of the kernel together; slot s of the SM (blockIdx / #SMs) and warp w start (s * warps + w) * step later.  Later waves inherit the offsets.
+__device__ __forceinline__ void stagger_first_wave(int dbg, int slots) {
+#ifndef SMX_STAGGER
+    return;
+#endif
+    const unsigned step = (unsigned)dbg >> 8;
+    if (step) {
+        unsigned nsm;
+        asm("mov.u32 %0, %%nsmid;" : "=r"(nsm));
+        const unsigned slot = blockIdx.x / nsm;
+        if (slot < (unsigned)slots) {
+            const unsigned u = slot * (blockDim.x >> 5) + (threadIdx.x >> 5);
+            if (u) __nanosleep(u * step);
+        }
+    }
+}
+
 #define SMX_TPB 128         // gather-type particle kernels
 #ifndef SMX_TPB_SC
 #define SMX_TPB_SC 128      // P2G: four warps x 13.6 KB of staging, four CTAs per SM at 128 registers (16 warps)
@@ -523,6 +542,7 @@ __global__ void __launch_bounds__(SMX_TPB_SC, SMX_SC_MINB) k_p2g(Params P, PrimS
                                                     const float* __restrict__ action, int accumulate,
                                                     const float* __restrict__ fprev, const float4* __restrict__ g_prev, float4* __restrict__ rec, int pf_dist) {
     pdl_prologue();
+    stagger_first_wave(P.dbg, SMX_SC_MINB);
     // EXTRA: particle-contact impulses (collision_type == 1) and / or particle control forces are present
     extern __shared__ __align__(128) float4 smx_dyn_smem[];     // STAGED: one WarpStage per warp (more than the 48 KB static limit)
     WarpStage* stage = reinterpret_cast<WarpStage*>(smx_dyn_smem);
@@ -1315,15 +1335,19 @@ __global__ void __launch_bounds__(SMX_TPB, SMX_P2GG_MINB) k_p2g_grad(Params P, P
 #ifndef SMX_FUSEB_MINB
 #define SMX_FUSEB_MINB 4
 #endif
+#ifndef SMX_TPB_FB
+#define SMX_TPB_FB 128
+#endif
 template <int MAT, bool REC, bool EXTRA>
-__global__ void __launch_bounds__(SMX_TPB, SMX_FUSEB_MINB) k_p2g_grad_g2p_grad(Params P, PrimSet ps, int f, const float* __restrict__ fin, float* ain, float* __restrict__ aout,
+__global__ void __launch_bounds__(SMX_TPB_FB, SMX_FUSEB_MINB) k_p2g_grad_g2p_grad(Params P, PrimSet ps, int f, const float* __restrict__ fin, float* ain, float* __restrict__ aout,
                                                                   const float4* __restrict__ gg, const int* __restrict__ ctrl_slot, const float* __restrict__ action,
                                                                   double* __restrict__ action_grad, const float4* __restrict__ rec, const float* __restrict__ fprev,
                                                                   const float4* __restrict__ g_prev, float4* __restrict__ gg_prev, int pf_dist) {
     pdl_prologue();
+    stagger_first_wave(P.dbg, SMX_FUSEB_MINB);
     constexpr bool corot = (MAT / 3 == 0) && (MAT % 3 != 2);
-    __shared__ WarpStage3 stage[SMX_TPB / 32];
-    int j = blockIdx.x * SMX_TPB + threadIdx.x;
+    __shared__ WarpStage3 stage[SMX_TPB_FB / 32];
+    int j = blockIdx.x * SMX_TPB_FB + threadIdx.x;
     bool live = j < P.n;
     int jj = live ? j : P.n - 1;
     {

@@ -20,16 +20,19 @@ ROWS = [
     ("neo-Hookean liquid", dict(ptype=2, material_model=1, collision_type=2, n_prim=1)),
     ("grid contact (collision_type 0)", dict(ptype=0, material_model=0, collision_type=0, n_prim=2)),
     ("blob on the sticky floor and against a wall, later frame (life = 1/2)", dict(ptype=0, material_model=0, collision_type=2, n_prim=1, center=(0.085, 0.085, 0.5), frame=3, max_steps=6)),
+    ("soft_cloth: corotated plastic with the von Mises return mapping (yield 50: about half of the particles yield)", dict(ptype=0, material_model=0, collision_type=2, n_prim=1, yield_stress=50.)),
     ("free-slip walls and ceiling", dict(ptype=1, material_model=0, collision_type=2, n_prim=0, center=(0.88, 0.88, 0.88), ground_friction=0., gravity=(3., 9.8, 2.))),
 ]
 
 
 def build(rng, n=500, n_grid=32, collision_type=2, ptype=0, material_model=0, n_prim=1, n_control=0, gravity=(0., -9.8, 0.),
-          ground_friction=20., substeps=5, center=(0.5, 0.3, 0.5), vctrl=False, frame=0, max_steps=4):
+          ground_friction=20., substeps=5, center=(0.5, 0.3, 0.5), vctrl=False, frame=0, max_steps=4, yield_stress=None):
     kw = dict(n_grid=n_grid, dt=2e-4, E=3e3, nu=0.2, gravity=gravity, ground_friction=ground_friction, material_model=material_model,
               ptype=ptype, collision_type=collision_type, substeps=substeps, n_control=n_control, rigid_velocity_control=vctrl)
     c = mo.OracleSim(n, max_steps=max_steps, **kw)
     t = TorchOracle(**kw)
+    if yield_stress is not None:                    # soft_cloth/engine/mpm_simulator.py:232
+        c.set_plasticity(1, yield_stress); t.set_plasticity(1, yield_stress)
     tab = scenes.sphere_table()
     s13s = []
     for i in range(n_prim):

@@ -89,6 +89,32 @@ def test_vjp_mixed_contact_corotated(ptype):
     assert np.abs(g_pr[0]).max() > 0  # contact was active: primitive received gradient
 
 
+def test_vjp_von_mises_return_mapping():
+    """soft_cloth's plastic material (soft_cloth/engine/mpm_simulator.py:172-189, :232): the adjoint through the log-strain return mapping,
+    with yielding and non-yielding particles in the same blob, and the forward against a direct numpy evaluation of the formula."""
+    rng = np.random.default_rng(77)
+    sim, st, prs = make_sim(rng, ptype=0, n_prim=1)
+    mu = 3e3 / (2 * 1.2)
+    F0, C0 = st[:, 6:15].reshape(-1, 3, 3), st[:, 15:24].reshape(-1, 3, 3)
+    Ftmp = (np.eye(3)[None] + 2e-4 * C0) @ F0
+    U, sg, Vt = np.linalg.svd(Ftmp)
+    eps = np.log(np.maximum(sg, 0.05))
+    eh = eps - eps.mean(1, keepdims=True)
+    nrm = np.sqrt((eh * eh).sum(1) + 1e-8)
+    yield_stress = 2 * mu * float(np.median(nrm))                 # half of the blob yields
+    sim.set_plasticity(1, yield_stress)
+    check_vjp(rng, sim, st, prs)
+    # forward: F[f+1] of every particle from numpy's SVD of F_tmp (U diag(.) V^T is invariant to the SVD's sign / ordering freedom)
+    run_forward(sim, st, prs, None)
+    F1 = sim.get_frame(1)[:, 6:15].reshape(-1, 3, 3)
+    dg = nrm - yield_stress / (2 * mu)
+    yields = dg > 0
+    assert 0.3 < yields.mean() < 0.7
+    Fy = U @ (np.exp(eps - (dg / nrm)[:, None] * eh)[:, :, None] * Vt)
+    want = np.where(yields[:, None, None], Fy, Ftmp)
+    assert np.abs(F1 - want).max() <= 1e-12
+
+
 def test_contact_is_exercised():
     rng = np.random.default_rng(3)
     sim, st, prs = make_sim(rng, n_prim=2)

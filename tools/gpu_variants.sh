@@ -10,7 +10,7 @@ for spec in "$@"; do
   name=$(basename $lib .so)$(printf '_%s' "${envs[@]}" | tr -d '=' | sed 's/^_$//')
   for init in $inits; do
     out=gpurun_out/${tag}_${name}_${init}
-    env SMX_LIB=$PWD/$lib "${envs[@]}" python bench.py --steps 6 --warmup 3 --init $init --no-e2e --no-cpu-baseline > $out.json 2> $out.err
+    env SMX_LIB=$PWD/$lib "${envs[@]}" python bench.py --steps 6 --warmup 3 --init $init --no-e2e --no-cpu-baseline --no-parity --no-subrecords > $out.json 2> $out.err
     python - <<PY
 import json
 try:
