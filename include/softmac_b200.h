@@ -190,6 +190,13 @@ int smx_rigid_linear_get_states(smx_sim* sim, int32_t k, double* out);
 int smx_rigid_linear_get_action_grads(smx_sim* sim, int32_t k0, int32_t k1, double* out);
 int smx_rigid_linear_get_state_grad(smx_sim* sim, double* out);
 
+/* Plastic flow rule of the co-rotated plastic material (material_model 0, ptype 0).  mode 0 (default): sigma clip to [1 - 2e-3, 1 + 3e-3]
+ * (softmac/engine/mpm_simulator.py:226-229).  mode 1: von Mises return mapping in log strain with cfg.SIMULATOR.yield_stress, the rule the
+ * soft_cloth variant runs (soft_cloth/engine/mpm_simulator.py:172-189 compute_von_mises, call site :232; yield_stress field :20,49,92) and
+ * that softmac keeps commented out at mpm_simulator.py:225.  Forward and adjoint (Taichi sub-gradients: max(sig, 0.05) passes its gradient
+ * iff 0.05 < sig, the yield test carries none).  Call between rollouts, not inside one. */
+int smx_set_plasticity(smx_sim* sim, int32_t mode, double yield_stress);
+
 /* particle-force control ("mpm" control mode) --------------------------------------------------- */
 /* MPMSimulator.set_action(action (n_control,3)); also zeroes action.grad (mpm_simulator.py:579-592).
  * With n_batch > 1 the array is (n_batch * n_control, 3), batch-major (likewise smx_get_action_grad). */

@@ -104,6 +104,7 @@ _SIGS = {
     "smx_rigid_linear_get_states": [vp, C.c_int32, dp],
     "smx_rigid_linear_get_action_grads": [vp, C.c_int32, C.c_int32, dp],
     "smx_rigid_linear_get_state_grad": [vp, dp],
+    "smx_set_plasticity": [vp, C.c_int32, C.c_double],
     "smx_set_action": [vp, dp],
     "smx_set_control_idx": [vp, ip],
     "smx_get_action_grad": [vp, dp],

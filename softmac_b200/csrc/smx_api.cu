@@ -359,10 +359,15 @@ static int ctrl_slots(smx_sim* s, int order_id, const int** out) {
 }
 
 template <typename F>
-static int dispatch_mat(int material, int ptype, F&& fn) {
+static int dispatch_mat(const Params& P, F&& fn) {
+    const int material = P.material, ptype = P.ptype;
     int mat = material * 3 + ptype;
     switch (mat) {
-        case 0: return fn(std::integral_constant<int, 0>());
+        case 0:
+#ifndef SMX_ONLY_MAT0
+            if (P.vm) return fn(std::integral_constant<int, 6>());     // von Mises return mapping (smx_set_plasticity)
+#endif
+            return fn(std::integral_constant<int, 0>());
 #ifndef SMX_ONLY_MAT0       // A/B variant builds (tools/gpu_variants.sh) instantiate the bench material only
         case 1: return fn(std::integral_constant<int, 1>());
         case 2: return fn(std::integral_constant<int, 2>());
@@ -441,7 +446,7 @@ static int forward_p2g(smx_sim* s, int f, bool write_F, bool accumulate, bool fu
         float4* rec = (write_F && s->svd_pool) ? s->svd_rec(f) : nullptr;
         const bool extra = P.ctype == 1 || P.n_control > 0;
         const int grid = nblk(P.n, SMX_TPB_SC), acc = accumulate ? 1 : 0;
-        TRY(dispatch_mat(P.material, P.ptype, [&](auto mat) {
+        TRY(dispatch_mat(P, [&](auto mat) {
             constexpr int M = decltype(mat)::value;
             auto go = [&](auto staged_c, auto extra_c) {
                 constexpr bool ST = decltype(staged_c)::value, EX = decltype(extra_c)::value;
@@ -708,6 +713,7 @@ static int create_body(smx_sim* s, const smx_config* cfg) {
     P.cs = (float)(-cfg->dt * p_vol * 4 * (double)cfg->n_grid * (double)cfg->n_grid);
     P.gx = (float)cfg->gravity[0]; P.gy = (float)cfg->gravity[1]; P.gz = (float)cfg->gravity[2];
     P.sticky = cfg->ground_friction >= 10.0;
+    P.vm = 0; P.vm_c = 0.f;
     P.material = cfg->material_model; P.ptype = cfg->ptype; P.ctype = cfg->collision_type; P.substeps = cfg->substeps; P.n_control = cfg->n_control; P.np = 0;
     s->dense = (cfg->flags & SMX_FLAG_DENSE_GRID) || (cfg->flags & SMX_FLAG_NO_SORT) || cfg->sort_every <= 0;
     P.Gb = P.ng * P.ng * P.ng; P.nb3 = P.nb * P.nb * P.nb;
@@ -1246,6 +1252,20 @@ int smx_reset_primitive(smx_sim* s, int32_t id) {
     return clear_ext_f(s, 0, s->B, id);
 }
 
+// ---- material variants ---------------------------------------------------------------------------
+int smx_set_plasticity(smx_sim* s, int32_t mode, double yield_stress) {
+    if (!s) return fail(SMX_ERR_ARG, "smx_set_plasticity: null simulator");
+    if (mode != 0 && mode != 1) return fail(SMX_ERR_ARG, "smx_set_plasticity: mode %d (0 sigma clip, 1 von Mises)", mode);
+    if (mode == 1 && !(s->cfg.material_model == 0 && s->cfg.ptype == 0))
+        return fail(SMX_ERR_STATE, "smx_set_plasticity: the von Mises return mapping belongs to the co-rotated plastic material (material_model 0, ptype 0)");
+    if (mode == 1 && !(yield_stress >= 0.0)) return fail(SMX_ERR_ARG, "smx_set_plasticity: yield_stress %g", yield_stress);
+    CK(cudaSetDevice(s->cfg.device));
+    CK(cudaStreamSynchronize(s->stream));
+    s->P.vm = mode;
+    s->P.vm_c = mode ? (float)(yield_stress / (2.0 * (s->cfg.E / (2.0 * (1.0 + s->cfg.nu))))) : 0.f;      // yield_stress / (2 mu), mu as in mpm_simulator.py:41
+    return SMX_OK;
+}
+
 // ---- control ------------------------------------------------------------------------------------
 int smx_set_action(smx_sim* s, const double* action) {
     if (!s || !action) return fail(SMX_ERR_ARG, "smx_set_action: null argument");
@@ -1591,7 +1611,7 @@ static int grad_end(smx_sim* s, int f, bool fuse) {
         const float4* rec = use_rec ? s->svd_rec(f) : nullptr;
         const bool extra = P.ctype == 1 || P.n_control > 0;
         const bool tiled = !(s->cfg.flags & SMX_FLAG_NO_TMA);
-        TRY(dispatch_mat(P.material, P.ptype, [&](auto mat) {
+        TRY(dispatch_mat(P, [&](auto mat) {
             constexpr int M = decltype(mat)::value;
             auto go = [&](auto rec_c, auto extra_c) {
                 constexpr bool R = decltype(rec_c)::value, E = decltype(extra_c)::value;

@@ -37,6 +37,8 @@ struct Params {
     long long stride;       // floats between components of a frame
     int ng, nb;             // grid nodes per axis, blocks per axis (ng/4)
     float dt, dx, inv_dx, p_mass, mu, lam, cs;      // cs = -dt*p_vol*4*inv_dx^2 (mpm_simulator.py:247)
+    float vm_c;             // yield_stress / (2 mu): von Mises return mapping (smx_set_plasticity)
+    int vm;                 // 1: co-rotated plastic uses the von Mises return mapping instead of the sigma clip
     float gx, gy, gz;       // gravity
     int sticky;             // ground_friction >= 10
     int material, ptype, ctype, substeps, n_control, np;
@@ -352,6 +354,43 @@ __device__ __forceinline__ void commit_prim_grad(double* g13, const PrimGrad& G,
     }
 }
 
+// MAT = material_model * 3 + ptype (0..5); 6 = co-rotated plastic with the von Mises return mapping of the soft_cloth variant
+// (soft_cloth/engine/mpm_simulator.py:172-189, :232) instead of the sigma clip (softmac mpm_simulator.py:226-229)
+__host__ __device__ constexpr int mat_model(int MAT) { return MAT == 6 ? 0 : MAT / 3; }
+__host__ __device__ constexpr int mat_ptype(int MAT) { return MAT == 6 ? 0 : MAT % 3; }
+__host__ __device__ constexpr bool mat_vm(int MAT) { return MAT == 6; }
+
+// compute_von_mises in deviation form: e = sigma - 1 in, g = sigma_new - 1 out; returns whether the particle yields (otherwise g = e and
+// new_F stays F_tmp).  c = yield_stress / (2 mu).  sig = max(sig, 0.05); epsilon = log(sig); epsilon_hat = epsilon - mean;
+// norm = sqrt(epsilon_hat . epsilon_hat + 1e-8); delta_gamma = norm - c; yields: epsilon -= (delta_gamma / norm) epsilon_hat, sig = exp(epsilon).
+// D (optional): d g_k / d e_i with Taichi's conventions (max passes its gradient iff 0.05 < sig; the yield test carries none).
+__device__ __forceinline__ bool von_mises_dev(const float* e, float c, float* g, float (*D)[3] = nullptr) {
+    float eps[3], eh[3], sc[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) { sc[d] = fmaxf(e[d], 0.05f - 1.f); eps[d] = log1pf(sc[d]); }
+    float m = (eps[0] + eps[1] + eps[2]) * (1.f / 3.f);
+    float q = 1e-8f;
+#pragma unroll
+    for (int d = 0; d < 3; d++) { eh[d] = eps[d] - m; q = fmaf(eh[d], eh[d], q); }
+    float nrm = sqrtf(q);
+    bool yields = nrm - c > 0.f;
+    float k = 1.f - c / nrm;            // delta_gamma / norm
+#pragma unroll
+    for (int d = 0; d < 3; d++) g[d] = yields ? expm1f(fmaf(-k, eh[d], eps[d])) : e[d];
+    if (D) {
+        float c3 = c / (nrm * nrm * nrm);
+#pragma unroll
+        for (int kk = 0; kk < 3; kk++)
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                float id = kk == i ? 1.f : 0.f;
+                float de = id - k * (id - 1.f / 3.f) - c3 * eh[i] * eh[kk];
+                D[kk][i] = (e[i] > 0.05f - 1.f) ? (1.f + g[kk]) * de / (1.f + sc[i]) : 0.f;
+            }
+    }
+    return yields;
+}
+
 // ------------------------------------------------------------------------------------------------
 // material point update (mpm_simulator.py:125-133, 219-248), deviation form.  Et = F_tmp - I.
 // ------------------------------------------------------------------------------------------------
@@ -372,7 +411,7 @@ __device__ __forceinline__ M3 compute_Et(const M3& C, const M3& F, float dt) {
 // REC: m.svd and m.Jm1 were loaded from the SVD record of the forward pass (co-rotated plastic / elastic only)
 template <int MAT, bool REC = false>
 __device__ __forceinline__ void material_update(const M3& Et, const Params& P, Material& m) {
-    constexpr int model = MAT / 3, ptype = MAT % 3;
+    constexpr int model = mat_model(MAT), ptype = mat_ptype(MAT);
     constexpr bool rec = REC && model == 0 && ptype != 2;
     if (!rec) m.Jm1 = det_minus_one(Et);
     m.J = 1.f + m.Jm1;
@@ -388,7 +427,13 @@ __device__ __forceinline__ void material_update(const M3& Et, const Params& P, M
             if (!rec) m.svd = svd_dev(Et);
             float g0 = m.svd.e[0], g1 = m.svd.e[1], g2 = m.svd.e[2];
             m.newF = Ftmp;
-            if (ptype == 0) {             // plastic: clip sigma to [1-2e-3, 1+3e-3] (:226-229)
+            if (mat_vm(MAT)) {            // soft_cloth plastic: von Mises return mapping; new_F stays F_tmp unless the particle yields
+                float g3[3];
+                bool yields = von_mises_dev(m.svd.e, P.vm_c, g3);
+                g0 = g3[0]; g1 = g3[1]; g2 = g3[2];
+                if (__any_sync(__activemask(), yields))
+                    m.newF = add(Ftmp, udvt(m.svd.U, g0 - m.svd.e[0], g1 - m.svd.e[1], g2 - m.svd.e[2], m.svd.V));
+            } else if (ptype == 0) {      // plastic: clip sigma to [1-2e-3, 1+3e-3] (:226-229)
                 g0 = fminf(fmaxf(g0, -2e-3f), 3e-3f); g1 = fminf(fmaxf(g1, -2e-3f), 3e-3f); g2 = fminf(fmaxf(g2, -2e-3f), 3e-3f);
                 // new_F = F_tmp + U (Sc - S) V^T: exactly F_tmp when nothing is clipped (skipped warp-wide in that case)
                 bool clipped = (g0 != m.svd.e[0]) | (g1 != m.svd.e[1]) | (g2 != m.svd.e[2]);
@@ -546,7 +591,7 @@ __global__ void __launch_bounds__(SMX_TPB_SC, SMX_SC_MINB) k_p2g(Params P, PrimS
     // EXTRA: particle-contact impulses (collision_type == 1) and / or particle control forces are present
     extern __shared__ __align__(128) float4 smx_dyn_smem[];     // STAGED: one WarpStage per warp (more than the 48 KB static limit)
     WarpStage* stage = reinterpret_cast<WarpStage*>(smx_dyn_smem);
-    constexpr bool has_svd = (MAT / 3 == 0) && (MAT % 3 != 2);
+    constexpr bool has_svd = (mat_model(MAT) == 0) && (mat_ptype(MAT) != 2);
     int j = blockIdx.x * SMX_TPB_SC + threadIdx.x;
     bool live = j < P.n;
     int jj = live ? j : P.n - 1;
@@ -1124,7 +1169,7 @@ __device__ __forceinline__ void p2g_grad_particle(const Params& P, const PrimSet
                                                   const float4* rb, long long rs, const float4* ab, long long astr, float4 gx_part, float* __restrict__ aout,
                                                   const float4* __restrict__ gg, const int* __restrict__ ctrl_slot, const float* __restrict__ action,
                                                   double* __restrict__ action_grad, V3* gxo = nullptr, V3* gvo = nullptr, M3* gCo = nullptr) {
-    constexpr int model = MAT / 3, ptype = MAT % 3;
+    constexpr int model = mat_model(MAT), ptype = mat_ptype(MAT);
     constexpr bool corot = model == 0 && ptype != 2;
     V3 x, v; M3 F, C;
     load_state_b<SM>(fb, fs, x, v, F, C);
@@ -1211,9 +1256,13 @@ __device__ __forceinline__ void p2g_grad_particle(const Params& P, const PrimSet
             // followed by the folded svd_grad (mpm_simulator.py:140-157): see DESIGN.md "SVD adjoint in divided-difference form"
             const M3 &U = m.svd.U, &V = m.svd.V;
             const float* e = m.svd.e;
-            float g3[3];
+            float g3[3], Dvm[3][3];
+            bool yields = false;        // von Mises only: a particle that does not yield keeps new_F = F_tmp (the elastic form below)
+            if (mat_vm(MAT)) yields = von_mises_dev(e, P.vm_c, g3, Dvm);
+            else {
 #pragma unroll
-            for (int i = 0; i < 3; i++) g3[i] = ptype == 0 ? fminf(fmaxf(e[i], -2e-3f), 3e-3f) : e[i];
+                for (int i = 0; i < 3; i++) g3[i] = ptype == 0 ? fminf(fmaxf(e[i], -2e-3f), 3e-3f) : e[i];
+            }
             M3 Gh = mul(Tmul(U, gstress), U);
             M3 M1 = mul(Tmul(U, gnewF), V), M2;
             float mu2 = 2.f * P.mu;
@@ -1229,13 +1278,14 @@ __device__ __forceinline__ void p2g_grad_particle(const Params& P, const PrimSet
 #pragma unroll
             for (int i = 0; i < 3; i++) {
                 // plastic: min(max(sig, lo), hi): gradient reaches sig iff lo < sig and max(sig, lo) < hi;  elastic: new_F = F_tmp
-                inner.m[4 * i] = (ptype == 1 || (e[i] > -2e-3f && e[i] < 3e-3f)) ? M1.m[4 * i] : 0.f;
+                if (mat_vm(MAT)) inner.m[4 * i] = yields ? M1.m[0] * Dvm[0][i] + M1.m[4] * Dvm[1][i] + M1.m[8] * Dvm[2][i] : M1.m[4 * i];
+                else inner.m[4 * i] = (ptype == 1 || (e[i] > -2e-3f && e[i] < 3e-3f)) ? M1.m[4 * i] : 0.f;
 #pragma unroll
                 for (int jx = 0; jx < 3; jx++) {
                     if (jx == i) continue;
                     float de = e[jx] - e[i];
                     float K = __fdividef(1.f, clamp_ref(de * (2.f + e[i] + e[jx])));
-                    if (ptype == 0) {
+                    if (ptype == 0 && (!mat_vm(MAT) || yields)) {
                         float dg = g3[jx] - g3[i];
                         float P1 = dg + de + (g3[jx] * e[jx] - g3[i] * e[i]);
                         float Q1 = dg - de + (g3[jx] * e[i] - g3[i] * e[jx]);
@@ -1307,7 +1357,7 @@ __global__ void __launch_bounds__(SMX_TPB, SMX_P2GG_MINB) k_p2g_grad(Params P, P
                                                       float* __restrict__ aout, const float4* __restrict__ gg, const int* __restrict__ ctrl_slot,
                                                       const float* __restrict__ action, double* __restrict__ action_grad, const float4* __restrict__ rec, int pf_dist) {
     pdl_prologue();
-    constexpr bool corot = (MAT / 3 == 0) && (MAT % 3 != 2);
+    constexpr bool corot = (mat_model(MAT) == 0) && (mat_ptype(MAT) != 2);
     int j = blockIdx.x * SMX_TPB + threadIdx.x;
     bool live = j < P.n;
     int jj = live ? j : P.n - 1;
@@ -1345,7 +1395,7 @@ __global__ void __launch_bounds__(SMX_TPB_FB, SMX_FUSEB_MINB) k_p2g_grad_g2p_gra
                                                                   const float4* __restrict__ g_prev, float4* __restrict__ gg_prev, int pf_dist) {
     pdl_prologue();
     stagger_first_wave(P.dbg, SMX_FUSEB_MINB);
-    constexpr bool corot = (MAT / 3 == 0) && (MAT % 3 != 2);
+    constexpr bool corot = (mat_model(MAT) == 0) && (mat_ptype(MAT) != 2);
     __shared__ WarpStage3 stage[SMX_TPB_FB / 32];
     int j = blockIdx.x * SMX_TPB_FB + threadIdx.x;
     bool live = j < P.n;
@@ -1380,7 +1430,7 @@ __global__ void __launch_bounds__(SMX_TPB_FB, SMX_FUSEB_MINB) k_p2g_grad_g2p_gra
 // Persistent, software-pipelined variant: every CTA walks tiles of SMX_P2GG_TPB particle slots; while tile i is being processed the
 // streaming planes of tile i+1 (frame f: 6, adjoint of F[f+1]: 3, SVD record: 4 -- each a contiguous 2 KB row) are brought into
 // the other half of a double buffer by TMA bulk copies (cp.async.bulk) that complete on an mbarrier, so no warp ever waits for HBM.
-#define SMX_P2GG_NPL(MAT, REC) (((MAT) / 3 == 0 && (MAT) % 3 != 2 && (REC)) ? 13 : 9)
+#define SMX_P2GG_NPL(MAT, REC) ((mat_model(MAT) == 0 && mat_ptype(MAT) != 2 && (REC)) ? 13 : 9)
 template <int MAT, bool REC, bool EXTRA>
 __global__ void __launch_bounds__(SMX_P2GG_TPB, SMX_P2GG_TILED_MINB) k_p2g_grad_tiled(Params P, PrimSet ps, int f, const float* __restrict__ fin, const float* __restrict__ ain,
                                                             float* __restrict__ aout, const float4* __restrict__ gg, const int* __restrict__ ctrl_slot,

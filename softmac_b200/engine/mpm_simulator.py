@@ -112,6 +112,17 @@ class MPMSimulator:
         for i in range(self.n_primitive):
             pid = self.primitives[i]._attach(self._h, True)
             assert pid == i
+        # cfg.plasticity = "von_mises": the soft_cloth variant's flow rule with cfg.yield_stress (soft_cloth/engine/mpm_simulator.py:20,232)
+        self.plasticity = "clip"
+        if str(getattr(cfg, "plasticity", "clip")) == "von_mises":
+            self.set_plasticity("von_mises", float(cfg.yield_stress))
+
+    def set_plasticity(self, mode, yield_stress=50.):
+        """"clip": sigma clip of softmac (mpm_simulator.py:226-229); "von_mises": the return mapping the soft_cloth variant runs
+        (soft_cloth/engine/mpm_simulator.py:172-189, call site :232) with cfg.yield_stress."""
+        m = {"clip": 0, "von_mises": 1, 0: 0, 1: 1}[mode]
+        check(lib().smx_set_plasticity(self._h, m, float(yield_stress)))
+        self.plasticity, self._yield_stress = ("von_mises" if m else "clip"), float(yield_stress)
 
     # ------------------------------------------------------------------------------------------------
     def __del__(self):

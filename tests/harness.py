@@ -15,7 +15,7 @@ def sim_cfg(n, n_grid=32, max_steps=8, dt=2e-4, E=3e3, nu=0.2, gravity=(0., -9.8
 class Pair:
     """oracle + cuda simulators with identical parameters, primitives and (fp32-rounded) inputs."""
 
-    def __init__(self, n, tables=(), prim_params=(), substeps=5, sort_every=None, flags=0, vctrl=False, **kw):
+    def __init__(self, n, tables=(), prim_params=(), substeps=5, sort_every=None, flags=0, vctrl=False, yield_stress=None, **kw):
         from oracle import mpm_oracle as mo
         from softmac_b200.engine import MPMSimulator, Primitives, Mesh
         cfg = sim_cfg(n, **kw)
@@ -37,6 +37,9 @@ class Pair:
         self.prims = Primitives(primitives=prims, max_timesteps=cfg.max_steps, rigid_velocity_control=vctrl)
         self.gpu = MPMSimulator(cfg, self.prims, env_dt=cfg.dt * substeps, rigid_velocity_control=vctrl, sort_every=sort_every, flags=flags)
         self.P = len(prims)
+        if yield_stress is not None:        # soft_cloth's flow rule (soft_cloth/engine/mpm_simulator.py:232)
+            self.orc.set_plasticity(1, yield_stress)
+            self.gpu.set_plasticity("von_mises", yield_stress)
 
     def set_prim_state(self, i, f0, f1, s13):
         s13 = np.asarray(s13, dtype=np.float32).astype(np.float64)

@@ -192,8 +192,12 @@ def test_door_like_episode_on_the_oracle_backend_matches_finite_differences():
 
 @pytest.mark.gpu
 def test_door_like_episode_action_gradient_cosine():
+    # The push is oblique: with a push along -z only, the tangential velocity at the leaf is EXACTLY zero in f64 at env step 0 (zero initial
+    # velocity, zero stress, axis-aligned normal), where collide_mixed switches the friction branch off through its flag
+    # sqrt(p_v_t . p_v_t) > 1e-30 (primitive_base.py:155-157) and the gradient jumps; fp32 leaves 1e-8 of rounding in p_v_t and takes the
+    # other side of that jump (measured: only the x / y action gradient of env step 0 differs, by 15 %).  Not a property worth pinning.
     env_steps = 12
-    actions = np.tile([[0.0, 0.0, -600.0]], (env_steps, 1, 1)) * (1 + 0.05 * np.arange(env_steps))[:, None, None]
+    actions = np.tile([[45.0, 30.0, -600.0]], (env_steps, 1, 1)) * (1 + 0.05 * np.arange(env_steps))[:, None, None]
     frames = [env_steps, env_steps - 3]
     lo, go, ro = run_door(build_door("oracle", env_steps=env_steps), actions, frames)
     lg, gg, rg = run_door(build_door("cuda", env_steps=env_steps), actions, frames)

@@ -102,6 +102,62 @@ def test_backward_substep_mixed_contact(ptype, material_model):
         assert rel_l2(pg, po) <= 5e-3 and cosine(pg, po) >= 0.9999, (pg, po)
 
 
+def test_von_mises_return_mapping_forward_backward_and_rollout():
+    """soft_cloth's plastic flow rule (soft_cloth/engine/mpm_simulator.py:172-189, :232) behind smx_set_plasticity: one substep forward and
+    adjoint with yielding and non-yielding particles in the same blob, then a fused 10-substep rollout (smx_step / smx_step_grad)."""
+    rng = np.random.default_rng(230)
+    pair, st = make_pair(rng, max_steps=14)
+    # yield stress at the median of the strain norm of frame 0 (numpy evaluation of the rule on F_tmp): half of the blob yields
+    st = np.asarray(st, dtype=np.float32).astype(np.float64)
+    F0, C0 = st[:, 6:15].reshape(-1, 3, 3), st[:, 15:24].reshape(-1, 3, 3)
+    sg = np.linalg.svd((np.eye(3)[None] + pair.cfg.dt * C0) @ F0, compute_uv=False)
+    eps = np.log(np.maximum(sg, 0.05)); eh = eps - eps.mean(1, keepdims=True)
+    nrm = np.sqrt((eh * eh).sum(1) + 1e-8)
+    mu = pair.cfg.E / (2 * (1 + pair.cfg.nu))
+    ys = 2 * mu * float(np.median(nrm))
+    pair.orc.set_plasticity(1, ys); pair.gpu.set_plasticity("von_mises", ys)
+    # particles whose norm is within fp32 resolution of the threshold may take the other branch on the device
+    yields, near = nrm - ys / (2 * mu) > 0, np.abs(nrm - ys / (2 * mu)) < 1e-6
+    assert 0.3 < yields.mean() < 0.7 and near.mean() < 0.01
+    pair.substep(0)
+    ref, got = pair.orc.get_frame(1), pair.gpu.get_state(1)
+    assert_state_close(got, ref)
+    yy, nn = yields & ~near, ~yields & ~near
+    assert rel_l2(got[yy, 6:15], ref[yy, 6:15]) <= 1e-5 and rel_l2(got[nn, 6:15], ref[nn, 6:15]) <= 1e-6
+    go, gg = run_backward(pair, rng, 0)
+    for k, sl in COLS.items():
+        e, c = rel_l2(gg[:, sl], go[:, sl]), cosine(gg[:, sl], go[:, sl])
+        assert e <= 2e-3 and c >= 0.9999, f"adjoint {k}: rel L2 {e:.3e}, cos {c:.6f}"
+    for i in range(pair.P):
+        po, pg = pair.orc.get_primitive_state_grad(i, 0), pair.prims[i].get_all_states_grad(0)
+        assert rel_l2(pg, po) <= 5e-3 and cosine(pg, po) >= 0.9999, (pg, po)
+    # rollout through the fused kernels (smx_step / smx_step_grad) on the scene of the rollout test below
+    T, n, center = 10, 4000, np.array([0.5, 0.3, 0.5])
+    pair = Pair(n, tables=[scenes.sphere_table()], prim_params=[(0.5, 666.)], max_steps=T + 2, sort_every=4, substeps=4)
+    pair.set_prim_state(0, 0, T + 2, np.concatenate([center, scenes.random_quat(rng), [0.0, 0.2, 0.0], 0.5 * rng.normal(size=3)]))
+    st = scenes.contact_rollout_state(n, rng, center)
+    sg = np.linalg.svd((np.eye(3)[None] + pair.cfg.dt * st[:, 15:24].reshape(-1, 3, 3)) @ st[:, 6:15].reshape(-1, 3, 3), compute_uv=False)
+    eps = np.log(sg); eh = eps - eps.mean(1, keepdims=True)
+    ys = 2 * mu * float(np.median(np.sqrt((eh * eh).sum(1) + 1e-8)))
+    pair.orc.set_plasticity(1, ys); pair.gpu.set_plasticity("von_mises", ys)
+    pair.reset(st); pair.clear_ext_f()
+    for f in range(T):
+        pair.orc.substep(f)
+    pair.gpu.step(0, T)
+    ref, got = pair.orc.get_frame(T), pair.gpu.get_state(T)
+    assert np.isfinite(ref).all()
+    assert rel_l2(got[:, 0:3], ref[:, 0:3]) <= 1e-5 and rel_l2(got[:, 3:6], ref[:, 3:6]) <= 2e-3 and rel_l2(got[:, 6:15], ref[:, 6:15]) <= 1e-4
+    cot = np.zeros((n, 24)); cot[:, :6] = rng.normal(size=(n, 6))
+    cot = cot.astype(np.float32).astype(np.float64)
+    pair.orc.clear_grads(); pair.gpu.clear_all_gradients()
+    pair.orc.add_frame_grad(T, cot); pair.gpu.add_state_grad(T, cot)
+    for f in range(T - 1, -1, -1):
+        pair.orc.substep_grad(f)
+    pair.gpu.step_grad(T, T)             # adjoint of substeps T-1 ... 0
+    go, gg = pair.orc.get_frame_grad(0), pair.gpu.get_state_grad(0)
+    assert np.abs(go[:, 6:15]).max() > 0 and cosine(gg, go) >= 0.999, cosine(gg, go)
+
+
 @pytest.mark.parametrize("collision_type", [0, 1])
 def test_backward_substep_other_contact_models(collision_type):
     rng = np.random.default_rng(210 + collision_type)
