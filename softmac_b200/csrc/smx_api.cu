@@ -454,7 +454,7 @@ static int forward_p2g(smx_sim* s, int f, bool write_F, bool accumulate, bool fu
                 // more than 48 KB of dynamic shared memory needs the per-device opt-in (remembered per handle)
                 if (ST && s->smem_optin.insert((const void*)k_p2g<M, ST, EX>).second) {
                     cudaFuncSetAttribute(k_p2g<M, ST, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                    cudaFuncSetAttribute(k_p2g<M, ST, EX>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+                    cudaFuncSetAttribute(k_p2g<M, ST, EX>, cudaFuncAttributePreferredSharedMemoryCarveout, getenv("SMX_CARVEOUT") ? atoi(getenv("SMX_CARVEOUT")) : (int)cudaSharedmemCarveoutMaxShared);   // SMX_CARVEOUT: A/B experiments (percent of shared memory)
                 }
                 launch_pdl(s, k_p2g<M, ST, EX>, grid, SMX_TPB_SC, smem, P, ps, f, fin, fout, s->g_in, cslot, s->action, acc, fprev, gprev, rec, s->pf_sc);
             };
@@ -1617,6 +1617,8 @@ static int grad_end(smx_sim* s, int f, bool fuse) {
                 constexpr bool R = decltype(rec_c)::value, E = decltype(extra_c)::value;
                 if (fuse) {
                     // + G2P adjoint of substep f-1: g_out of f-1 and its cleared adjoint grid were put in place by k_grid_grad above
+                    if (getenv("SMX_CARVEOUT_FB") && s->smem_optin.insert((const void*)k_p2g_grad_g2p_grad<M, R, E>).second)      // A/B experiments: L1 / shared split
+                        cudaFuncSetAttribute(k_p2g_grad_g2p_grad<M, R, E>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(getenv("SMX_CARVEOUT_FB")));
                     launch_pdl(s, k_p2g_grad_g2p_grad<M, R, E>, nblk(P.n, SMX_TPB_FB), SMX_TPB_FB, 0, P, ps, f, fin, s->adj_cur, s->adj_nxt, gg, cslot, s->action, s->action_grad, rec,
                                (const float*)s->frame_ptr(f - 1), (const float4*)s->g_out, s->gg_of(f - 1), s->pf_g);
                 } else if (tiled) {

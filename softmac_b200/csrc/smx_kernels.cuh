@@ -70,8 +70,19 @@ __device__ __forceinline__ long long comp_index(long long stride, int j, int c) 
     int p = comp_pos(c);
     return (((long long)(p >> 2) * stride + j) << 2) + (p & 3);
 }
+// read-once load of a streaming particle plane: ld.global.nc.L1::no_allocate -- the planes pass through L1 without evicting the grid
+// nodes that the 27-node gathers of the same kernel re-use (fused adjoint 142.6 -> 140.4 us; -DSMX_STREAM_ALLOC for the plain __ldg)
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+#ifndef SMX_STREAM_ALLOC
+    float4 r;       // not volatile: read-only data, the compiler may schedule the load freely
+    asm("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+#else
+    return __ldg(p);
+#endif
+}
 __device__ __forceinline__ float4 ld_plane(const float* __restrict__ fr, long long stride, int j, int p) {
-    return __ldg(reinterpret_cast<const float4*>(fr) + ((long long)p * stride + j));
+    return ldg_stream(reinterpret_cast<const float4*>(fr) + ((long long)p * stride + j));
 }
 __device__ __forceinline__ void st_plane(float* __restrict__ fr, long long stride, int j, int p, float4 v) {
     reinterpret_cast<float4*>(fr)[(long long)p * stride + j] = v;
@@ -465,11 +476,11 @@ __device__ __forceinline__ void unpack_state(const float4& p0, const float4& p1,
 }
 __device__ __forceinline__ void load_state(const float* __restrict__ fr, long long stride, int j, V3& x, V3& v, M3& F, M3& C) {
     const float4* b = reinterpret_cast<const float4*>(fr) + j;
-    float4 p0 = __ldg(b), p1 = __ldg(b + stride), p2 = __ldg(b + 2 * stride), p3 = __ldg(b + 3 * stride), p4 = __ldg(b + 4 * stride), p5 = __ldg(b + 5 * stride);
+    float4 p0 = ldg_stream(b), p1 = ldg_stream(b + stride), p2 = ldg_stream(b + 2 * stride), p3 = ldg_stream(b + 3 * stride), p4 = ldg_stream(b + 4 * stride), p5 = ldg_stream(b + 5 * stride);
     unpack_state(p0, p1, p2, p3, p4, p5, x, v, F, C);
 }
 // loaders on a per-particle base pointer b (plane p at b[p * stride]); SM: the planes were staged in shared memory by a bulk copy
-template <bool SM> __device__ __forceinline__ float4 ld4(const float4* p) { if (SM) return *p; else return __ldg(p); }
+template <bool SM> __device__ __forceinline__ float4 ld4(const float4* p) { if (SM) return *p; else return ldg_stream(p); }
 // re-read of a staged plane that the compiler must not merge with an earlier read (keeps the value out of registers in between)
 __device__ __forceinline__ float4 lds4_again(const float4* p) {
     float4 r;
@@ -505,7 +516,7 @@ __device__ __forceinline__ void store_F(float* __restrict__ fr, long long stride
 __device__ __forceinline__ M3 load_F(const float* __restrict__ fr, long long stride, int j) {
     const float4* b = reinterpret_cast<const float4*>(fr) + j;
     float f0 = __ldg(reinterpret_cast<const float*>(b + 3 * stride) + 3);
-    float4 p4 = __ldg(b + 4 * stride), p5 = __ldg(b + 5 * stride);
+    float4 p4 = ldg_stream(b + 4 * stride), p5 = ldg_stream(b + 5 * stride);
     M3 F; F.m[0] = f0; F.m[1] = p4.x; F.m[2] = p4.y; F.m[3] = p4.z; F.m[4] = p4.w; F.m[5] = p5.x; F.m[6] = p5.y; F.m[7] = p5.z; F.m[8] = p5.w;
     return F;
 }

@@ -20,3 +20,8 @@ ncu --set full --metrics lts__t_sectors_op_red.sum,lts__t_sectors_op_atom.sum,lt
 echo "ncu full rc=$?"
 ncu -i gpurun_out/${tag}_prof.ncu-rep --page raw --csv > gpurun_out/${tag}_ncu_full_raw.csv 2>/dev/null
 ls -la gpurun_out | tail -12
+# per-source-line executed instructions and stall samples of the two hot kernels (read with tools/ncu_src_summary.py)
+for k in k_p2g_grad_g2p_grad k_p2g; do
+  ncu -i gpurun_out/${tag}_prof.ncu-rep --page source --csv -k regex:"^${k}" -c 1 > gpurun_out/${tag}_src_${k}.csv 2>/dev/null
+done
+ls -la gpurun_out | tail -6
