@@ -1,5 +1,5 @@
 #!/bin/bash
-# round-2: the driver's N-GPU launch of bench.py (headline arm + rollouts64 + slab_8M sub-records).  Usage: bash tools/gpu_r2e.sh N [extra bench args]
+# round-2: the driver's N-GPU launch of bench.py (headline arm + rollouts64 + slab_8M sub-records).  Usage: bash tools/gpu_bench_ngpu.sh N [extra bench args]
 set -u
 N=${1:-2}; shift
 mkdir -p gpurun_out

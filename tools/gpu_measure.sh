@@ -1,8 +1,8 @@
 #!/bin/bash
 # round-2 measurement pass (run under gpurun): GPU tests, the driver's bench line, ncu launch list of the same command,
-# ncu --set full of every substep kernel (+ the L2 reduction counters).  Usage: bash tools/gpu_r2b.sh TAG [skiptests]
+# ncu --set full of every substep kernel (+ the L2 reduction counters).  Usage: bash tools/gpu_measure.sh TAG [skiptests]
 set -u
-tag=${1:-r2b}
+tag=${1:-r2}
 mkdir -p gpurun_out
 if [ "${2:-}" != "skiptests" ]; then
   python -m pytest tests -m gpu -x -q > gpurun_out/${tag}_pytest.log 2>&1; echo "pytest rc=$?"
