@@ -114,6 +114,8 @@ struct smx_sim {
     // grid
     size_t G = 0;
     float4 *g_in = nullptr, *g_out = nullptr, *g_mix = nullptr, *gg_out = nullptr, *gg_out_b = nullptr, *gg_mix = nullptr, *g_lin = nullptr;
+    uint8_t* mixflag = nullptr;     // [2][blocks]: blocks of gg_mix the contact adjoint of an (even / odd) substep scattered into (k_grid_grad sweeps only those)
+    uint8_t* mixflag_of(int f, bool other = false) { return (mixflag && !slab) ? mixflag + (size_t)(((f & 1) != 0) != other) * (G / 64) : nullptr; }
     // adjoint grid of substep f: double-buffered by parity so that k_grid_grad(f) can already clear the one of substep f-1
     // halo exchange over peer memory (smx_slab_halo_*): receive slots + stamps + flags of both sides live in ONE allocation (`halo_mem`,
     // IPC-exportable) that the x-neighbours write into; peer_base[side] is the neighbour's allocation as mapped here
@@ -741,6 +743,7 @@ static int create_body(smx_sim* s, const smx_config* cfg) {
     CK(cudaMemsetAsync(s->g_in, 0, s->G * sizeof(float4), s->stream)); CK(cudaMemsetAsync(s->g_out, 0, s->G * sizeof(float4), s->stream));
     CK(cudaMemsetAsync(s->g_mix, 0, s->G * sizeof(float4), s->stream)); CK(cudaMemsetAsync(s->gg_out, 0, s->G * sizeof(float4), s->stream));
     CK(cudaMemsetAsync(s->gg_mix, 0, s->G * sizeof(float4), s->stream));
+    CK(cudaMalloc(&s->mixflag, 2 * (s->G / 64))); CK(cudaMemsetAsync(s->mixflag, 0, 2 * (s->G / 64), s->stream));
     CK(cudaMalloc(&s->adj_cur, s->frame_floats * sizeof(float))); CK(cudaMalloc(&s->adj_nxt, s->frame_floats * sizeof(float)));
     size_t stage = (size_t)std::max(n, 1) * 24;
     CK(cudaMalloc(&s->stage_dev, stage * sizeof(float))); CK(cudaMallocHost(&s->stage_host, stage * sizeof(float)));
@@ -780,7 +783,7 @@ int smx_destroy(smx_sim* s) {
     for (auto& p : s->prims) { cudaFree(p.sdf_dev); cudaFree(p.nrm_dev); }
     for (int side = 0; side < 2; side++) if (s->peer_base[side] && s->peer_ipc[side]) cudaIpcCloseMemHandle(s->peer_base[side]);
     for (int d = 0; d < 2; d++) for (auto& kv : s->gexec[d]) if (kv.second) cudaGraphExecDestroy(kv.second);
-    void* ptrs[] = {s->halo_mem, s->halo_done, s->near_pool, s->svd_pool, s->ch_target, s->ch_loss, s->cd_buf, s->ckpt, s->pool, s->g_in, s->g_out, s->g_mix, s->gg_out, s->gg_out_b, s->gg_mix, s->g_lin, s->adj_cur, s->adj_nxt, s->stage_dev, s->keys_a, s->keys_b, s->iota, s->cub_tmp,
+    void* ptrs[] = {s->halo_mem, s->halo_done, s->near_pool, s->svd_pool, s->ch_target, s->ch_loss, s->cd_buf, s->ckpt, s->pool, s->g_in, s->g_out, s->g_mix, s->gg_out, s->gg_out_b, s->gg_mix, s->mixflag, s->g_lin, s->adj_cur, s->adj_nxt, s->stage_dev, s->keys_a, s->keys_b, s->iota, s->cub_tmp,
                     s->counters, s->prims_dev, s->pstate, s->pgrad, s->ext_f, s->ext_f_grad, s->abuf, s->gabuf, s->ctrl_id, s->action, s->action_grad,
                     s->rig_arena, s->rig_enable, s->rig_masks, s->ckpt_need};
     for (void* p : ptrs) cudaFree(p);
@@ -1548,9 +1551,9 @@ int smx_substep_grad_mid(smx_sim* s, int32_t f) {
         if (near) {
             const int nwords = (int)s->near_words();
             const int grid = s->sm_count * 2;
-            launch_pdl(s, k_contact_grad_sparse, grid, SMX_TPB, 0, P, ps, f, life, s->frame_ptr(f), s->adj_nxt, s->g_mix, s->gg_of(f), s->gg_mix, near, nwords);
+            launch_pdl(s, k_contact_grad_sparse, grid, SMX_TPB, 0, P, ps, f, life, s->frame_ptr(f), s->adj_nxt, s->g_mix, s->gg_of(f), s->gg_mix, near, nwords, s->mixflag_of(f));
         } else {
-            launch_pdl(s, k_contact_grad, nblk(P.n, SMX_TPB), SMX_TPB, 0, P, ps, f, life, s->frame_ptr(f), s->adj_nxt, s->g_mix, s->gg_of(f), s->gg_mix);
+            launch_pdl(s, k_contact_grad, nblk(P.n, SMX_TPB), SMX_TPB, 0, P, ps, f, life, s->frame_ptr(f), s->adj_nxt, s->g_mix, s->gg_of(f), s->gg_mix, s->mixflag_of(f));
         }
         CKLN(s, "k_contact_grad");
     }
@@ -1593,9 +1596,9 @@ static int grad_end(smx_sim* s, int f, bool fuse) {
         const float4* rec_prev = prep ? s->ckpt + (size_t)(f - 1) * s->ckpt_rec : nullptr;
         { const bool saved_pdl = s->pdl; s->pdl = s->pdl && s->pdl_grid;
         if (P.ctype == 0) launch_pdl(s, k_grid_grad<true>, grid_blocks_launch(s), 256, 0, P, ps, f, s->dense ? nullptr : ord.blocks, ord.nblocks, s->g_in, gg, contact ? s->gg_mix : nullptr,
-                                                                 rec_in, rec_prev, s->ckpt_cap, contact ? 1 : 0, s->g_out, s->g_mix, s->gg_of(f - 1));
+                                                                 rec_in, rec_prev, s->ckpt_cap, contact ? 1 : 0, s->g_out, s->g_mix, s->gg_of(f - 1), contact ? s->mixflag_of(f) : nullptr, contact ? s->mixflag_of(f, true) : nullptr);
         else launch_pdl(s, k_grid_grad<false>, grid_blocks_launch(s), 256, 0, P, ps, f, s->dense ? nullptr : ord.blocks, ord.nblocks, s->g_in, gg, contact ? s->gg_mix : nullptr,
-                                                                 rec_in, rec_prev, s->ckpt_cap, contact ? 1 : 0, s->g_out, s->g_mix, s->gg_of(f - 1));
+                                                                 rec_in, rec_prev, s->ckpt_cap, contact ? 1 : 0, s->g_out, s->g_mix, s->gg_of(f - 1), contact ? s->mixflag_of(f) : nullptr, contact ? s->mixflag_of(f, true) : nullptr);
         s->pdl = saved_pdl; }
         CKLN(s, "k_grid_grad");
         s->bwd_prepared = prep ? f - 1 : -1; s->bwd_prepared_uid = ord.uid;
