@@ -747,7 +747,12 @@ __global__ void __launch_bounds__(256) k_grid_op(Params P, PrimSet ps, int f, co
 // forecast contact: gather v_tmp from g_mix, chain collide_mixed over the enabled primitives,
 // scatter -2 w (v_tmp - v_tgt) into g_out where the node is active; reduce the wrench per body.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SMX_TPB) k_contact(Params P, PrimSet ps, int f, float life, const float* __restrict__ fin,
+// eight CTAs per SM (64 registers): nearly every warp leaves after the reach test, so the kernel is bound by the latency of the x load and
+// occupancy pays (20.4 -> 18.6 us at 1M particles); the few warps that stay spill 96 bytes
+#ifndef SMX_CONTACT_MINB
+#define SMX_CONTACT_MINB 8
+#endif
+__global__ void __launch_bounds__(SMX_TPB, SMX_CONTACT_MINB) k_contact(Params P, PrimSet ps, int f, float life, const float* __restrict__ fin,
                                                      const float4* __restrict__ g_mix, float4* __restrict__ g_out, int accumulate,
                                                      uint32_t* __restrict__ near_mask, int nwords) {
     pdl_prologue();
@@ -1018,7 +1023,7 @@ __device__ __forceinline__ void contact_grad_slot(const Params& P, const PrimSet
                 float4 gm = g_mix[node];
                 float w = s.wx[a] * s.wy[b] * s.wz[c];
                 red_add_f4(gg_mix + node, w * gvtmp.x, w * gvtmp.y, w * gvtmp.z, 0.f);
-                if (mixflag) mixflag[node >> 6] = 1;
+                if (mixflag && a != 1 && b != 1 && c != 1) mixflag[node >> 6] = 1;      // every block the 3x3x3 stencil touches holds one of its 8 corners
                 float gw = gm.x * gvtmp.x + gm.y * gvtmp.y + gm.z * gvtmp.z;
                 gfx.x = fmaf(gw, dwx[a] * s.wy[b] * s.wz[c], gfx.x);
                 gfx.y = fmaf(gw, s.wx[a] * dwy[b] * s.wz[c], gfx.y);

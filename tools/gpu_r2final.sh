@@ -1,10 +1,13 @@
 #!/bin/bash
+# timing experiment (results invalid): which access of k_grid_grad costs what (variant A)
 set -u
 mkdir -p gpurun_out
-( time python -m pytest tests -m gpu -q 2>&1 | tail -8 ) 2>&1
-python bench.py > gpurun_out/r2y_bench.json 2> gpurun_out/r2y_bench.err; echo "bench rc=$?"
-python - <<PY
+L=$PWD/softmac_b200/lib/var_dbg.so
+for D in 0 8 16 32 56; do
+  SMX_LIB=$L SMX_DBG=$D python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline --no-parity --no-subrecords > gpurun_out/r2y_dbg_$D.json 2>/dev/null
+  python - <<PY
 import json
-d = json.load(open("gpurun_out/r2y_bench.json"))
-print("A %.3f stressed %.3f B %.3f e2e %.3f" % (d["value"] / 1e9, d["stressed"]["value"] / 1e9, d["variant_B"]["value"] / 1e9, d["e2e"]["value"] / 1e9), d["variant_B"]["parity"])
+d = json.load(open("gpurun_out/r2y_dbg_$D.json")); k = d["roofline"]["kernel_ms"]
+print("dbg $D: %.3f G/s %.2f ms " % (d["value"] / 1e9, d["ms_per_step"]) + " ".join("%s=%.1f" % (a, 1e3 * k[a]) for a in ("k_grid_op", "k_grid_grad", "k_g2p2g", "k_p2g_grad+g2p_grad") if a in k))
 PY
+done
