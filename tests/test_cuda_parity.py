@@ -642,6 +642,41 @@ def test_fused_step_matches_substep_loop():
     assert la <= lb - 4, (la, lb)                   # at least four of the eight boundaries were fused
 
 
+def test_repeated_backward_passes_on_one_forward_are_identical():
+    """Nothing a backward pass leaves behind may leak into the next one: the grids restored from the per-substep records, the adjoint grids
+    re-zeroed block by block (gg_mix only where the contact adjoint scattered: the block flags of k_contact_grad) and the flags themselves.
+    Two fused passes (smx_step_grad) and one substep-wise pass over the same forward rollout, with forecast contact and re-sorts."""
+    center, steps, n = np.array([0.5, 0.3, 0.5]), 10, 5000
+    rng = np.random.default_rng(310)
+    pair = Pair(n, tables=[scenes.sphere_table()], prim_params=[(0.5, 666.)], max_steps=steps + 2, sort_every=4)
+    pair.prims[0].set_all_states(0, np.concatenate([center, [1, 0, 0, 0], [0.0, 0.2, 0.0], [0, 0, 0.3]]), f_end=steps + 2)
+    pair.gpu.reset(scenes.contact_rollout_state(n, rng, center))
+    pair.prims[0].clear_ext_f()
+    pair.gpu.step(0, steps)
+    seed, ext = rng.normal(size=(n, 3)), 1e-3 * rng.normal(size=6)
+
+    def backward(fused):
+        pair.gpu.clear_all_gradients()
+        pair.gpu.add_x_grad(steps, seed)
+        pair.prims[0].set_ext_f_grad(ext)
+        if fused:
+            pair.gpu.step_grad(steps, steps)
+        else:
+            for f in range(steps - 1, -1, -1):
+                pair.gpu.substep_grad(f)
+        return pair.gpu.get_state_grad(0), pair.prims[0].get_all_states_grad(0, f_end=steps)
+
+    g1, p1 = backward(True)
+    g2, p2 = backward(True)
+    g3, p3 = backward(False)
+    g4, p4 = backward(True)
+    assert np.abs(g1).max() > 0 and np.abs(p1).max() > 0
+    # the scatter's L2 reductions arrive in any order: equal up to fp32 summation order
+    assert rel_l2(g2, g1) <= 1e-5 and rel_l2(p2, p1) <= 1e-4
+    assert rel_l2(g3, g1) <= 1e-4 and rel_l2(p3, p1) <= 1e-3
+    assert rel_l2(g4, g1) <= 1e-5 and rel_l2(p4, p1) <= 1e-4
+
+
 def test_copy_mode_resorts_by_age_not_by_frame_index():
     """TaichiEnv.set_copy(True) (taichi_env.py:106-115): step `substeps` substeps from frame 0, copyframe(cur, 0), cur = 0 -- frame
     indices never reach sort_every = max(substeps, 4) when substeps < 4 (demo_pour has 1).  The re-sort is triggered by the number
