@@ -133,10 +133,10 @@ __device__ __forceinline__ void stagger_first_wave(int dbg, int slots) {
 
 #define SMX_TPB 128         // gather-type particle kernels
 #ifndef SMX_TPB_SC
-#define SMX_TPB_SC 128      // P2G: four warps x 13.6 KB of staging, four CTAs per SM at 128 registers (16 warps)
-#endif
+#define SMX_TPB_SC 64       // P2G: two warps x 13.6 KB of staging, eight CTAs per SM at 128 registers (16 warps).  Same residency as four
+#endif                      // CTAs of four warps, finer-grained CTA turnover: G2P2G 94.9 -> 92.7 us (96- and 32-thread CTAs measured slower)
 #ifndef SMX_SC_MINB
-#define SMX_SC_MINB 4
+#define SMX_SC_MINB 8
 #endif
 #ifndef SMX_TPB_G2PG
 #define SMX_TPB_G2PG 96     // G2P adjoint: three warps x 10.3 KB of staging, seven CTAs per SM at <= 96 registers (21 warps)
